@@ -1,0 +1,580 @@
+// hts_io.hpp — minimal BGZF/BAM, VCF (text, plain or gzip/bgzip), FASTA(+.fai) and GTF2
+// readers. zlib is the only dependency (no htslib / rust-htslib in this image).
+//
+// These readers restate only the *observable* behaviour the reference relies on at its
+// call sites:
+//   - bam::Record::{pos,mapq,seq,qual,qname,cigar}, CigarStringView::{end_pos,read_pos}
+//     used at reference src/microphasing.rs:78-139,297-343
+//   - bam::RecordBuffer::fetch  (reference src/microphasing.rs:905-920)
+//   - bcf::buffer::RecordBuffer::fetch (reference src/microphasing.rs:932-942)
+//   - bio::io::fasta::IndexedReader::{fetch,read} (reference src/microphasing.rs:895-901)
+//   - bio::io::gff::Reader(GTF2) (reference src/microphasing.rs:1982-2124)
+// Header-only, C++17. Used by the product host code and by the oracle's input side.
+#pragma once
+#include <zlib.h>
+
+#include <algorithm>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <deque>
+#include <fstream>
+#include <map>
+#include <memory>
+#include <set>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+namespace mphio {
+
+struct IoError : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+
+// ---------------------------------------------------------------- file slurp
+inline std::vector<uint8_t> read_file(const std::string& path) {
+  FILE* f = fopen(path.c_str(), "rb");
+  if (!f) throw IoError("cannot open " + path);
+  std::vector<uint8_t> buf;
+  uint8_t tmp[1 << 16];
+  size_t n;
+  while ((n = fread(tmp, 1, sizeof tmp, f)) > 0) buf.insert(buf.end(), tmp, tmp + n);
+  fclose(f);
+  return buf;
+}
+
+// ---------------------------------------------------------------- BGZF
+// Streaming BGZF block reader: each block is an independent gzip member with a BC extra
+// subfield holding the block size. inflate is done with raw deflate (windowBits -15).
+class BgzfReader {
+ public:
+  explicit BgzfReader(const std::string& path) : path_(path) {
+    f_ = fopen(path.c_str(), "rb");
+    if (!f_) throw IoError("cannot open " + path);
+  }
+  ~BgzfReader() {
+    if (f_) fclose(f_);
+  }
+  BgzfReader(const BgzfReader&) = delete;
+  BgzfReader& operator=(const BgzfReader&) = delete;
+
+  // read exactly n bytes; returns false on clean EOF at a record boundary (0 bytes read)
+  bool read(void* dst, size_t n) {
+    uint8_t* d = static_cast<uint8_t*>(dst);
+    size_t got = 0;
+    while (got < n) {
+      if (pos_ == block_.size()) {
+        if (!next_block()) {
+          if (got == 0) return false;
+          throw IoError("truncated BGZF stream in " + path_);
+        }
+        continue;
+      }
+      size_t take = std::min(n - got, block_.size() - pos_);
+      memcpy(d + got, block_.data() + pos_, take);
+      pos_ += take;
+      got += take;
+    }
+    return true;
+  }
+
+ private:
+  bool next_block() {
+    for (;;) {
+      uint8_t hdr[18];
+      size_t n = fread(hdr, 1, 18, f_);
+      if (n == 0) return false;
+      if (n != 18 || hdr[0] != 31 || hdr[1] != 139 || hdr[2] != 8 || !(hdr[3] & 4))
+        throw IoError("not a BGZF file: " + path_);
+      uint16_t xlen = hdr[10] | (hdr[11] << 8);
+      // the BC subfield is normally the first (and only) one
+      std::vector<uint8_t> extra(xlen);
+      memcpy(extra.data(), hdr + 12, std::min<size_t>(6, xlen));
+      if (xlen > 6 && fread(extra.data() + 6, 1, xlen - 6, f_) != size_t(xlen - 6))
+        throw IoError("truncated BGZF header in " + path_);
+      int bsize = -1;
+      for (size_t o = 0; o + 4 <= extra.size();) {
+        uint16_t slen = extra[o + 2] | (extra[o + 3] << 8);
+        if (extra[o] == 'B' && extra[o + 1] == 'C' && slen == 2) bsize = extra[o + 4] | (extra[o + 5] << 8);
+        o += 4 + slen;
+      }
+      if (bsize < 0) throw IoError("BGZF block without BC field in " + path_);
+      size_t clen = size_t(bsize) + 1 - 12 - xlen - 8;  // compressed payload
+      cbuf_.resize(clen + 8);
+      if (fread(cbuf_.data(), 1, clen + 8, f_) != clen + 8) throw IoError("truncated BGZF block in " + path_);
+      uint32_t isize;
+      memcpy(&isize, cbuf_.data() + clen + 4, 4);
+      block_.resize(isize);
+      pos_ = 0;
+      if (isize == 0) continue;  // EOF marker / empty block
+      z_stream zs;
+      memset(&zs, 0, sizeof zs);
+      if (inflateInit2(&zs, -15) != Z_OK) throw IoError("zlib init failed");
+      zs.next_in = cbuf_.data();
+      zs.avail_in = uInt(clen);
+      zs.next_out = block_.data();
+      zs.avail_out = isize;
+      int rc = inflate(&zs, Z_FINISH);
+      inflateEnd(&zs);
+      if (rc != Z_STREAM_END) throw IoError("BGZF inflate failed in " + path_);
+      return true;
+    }
+  }
+  std::string path_;
+  FILE* f_ = nullptr;
+  std::vector<uint8_t> cbuf_, block_;
+  size_t pos_ = 0;
+};
+
+// ---------------------------------------------------------------- BAM
+enum CigarOp : uint32_t { C_M = 0, C_I = 1, C_D = 2, C_N = 3, C_S = 4, C_H = 5, C_P = 6, C_EQ = 7, C_X = 8 };
+
+struct BamRecord {
+  int32_t tid = -1;
+  int32_t pos = -1;
+  uint8_t mapq = 0;
+  uint16_t flag = 0;
+  uint32_t l_seq = 0;
+  std::string qname;             // without the trailing NUL
+  std::vector<uint32_t> cigar;   // BAM encoding: len<<4 | op
+  std::vector<uint8_t> seq4;     // 4-bit packed, high nibble first
+  std::vector<uint8_t> qual;     // raw phred
+  std::vector<uint8_t> aux;      // raw aux block (tests/fixture tooling use MD)
+
+  bool is_unmapped() const { return flag & 4; }
+  // bam::Record::seq()[i] -> ASCII from "=ACMGRSVTWYHKDBN"
+  uint8_t base(uint32_t i) const {
+    static const char* dec = "=ACMGRSVTWYHKDBN";
+    uint8_t b = seq4[i >> 1];
+    return uint8_t(dec[(i & 1) ? (b & 15) : (b >> 4)]);
+  }
+  // CigarStringView::end_pos(): pos + sum of reference-consuming op lengths (M,D,N,=,X)
+  int64_t end_pos() const {
+    int64_t e = pos;
+    for (uint32_t c : cigar) {
+      uint32_t op = c & 15, len = c >> 4;
+      if (op == C_M || op == C_D || op == C_N || op == C_EQ || op == C_X) e += len;
+    }
+    return e;
+  }
+};
+
+// CigarStringView::read_pos(ref_pos, include_softclips=false, include_dels=false).
+// Returns: 1 = Some(qpos) (written to *out), 0 = None, -1 = Err.
+// Restated from rust-htslib 0.36 bam/record.rs (crate not vendored under /root/reference;
+// semantics pinned indirectly by the somatic fixtures).
+inline int cigar_read_pos(const std::vector<uint32_t>& cigar, int64_t read_start, int64_t ref_pos, uint32_t* out) {
+  int64_t rpos = read_start;  // reference position
+  int64_t qpos = 0;           // position within read
+  size_t j = 0;               // index into cigar operation vector
+  const size_t n = cigar.size();
+  // find the first operation that refers to qpos = 0 (i.e. to bases in record.seq())
+  for (size_t i = 0; i < n; ++i) {
+    uint32_t op = cigar[i] & 15;
+    if (op == C_M || op == C_X || op == C_EQ || op == C_I || op == C_S) {
+      j = i;  // include_softclips == false: a leading S is consumed by the main loop
+      break;
+    }
+    if (op == C_D || op == C_N) return -1;  // D/N before any op describing read sequence
+    if (op == C_H && i > 0 && i + 1 < n) return -1;  // hard clip between operations
+    if ((op == C_P || op == C_H) && i + 1 == n) return 0;  // only pads / hard clips
+    // otherwise: leading H / P, consumes nothing
+  }
+  while (rpos <= ref_pos && j < n) {
+    uint32_t op = cigar[j] & 15;
+    int64_t l = cigar[j] >> 4;
+    switch (op) {
+      case C_M:
+      case C_X:
+      case C_EQ:
+        if (rpos <= ref_pos && rpos + l > ref_pos) {
+          *out = uint32_t(qpos + (ref_pos - rpos));
+          return 1;
+        }
+        rpos += l;
+        qpos += l;
+        ++j;
+        break;
+      case C_S:
+      case C_I:
+        qpos += l;
+        ++j;
+        break;
+      case C_N:
+      case C_D:  // include_dels == false
+        rpos += l;
+        ++j;
+        break;
+      case C_P:
+        ++j;
+        break;
+      case C_H:
+        if (j + 1 < n) return -1;
+        return 0;
+      default:
+        return -1;
+    }
+  }
+  return 0;
+}
+
+struct BamFile {
+  std::string header_text;
+  std::vector<std::string> ref_names;
+  std::vector<int64_t> ref_lens;
+  std::unordered_map<std::string, int> tid_of;
+
+  explicit BamFile(const std::string& path) : rd_(path) {
+    char magic[4];
+    if (!rd_.read(magic, 4) || memcmp(magic, "BAM\1", 4) != 0) throw IoError("not a BAM file: " + path);
+    int32_t l_text;
+    rd_.read(&l_text, 4);
+    header_text.resize(l_text);
+    if (l_text) rd_.read(&header_text[0], l_text);
+    int32_t n_ref;
+    rd_.read(&n_ref, 4);
+    for (int i = 0; i < n_ref; ++i) {
+      int32_t l_name;
+      rd_.read(&l_name, 4);
+      std::string nm(l_name, 0);
+      rd_.read(&nm[0], l_name);
+      if (!nm.empty() && nm.back() == 0) nm.pop_back();
+      int32_t l_ref;
+      rd_.read(&l_ref, 4);
+      tid_of[nm] = i;
+      ref_names.push_back(nm);
+      ref_lens.push_back(l_ref);
+    }
+  }
+
+  // next alignment record; false on EOF
+  bool next(BamRecord& r) {
+    int32_t bs;
+    if (!rd_.read(&bs, 4)) return false;
+    buf_.resize(bs);
+    rd_.read(buf_.data(), bs);
+    const uint8_t* p = buf_.data();
+    auto i32 = [&](size_t o) { int32_t v; memcpy(&v, p + o, 4); return v; };
+    auto u16 = [&](size_t o) { uint16_t v; memcpy(&v, p + o, 2); return v; };
+    r.tid = i32(0);
+    r.pos = i32(4);
+    uint8_t l_read_name = p[8];
+    r.mapq = p[9];
+    uint16_t n_cigar = u16(12);
+    r.flag = u16(14);
+    r.l_seq = uint32_t(i32(16));
+    size_t o = 32;
+    r.qname.assign(reinterpret_cast<const char*>(p + o), l_read_name ? l_read_name - 1 : 0);
+    o += l_read_name;
+    r.cigar.resize(n_cigar);
+    if (n_cigar) memcpy(r.cigar.data(), p + o, 4 * size_t(n_cigar));
+    o += 4 * size_t(n_cigar);
+    size_t sb = (r.l_seq + 1) / 2;
+    r.seq4.assign(p + o, p + o + sb);
+    o += sb;
+    r.qual.assign(p + o, p + o + r.l_seq);
+    o += r.l_seq;
+    r.aux.assign(p + o, p + bs);
+    return true;
+  }
+
+ private:
+  BgzfReader rd_;
+  std::vector<uint8_t> buf_;
+};
+
+// ---------------------------------------------------------------- line reader (plain or gzip)
+class LineReader {
+ public:
+  explicit LineReader(const std::string& path) {
+    gz_ = gzopen(path.c_str(), "rb");
+    if (!gz_) throw IoError("cannot open " + path);
+    gzbuffer(gz_, 1 << 18);
+  }
+  ~LineReader() {
+    if (gz_) gzclose(gz_);
+  }
+  bool getline(std::string& line) {
+    line.clear();
+    char buf[1 << 14];
+    for (;;) {
+      if (!gzgets(gz_, buf, sizeof buf)) return !line.empty();
+      size_t n = strlen(buf);
+      if (n && buf[n - 1] == '\n') {
+        line.append(buf, n - 1);
+        if (!line.empty() && line.back() == '\r') line.pop_back();
+        return true;
+      }
+      line.append(buf, n);
+    }
+  }
+
+ private:
+  gzFile gz_;
+};
+
+inline std::vector<std::string> split(const std::string& s, char d) {
+  std::vector<std::string> out;
+  size_t b = 0;
+  for (;;) {
+    size_t e = s.find(d, b);
+    if (e == std::string::npos) {
+      out.emplace_back(s.substr(b));
+      break;
+    }
+    out.emplace_back(s.substr(b, e - b));
+    b = e + 1;
+  }
+  return out;
+}
+
+// ---------------------------------------------------------------- VCF (text)
+struct VcfRecord {
+  int rid = -1;
+  int64_t pos = 0;  // 0-based
+  std::string ref;
+  std::vector<std::string> alts;
+  // INFO access mirrors bcf::Record::info(tag): *_defined = tag declared in the header
+  bool somatic_flag = false;   // INFO/SOMATIC present (only meaningful if declared as Flag)
+  bool has_ann = false;        // INFO/ANN key present on this record
+  std::string ann_first;       // first comma-separated ANN entry
+  bool has_svlen = false;
+  std::vector<int64_t> svlen;  // INT64_MIN marks a missing value
+};
+
+struct VcfFile {
+  std::vector<std::string> contigs;
+  std::unordered_map<std::string, int> rid_of;
+  bool somatic_defined = false, ann_defined = false, svlen_defined = false;
+
+  explicit VcfFile(const std::string& path) : lr_(path) {
+    std::string line;
+    while (lr_.getline(line)) {
+      if (line.rfind("##", 0) == 0) {
+        if (line.rfind("##contig=<", 0) == 0) {
+          size_t p = line.find("ID=");
+          if (p != std::string::npos) {
+            size_t e = line.find_first_of(",>", p);
+            add_contig(line.substr(p + 3, e - p - 3));
+          }
+        } else if (line.rfind("##INFO=<ID=", 0) == 0) {
+          size_t e = line.find_first_of(",>", 11);
+          std::string id = line.substr(11, e - 11);
+          if (id == "SOMATIC") somatic_defined = line.find("Type=Flag") != std::string::npos;
+          if (id == "ANN") ann_defined = true;
+          if (id == "SVLEN") svlen_defined = true;
+        }
+        continue;
+      }
+      if (!line.empty() && line[0] == '#') break;  // #CHROM line
+      pending_ = line;
+      have_pending_ = true;
+      break;
+    }
+  }
+
+  // htslib: name2rid fails for contigs absent from the header; text VCFs whose records
+  // use undeclared contigs get them appended on the fly (with a warning) by htslib.
+  int name2rid(const std::string& c) const {
+    auto it = rid_of.find(c);
+    return it == rid_of.end() ? -1 : it->second;
+  }
+
+  bool next(VcfRecord& r) {
+    std::string line;
+    for (;;) {
+      if (have_pending_) {
+        line.swap(pending_);
+        have_pending_ = false;
+      } else if (!lr_.getline(line)) {
+        return false;
+      }
+      if (line.empty() || line[0] == '#') continue;
+      break;
+    }
+    // CHROM POS ID REF ALT QUAL FILTER INFO ...
+    size_t f[9];
+    size_t nf = 0, b = 0;
+    f[nf++] = 0;
+    while (nf < 9 && (b = line.find('\t', b)) != std::string::npos) f[nf++] = ++b;
+    if (nf < 5) throw IoError("malformed VCF line: " + line.substr(0, 80));
+    auto field = [&](size_t i) -> std::string {
+      if (i >= nf) return std::string();
+      size_t s = f[i];
+      size_t e = (i + 1 < nf) ? f[i + 1] - 1 : line.find('\t', s);
+      if (e == std::string::npos) e = line.size();
+      return line.substr(s, e - s);
+    };
+    std::string chrom = field(0);
+    int rid = name2rid(chrom);
+    if (rid < 0) rid = add_contig(chrom);
+    r.rid = rid;
+    r.pos = std::stoll(field(1)) - 1;
+    r.ref = field(3);
+    r.alts.clear();
+    std::string alt = field(4);
+    if (alt != ".") r.alts = split(alt, ',');
+    r.somatic_flag = r.has_ann = r.has_svlen = false;
+    r.ann_first.clear();
+    r.svlen.clear();
+    std::string info = field(7);
+    if (!info.empty() && info != ".") {
+      size_t s = 0;
+      while (s <= info.size()) {
+        size_t e = info.find(';', s);
+        if (e == std::string::npos) e = info.size();
+        size_t eq = info.find('=', s);
+        if (eq == std::string::npos || eq > e) eq = e;
+        size_t klen = eq - s;
+        if (klen == 7 && info.compare(s, 7, "SOMATIC") == 0) {
+          r.somatic_flag = true;
+        } else if (klen == 3 && info.compare(s, 3, "ANN") == 0) {
+          r.has_ann = true;
+          std::string v = eq < e ? info.substr(eq + 1, e - eq - 1) : std::string();
+          size_t c = v.find(',');
+          r.ann_first = c == std::string::npos ? v : v.substr(0, c);
+        } else if (klen == 5 && info.compare(s, 5, "SVLEN") == 0) {
+          r.has_svlen = true;
+          std::string v = eq < e ? info.substr(eq + 1, e - eq - 1) : std::string();
+          for (auto& t : split(v, ',')) r.svlen.push_back(t == "." || t.empty() ? INT64_MIN : std::stoll(t));
+        }
+        s = e + 1;
+      }
+    }
+    return true;
+  }
+
+ private:
+  int add_contig(const std::string& c) {
+    auto it = rid_of.find(c);
+    if (it != rid_of.end()) return it->second;
+    int id = int(contigs.size());
+    contigs.push_back(c);
+    rid_of[c] = id;
+    return id;
+  }
+  LineReader lr_;
+  std::string pending_;
+  bool have_pending_ = false;
+};
+
+// ---------------------------------------------------------------- FASTA + .fai
+// bio::io::fasta::IndexedReader: fetch(name, start, stop) 0-based half-open, read() strips
+// line terminators and preserves case; out-of-range stop is an error.
+class FastaIndexed {
+ public:
+  explicit FastaIndexed(const std::string& path) : path_(path) {
+    std::ifstream fai(path + ".fai");
+    if (!fai) throw IoError("cannot open " + path + ".fai");
+    std::string line;
+    while (std::getline(fai, line)) {
+      if (line.empty()) continue;
+      auto t = split(line, '\t');
+      if (t.size() < 5) throw IoError("malformed .fai line");
+      Entry e{std::stoull(t[1]), std::stoull(t[2]), std::stoull(t[3]), std::stoull(t[4])};
+      idx_[t[0]] = e;
+    }
+    f_ = fopen(path.c_str(), "rb");
+    if (!f_) throw IoError("cannot open " + path);
+  }
+  ~FastaIndexed() {
+    if (f_) fclose(f_);
+  }
+  bool has(const std::string& name) const { return idx_.count(name) != 0; }
+  uint64_t length(const std::string& name) const { return idx_.at(name).len; }
+
+  void fetch(const std::string& name, uint64_t start, uint64_t stop, std::vector<uint8_t>& out) {
+    auto it = idx_.find(name);
+    if (it == idx_.end()) throw IoError("Unknown sequence name: " + name);
+    const Entry& e = it->second;
+    if (start > stop) throw IoError("Invalid query interval");
+    if (stop > e.len) throw IoError("FASTA read interval was out of bounds");
+    out.clear();
+    out.reserve(stop - start);
+    if (start == stop) return;
+    uint64_t line = start / e.line_bases, col = start % e.line_bases;
+    uint64_t off = e.offset + line * e.line_bytes + col;
+    if (fseeko(f_, off_t(off), SEEK_SET) != 0) throw IoError("seek failed in " + path_);
+    uint64_t need = stop - start;
+    // bytes spanned on disk
+    uint64_t last = stop - 1;
+    uint64_t last_off = e.offset + (last / e.line_bases) * e.line_bytes + last % e.line_bases;
+    std::vector<uint8_t> raw(last_off - off + 1);
+    if (fread(raw.data(), 1, raw.size(), f_) != raw.size()) throw IoError("short read in " + path_);
+    uint64_t c = col;
+    for (size_t i = 0; i < raw.size() && out.size() < need;) {
+      uint64_t take = std::min<uint64_t>(e.line_bases - c, need - out.size());
+      out.insert(out.end(), raw.begin() + i, raw.begin() + i + take);
+      i += take + (e.line_bytes - e.line_bases);
+      c = 0;
+    }
+  }
+
+ private:
+  struct Entry {
+    uint64_t len, offset, line_bases, line_bytes;
+  };
+  std::string path_;
+  std::map<std::string, Entry> idx_;
+  FILE* f_ = nullptr;
+};
+
+// ---------------------------------------------------------------- GTF2
+struct GtfRecord {
+  std::string seqname, feature, frame;
+  uint64_t start = 0, end = 0;  // 1-based inclusive, as in the file
+  char strand = '.';
+  // bio::io::gff attributes() is a multimap; .get(k) yields the first value
+  std::vector<std::pair<std::string, std::string>> attrs;
+  const std::string* get(const char* k) const {
+    for (auto& kv : attrs)
+      if (kv.first == k) return &kv.second;
+    return nullptr;
+  }
+};
+
+// Parses one GTF2 line (bio 0.34 gff::Reader with GffType::GTF2: key/value separated by
+// ' ', entries terminated by ';', surrounding quotes stripped). Returns false for
+// comment / blank lines.
+inline bool parse_gtf_line(const std::string& line, GtfRecord& r) {
+  if (line.empty() || line[0] == '#') return false;
+  auto t = split(line, '\t');
+  if (t.size() < 9) throw IoError("malformed GTF line: " + line.substr(0, 80));
+  r.seqname = t[0];
+  r.feature = t[2];
+  r.start = std::stoull(t[3]);
+  r.end = std::stoull(t[4]);
+  r.strand = t[6].empty() ? '.' : t[6][0];
+  r.frame = t[7];
+  r.attrs.clear();
+  const std::string& a = t[8];
+  size_t i = 0;
+  while (i < a.size()) {
+    while (i < a.size() && (a[i] == ' ' || a[i] == ';')) ++i;
+    if (i >= a.size()) break;
+    size_t ks = i;
+    while (i < a.size() && a[i] != ' ' && a[i] != ';') ++i;
+    std::string key = a.substr(ks, i - ks);
+    while (i < a.size() && a[i] == ' ') ++i;
+    std::string val;
+    if (i < a.size() && a[i] == '"') {
+      size_t e = a.find('"', i + 1);
+      if (e == std::string::npos) e = a.size();
+      val = a.substr(i + 1, e - i - 1);
+      i = e + 1;
+    } else {
+      size_t vs = i;
+      while (i < a.size() && a[i] != ';') ++i;
+      val = a.substr(vs, i - vs);
+      while (!val.empty() && val.back() == ' ') val.pop_back();
+    }
+    r.attrs.emplace_back(std::move(key), std::move(val));
+    while (i < a.size() && a[i] != ';') ++i;
+  }
+  return true;
+}
+
+}  // namespace mphio

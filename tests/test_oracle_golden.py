@@ -1,0 +1,52 @@
+"""The CPU oracle against the reference's own golden outputs (reference tests/lib.rs).
+
+Each case mirrors one `#[test]` of the reference: same inputs, same command line, outputs
+compared byte-for-byte with the reference's checked-in `expected_output` files (copied to
+tests/golden/<case>/expected by tests/golden/make_fixtures.py).
+"""
+import os
+import subprocess
+
+import pytest
+
+from conftest import GOLDEN, materialize_reference
+
+SOMATIC = ["forward_somatic", "empty", "reverse_somatic", "splice_forward_somatic", "splice_reverse_somatic"]
+
+
+def run_cli(binary, case, tmp_path, gtf="annotation.gtf", extra_env=None):
+    d = os.path.join(GOLDEN, case)
+    meta = dict(l.rstrip("\n").split("\t") for l in open(os.path.join(d, "case.txt")))
+    fa = materialize_reference(d, str(tmp_path))
+    cmd = [binary, meta["subcommand"], os.path.join(d, "reads.bam"), "--ref", fa, "--variants",
+           os.path.join(d, "variants.vcf"), "--tsv", str(tmp_path / "out.tsv")]
+    if meta["subcommand"] == "somatic":
+        cmd += ["--normal-output", str(tmp_path / "out.normal.fa")]
+    env = dict(os.environ)
+    env.update(extra_env or {})
+    with open(os.path.join(d, gtf)) as gin, open(tmp_path / "out.fa", "wb") as fout:
+        res = subprocess.run(cmd, stdin=gin, stdout=fout, stderr=subprocess.PIPE, env=env, timeout=600)
+    return res
+
+
+def assert_outputs(case, tmp_path):
+    exp = os.path.join(GOLDEN, case, "expected")
+    for name in sorted(os.listdir(exp)):
+        want = open(os.path.join(exp, name), "rb").read()
+        got = open(tmp_path / name, "rb").read()
+        assert got == want, "%s/%s differs from the reference's expected output" % (case, name)
+
+
+@pytest.mark.parametrize("case", SOMATIC)
+def test_oracle_somatic_matches_reference_golden(oracle_bin, case, tmp_path):
+    res = run_cli(oracle_bin, case, tmp_path)
+    assert res.returncode == 0, res.stderr.decode()
+    assert_outputs(case, tmp_path)
+
+
+def test_oracle_unsorted_gtf_is_fatal(oracle_bin, tmp_path):
+    """reference tests/lib.rs:344-382 — unsorted GTF must exit non-zero, sorted must exit zero."""
+    res = run_cli(oracle_bin, "unsorted_gtf", tmp_path, gtf="unsorted.gtf")
+    assert res.returncode != 0
+    res = run_cli(oracle_bin, "unsorted_gtf", tmp_path, gtf="sorted.gtf")
+    assert res.returncode == 0, res.stderr.decode()
