@@ -1,0 +1,446 @@
+// phase_core.h — the per-item arithmetic of the phasing kernels, written once as
+// host+device inline functions. The CUDA kernels (csrc/kernels/*.cu) wrap these in the
+// parallel structure (warp per window, match_any histogram, compaction); the test-only CPU
+// emulator (tests/emu) wraps the same functions in plain loops so the closed forms below can be
+// diffed against the oracle without a GPU.
+//
+// What is restated here, with the reference lines it replaces (src/microphasing.rs):
+//   mph_geom          window 4-tuple (splice_side_offset, splice_end, splice_gap, splice_pos)  :1050-1111
+//   mph_call_read     supports_variant :95-139 + bad_quality :78-93 for every variant inside a read
+//   mph_fwd_state /   closed form of the ObservationMatrix bookkeeping — cleanup_reads :259-278,
+//   mph_rev_*         shrink_left :220-229, push_read :297-343, extend_right :232-256,
+//                     update_haplotype :157-197 — for one (read, window) pair
+//   mph_assemble      the haplotype sequence walk of print_haplotypes :458-603
+//   mph_has_stop      has_stop_codon :42-76
+#pragma once
+#include "layout.h"
+
+typedef struct {
+  uint32_t s, e, gap, spos;
+} MphGeom;
+
+// :1050-1111. k-th iteration of a segment (read_through is always false once `valid` held, :1041-1045)
+MPH_HD MphGeom mph_geom(const MphSegment& g, uint32_t k) {
+  const bool rev = (g.flags & MPH_SF_REVERSE) != 0, shrt = (g.flags & MPH_SF_SHORT) != 0;
+  const uint32_t ceo = g.ceo, ewl = g.ewl;
+  MphGeom o;
+  if (!rev) {
+    const uint32_t off = g.off0 + k;
+    const uint32_t rest = g.exon_end - (off + ewl);
+    const bool first = k == 0, last = rest < 3;
+    if (shrt || (first && last)) { o.s = off - ceo; o.e = off + ewl + rest; o.gap = ceo + rest; o.spos = 2; }
+    else if (first) { o.s = off - ceo; o.e = off + ewl; o.gap = ceo; o.spos = 1; }
+    else if (last) { o.s = off; o.e = off + ewl + rest; o.gap = rest; o.spos = 0; }
+    else { o.s = off; o.e = off + ewl; o.gap = 0; o.spos = 0; }
+  } else {
+    const uint32_t off = g.off0 - k;
+    const uint32_t rest = off - g.exon_start;
+    const bool first = k == 0, last = rest < 3;
+    if (shrt) { o.s = off - rest; o.e = off + ewl + ceo; o.gap = ceo + rest; o.spos = 2; }
+    else if (first) { o.s = off; o.e = off + ewl + ceo; o.gap = ceo; o.spos = 0; }
+    else if (last) { o.s = off - rest; o.e = off + ewl; o.gap = rest; o.spos = 1; }
+    else { o.s = off; o.e = off + ewl; o.gap = 0; o.spos = 0; }
+  }
+  return o;
+}
+
+// first variant index in [lo, hi) with pos >= p
+MPH_HD uint32_t mph_var_lb(const MphVar* vars, uint32_t lo, uint32_t hi, uint32_t p) {
+  while (lo < hi) {
+    uint32_t mid = lo + ((hi - lo) >> 1);
+    if (vars[mid].pos < p) lo = mid + 1;
+    else hi = mid;
+  }
+  return lo;
+}
+
+// first index in [lo, hi) with a[idx] >= p
+MPH_HD uint32_t mph_u32_lb(const uint32_t* a, uint32_t lo, uint32_t hi, uint32_t p) {
+  while (lo < hi) {
+    uint32_t mid = lo + ((hi - lo) >> 1);
+    if (a[mid] < p) lo = mid + 1;
+    else hi = mid;
+  }
+  return lo;
+}
+
+// bits j with ia <= vlo + j < ib
+MPH_HD uint64_t mph_range_mask(uint32_t ia, uint32_t ib, uint32_t vlo) {
+  if (ib <= ia) return 0;
+  int64_t lo = (int64_t)ia - (int64_t)vlo, hi = (int64_t)ib - (int64_t)vlo;
+  if (lo < 0) lo = 0;
+  if (hi > 64) hi = 64;
+  if (hi <= lo) return 0;
+  const uint64_t m = (hi - lo >= 64) ? ~(uint64_t)0 : (((uint64_t)1 << (hi - lo)) - 1);
+  return m << lo;
+}
+
+MPH_HD uint64_t mph_bitrev64(uint64_t x) {
+#if defined(__CUDA_ARCH__)
+  return __brevll(x);
+#else
+  x = ((x >> 1) & 0x5555555555555555ull) | ((x & 0x5555555555555555ull) << 1);
+  x = ((x >> 2) & 0x3333333333333333ull) | ((x & 0x3333333333333333ull) << 2);
+  x = ((x >> 4) & 0x0F0F0F0F0F0F0F0Full) | ((x & 0x0F0F0F0F0F0F0F0Full) << 4);
+  x = ((x >> 8) & 0x00FF00FF00FF00FFull) | ((x & 0x00FF00FF00FF00FFull) << 8);
+  x = ((x >> 16) & 0x0000FFFF0000FFFFull) | ((x & 0x0000FFFF0000FFFFull) << 16);
+  return (x >> 32) | (x << 32);
+#endif
+}
+
+// ------------------------------------------------------------------ K1: allele calls
+// CigarStringView::read_pos(ref_pos, false, false) over BAM-encoded ops; n_cig == 0 means one M.
+// Returns 1 and *qpos on Some, 0 on None / Err (the caller treats both as "no support", :106-110).
+MPH_HD int mph_read_pos(const uint32_t* cig, uint32_t n_cig, uint32_t l_seq, uint32_t start, uint32_t ref_pos,
+                        uint32_t* qpos_out) {
+  if (n_cig == 0) {
+    if (ref_pos >= start && ref_pos - start < l_seq) { *qpos_out = ref_pos - start; return 1; }
+    return 0;
+  }
+  uint32_t j = 0;
+  for (uint32_t i = 0; i < n_cig; ++i) {
+    const uint32_t op = cig[i] & 15u;
+    if (op == 0 || op == 8 || op == 7 || op == 1 || op == 4) { j = i; break; }  // M X = I S
+    if (op == 2 || op == 3) return 0;                                          // D / N first: Err
+    if (op == 5 && i > 0 && i + 1 < n_cig) return 0;                           // H in the middle: Err
+    if ((op == 6 || op == 5) && i + 1 == n_cig) return 0;                      // only P / H: None
+  }
+  uint64_t rpos = start, qpos = 0;
+  while (rpos <= ref_pos && j < n_cig) {
+    const uint32_t op = cig[j] & 15u;
+    const uint64_t l = cig[j] >> 4;
+    if (op == 0 || op == 8 || op == 7) {
+      if (rpos + l > ref_pos) { *qpos_out = (uint32_t)(qpos + (ref_pos - rpos)); return 1; }
+      rpos += l; qpos += l; ++j;
+    } else if (op == 4 || op == 1) { qpos += l; ++j; }
+    else if (op == 3 || op == 2) { rpos += l; ++j; }
+    else if (op == 6) { ++j; }
+    else { return 0; }  // H: Err in the middle, None at the end
+  }
+  return 0;
+}
+
+// supports_variant / bad_quality for every variant with pos in [start, end) of one read.
+// `bases` points at the read's packed record: ceil(l_seq/2) B of 4-bit codes (high nibble first),
+// then ceil(l_seq/8) B with bit i set iff qual[i] < 10.
+MPH_HD MphCall mph_call_read(const MphRead& r, const uint8_t* bases, const uint32_t* cig, const MphVar* vars) {
+  MphCall c;
+  c.S = 0;
+  c.B = 0;
+  const uint32_t nv = r.nv;
+  if (nv == 0) return c;
+  const uint8_t* lowq = bases + ((r.l_seq + 1u) >> 1);
+  for (uint32_t j = 0; j < nv; ++j) {
+    const MphVar v = vars[r.vlo + j];
+    bool sup = false;
+    if (v.kind == MPH_SNV) {
+      const uint32_t rel = v.pos - r.start;  // raw reference offset indexes the *query* qualities (:82-84,99-101)
+      bool low = false;
+      if (rel < r.l_seq) low = (lowq[rel >> 3] >> (rel & 7u)) & 1u;
+      if (low) {
+        c.B |= (uint64_t)1 << j;
+      } else {
+        uint32_t q;
+        if (mph_read_pos(cig, r.n_cig, r.l_seq, r.start, v.pos, &q) && q < r.l_seq) {
+          const uint8_t b = bases[q >> 1];
+          const uint8_t code = (q & 1u) ? (b & 15u) : (b >> 4);
+          sup = code == v.alt4;
+        }
+      }
+    } else {
+      const uint32_t want = v.kind == MPH_INS ? 1u : 2u;  // BAM op codes: I = 1, D = 2
+      for (uint32_t i = 0; i < r.n_cig; ++i)
+        if ((cig[i] & 15u) == want && (cig[i] >> 4) == v.len) { sup = true; break; }
+    }
+    if (sup) c.S |= (uint64_t)1 << j;
+  }
+  return c;
+}
+
+// Reads that can be observations of window gk: start <= s, and start not further left than the
+// candidate range of the reference (:1191-1249) nor than the longest alignment allows.
+MPH_HD void mph_candidate_range(const MphSegment& g, const uint32_t* read_start, const MphGeom& gk, uint32_t* rlo, uint32_t* rhi) {
+  const bool rev = (g.flags & MPH_SF_REVERSE) != 0;
+  int64_t lo = rev ? (int64_t)gk.s - (int64_t)g.K : (int64_t)(g.off0 - g.ceo) - (int64_t)g.K;
+  const int64_t lo2 = (int64_t)gk.e - (int64_t)g.max_span;
+  if (lo2 > lo) lo = lo2;
+  if (lo < 0) lo = 0;
+  *rlo = mph_u32_lb(read_start, g.read_lo, g.read_hi, (uint32_t)lo);
+  *rhi = mph_u32_lb(read_start, *rlo, g.read_hi, gk.s + 1u);
+}
+
+// ------------------------------------------------------------------ K2: one (read, window) pair
+typedef struct {
+  uint32_t member;  // the read is an observation of the matrix at this window (counts towards depth)
+  uint32_t bad;     // obs.bad_qual
+  uint64_t hap;     // obs.haplotype
+  uint32_t frame;   // obs.frame.0 | (obs.frame.1 != 0) << 31
+} MphPair;
+
+// bit j of the result <-> window variant j (list order), from the read's S mask
+MPH_HD uint64_t mph_window_bits(uint64_t S, uint32_t vlo, uint32_t va, uint32_t n) {
+  if (n == 0 || va < vlo || va - vlo >= 64) return 0;
+  uint64_t b = S >> (va - vlo);
+  if (n < 64) b &= (((uint64_t)1 << n) - 1);
+  return b;
+}
+
+// obs.frame accumulators over the variants the observation has evaluated so far (:172-174,188)
+MPH_HD uint32_t mph_frames(const MphVar* vars, uint32_t ia, uint32_t ib, uint32_t vlo, uint64_t S) {
+  uint32_t f0 = 0, f1nz = 0;
+  for (uint32_t j = ia; j < ib; ++j) {
+    const uint32_t fs = (vars[j].flags & MPH_VF_FS_MASK) >> MPH_VF_FS_SHIFT;
+    if (fs) {
+      if (vars[j].pos != 0) f1nz = 1;
+      if (j >= vlo && j - vlo < 64 && ((S >> (j - vlo)) & 1)) f0 += fs;
+    }
+  }
+  return f0 | (f1nz << 31);
+}
+
+// Forward strand: the read is offered exactly once per segment — at iteration 0 if
+// start in [s0-K, s0], else at the iteration whose window starts at `start` (:1227-1248); a read
+// that turns bad_qual while the variants retained from the previous window are evaluated is dropped
+// for good (:324-335); afterwards badness is sticky (:192-195) and the read stays while
+// end_pos >= splice_end (:259-273).
+MPH_HD MphPair mph_fwd_state(const MphSegment& g, const MphVar* vars, uint32_t k, const MphGeom& gk, uint32_t va, uint32_t vb,
+                             uint32_t start, uint32_t end, uint32_t vlo, uint64_t S, uint64_t B) {
+  MphPair o;
+  o.member = 0; o.bad = 0; o.hap = 0; o.frame = 0;
+  if (end < gk.e) return o;
+  const uint32_t s0 = g.off0 - g.ceo;
+  uint32_t k_ins;
+  if (start <= s0) {
+    if ((int64_t)start < (int64_t)s0 - (int64_t)g.K) return o;
+    k_ins = 0;
+  } else {
+    if (start <= g.off0) return o;  // starts in (s0, off0] are never offered when ceo > 0
+    k_ins = start - g.off0;
+    if (k_ins > k) return o;
+  }
+  const uint64_t Bx = B | (S & mph_range_mask(g.sl_va, g.sl_vb, vlo));
+  const bool has_fs = (g.flags & MPH_SF_HAS_FS) != 0;
+  if (Bx || has_fs) {
+    const MphGeom gi = k_ins == k ? gk : mph_geom(g, k_ins);
+    const uint32_t ia = mph_var_lb(vars, g.var_lo, g.var_hi, gi.s);
+    if (Bx) {
+      if (k_ins > 0) {
+        const uint32_t ib = mph_var_lb(vars, g.var_lo, g.var_hi, mph_geom(g, k_ins - 1).e);
+        if (Bx & mph_range_mask(ia, ib, vlo)) return o;  // rejected at push
+      }
+      o.bad = (Bx & mph_range_mask(ia, vb, vlo)) != 0;
+    }
+    if (has_fs) o.frame = mph_frames(vars, ia, vb, vlo, S);
+  }
+  o.member = 1;
+  if (!o.bad) {
+    const uint32_t n = vb - va;
+    const uint64_t bits = mph_window_bits(S, vlo, va, n);
+    o.hap = n ? (mph_bitrev64(bits) >> (64 - n)) : 0;  // newest variant = bit 0 (:324,248)
+  }
+  return o;
+}
+
+// Reverse strand: every read with start in [s-K, s] is re-offered at every iteration (:1191-1226);
+// it enters at the first iteration where it encloses the window and none of the variants retained
+// from the previous window is bad for it; `contains` (:281-294) keeps it from entering twice.
+// Returns the entry iteration or 0xFFFFFFFF.
+MPH_HD uint32_t mph_rev_entry(const MphSegment& g, const MphVar* vars, uint32_t k, uint32_t start, uint32_t end, uint32_t vlo,
+                              uint64_t Bx) {
+  const uint64_t lim = (uint64_t)start + g.K;
+  uint32_t kc = g.off0 > lim ? (uint32_t)(g.off0 - lim) : 0;
+  if (mph_geom(g, 0).e > end) {
+    const uint64_t t = (uint64_t)g.off0 + g.ewl;
+    const uint32_t k2 = t > end ? (uint32_t)(t - end) : 1;
+    if (k2 > kc) kc = k2;
+    if (kc == 0) kc = 1;
+  }
+  for (; kc <= k; ++kc) {
+    const MphGeom gc = mph_geom(g, kc);
+    if (gc.s <= lim && gc.e <= end && start <= gc.s) break;
+  }
+  if (kc > k) return 0xFFFFFFFFu;
+  if (!Bx) return kc;
+  for (uint32_t ke = kc; ke <= k; ++ke) {
+    if (ke == 0) return 0;
+    const uint32_t ia = mph_var_lb(vars, g.var_lo, g.var_hi, mph_geom(g, ke - 1).s);
+    const uint32_t ib = mph_var_lb(vars, g.var_lo, g.var_hi, mph_geom(g, ke).e);
+    if (!(Bx & mph_range_mask(ia, ib, vlo))) return ke;
+  }
+  return 0xFFFFFFFFu;
+}
+
+MPH_HD MphPair mph_rev_state(const MphSegment& g, const MphVar* vars, uint32_t k, const MphGeom& gk, uint32_t va, uint32_t vb,
+                             uint32_t start, uint32_t end, uint32_t vlo, uint64_t S, uint64_t B, uint32_t ke) {
+  MphPair o;
+  o.member = 1; o.bad = 0; o.hap = 0; o.frame = 0;
+  (void)end; (void)k;
+  const uint64_t Bx = B | (S & mph_range_mask(g.sl_va, g.sl_vb, vlo));
+  const bool has_fs = (g.flags & MPH_SF_HAS_FS) != 0;
+  if (Bx || has_fs) {
+    const uint32_t ib = mph_var_lb(vars, g.var_lo, g.var_hi, mph_geom(g, ke).e);
+    if (Bx) o.bad = (Bx & mph_range_mask(va, ib, vlo)) != 0;
+    if (has_fs) o.frame = mph_frames(vars, va, ib, vlo, S);
+  }
+  if (!o.bad) o.hap = mph_window_bits(S, vlo, va, vb - va);  // bit j <-> variants[j] (:486-489)
+  (void)gk; (void)start;
+  return o;
+}
+
+// ------------------------------------------------------------------ K3: haplotype assembly
+MPH_HD bool mph_is_upper(uint8_t c) { return c >= 'A' && c <= 'Z'; }
+MPH_HD uint8_t mph_lower(uint8_t c) { return (c >= 'A' && c <= 'Z') ? (uint8_t)(c + 32) : c; }
+MPH_HD uint8_t mph_upper(uint8_t c) { return (c >= 'a' && c <= 'z') ? (uint8_t)(c - 32) : c; }
+
+// has_stop_codon :42-76 — case-sensitive, forward scans codons from the front, reverse from the back
+MPH_HD bool mph_has_stop(const uint8_t* p, uint32_t n, bool forward) {
+  if (n < 3) return false;
+  if (forward) {
+    for (uint32_t c = 0; c + 3 <= n; c += 3) {
+      if (p[c] == 'T' && ((p[c + 1] == 'G' && p[c + 2] == 'A') || (p[c + 1] == 'A' && (p[c + 2] == 'G' || p[c + 2] == 'A')))) return true;
+    }
+    return false;
+  }
+  uint32_t c = n - 3;
+  for (;;) {
+    if (p[c + 2] == 'A' && ((p[c] == 'T' && p[c + 1] == 'C') || (p[c] == 'C' && p[c + 1] == 'T') || (p[c] == 'T' && p[c + 1] == 'T'))) return true;
+    if (c < 3) return false;
+    c -= 3;
+  }
+}
+
+// neopeptide slice of the assembled sequence (:686-693): [a, b)
+MPH_HD void mph_neo_slice(const MphGeom& g, uint32_t seq_len, uint32_t window_len, bool insertion, uint32_t* a, uint32_t* b) {
+  const uint32_t twl = seq_len < window_len ? seq_len : window_len;  // this_window_len :651-654
+  if (g.spos == 1) { *a = g.gap < seq_len ? g.gap : seq_len; *b = seq_len; }
+  else if (g.spos == 0) { *a = 0; *b = insertion ? seq_len : twl; }
+  else { *a = 0; *b = seq_len; }
+}
+
+// Walk of print_haplotypes :458-603 for one haplotype. seq / germ must hold `cap` bytes each;
+// bytes beyond cap are dropped and MPH_HF_OVERFLOW is raised. Returns MPH_E_* error bits.
+MPH_HD uint32_t mph_assemble(const MphSegment& g, const MphGeom& gk, const MphVar* vars, uint32_t va, uint32_t vb,
+                             const uint8_t* ref_arena, const uint8_t* ins_arena, uint64_t hap, uint8_t* seq, uint8_t* germ,
+                             uint32_t cap, MphHap* out) {
+  const bool rev = (g.flags & MPH_SF_REVERSE) != 0;
+  const uint32_t n = vb - va;
+  uint32_t err = 0, sl = 0, gl = 0, flags = 0, n_var = 0, n_som = 0, n_prof = 0;
+  uint64_t profile = 0;
+  const uint8_t* ref = ref_arena + g.ref_off;
+#define MPH_REF(i_, dst_)                                          \
+  do {                                                             \
+    const uint64_t ri_ = (uint64_t)(i_) - g.ref_pos0;              \
+    if ((i_) < g.ref_pos0 || ri_ >= g.ref_len) { err |= MPH_E_REF_RANGE; dst_ = 'N'; } \
+    else dst_ = ref[ri_];                                          \
+  } while (0)
+#define MPH_PUSH(buf_, len_, c_)           \
+  do {                                     \
+    if ((len_) < cap) (buf_)[len_] = (c_); \
+    else flags |= MPH_HF_OVERFLOW;         \
+    ++(len_);                              \
+  } while (0)
+  uint64_t i = gk.s;
+  uint32_t j = 0;
+  const uint64_t window_end = gk.e;
+  while (i < window_end) {
+    while (j < n && i == vars[va + j].pos) {
+      const MphVar v = vars[va + j];
+      const uint32_t bit_pos = rev ? j : n - 1 - j;
+      const bool germline = (v.flags & MPH_VF_GERMLINE) != 0;
+      if ((hap >> (bit_pos & 63)) & 1) {
+        uint8_t r;
+        if (v.kind == MPH_SNV) {
+          MPH_REF(i, r);
+          const uint8_t a = mph_is_upper(r) ? mph_lower(v.alt) : v.alt;  // switch_ascii_case :26-32
+          MPH_PUSH(germ, gl, germline ? a : r);
+          MPH_PUSH(seq, sl, a);
+          i += 1;
+        } else if (v.kind == MPH_INS) {
+          MPH_REF(i, r);
+          const bool up = mph_is_upper(r);
+          for (uint32_t t = 0; t <= v.len; ++t) {
+            const uint8_t c0 = ins_arena[v.ins_off + t];
+            const uint8_t c = up ? mph_lower(c0) : mph_upper(c0);  // switch_ascii_case_vec :34-40
+            if (germline) MPH_PUSH(germ, gl, c);
+            MPH_PUSH(seq, sl, c);
+          }
+          if (!germline) flags |= MPH_HF_INDEL;
+          flags |= MPH_HF_INSERTION;
+          i += 1;
+        } else {
+          if (rev && (uint64_t)v.pos + v.len - 1 >= window_end) break;  // :549-552 (j stays stuck)
+          MPH_REF(i, r);
+          if (germline || i == window_end - 1) {
+            MPH_PUSH(germ, gl, r);
+          } else {
+            for (uint64_t t = i; t < i + v.len + 1; ++t) {
+              uint8_t rr;
+              MPH_REF(t, rr);
+              MPH_PUSH(germ, gl, rr);
+            }
+            flags |= MPH_HF_INDEL;
+          }
+          MPH_PUSH(seq, sl, r);
+          i += (uint64_t)v.len + 1;
+        }
+        const uint64_t code = germline ? 1 : 2;
+        if (n_prof < 32) profile |= code << (2 * n_prof);
+        if (!germline) ++n_som;
+        ++n_var;
+      }
+      ++n_prof;
+      ++j;
+    }
+    if (i < window_end) {
+      uint8_t r;
+      MPH_REF(i, r);
+      MPH_PUSH(seq, sl, r);
+      MPH_PUSH(germ, gl, r);
+      i += 1;
+    }
+  }
+#undef MPH_REF
+#undef MPH_PUSH
+  if (n_prof > 32) err |= MPH_E_VARS_PER_WINDOW;
+  bool eq = sl == gl;
+  const uint32_t lim = sl < cap ? sl : cap;
+  for (uint32_t t = 0; eq && t < lim; ++t) eq = seq[t] == germ[t];
+  if (eq) flags |= MPH_HF_GERM_EQ;
+  uint32_t a, b;
+  mph_neo_slice(gk, sl < cap ? sl : cap, g.ewl, (flags & MPH_HF_INSERTION) != 0, &a, &b);
+  if (mph_has_stop(seq + a, b - a, !rev)) flags |= MPH_HF_STOP;
+  out->flags = flags;
+  out->seq_len = (uint16_t)sl;
+  out->germ_len = (uint16_t)gl;
+  out->n_var = (uint8_t)n_var;
+  out->n_som = (uint8_t)n_som;
+  out->n_prof = (uint8_t)(n_prof < 255 ? n_prof : 255);
+  out->pad = 0;
+  out->seq_off = 0xFFFFFFFFu;
+  out->profile = profile;
+  out->pad2 = 0;
+  return err;
+}
+
+// window without variants: seq == germline_seq == refseq[s..e) (:464-471); only the stop test is needed
+MPH_HD uint32_t mph_plain_window(const MphSegment& g, const MphGeom& gk, const uint8_t* ref_arena, MphHap* out) {
+  uint32_t err = 0;
+  const uint32_t len = gk.e - gk.s;
+  uint32_t flags = MPH_HF_GERM_EQ;
+  if (gk.s < g.ref_pos0 || (uint64_t)gk.e - g.ref_pos0 > g.ref_len) {
+    err |= MPH_E_REF_RANGE;
+  } else {
+    const uint8_t* p = ref_arena + g.ref_off + (gk.s - g.ref_pos0);
+    uint32_t a, b;
+    mph_neo_slice(gk, len, g.ewl, false, &a, &b);
+    if (mph_has_stop(p + a, b - a, (g.flags & MPH_SF_REVERSE) == 0)) flags |= MPH_HF_STOP;
+  }
+  out->flags = flags;
+  out->seq_len = (uint16_t)len;
+  out->germ_len = (uint16_t)len;
+  out->n_var = 0; out->n_som = 0; out->n_prof = 0; out->pad = 0;
+  out->seq_off = 0xFFFFFFFFu;
+  out->profile = 0;
+  out->pad2 = 0;
+  return err;
+}

@@ -1,0 +1,351 @@
+// batch.hpp — host-side batch: the structure-of-arrays buffers that cross the C ABI
+// (include/microphaser_gpu.h: mph_batch_in) plus the host-only metadata needed to print records.
+//
+// The Packer restates the data-independent part of the reference's per-gene set-up and exon loop
+// (reference src/microphasing.rs:894-1029): read selection (mapq >= 5, :910), max_read_len (:913),
+// variant_tree flattening (:932-942), per-exon current_exon_offset / is_short_exon /
+// exon_window_len / start offset (:989-1019) and the exon_rest carry between exons (:1386-1400).
+#pragma once
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../core/layout.h"
+#include "../core/phase_core.h"
+
+namespace mph {
+
+struct Fatal : std::runtime_error {  // the reference panics (exit status 101)
+  using std::runtime_error::runtime_error;
+};
+struct Unsupported : std::runtime_error {  // input needs the serial path that is not built yet
+  using std::runtime_error::runtime_error;
+};
+
+struct HostVariant {
+  uint32_t pos = 0, len = 0;
+  uint8_t kind = MPH_SNV, alt = 0;
+  bool germline = true;
+  std::string ins;          // whole ALT allele for insertions
+  std::string prot_change;  // common.rs:23-33
+  uint32_t fs() const {     // common.rs:215-221
+    if (kind == MPH_SNV) return 0;
+    if (kind == MPH_DEL) return len % 3;
+    return (3 - ((uint32_t(ins.size()) - 1) % 3)) % 3;
+  }
+};
+
+struct HostRead {  // what the host parser hands over per alignment record
+  uint32_t start = 0, end = 0, l_seq = 0;
+  const uint8_t* seq4 = nullptr;  // BAM 4-bit bases
+  const uint8_t* qual = nullptr;  // raw phred
+  const uint32_t* cigar = nullptr;
+  uint32_t n_cigar = 0;
+  uint64_t qname_hash = 0;
+};
+
+struct HostExon {
+  uint32_t start, end, frame;
+};
+struct HostTranscript {
+  std::string id;
+  bool reverse = false;
+  std::vector<HostExon> exons;
+};
+struct HostGene {
+  std::string id, name, chrom;
+  uint32_t start = 0, end = 0;
+  std::vector<HostTranscript> transcripts;
+};
+
+struct TxMeta {
+  std::string id;
+  uint32_t gene;  // index into Batch::genes
+  bool reverse;
+  uint32_t seg_lo, seg_hi;
+};
+struct GeneMeta {
+  std::string id, name, chrom;
+  uint32_t start, end;
+  uint32_t var_lo, var_hi, read_lo, read_hi;
+  std::vector<uint8_t> refseq;  // [start, end + 100) as fetched by the reference (:895-901); host keeps it for splice merging
+};
+
+struct Batch {
+  uint32_t window_len = 27;
+  // reads (SoA)
+  std::vector<uint32_t> read_start, read_end, read_vlo, read_seq_off, read_cig_off;
+  std::vector<uint16_t> read_lseq, read_ncig;
+  std::vector<uint8_t> read_nv, read_flags;
+  std::vector<uint32_t> partner_a, partner_b;  // sorted pairs (a < b) of reads with identical (start, qname)
+  std::vector<uint8_t> bases;                  // 16-B aligned packed records: 4-bit bases + (qual<10) bits
+  std::vector<uint32_t> cigars;
+  // variants
+  std::vector<MphVar> vars;
+  std::vector<uint8_t> ins_bytes;
+  std::vector<std::string> var_prot;  // host only
+  // geometry
+  std::vector<MphSegment> segs;
+  std::vector<MphChunk> chunks;
+  std::vector<uint8_t> ref;  // per-segment reference slices
+  uint64_t n_windows = 0;
+  uint32_t seq_cap = 64;  // bytes per assembled sequence slot
+  // host-only
+  std::vector<TxMeta> txs;
+  std::vector<GeneMeta> genes;
+
+  uint64_t n_reads() const { return read_start.size(); }
+};
+
+inline uint8_t base_code(uint8_t c) {
+  static const char* dec = "=ACMGRSVTWYHKDBN";
+  for (int i = 0; i < 16; ++i)
+    if (uint8_t(dec[i]) == c) return uint8_t(i);
+  return 0xFF;
+}
+
+class Packer {
+ public:
+  explicit Packer(uint32_t window_len, uint32_t chunk_windows = 32) : chunk_windows_(chunk_windows) { b_.window_len = window_len; }
+
+  // `reads`: the records bam::RecordBuffer holds for this gene after the mapq filter, in file order;
+  // `max_read_len`: max seq().len() over them (:913-915); `sites`: variant_tree in ascending position
+  // order, each site holding its ALT alleles in VCF order (:937); `refseq`: bases of
+  // [gene.start, gene.end + 100).
+  void add_gene(const HostGene& g, const std::vector<HostRead>& reads, uint32_t max_read_len,
+                const std::vector<std::vector<HostVariant>>& sites, std::vector<uint8_t> refseq) {
+    const uint32_t wl = b_.window_len;
+    GeneMeta gm;
+    gm.id = g.id; gm.name = g.name; gm.chrom = g.chrom; gm.start = g.start; gm.end = g.end;
+    const uint32_t gi = uint32_t(b_.genes.size());
+    // strand decides the ALT order inside a multi-allelic site (print_haplotypes :373-379)
+    int strand = -1;
+    bool mixed = false;
+    for (auto& t : g.transcripts) {
+      if (t.exons.empty()) continue;
+      if (strand < 0) strand = t.reverse ? 1 : 0;
+      else if (strand != (t.reverse ? 1 : 0)) mixed = true;
+    }
+    bool multi = false;
+    gm.var_lo = uint32_t(b_.vars.size());
+    uint32_t max_del = 0, max_ins = 0;
+    bool has_fs = false;
+    for (auto& site : sites) {
+      if (site.size() > 1) multi = true;
+      for (size_t a = 0; a < site.size(); ++a) {
+        const HostVariant& hv = site[strand == 1 ? site.size() - 1 - a : a];
+        MphVar v;
+        memset(&v, 0, sizeof v);
+        v.pos = hv.pos; v.len = hv.len; v.kind = hv.kind; v.alt = hv.alt;
+        v.flags = uint8_t((hv.germline ? MPH_VF_GERMLINE : 0) | (hv.fs() << MPH_VF_FS_SHIFT));
+        v.alt4 = hv.kind == MPH_SNV ? base_code(hv.alt) : 0xFF;
+        if (hv.kind == MPH_INS) {
+          v.ins_off = uint32_t(b_.ins_bytes.size());
+          b_.ins_bytes.insert(b_.ins_bytes.end(), hv.ins.begin(), hv.ins.end());
+          if (hv.len + 1 > max_ins) max_ins = hv.len + 1;
+        }
+        if (hv.kind == MPH_DEL && hv.len > max_del) max_del = hv.len;
+        if (hv.fs()) has_fs = true;
+        b_.vars.push_back(v);
+        b_.var_prot.push_back(hv.prot_change);
+      }
+    }
+    gm.var_hi = uint32_t(b_.vars.size());
+    if (mixed && multi) throw Unsupported("gene " + g.id + ": multi-allelic sites with transcripts on both strands");
+    // assembled sequences can grow by insertions / deleted reference bases
+    uint32_t need = wl + 8 + 2 * (max_ins + max_del);
+    need = (need + 15u) & ~15u;
+    if (need > b_.seq_cap) b_.seq_cap = need;
+
+    // reads
+    gm.read_lo = uint32_t(b_.read_start.size());
+    uint32_t vcur = gm.var_lo, max_span = 0;
+    std::unordered_map<uint64_t, uint32_t> seen;  // (start, qname) -> first read index
+    for (auto& r : reads) {
+      const uint32_t idx = uint32_t(b_.read_start.size());
+      while (vcur < gm.var_hi && b_.vars[vcur].pos < r.start) ++vcur;
+      uint32_t ve = vcur;
+      while (ve < gm.var_hi && b_.vars[ve].pos < r.end) ++ve;
+      uint32_t nv = ve - vcur;
+      uint8_t flags = 0;
+      if (nv > 64) { nv = 64; flags |= MPH_RF_OVERFLOW; }
+      const bool single_m = r.n_cigar == 1 && (r.cigar[0] & 15u) == 0 && (r.cigar[0] >> 4) == r.l_seq;
+      b_.read_start.push_back(r.start);
+      b_.read_end.push_back(r.end);
+      b_.read_vlo.push_back(vcur);
+      b_.read_lseq.push_back(uint16_t(r.l_seq));
+      b_.read_nv.push_back(uint8_t(nv));
+      if (r.l_seq > 0xFFFF) throw Unsupported("read longer than 65535 bases");
+      if (nv > 0) {
+        // packed record: 4-bit bases then (qual < 10) bits, 16-B aligned
+        const size_t off = (b_.bases.size() + 15u) & ~size_t(15);
+        const size_t nb = (r.l_seq + 1u) / 2, nq = (r.l_seq + 7u) / 8;
+        b_.bases.resize(off + nb + nq, 0);
+        memcpy(&b_.bases[off], r.seq4, nb);
+        for (uint32_t i = 0; i < r.l_seq; ++i)
+          if (r.qual[i] < 10) b_.bases[off + nb + (i >> 3)] |= uint8_t(1u << (i & 7));
+        b_.read_seq_off.push_back(uint32_t(off / 16));
+        if (!single_m) {
+          b_.read_cig_off.push_back(uint32_t(b_.cigars.size()));
+          b_.read_ncig.push_back(uint16_t(r.n_cigar));
+          b_.cigars.insert(b_.cigars.end(), r.cigar, r.cigar + r.n_cigar);
+        } else {
+          b_.read_cig_off.push_back(0);
+          b_.read_ncig.push_back(0);
+        }
+      } else {
+        b_.read_seq_off.push_back(0xFFFFFFFFu);
+        b_.read_cig_off.push_back(0);
+        b_.read_ncig.push_back(0);
+      }
+      if (strand == 1) {  // `contains` only bites on the reverse strand (keys are read starts, :328-331)
+        const uint64_t key = r.qname_hash * 0x9E3779B97F4A7C15ull ^ (uint64_t(r.start) << 1);
+        auto it = seen.find(key);
+        if (it == seen.end()) {
+          seen.emplace(key, idx);
+        } else {
+          const uint32_t first = it->second;
+          if (b_.read_flags[first] & MPH_RF_PARTNER) throw Unsupported("gene " + g.id + ": more than two reads share (start, qname)");
+          b_.read_flags[first] |= MPH_RF_PARTNER;
+          flags |= MPH_RF_PARTNER;
+          b_.partner_a.push_back(first);
+          b_.partner_b.push_back(idx);
+        }
+      }
+      b_.read_flags.push_back(flags);
+      if (r.end - r.start > max_span) max_span = r.end - r.start;
+    }
+    gm.read_hi = uint32_t(b_.read_start.size());
+
+    // transcripts -> segments
+    const uint32_t ref_end = g.start + uint32_t(refseq.size());
+    const uint32_t margin = max_del + 2;
+    for (auto& t : g.transcripts) {
+      if (t.exons.empty()) continue;  // is_coding (:947)
+      TxMeta tm;
+      tm.id = t.id; tm.gene = gi; tm.reverse = t.reverse;
+      tm.seg_lo = uint32_t(b_.segs.size());
+      const uint32_t txi = uint32_t(b_.txs.size());
+      uint64_t exon_rest = 0;
+      uint32_t exon_count = 0;
+      const size_t exon_number = t.exons.size();
+      for (auto& ex : t.exons) {
+        if (ex.start > ex.end) continue;  // :981
+        exon_count += 1;
+        const uint64_t exon_len = ex.end - ex.start;
+        const uint64_t ceo = exon_count == 1 ? ex.frame : (exon_rest == 0 ? 0 : 3 - exon_rest);
+        const bool is_short = exon_len < 3 ? true : uint64_t(wl) >= exon_len - ceo - (3 - ceo) % 3;
+        if (ceo > exon_len || ceo > 2) throw Unsupported("transcript " + t.id + ": exon offset " + std::to_string(ceo) + " does not fit the exon");
+        uint64_t ewl = !is_short ? wl : (exon_len - ceo) - ((exon_len - ceo) % 3);
+        if (ewl == 0) ewl = exon_len;
+        exon_rest = 0;
+        if (max_read_len < ewl) continue;  // :1046 — loop breaks before touching the matrix
+        MphSegment sg;
+        memset(&sg, 0, sizeof sg);
+        sg.exon_start = ex.start; sg.exon_end = ex.end;
+        sg.ewl = uint32_t(ewl); sg.ceo = uint32_t(ceo);
+        sg.flags = (t.reverse ? MPH_SF_REVERSE : 0) | (is_short ? MPH_SF_SHORT : 0) | (exon_count == 1 ? MPH_SF_FIRST_EXON : 0) |
+                   (exon_count == exon_number ? MPH_SF_LAST_EXON : 0) | (has_fs ? MPH_SF_HAS_FS : 0);
+        if (t.reverse) {
+          if (uint64_t(ex.end) < ewl + ceo) throw Unsupported("transcript " + t.id + ": exon offset underflow");
+          sg.off0 = uint32_t(ex.end - ewl - ceo);
+          if (sg.off0 < ex.start) continue;  // !valid at the first iteration
+          sg.n_iter = is_short ? 1 : sg.off0 - ex.start + 1;
+        } else {
+          sg.off0 = uint32_t(ex.start + ceo);
+          if (uint64_t(sg.off0) + ewl > ex.end) continue;
+          sg.n_iter = is_short ? 1 : uint32_t(ex.end - ewl - sg.off0 + 1);
+        }
+        sg.K = uint32_t(max_read_len - ewl);
+        if (!t.reverse && uint64_t(sg.off0 - sg.ceo) < sg.K) throw Fatal("range start is greater than range end in BTreeMap");
+        sg.read_lo = gm.read_lo; sg.read_hi = gm.read_hi;
+        sg.var_lo = gm.var_lo; sg.var_hi = gm.var_hi;
+        sg.max_span = max_span;
+        if (exon_count == 1) {  // start-loss positions (:1305-1316)
+          const uint32_t lo = t.reverse ? (ex.end >= 3 ? ex.end - 3 : 0) : ex.start;
+          const uint32_t hi = t.reverse ? ex.end : ex.start + 3;
+          sg.sl_va = mph_var_lb(b_.vars.data(), gm.var_lo, gm.var_hi, lo);
+          sg.sl_vb = mph_var_lb(b_.vars.data(), gm.var_lo, gm.var_hi, hi);
+        }
+        // windows: main-ORF iterations only, unless the gene has frameshifting variants
+        if (is_short) { sg.k_first = 0; sg.k_stride = 1; sg.n_win = 1; }
+        else if (has_fs) { sg.k_first = 0; sg.k_stride = 1; sg.n_win = sg.n_iter; }
+        else {
+          sg.k_stride = 3;
+          sg.k_first = t.reverse ? (3 - uint32_t(ewl % 3)) % 3 : 0;  // coding_shift % 3 == ceo % 3 (:1372-1381)
+          sg.n_win = sg.k_first < sg.n_iter ? (sg.n_iter - 1 - sg.k_first) / 3 + 1 : 0;
+        }
+        // exon_rest after this exon = rest at the last main-ORF window (:1386-1400)
+        {
+          uint32_t k_last_main;
+          bool any = true;
+          if (is_short) k_last_main = 0;
+          else {
+            const uint32_t kf = t.reverse ? (3 - uint32_t(ewl % 3)) % 3 : 0;
+            if (kf >= sg.n_iter) any = false;
+            k_last_main = any ? kf + ((sg.n_iter - 1 - kf) / 3) * 3 : 0;
+          }
+          if (any) {
+            exon_rest = t.reverse ? (sg.off0 - k_last_main) - ex.start : ex.end - (sg.off0 + k_last_main + ewl);
+            if (ewl < 3) exon_rest = ewl;
+          }
+        }
+        // reference slice: the exon plus the overhang a deletion can reach (:560-563)
+        sg.ref_pos0 = ex.start;
+        const uint32_t slice_end = std::min<uint64_t>(uint64_t(ex.end) + margin, ref_end);
+        if (ex.start < g.start || slice_end < ex.start) throw Fatal("slice index out of range: refseq");
+        sg.ref_off = uint32_t(b_.ref.size());
+        sg.ref_len = slice_end - ex.start;
+        b_.ref.insert(b_.ref.end(), refseq.begin() + (ex.start - g.start), refseq.begin() + (slice_end - g.start));
+        sg.tx = txi;
+        sg.win_base = uint32_t(b_.n_windows);
+        b_.n_windows += sg.n_win;
+        const uint32_t si = uint32_t(b_.segs.size());
+        // carry-over of observations from the previous exon needs the serial path
+        if (si > tm.seg_lo) check_carry_over(b_.segs[si - 1], sg, t.id);
+        b_.segs.push_back(sg);
+        for (uint32_t i = 0; i < sg.n_win; i += chunk_windows_) {
+          MphChunk c;
+          c.seg = si; c.i_first = i; c.n = std::min(chunk_windows_, sg.n_win - i); c.pad = 0;
+          b_.chunks.push_back(c);
+        }
+      }
+      tm.seg_hi = uint32_t(b_.segs.size());
+      b_.txs.push_back(std::move(tm));
+    }
+    gm.refseq = std::move(refseq);
+    b_.genes.push_back(std::move(gm));
+  }
+
+  Batch& batch() { return b_; }
+
+ private:
+  // An observation survives into the next exon when it still passes cleanup_reads there
+  // (:259-278); exome introns are longer than a read, so this is rare, and the closed form of
+  // phase_core.h does not model it.
+  void check_carry_over(const MphSegment& a, const MphSegment& bseg, const std::string& tx) {
+    if (a.n_iter == 0) return;
+    const MphGeom ga = mph_geom(a, a.n_iter - 1), gb = mph_geom(bseg, 0);
+    const bool rev = (a.flags & MPH_SF_REVERSE) != 0;
+    // a carried read encloses the last window of A and still passes B's first cleanup:
+    //   forward: start <= s_A and end >= e_B ; reverse: start <= s_B and end >= e_A
+    const uint32_t need_end = rev ? ga.e : gb.e;
+    const uint32_t max_start = rev ? std::min(ga.s, gb.s) : ga.s;
+    const uint32_t min_start = need_end > a.max_span ? need_end - a.max_span : 0;
+    if (min_start > max_start) return;
+    auto lo = std::lower_bound(b_.read_start.begin() + a.read_lo, b_.read_start.begin() + a.read_hi, min_start) - b_.read_start.begin();
+    for (uint32_t r = uint32_t(lo); r < a.read_hi && b_.read_start[r] <= max_start; ++r)
+      if (b_.read_end[r] >= need_end && b_.read_end[r] >= ga.e)
+        throw Unsupported("transcript " + tx + ": a read spans two exons' windows (observation carry-over)");
+  }
+
+  Batch b_;
+  uint32_t chunk_windows_;
+};
+
+}  // namespace mph

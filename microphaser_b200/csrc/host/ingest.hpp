@@ -1,0 +1,315 @@
+// ingest.hpp — host side of the `somatic` sub-command up to the device boundary:
+// GTF streaming and gene assembly (reference src/microphasing.rs:1982-2125), the per-gene read /
+// variant / reference fetch (:894-942, src/common.rs:71-175) and hand-over to the Packer.
+// rust-htslib's bam::RecordBuffer / bcf::buffer::RecordBuffer fetch semantics are restated from the
+// crate's published behaviour; the crate is not vendored under /root/reference.
+#pragma once
+#include <deque>
+#include <istream>
+#include <memory>
+
+#include "../io/hts_io.hpp"
+#include "batch.hpp"
+
+namespace mph {
+
+inline uint64_t fnv1a(const std::string& s) {
+  uint64_t h = 1469598103934665603ull;
+  for (unsigned char c : s) { h ^= c; h *= 1099511628211ull; }
+  return h;
+}
+
+// bam::RecordBuffer::fetch over a coordinate-sorted BAM held in memory per contig
+class ReadBuffer {
+ public:
+  explicit ReadBuffer(mphio::BamFile& bam) : bam_(bam) {
+    by_tid_.resize(bam.ref_names.size());
+    mphio::BamRecord r;
+    while (bam.next(r)) {
+      if (r.tid < 0 || size_t(r.tid) >= by_tid_.size()) continue;
+      r.aux.clear();
+      by_tid_[r.tid].push_back(std::make_shared<mphio::BamRecord>(std::move(r)));
+    }
+  }
+  using Ptr = std::shared_ptr<const mphio::BamRecord>;
+  const std::deque<Ptr>& fetch(const std::string& chrom, uint64_t start, uint64_t end) {
+    if (overflow_) { inner_.push_back(overflow_); overflow_.reset(); }
+    auto it = bam_.tid_of.find(chrom);
+    if (it == bam_.tid_of.end()) throw std::runtime_error("sequence " + chrom + " not found in BAM header");
+    const int tid = it->second;
+    const auto& v = by_tid_[tid];
+    const bool refetch = inner_.empty() || uint64_t(inner_.back()->pos) < start || inner_.front()->tid != tid ||
+                         uint64_t(inner_.front()->pos) > start;
+    if (refetch) {
+      inner_.clear();
+      tid_ = tid;
+      cur_ = 0;
+      // an index query starts at the first record overlapping `start`
+      while (cur_ < v.size() && uint64_t(v[cur_]->pos) < start && (v[cur_]->is_unmapped() || uint64_t(v[cur_]->end_pos()) <= start)) ++cur_;
+    } else {
+      while (!inner_.empty() && uint64_t(inner_.front()->pos) < start) inner_.pop_front();
+    }
+    while (tid_ == tid && cur_ < v.size()) {
+      const Ptr& r = v[cur_++];
+      if (r->is_unmapped()) continue;
+      const uint64_t pos = uint64_t(r->pos);
+      if (pos >= end) { overflow_ = r; break; }
+      if (pos >= start) inner_.push_back(r);
+    }
+    return inner_;
+  }
+
+ private:
+  mphio::BamFile& bam_;
+  std::vector<std::vector<Ptr>> by_tid_;
+  std::deque<Ptr> inner_;
+  Ptr overflow_;
+  int tid_ = -1;
+  size_t cur_ = 0;
+};
+
+// bcf::Reader (streaming) + bcf::buffer::RecordBuffer::fetch
+class VariantBuffer {
+ public:
+  explicit VariantBuffer(mphio::VcfFile& vcf) : vcf_(vcf) {}
+  const std::deque<mphio::VcfRecord>& fetch(const std::string& chrom, uint64_t start, uint64_t end) {
+    const int rid = vcf_.name2rid(chrom);
+    if (rid < 0) throw std::runtime_error("contig " + chrom + " not found in VCF header");
+    if (!ring_.empty()) {
+      if (ring_.back().rid != rid) { ring_.swap(ring2_); ring2_.clear(); }
+      else drain_left(rid, start);
+    } else if (!ring2_.empty()) {
+      ring_.swap(ring2_); ring2_.clear();
+      drain_left(rid, start);
+    }
+    if (!ring2_.empty()) return ring_;
+    if (have_overflow_) {
+      const uint64_t pos = uint64_t(overflow_.pos);
+      if (pos >= start) {
+        if (pos <= end) { ring_.push_back(overflow_); have_overflow_ = false; }
+        else return ring_;
+      } else {
+        have_overflow_ = false;
+      }
+    }
+    mphio::VcfRecord rec;
+    while (vcf_.next(rec)) {
+      const uint64_t pos = uint64_t(rec.pos);
+      if (rec.rid == rid) {
+        if (pos >= end) { overflow_ = rec; have_overflow_ = true; break; }
+        if (pos >= start) ring_.push_back(rec);
+      } else if (rec.rid > rid) {
+        ring2_.push_back(rec);
+        break;
+      }
+    }
+    return ring_;
+  }
+
+ private:
+  void drain_left(int rid, uint64_t start) {
+    while (!ring_.empty() && ring_.front().rid == rid && uint64_t(ring_.front().pos) < start) ring_.pop_front();
+  }
+  mphio::VcfFile& vcf_;
+  std::deque<mphio::VcfRecord> ring_, ring2_;
+  mphio::VcfRecord overflow_;
+  bool have_overflow_ = false;
+};
+
+// Variant::new (common.rs:71-175)
+inline std::vector<HostVariant> alleles_of(const mphio::VcfFile& vcf, const mphio::VcfRecord& rec, bool warn_only) {
+  auto warn_or_error = [&](const std::string& msg) {
+    fprintf(stderr, "%s\n", msg.c_str());
+    if (!warn_only) throw Fatal(msg);
+  };
+  const bool germline = !(vcf.somatic_defined && rec.somatic_flag);
+  std::string ann;
+  if (vcf.ann_defined) {
+    if (!rec.has_ann) throw Fatal("called `Option::unwrap()` on a `None` value (INFO/ANN declared in the header but absent)");
+    ann = rec.ann_first;
+  }
+  std::string pc;
+  for (auto& f : mphio::split(ann, '|'))
+    if (f.find("p.") != std::string::npos) { pc = f; break; }
+  std::vector<HostVariant> out;
+  if (rec.pos < 0 || rec.pos > 0xFFFFFFF0ll) throw Unsupported("variant position beyond 32 bits");
+  for (const std::string& a : rec.alts) {
+    HostVariant v;
+    v.pos = uint32_t(rec.pos);
+    v.germline = germline;
+    v.prot_change = pc;
+    if (a.size() == 1 && rec.ref.size() > 1) {
+      v.kind = MPH_DEL;
+      v.len = uint32_t(rec.ref.size() - 1);
+      out.push_back(v);
+    } else if (a.size() > 1 && rec.ref.size() == 1) {
+      if (a[0] == '<') {
+        if (a == "<DEL>") {
+          std::string where = " contig " + std::to_string(rec.rid) + " pos " + std::to_string(rec.pos);
+          if (!vcf.svlen_defined || !rec.has_svlen) warn_or_error("Found no 'SVLEN' info tag for <DEL> alternative allele at" + where);
+          else if (rec.svlen.size() > 1) warn_or_error("microphaser does not handle multiallelic records. Please normalize, e.g. with `bcftools norm -m-`.");
+          else if (rec.svlen[0] == INT64_MIN) warn_or_error("Found no 'SVLEN' info tag for <DEL> alternative allele on" + where);
+          else {
+            const int64_t l = rec.svlen[0] < 0 ? -rec.svlen[0] : rec.svlen[0];
+            if (l > 0x7FFFFFFF) throw Unsupported("deletion longer than 2^31");
+            v.kind = MPH_DEL;
+            v.len = uint32_t(l);
+            out.push_back(v);
+          }
+        } else {
+          warn_or_error("Alternative allele type '" + a + "' not yet supported.");
+        }
+      } else {
+        v.kind = MPH_INS;
+        v.ins = a;
+        v.len = uint32_t(a.size() - 1);
+        out.push_back(v);
+      }
+    } else if (a.size() == 1 && rec.ref.size() == 1) {
+      v.kind = MPH_SNV;
+      v.alt = uint8_t(a[0]);
+      out.push_back(v);
+    } else {
+      fprintf(stderr, "Unsupported variant %s -> %s\n", rec.ref.c_str(), a.c_str());
+    }
+  }
+  return out;
+}
+
+struct ParsedGene {
+  HostGene gene;
+  std::string biotype;
+};
+
+// GTF streaming rules of `phase` (:1982-2125): gene / transcript / CDS / start_codon / three_prime_utr
+inline std::vector<ParsedGene> read_gtf(std::istream& in) {
+  std::vector<ParsedGene> genes;
+  bool start_codon_found = false, three_prime_found = false;
+  std::string last_chrom = "not_yet_set";
+  uint64_t last_start = 0;
+  std::string line;
+  mphio::GtfRecord r;
+  auto need = [](const mphio::GtfRecord& rec, const char* k, const char* msg) -> const std::string& {
+    const std::string* v = rec.get(k);
+    if (!v) throw Fatal(msg);
+    return *v;
+  };
+  auto frame_of = [](const std::string& f) -> uint32_t {
+    if (f == ".") return 0;
+    if (f.empty()) throw Fatal("ParseIntError (GTF frame)");
+    uint32_t v = 0;
+    for (char c : f) {
+      if (c < '0' || c > '9') throw Fatal("ParseIntError (GTF frame)");
+      v = v * 10 + uint32_t(c - '0');
+    }
+    return v;
+  };
+  auto cur_tx = [&](const char* m1, const char* m2) -> HostTranscript& {
+    if (genes.empty()) throw Fatal(m1);
+    if (genes.back().gene.transcripts.empty()) throw Fatal(m2);
+    return genes.back().gene.transcripts.back();
+  };
+  while (std::getline(in, line)) {
+    if (!line.empty() && line.back() == '\r') line.pop_back();
+    if (!mphio::parse_gtf_line(line, r)) continue;
+    if (r.end > 0xFFFFFF00ull) throw Unsupported("coordinate beyond 32 bits");
+    if (r.feature == "gene") {
+      if (!genes.empty()) {
+        last_chrom = genes.back().gene.chrom;
+        last_start = genes.back().gene.start;
+      }
+      const std::string& gene_name = need(r, "gene_name", "missing gene_name in GTF");
+      if (last_chrom == r.seqname && !(last_start <= r.start))
+        throw Fatal("Your GTF file is not sorted correctly. Gene " + gene_name + " starts at " + std::to_string(r.start) +
+                    ", while previous gene record started at " + std::to_string(last_start) + ".");
+      ParsedGene pg;
+      pg.gene.id = need(r, "gene_id", "missing gene_id in GTF");
+      pg.gene.name = gene_name;
+      pg.gene.chrom = r.seqname;
+      pg.gene.start = uint32_t(r.start - 1);
+      pg.gene.end = uint32_t(r.end);
+      frame_of(r.frame);
+      pg.biotype = need(r, "gene_biotype", "missing gene_biotype in GTF");
+      genes.push_back(std::move(pg));
+    } else if (r.feature == "transcript") {
+      start_codon_found = false;
+      three_prime_found = false;
+      if (genes.empty()) throw Fatal("no gene record before transcript in GTF");
+      HostTranscript t;
+      t.id = need(r, "transcript_id", "missing transcript_id attribute in GTF");
+      need(r, "transcript_biotype", "missing transcript_biotype in GTF");
+      if (r.strand == '+') t.reverse = false;
+      else if (r.strand == '-') t.reverse = true;
+      else throw Fatal("missing strand information in GTF");
+      genes.back().gene.transcripts.push_back(std::move(t));
+    } else if (r.feature == "CDS") {
+      HostTranscript& t = cur_tx("no gene record before exon in GTF", "no transcript record before exon in GTF");
+      t.exons.push_back(HostExon{uint32_t(r.start - 1), uint32_t(r.end), frame_of(r.frame)});
+    } else if (r.feature == "start_codon") {
+      if (start_codon_found) continue;
+      start_codon_found = true;
+      HostTranscript& t = cur_tx("no gene record before start_codon in GTF", "no transcript record before start codon in GTF");
+      if (t.exons.empty()) throw Fatal("no exon record before start codon in GTF");
+      if (r.strand == '+') t.exons.back().start = uint32_t(r.start - 1);
+      else t.exons.back().end = uint32_t(r.end);
+    } else if (r.feature == "three_prime_utr") {
+      HostTranscript& t = cur_tx("no gene record before exon in GTF", "no transcript record before exon in GTF");
+      if (three_prime_found) {
+        t.exons.push_back(HostExon{uint32_t(r.start - 1), uint32_t(r.end), frame_of(r.frame)});
+      } else {
+        three_prime_found = true;
+        if (t.exons.empty()) throw Fatal("no exon record before start codon in GTF");
+        if (r.strand == '+') t.exons.back().end = uint32_t(r.end);
+        else t.exons.back().start = uint32_t(r.start - 1);
+      }
+    }
+  }
+  return genes;
+}
+
+struct IngestOptions {
+  uint32_t window_len = 27;
+  bool warn_only = false;
+  uint32_t min_mapq = 5;  // somatic: rec.mapq() < 5 is skipped (:910); normal mode has no filter
+};
+
+// Builds the batch for every protein-coding gene of the GTF, in GTF order.
+inline void ingest(std::istream& gtf, mphio::BamFile& bam, mphio::VcfFile& vcf, mphio::FastaIndexed& fasta, const IngestOptions& opt,
+                   Packer& packer) {
+  std::vector<ParsedGene> genes = read_gtf(gtf);
+  ReadBuffer reads(bam);
+  VariantBuffer variants(vcf);
+  for (auto& pg : genes) {
+    if (pg.biotype != "protein_coding") continue;  // :1964
+    const HostGene& g = pg.gene;
+    std::vector<uint8_t> refseq;
+    fasta.fetch(g.chrom, g.start, uint64_t(g.end) + 100, refseq);  // end_overflow (:895-901)
+    const auto& rb = reads.fetch(g.chrom, g.start, g.end);
+    std::vector<HostRead> hr;
+    hr.reserve(rb.size());
+    uint32_t max_read_len = 0;
+    for (auto& rec : rb) {
+      if (rec->mapq < opt.min_mapq) continue;
+      if (rec->l_seq > max_read_len) max_read_len = rec->l_seq;
+      HostRead h;
+      h.start = uint32_t(rec->pos);
+      h.end = uint32_t(rec->end_pos());
+      h.l_seq = rec->l_seq;
+      h.seq4 = rec->seq4.data();
+      h.qual = rec->qual.data();
+      h.cigar = rec->cigar.data();
+      h.n_cigar = uint32_t(rec->cigar.size());
+      h.qname_hash = fnv1a(rec->qname);
+      hr.push_back(h);
+    }
+    // variant_tree.insert(rec.pos(), Variant::new(rec)): a later record at the same position replaces the earlier (:937)
+    std::map<uint32_t, std::vector<HostVariant>> tree;
+    for (auto& rec : variants.fetch(g.chrom, g.start, g.end)) tree[uint32_t(rec.pos)] = alleles_of(vcf, rec, opt.warn_only);
+    std::vector<std::vector<HostVariant>> sites;
+    for (auto& kv : tree)
+      if (!kv.second.empty()) sites.push_back(std::move(kv.second));
+    packer.add_gene(g, hr, max_read_len, sites, std::move(refseq));
+  }
+}
+
+}  // namespace mph

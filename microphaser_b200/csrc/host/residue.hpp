@@ -1,0 +1,657 @@
+// residue.hpp — the serial part of the reference's window loop that stays on the host.
+//
+// The device returns, per *interesting* window (one that contains variants, a stop codon, or sits
+// at an exon boundary), the observation count, the haplotype histogram and the assembled
+// sequences. What is left is inherently sequential per transcript and touches only those few
+// windows: the frameshift_frequencies map threaded through print_haplotypes
+// (reference src/microphasing.rs:370,496-500,604-631,703-718), the ORF termination tests
+// (:1465-1488), record construction (:720-837), the emission predicate (:839-875) and the
+// splice-junction merge (:1497-1908, src/common.rs:376-568).
+#pragma once
+#include <cmath>
+#include <limits>
+#include <map>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../io/fmt_util.hpp"
+#include "batch.hpp"
+
+namespace mph {
+
+// what comes back from the device for one batch
+struct PhaseRaw {
+  std::vector<uint32_t> iw;       // interesting window indices, ascending
+  std::vector<MphWinOut> iw_out;  // per interesting window
+  std::vector<MphHap> iw_hap0;    // per interesting window: assembly of haplotype 0
+  std::vector<MphHist> hist;      // extra histogram keys (whole arena)
+  std::vector<MphHap> hapx;       // per extra key
+  std::vector<uint8_t> seq;       // sequence arena: slots of 2 * seq_cap bytes
+  uint32_t err = 0;
+  uint64_t sum_depth = 0;         // over every enumerated window
+};
+
+// src/common.rs:350-373
+struct InfoRecord {
+  std::string id;
+  uint32_t tx = 0;
+  uint64_t offset = 0, frame = 0;
+  double freq = 0;
+  uint32_t depth = 0, nvar = 0, nsomatic = 0, nvariant_sites = 0, nsomvariant_sites = 0;
+  std::string variant_sites, somatic_positions, somatic_aa_change, germline_positions, germline_aa_change;
+  std::string normal_sequence, mutant_sequence;
+};
+
+struct OutRecord {
+  InfoRecord info;       // the TSV row
+  std::string mt;        // mutant FASTA sequence (stdout), valid if has_mt
+  std::string wt;        // normal FASTA sequence (--normal-output), valid if has_wt
+  bool has_mt = false, has_wt = false;
+};
+
+struct ResidueStats {
+  uint64_t windows = 0;       // main-ORF print_haplotypes calls the reference would make
+  uint64_t read_windows = 0;  // sum of depth over them
+};
+
+namespace detail {
+
+inline std::vector<std::string> split_bar(const std::string& s) {
+  std::vector<std::string> out;
+  size_t b = 0;
+  for (;;) {
+    size_t e = s.find('|', b);
+    if (e == std::string::npos) { out.emplace_back(s.substr(b)); break; }
+    out.emplace_back(s.substr(b, e - b));
+    b = e + 1;
+  }
+  return out;
+}
+inline std::string join_bar(const std::vector<std::string>& v) {
+  std::string s;
+  for (size_t i = 0; i < v.size(); ++i) {
+    if (i) s.push_back('|');
+    s += v[i];
+  }
+  return s;
+}
+inline uint64_t parse_u64(const std::string& p) {
+  if (p.empty()) throw Fatal("ParseIntError");
+  uint64_t v = 0;
+  for (char c : p) {
+    if (c < '0' || c > '9') throw Fatal("ParseIntError");
+    v = v * 10 + uint64_t(c - '0');
+  }
+  return v;
+}
+inline const std::string& at(const std::vector<std::string>& v, size_t i) {
+  if (i >= v.size()) throw Fatal("index out of bounds");
+  return v[i];
+}
+
+// IDRecord::update (common.rs:376-526)
+inline InfoRecord merge_records(const InfoRecord& self, const InfoRecord& rec, bool forward, const std::string& tx_id, uint64_t offset,
+                                uint64_t frame, double freq, const std::string& wt_seq, const std::string& mt_seq, uint64_t wlen) {
+  InfoRecord o;
+  o.id = mphfmt::record_id(reinterpret_cast<const uint8_t*>(mt_seq.data()), mt_seq.size(), tx_id, offset, forward ? 'F' : 'R');
+  auto sp = split_bar(self.somatic_positions), saa = split_bar(self.somatic_aa_change), osaa = split_bar(rec.somatic_aa_change);
+  auto gp = split_bar(self.germline_positions), gaa = split_bar(self.germline_aa_change), ogaa = split_bar(rec.germline_aa_change);
+  std::vector<std::string> s_p, g_p, s_aa, g_aa;
+  uint32_t nvariants = 0, nsom = 0;
+  size_t c = 0;
+  for (auto& p : sp) {
+    if (p.empty()) break;
+    const uint64_t pv = parse_u64(p);
+    if (forward ? (self.offset + offset <= pv) : (self.offset + wlen - offset >= pv)) { s_p.push_back(p); s_aa.push_back(at(saa, c)); ++nsom; ++nvariants; }
+    ++c;
+  }
+  c = 0;
+  for (auto& p : split_bar(rec.somatic_positions)) {
+    if (p.empty()) break;
+    const uint64_t pv = parse_u64(p);
+    if (forward ? (rec.offset + offset >= pv) : (rec.offset + wlen - 3 - offset <= pv)) { s_p.push_back(p); s_aa.push_back(at(osaa, c)); ++nsom; ++nvariants; }
+    ++c;
+  }
+  c = 0;
+  for (auto& p : gp) {
+    if (p.empty()) break;
+    if (self.offset + offset <= parse_u64(p)) { g_p.push_back(p); g_aa.push_back(at(gaa, c)); ++nvariants; }
+    ++c;
+  }
+  c = 0;
+  for (auto& p : split_bar(rec.germline_positions)) {
+    if (p.empty()) break;
+    if (rec.offset >= parse_u64(p) - offset) { g_p.push_back(p); g_aa.push_back(at(ogaa, c)); ++nvariants; }
+    ++c;
+  }
+  o.tx = self.tx;
+  o.offset = forward ? self.offset + offset : rec.offset + wlen + 3 - offset;
+  o.frame = frame;
+  o.freq = freq;
+  o.depth = (rec.depth == 0 || self.depth == 0) ? 0 : (rec.depth + self.depth) / 2;
+  o.nvar = nvariants;
+  o.nsomatic = nsom;
+  o.nvariant_sites = self.nvariant_sites + rec.nvariant_sites;
+  o.nsomvariant_sites = self.nsomvariant_sites + rec.nsomvariant_sites;
+  std::string vr = self.variant_sites + "|" + rec.variant_sites;
+  if (!vr.empty() && vr.front() == '|') vr.erase(0, 1);
+  if (!vr.empty() && vr.back() == '|') vr.pop_back();
+  o.variant_sites = vr;
+  o.somatic_positions = join_bar(s_p);
+  o.somatic_aa_change = join_bar(s_aa);
+  o.germline_positions = join_bar(g_p);
+  o.germline_aa_change = join_bar(g_aa);
+  o.normal_sequence = wt_seq;
+  o.mutant_sequence = mt_seq;
+  return o;
+}
+
+// IDRecord::add_freq (common.rs:528-568)
+inline InfoRecord add_freq(const InfoRecord& r, double f) {
+  InfoRecord o = r;
+  const uint32_t new_nvar = r.nvar == 0 ? r.nvar : (f > 0.0 ? r.nvar - 1 : r.nvar);
+  o.nsomatic = new_nvar < r.nsomatic ? r.nsomatic - 1 : r.nsomatic;
+  o.nvar = new_nvar;
+  o.freq = r.freq > 0.5 ? r.freq : r.freq + f;
+  return o;
+}
+
+}  // namespace detail
+
+class Residue {
+ public:
+  Residue(const Batch& b, const PhaseRaw& raw) : b_(b), raw_(raw) {}
+
+  // Processes transcripts [tx_lo, tx_hi) and appends their records in the reference's order.
+  void run(uint32_t tx_lo, uint32_t tx_hi, std::vector<OutRecord>& out, ResidueStats& stats) {
+    for (uint32_t t = tx_lo; t < tx_hi; ++t) run_transcript(t, out, stats);
+  }
+
+ private:
+  using FrameFreqs = std::map<uint64_t, std::pair<double, bool>>;
+  struct HapSeq {  // HaplotypeSeq (:141-145): only the record is ever read
+    InfoRecord rec;
+    bool partial = false;  // sequences were not shipped (window is not at an exon boundary)
+  };
+
+  struct Key {
+    uint64_t hap, frame;
+    uint64_t count;
+    const MphHap* info;
+  };
+
+  size_t find_iw(uint32_t widx) const {
+    auto it = std::lower_bound(raw_.iw.begin(), raw_.iw.end(), widx);
+    if (it == raw_.iw.end() || *it != widx) return SIZE_MAX;
+    return size_t(it - raw_.iw.begin());
+  }
+
+  std::string arena(const MphHap& h, bool germ) const {
+    if (!(h.flags & MPH_HF_SEQ)) throw std::logic_error("internal: sequence not shipped for a haplotype that needs it");
+    if (h.flags & MPH_HF_OVERFLOW) throw Unsupported("assembled haplotype longer than the sequence slot");
+    const uint8_t* p = raw_.seq.data() + h.seq_off + (germ ? b_.seq_cap : 0);
+    return std::string(reinterpret_cast<const char*>(p), germ ? h.germ_len : h.seq_len);
+  }
+
+  // print_haplotypes (:353-879) with the matrix scan and the sequence walk replaced by device results
+  std::vector<HapSeq> print(uint32_t t, const MphSegment& sg, uint32_t k, size_t iwi, uint64_t frame_in, FrameFreqs& ff,
+                            bool is_first_exon_window, std::vector<OutRecord>& out) {
+    const TxMeta& tm = b_.txs[t];
+    const GeneMeta& gm = b_.genes[tm.gene];
+    const bool rev = tm.reverse;
+    const MphGeom g = mph_geom(sg, k);
+    const uint32_t va = mph_var_lb(b_.vars.data(), sg.var_lo, sg.var_hi, g.s);
+    const uint32_t vb = mph_var_lb(b_.vars.data(), sg.var_lo, sg.var_hi, g.e);
+    const uint32_t nv = vb - va;
+    const MphWinOut& wo = raw_.iw_out[iwi];
+    const MphHap& h0 = raw_.iw_hap0[iwi];
+    const uint64_t window_len = sg.ewl;
+    const bool is_short_exon = (sg.flags & MPH_SF_SHORT) != 0;
+    uint64_t frame = frame_in;
+    // histogram for this frame (:383-411) from the fine keys (hap, obs.frame.0, obs.frame.1 != 0)
+    std::map<std::pair<uint64_t, uint64_t>, Key> keys;
+    uint64_t frame_depth = 0;
+    auto add = [&](uint64_t hap, uint32_t fr, uint64_t count, const MphHap* info) {
+      const uint64_t f0 = fr & 0x7FFFFFFFu;
+      const bool f1nz = (fr >> 31) != 0;
+      if (frame > 0 && f0 != frame && f1nz) return;
+      frame_depth += count;
+      const uint64_t kf = frame > 0 ? frame : f0;
+      auto it = keys.find({hap, kf});
+      if (it == keys.end()) keys[{hap, kf}] = Key{hap, kf, count, info};
+      else it->second.count += count;
+    };
+    if (wo.c0 > 0) add(0, 0, wo.c0, &h0);
+    for (uint32_t x = 0; x < wo.n_extra; ++x) {
+      const MphHist& e = raw_.hist[wo.extra_off + x];
+      const MphHap* info = e.hap == 0 ? &h0 : &raw_.hapx[wo.extra_off + x];
+      add(e.hap, e.frame, e.count, info);
+    }
+    const bool has_frameshift = frame > 0;
+    if (keys.empty()) keys[{0, 0}] = Key{0, 0, 0, &h0};
+    std::vector<HapSeq> haplotypes_vec;
+    uint64_t shift_in_window = 0;
+    const bool boundary = is_boundary(sg, k);
+    for (auto& kv : keys) {
+      const Key& key = kv.second;
+      const MphHap& h = *key.info;
+      const uint64_t haplotype_frame = key.frame;
+      const bool indel = (h.flags & MPH_HF_INDEL) != 0, insertion = (h.flags & MPH_HF_INSERTION) != 0;
+      bool shift_is_set = false;
+      const double freq = key.count == 0 ? 0.0 : double(key.count) / double(frame_depth);
+      const uint32_t depth = wo.depth;
+      // replay of the frameshift side effects of the sequence walk (:482-502): the visited
+      // variants are variants[0 .. n_prof) in order, profile != 0 <=> the haplotype carries it
+      for (uint32_t c = 0; c < h.n_prof && c < 32; ++c) {
+        const MphVar& v = b_.vars[va + c];
+        const uint64_t vfs = (v.flags & MPH_VF_FS_MASK) >> MPH_VF_FS_SHIFT;
+        shift_in_window = shift_in_window > 0 ? shift_in_window : vfs;
+        if ((h.profile >> (2 * c)) & 3) {
+          if (shift_in_window > 0) {
+            shift_is_set = true;
+            ff[vfs] = {freq, !(v.flags & MPH_VF_GERMLINE)};
+            ff[0] = {1.0 - freq, false};
+          }
+        }
+      }
+      double frame_frequency = freq;
+      if (shift_is_set && frame == 0) frame = shift_in_window;
+      ff.emplace(frame, std::make_pair(0.0, false));
+      if (shift_in_window == 0) frame_frequency = freq * ff.at(frame).first;
+      if (shift_in_window == 0 && haplotype_frame > 0 && frame == 0) frame_frequency = 0.0;
+      const bool germ_eq = (h.flags & MPH_HF_GERM_EQ) != 0;
+      bool germ_cleared = false;
+      if ((indel && insertion) || (shift_in_window == 0 && (ff.at(frame).second || (has_frameshift && !germ_eq)))) germ_cleared = true;
+      const uint64_t seq_len = h.seq_len;
+      const uint64_t germ_len = germ_cleared ? 0 : h.germ_len;
+      const uint64_t this_window_len = seq_len < window_len ? seq_len : window_len;
+      const uint64_t normal_window_len = indel ? (germ_len < window_len ? germ_len : window_len) : this_window_len;
+      const bool stop_gain = (h.flags & MPH_HF_STOP) != 0;
+      const bool seqs_equal = germ_cleared ? seq_len == 0 : germ_eq;  // germline_seq == seq after clearing
+      // does anything below need the actual bytes?
+      const bool emit = (h.n_som > 0 || has_frameshift) && !is_short_exon && !seqs_equal && frame_frequency > 0.0 && (!stop_gain || has_frameshift);
+      const bool want_seq = emit || boundary || (h.flags & MPH_HF_SEQ);
+      std::string seq, germline_seq;
+      if (want_seq && (h.flags & MPH_HF_SEQ)) {
+        seq = arena(h, false);
+        if (!germ_cleared) germline_seq = arena(h, true);
+      } else if (emit || boundary) {
+        throw std::logic_error("internal: sequence not shipped for an emitted / boundary haplotype");
+      }
+      const bool have_seq = (h.flags & MPH_HF_SEQ) != 0;
+      auto slice = [](const std::string& s, uint64_t a, uint64_t e) -> std::string {
+        if (a > e || e > s.size()) throw Fatal("slice index out of range");
+        return s.substr(size_t(a), size_t(e - a));
+      };
+      std::string normal_peptide, neopeptide;
+      bool peptides_differ;  // normal_peptide != neopeptide (:707)
+      if (have_seq) {
+        if (germline_seq.empty()) normal_peptide = "";
+        else if (g.spos == 1) normal_peptide = slice(germline_seq, g.gap, germline_seq.size());
+        else if (g.spos == 0) normal_peptide = slice(germline_seq, 0, normal_window_len);
+        else normal_peptide = germline_seq;
+        if (g.spos == 1) neopeptide = slice(seq, g.gap, seq.size());
+        else if (g.spos == 0) neopeptide = insertion ? seq : slice(seq, 0, this_window_len);
+        else neopeptide = seq;
+        peptides_differ = normal_peptide != neopeptide;
+      } else {
+        // only reachable for haplotypes without indels, where the test below ignores it (`|| !indel`)
+        peptides_differ = !seqs_equal;
+      }
+      bool remove_peptide = false;
+      if (stop_gain && g.spos != 2 && (window_len == this_window_len || indel) && !is_first_exon_window &&
+          (peptides_differ || !indel || std::fabs(freq - 1.0) < std::numeric_limits<double>::epsilon())) {
+        if (indel && !have_seq) throw std::logic_error("internal: indel haplotype without shipped sequence");
+        remove_peptide = true;
+        if (frame == 0) ff[frame] = {0.0, false};
+        else ff.erase(frame);
+      }
+      // meta information (:720-769)
+      InfoRecord rec;
+      rec.tx = t;
+      if (have_seq) {
+        uint32_t n_variantsites = 0, n_som_variantsites = 0;
+        std::vector<std::string> s_pc, g_pc, s_pos, g_pos, sites;
+        for (uint32_t c = 0; c < nv; ++c) {
+          const MphVar& v = b_.vars[va + c];
+          if (c < h.n_prof && c < 32) {
+            const unsigned code = unsigned((h.profile >> (2 * c)) & 3);
+            if (code == 2) { s_pos.push_back(std::to_string(uint64_t(v.pos) + 1)); s_pc.push_back(b_.var_prot[va + c]); }
+            else if (code == 1) { g_pos.push_back(std::to_string(uint64_t(v.pos) + 1)); g_pc.push_back(b_.var_prot[va + c]); }
+          }
+          if (c == 0 || v.pos != b_.vars[va + c - 1].pos) {
+            ++n_variantsites;
+            sites.push_back(std::to_string(uint64_t(v.pos) + 1));
+            if (!(v.flags & MPH_VF_GERMLINE)) ++n_som_variantsites;
+          }
+        }
+        rec.id = mphfmt::record_id(reinterpret_cast<const uint8_t*>(seq.data()), seq.size(), tm.id, g.s, rev ? 'R' : 'F');
+        rec.offset = g.spos == 0 ? uint64_t(g.s) + 1 : uint64_t(g.s) + 1 + g.gap;
+        rec.frame = frame;
+        rec.freq = frame_frequency;
+        rec.depth = depth;
+        rec.nvar = h.n_var;
+        rec.nsomatic = h.n_som;
+        rec.nvariant_sites = n_variantsites;
+        rec.nsomvariant_sites = n_som_variantsites;
+        rec.variant_sites = detail::join_bar(sites);
+        rec.somatic_positions = detail::join_bar(s_pos);
+        rec.somatic_aa_change = detail::join_bar(s_pc);
+        rec.germline_positions = detail::join_bar(g_pos);
+        rec.germline_aa_change = detail::join_bar(g_pc);
+        rec.normal_sequence = normal_peptide;
+        rec.mutant_sequence = neopeptide;
+      }
+      if (!remove_peptide || frame == 0) {
+        HapSeq hs;
+        hs.partial = !have_seq;
+        if (have_seq) {
+          hs.rec = rec;
+          hs.rec.normal_sequence = germline_seq;
+          hs.rec.mutant_sequence = seq;
+        }
+        haplotypes_vec.push_back(std::move(hs));
+      }
+      if (emit) {
+        OutRecord o;
+        if (g.spos == 1) { o.mt = slice(seq, g.gap, seq.size()); o.has_mt = true; }
+        else if (g.spos == 0) { o.mt = slice(seq, 0, this_window_len); o.has_mt = true; }
+        if (!germline_seq.empty()) {
+          if (g.spos == 1) { o.wt = slice(germline_seq, g.gap, germline_seq.size()); o.has_wt = true; }
+          else if (g.spos == 0) { o.wt = slice(germline_seq, 0, this_window_len); o.has_wt = true; }
+        }
+        o.info = rec;
+        out.push_back(std::move(o));
+      }
+    }
+    (void)gm;
+    return haplotypes_vec;
+  }
+
+  static bool is_boundary(const MphSegment& sg, uint32_t k) {
+    if (sg.n_win == 0) return false;
+    if (k == sg.k_first) return true;
+    if (sg.flags & MPH_SF_HAS_FS) return true;
+    return k == sg.k_first + (sg.n_win - 1) * sg.k_stride;
+  }
+
+  void run_transcript(uint32_t t, std::vector<OutRecord>& out, ResidueStats& stats) {
+    const TxMeta& tm = b_.txs[t];
+    const GeneMeta& gm = b_.genes[tm.gene];
+    const bool fwd = !tm.reverse;
+    const uint64_t window_len = b_.window_len;
+    std::map<uint64_t, uint64_t> frameshifts;
+    if (fwd) frameshifts[0] = 0;
+    else frameshifts[gm.end] = 0;
+    std::vector<HapSeq> prev_hap_vec, hap_vec;
+    FrameFreqs ff;
+    ff[0] = {1.0, false};
+    uint64_t exon_rest = 0;
+    for (uint32_t si = tm.seg_lo; si < tm.seg_hi; ++si) {
+      if (frameshifts.empty()) break;
+      const MphSegment& sg = b_.segs[si];
+      const bool is_short_exon = (sg.flags & MPH_SF_SHORT) != 0;
+      const bool is_first_exon = (sg.flags & MPH_SF_FIRST_EXON) != 0;
+      const bool is_last_exon = (sg.flags & MPH_SF_LAST_EXON) != 0;
+      const bool has_fs = (sg.flags & MPH_SF_HAS_FS) != 0;
+      const uint64_t current_exon_offset = sg.ceo;
+      const uint64_t exon_window_len = sg.ewl;
+      exon_rest = 0;
+      // Iterations the serial loop has to visit: every iteration when frameshifting variants can
+      // open further reading frames, otherwise only the interesting main-ORF windows (all other
+      // iterations leave the state untouched).
+      std::vector<uint32_t> ks;
+      if (has_fs) {
+        for (uint32_t k = 0; k < sg.n_iter; ++k) ks.push_back(k);
+      } else {
+        auto lo = std::lower_bound(raw_.iw.begin(), raw_.iw.end(), sg.win_base);
+        auto hi = std::lower_bound(raw_.iw.begin(), raw_.iw.end(), sg.win_base + sg.n_win);
+        for (auto it = lo; it != hi; ++it) ks.push_back(sg.k_first + (*it - sg.win_base) * sg.k_stride);
+      }
+      uint32_t prev_vb_fs = 0, prev_va_fs = 0;
+      bool fs_init = false;
+      uint64_t live_windows_end = sg.n_win;  // windows of this segment the reference reaches
+      bool stopped = false;
+      for (uint32_t k : ks) {
+        if (frameshifts.empty()) { stopped = true; break; }
+        const MphGeom g = mph_geom(sg, k);
+        const uint64_t offset = fwd ? uint64_t(sg.off0) + k : uint64_t(sg.off0) - k;
+        const bool is_first_exon_window = k == 0;
+        const uint64_t rest = fwd ? sg.exon_end - (offset + exon_window_len) : offset - sg.exon_start;
+        const bool is_last_exon_window = rest < 3;
+        if (has_fs) {
+          // newly collected variants (:1280-1342): frameshift map bookkeeping
+          const uint32_t va = mph_var_lb(b_.vars.data(), sg.var_lo, sg.var_hi, g.s);
+          const uint32_t vb = mph_var_lb(b_.vars.data(), sg.var_lo, sg.var_hi, g.e);
+          uint32_t na, nb;  // index range of the new variants, in collection order
+          if (!fs_init || k == 0) { na = va; nb = vb; }
+          else if (fwd) { na = std::max(prev_vb_fs, va); nb = vb; }
+          else { na = va; nb = std::min(prev_va_fs, vb); }
+          fs_init = true;
+          prev_va_fs = va; prev_vb_fs = vb;
+          auto handle = [&](const MphVar& v) {
+            const uint64_t s = (v.flags & MPH_VF_FS_MASK) >> MPH_VF_FS_SHIFT;
+            if ((s % 3) > 0) {
+              std::vector<uint64_t> previous;
+              for (auto& kv : frameshifts) previous.push_back(kv.second + s);
+              const uint64_t end_pos = v.kind == MPH_DEL ? uint64_t(v.pos) + v.len - 1 : v.pos;
+              for (uint64_t s_ : previous) frameshifts[fwd ? end_pos : uint64_t(v.pos)] = s_ % 3;
+            }
+          };
+          if (fwd) for (uint32_t j = na; j < nb; ++j) handle(b_.vars[j]);
+          else for (uint32_t j = nb; j > na; --j) handle(b_.vars[j - 1]);
+        }
+        uint64_t stopped_frameshift = 3;
+        std::vector<std::pair<uint64_t, uint64_t>> active;
+        if (fwd) { for (auto it = frameshifts.begin(); it != frameshifts.end() && it->first < offset; ++it) active.push_back(*it); }
+        else { for (auto it = frameshifts.lower_bound(offset + exon_window_len); it != frameshifts.end(); ++it) active.push_back(*it); }
+        uint64_t frameshift_count = 0;
+        bool main_orf = false;
+        for (auto& kf : active) {
+          const uint64_t key = kf.first, frameshift = kf.second;
+          ++frameshift_count;
+          if (frameshift == 0) main_orf = true;
+          const uint64_t coding_shift = fwd ? offset - sg.exon_start : sg.exon_end - offset;
+          const bool has_frameshift = frameshift > 0;
+          if (coding_shift % 3 == (frameshift + current_exon_offset) % 3 || is_short_exon) {
+            if (!has_frameshift) {
+              exon_rest = rest;
+              if (exon_window_len < 3) exon_rest = exon_window_len;
+            }
+            if (k < sg.k_first || (k - sg.k_first) % sg.k_stride != 0) throw std::logic_error("internal: window was not enumerated");
+            const uint32_t widx = sg.win_base + (k - sg.k_first) / sg.k_stride;
+            const size_t iwi = find_iw(widx);
+            if (iwi == SIZE_MAX) throw std::logic_error("internal: window summary missing");
+            if (has_fs && frameshift == 0) {
+              stats.windows += 1;
+              stats.read_windows += raw_.iw_out[iwi].depth;
+            }
+            auto res = print(t, sg, k, iwi, frameshift, ff, is_first_exon_window, out);
+            if (res.empty() || !ff.count(frameshift)) stopped_frameshift = key;
+            if (exon_rest < 3 && (!is_short_exon || is_first_exon) && !has_frameshift) prev_hap_vec = std::move(res);
+            else hap_vec = std::move(res);
+            if (frameshift != 0 && ff.count(frameshift) && ff.at(frameshift).first == 0.0) stopped_frameshift = key;
+          }
+        }
+        if (frameshift_count == 0 || !main_orf || !ff.count(0)) {
+          frameshifts.clear();
+          live_windows_end = live_index(sg, k);
+          stopped = true;
+          break;
+        }
+        if (stopped_frameshift != 3) {
+          auto it = frameshifts.find(stopped_frameshift);
+          if (it == frameshifts.end()) throw Fatal("called `Option::unwrap()` on a `None` value");
+          if (it->second != 0) frameshifts.erase(it);
+        }
+        if (frameshifts.empty()) { live_windows_end = live_index(sg, k); stopped = true; break; }
+        if (ff.at(0).first == 0.0 && frameshifts.size() == 1) {
+          frameshifts.clear();
+          live_windows_end = live_index(sg, k);
+          stopped = true;
+          break;
+        }
+        const bool at_splice_side = fwd ? offset - current_exon_offset == sg.exon_start
+                                        : offset + exon_window_len + current_exon_offset == sg.exon_end;
+        if (at_splice_side && !is_first_exon)
+          splice_merge(t, sg, offset, is_short_exon, is_last_exon, is_last_exon_window, exon_rest, frameshifts, ff, hap_vec, prev_hap_vec, out);
+        (void)window_len;
+      }
+      // statistics: main-ORF windows the reference evaluates in this segment (depth is summed on the
+      // device over exactly these windows)
+      if (!has_fs) {
+        stats.windows += live_windows_end;
+        seg_live_.push_back({si, uint32_t(live_windows_end)});
+      }
+      if (stopped) break;
+    }
+  }
+
+  // number of enumerated windows of `sg` up to and including iteration k
+  static uint64_t live_index(const MphSegment& sg, uint32_t k) {
+    if (k < sg.k_first) return 0;
+    return uint64_t((k - sg.k_first) / sg.k_stride) + 1;
+  }
+
+  // :1505-1908
+  void splice_merge(uint32_t t, const MphSegment& sg, uint64_t offset, bool is_short_exon, bool is_last_exon, bool is_last_exon_window,
+                    uint64_t exon_rest, const std::map<uint64_t, uint64_t>& frameshifts, FrameFreqs& ff, std::vector<HapSeq>& hap_vec,
+                    std::vector<HapSeq>& prev_hap_vec, std::vector<OutRecord>& out) {
+    const TxMeta& tm = b_.txs[t];
+    const bool fwd = !tm.reverse;
+    const uint64_t window_len = b_.window_len;
+    const uint64_t exon_window_len = sg.ewl;
+    const std::vector<HapSeq>& first_hap_vec = fwd ? hap_vec : prev_hap_vec;
+    const std::vector<HapSeq>& sec_hap_vec = fwd ? prev_hap_vec : hap_vec;
+    struct OutVal { std::string mt; InfoRecord rec; std::string wt; };
+    std::map<std::tuple<uint64_t, std::string, std::string>, OutVal> output_map;
+    std::vector<HapSeq> new_hap_vec;
+    const double eps = std::numeric_limits<double>::epsilon();
+    for (const HapSeq& hapseq : first_hap_vec) {
+      if (hapseq.partial) throw Unsupported("transcript " + tm.id + ": splice merge needs a window that is not at an exon boundary");
+      const InfoRecord& record = hapseq.rec;
+      const std::string& wt_sequence = record.normal_sequence;
+      const std::string& mt_sequence = record.mutant_sequence;
+      for (const HapSeq& prev_hapseq : sec_hap_vec) {
+        if (prev_hapseq.partial) throw Unsupported("transcript " + tm.id + ": splice merge needs a window that is not at an exon boundary");
+        const InfoRecord& prev_record = prev_hapseq.rec;
+        const std::string& prev_wt_sequence = prev_record.normal_sequence;
+        const std::string& prev_mt_sequence = prev_record.mutant_sequence;
+        const std::string new_wt_sequence = prev_wt_sequence + wt_sequence;
+        std::vector<std::string> new_mt_sequences;
+        if (wt_sequence != mt_sequence) {
+          new_mt_sequences.push_back(prev_wt_sequence + mt_sequence);
+          if (prev_wt_sequence != prev_mt_sequence) {
+            new_mt_sequences.push_back(prev_mt_sequence + wt_sequence);
+            new_mt_sequences.push_back(prev_mt_sequence + mt_sequence);
+          }
+        } else {
+          new_mt_sequences.push_back(prev_mt_sequence + mt_sequence);
+        }
+        if (is_short_exon && !is_last_exon) {
+          const double out_freq = std::fabs(record.freq - prev_record.freq) < eps ? record.freq : record.freq * prev_record.freq;
+          HapSeq nh;
+          nh.rec = detail::merge_records(prev_record, record, fwd, tm.id, 0, record.frame, out_freq, new_wt_sequence, new_wt_sequence, window_len);
+          new_hap_vec.push_back(std::move(nh));
+        }
+        for (const std::string& new_mt_sequence : new_mt_sequences) {
+          if (is_short_exon && !is_last_exon) {
+            const double out_freq = std::fabs(record.freq - prev_record.freq) < eps ? record.freq : record.freq * prev_record.freq;
+            HapSeq nh;
+            nh.rec = detail::merge_records(prev_record, record, fwd, tm.id, 0, record.frame, out_freq, new_wt_sequence, new_mt_sequence, window_len);
+            new_hap_vec.push_back(std::move(nh));
+            continue;
+          }
+          std::vector<std::pair<uint64_t, uint64_t>> active;
+          if (fwd) { for (auto it = frameshifts.begin(); it != frameshifts.end() && it->first < offset; ++it) active.push_back(*it); }
+          else { for (auto it = frameshifts.lower_bound(offset + exon_window_len); it != frameshifts.end(); ++it) active.push_back(*it); }
+          for (auto& pf : active) {
+            const uint64_t pos = pf.first, frameshift = pf.second;
+            ff.emplace(frameshift, std::make_pair(0.0, false));
+            const bool shift_in_window = fwd ? pos >= prev_record.offset : pos < record.offset + exon_window_len;
+            const bool somatic_shift = ff.at(frameshift).second;
+            const double frameshift_freq = ff.at(frameshift).first;
+            const double ff0 = ff.at(0).first;
+            const double main_orf_freq = ff0 == 0.0 ? frameshift_freq : ff0;
+            const double shift_orf_freq = shift_in_window ? frameshift_freq : (ff0 == 0.0 ? frameshift_freq : ff0);
+            const double variant_freq_record = fwd ? record.freq / main_orf_freq : record.freq / shift_orf_freq;
+            const double variant_freq_prev_record = fwd ? prev_record.freq / shift_orf_freq : prev_record.freq / main_orf_freq;
+            const double freq_record = ff0 == 0.0 ? frameshift_freq : variant_freq_record * frameshift_freq;
+            const double freq_prev_record = ff0 == 0.0 ? frameshift_freq : variant_freq_prev_record * frameshift_freq;
+            const double out_freq = std::fabs(record.freq - prev_record.freq) < eps ? freq_record : freq_record * freq_prev_record;
+            const uint64_t out_shift = shift_in_window ? 0 : frameshift;
+            uint64_t splice_offset = 3 - out_shift;
+            if (!fwd && exon_rest < 3) splice_offset += exon_rest;
+            size_t end_offset = 3 + size_t(out_shift);
+            if (is_last_exon_window) end_offset = 0;
+            if (uint64_t(new_mt_sequence.size()) < 2 * window_len) {
+              if (fwd) splice_offset = 0;
+              else end_offset = 0;
+            }
+            auto sub = [](const std::string& s, uint64_t a, uint64_t e) -> std::string {
+              if (a > e || e > s.size()) throw Fatal("slice index out of range");
+              return s.substr(size_t(a), size_t(e - a));
+            };
+            while (splice_offset + window_len <= uint64_t(new_mt_sequence.size() - end_offset)) {
+              std::string out_wt_seq;
+              if (splice_offset + window_len <= uint64_t(new_wt_sequence.size())) {
+                if (fwd) out_wt_seq = sub(new_wt_sequence, splice_offset, splice_offset + window_len);
+                else out_wt_seq = sub(new_wt_sequence, new_wt_sequence.size() - end_offset - size_t(window_len), new_wt_sequence.size() - end_offset);
+              }
+              std::string out_mt_seq = fwd ? sub(new_mt_sequence, splice_offset, splice_offset + window_len)
+                                           : sub(new_mt_sequence, new_mt_sequence.size() - end_offset - size_t(window_len),
+                                                 new_mt_sequence.size() - end_offset);
+              if (out_shift > 0 && out_wt_seq == out_mt_seq && somatic_shift) out_wt_seq.clear();
+              if (out_wt_seq == out_mt_seq || (out_wt_seq.empty() && frameshift == 0)) {
+                if (fwd) splice_offset += 3;
+                else end_offset += 3;
+                continue;
+              }
+              const uint64_t out_offset = fwd ? splice_offset : uint64_t(end_offset);
+              InfoRecord out_record = fwd ? detail::merge_records(prev_record, record, true, tm.id, out_offset, frameshift, out_freq, out_wt_seq, out_mt_seq, window_len)
+                                          : detail::merge_records(record, prev_record, false, tm.id, out_offset, frameshift, out_freq, out_wt_seq, out_mt_seq, window_len);
+              auto id_tuple = std::make_tuple(out_offset, out_mt_seq, out_wt_seq);
+              auto itx = output_map.find(id_tuple);
+              const double old_freq = itx != output_map.end() ? itx->second.rec.freq : 0.0;
+              output_map[id_tuple] = OutVal{out_mt_seq, detail::add_freq(out_record, old_freq), out_wt_seq};
+              if (fwd) splice_offset += 3;
+              else end_offset += 3;
+            }
+          }
+        }
+      }
+    }
+    if (is_short_exon && !is_last_exon) {
+      prev_hap_vec = std::move(new_hap_vec);
+    } else {
+      for (auto& kv : output_map) {
+        const OutVal& v = kv.second;
+        if (v.mt != v.wt) {
+          OutRecord o;
+          if (window_len > v.mt.size()) throw Fatal("slice index out of range");
+          o.mt = v.mt.substr(0, size_t(window_len));
+          o.has_mt = true;
+          if (!v.wt.empty()) {
+            if (window_len > v.wt.size()) throw Fatal("slice index out of range");
+            o.wt = v.wt.substr(0, size_t(window_len));
+            o.has_wt = true;
+          }
+          o.info = v.rec;
+          out.push_back(std::move(o));
+        }
+      }
+      if (is_short_exon) prev_hap_vec = std::move(new_hap_vec);
+    }
+  }
+
+ public:
+  // (segment, number of windows the reference reaches) — used to sum depth over live windows only
+  std::vector<std::pair<uint32_t, uint32_t>> seg_live_;
+
+ private:
+  const Batch& b_;
+  const PhaseRaw& raw_;
+};
+
+}  // namespace mph

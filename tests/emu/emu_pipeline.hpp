@@ -1,0 +1,131 @@
+// emu_pipeline.hpp — TEST INFRASTRUCTURE ONLY. A CPU stand-in for the device side of
+// mph_phase_batch: the same per-item functions as the CUDA kernels (csrc/core/phase_core.h)
+// driven by plain loops. It exists so the closed-form window logic, the packer and the host
+// residue can be diffed against the oracle in the GPU-less build container. The product library
+// never includes this file; on a GPU box the parity tests call the CUDA path through the C ABI.
+#pragma once
+#include <map>
+
+#include "../../microphaser_b200/csrc/host/residue.hpp"
+
+namespace mphemu {
+
+using namespace mph;
+
+inline uint32_t partner_of(const Batch& b, uint32_t r) {
+  for (size_t i = 0; i < b.partner_a.size(); ++i) {
+    if (b.partner_a[i] == r) return b.partner_b[i];
+    if (b.partner_b[i] == r) return b.partner_a[i];
+  }
+  return 0xFFFFFFFFu;
+}
+
+inline PhaseRaw phase(const Batch& b) {
+  PhaseRaw raw;
+  const size_t nr = b.read_start.size();
+  // K1
+  std::vector<MphCall> calls(nr);
+  for (size_t r = 0; r < nr; ++r) {
+    MphRead rd{b.read_start[r], b.read_end[r], b.read_vlo[r], b.read_lseq[r], b.read_nv[r], b.read_ncig[r]};
+    const uint8_t* bases = rd.nv ? b.bases.data() + size_t(b.read_seq_off[r]) * 16 : nullptr;
+    const uint32_t* cig = b.cigars.data() + b.read_cig_off[r];
+    calls[r] = mph_call_read(rd, bases, cig, b.vars.data());
+    if (b.read_flags[r] & MPH_RF_OVERFLOW) raw.err |= MPH_E_VARS_PER_WINDOW;
+  }
+  // K2 + K3 + K4
+  std::vector<uint8_t> seqbuf(b.seq_cap), germbuf(b.seq_cap);
+  for (const MphChunk& ch : b.chunks) {
+    const MphSegment& sg = b.segs[ch.seg];
+    const bool rev = sg.flags & MPH_SF_REVERSE;
+    for (uint32_t i = ch.i_first; i < ch.i_first + ch.n; ++i) {
+      const uint32_t k = sg.k_first + i * sg.k_stride;
+      const uint32_t widx = sg.win_base + i;
+      const MphGeom g = mph_geom(sg, k);
+      const uint32_t va = mph_var_lb(b.vars.data(), sg.var_lo, sg.var_hi, g.s);
+      const uint32_t vb = mph_var_lb(b.vars.data(), sg.var_lo, sg.var_hi, g.e);
+      if (vb - va > 64) raw.err |= MPH_E_VARS_PER_WINDOW;
+      uint32_t rlo, rhi;
+      mph_candidate_range(sg, b.read_start.data(), g, &rlo, &rhi);
+      uint32_t depth = 0;
+      std::map<std::tuple<uint64_t, uint32_t, uint32_t>, uint32_t> hist;  // (hap, frame0, f1nz) -> count
+      for (uint32_t r = rlo; r < rhi; ++r) {
+        MphPair p;
+        const uint32_t st = b.read_start[r], en = b.read_end[r], vlo = b.read_vlo[r];
+        if (!rev) {
+          p = mph_fwd_state(sg, b.vars.data(), k, g, va, vb, st, en, vlo, calls[r].S, calls[r].B);
+        } else {
+          p.member = 0;
+          if (st <= g.s && en >= g.e) {
+            const uint64_t Bx = calls[r].B | (calls[r].S & mph_range_mask(sg.sl_va, sg.sl_vb, vlo));
+            uint32_t ke = mph_rev_entry(sg, b.vars.data(), k, st, en, vlo, Bx);
+            if (ke != 0xFFFFFFFFu && (b.read_flags[r] & MPH_RF_PARTNER)) {
+              const uint32_t q = partner_of(b, r);
+              const uint64_t Bq = calls[q].B | (calls[q].S & mph_range_mask(sg.sl_va, sg.sl_vb, b.read_vlo[q]));
+              uint32_t kq = 0xFFFFFFFFu;
+              if (b.read_start[q] <= g.s && b.read_end[q] >= g.e) kq = mph_rev_entry(sg, b.vars.data(), k, b.read_start[q], b.read_end[q], b.read_vlo[q], Bq);
+              if (kq != 0xFFFFFFFFu && (kq < ke || (kq == ke && q < r))) ke = 0xFFFFFFFFu;
+            }
+            if (ke != 0xFFFFFFFFu) p = mph_rev_state(sg, b.vars.data(), k, g, va, vb, st, en, vlo, calls[r].S, calls[r].B, ke);
+          }
+        }
+        if (!p.member) continue;
+        ++depth;
+        if (p.bad) continue;
+        hist[{p.hap, p.frame & 0x7FFFFFFFu, p.frame >> 31}] += 1;
+      }
+      raw.sum_depth += depth;
+      MphWinOut wo;
+      wo.depth = depth;
+      wo.c0 = 0;
+      wo.extra_off = uint32_t(raw.hist.size());
+      wo.n_extra = 0;
+      std::vector<MphHist> extras;
+      for (auto& kv : hist) {
+        if (std::get<0>(kv.first) == 0 && std::get<1>(kv.first) == 0 && std::get<2>(kv.first) == 0) { wo.c0 = kv.second; continue; }
+        extras.push_back(MphHist{std::get<0>(kv.first), kv.second, std::get<1>(kv.first) | (std::get<2>(kv.first) << 31)});
+      }
+      wo.n_extra = uint32_t(extras.size());
+      // K3
+      const bool boundary = i == 0 || i + 1 == sg.n_win || (sg.flags & MPH_SF_HAS_FS);
+      auto assemble = [&](uint64_t hap, MphHap* out) {
+        if (va == vb) {
+          raw.err |= mph_plain_window(sg, g, b.ref.data(), out);
+          if (boundary) {
+            out->seq_off = uint32_t(raw.seq.size());
+            raw.seq.resize(raw.seq.size() + 2 * b.seq_cap, 0);
+            const uint8_t* p = b.ref.data() + sg.ref_off + (g.s - sg.ref_pos0);
+            memcpy(&raw.seq[out->seq_off], p, g.e - g.s);
+            memcpy(&raw.seq[out->seq_off + b.seq_cap], p, g.e - g.s);
+            out->flags |= MPH_HF_SEQ;
+          }
+          return;
+        }
+        raw.err |= mph_assemble(sg, g, b.vars.data(), va, vb, b.ref.data(), b.ins_bytes.data(), hap, seqbuf.data(), germbuf.data(), b.seq_cap, out);
+        if (boundary || out->n_som > 0) {
+          out->seq_off = uint32_t(raw.seq.size());
+          raw.seq.resize(raw.seq.size() + 2 * b.seq_cap, 0);
+          memcpy(&raw.seq[out->seq_off], seqbuf.data(), std::min<uint32_t>(out->seq_len, b.seq_cap));
+          memcpy(&raw.seq[out->seq_off + b.seq_cap], germbuf.data(), std::min<uint32_t>(out->germ_len, b.seq_cap));
+          out->flags |= MPH_HF_SEQ;
+        }
+      };
+      MphHap h0;
+      assemble(0, &h0);
+      bool interesting = va != vb || (h0.flags & MPH_HF_STOP) || boundary || wo.n_extra > 0;
+      for (auto& e : extras) {
+        MphHap hx;
+        assemble(e.hap, &hx);
+        raw.hist.push_back(e);
+        raw.hapx.push_back(hx);
+      }
+      if (interesting) {
+        raw.iw.push_back(widx);
+        raw.iw_out.push_back(wo);
+        raw.iw_hap0.push_back(h0);
+      }
+    }
+  }
+  return raw;
+}
+
+}  // namespace mphemu
