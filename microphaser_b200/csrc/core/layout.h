@@ -133,7 +133,8 @@ typedef struct {
   uint8_t n_var;       // n_variants (:452)
   uint8_t n_som;       // n_somatic (:451)
   uint8_t n_prof;      // variant_profile.len() (:462)
-  uint8_t pad;
+  uint8_t brk;         // 1: the walk hit `break` at :549-552 on variants[n_prof] with its bit set
+                       //    (its frameshift side effects :482-502 happened, its profile entry did not)
   uint32_t seq_off;    // byte offset into the sequence arena: seq then germline_seq
   uint64_t profile;    // 2 bits per visited variant: 0 absent, 1 germline, 2 somatic (:583-590)
   uint64_t pad2;

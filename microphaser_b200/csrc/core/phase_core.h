@@ -255,6 +255,9 @@ MPH_HD uint32_t mph_rev_entry(const MphSegment& g, const MphVar* vars, uint32_t 
     if (k2 > kc) kc = k2;
     if (kc == 0) kc = 1;
   }
+  // in the last three iterations of the exon s(k') = exon.start < off0 - k' (:1105-1106), so the
+  // start-range condition can become true up to two iterations before the linear guess
+  kc = kc >= 2 ? kc - 2 : 0;
   for (; kc <= k; ++kc) {
     const MphGeom gc = mph_geom(g, kc);
     if (gc.s <= lim && gc.e <= end && start <= gc.s) break;
@@ -324,7 +327,7 @@ MPH_HD uint32_t mph_assemble(const MphSegment& g, const MphGeom& gk, const MphVa
                              uint32_t cap, MphHap* out) {
   const bool rev = (g.flags & MPH_SF_REVERSE) != 0;
   const uint32_t n = vb - va;
-  uint32_t err = 0, sl = 0, gl = 0, flags = 0, n_var = 0, n_som = 0, n_prof = 0;
+  uint32_t err = 0, sl = 0, gl = 0, flags = 0, n_var = 0, n_som = 0, n_prof = 0, brk = 0;
   uint64_t profile = 0;
   const uint8_t* ref = ref_arena + g.ref_off;
 #define MPH_REF(i_, dst_)                                          \
@@ -368,7 +371,7 @@ MPH_HD uint32_t mph_assemble(const MphSegment& g, const MphGeom& gk, const MphVa
           flags |= MPH_HF_INSERTION;
           i += 1;
         } else {
-          if (rev && (uint64_t)v.pos + v.len - 1 >= window_end) break;  // :549-552 (j stays stuck)
+          if (rev && (uint64_t)v.pos + v.len - 1 >= window_end) { brk = 1; break; }  // :549-552 (j stays stuck)
           MPH_REF(i, r);
           if (germline || i == window_end - 1) {
             MPH_PUSH(germ, gl, r);
@@ -415,7 +418,7 @@ MPH_HD uint32_t mph_assemble(const MphSegment& g, const MphGeom& gk, const MphVa
   out->n_var = (uint8_t)n_var;
   out->n_som = (uint8_t)n_som;
   out->n_prof = (uint8_t)(n_prof < 255 ? n_prof : 255);
-  out->pad = 0;
+  out->brk = (uint8_t)brk;
   out->seq_off = 0xFFFFFFFFu;
   out->profile = profile;
   out->pad2 = 0;
@@ -438,7 +441,7 @@ MPH_HD uint32_t mph_plain_window(const MphSegment& g, const MphGeom& gk, const u
   out->flags = flags;
   out->seq_len = (uint16_t)len;
   out->germ_len = (uint16_t)len;
-  out->n_var = 0; out->n_som = 0; out->n_prof = 0; out->pad = 0;
+  out->n_var = 0; out->n_som = 0; out->n_prof = 0; out->brk = 0;
   out->seq_off = 0xFFFFFFFFu;
   out->profile = 0;
   out->pad2 = 0;

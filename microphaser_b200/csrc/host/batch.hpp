@@ -261,6 +261,15 @@ class Packer {
           if (uint64_t(sg.off0) + ewl > ex.end) continue;
           sg.n_iter = is_short ? 1 : uint32_t(ex.end - ewl - sg.off0 + 1);
         }
+        // reference quirk: at the last iteration of a reverse-strand exon `offset == old_offset`
+        // (:1159) suppresses the deletion of the variants at exon.start + ewl, which then stay in
+        // the matrix for the rest of the transcript. Only the serial replay reproduces that.
+        if (t.reverse && !is_short && sg.n_iter >= 2) {
+          const uint32_t pstar = ex.start + uint32_t(ewl);
+          const uint32_t vi = mph_var_lb(b_.vars.data(), gm.var_lo, gm.var_hi, pstar);
+          if (vi < gm.var_hi && b_.vars[vi].pos == pstar)
+            throw Unsupported("transcript " + t.id + ": variant at exon.start + window_len on a reverse-strand exon (stale matrix column)");
+        }
         sg.K = uint32_t(max_read_len - ewl);
         if (!t.reverse && uint64_t(sg.off0 - sg.ceo) < sg.K) throw Fatal("range start is greater than range end in BTreeMap");
         sg.read_lo = gm.read_lo; sg.read_hi = gm.read_hi;

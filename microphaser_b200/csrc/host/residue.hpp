@@ -9,6 +9,8 @@
 // splice-junction merge (:1497-1908, src/common.rs:376-568).
 #pragma once
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <limits>
 #include <map>
 #include <string>
@@ -161,7 +163,13 @@ inline InfoRecord add_freq(const InfoRecord& r, double f) {
 
 class Residue {
  public:
-  Residue(const Batch& b, const PhaseRaw& raw) : b_(b), raw_(raw) {}
+  Residue(const Batch& b, const PhaseRaw& raw) : b_(b), raw_(raw) {
+    const char* tr = getenv("MPH_TRACE");
+    if (tr && *tr) trace_ = fopen(tr, "w");
+  }
+  ~Residue() {
+    if (trace_) fclose(trace_);
+  }
 
   // Processes transcripts [tx_lo, tx_hi) and appends their records in the reference's order.
   void run(uint32_t tx_lo, uint32_t tx_hi, std::vector<OutRecord>& out, ResidueStats& stats) {
@@ -230,6 +238,13 @@ class Residue {
     }
     const bool has_frameshift = frame > 0;
     if (keys.empty()) keys[{0, 0}] = Key{0, 0, 0, &h0};
+    if (trace_) {  // same line format as the oracle's MPH_ORACLE_TRACE
+      fprintf(trace_, "W\t%s\t%llu\t%llu\t%llu\t%u\t%llu\t%u", tm.id.c_str(), (unsigned long long)g.s, (unsigned long long)g.e,
+              (unsigned long long)frame_in, wo.depth, (unsigned long long)frame_depth, nv);
+      for (auto& kv : keys)
+        fprintf(trace_, "\t%llu:%llu:%llu", (unsigned long long)kv.second.hap, (unsigned long long)kv.second.frame, (unsigned long long)kv.second.count);
+      fputc('\n', trace_);
+    }
     std::vector<HapSeq> haplotypes_vec;
     uint64_t shift_in_window = 0;
     const bool boundary = is_boundary(sg, k);
@@ -243,11 +258,11 @@ class Residue {
       const uint32_t depth = wo.depth;
       // replay of the frameshift side effects of the sequence walk (:482-502): the visited
       // variants are variants[0 .. n_prof) in order, profile != 0 <=> the haplotype carries it
-      for (uint32_t c = 0; c < h.n_prof && c < 32; ++c) {
+      for (uint32_t c = 0; c < uint32_t(h.n_prof) + h.brk && c < 32; ++c) {
         const MphVar& v = b_.vars[va + c];
         const uint64_t vfs = (v.flags & MPH_VF_FS_MASK) >> MPH_VF_FS_SHIFT;
         shift_in_window = shift_in_window > 0 ? shift_in_window : vfs;
-        if ((h.profile >> (2 * c)) & 3) {
+        if (c == h.n_prof || ((h.profile >> (2 * c)) & 3)) {  // c == n_prof: the variant the walk broke on
           if (shift_in_window > 0) {
             shift_is_set = true;
             ff[vfs] = {freq, !(v.flags & MPH_VF_GERMLINE)};
@@ -652,6 +667,7 @@ class Residue {
  private:
   const Batch& b_;
   const PhaseRaw& raw_;
+  FILE* trace_ = nullptr;
 };
 
 }  // namespace mph
