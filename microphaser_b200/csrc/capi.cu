@@ -1,0 +1,649 @@
+// capi.cu — implementation of include/microphaser_gpu.h: packer, device pipeline (H2D, K1-K4, D2H),
+// host residue, writers and the file-level `somatic` driver. No CPU fallback: every phase call runs
+// the CUDA kernels of kernels/phase_kernels.cu or fails.
+#include <cuda_runtime.h>
+#include <unistd.h>
+
+#include <chrono>
+#include <cstdarg>
+#include <fstream>
+#include <iostream>
+#include <memory>
+#include <thread>
+
+#include "../../include/microphaser_gpu.h"
+#include "host/cli.hpp"
+#include "host/synth_native.hpp"
+#include "kernels/phase_kernels.cuh"
+
+using namespace mph;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+struct CudaError : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+
+#define CU(call)                                                                                          \
+  do {                                                                                                    \
+    cudaError_t e_ = (call);                                                                              \
+    if (e_ != cudaSuccess) throw CudaError(std::string(#call) + ": " + cudaGetErrorString(e_));          \
+  } while (0)
+
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  void ensure(size_t n) {
+    if (n <= cap) return;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = n + n / 8 + 64;
+    CU(cudaMalloc(&p, want * sizeof(T)));
+    cap = want;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+}  // namespace
+
+struct mph_batch {
+  Batch b;
+  std::vector<uint2> pairs;
+  bool pinned = false;
+  std::vector<std::pair<void*, size_t>> registered;
+  uint64_t h2d_bytes = 0;
+  ~mph_batch() {
+    for (auto& r : registered) cudaHostUnregister(r.first);
+  }
+};
+
+struct mph_packer {
+  std::unique_ptr<Packer> p;
+  int mode = 0;
+};
+
+struct mph_result {
+  std::vector<OutRecord> recs;
+  std::vector<std::string> tx_id, gene_id, gene_name, chrom;
+  std::vector<uint8_t> tx_reverse;
+};
+
+struct mph_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[8] = {};
+  std::string last_error;
+  const mph_batch* cur = nullptr;
+  mphk::DeviceBatch d;
+  DevBuf<uint32_t> read_start, read_end, read_vlo, read_seq_off, read_cig_off, cigars, block_counts, iw, counters, seg_live;
+  DevBuf<uint16_t> read_lseq, read_ncig;
+  DevBuf<uint8_t> read_nv, read_flags, bases, ins_bytes, ref, call_flags, seq, win_flag;
+  DevBuf<uint2> pairs;
+  DevBuf<MphVar> vars;
+  DevBuf<MphSegment> segs;
+  DevBuf<MphChunk> chunks;
+  DevBuf<uint64_t> call_S, call_B;
+  DevBuf<MphWinOut> win_out, iw_out;
+  DevBuf<MphHist> hist;
+  DevBuf<MphHap> hap0, hapx, iw_hap0;
+  DevBuf<unsigned long long> sums;
+  mph_timing timing = {};
+  bool have_h2d_time = false;
+};
+
+namespace {
+
+int fail(mph_ctx* ctx, int code, const std::string& msg) {
+  g_last_error = msg;
+  if (ctx) ctx->last_error = msg;
+  return code;
+}
+
+template <class F>
+int guarded(mph_ctx* ctx, F&& f) {
+  try {
+    f();
+    return MPH_OK;
+  } catch (const CudaError& e) {
+    return fail(ctx, MPH_ERR_CUDA, e.what());
+  } catch (const Fatal& e) {
+    return fail(ctx, MPH_ERR_PANIC, e.what());
+  } catch (const Unsupported& e) {
+    return fail(ctx, MPH_ERR_UNSUPPORTED, e.what());
+  } catch (const std::logic_error& e) {
+    return fail(ctx, MPH_ERR_INTERNAL, e.what());
+  } catch (const std::exception& e) {
+    return fail(ctx, MPH_ERR_INPUT, e.what());
+  }
+}
+
+void finish_batch(mph_batch* mb, bool pin) {
+  Batch& b = mb->b;
+  if (b.seq_cap > 256) throw Unsupported("insertion / deletion alleles too long for the device sequence slot");
+  mb->pairs.clear();
+  for (size_t i = 0; i < b.partner_a.size(); ++i) {
+    mb->pairs.push_back(make_uint2(b.partner_a[i], b.partner_b[i]));
+    mb->pairs.push_back(make_uint2(b.partner_b[i], b.partner_a[i]));
+  }
+  std::sort(mb->pairs.begin(), mb->pairs.end(), [](const uint2& a, const uint2& c) { return a.x < c.x; });
+  auto bytes = [](auto& v) { return v.size() * sizeof(v[0]); };
+  mb->h2d_bytes = bytes(b.read_start) + bytes(b.read_end) + bytes(b.read_vlo) + bytes(b.read_seq_off) + bytes(b.read_cig_off) +
+                  bytes(b.read_lseq) + bytes(b.read_ncig) + bytes(b.read_nv) + bytes(b.read_flags) + bytes(b.bases) + bytes(b.cigars) +
+                  bytes(b.vars) + bytes(b.ins_bytes) + bytes(b.segs) + bytes(b.chunks) + bytes(b.ref) + bytes(mb->pairs);
+  if (pin) {
+    auto reg = [&](auto& v) {
+      if (v.empty()) return;
+      if (cudaHostRegister(v.data(), v.size() * sizeof(v[0]), cudaHostRegisterDefault) == cudaSuccess)
+        mb->registered.emplace_back(v.data(), v.size() * sizeof(v[0]));
+      else
+        cudaGetLastError();
+    };
+    reg(b.read_start); reg(b.read_end); reg(b.read_vlo); reg(b.read_seq_off); reg(b.read_cig_off); reg(b.read_lseq); reg(b.read_ncig);
+    reg(b.read_nv); reg(b.read_flags); reg(b.bases); reg(b.cigars); reg(b.vars); reg(b.ins_bytes); reg(b.segs); reg(b.chunks); reg(b.ref);
+    reg(mb->pairs);
+    mb->pinned = true;
+  }
+}
+
+template <class T, class V>
+void h2d(mph_ctx* c, DevBuf<T>& dst, const V& src) {
+  dst.ensure(src.size() ? src.size() : 1);
+  if (!src.empty()) CU(cudaMemcpyAsync(dst.p, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+}
+
+void upload(mph_ctx* c, const mph_batch* mb) {
+  const Batch& b = mb->b;
+  CU(cudaSetDevice(c->device));
+  if (b.n_windows > 0xFFFFFF00ull || b.n_reads() > 0xFFFFFF00ull) throw Unsupported("batch too large: split it into gene ranges");
+  CU(cudaEventRecord(c->ev[0], c->stream));
+  h2d(c, c->read_start, b.read_start); h2d(c, c->read_end, b.read_end); h2d(c, c->read_vlo, b.read_vlo);
+  h2d(c, c->read_seq_off, b.read_seq_off); h2d(c, c->read_cig_off, b.read_cig_off); h2d(c, c->read_lseq, b.read_lseq);
+  h2d(c, c->read_ncig, b.read_ncig); h2d(c, c->read_nv, b.read_nv); h2d(c, c->read_flags, b.read_flags); h2d(c, c->bases, b.bases);
+  h2d(c, c->cigars, b.cigars); h2d(c, c->vars, b.vars); h2d(c, c->ins_bytes, b.ins_bytes); h2d(c, c->segs, b.segs);
+  h2d(c, c->chunks, b.chunks); h2d(c, c->ref, b.ref); h2d(c, c->pairs, mb->pairs);
+  CU(cudaEventRecord(c->ev[1], c->stream));
+  const size_t nr = b.n_reads(), nw = size_t(b.n_windows);
+  c->call_S.ensure(nr + 1); c->call_B.ensure(nr + 1); c->call_flags.ensure(nr + 1);
+  c->win_out.ensure(nw + 1); c->hap0.ensure(nw + 1); c->win_flag.ensure(nw + 1);
+  c->block_counts.ensure(nw / 1024 + 2);
+  c->iw.ensure(nw + 1); c->iw_out.ensure(nw + 1); c->iw_hap0.ensure(nw + 1);
+  c->counters.ensure(8); c->sums.ensure(2); c->seg_live.ensure(b.segs.size() + 1);
+  if (c->hist.cap == 0) { c->hist.ensure(std::max<size_t>(nw / 2, 1 << 16)); c->hapx.ensure(c->hist.cap); }
+  if (c->hapx.cap < c->hist.cap) c->hapx.ensure(c->hist.cap);
+  const size_t seq_want = (2 * b.segs.size() + nw / 8 + 4096) * 2 * b.seq_cap;
+  if (c->seq.cap < seq_want) c->seq.ensure(seq_want);
+  mphk::DeviceBatch& d = c->d;
+  d.n_reads = uint32_t(nr); d.n_vars = uint32_t(b.vars.size()); d.n_segs = uint32_t(b.segs.size()); d.n_chunks = uint32_t(b.chunks.size());
+  d.n_windows = uint32_t(nw); d.seq_cap = b.seq_cap; d.n_pairs = uint32_t(mb->pairs.size());
+  d.read_start = c->read_start.p; d.read_end = c->read_end.p; d.read_vlo = c->read_vlo.p; d.read_seq_off = c->read_seq_off.p;
+  d.read_cig_off = c->read_cig_off.p; d.read_lseq = c->read_lseq.p; d.read_ncig = c->read_ncig.p; d.read_nv = c->read_nv.p;
+  d.read_flags = c->read_flags.p; d.pairs = c->pairs.p; d.bases = c->bases.p; d.cigars = c->cigars.p; d.vars = c->vars.p;
+  d.ins_bytes = c->ins_bytes.p; d.segs = c->segs.p; d.chunks = c->chunks.p; d.ref = c->ref.p;
+  d.call_S = reinterpret_cast<uint64_t*>(c->call_S.p); d.call_B = reinterpret_cast<uint64_t*>(c->call_B.p); d.call_flags = c->call_flags.p;
+  d.win_out = c->win_out.p; d.hap0 = c->hap0.p; d.win_flag = c->win_flag.p; d.block_counts = c->block_counts.p;
+  d.iw = c->iw.p; d.iw_out = c->iw_out.p; d.iw_hap0 = c->iw_hap0.p; d.counters = c->counters.p;
+  d.sum_depth = c->sums.p; d.live_depth = c->sums.p + 1; d.seg_live = c->seg_live.p;
+  c->cur = mb;
+  c->timing.h2d_bytes = mb->h2d_bytes;
+  c->have_h2d_time = true;
+}
+
+void run_kernels(mph_ctx* c) {
+  if (!c->cur) throw std::runtime_error("no batch uploaded");
+  mphk::DeviceBatch& d = c->d;
+  d.hist = c->hist.p; d.hapx = c->hapx.p; d.hist_cap = uint32_t(std::min<size_t>(c->hist.cap, 0xFFFFFFF0u));
+  d.seq = c->seq.p; d.seq_cap_bytes = uint32_t(std::min<size_t>(c->seq.cap, 0xFFFFFF00u));
+  CU(cudaMemsetAsync(c->counters.p, 0, 8 * sizeof(uint32_t), c->stream));
+  CU(cudaMemsetAsync(c->sums.p, 0, 2 * sizeof(unsigned long long), c->stream));
+  CU(cudaEventRecord(c->ev[2], c->stream));
+  mphk::launch_allele_call(d, c->stream);
+  CU(cudaEventRecord(c->ev[3], c->stream));
+  mphk::launch_window_hist(d, c->stream);
+  CU(cudaEventRecord(c->ev[4], c->stream));
+  mphk::launch_assemble(d, c->stream);
+  CU(cudaEventRecord(c->ev[5], c->stream));
+  mphk::launch_compact(d, c->stream);
+  CU(cudaEventRecord(c->ev[6], c->stream));
+  CU(cudaGetLastError());
+}
+
+void collect(mph_ctx* c, mph_result** out) {
+  const Batch& b = c->cur->b;
+  PhaseRaw raw;
+  uint32_t ctr[8];
+  for (int attempt = 0;; ++attempt) {
+    CU(cudaMemcpyAsync(ctr, c->counters.p, sizeof ctr, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    const uint32_t err = ctr[mphk::CTR_ERR];
+    if ((err & (MPH_E_HIST_OVERFLOW | MPH_E_SEQ_OVERFLOW)) && attempt < 6) {
+      if (err & MPH_E_HIST_OVERFLOW) { c->hist.ensure(size_t(ctr[mphk::CTR_HIST]) * 2 + 1024); c->hapx.ensure(c->hist.cap); }
+      if (err & MPH_E_SEQ_OVERFLOW) c->seq.ensure(size_t(ctr[mphk::CTR_SEQ]) * 2 + 4096);
+      run_kernels(c);
+      continue;
+    }
+    break;
+  }
+  float ms;
+  if (c->have_h2d_time) { CU(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1])); c->timing.h2d_ms = ms; }
+  CU(cudaEventElapsedTime(&ms, c->ev[2], c->ev[3])); c->timing.k1_ms = ms;
+  CU(cudaEventElapsedTime(&ms, c->ev[3], c->ev[4])); c->timing.k2_ms = ms;
+  CU(cudaEventElapsedTime(&ms, c->ev[4], c->ev[5])); c->timing.k3_ms = ms;
+  CU(cudaEventElapsedTime(&ms, c->ev[5], c->ev[6])); c->timing.k4_ms = ms;
+  raw.err = ctr[mphk::CTR_ERR];
+  if (raw.err & MPH_E_REF_RANGE) throw Fatal("slice index out of range: refseq");
+  if (raw.err & MPH_E_VARS_PER_WINDOW) throw Unsupported("more than 32 variants in one window / 64 inside one read");
+  if (raw.err & MPH_E_KEYS_PER_WINDOW) throw Unsupported("more than 32 distinct haplotypes in one window");
+  if (raw.err) throw std::logic_error("device error bits " + std::to_string(raw.err));
+  const uint32_t n_iw = ctr[mphk::CTR_NIW], n_hist = ctr[mphk::CTR_HIST], n_seq = ctr[mphk::CTR_SEQ];
+  raw.iw.resize(n_iw); raw.iw_out.resize(n_iw); raw.iw_hap0.resize(n_iw); raw.hist.resize(n_hist); raw.hapx.resize(n_hist); raw.seq.resize(n_seq);
+  CU(cudaEventRecord(c->ev[0], c->stream));
+  if (n_iw) {
+    CU(cudaMemcpyAsync(raw.iw.data(), c->iw.p, n_iw * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(raw.iw_out.data(), c->iw_out.p, n_iw * sizeof(MphWinOut), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(raw.iw_hap0.data(), c->iw_hap0.p, n_iw * sizeof(MphHap), cudaMemcpyDeviceToHost, c->stream));
+  }
+  if (n_hist) {
+    CU(cudaMemcpyAsync(raw.hist.data(), c->hist.p, n_hist * sizeof(MphHist), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(raw.hapx.data(), c->hapx.p, n_hist * sizeof(MphHap), cudaMemcpyDeviceToHost, c->stream));
+  }
+  if (n_seq) CU(cudaMemcpyAsync(raw.seq.data(), c->seq.p, n_seq, cudaMemcpyDeviceToHost, c->stream));
+  unsigned long long sums[2];
+  CU(cudaMemcpyAsync(sums, c->sums.p, sizeof sums, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaEventRecord(c->ev[1], c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
+  c->timing.d2h_ms = ms;
+  c->timing.d2h_bytes = sizeof ctr + sizeof sums + size_t(n_iw) * (4 + sizeof(MphWinOut) + sizeof(MphHap)) + size_t(n_hist) * (sizeof(MphHist) + sizeof(MphHap)) + n_seq;
+  raw.sum_depth = sums[0];
+
+  // host residue: the serial part of the window loop, transcripts are independent
+  const auto t0 = std::chrono::steady_clock::now();
+  std::unique_ptr<mph_result> res(new mph_result);
+  ResidueStats st;
+  const uint32_t n_tx = uint32_t(b.txs.size());
+  unsigned n_thr = std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 32u);
+  if (n_tx < 256) n_thr = 1;
+  std::vector<std::vector<OutRecord>> parts(n_thr);
+  std::vector<ResidueStats> pstats(n_thr);
+  std::vector<std::vector<std::pair<uint32_t, uint32_t>>> plive(n_thr);
+  std::vector<std::exception_ptr> perr(n_thr);
+  auto work = [&](unsigned ti) {
+    try {
+      Residue r(b, raw);
+      const uint32_t lo = uint32_t(uint64_t(n_tx) * ti / n_thr), hi = uint32_t(uint64_t(n_tx) * (ti + 1) / n_thr);
+      r.run(lo, hi, parts[ti], pstats[ti]);
+      plive[ti] = std::move(r.seg_live_);
+    } catch (...) {
+      perr[ti] = std::current_exception();
+    }
+  };
+  if (n_thr == 1) {
+    work(0);
+  } else {
+    std::vector<std::thread> th;
+    for (unsigned ti = 0; ti < n_thr; ++ti) th.emplace_back(work, ti);
+    for (auto& t : th) t.join();
+  }
+  for (auto& e : perr)
+    if (e) std::rethrow_exception(e);
+  size_t total = 0;
+  for (auto& p : parts) total += p.size();
+  res->recs.reserve(total);
+  for (unsigned ti = 0; ti < n_thr; ++ti) {
+    for (auto& r : parts[ti]) res->recs.push_back(std::move(r));
+    st.windows += pstats[ti].windows;
+    st.read_windows += pstats[ti].read_windows;
+  }
+  c->timing.residue_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  // statistics: depth summed on the device over the windows the reference reaches
+  std::vector<uint32_t> live(b.segs.size() + 1, 0);
+  for (auto& pl : plive)
+    for (auto& sl : pl) live[sl.first] = sl.second;
+  CU(cudaMemcpyAsync(c->seg_live.p, live.data(), live.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+  mphk::launch_live_depth(c->d, c->stream);
+  CU(cudaMemcpyAsync(sums, c->sums.p, sizeof sums, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  c->timing.windows = st.windows;
+  c->timing.read_windows = st.read_windows + sums[1];
+  c->timing.windows_enumerated = b.n_windows;
+  c->timing.n_interesting = n_iw;
+  c->timing.n_records = res->recs.size();
+  c->timing.kernel_launches = uint32_t(mphk::kernel_launch_count());
+  c->timing.total_ms = c->timing.h2d_ms + c->timing.k1_ms + c->timing.k2_ms + c->timing.k3_ms + c->timing.k4_ms + c->timing.d2h_ms + c->timing.residue_ms;
+  for (auto& t : b.txs) {
+    res->tx_id.push_back(t.id);
+    res->gene_id.push_back(b.genes[t.gene].id);
+    res->gene_name.push_back(b.genes[t.gene].name);
+    res->chrom.push_back(b.genes[t.gene].chrom);
+    res->tx_reverse.push_back(t.reverse ? 1 : 0);
+  }
+  *out = res.release();
+}
+
+void write_all(int fd, const std::string& s) {
+  size_t off = 0;
+  while (off < s.size()) {
+    ssize_t n = ::write(fd, s.data() + off, s.size() - off);
+    if (n <= 0) throw std::runtime_error("write failed");
+    off += size_t(n);
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int mph_ctx_create(int device, mph_ctx** out) {
+  if (!out) return fail(nullptr, MPH_ERR_INPUT, "out is NULL");
+  *out = nullptr;
+  std::unique_ptr<mph_ctx> c(new mph_ctx);
+  int rc = guarded(nullptr, [&] {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) throw CudaError(std::string("no CUDA device: ") + cudaGetErrorString(e));
+    if (device < 0 || device >= n) throw CudaError("device index out of range");
+    c->device = device;
+    CU(cudaSetDevice(device));
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    for (auto& e2 : c->ev) CU(cudaEventCreate(&e2));
+  });
+  if (rc != MPH_OK) return rc;
+  *out = c.release();
+  return MPH_OK;
+}
+
+void mph_ctx_destroy(mph_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  c->read_start.release(); c->read_end.release(); c->read_vlo.release(); c->read_seq_off.release(); c->read_cig_off.release();
+  c->cigars.release(); c->block_counts.release(); c->iw.release(); c->counters.release(); c->seg_live.release(); c->read_lseq.release();
+  c->read_ncig.release(); c->read_nv.release(); c->read_flags.release(); c->bases.release(); c->ins_bytes.release(); c->ref.release();
+  c->call_flags.release(); c->seq.release(); c->win_flag.release(); c->pairs.release(); c->vars.release(); c->segs.release();
+  c->chunks.release(); c->call_S.release(); c->call_B.release(); c->win_out.release(); c->iw_out.release(); c->hist.release();
+  c->hap0.release(); c->hapx.release(); c->iw_hap0.release(); c->sums.release();
+  for (auto& e : c->ev)
+    if (e) cudaEventDestroy(e);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+const char* mph_last_error(const mph_ctx* ctx) { return ctx ? ctx->last_error.c_str() : g_last_error.c_str(); }
+
+int mph_packer_create(uint32_t window_len, int mode, mph_packer** out) {
+  if (!out) return fail(nullptr, MPH_ERR_INPUT, "out is NULL");
+  if (mode != 0) return fail(nullptr, MPH_ERR_UNSUPPORTED, "only mode 0 (somatic) is implemented");
+  if (window_len == 0 || window_len % 3 != 0) return fail(nullptr, MPH_ERR_UNSUPPORTED, "window length must be a positive multiple of 3");
+  *out = new mph_packer;
+  (*out)->p.reset(new Packer(window_len));
+  (*out)->mode = mode;
+  return MPH_OK;
+}
+
+void mph_packer_destroy(mph_packer* p) { delete p; }
+
+int mph_packer_add_gene(mph_packer* p, const mph_gene_in* g) {
+  if (!p || !g || !p->p) return fail(nullptr, MPH_ERR_INPUT, "null argument");
+  return guarded(nullptr, [&] {
+    HostGene hg;
+    hg.id = g->gene_id ? g->gene_id : "";
+    hg.name = g->gene_name ? g->gene_name : "";
+    hg.chrom = g->chrom ? g->chrom : "";
+    hg.start = g->gene_start;
+    hg.end = g->gene_end;
+    for (uint32_t t = 0; t < g->n_tx; ++t) {
+      HostTranscript ht;
+      ht.id = g->tx_id[t];
+      ht.reverse = g->tx_reverse[t] != 0;
+      for (uint32_t e = g->tx_exon_off[t]; e < g->tx_exon_off[t + 1]; ++e) ht.exons.push_back(HostExon{g->exon_start[e], g->exon_end[e], g->exon_frame[e]});
+      hg.transcripts.push_back(std::move(ht));
+    }
+    std::vector<HostRead> reads(g->n_reads);
+    for (uint32_t r = 0; r < g->n_reads; ++r) {
+      HostRead& h = reads[r];
+      h.start = g->read_start[r];
+      h.end = g->read_end[r];
+      h.l_seq = g->read_lseq[r];
+      h.seq4 = g->seq4 + g->read_seq_off[r];
+      h.qual = g->qual + g->read_qual_off[r];
+      h.cigar = g->cigar + g->read_cigar_off[r];
+      h.n_cigar = g->read_cigar_off[r + 1] - g->read_cigar_off[r];
+      h.qname_hash = g->read_qname_hash ? g->read_qname_hash[r] : r;
+    }
+    std::vector<std::vector<HostVariant>> sites;
+    for (uint32_t v = 0; v < g->n_vars; ++v) {
+      HostVariant hv;
+      hv.pos = g->var_pos[v];
+      hv.kind = g->var_kind[v];
+      hv.germline = g->var_germline[v] != 0;
+      hv.alt = g->var_alt[v];
+      hv.len = g->var_len[v];
+      if (hv.kind == MPH_INS) hv.ins.assign(reinterpret_cast<const char*>(g->ins_bytes + g->var_ins_off[v]), g->var_ins_off[v + 1] - g->var_ins_off[v]);
+      if (g->var_prot_change && g->var_prot_change[v]) hv.prot_change = g->var_prot_change[v];
+      if (sites.empty() || sites.back().back().pos != hv.pos) sites.emplace_back();
+      sites.back().push_back(std::move(hv));
+    }
+    std::vector<uint8_t> refseq(g->refseq, g->refseq + g->refseq_len);
+    p->p->add_gene(hg, reads, g->max_read_len, sites, std::move(refseq));
+  });
+}
+
+int mph_packer_finish(mph_packer* p, int pin, mph_batch** out) {
+  if (!p || !out || !p->p) return fail(nullptr, MPH_ERR_INPUT, "null argument");
+  std::unique_ptr<mph_batch> mb(new mph_batch);
+  int rc = guarded(nullptr, [&] {
+    mb->b = std::move(p->p->batch());
+    p->p.reset();
+    finish_batch(mb.get(), pin != 0);
+  });
+  if (rc != MPH_OK) return rc;
+  *out = mb.release();
+  return MPH_OK;
+}
+
+void mph_batch_destroy(mph_batch* b) { delete b; }
+
+int mph_batch_get_view(const mph_batch* mb, mph_batch_view* v) {
+  if (!mb || !v) return fail(nullptr, MPH_ERR_INPUT, "null argument");
+  const Batch& b = mb->b;
+  memset(v, 0, sizeof *v);
+  v->window_len = b.window_len;
+  v->n_reads = b.n_reads(); v->n_vars = b.vars.size(); v->n_segments = b.segs.size(); v->n_chunks = b.chunks.size();
+  v->n_windows = b.n_windows; v->n_transcripts = b.txs.size(); v->n_genes = b.genes.size();
+  v->read_start = b.read_start.data(); v->read_end = b.read_end.data(); v->read_vlo = b.read_vlo.data();
+  v->read_seq_off = b.read_seq_off.data(); v->read_cig_off = b.read_cig_off.data(); v->read_lseq = b.read_lseq.data();
+  v->read_ncig = b.read_ncig.data(); v->read_nv = b.read_nv.data(); v->read_flags = b.read_flags.data();
+  v->bases = b.bases.data(); v->bases_bytes = b.bases.size(); v->cigars = b.cigars.data(); v->n_cigar_ops = b.cigars.size();
+  v->vars = b.vars.data(); v->segments = b.segs.data(); v->chunks = b.chunks.data(); v->ref = b.ref.data(); v->ref_bytes = b.ref.size();
+  v->h2d_bytes = mb->h2d_bytes;
+  return MPH_OK;
+}
+
+int mph_batch_upload(mph_ctx* ctx, const mph_batch* batch) {
+  if (!ctx || !batch) return fail(ctx, MPH_ERR_INPUT, "null argument");
+  return guarded(ctx, [&] {
+    upload(ctx, batch);
+    CU(cudaStreamSynchronize(ctx->stream));
+  });
+}
+
+int mph_phase_resident(mph_ctx* ctx) {
+  if (!ctx) return fail(ctx, MPH_ERR_INPUT, "null argument");
+  return guarded(ctx, [&] {
+    CU(cudaSetDevice(ctx->device));
+    ctx->have_h2d_time = false;
+    ctx->timing.h2d_ms = 0;
+    run_kernels(ctx);
+    CU(cudaStreamSynchronize(ctx->stream));
+    float ms;
+    CU(cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3])); ctx->timing.k1_ms = ms;
+    CU(cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4])); ctx->timing.k2_ms = ms;
+    CU(cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5])); ctx->timing.k3_ms = ms;
+    CU(cudaEventElapsedTime(&ms, ctx->ev[5], ctx->ev[6])); ctx->timing.k4_ms = ms;
+  });
+}
+
+int mph_phase_collect(mph_ctx* ctx, mph_result** out) {
+  if (!ctx || !out) return fail(ctx, MPH_ERR_INPUT, "null argument");
+  *out = nullptr;
+  return guarded(ctx, [&] {
+    if (!ctx->cur) throw std::runtime_error("no resident run to collect");
+    collect(ctx, out);
+  });
+}
+
+int mph_phase_batch(mph_ctx* ctx, const mph_batch* batch, mph_result** out) {
+  if (!ctx || !batch || !out) return fail(ctx, MPH_ERR_INPUT, "null argument");
+  *out = nullptr;
+  return guarded(ctx, [&] {
+    upload(ctx, batch);
+    run_kernels(ctx);
+    collect(ctx, out);
+  });
+}
+
+int mph_ctx_timing(const mph_ctx* ctx, mph_timing* out) {
+  if (!ctx || !out) return fail(nullptr, MPH_ERR_INPUT, "null argument");
+  *out = ctx->timing;
+  return MPH_OK;
+}
+
+void mph_result_destroy(mph_result* r) { delete r; }
+uint64_t mph_result_count(const mph_result* r) { return r ? r->recs.size() : 0; }
+
+int mph_result_get(const mph_result* r, uint64_t i, mph_record* o) {
+  if (!r || !o || i >= r->recs.size()) return fail(nullptr, MPH_ERR_INPUT, "record index out of range");
+  const OutRecord& rec = r->recs[i];
+  const uint32_t t = rec.info.tx;
+  o->id = rec.info.id.c_str();
+  o->transcript = r->tx_id[t].c_str(); o->gene_id = r->gene_id[t].c_str(); o->gene_name = r->gene_name[t].c_str(); o->chrom = r->chrom[t].c_str();
+  o->offset = rec.info.offset; o->frame = rec.info.frame; o->freq = rec.info.freq;
+  o->depth = rec.info.depth; o->nvar = rec.info.nvar; o->nsomatic = rec.info.nsomatic;
+  o->nvariant_sites = rec.info.nvariant_sites; o->nsomvariant_sites = rec.info.nsomvariant_sites;
+  o->reverse = r->tx_reverse[t];
+  o->variant_sites = rec.info.variant_sites.c_str(); o->somatic_positions = rec.info.somatic_positions.c_str();
+  o->somatic_aa_change = rec.info.somatic_aa_change.c_str(); o->germline_positions = rec.info.germline_positions.c_str();
+  o->germline_aa_change = rec.info.germline_aa_change.c_str(); o->normal_sequence = rec.info.normal_sequence.c_str();
+  o->mutant_sequence = rec.info.mutant_sequence.c_str();
+  o->fasta_mutant = rec.has_mt ? rec.mt.c_str() : nullptr;
+  o->fasta_normal = rec.has_wt ? rec.wt.c_str() : nullptr;
+  return MPH_OK;
+}
+
+int mph_result_write(const mph_result* r, int fd_fasta, int fd_tsv, int fd_normal, int* header_written) {
+  if (!r) return fail(nullptr, MPH_ERR_INPUT, "null argument");
+  return guarded(nullptr, [&] {
+    static const char* header =
+        "id\ttranscript\tgene_id\tgene_name\tchrom\toffset\tframe\tfreq\tdepth\tnvar\tnsomatic\tnvariant_sites\tnsomvariant_sites\t"
+        "strand\tvariant_sites\tsomatic_positions\tsomatic_aa_change\tgermline_positions\tgermline_aa_change\tnormal_sequence\t"
+        "mutant_sequence\n";
+    std::string fa, tsv, nrm;
+    int hw = header_written ? *header_written : 0;
+    for (const OutRecord& rec : r->recs) {
+      const uint32_t t = rec.info.tx;
+      if (rec.has_mt) { fa += '>'; fa += rec.info.id; fa += '\n'; fa += rec.mt; fa += '\n'; }
+      if (rec.has_wt) { nrm += '>'; nrm += rec.info.id; nrm += '\n'; nrm += rec.wt; nrm += '\n'; }
+      if (!hw) { tsv += header; hw = 1; }
+      const std::string fields[21] = {rec.info.id, r->tx_id[t], r->gene_id[t], r->gene_name[t], r->chrom[t], std::to_string(rec.info.offset),
+                                      std::to_string(rec.info.frame), mphfmt::format_f64(rec.info.freq), std::to_string(rec.info.depth),
+                                      std::to_string(rec.info.nvar), std::to_string(rec.info.nsomatic), std::to_string(rec.info.nvariant_sites),
+                                      std::to_string(rec.info.nsomvariant_sites), r->tx_reverse[t] ? "Reverse" : "Forward",
+                                      rec.info.variant_sites, rec.info.somatic_positions, rec.info.somatic_aa_change,
+                                      rec.info.germline_positions, rec.info.germline_aa_change, rec.info.normal_sequence, rec.info.mutant_sequence};
+      for (int i = 0; i < 21; ++i) {
+        if (i) tsv.push_back('\t');
+        mphfmt::csv_field(fields[i], '\t', tsv);
+      }
+      tsv.push_back('\n');
+    }
+    if (fd_fasta >= 0) write_all(fd_fasta, fa);
+    if (fd_tsv >= 0) write_all(fd_tsv, tsv);
+    if (fd_normal >= 0) write_all(fd_normal, nrm);
+    if (header_written) *header_written = hw;
+  });
+}
+
+int mph_run_somatic(mph_ctx* ctx, const char* bam_path, const char* ref_path, const char* variants_path, const char* gtf_path,
+                    const char* fasta_out_path, const char* tsv_path, const char* normal_path, uint32_t window_len, int warn_only) {
+  if (!ctx || !bam_path || !ref_path || !variants_path || !gtf_path || !fasta_out_path || !tsv_path || !normal_path)
+    return fail(ctx, MPH_ERR_INPUT, "null argument");
+  if (window_len == 0 || window_len % 3 != 0) return fail(ctx, MPH_ERR_UNSUPPORTED, "window length must be a positive multiple of 3");
+  return guarded(ctx, [&] {
+    mphio::BamFile bam(bam_path);
+    mphio::VcfFile vcf(variants_path);
+    mphio::FastaIndexed fasta(ref_path);
+    // the reference creates its output files before it starts phasing (src/main.rs:79-85)
+    auto open_out = [](const char* p) -> int {
+      if (std::string(p) == "-") return 1;
+      FILE* f = fopen(p, "wb");
+      if (!f) throw std::runtime_error(std::string("cannot create ") + p);
+      int fd = dup(fileno(f));
+      fclose(f);
+      return fd;
+    };
+    const int fd_fa = open_out(fasta_out_path), fd_tsv = open_out(tsv_path), fd_n = open_out(normal_path);
+    auto close_all = [&] {
+      if (fd_fa > 2) close(fd_fa);
+      if (fd_tsv > 2) close(fd_tsv);
+      if (fd_n > 2) close(fd_n);
+    };
+    try {
+      IngestOptions io;
+      io.window_len = window_len;
+      io.warn_only = warn_only != 0;
+      Packer packer(window_len);
+      std::ifstream gf;
+      std::istream* gin = &std::cin;
+      if (std::string(gtf_path) != "-") {
+        gf.open(gtf_path);
+        if (!gf) throw std::runtime_error(std::string("cannot open ") + gtf_path);
+        gin = &gf;
+      }
+      ingest(*gin, bam, vcf, fasta, io, packer);
+      mph_batch mb;
+      mb.b = std::move(packer.batch());
+      finish_batch(&mb, false);
+      mph_result* res = nullptr;
+      upload(ctx, &mb);
+      run_kernels(ctx);
+      collect(ctx, &res);
+      std::unique_ptr<mph_result> holder(res);
+      ctx->cur = nullptr;
+      int hw = 0;
+      int rc = mph_result_write(res, fd_fa, fd_tsv, fd_n, &hw);
+      if (rc != MPH_OK) throw std::runtime_error(g_last_error);
+    } catch (...) {
+      close_all();
+      throw;
+    }
+    close_all();
+  });
+}
+
+int mph_synth_batch(const mph_synth_params* sp, uint32_t window_len, int pin, mph_batch** out) {
+  if (!sp || !out) return fail(nullptr, MPH_ERR_INPUT, "null argument");
+  std::unique_ptr<mph_batch> mb(new mph_batch);
+  int rc = guarded(nullptr, [&] {
+    Packer packer(window_len);
+    SynthParams p;
+    p.seed = sp->seed; p.n_transcripts = sp->n_transcripts; p.exons = sp->exons_per_transcript; p.exon_min = sp->exon_len_min;
+    p.exon_max = sp->exon_len_max; p.read_len = sp->read_len; p.coverage = sp->coverage; p.germline_per_kb = sp->germline_per_kb;
+    p.somatic_per_kb = sp->somatic_per_kb; p.lowq_frac = sp->lowq_frac; p.indel_read_frac = sp->indel_read_frac;
+    synth_into(packer, p);
+    mb->b = std::move(packer.batch());
+    finish_batch(mb.get(), pin != 0);
+  });
+  if (rc != MPH_OK) return rc;
+  *out = mb.release();
+  return MPH_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,66 @@
+// cli_main.cpp — `microphaser` command line with the reference's surface (src/main.rs:34-265,
+// src/somatic_cli.yaml): GTF on stdin, mutant FASTA on stdout. Thin host over the C ABI of
+// include/microphaser_gpu.h; the phasing itself runs on the GPU, there is no CPU fallback.
+//   microphaser somatic <tumor.bam> --ref genome.fasta --variants tumor.vcf [-w 27] [--tsv info.tsv]
+//                       [--normal-output normal.fasta] [-u] [-v]   < annotation.gtf > peptides.mt.fa
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/microphaser_gpu.h"
+
+int main(int argc, char** argv) {
+  if (argc < 2) return 0;
+  const std::string sub = argv[1];
+  if (sub != "somatic") {
+    fprintf(stderr, "error: sub-command '%s' is not part of the GPU phasing path\n", sub.c_str());
+    return 1;
+  }
+  std::map<std::string, std::string> opt;
+  std::vector<std::string> pos;
+  bool warn_only = false;
+  struct Spec { const char* lng; char shrt; bool value; };
+  const Spec specs[] = {{"ref", 'r', true}, {"variants", 'b', true}, {"window-len", 'w', true}, {"tsv", 't', true},
+                        {"normal-output", 'n', true}, {"unsupported-allele-warning-only", 'u', false}, {"verbose", 'v', false}};
+  for (int i = 2; i < argc; ++i) {
+    std::string s = argv[i];
+    const Spec* sp = nullptr;
+    std::string val;
+    bool have = false;
+    if (s.rfind("--", 0) == 0) {
+      std::string name = s.substr(2);
+      size_t eq = name.find('=');
+      if (eq != std::string::npos) { val = name.substr(eq + 1); name = name.substr(0, eq); have = true; }
+      for (auto& x : specs) if (name == x.lng) sp = &x;
+    } else if (s.size() >= 2 && s[0] == '-') {
+      for (auto& x : specs) if (s[1] == x.shrt) sp = &x;
+      if (sp && s.size() > 2) { val = s.substr(s[2] == '=' ? 3 : 2); have = true; }
+    } else { pos.push_back(s); continue; }
+    if (!sp) { fprintf(stderr, "error: Found argument '%s' which wasn't expected\n", s.c_str()); return 1; }
+    if (sp->value) {
+      if (!have) { if (i + 1 >= argc) { fprintf(stderr, "error: The argument '--%s' requires a value\n", sp->lng); return 1; } val = argv[++i]; }
+      opt[sp->lng] = val;
+    } else if (std::string(sp->lng) == "unsupported-allele-warning-only") warn_only = true;
+  }
+  if (pos.size() != 1 || !opt.count("ref") || !opt.count("variants")) {
+    fprintf(stderr, "error: The following required arguments were not provided: <tumor-sample> --ref <FILE> --variants <FILE>\n");
+    return 1;
+  }
+  const std::string tsv = opt.count("tsv") ? opt["tsv"] : "info.tsv";
+  const std::string nrm = opt.count("normal-output") ? opt["normal-output"] : "normal.fasta";
+  const uint32_t wl = opt.count("window-len") ? uint32_t(strtoul(opt["window-len"].c_str(), nullptr, 10)) : 27;
+  const char* dev = getenv("MPH_DEVICE");
+  mph_ctx* ctx = nullptr;
+  int rc = mph_ctx_create(dev ? atoi(dev) : 0, &ctx);
+  if (rc != MPH_OK) { fprintf(stderr, "microphaser: %s\n", mph_last_error(nullptr)); return 1; }
+  rc = mph_run_somatic(ctx, pos[0].c_str(), opt["ref"].c_str(), opt["variants"].c_str(), "-", "-", tsv.c_str(), nrm.c_str(), wl, warn_only);
+  int status = 0;
+  if (rc == MPH_ERR_PANIC) { fprintf(stderr, "thread 'main' panicked at '%s'\n", mph_last_error(ctx)); status = 101; }
+  else if (rc == MPH_ERR_UNSUPPORTED) { fprintf(stderr, "microphaser: input needs the serial replay path, which is not implemented: %s\n", mph_last_error(ctx)); status = 3; }
+  else if (rc != MPH_OK) { fprintf(stderr, "%s\n", mph_last_error(ctx)); status = 1; }
+  mph_ctx_destroy(ctx);
+  return status;
+}

@@ -73,7 +73,6 @@ struct GeneMeta {
   std::string id, name, chrom;
   uint32_t start, end;
   uint32_t var_lo, var_hi, read_lo, read_hi;
-  std::vector<uint8_t> refseq;  // [start, end + 100) as fetched by the reference (:895-901); host keeps it for splice merging
 };
 
 struct Batch {
@@ -327,7 +326,6 @@ class Packer {
       tm.seg_hi = uint32_t(b_.segs.size());
       b_.txs.push_back(std::move(tm));
     }
-    gm.refseq = std::move(refseq);
     b_.genes.push_back(std::move(gm));
   }
 

@@ -1,0 +1,67 @@
+// phase_kernels.cuh — device-side view of one batch and the launch entry points of the phasing
+// kernels (sm_100a). Definitions in phase_kernels.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../core/layout.h"
+
+namespace mphk {
+
+// everything the kernels read or write, all device pointers
+struct DeviceBatch {
+  // inputs
+  uint32_t n_reads = 0, n_vars = 0, n_segs = 0, n_chunks = 0, n_windows = 0, seq_cap = 64, n_pairs = 0;
+  const uint32_t* read_start = nullptr;
+  const uint32_t* read_end = nullptr;
+  const uint32_t* read_vlo = nullptr;
+  const uint32_t* read_seq_off = nullptr;
+  const uint32_t* read_cig_off = nullptr;
+  const uint16_t* read_lseq = nullptr;
+  const uint16_t* read_ncig = nullptr;
+  const uint8_t* read_nv = nullptr;
+  const uint8_t* read_flags = nullptr;
+  const uint2* pairs = nullptr;  // (read, partner) sorted by read — both directions
+  const uint8_t* bases = nullptr;
+  const uint32_t* cigars = nullptr;
+  const MphVar* vars = nullptr;
+  const uint8_t* ins_bytes = nullptr;
+  const MphSegment* segs = nullptr;
+  const MphChunk* chunks = nullptr;
+  const uint8_t* ref = nullptr;
+  // K1 output
+  uint64_t* call_S = nullptr;
+  uint64_t* call_B = nullptr;
+  uint8_t* call_flags = nullptr;  // bit0: S|B != 0 or host flag PARTNER — the read needs the full pair evaluation
+  // K2 output
+  MphWinOut* win_out = nullptr;
+  MphHist* hist = nullptr;
+  uint32_t hist_cap = 0;
+  // K3 output
+  MphHap* hap0 = nullptr;
+  MphHap* hapx = nullptr;  // parallel to hist
+  uint8_t* seq = nullptr;
+  uint32_t seq_cap_bytes = 0;
+  uint8_t* win_flag = nullptr;  // 1: interesting
+  // K4 output
+  uint32_t* block_counts = nullptr;
+  uint32_t* iw = nullptr;
+  MphWinOut* iw_out = nullptr;
+  MphHap* iw_hap0 = nullptr;
+  // counters: [0] hist_used [1] seq_used [2] n_interesting [3] err bits ; u64 sum_depth at +8
+  uint32_t* counters = nullptr;
+  unsigned long long* sum_depth = nullptr;
+  unsigned long long* live_depth = nullptr;
+  const uint32_t* seg_live = nullptr;  // per segment: number of windows the reference reaches
+};
+
+enum { CTR_HIST = 0, CTR_SEQ = 1, CTR_NIW = 2, CTR_ERR = 3 };
+
+void launch_allele_call(const DeviceBatch& d, cudaStream_t st);
+void launch_window_hist(const DeviceBatch& d, cudaStream_t st);
+void launch_assemble(const DeviceBatch& d, cudaStream_t st);
+void launch_compact(const DeviceBatch& d, cudaStream_t st);
+void launch_live_depth(const DeviceBatch& d, cudaStream_t st);
+int kernel_launch_count();  // kernels launched by one launch_* sequence K1..K4 (for bench "gpu_launches")
+
+}  // namespace mphk

@@ -74,6 +74,53 @@ def build_oracle():
     return ORACLE_BIN
 
 
+EMU_BIN = os.path.join(ROOT, "tests", "emu", "_build", "mph_emu")
+
+
+def build_emu():
+    """Compile the test-only CPU emulator CLI (product host code + emulated device side)."""
+    srcs = []
+    for d in ("tests/emu", "microphaser_b200/csrc/host", "microphaser_b200/csrc/core", "microphaser_b200/csrc/io"):
+        srcs += [os.path.join(ROOT, d, f) for f in os.listdir(os.path.join(ROOT, d)) if f.endswith((".cpp", ".hpp", ".h"))]
+    if os.path.exists(EMU_BIN) and all(os.path.getmtime(s) <= os.path.getmtime(EMU_BIN) for s in srcs):
+        return EMU_BIN
+    os.makedirs(os.path.dirname(EMU_BIN), exist_ok=True)
+    subprocess.run(["g++", "-std=c++17", "-O2", "-Wall", "-Wno-missing-field-initializers", "-o", EMU_BIN,
+                    os.path.join(ROOT, "tests", "emu", "emu_cli.cpp"), "-lz"], check=True)
+    return EMU_BIN
+
+
+def build_product():
+    from microphaser_b200 import build
+    return build.build_all()
+
+
+def run_cli(binary, case_dir, out_dir, gtf="annotation.gtf", ref=None, subcommand="somatic"):
+    """Run `<binary> somatic ...` the way the reference's tests do (tests/lib.rs:23-35); returns CompletedProcess."""
+    ref = ref or os.path.join(case_dir, "ref.fa")
+    cmd = [binary, subcommand, os.path.join(case_dir, "reads.bam"), "--ref", ref, "--variants", os.path.join(case_dir, "variants.vcf"),
+           "--tsv", os.path.join(out_dir, "out.tsv")]
+    if subcommand == "somatic":
+        cmd += ["--normal-output", os.path.join(out_dir, "out.normal.fa")]
+    with open(os.path.join(case_dir, gtf)) as gin, open(os.path.join(out_dir, "out.fa"), "wb") as fout:
+        return subprocess.run(cmd, stdin=gin, stdout=fout, stderr=subprocess.PIPE, timeout=900)
+
+
+def read_outputs(out_dir):
+    return {n: open(os.path.join(out_dir, n), "rb").read() for n in ("out.fa", "out.tsv", "out.normal.fa")}
+
+
 @pytest.fixture(scope="session")
 def oracle_bin():
     return build_oracle()
+
+
+@pytest.fixture(scope="session")
+def emu_bin():
+    return build_emu()
+
+
+@pytest.fixture(scope="session")
+def product():
+    """(library path, CLI path) of the CUDA build; compiled on demand (nvcc cross-compiles without a GPU)."""
+    return build_product()

@@ -1,0 +1,99 @@
+"""Parity of the CUDA path (through the C ABI / the CLI built on it) with the reference goldens and
+with the oracle. Bit-exact: all outputs are integer / byte work plus one IEEE-754 f64 division per
+record computed from identical integer counts."""
+import os
+import sys
+
+import pytest
+
+from conftest import GOLDEN, ROOT, materialize_reference, read_outputs, run_cli
+
+sys.path.insert(0, ROOT)
+from microphaser_b200 import synth  # noqa: E402
+from test_emu_parity import PROFILES, SOMATIC  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("case", SOMATIC)
+def test_cuda_cli_matches_reference_golden(product, case, tmp_path):
+    d = os.path.join(GOLDEN, case)
+    fa = materialize_reference(d, str(tmp_path))
+    res = run_cli(product[1], d, str(tmp_path), ref=fa)
+    assert res.returncode == 0, res.stderr.decode()
+    for name in sorted(os.listdir(os.path.join(d, "expected"))):
+        assert open(tmp_path / name, "rb").read() == open(os.path.join(d, "expected", name), "rb").read(), name
+
+
+def test_cuda_unsorted_gtf_is_fatal(product, tmp_path):
+    d = os.path.join(GOLDEN, "unsorted_gtf")
+    fa = materialize_reference(d, str(tmp_path))
+    assert run_cli(product[1], d, str(tmp_path), gtf="unsorted.gtf", ref=fa).returncode != 0
+    assert run_cli(product[1], d, str(tmp_path), gtf="sorted.gtf", ref=fa).returncode == 0
+
+
+def test_c_abi_run_somatic_matches_golden(product, tmp_path):
+    """Same call a host would make through FFI: mph_ctx_create + mph_run_somatic."""
+    import microphaser_b200 as m
+    d = os.path.join(GOLDEN, "reverse_somatic")
+    fa = materialize_reference(d, str(tmp_path))
+    ctx = m.Context(0)
+    ctx.run_somatic(os.path.join(d, "reads.bam"), fa, os.path.join(d, "variants.vcf"), os.path.join(d, "annotation.gtf"),
+                    str(tmp_path / "out.fa"), str(tmp_path / "out.tsv"), str(tmp_path / "out.normal.fa"))
+    t = ctx.timing()
+    ctx.close()
+    for name in ("out.fa", "out.tsv", "out.normal.fa"):
+        assert open(tmp_path / name, "rb").read() == open(os.path.join(d, "expected", name), "rb").read(), name
+    assert t["kernel_launches"] >= 6 and t["windows"] > 0 and t["n_records"] == 27
+
+
+@pytest.mark.parametrize("profile,seed", [(p, s) for p in PROFILES for s in (21, 22, 23, 24)])
+def test_cuda_matches_oracle_on_synthetic(product, oracle_bin, profile, seed, tmp_path):
+    kw = dict(PROFILES[profile])
+    kw.update(seed=seed * 104729 + len(profile), n_genes=4, coverage=30.0)
+    d = str(tmp_path / "in")
+    synth.generate(d, synth.Params(**kw))
+    o, p = tmp_path / "o", tmp_path / "p"
+    o.mkdir()
+    p.mkdir()
+    ro = run_cli(oracle_bin, d, str(o))
+    rp = run_cli(product[1], d, str(p))
+    if rp.returncode == 3:
+        pytest.skip("input needs the serial replay path: " + rp.stderr.decode().strip()[-120:])
+    assert (ro.returncode == 0) == (rp.returncode == 0), (ro.stderr.decode()[-300:], rp.stderr.decode()[-300:])
+    if ro.returncode == 0:
+        assert read_outputs(str(o)) == read_outputs(str(p))
+
+
+def test_cuda_matches_oracle_chr22_shape(product, oracle_bin, tmp_path):
+    """BASELINE.json config 2 geometry (8 exons, 150 bp reads, 30x, SNVs) on 40 transcripts, incl. window statistics."""
+    import json
+    import subprocess
+    kw = dict(seed=0x4D500002, n_genes=40, exons=(8, 8), exon_len=(90, 250), intron_len=(300, 2000), read_len=150, coverage=30.0,
+              germline_per_kb=1.0, somatic_per_kb=1.0, lowercase_frac=0.0)
+    d = str(tmp_path / "in")
+    synth.generate(d, synth.Params(**kw))
+    o, p = tmp_path / "o", tmp_path / "p"
+    o.mkdir()
+    p.mkdir()
+    env = dict(os.environ, MPH_ORACLE_STATS=str(tmp_path / "stats.json"))
+    with open(os.path.join(d, "annotation.gtf")) as gin, open(o / "out.fa", "wb") as fo:
+        ro = subprocess.run([oracle_bin, "somatic", os.path.join(d, "reads.bam"), "-r", os.path.join(d, "ref.fa"), "-b",
+                             os.path.join(d, "variants.vcf"), "-t", str(o / "out.tsv"), "-n", str(o / "out.normal.fa")],
+                            stdin=gin, stdout=fo, stderr=subprocess.PIPE, env=env)
+    assert ro.returncode == 0, ro.stderr.decode()
+    import microphaser_b200 as m
+    ctx = m.Context(0)
+    try:
+        ctx.run_somatic(os.path.join(d, "reads.bam"), os.path.join(d, "ref.fa"), os.path.join(d, "variants.vcf"),
+                        os.path.join(d, "annotation.gtf"), str(p / "out.fa"), str(p / "out.tsv"), str(p / "out.normal.fa"))
+    except m.MphError as e:
+        if e.code == m.MPH_ERR_UNSUPPORTED:
+            pytest.skip(str(e))
+        raise
+    t = ctx.timing()
+    ctx.close()
+    assert read_outputs(str(o)) == read_outputs(str(p))
+    st = json.load(open(tmp_path / "stats.json"))
+    assert t["windows"] == st["windows"], "main-ORF window count differs from the oracle's print_haplotypes calls"
+    assert t["read_windows"] == st["read_windows"], "sum of depth differs from the oracle"
