@@ -177,6 +177,8 @@ typedef struct {
   double coverage, germline_per_kb, somatic_per_kb, lowq_frac, indel_read_frac;
 } mph_synth_params;
 int mph_synth_batch(const mph_synth_params* params, uint32_t window_len, int pin, mph_batch** out);
+/* the same genes / reads / variants as real files in `dir`: ref.fa(.fai), annotation.gtf, variants.vcf, reads.bam */
+int mph_synth_write_files(const mph_synth_params* params, uint32_t window_len, const char* dir);
 
 #ifdef __cplusplus
 }

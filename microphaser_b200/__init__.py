@@ -55,7 +55,7 @@ class BatchView(C.Structure):
 EXPORTS = ["mph_ctx_create", "mph_ctx_destroy", "mph_last_error", "mph_packer_create", "mph_packer_destroy", "mph_packer_add_gene",
            "mph_packer_finish", "mph_batch_destroy", "mph_batch_get_view", "mph_phase_batch", "mph_batch_upload", "mph_phase_resident",
            "mph_phase_collect", "mph_ctx_timing", "mph_result_destroy", "mph_result_count", "mph_result_get", "mph_result_write",
-           "mph_run_somatic", "mph_synth_batch"]
+           "mph_run_somatic", "mph_synth_batch", "mph_synth_write_files"]
 
 _lib = None
 
@@ -90,6 +90,7 @@ def load():
     lib.mph_result_write.argtypes = [P, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
     lib.mph_run_somatic.argtypes = [P] + [C.c_char_p] * 7 + [C.c_uint32, C.c_int]
     lib.mph_synth_batch.argtypes = [C.POINTER(SynthParams), C.c_uint32, C.c_int, C.POINTER(P)]
+    lib.mph_synth_write_files.argtypes = [C.POINTER(SynthParams), C.c_uint32, C.c_char_p]
     _lib = lib
     return lib
 
@@ -97,6 +98,15 @@ def load():
 def _check(rc, ctx=None):
     if rc != MPH_OK:
         raise MphError(rc, (load().mph_last_error(ctx) or b"").decode(errors="replace"))
+
+
+def synth_write_files(outdir, n_transcripts=450, coverage=30.0, read_len=150, exons=8, exon_len=(90, 250), germline_per_kb=1.0,
+                      somatic_per_kb=1.0, lowq_frac=0.02, indel_read_frac=0.03, seed=0x4D500002, window_len=27):
+    """Write the workload of Batch.synthetic(...) with the same arguments as FASTA / GTF / VCF / BAM files."""
+    os.makedirs(outdir, exist_ok=True)
+    sp = SynthParams(seed, n_transcripts, exons, exon_len[0], exon_len[1], read_len, coverage, germline_per_kb, somatic_per_kb,
+                     lowq_frac, indel_read_frac)
+    _check(load().mph_synth_write_files(C.byref(sp), window_len, outdir.encode()))
 
 
 class Context:

@@ -13,7 +13,7 @@
 
 #include "../../include/microphaser_gpu.h"
 #include "host/cli.hpp"
-#include "host/synth_native.hpp"
+#include "host/synth_files.hpp"
 #include "kernels/phase_kernels.cuh"
 
 using namespace mph;
@@ -644,6 +644,17 @@ int mph_synth_batch(const mph_synth_params* sp, uint32_t window_len, int pin, mp
   if (rc != MPH_OK) return rc;
   *out = mb.release();
   return MPH_OK;
+}
+
+int mph_synth_write_files(const mph_synth_params* sp, uint32_t window_len, const char* dir) {
+  if (!sp || !dir) return fail(nullptr, MPH_ERR_INPUT, "null argument");
+  return guarded(nullptr, [&] {
+    SynthParams p;
+    p.seed = sp->seed; p.n_transcripts = sp->n_transcripts; p.exons = sp->exons_per_transcript; p.exon_min = sp->exon_len_min;
+    p.exon_max = sp->exon_len_max; p.read_len = sp->read_len; p.coverage = sp->coverage; p.germline_per_kb = sp->germline_per_kb;
+    p.somatic_per_kb = sp->somatic_per_kb; p.lowq_frac = sp->lowq_frac; p.indel_read_frac = sp->indel_read_frac;
+    synth_write_files(p, window_len, dir);
+  });
 }
 
 }  // extern "C"

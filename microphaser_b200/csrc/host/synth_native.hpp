@@ -52,7 +52,22 @@ struct Rng {  // splitmix64 / xoshiro256**
   }
 };
 
-inline void synth_into(Packer& packer, const SynthParams& sp) {
+// what the generator hands over per gene
+struct SynthGene {
+  HostGene gene;
+  std::vector<HostExon> cds;  // genomic order, CDS only (without stop codon + UTR)
+  uint32_t tail_len = 63;     // stop codon + 3' UTR appended to the last exon
+  std::vector<HostRead> reads;
+  std::vector<std::string> qnames;
+  std::vector<std::vector<HostVariant>> sites;
+  std::vector<uint8_t> ref;   // [gene.start, gene.end + 100)
+  uint32_t max_read_len = 0;
+};
+
+// Generates gene after gene and calls sink(SynthGene&). With all_bases every read carries real
+// bases / qualities (needed to write a BAM); otherwise only reads that overlap a variant do.
+template <class Sink>
+inline void synth_generate(const SynthParams& sp, uint32_t window_len, bool all_bases, Sink&& sink) {
   Rng rng(sp.seed);
   static const char B[4] = {'A', 'C', 'G', 'T'};
   auto comp = [](char c) { return c == 'A' ? 'T' : c == 'C' ? 'G' : c == 'G' ? 'C' : c == 'T' ? 'A' : 'N'; };
@@ -153,7 +168,7 @@ inline void synth_into(Packer& packer, const SynthParams& sp) {
         const uint32_t vp = rng.range(e.start, e.end - 1);
         // a variant exactly window_len after the start of a reverse-strand exon triggers the
         // reference's stale-column quirk, which needs the serial replay path (not built yet)
-        if (reverse && vp == e.start + packer.batch().window_len) continue;
+        if (reverse && vp == e.start + window_len) continue;
         const char r = char(ref[vp - gstart]);
         char a;
         do a = B[rng.below(4)]; while (a == r);
@@ -202,7 +217,7 @@ inline void synth_into(Packer& packer, const SynthParams& sp) {
       h.start = r.start; h.end = r.end; h.l_seq = L; h.n_cigar = r.ncig; h.cigar = rs[i].cig;
       h.qname_hash = (uint64_t(gi) << 32) | r.id;
       auto lo = std::lower_bound(vs.begin(), vs.end(), r.start, [](const V& v, uint32_t p) { return v.pos < p; });
-      if (lo == vs.end() || lo->pos >= r.end) {
+      if (!all_bases && (lo == vs.end() || lo->pos >= r.end)) {
         h.seq4 = dummy_seq.data();
         h.qual = dummy_qual.data();
         continue;
@@ -239,8 +254,26 @@ inline void synth_into(Packer& packer, const SynthParams& sp) {
     }
     for (size_t i = 0; i < rs.size(); ++i) hr[i].cigar = rs[i].cig;
     ref.resize(size_t(gend) + 100 - gstart, 'A');
-    packer.add_gene(g, hr, L, sites, std::move(ref));
+    SynthGene sgene;
+    sgene.gene = g;
+    sgene.cds = gex;
+    if (reverse) sgene.cds.front().start += 63;
+    else sgene.cds.back().end -= 63;
+    sgene.reads = std::move(hr);
+    if (all_bases) {
+      sgene.qnames.resize(rs.size());
+      for (size_t i = 0; i < rs.size(); ++i) sgene.qnames[i] = "r" + std::to_string(gi) + "_" + std::to_string(rs[i].id);
+    }
+    sgene.sites = std::move(sites);
+    sgene.ref = std::move(ref);
+    sgene.max_read_len = L;
+    sink(sgene);
   }
+}
+
+inline void synth_into(Packer& packer, const SynthParams& sp) {
+  synth_generate(sp, packer.batch().window_len, false,
+                 [&](SynthGene& sg) { packer.add_gene(sg.gene, sg.reads, sg.max_read_len, sg.sites, std::move(sg.ref)); });
 }
 
 }  // namespace mph
