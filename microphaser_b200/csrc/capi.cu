@@ -83,7 +83,7 @@ struct mph_ctx {
   std::string last_error;
   const mph_batch* cur = nullptr;
   mphk::DeviceBatch d;
-  DevBuf<uint32_t> read_start, read_end, read_vlo, read_seq_off, read_cig_off, cigars, block_counts, iw, counters, seg_live;
+  DevBuf<uint32_t> read_start, read_end, read_vlo, read_seq_off, read_cig_off, cigars, block_counts, iw, counters, seg_live, ovf_list;
   DevBuf<uint16_t> read_lseq, read_ncig;
   DevBuf<uint8_t> read_nv, read_flags, bases, ins_bytes, ref, call_flags, seq, win_flag;
   DevBuf<uint2> pairs;
@@ -174,7 +174,8 @@ void upload(mph_ctx* c, const mph_batch* mb) {
   c->call_S.ensure(nr + 1); c->call_B.ensure(nr + 1); c->call_flags.ensure(nr + 1);
   c->win_out.ensure(nw + 1); c->hap0.ensure(nw + 1); c->win_flag.ensure(nw + 1);
   c->block_counts.ensure(nw / 1024 + 2);
-  c->iw.ensure(nw + 1); c->iw_out.ensure(nw + 1); c->iw_hap0.ensure(nw + 1);
+  c->iw.ensure(nw + 1); c->iw_out.ensure(nw + 1); c->iw_hap0.ensure(nw + 1); c->ovf_list.ensure(nw + 1);
+  if (b.chunks.size() >= (1u << 27)) throw Unsupported("batch too large: split it into gene ranges");
   c->counters.ensure(8); c->sums.ensure(2); c->seg_live.ensure(b.segs.size() + 1);
   if (c->hist.cap == 0) { c->hist.ensure(std::max<size_t>(nw / 2, 1 << 16)); c->hapx.ensure(c->hist.cap); }
   if (c->hapx.cap < c->hist.cap) c->hapx.ensure(c->hist.cap);
@@ -189,6 +190,7 @@ void upload(mph_ctx* c, const mph_batch* mb) {
   d.ins_bytes = c->ins_bytes.p; d.segs = c->segs.p; d.chunks = c->chunks.p; d.ref = c->ref.p;
   d.call_S = reinterpret_cast<uint64_t*>(c->call_S.p); d.call_B = reinterpret_cast<uint64_t*>(c->call_B.p); d.call_flags = c->call_flags.p;
   d.win_out = c->win_out.p; d.hap0 = c->hap0.p; d.win_flag = c->win_flag.p; d.block_counts = c->block_counts.p;
+  d.ovf_list = c->ovf_list.p;
   d.iw = c->iw.p; d.iw_out = c->iw_out.p; d.iw_hap0 = c->iw_hap0.p; d.counters = c->counters.p;
   d.sum_depth = c->sums.p; d.live_depth = c->sums.p + 1; d.seg_live = c->seg_live.p;
   c->cur = mb;
@@ -199,6 +201,7 @@ void upload(mph_ctx* c, const mph_batch* mb) {
 void run_kernels(mph_ctx* c) {
   if (!c->cur) throw std::runtime_error("no batch uploaded");
   mphk::DeviceBatch& d = c->d;
+  { const char* fw = getenv("MPH_FORCE_WIDE"); d.force_wide = (fw && *fw == '1') ? 1u : 0u; }
   d.hist = c->hist.p; d.hapx = c->hapx.p; d.hist_cap = uint32_t(std::min<size_t>(c->hist.cap, 0xFFFFFFF0u));
   d.seq = c->seq.p; d.seq_cap_bytes = uint32_t(std::min<size_t>(c->seq.cap, 0xFFFFFF00u));
   CU(cudaMemsetAsync(c->counters.p, 0, 8 * sizeof(uint32_t), c->stream));
@@ -367,7 +370,7 @@ void mph_ctx_destroy(mph_ctx* c) {
   c->read_start.release(); c->read_end.release(); c->read_vlo.release(); c->read_seq_off.release(); c->read_cig_off.release();
   c->cigars.release(); c->block_counts.release(); c->iw.release(); c->counters.release(); c->seg_live.release(); c->read_lseq.release();
   c->read_ncig.release(); c->read_nv.release(); c->read_flags.release(); c->bases.release(); c->ins_bytes.release(); c->ref.release();
-  c->call_flags.release(); c->seq.release(); c->win_flag.release(); c->pairs.release(); c->vars.release(); c->segs.release();
+  c->ovf_list.release(); c->call_flags.release(); c->seq.release(); c->win_flag.release(); c->pairs.release(); c->vars.release(); c->segs.release();
   c->chunks.release(); c->call_S.release(); c->call_B.release(); c->win_out.release(); c->iw_out.release(); c->hist.release();
   c->hap0.release(); c->hapx.release(); c->iw_hap0.release(); c->sums.release();
   for (auto& e : c->ev)

@@ -80,142 +80,281 @@ __device__ __forceinline__ bool hist_less(const MphHist& a, const MphHist& b) {
   return (a.frame >> 31) < (b.frame >> 31);
 }
 
-__global__ void __launch_bounds__(K2_WARPS * 32) k_window_hist(const DeviceBatch d) {
+// One (read, window) pair with the read flagged by K1 (allele calls, bad bases or a duplicate qname).
+__device__ __forceinline__ MphPair eval_flagged(const DeviceBatch& d, const MphSegment& sg, bool rev, uint32_t k, const MphGeom& g, uint32_t va,
+                                                uint32_t vb, uint32_t r, uint32_t st, uint32_t en, uint32_t cf, uint32_t vlo, uint64_t S, uint64_t B) {
+  MphPair p;
+  if (!rev) return mph_fwd_state(sg, d.vars, k, g, va, vb, st, en, vlo, S, B);
+  p.member = 0; p.bad = 0; p.hap = 0; p.frame = 0;
+  if (st > g.s || en < g.e) return p;
+  const uint64_t Bx = B | (S & mph_range_mask(sg.sl_va, sg.sl_vb, vlo));
+  uint32_t ke = mph_rev_entry(sg, d.vars, k, st, en, vlo, Bx);
+  if (ke != NONE && (cf & 2u)) {
+    // `contains` (:281-294): of two reads sharing (start, qname) only the first to enter stays
+    const uint32_t q = partner_lookup(d, r);
+    if (q != NONE) {
+      const uint32_t qs = d.read_start[q], qe = d.read_end[q], qv = d.read_vlo[q];
+      if (qs <= g.s && qe >= g.e) {
+        const uint64_t Bq = d.call_B[q] | (d.call_S[q] & mph_range_mask(sg.sl_va, sg.sl_vb, qv));
+        const uint32_t kq = mph_rev_entry(sg, d.vars, k, qs, qe, qv, Bq);
+        if (kq != NONE && (kq < ke || (kq == ke && q < r))) ke = NONE;
+      }
+    }
+  }
+  if (ke != NONE) p = mph_rev_state(sg, d.vars, k, g, va, vb, st, en, vlo, S, B, ke);
+  return p;
+}
+
+// Wide variant: one warp per window, lanes over the candidate reads, keys in a 32-entry table.
+// Used only for windows whose key count overflows the per-lane table of k_window_hist.
+__device__ void window_hist_warp(const DeviceBatch& d, const MphSegment& sg, uint32_t i, MphHist* table, int lane) {
+  const bool rev = (sg.flags & MPH_SF_REVERSE) != 0;
+  const uint32_t k = sg.k_first + i * sg.k_stride;
+  const uint32_t widx = sg.win_base + i;
+  const MphGeom g = mph_geom(sg, k);
+  const uint32_t va = mph_var_lb(d.vars, sg.var_lo, sg.var_hi, g.s);
+  const uint32_t vb = mph_var_lb(d.vars, va, sg.var_hi, g.e);
+  uint32_t rlo, rhi;
+  mph_candidate_range(sg, d.read_start, g, &rlo, &rhi);
+  uint32_t depth = 0, c0 = 0, n_keys = 0;
+  for (uint32_t base = rlo; base < rhi; base += 32) {
+    const uint32_t r = base + lane;
+    bool member = false, counted = false;
+    uint64_t hap = 0;
+    uint32_t frame = 0;
+    if (r < rhi) {
+      const uint32_t st = d.read_start[r], en = d.read_end[r];
+      if (en >= g.e) {
+        const MphPair p = eval_flagged(d, sg, rev, k, g, va, vb, r, st, en, d.call_flags[r], d.read_vlo[r], d.call_S[r], d.call_B[r]);
+        member = p.member != 0;
+        counted = member && !p.bad;
+        hap = p.hap;
+        frame = p.frame;
+      }
+    }
+    depth += __popc(__ballot_sync(FULL, member));
+    const bool zero_key = counted && hap == 0 && frame == 0;
+    c0 += __popc(__ballot_sync(FULL, zero_key));
+    unsigned pending = __ballot_sync(FULL, counted && !zero_key);
+    while (pending) {
+      const int leader = __ffs(pending) - 1;
+      const uint64_t lh = __shfl_sync(FULL, hap, leader);
+      const uint32_t lf = __shfl_sync(FULL, frame, leader);
+      const unsigned same = __ballot_sync(FULL, counted && !zero_key && hap == lh && frame == lf);
+      if (lane == 0) {
+        uint32_t t = 0;
+        for (; t < n_keys; ++t)
+          if (table[t].hap == lh && table[t].frame == lf) break;
+        if (t == n_keys) {
+          if (n_keys < K2_TABLE) {
+            table[t].hap = lh;
+            table[t].frame = lf;
+            table[t].count = 0;
+            ++n_keys;
+          } else {
+            raise(d, MPH_E_KEYS_PER_WINDOW);
+            t = K2_TABLE - 1;
+          }
+        }
+        table[t].count += __popc(same);
+      }
+      pending &= ~same;
+    }
+  }
+  if (lane == 0) {
+    for (uint32_t a = 1; a < n_keys; ++a) {  // keys in the reference's BTreeMap order (:383,434)
+      const MphHist key = table[a];
+      uint32_t b = a;
+      while (b > 0 && hist_less(key, table[b - 1])) {
+        table[b] = table[b - 1];
+        --b;
+      }
+      table[b] = key;
+    }
+    MphWinOut wo;
+    wo.depth = depth;
+    wo.c0 = c0;
+    wo.n_extra = n_keys;
+    wo.extra_off = 0;
+    if (n_keys) {
+      const uint32_t off = atomicAdd(&d.counters[CTR_HIST], n_keys);
+      if (off + n_keys <= d.hist_cap) {
+        wo.extra_off = off;
+        for (uint32_t a = 0; a < n_keys; ++a) d.hist[off + a] = table[a];
+      } else {
+        raise(d, MPH_E_HIST_OVERFLOW);
+        wo.n_extra = 0;
+      }
+    }
+    d.win_out[widx] = wo;
+    atomicAdd(d.sum_depth, (unsigned long long)depth);
+  }
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(K2_WARPS * 32) k_window_hist_wide(const DeviceBatch d) {
   __shared__ MphHist table[K2_WARPS][K2_TABLE];
-  __shared__ MphSegment s_seg;
-  __shared__ unsigned long long cta_depth;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const MphChunk ch = d.chunks[blockIdx.x];
-  if (threadIdx.x < sizeof(MphSegment) / 4) reinterpret_cast<uint32_t*>(&s_seg)[threadIdx.x] = reinterpret_cast<const uint32_t*>(&d.segs[ch.seg])[threadIdx.x];
-  if (threadIdx.x == 0) cta_depth = 0;
-  __syncthreads();
-  const MphSegment& sg = s_seg;
+  const uint32_t n = d.counters[CTR_OVF];
+  for (uint32_t o = blockIdx.x * K2_WARPS + warp; o < n; o += gridDim.x * K2_WARPS) {
+    const uint32_t code = d.ovf_list[o];
+    const MphChunk ch = d.chunks[code >> 5];
+    const MphSegment sg = d.segs[ch.seg];
+    window_hist_warp(d, sg, ch.i_first + (code & 31u), table[warp], lane);
+  }
+}
+
+// Main K2: one warp per chunk, one lane per window. Consecutive windows of an exon share almost
+// all candidate reads, so the warp walks the union of their candidate ranges once: 32 reads are
+// loaded coalesced, then broadcast one by one (shuffles) and every lane tests its own window.
+constexpr int K2_LANE_KEYS = 8;
+
+__global__ void __launch_bounds__(K2_WARPS * 32) k_window_hist(const DeviceBatch d) {
+  // per-lane key tables, [key][lane] so that a warp touches 32 distinct banks
+  __shared__ uint64_t t_hap[K2_WARPS][K2_LANE_KEYS][32];
+  __shared__ uint32_t t_cnt[K2_WARPS][K2_LANE_KEYS][32];
+  __shared__ uint32_t t_frm[K2_WARPS][K2_LANE_KEYS][32];
+  __shared__ MphSegment s_seg[K2_WARPS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t chunk = blockIdx.x * K2_WARPS + warp;
+  if (chunk >= d.n_chunks) return;
+  const MphChunk ch = d.chunks[chunk];
+  if (lane < (int)(sizeof(MphSegment) / 4)) reinterpret_cast<uint32_t*>(&s_seg[warp])[lane] = reinterpret_cast<const uint32_t*>(&d.segs[ch.seg])[lane];
+  __syncwarp();
+  const MphSegment& sg = s_seg[warp];
   const bool rev = (sg.flags & MPH_SF_REVERSE) != 0;
   const bool has_fs = (sg.flags & MPH_SF_HAS_FS) != 0;
+  const bool active = (uint32_t)lane < ch.n;
+  const uint32_t i = ch.i_first + (active ? lane : 0);
+  const uint32_t k = sg.k_first + i * sg.k_stride;
+  const MphGeom g = mph_geom(sg, k);
+  const uint32_t va = mph_var_lb(d.vars, sg.var_lo, sg.var_hi, g.s);
+  const uint32_t vb = mph_var_lb(d.vars, va, sg.var_hi, g.e);
+  const uint32_t nvar = vb - va;
+  if (active && nvar > 64) raise(d, MPH_E_VARS_PER_WINDOW);
+  // union of the lanes' candidate start ranges
   const uint32_t s0 = sg.off0 - sg.ceo;
-  unsigned long long warp_depth = 0;
-  for (uint32_t wi = warp; wi < ch.n; wi += K2_WARPS) {
-    const uint32_t i = ch.i_first + wi;
-    const uint32_t k = sg.k_first + i * sg.k_stride;
-    const uint32_t widx = sg.win_base + i;
-    const MphGeom g = mph_geom(sg, k);
-    const uint32_t va = mph_var_lb(d.vars, sg.var_lo, sg.var_hi, g.s);
-    const uint32_t vb = mph_var_lb(d.vars, va, sg.var_hi, g.e);
-    if (vb - va > 64 && lane == 0) raise(d, MPH_E_VARS_PER_WINDOW);
-    uint32_t rlo, rhi;
-    mph_candidate_range(sg, d.read_start, g, &rlo, &rhi);
-    uint32_t depth = 0, c0 = 0, n_keys = 0;
-    for (uint32_t base = rlo; base < rhi; base += 32) {
-      const uint32_t r = base + lane;
-      const bool valid = r < rhi;
-      uint32_t st = 0, en = 0, cf = 0;
-      if (valid) {
-        st = d.read_start[r];
-        en = d.read_end[r];
-        cf = d.call_flags[r];
-      }
-      bool member = false, counted = false;
-      uint64_t hap = 0;
-      uint32_t frame = 0;
-      if (valid && en >= g.e) {
-        if (cf == 0 && !has_fs) {
-          // no allele call, no bad base, no duplicate qname: membership only
-          if (!rev) member = (st <= s0) ? ((int64_t)st >= (int64_t)s0 - (int64_t)sg.K) : (st > sg.off0 && st - sg.off0 <= k);
-          else member = (uint64_t)st + sg.K >= g.s;
-          counted = member;
-        } else {
-          const uint32_t vlo = d.read_vlo[r];
-          const uint64_t S = d.call_S[r], B = d.call_B[r];
-          MphPair p;
-          if (!rev) {
-            p = mph_fwd_state(sg, d.vars, k, g, va, vb, st, en, vlo, S, B);
-          } else {
-            p.member = 0; p.bad = 0; p.hap = 0; p.frame = 0;
-            const uint64_t Bx = B | (S & mph_range_mask(sg.sl_va, sg.sl_vb, vlo));
-            uint32_t ke = mph_rev_entry(sg, d.vars, k, st, en, vlo, Bx);
-            if (ke != NONE && (cf & 2u)) {
-              // `contains` (:281-294): of two reads sharing (start, qname) only the first to enter stays
-              const uint32_t q = partner_lookup(d, r);
-              if (q != NONE) {
-                const uint32_t qs = d.read_start[q], qe = d.read_end[q], qv = d.read_vlo[q];
-                if (qs <= g.s && qe >= g.e) {
-                  const uint64_t Bq = d.call_B[q] | (d.call_S[q] & mph_range_mask(sg.sl_va, sg.sl_vb, qv));
-                  const uint32_t kq = mph_rev_entry(sg, d.vars, k, qs, qe, qv, Bq);
-                  if (kq != NONE && (kq < ke || (kq == ke && q < r))) ke = NONE;
-                }
-              }
-            }
-            if (ke != NONE) p = mph_rev_state(sg, d.vars, k, g, va, vb, st, en, vlo, S, B, ke);
-          }
-          member = p.member != 0;
-          counted = member && !p.bad;
-          hap = p.hap;
-          frame = p.frame;
-        }
-      }
-      depth += __popc(__ballot_sync(FULL, member));
-      const bool zero_key = counted && hap == 0 && frame == 0;
-      c0 += __popc(__ballot_sync(FULL, zero_key));
-      unsigned pending = __ballot_sync(FULL, counted && !zero_key);
-      while (pending) {
-        const int leader = __ffs(pending) - 1;
-        const uint64_t lh = __shfl_sync(FULL, hap, leader);
-        const uint32_t lf = __shfl_sync(FULL, frame, leader);
-        const unsigned same = __ballot_sync(FULL, counted && !zero_key && hap == lh && frame == lf);
-        if (lane == 0) {
-          uint32_t t = 0;
-          for (; t < n_keys; ++t)
-            if (table[warp][t].hap == lh && table[warp][t].frame == lf) break;
-          if (t == n_keys) {
-            if (n_keys < K2_TABLE) {
-              table[warp][t].hap = lh;
-              table[warp][t].frame = lf;
-              table[warp][t].count = 0;
-              ++n_keys;
-            } else {
-              raise(d, MPH_E_KEYS_PER_WINDOW);
-              t = K2_TABLE - 1;
-            }
-          }
-          table[warp][t].count += __popc(same);
-        }
-        pending &= ~same;
-      }
-    }
-    if (lane == 0) {
-      // keys in the reference's BTreeMap order (:383,434)
-      for (uint32_t a = 1; a < n_keys; ++a) {
-        const MphHist key = table[warp][a];
-        uint32_t b = a;
-        while (b > 0 && hist_less(key, table[warp][b - 1])) {
-          table[warp][b] = table[warp][b - 1];
-          --b;
-        }
-        table[warp][b] = key;
-      }
-      MphWinOut wo;
-      wo.depth = depth;
-      wo.c0 = c0;
-      wo.n_extra = n_keys;
-      wo.extra_off = 0;
-      if (n_keys) {
-        const uint32_t off = atomicAdd(&d.counters[CTR_HIST], n_keys);
-        if (off + n_keys <= d.hist_cap) {
-          wo.extra_off = off;
-          for (uint32_t a = 0; a < n_keys; ++a) d.hist[off + a] = table[warp][a];
-        } else {
-          raise(d, MPH_E_HIST_OVERFLOW);
-          wo.n_extra = 0;
-        }
-      }
-      d.win_out[widx] = wo;
-      warp_depth += depth;
-    }
-    __syncwarp();
+  int64_t lo = rev ? (int64_t)g.s - (int64_t)sg.K : (int64_t)s0 - (int64_t)sg.K;
+  const int64_t lo2 = (int64_t)g.e - (int64_t)sg.max_span;
+  if (lo2 > lo) lo = lo2;
+  if (lo < 0) lo = 0;
+  uint32_t lo_u = active ? (uint32_t)lo : 0xFFFFFFFFu, hi_u = active ? g.s : 0u;
+  for (int o = 16; o; o >>= 1) {
+    lo_u = min(lo_u, __shfl_xor_sync(FULL, lo_u, o));
+    hi_u = max(hi_u, __shfl_xor_sync(FULL, hi_u, o));
   }
-  if (lane == 0 && warp_depth) atomicAdd(&cta_depth, warp_depth);
-  __syncthreads();
-  if (threadIdx.x == 0 && cta_depth) atomicAdd(d.sum_depth, cta_depth);
+  const uint32_t rlo = mph_u32_lb(d.read_start, sg.read_lo, sg.read_hi, lo_u);
+  const uint32_t rhi = mph_u32_lb(d.read_start, rlo, sg.read_hi, hi_u + 1u);
+  const uint32_t my_s = active ? g.s : 0u;             // inactive lanes: nothing encloses e = 0xFFFFFFFF
+  const uint32_t my_e = active ? g.e : 0xFFFFFFFFu;
+  const int64_t c1_lo = (int64_t)s0 - (int64_t)sg.K;   // forward: class-1 reads (offered at iteration 0)
+  uint32_t depth = 0, c0 = 0, n_keys = 0;
+  bool overflow = false;
+  auto add_key = [&](uint64_t hap, uint32_t frame) {
+    uint32_t t = 0;
+    for (; t < n_keys; ++t)
+      if (t_hap[warp][t][lane] == hap && t_frm[warp][t][lane] == frame) break;
+    if (t == n_keys) {
+      if (n_keys == K2_LANE_KEYS || d.force_wide) { overflow = true; return; }
+      t_hap[warp][t][lane] = hap;
+      t_frm[warp][t][lane] = frame;
+      t_cnt[warp][t][lane] = 0;
+      ++n_keys;
+    }
+    t_cnt[warp][t][lane] += 1;
+  };
+  for (uint32_t base = rlo; base < rhi; base += 32) {
+    const uint32_t rr = base + lane;
+    uint32_t l_st = 0, l_en = 0, l_cf = 0;
+    if (rr < rhi) {
+      l_st = d.read_start[rr];
+      l_en = d.read_end[rr];
+      l_cf = d.call_flags[rr];
+    }
+    const uint32_t cnt = min(32u, rhi - base);
+    for (uint32_t j = 0; j < cnt; ++j) {
+      const uint32_t st = __shfl_sync(FULL, l_st, j), en = __shfl_sync(FULL, l_en, j), cf = __shfl_sync(FULL, l_cf, j);
+      bool simple_member;
+      if (!rev) simple_member = en >= my_e && ((st <= s0) ? ((int64_t)st >= c1_lo) : (st > sg.off0 && st - sg.off0 <= k));
+      else simple_member = st <= my_s && en >= my_e && (uint64_t)st + sg.K >= my_s;
+      if (cf == 0 && !has_fs) {  // warp-uniform: no allele call, no bad base, no duplicate qname
+        depth += simple_member;
+        c0 += simple_member;
+        continue;
+      }
+      const uint32_t r = base + j;
+      const uint32_t vlo = d.read_vlo[r];
+      const uint64_t S = d.call_S[r], B = d.call_B[r];
+      const uint64_t Bx = B | (S & mph_range_mask(sg.sl_va, sg.sl_vb, vlo));
+      if (Bx == 0 && !(cf & 2u) && !has_fs) {  // warp-uniform: never bad, membership is the simple test
+        depth += simple_member;
+        if (simple_member) {
+          const uint64_t bits = mph_window_bits(S, vlo, va, nvar);
+          const uint64_t hap = (rev || nvar == 0) ? bits : (mph_bitrev64(bits) >> (64 - nvar));
+          if (hap == 0) c0 += 1;
+          else add_key(hap, 0);
+        }
+        continue;
+      }
+      if (en >= my_e && st <= my_s) {
+        const MphPair p = eval_flagged(d, sg, rev, k, g, va, vb, r, st, en, cf, vlo, S, B);
+        depth += p.member;
+        if (p.member && !p.bad) {
+          if (p.hap == 0 && p.frame == 0) c0 += 1;
+          else add_key(p.hap, p.frame);
+        }
+      }
+    }
+  }
+  // each lane sorts its keys (reference BTreeMap order :383,434)
+  for (uint32_t a = 1; a < n_keys; ++a) {
+    MphHist key;
+    key.hap = t_hap[warp][a][lane]; key.frame = t_frm[warp][a][lane]; key.count = t_cnt[warp][a][lane];
+    uint32_t b = a;
+    while (b > 0) {
+      MphHist prev;
+      prev.hap = t_hap[warp][b - 1][lane]; prev.frame = t_frm[warp][b - 1][lane]; prev.count = t_cnt[warp][b - 1][lane];
+      if (!hist_less(key, prev)) break;
+      t_hap[warp][b][lane] = prev.hap; t_frm[warp][b][lane] = prev.frame; t_cnt[warp][b][lane] = prev.count;
+      --b;
+    }
+    t_hap[warp][b][lane] = key.hap; t_frm[warp][b][lane] = key.frame; t_cnt[warp][b][lane] = key.count;
+  }
+  const bool ovf = active && overflow;
+  const uint32_t mine = (active && !ovf) ? n_keys : 0;
+  // warp-aggregated allocation in the key arena
+  uint32_t incl = mine;
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t y = __shfl_up_sync(FULL, incl, o);
+    if (lane >= o) incl += y;
+  }
+  const uint32_t total = __shfl_sync(FULL, incl, 31);
+  uint32_t base_off = 0;
+  if (lane == 0 && total) base_off = atomicAdd(&d.counters[CTR_HIST], total);
+  base_off = __shfl_sync(FULL, base_off, 0);
+  const bool fits = base_off + total <= d.hist_cap;
+  if (lane == 0 && total && !fits) raise(d, MPH_E_HIST_OVERFLOW);
+  if (active && !ovf) {
+    MphWinOut wo;
+    wo.depth = depth;
+    wo.c0 = c0;
+    wo.n_extra = fits ? mine : 0;
+    wo.extra_off = base_off + incl - mine;
+    if (fits)
+      for (uint32_t a = 0; a < mine; ++a) {
+        MphHist h;
+        h.hap = t_hap[warp][a][lane]; h.frame = t_frm[warp][a][lane]; h.count = t_cnt[warp][a][lane];
+        d.hist[wo.extra_off + a] = h;
+      }
+    d.win_out[sg.win_base + i] = wo;
+  }
+  if (ovf) {
+    const uint32_t o = atomicAdd(&d.counters[CTR_OVF], 1u);
+    d.ovf_list[o] = (chunk << 5) | (uint32_t)lane;
+  }
+  unsigned long long dsum = (active && !ovf) ? depth : 0;
+  for (int o = 16; o; o >>= 1) dsum += __shfl_down_sync(FULL, dsum, o);
+  if (lane == 0 && dsum) atomicAdd(d.sum_depth, dsum);
 }
 
 // ------------------------------------------------------------------ K3
@@ -379,7 +518,10 @@ void launch_allele_call(const DeviceBatch& d, cudaStream_t st) {
   if (d.n_reads) k_allele_call<<<(d.n_reads + 255) / 256, 256, 0, st>>>(d);
 }
 void launch_window_hist(const DeviceBatch& d, cudaStream_t st) {
-  if (d.n_chunks) k_window_hist<<<d.n_chunks, K2_WARPS * 32, 0, st>>>(d);
+  if (!d.n_chunks) return;
+  k_window_hist<<<(d.n_chunks + K2_WARPS - 1) / K2_WARPS, K2_WARPS * 32, 0, st>>>(d);
+  // windows with more distinct haplotypes than a lane table holds (rare): one warp per window
+  k_window_hist_wide<<<148 * 2, K2_WARPS * 32, 0, st>>>(d);
 }
 void launch_assemble(const DeviceBatch& d, cudaStream_t st) {
   if (d.n_chunks) k_assemble<<<(d.n_chunks + 7) / 8, 256, 0, st>>>(d);
@@ -393,6 +535,6 @@ void launch_compact(const DeviceBatch& d, cudaStream_t st) {
 void launch_live_depth(const DeviceBatch& d, cudaStream_t st) {
   if (d.n_chunks) k_live_depth<<<(d.n_chunks + 7) / 8, 256, 0, st>>>(d);
 }
-int kernel_launch_count() { return 6; }
+int kernel_launch_count() { return 7; }
 
 }  // namespace mphk

@@ -12,6 +12,7 @@ namespace mphk {
 struct DeviceBatch {
   // inputs
   uint32_t n_reads = 0, n_vars = 0, n_segs = 0, n_chunks = 0, n_windows = 0, seq_cap = 64, n_pairs = 0;
+  uint32_t force_wide = 0;  // test hook (MPH_FORCE_WIDE=1): send every window with extra keys through k_window_hist_wide
   const uint32_t* read_start = nullptr;
   const uint32_t* read_end = nullptr;
   const uint32_t* read_vlo = nullptr;
@@ -37,6 +38,7 @@ struct DeviceBatch {
   MphWinOut* win_out = nullptr;
   MphHist* hist = nullptr;
   uint32_t hist_cap = 0;
+  uint32_t* ovf_list = nullptr;  // (chunk << 5 | lane) of windows whose keys overflow a lane table; chunk count must be < 2^27
   // K3 output
   MphHap* hap0 = nullptr;
   MphHap* hapx = nullptr;  // parallel to hist
@@ -55,7 +57,7 @@ struct DeviceBatch {
   const uint32_t* seg_live = nullptr;  // per segment: number of windows the reference reaches
 };
 
-enum { CTR_HIST = 0, CTR_SEQ = 1, CTR_NIW = 2, CTR_ERR = 3 };
+enum { CTR_HIST = 0, CTR_SEQ = 1, CTR_NIW = 2, CTR_ERR = 3, CTR_OVF = 4 };
 
 void launch_allele_call(const DeviceBatch& d, cudaStream_t st);
 void launch_window_hist(const DeviceBatch& d, cudaStream_t st);

@@ -97,3 +97,15 @@ def test_cuda_matches_oracle_chr22_shape(product, oracle_bin, tmp_path):
     st = json.load(open(tmp_path / "stats.json"))
     assert t["windows"] == st["windows"], "main-ORF window count differs from the oracle's print_haplotypes calls"
     assert t["read_windows"] == st["read_windows"], "sum of depth differs from the oracle"
+
+
+@pytest.mark.parametrize("case", ["reverse_somatic", "forward_somatic"])
+def test_wide_histogram_kernel_matches_golden(product, case, tmp_path, monkeypatch):
+    """MPH_FORCE_WIDE=1 routes every window with extra haplotype keys through the warp-per-window overflow kernel."""
+    monkeypatch.setenv("MPH_FORCE_WIDE", "1")
+    d = os.path.join(GOLDEN, case)
+    fa = materialize_reference(d, str(tmp_path))
+    res = run_cli(product[1], d, str(tmp_path), ref=fa)
+    assert res.returncode == 0, res.stderr.decode()
+    for name in sorted(os.listdir(os.path.join(d, "expected"))):
+        assert open(tmp_path / name, "rb").read() == open(os.path.join(d, "expected", name), "rb").read(), name
