@@ -286,15 +286,24 @@ class Residue {
       const bool seqs_equal = germ_cleared ? seq_len == 0 : germ_eq;  // germline_seq == seq after clearing
       // does anything below need the actual bytes?
       const bool emit = (h.n_som > 0 || has_frameshift) && !is_short_exon && !seqs_equal && frame_frequency > 0.0 && (!stop_gain || has_frameshift);
-      const bool want_seq = emit || boundary || (h.flags & MPH_HF_SEQ);
+      // bytes are needed for emitted records and for the windows a splice merge can read (:1497-1908);
+      // an indel haplotype also needs them for the stop-codon side condition (:707)
+      const bool need_rec = emit || boundary;
+      const bool want_seq = need_rec || (stop_gain && indel);
       std::string seq, germline_seq;
-      if (want_seq && (h.flags & MPH_HF_SEQ)) {
-        seq = arena(h, false);
-        if (!germ_cleared) germline_seq = arena(h, true);
-      } else if (emit || boundary) {
-        throw std::logic_error("internal: sequence not shipped for an emitted / boundary haplotype");
+      if (want_seq) {
+        if (nv == 0) {
+          // no variant in the window: seq == germline_seq == refseq[s..e) (:464-471), the host has those bytes
+          if (g.s < sg.ref_pos0 || uint64_t(g.e) - sg.ref_pos0 > sg.ref_len) throw Fatal("slice index out of range: refseq");
+          seq.assign(reinterpret_cast<const char*>(b_.ref.data()) + sg.ref_off + (g.s - sg.ref_pos0), g.e - g.s);
+          if (!germ_cleared) germline_seq = seq;
+        } else {
+          if (!(h.flags & MPH_HF_SEQ)) throw std::logic_error("internal: sequence not shipped for an emitted / boundary haplotype");
+          seq = arena(h, false);
+          if (!germ_cleared) germline_seq = arena(h, true);
+        }
       }
-      const bool have_seq = (h.flags & MPH_HF_SEQ) != 0;
+      const bool have_seq = want_seq;
       auto slice = [](const std::string& s, uint64_t a, uint64_t e) -> std::string {
         if (a > e || e > s.size()) throw Fatal("slice index out of range");
         return s.substr(size_t(a), size_t(e - a));
@@ -325,7 +334,7 @@ class Residue {
       // meta information (:720-769)
       InfoRecord rec;
       rec.tx = t;
-      if (have_seq) {
+      if (need_rec) {
         uint32_t n_variantsites = 0, n_som_variantsites = 0;
         std::vector<std::string> s_pc, g_pc, s_pos, g_pos, sites;
         for (uint32_t c = 0; c < nv; ++c) {
@@ -341,7 +350,8 @@ class Residue {
             if (!(v.flags & MPH_VF_GERMLINE)) ++n_som_variantsites;
           }
         }
-        rec.id = mphfmt::record_id(reinterpret_cast<const uint8_t*>(seq.data()), seq.size(), tm.id, g.s, rev ? 'R' : 'F');
+        // the id of a record that is not written is never read (IDRecord::update derives a new one)
+        if (emit) rec.id = mphfmt::record_id(reinterpret_cast<const uint8_t*>(seq.data()), seq.size(), tm.id, g.s, rev ? 'R' : 'F');
         rec.offset = g.spos == 0 ? uint64_t(g.s) + 1 : uint64_t(g.s) + 1 + g.gap;
         rec.frame = frame;
         rec.freq = frame_frequency;
@@ -360,8 +370,8 @@ class Residue {
       }
       if (!remove_peptide || frame == 0) {
         HapSeq hs;
-        hs.partial = !have_seq;
-        if (have_seq) {
+        hs.partial = !boundary;
+        if (boundary) {
           hs.rec = rec;
           hs.rec.normal_sequence = germline_seq;
           hs.rec.mutant_sequence = seq;

@@ -204,10 +204,17 @@ __global__ void __launch_bounds__(K2_WARPS * 32) k_window_hist_wide(const Device
   }
 }
 
-// Main K2: one warp per chunk, one lane per window. Consecutive windows of an exon share almost
-// all candidate reads, so the warp walks the union of their candidate ranges once: 32 reads are
-// loaded coalesced, then broadcast one by one (shuffles) and every lane tests its own window.
+// Main K2: one warp per chunk (<= 32 consecutive windows of one exon), two phases.
+//  A (lane = read): walk the union of the windows' candidate ranges 32 reads at a time. A read
+//    without allele calls / bad bases / duplicate qname is an observation of a *contiguous* run of
+//    the chunk's windows (membership is monotone in the iteration number), so it contributes a
+//    +1/-1 pair to a 33-entry difference array instead of 32 separate tests. Reads that carry an
+//    allele call go to a short list, and so do the rare reads that need the full closed form.
+//  B (lane = window): prefix-sum the difference array -> depth and the (hap 0, frame 0) count; then
+//    only the listed reads are broadcast and evaluated per window, and their haplotype keys go to
+//    per-lane shared-memory tables.
 constexpr int K2_LANE_KEYS = 8;
+constexpr int K2_LIST = 64;
 
 __global__ void __launch_bounds__(K2_WARPS * 32) k_window_hist(const DeviceBatch d) {
   // per-lane key tables, [key][lane] so that a warp touches 32 distinct banks
@@ -215,16 +222,22 @@ __global__ void __launch_bounds__(K2_WARPS * 32) k_window_hist(const DeviceBatch
   __shared__ uint32_t t_cnt[K2_WARPS][K2_LANE_KEYS][32];
   __shared__ uint32_t t_frm[K2_WARPS][K2_LANE_KEYS][32];
   __shared__ MphSegment s_seg[K2_WARPS];
+  __shared__ uint32_t s_s[K2_WARPS][32], s_e[K2_WARPS][32];
+  __shared__ int s_add[K2_WARPS][34];
+  __shared__ uint32_t s_list[K2_WARPS][K2_LIST];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t chunk = blockIdx.x * K2_WARPS + warp;
   if (chunk >= d.n_chunks) return;
   const MphChunk ch = d.chunks[chunk];
   if (lane < (int)(sizeof(MphSegment) / 4)) reinterpret_cast<uint32_t*>(&s_seg[warp])[lane] = reinterpret_cast<const uint32_t*>(&d.segs[ch.seg])[lane];
+  s_add[warp][lane] = 0;
+  if (lane < 2) s_add[warp][32 + lane] = 0;
   __syncwarp();
   const MphSegment& sg = s_seg[warp];
   const bool rev = (sg.flags & MPH_SF_REVERSE) != 0;
   const bool has_fs = (sg.flags & MPH_SF_HAS_FS) != 0;
-  const bool active = (uint32_t)lane < ch.n;
+  const int n = (int)ch.n;
+  const bool active = lane < n;
   const uint32_t i = ch.i_first + (active ? lane : 0);
   const uint32_t k = sg.k_first + i * sg.k_stride;
   const MphGeom g = mph_geom(sg, k);
@@ -232,24 +245,29 @@ __global__ void __launch_bounds__(K2_WARPS * 32) k_window_hist(const DeviceBatch
   const uint32_t vb = mph_var_lb(d.vars, va, sg.var_hi, g.e);
   const uint32_t nvar = vb - va;
   if (active && nvar > 64) raise(d, MPH_E_VARS_PER_WINDOW);
+  const bool chunk_has_var = __ballot_sync(FULL, active && nvar > 0) != 0;
+  s_s[warp][lane] = g.s;
+  s_e[warp][lane] = g.e;
   // union of the lanes' candidate start ranges
   const uint32_t s0 = sg.off0 - sg.ceo;
-  int64_t lo = rev ? (int64_t)g.s - (int64_t)sg.K : (int64_t)s0 - (int64_t)sg.K;
+  int64_t lo64 = rev ? (int64_t)g.s - (int64_t)sg.K : (int64_t)s0 - (int64_t)sg.K;
   const int64_t lo2 = (int64_t)g.e - (int64_t)sg.max_span;
-  if (lo2 > lo) lo = lo2;
-  if (lo < 0) lo = 0;
-  uint32_t lo_u = active ? (uint32_t)lo : 0xFFFFFFFFu, hi_u = active ? g.s : 0u;
+  if (lo2 > lo64) lo64 = lo2;
+  if (lo64 < 0) lo64 = 0;
+  uint32_t lo_u = active ? (uint32_t)lo64 : 0xFFFFFFFFu, hi_u = active ? g.s : 0u;
   for (int o = 16; o; o >>= 1) {
     lo_u = min(lo_u, __shfl_xor_sync(FULL, lo_u, o));
     hi_u = max(hi_u, __shfl_xor_sync(FULL, hi_u, o));
   }
   const uint32_t rlo = mph_u32_lb(d.read_start, sg.read_lo, sg.read_hi, lo_u);
   const uint32_t rhi = mph_u32_lb(d.read_start, rlo, sg.read_hi, hi_u + 1u);
-  const uint32_t my_s = active ? g.s : 0u;             // inactive lanes: nothing encloses e = 0xFFFFFFFF
-  const uint32_t my_e = active ? g.e : 0xFFFFFFFFu;
-  const int64_t c1_lo = (int64_t)s0 - (int64_t)sg.K;   // forward: class-1 reads (offered at iteration 0)
-  uint32_t depth = 0, c0 = 0, n_keys = 0;
+  const uint32_t my_s = active ? g.s : 0u;
+  const uint32_t my_e = active ? g.e : 0xFFFFFFFFu;  // inactive lanes: nothing encloses e = 0xFFFFFFFF
+  const int64_t c1_lo = (int64_t)s0 - (int64_t)sg.K;  // forward: class-1 reads (offered at iteration 0)
+  uint32_t depth_x = 0, n_keys = 0;  // depth_x: observations counted in phase B (complex reads)
+  int c0_adj = 0;
   bool overflow = false;
+  __syncwarp();
   auto add_key = [&](uint64_t hap, uint32_t frame) {
     uint32_t t = 0;
     for (; t < n_keys; ++t)
@@ -263,49 +281,117 @@ __global__ void __launch_bounds__(K2_WARPS * 32) k_window_hist(const DeviceBatch
     }
     t_cnt[warp][t][lane] += 1;
   };
-  for (uint32_t base = rlo; base < rhi; base += 32) {
-    const uint32_t rr = base + lane;
-    uint32_t l_st = 0, l_en = 0, l_cf = 0;
-    if (rr < rhi) {
-      l_st = d.read_start[rr];
-      l_en = d.read_end[rr];
-      l_cf = d.call_flags[rr];
-    }
-    const uint32_t cnt = min(32u, rhi - base);
-    for (uint32_t j = 0; j < cnt; ++j) {
-      const uint32_t st = __shfl_sync(FULL, l_st, j), en = __shfl_sync(FULL, l_en, j), cf = __shfl_sync(FULL, l_cf, j);
-      bool simple_member;
-      if (!rev) simple_member = en >= my_e && ((st <= s0) ? ((int64_t)st >= c1_lo) : (st > sg.off0 && st - sg.off0 <= k));
-      else simple_member = st <= my_s && en >= my_e && (uint64_t)st + sg.K >= my_s;
-      if (cf == 0 && !has_fs) {  // warp-uniform: no allele call, no bad base, no duplicate qname
-        depth += simple_member;
-        c0 += simple_member;
-        continue;
-      }
-      const uint32_t r = base + j;
-      const uint32_t vlo = d.read_vlo[r];
-      const uint64_t S = d.call_S[r], B = d.call_B[r];
-      const uint64_t Bx = B | (S & mph_range_mask(sg.sl_va, sg.sl_vb, vlo));
-      if (Bx == 0 && !(cf & 2u) && !has_fs) {  // warp-uniform: never bad, membership is the simple test
-        depth += simple_member;
-        if (simple_member) {
-          const uint64_t bits = mph_window_bits(S, vlo, va, nvar);
-          const uint64_t hap = (rev || nvar == 0) ? bits : (mph_bitrev64(bits) >> (64 - nvar));
-          if (hap == 0) c0 += 1;
-          else add_key(hap, 0);
+  // phase B body for the listed reads (lane = window)
+  auto process_list = [&](uint32_t list_n) {
+    for (uint32_t x = 0; x < list_n; ++x) {
+      const uint32_t code = s_list[warp][x];
+      const uint32_t r = code & 0x7FFFFFFFu;
+      const uint32_t st = d.read_start[r], en = d.read_end[r], vlo = d.read_vlo[r];
+      const uint64_t S = d.call_S[r];
+      if (!(code >> 31)) {
+        // already counted as a plain observation; windows with variants still need its haplotype
+        if (nvar == 0) continue;
+        bool member;
+        if (!rev) member = en >= my_e && ((st <= s0) ? ((int64_t)st >= c1_lo) : (st > sg.off0 && st - sg.off0 <= k));
+        else member = st <= my_s && en >= my_e && (uint64_t)st + sg.K >= my_s;
+        if (!member) continue;
+        const uint64_t bits = mph_window_bits(S, vlo, va, nvar);
+        const uint64_t hap = rev ? bits : (mph_bitrev64(bits) >> (64 - nvar));
+        if (hap != 0) {
+          c0_adj -= 1;
+          add_key(hap, 0);
         }
-        continue;
-      }
-      if (en >= my_e && st <= my_s) {
-        const MphPair p = eval_flagged(d, sg, rev, k, g, va, vb, r, st, en, cf, vlo, S, B);
-        depth += p.member;
+      } else if (en >= my_e && st <= my_s) {
+        const MphPair p = eval_flagged(d, sg, rev, k, g, va, vb, r, st, en, d.call_flags[r], vlo, S, d.call_B[r]);
+        depth_x += p.member;
         if (p.member && !p.bad) {
-          if (p.hap == 0 && p.frame == 0) c0 += 1;
+          if (p.hap == 0 && p.frame == 0) c0_adj += 1;
           else add_key(p.hap, p.frame);
         }
       }
     }
+  };
+  // ---- phase A (lane = read)
+  uint32_t list_n = 0;
+  const uint32_t* ss = s_s[warp];
+  const uint32_t* se = s_e[warp];
+  for (uint32_t base = rlo; base < rhi; base += 32) {
+    const uint32_t r = base + lane;
+    int cls = 0, ilo = 1, ihi = 0;
+    if (r < rhi) {
+      const uint32_t st = d.read_start[r], en = d.read_end[r], cf = d.call_flags[r];
+      if (cf == 0 && !has_fs) {
+        cls = 1;
+      } else {
+        const uint32_t vlo = d.read_vlo[r];
+        const uint64_t S = d.call_S[r], B = d.call_B[r];
+        const uint64_t Bx = B | (S & mph_range_mask(sg.sl_va, sg.sl_vb, vlo));
+        if (Bx == 0 && !(cf & 2u) && !has_fs) cls = (S != 0 && chunk_has_var) ? 2 : 1;
+        else cls = 3;
+      }
+      if (cls != 3) {
+        // run of windows [ilo, ihi] of this chunk at which the read is an observation
+        if (!rev) {
+          int a = 0, b = n;  // e non-decreasing: windows with e <= en form a prefix
+          while (a < b) { const int m = (a + b) >> 1; if (se[m] <= en) a = m + 1; else b = m; }
+          ihi = a - 1;
+          if (st <= s0) {
+            ilo = ((int64_t)st >= c1_lo) ? 0 : n;
+          } else if (st <= sg.off0) {
+            ilo = n;
+          } else {
+            const uint32_t k_ins = st - sg.off0;  // first window with k >= k_ins
+            const uint32_t t = k_ins > sg.k_first ? (k_ins - sg.k_first + sg.k_stride - 1) / sg.k_stride : 0;
+            ilo = t > ch.i_first ? (int)min(t - ch.i_first, (uint32_t)n) : 0;
+          }
+        } else {
+          int a = 0, b = n;  // s non-increasing: windows with s >= st form a prefix
+          while (a < b) { const int m = (a + b) >> 1; if (ss[m] >= st) a = m + 1; else b = m; }
+          ihi = a - 1;
+          a = 0; b = n;      // first window with e <= en
+          while (a < b) { const int m = (a + b) >> 1; if (se[m] > en) a = m + 1; else b = m; }
+          ilo = a;
+          const uint64_t lim = (uint64_t)st + sg.K;
+          a = 0; b = n;      // first window with s <= st + K
+          while (a < b) { const int m = (a + b) >> 1; if ((uint64_t)ss[m] > lim) a = m + 1; else b = m; }
+          if (a > ilo) ilo = a;
+        }
+      }
+    }
+    const bool counted = (cls == 1 || cls == 2) && ilo <= ihi;
+    // warp-aggregated updates of the difference array (one writer per distinct index)
+    {
+      const int key = counted ? ilo : 33;
+      const unsigned m = __match_any_sync(FULL, key);
+      if (counted && lane == __ffs(m) - 1) s_add[warp][ilo] += __popc(m);
+      __syncwarp();
+      const int key2 = counted ? ihi + 1 : 33;
+      const unsigned m2 = __match_any_sync(FULL, key2);
+      if (counted && lane == __ffs(m2) - 1) s_add[warp][ihi + 1] -= __popc(m2);
+      __syncwarp();
+    }
+    const bool need = (cls == 2 && counted) || cls == 3;
+    const unsigned nm = __ballot_sync(FULL, need);
+    if (nm) {
+      if (list_n + __popc(nm) > K2_LIST) {
+        process_list(list_n);
+        list_n = 0;
+        __syncwarp();
+      }
+      if (need) s_list[warp][list_n + __popc(nm & ((1u << lane) - 1))] = r | (cls == 3 ? 0x80000000u : 0u);
+      list_n += __popc(nm);
+      __syncwarp();
+    }
   }
+  process_list(list_n);
+  // ---- phase B: prefix sum of the difference array
+  int run = s_add[warp][lane];
+  for (int o = 1; o < 32; o <<= 1) {
+    const int y = __shfl_up_sync(FULL, run, o);
+    if (lane >= o) run += y;
+  }
+  const uint32_t depth = (uint32_t)run + depth_x;
+  const uint32_t c0 = (uint32_t)(run + c0_adj);
   // each lane sorts its keys (reference BTreeMap order :383,434)
   for (uint32_t a = 1; a < n_keys; ++a) {
     MphHist key;
@@ -362,24 +448,8 @@ __device__ void assemble_entry(const DeviceBatch& d, const MphSegment& sg, const
                                bool boundary, uint8_t* seq, uint8_t* germ, MphHap* out, uint32_t* err) {
   const uint32_t cap = d.seq_cap;
   if (va == vb) {
+    // no variant: only the stop test; the host reads the bytes from its own copy of the reference slice
     *err |= mph_plain_window(sg, g, d.ref, out);
-    if (boundary && !(*err & MPH_E_REF_RANGE)) {
-      const uint32_t off = atomicAdd(&d.counters[CTR_SEQ], 2 * cap);
-      if (off + 2 * cap <= d.seq_cap_bytes) {
-        const uint8_t* p = d.ref + sg.ref_off + (g.s - sg.ref_pos0);
-        const uint32_t len = g.e - g.s;
-        for (uint32_t t = 0; t < len && t < cap; ++t) {
-          const uint8_t c = p[t];
-          d.seq[off + t] = c;
-          d.seq[off + cap + t] = c;
-        }
-        if (len > cap) out->flags |= MPH_HF_OVERFLOW;
-        out->seq_off = off;
-        out->flags |= MPH_HF_SEQ;
-      } else {
-        *err |= MPH_E_SEQ_OVERFLOW;
-      }
-    }
     return;
   }
   *err |= mph_assemble(sg, g, d.vars, va, vb, d.ref, d.ins_bytes, hap, seq, germ, cap, out);

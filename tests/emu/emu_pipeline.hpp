@@ -90,14 +90,6 @@ inline PhaseRaw phase(const Batch& b) {
       auto assemble = [&](uint64_t hap, MphHap* out) {
         if (va == vb) {
           raw.err |= mph_plain_window(sg, g, b.ref.data(), out);
-          if (boundary) {
-            out->seq_off = uint32_t(raw.seq.size());
-            raw.seq.resize(raw.seq.size() + 2 * b.seq_cap, 0);
-            const uint8_t* p = b.ref.data() + sg.ref_off + (g.s - sg.ref_pos0);
-            memcpy(&raw.seq[out->seq_off], p, g.e - g.s);
-            memcpy(&raw.seq[out->seq_off + b.seq_cap], p, g.e - g.s);
-            out->flags |= MPH_HF_SEQ;
-          }
           return;
         }
         raw.err |= mph_assemble(sg, g, b.vars.data(), va, vb, b.ref.data(), b.ins_bytes.data(), hap, seqbuf.data(), germbuf.data(), b.seq_cap, out);
