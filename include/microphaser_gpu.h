@@ -118,7 +118,7 @@ typedef struct {
   const uint32_t* cigars; uint64_t n_cigar_ops;
   const void* vars;       /* MphVar[n_vars], 16 B each (csrc/core/layout.h) */
   const void* segments;   /* MphSegment[n_segments], 96 B each */
-  const void* chunks;     /* MphChunk[n_chunks], 16 B each */
+  const void* chunks;     /* MphChunk[n_chunks], 32 B each */
   const uint8_t* ref;     uint64_t ref_bytes;     /* per-exon reference slices */
   uint64_t h2d_bytes;     /* bytes copied host -> device per mph_phase_batch call */
 } mph_batch_view;

@@ -68,11 +68,15 @@ typedef struct {
   uint32_t pad;
 } MphSegment;
 
-// A unit of K2/K3 work: n consecutive windows of one segment, 16 B.
+// A unit of K2/K3 work: n consecutive windows of one segment, 32 B. The read / variant index
+// ranges the chunk can touch are data independent, so the packer resolves them once (it saves the
+// kernels ~27 dependent binary-search loads per chunk).
 typedef struct {
   uint32_t seg;
   uint32_t i_first;
   uint32_t n;
+  uint32_t rlo, rhi;  // union of the windows' candidate reads (global read indices)
+  uint32_t va0, vb1;  // variants with pos in [min s, max e) over the chunk's windows
   uint32_t pad;
 } MphChunk;
 

@@ -320,6 +320,16 @@ class Packer {
         for (uint32_t i = 0; i < sg.n_win; i += chunk_windows_) {
           MphChunk c;
           c.seg = si; c.i_first = i; c.n = std::min(chunk_windows_, sg.n_win - i); c.pad = 0;
+          // s and e are monotone in the iteration number (non-decreasing forward, non-increasing reverse)
+          const MphGeom ga = mph_geom(sg, sg.k_first + i * sg.k_stride), gz = mph_geom(sg, sg.k_first + (i + c.n - 1) * sg.k_stride);
+          const uint32_t s_min = std::min(ga.s, gz.s), s_max = std::max(ga.s, gz.s), e_min = std::min(ga.e, gz.e), e_max = std::max(ga.e, gz.e);
+          int64_t lo = t.reverse ? int64_t(s_min) - int64_t(sg.K) : int64_t(sg.off0 - sg.ceo) - int64_t(sg.K);
+          lo = std::max<int64_t>(lo, int64_t(e_min) - int64_t(sg.max_span));
+          lo = std::max<int64_t>(lo, 0);
+          c.rlo = mph_u32_lb(b_.read_start.data(), sg.read_lo, sg.read_hi, uint32_t(lo));
+          c.rhi = mph_u32_lb(b_.read_start.data(), c.rlo, sg.read_hi, s_max + 1u);
+          c.va0 = mph_var_lb(b_.vars.data(), sg.var_lo, sg.var_hi, s_min);
+          c.vb1 = mph_var_lb(b_.vars.data(), c.va0, sg.var_hi, e_max);
           b_.chunks.push_back(c);
         }
       }

@@ -27,7 +27,7 @@ namespace {
 
 constexpr unsigned FULL = 0xFFFFFFFFu;
 constexpr uint32_t NONE = 0xFFFFFFFFu;
-constexpr int K2_WARPS = 8;
+constexpr int K2_WARPS = 4;
 constexpr int K2_TABLE = 32;
 constexpr int MAX_SEQ_CAP = 256;  // bytes per assembled sequence kept in local memory
 
@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(K2_WARPS * 32) k_window_hist_wide(const Device
 //  B (lane = window): prefix-sum the difference array -> depth and the (hap 0, frame 0) count; then
 //    only the listed reads are broadcast and evaluated per window, and their haplotype keys go to
 //    per-lane shared-memory tables.
-constexpr int K2_LANE_KEYS = 8;
+constexpr int K2_LANE_KEYS = 4;
 constexpr int K2_LIST = 64;
 
 __global__ void __launch_bounds__(K2_WARPS * 32) k_window_hist(const DeviceBatch d) {
@@ -241,26 +241,15 @@ __global__ void __launch_bounds__(K2_WARPS * 32) k_window_hist(const DeviceBatch
   const uint32_t i = ch.i_first + (active ? lane : 0);
   const uint32_t k = sg.k_first + i * sg.k_stride;
   const MphGeom g = mph_geom(sg, k);
-  const uint32_t va = mph_var_lb(d.vars, sg.var_lo, sg.var_hi, g.s);
-  const uint32_t vb = mph_var_lb(d.vars, va, sg.var_hi, g.e);
+  const uint32_t va = mph_var_lb(d.vars, ch.va0, ch.vb1, g.s);
+  const uint32_t vb = mph_var_lb(d.vars, va, ch.vb1, g.e);
   const uint32_t nvar = vb - va;
   if (active && nvar > 64) raise(d, MPH_E_VARS_PER_WINDOW);
-  const bool chunk_has_var = __ballot_sync(FULL, active && nvar > 0) != 0;
+  const bool chunk_has_var = ch.vb1 > ch.va0;
   s_s[warp][lane] = g.s;
   s_e[warp][lane] = g.e;
-  // union of the lanes' candidate start ranges
   const uint32_t s0 = sg.off0 - sg.ceo;
-  int64_t lo64 = rev ? (int64_t)g.s - (int64_t)sg.K : (int64_t)s0 - (int64_t)sg.K;
-  const int64_t lo2 = (int64_t)g.e - (int64_t)sg.max_span;
-  if (lo2 > lo64) lo64 = lo2;
-  if (lo64 < 0) lo64 = 0;
-  uint32_t lo_u = active ? (uint32_t)lo64 : 0xFFFFFFFFu, hi_u = active ? g.s : 0u;
-  for (int o = 16; o; o >>= 1) {
-    lo_u = min(lo_u, __shfl_xor_sync(FULL, lo_u, o));
-    hi_u = max(hi_u, __shfl_xor_sync(FULL, hi_u, o));
-  }
-  const uint32_t rlo = mph_u32_lb(d.read_start, sg.read_lo, sg.read_hi, lo_u);
-  const uint32_t rhi = mph_u32_lb(d.read_start, rlo, sg.read_hi, hi_u + 1u);
+  const uint32_t rlo = ch.rlo, rhi = ch.rhi;  // union of the lanes' candidate ranges, resolved by the packer
   const uint32_t my_s = active ? g.s : 0u;
   const uint32_t my_e = active ? g.e : 0xFFFFFFFFu;  // inactive lanes: nothing encloses e = 0xFFFFFFFF
   const int64_t c1_lo = (int64_t)s0 - (int64_t)sg.K;  // forward: class-1 reads (offered at iteration 0)
@@ -478,8 +467,8 @@ __global__ void __launch_bounds__(256) k_assemble(const DeviceBatch d) {
   const uint32_t k = sg.k_first + i * sg.k_stride;
   const uint32_t widx = sg.win_base + i;
   const MphGeom g = mph_geom(sg, k);
-  const uint32_t va = mph_var_lb(d.vars, sg.var_lo, sg.var_hi, g.s);
-  const uint32_t vb = mph_var_lb(d.vars, va, sg.var_hi, g.e);
+  const uint32_t va = mph_var_lb(d.vars, ch.va0, ch.vb1, g.s);
+  const uint32_t vb = mph_var_lb(d.vars, va, ch.vb1, g.e);
   const MphWinOut wo = d.win_out[widx];
   const bool boundary = i == 0 || i + 1 == sg.n_win || (sg.flags & MPH_SF_HAS_FS);
   uint8_t seq[MAX_SEQ_CAP], germ[MAX_SEQ_CAP];
