@@ -83,7 +83,7 @@ struct mph_ctx {
   std::string last_error;
   const mph_batch* cur = nullptr;
   mphk::DeviceBatch d;
-  DevBuf<uint32_t> read_start, read_end, read_vlo, read_seq_off, read_cig_off, cigars, block_counts, iw, counters, seg_live, ovf_list;
+  DevBuf<uint32_t> read_start, read_end, read_vlo, read_seq_off, read_cig_off, cigars, block_counts, iw, counters, seg_live, ovf_list, stopmap, hist_win;
   DevBuf<uint16_t> read_lseq, read_ncig;
   DevBuf<uint8_t> read_nv, read_flags, bases, ins_bytes, ref, call_flags, seq, win_flag;
   DevBuf<uint2> pairs;
@@ -137,7 +137,7 @@ void finish_batch(mph_batch* mb, bool pin) {
   auto bytes = [](auto& v) { return v.size() * sizeof(v[0]); };
   mb->h2d_bytes = bytes(b.read_start) + bytes(b.read_end) + bytes(b.read_vlo) + bytes(b.read_seq_off) + bytes(b.read_cig_off) +
                   bytes(b.read_lseq) + bytes(b.read_ncig) + bytes(b.read_nv) + bytes(b.read_flags) + bytes(b.bases) + bytes(b.cigars) +
-                  bytes(b.vars) + bytes(b.ins_bytes) + bytes(b.segs) + bytes(b.chunks) + bytes(b.ref) + bytes(mb->pairs);
+                  bytes(b.vars) + bytes(b.ins_bytes) + bytes(b.segs) + bytes(b.chunks) + bytes(b.ref) + bytes(b.stopmap) + bytes(mb->pairs);
   if (pin) {
     auto reg = [&](auto& v) {
       if (v.empty()) return;
@@ -147,7 +147,7 @@ void finish_batch(mph_batch* mb, bool pin) {
         cudaGetLastError();
     };
     reg(b.read_start); reg(b.read_end); reg(b.read_vlo); reg(b.read_seq_off); reg(b.read_cig_off); reg(b.read_lseq); reg(b.read_ncig);
-    reg(b.read_nv); reg(b.read_flags); reg(b.bases); reg(b.cigars); reg(b.vars); reg(b.ins_bytes); reg(b.segs); reg(b.chunks); reg(b.ref);
+    reg(b.read_nv); reg(b.read_flags); reg(b.bases); reg(b.cigars); reg(b.vars); reg(b.ins_bytes); reg(b.segs); reg(b.chunks); reg(b.ref); reg(b.stopmap);
     reg(mb->pairs);
     mb->pinned = true;
   }
@@ -168,7 +168,7 @@ void upload(mph_ctx* c, const mph_batch* mb) {
   h2d(c, c->read_seq_off, b.read_seq_off); h2d(c, c->read_cig_off, b.read_cig_off); h2d(c, c->read_lseq, b.read_lseq);
   h2d(c, c->read_ncig, b.read_ncig); h2d(c, c->read_nv, b.read_nv); h2d(c, c->read_flags, b.read_flags); h2d(c, c->bases, b.bases);
   h2d(c, c->cigars, b.cigars); h2d(c, c->vars, b.vars); h2d(c, c->ins_bytes, b.ins_bytes); h2d(c, c->segs, b.segs);
-  h2d(c, c->chunks, b.chunks); h2d(c, c->ref, b.ref); h2d(c, c->pairs, mb->pairs);
+  h2d(c, c->chunks, b.chunks); h2d(c, c->ref, b.ref); h2d(c, c->stopmap, b.stopmap); h2d(c, c->pairs, mb->pairs);
   CU(cudaEventRecord(c->ev[1], c->stream));
   const size_t nr = b.n_reads(), nw = size_t(b.n_windows);
   c->call_S.ensure(nr + 1); c->call_B.ensure(nr + 1); c->call_flags.ensure(nr + 1);
@@ -179,6 +179,7 @@ void upload(mph_ctx* c, const mph_batch* mb) {
   c->counters.ensure(8); c->sums.ensure(2); c->seg_live.ensure(b.segs.size() + 1);
   if (c->hist.cap == 0) { c->hist.ensure(std::max<size_t>(nw / 2, 1 << 16)); c->hapx.ensure(c->hist.cap); }
   if (c->hapx.cap < c->hist.cap) c->hapx.ensure(c->hist.cap);
+  if (c->hist_win.cap < c->hist.cap) c->hist_win.ensure(c->hist.cap);
   const size_t seq_want = (2 * b.segs.size() + nw / 8 + 4096) * 2 * b.seq_cap;
   if (c->seq.cap < seq_want) c->seq.ensure(seq_want);
   mphk::DeviceBatch& d = c->d;
@@ -187,7 +188,7 @@ void upload(mph_ctx* c, const mph_batch* mb) {
   d.read_start = c->read_start.p; d.read_end = c->read_end.p; d.read_vlo = c->read_vlo.p; d.read_seq_off = c->read_seq_off.p;
   d.read_cig_off = c->read_cig_off.p; d.read_lseq = c->read_lseq.p; d.read_ncig = c->read_ncig.p; d.read_nv = c->read_nv.p;
   d.read_flags = c->read_flags.p; d.pairs = c->pairs.p; d.bases = c->bases.p; d.cigars = c->cigars.p; d.vars = c->vars.p;
-  d.ins_bytes = c->ins_bytes.p; d.segs = c->segs.p; d.chunks = c->chunks.p; d.ref = c->ref.p;
+  d.ins_bytes = c->ins_bytes.p; d.segs = c->segs.p; d.chunks = c->chunks.p; d.ref = c->ref.p; d.stopmap = c->stopmap.p;
   d.call_S = reinterpret_cast<uint64_t*>(c->call_S.p); d.call_B = reinterpret_cast<uint64_t*>(c->call_B.p); d.call_flags = c->call_flags.p;
   d.win_out = c->win_out.p; d.hap0 = c->hap0.p; d.win_flag = c->win_flag.p; d.block_counts = c->block_counts.p;
   d.ovf_list = c->ovf_list.p;
@@ -202,7 +203,8 @@ void run_kernels(mph_ctx* c) {
   if (!c->cur) throw std::runtime_error("no batch uploaded");
   mphk::DeviceBatch& d = c->d;
   { const char* fw = getenv("MPH_FORCE_WIDE"); d.force_wide = (fw && *fw == '1') ? 1u : 0u; }
-  d.hist = c->hist.p; d.hapx = c->hapx.p; d.hist_cap = uint32_t(std::min<size_t>(c->hist.cap, 0xFFFFFFF0u));
+  if (c->hist_win.cap < c->hist.cap) c->hist_win.ensure(c->hist.cap);
+  d.hist = c->hist.p; d.hapx = c->hapx.p; d.hist_win = c->hist_win.p; d.hist_cap = uint32_t(std::min<size_t>(c->hist.cap, 0xFFFFFFF0u));
   d.seq = c->seq.p; d.seq_cap_bytes = uint32_t(std::min<size_t>(c->seq.cap, 0xFFFFFF00u));
   CU(cudaMemsetAsync(c->counters.p, 0, 8 * sizeof(uint32_t), c->stream));
   CU(cudaMemsetAsync(c->sums.p, 0, 2 * sizeof(unsigned long long), c->stream));
@@ -370,7 +372,7 @@ void mph_ctx_destroy(mph_ctx* c) {
   c->read_start.release(); c->read_end.release(); c->read_vlo.release(); c->read_seq_off.release(); c->read_cig_off.release();
   c->cigars.release(); c->block_counts.release(); c->iw.release(); c->counters.release(); c->seg_live.release(); c->read_lseq.release();
   c->read_ncig.release(); c->read_nv.release(); c->read_flags.release(); c->bases.release(); c->ins_bytes.release(); c->ref.release();
-  c->ovf_list.release(); c->call_flags.release(); c->seq.release(); c->win_flag.release(); c->pairs.release(); c->vars.release(); c->segs.release();
+  c->ovf_list.release(); c->stopmap.release(); c->hist_win.release(); c->call_flags.release(); c->seq.release(); c->win_flag.release(); c->pairs.release(); c->vars.release(); c->segs.release();
   c->chunks.release(); c->call_S.release(); c->call_B.release(); c->win_out.release(); c->iw_out.release(); c->hist.release();
   c->hap0.release(); c->hapx.release(); c->iw_hap0.release(); c->sums.release();
   for (auto& e : c->ev)

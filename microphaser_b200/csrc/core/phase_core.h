@@ -425,7 +425,52 @@ MPH_HD uint32_t mph_assemble(const MphSegment& g, const MphGeom& gk, const MphVa
   return err;
 }
 
-// window without variants: seq == germline_seq == refseq[s..e) (:464-471); only the stop test is needed
+// Haplotype 0 of any window: no variant is applied, so seq == germline_seq == refseq[s..e)
+// (:464-471, :594-599) and the walk visits all nvar variants without touching the sequence. Only
+// the stop test remains; it reads the packer's stop-codon bitmap (bit t <=> the three reference
+// bytes starting at arena byte t spell a stop codon for the segment's strand).
+MPH_HD uint32_t mph_plain_hap(const MphSegment& g, const MphGeom& gk, const uint32_t* stopmap, const uint8_t* ref_arena, uint32_t nvar,
+                              MphHap* out) {
+  uint32_t err = 0;
+  const uint32_t len = gk.e - gk.s;
+  uint32_t flags = MPH_HF_GERM_EQ;
+  if (gk.s < g.ref_pos0 || (uint64_t)gk.e - g.ref_pos0 > g.ref_len) {
+    err |= MPH_E_REF_RANGE;
+  } else {
+    uint32_t a, b;
+    mph_neo_slice(gk, len, g.ewl, false, &a, &b);
+    const bool fwd = (g.flags & MPH_SF_REVERSE) == 0;
+    if (b >= a + 3) {
+      if (len <= 61) {
+        // codon starts q in [a, b-3] with q = a (mod 3) forward / q = b (mod 3) reverse (:42-76)
+        const uint64_t bit0 = (uint64_t)g.ref_off + (gk.s - g.ref_pos0);
+        const uint32_t w = (uint32_t)(bit0 >> 5), sh = (uint32_t)(bit0 & 31);
+        const uint64_t lo = stopmap[w] | ((uint64_t)stopmap[w + 1] << 32);
+        uint64_t bits = lo >> sh;
+        if (sh) bits |= (uint64_t)stopmap[w + 2] << (64 - sh);
+        const uint32_t phase = (fwd ? a : b) % 3;
+        uint64_t mask = 0x9249249249249249ull << phase;
+        mask &= ~(uint64_t)0 << a;
+        mask &= ~(uint64_t)0 >> (64 - (b - 2));
+        if (bits & mask) flags |= MPH_HF_STOP;
+      } else {
+        const uint8_t* p = ref_arena + g.ref_off + (gk.s - g.ref_pos0);
+        if (mph_has_stop(p + a, b - a, fwd)) flags |= MPH_HF_STOP;
+      }
+    }
+  }
+  out->flags = flags;
+  out->seq_len = (uint16_t)len;
+  out->germ_len = (uint16_t)len;
+  out->n_var = 0; out->n_som = 0; out->n_prof = (uint8_t)(nvar < 255 ? nvar : 255); out->brk = 0;
+  out->seq_off = 0xFFFFFFFFu;
+  out->profile = 0;
+  out->pad2 = 0;
+  if (nvar > 32) err |= MPH_E_VARS_PER_WINDOW;
+  return err;
+}
+
+// byte-wise variant of the above for a window without variants (kept for cross-checks)
 MPH_HD uint32_t mph_plain_window(const MphSegment& g, const MphGeom& gk, const uint8_t* ref_arena, MphHap* out) {
   uint32_t err = 0;
   const uint32_t len = gk.e - gk.s;

@@ -92,6 +92,7 @@ struct Batch {
   std::vector<MphSegment> segs;
   std::vector<MphChunk> chunks;
   std::vector<uint8_t> ref;  // per-segment reference slices
+  std::vector<uint32_t> stopmap;  // 1 bit per ref byte: a stop codon (for the slice's strand) starts here; 2 words of slack
   uint64_t n_windows = 0;
   uint32_t seq_cap = 64;  // bytes per assembled sequence slot
   // host-only
@@ -310,6 +311,13 @@ class Packer {
         sg.ref_off = uint32_t(b_.ref.size());
         sg.ref_len = slice_end - ex.start;
         b_.ref.insert(b_.ref.end(), refseq.begin() + (ex.start - g.start), refseq.begin() + (slice_end - g.start));
+        b_.stopmap.resize(b_.ref.size() / 32 + 4, 0);
+        for (uint32_t x = 0; x + 3 <= sg.ref_len; ++x) {  // case-sensitive like has_stop_codon (:42-76)
+          const uint8_t* c = &b_.ref[sg.ref_off + x];
+          const bool stop = t.reverse ? (c[2] == 'A' && ((c[0] == 'T' && (c[1] == 'C' || c[1] == 'T')) || (c[0] == 'C' && c[1] == 'T')))
+                                      : (c[0] == 'T' && ((c[1] == 'G' && c[2] == 'A') || (c[1] == 'A' && (c[2] == 'G' || c[2] == 'A'))));
+          if (stop) b_.stopmap[(sg.ref_off + x) >> 5] |= 1u << ((sg.ref_off + x) & 31);
+        }
         sg.tx = txi;
         sg.win_base = uint32_t(b_.n_windows);
         b_.n_windows += sg.n_win;

@@ -292,8 +292,8 @@ class Residue {
       const bool want_seq = need_rec || (stop_gain && indel);
       std::string seq, germline_seq;
       if (want_seq) {
-        if (nv == 0) {
-          // no variant in the window: seq == germline_seq == refseq[s..e) (:464-471), the host has those bytes
+        if (nv == 0 || key.hap == 0) {
+          // no variant applied: seq == germline_seq == refseq[s..e) (:464-471,594-599), the host has those bytes
           if (g.s < sg.ref_pos0 || uint64_t(g.e) - sg.ref_pos0 > sg.ref_len) throw Fatal("slice index out of range: refseq");
           seq.assign(reinterpret_cast<const char*>(b_.ref.data()) + sg.ref_off + (g.s - sg.ref_pos0), g.e - g.s);
           if (!germ_cleared) germline_seq = seq;

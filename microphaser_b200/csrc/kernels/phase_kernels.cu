@@ -107,7 +107,7 @@ __device__ __forceinline__ MphPair eval_flagged(const DeviceBatch& d, const MphS
 
 // Wide variant: one warp per window, lanes over the candidate reads, keys in a 32-entry table.
 // Used only for windows whose key count overflows the per-lane table of k_window_hist.
-__device__ void window_hist_warp(const DeviceBatch& d, const MphSegment& sg, uint32_t i, MphHist* table, int lane) {
+__device__ void window_hist_warp(const DeviceBatch& d, const MphSegment& sg, uint32_t i, uint32_t code, MphHist* table, int lane) {
   const bool rev = (sg.flags & MPH_SF_REVERSE) != 0;
   const uint32_t k = sg.k_first + i * sg.k_stride;
   const uint32_t widx = sg.win_base + i;
@@ -180,7 +180,10 @@ __device__ void window_hist_warp(const DeviceBatch& d, const MphSegment& sg, uin
       const uint32_t off = atomicAdd(&d.counters[CTR_HIST], n_keys);
       if (off + n_keys <= d.hist_cap) {
         wo.extra_off = off;
-        for (uint32_t a = 0; a < n_keys; ++a) d.hist[off + a] = table[a];
+        for (uint32_t a = 0; a < n_keys; ++a) {
+          d.hist[off + a] = table[a];
+          d.hist_win[off + a] = code;
+        }
       } else {
         raise(d, MPH_E_HIST_OVERFLOW);
         wo.n_extra = 0;
@@ -188,6 +191,11 @@ __device__ void window_hist_warp(const DeviceBatch& d, const MphSegment& sg, uin
     }
     d.win_out[widx] = wo;
     atomicAdd(d.sum_depth, (unsigned long long)depth);
+    MphHap h0;
+    const uint32_t err = mph_plain_hap(sg, g, d.stopmap, d.ref, vb - va, &h0);
+    d.win_flag[widx] = 1;  // it has extra keys, hence it is interesting
+    d.hap0[widx] = h0;
+    raise(d, err);
   }
   __syncwarp();
 }
@@ -200,7 +208,7 @@ __global__ void __launch_bounds__(K2_WARPS * 32) k_window_hist_wide(const Device
     const uint32_t code = d.ovf_list[o];
     const MphChunk ch = d.chunks[code >> 5];
     const MphSegment sg = d.segs[ch.seg];
-    window_hist_warp(d, sg, ch.i_first + (code & 31u), table[warp], lane);
+    window_hist_warp(d, sg, ch.i_first + (code & 31u), code, table[warp], lane);
   }
 }
 
@@ -420,8 +428,19 @@ __global__ void __launch_bounds__(K2_WARPS * 32) k_window_hist(const DeviceBatch
         MphHist h;
         h.hap = t_hap[warp][a][lane]; h.frame = t_frm[warp][a][lane]; h.count = t_cnt[warp][a][lane];
         d.hist[wo.extra_off + a] = h;
+        d.hist_win[wo.extra_off + a] = (chunk << 5) | (uint32_t)lane;
       }
-    d.win_out[sg.win_base + i] = wo;
+    const uint32_t widx = sg.win_base + i;
+    d.win_out[widx] = wo;
+    // Haplotype 0 needs no sequence walk (no variant is applied): stop test from the bitmap, and the
+    // "interesting" decision. Only the extra keys (hap != 0) go through K3.
+    MphHap h0;
+    const uint32_t err = mph_plain_hap(sg, g, d.stopmap, d.ref, nvar, &h0);
+    const bool boundary = i == 0 || i + 1 == sg.n_win || has_fs;
+    const bool interesting = nvar > 0 || (h0.flags & MPH_HF_STOP) || boundary || wo.n_extra > 0;
+    d.win_flag[widx] = interesting ? 1 : 0;
+    if (interesting) d.hap0[widx] = h0;
+    raise(d, err);
   }
   if (ovf) {
     const uint32_t o = atomicAdd(&d.counters[CTR_OVF], 1u);
@@ -433,56 +452,42 @@ __global__ void __launch_bounds__(K2_WARPS * 32) k_window_hist(const DeviceBatch
 }
 
 // ------------------------------------------------------------------ K3
-__device__ void assemble_entry(const DeviceBatch& d, const MphSegment& sg, const MphGeom& g, uint32_t va, uint32_t vb, uint64_t hap,
-                               bool boundary, uint8_t* seq, uint8_t* germ, MphHap* out, uint32_t* err) {
-  const uint32_t cap = d.seq_cap;
-  if (va == vb) {
-    // no variant: only the stop test; the host reads the bytes from its own copy of the reference slice
-    *err |= mph_plain_window(sg, g, d.ref, out);
-    return;
-  }
-  *err |= mph_assemble(sg, g, d.vars, va, vb, d.ref, d.ins_bytes, hap, seq, germ, cap, out);
-  if (boundary || out->n_som > 0) {
-    const uint32_t off = atomicAdd(&d.counters[CTR_SEQ], 2 * cap);
-    if (off + 2 * cap <= d.seq_cap_bytes) {
-      const uint32_t sl = out->seq_len < cap ? out->seq_len : cap, gl = out->germ_len < cap ? out->germ_len : cap;
-      for (uint32_t t = 0; t < sl; ++t) d.seq[off + t] = seq[t];
-      for (uint32_t t = 0; t < gl; ++t) d.seq[off + cap + t] = germ[t];
-      out->seq_off = off;
-      out->flags |= MPH_HF_SEQ;
-    } else {
-      *err |= MPH_E_SEQ_OVERFLOW;
-    }
-  }
-}
-
-__global__ void __launch_bounds__(256) k_assemble(const DeviceBatch d) {
-  const uint32_t chunk = blockIdx.x * 8 + (threadIdx.x >> 5);
-  const uint32_t lane = threadIdx.x & 31;
-  if (chunk >= d.n_chunks) return;
-  const MphChunk ch = d.chunks[chunk];
-  if (lane >= ch.n) return;
-  const MphSegment sg = d.segs[ch.seg];
-  const uint32_t i = ch.i_first + lane;
-  const uint32_t k = sg.k_first + i * sg.k_stride;
-  const uint32_t widx = sg.win_base + i;
-  const MphGeom g = mph_geom(sg, k);
-  const uint32_t va = mph_var_lb(d.vars, ch.va0, ch.vb1, g.s);
-  const uint32_t vb = mph_var_lb(d.vars, va, ch.vb1, g.e);
-  const MphWinOut wo = d.win_out[widx];
-  const bool boundary = i == 0 || i + 1 == sg.n_win || (sg.flags & MPH_SF_HAS_FS);
+// One thread per extra histogram key (haplotype != 0): the sequence walk of print_haplotypes
+// (:458-603) into thread-local buffers, then the stop test; the bytes are kept only for haplotypes
+// that can be written (n_somatic > 0) or merged across a splice junction (boundary windows).
+__global__ void __launch_bounds__(128) k_assemble(const DeviceBatch d) {
+  const uint32_t n = min(d.counters[CTR_HIST], d.hist_cap);
   uint8_t seq[MAX_SEQ_CAP], germ[MAX_SEQ_CAP];
-  uint32_t err = 0;
-  MphHap h0;
-  assemble_entry(d, sg, g, va, vb, 0, boundary, seq, germ, &h0, &err);
-  d.hap0[widx] = h0;
-  for (uint32_t x = 0; x < wo.n_extra; ++x) {
-    MphHap hx;
-    assemble_entry(d, sg, g, va, vb, d.hist[wo.extra_off + x].hap, boundary, seq, germ, &hx, &err);
-    d.hapx[wo.extra_off + x] = hx;
+  const uint32_t cap = d.seq_cap;
+  for (uint32_t x = blockIdx.x * blockDim.x + threadIdx.x; x < n; x += gridDim.x * blockDim.x) {
+    const uint64_t hap = d.hist[x].hap;
+    if (hap == 0) continue;  // a (hap 0, frame != 0) key shares the window's haplotype-0 record
+    const uint32_t code = d.hist_win[x];
+    const MphChunk ch = d.chunks[code >> 5];
+    const MphSegment sg = d.segs[ch.seg];
+    const uint32_t i = ch.i_first + (code & 31u);
+    const uint32_t k = sg.k_first + i * sg.k_stride;
+    const MphGeom g = mph_geom(sg, k);
+    const uint32_t va = mph_var_lb(d.vars, ch.va0, ch.vb1, g.s);
+    const uint32_t vb = mph_var_lb(d.vars, va, ch.vb1, g.e);
+    const bool boundary = i == 0 || i + 1 == sg.n_win || (sg.flags & MPH_SF_HAS_FS);
+    MphHap out;
+    uint32_t err = mph_assemble(sg, g, d.vars, va, vb, d.ref, d.ins_bytes, hap, seq, germ, cap, &out);
+    if (boundary || out.n_som > 0) {
+      const uint32_t off = atomicAdd(&d.counters[CTR_SEQ], 2 * cap);
+      if (off + 2 * cap <= d.seq_cap_bytes) {
+        const uint32_t sl = out.seq_len < cap ? out.seq_len : cap, gl = out.germ_len < cap ? out.germ_len : cap;
+        for (uint32_t t = 0; t < sl; ++t) d.seq[off + t] = seq[t];
+        for (uint32_t t = 0; t < gl; ++t) d.seq[off + cap + t] = germ[t];
+        out.seq_off = off;
+        out.flags |= MPH_HF_SEQ;
+      } else {
+        err |= MPH_E_SEQ_OVERFLOW;
+      }
+    }
+    d.hapx[x] = out;
+    raise(d, err);
   }
-  d.win_flag[widx] = (va != vb || (h0.flags & MPH_HF_STOP) || boundary || wo.n_extra > 0) ? 1 : 0;
-  raise(d, err);
 }
 
 // ------------------------------------------------------------------ K4: stable compaction
@@ -580,10 +585,10 @@ void launch_window_hist(const DeviceBatch& d, cudaStream_t st) {
   if (!d.n_chunks) return;
   k_window_hist<<<(d.n_chunks + K2_WARPS - 1) / K2_WARPS, K2_WARPS * 32, 0, st>>>(d);
   // windows with more distinct haplotypes than a lane table holds (rare): one warp per window
-  k_window_hist_wide<<<148 * 2, K2_WARPS * 32, 0, st>>>(d);
+  k_window_hist_wide<<<148, K2_WARPS * 32, 0, st>>>(d);
 }
 void launch_assemble(const DeviceBatch& d, cudaStream_t st) {
-  if (d.n_chunks) k_assemble<<<(d.n_chunks + 7) / 8, 256, 0, st>>>(d);
+  if (d.n_chunks) k_assemble<<<148 * 8, 128, 0, st>>>(d);  // grid-stride over the key arena (its size lives on the device)
 }
 void launch_compact(const DeviceBatch& d, cudaStream_t st) {
   const uint32_t nb = (d.n_windows + SCAN_THREADS - 1) / SCAN_THREADS;

@@ -30,6 +30,7 @@ struct DeviceBatch {
   const MphSegment* segs = nullptr;
   const MphChunk* chunks = nullptr;
   const uint8_t* ref = nullptr;
+  const uint32_t* stopmap = nullptr;  // 1 bit per ref byte: a stop codon starts here
   // K1 output
   uint64_t* call_S = nullptr;
   uint64_t* call_B = nullptr;
@@ -37,6 +38,7 @@ struct DeviceBatch {
   // K2 output
   MphWinOut* win_out = nullptr;
   MphHist* hist = nullptr;
+  uint32_t* hist_win = nullptr;  // per key: (chunk << 5 | lane) of its window
   uint32_t hist_cap = 0;
   uint32_t* ovf_list = nullptr;  // (chunk << 5 | lane) of windows whose keys overflow a lane table; chunk count must be < 2^27
   // K3 output

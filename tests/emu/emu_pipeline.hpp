@@ -88,8 +88,8 @@ inline PhaseRaw phase(const Batch& b) {
       // K3
       const bool boundary = i == 0 || i + 1 == sg.n_win || (sg.flags & MPH_SF_HAS_FS);
       auto assemble = [&](uint64_t hap, MphHap* out) {
-        if (va == vb) {
-          raw.err |= mph_plain_window(sg, g, b.ref.data(), out);
+        if (hap == 0) {
+          raw.err |= mph_plain_hap(sg, g, b.stopmap.data(), b.ref.data(), vb - va, out);
           return;
         }
         raw.err |= mph_assemble(sg, g, b.vars.data(), va, vb, b.ref.data(), b.ins_bytes.data(), hap, seqbuf.data(), germbuf.data(), b.seq_cap, out);
