@@ -138,6 +138,24 @@ def reference_arm(args, rank, world):
     }))
 
 
+def shard_seed(rank):
+    """Weak scaling: every rank phases its own whole-exome-shaped shard (a different gene range of a larger cohort)."""
+    return SEED + rank
+
+
+def aggregate_over_ranks(dist, device, dev_ms, e2e_ms, windows, read_windows):
+    """Time = max over ranks, work = sum over ranks (no other communication happens on this path)."""
+    import torch
+    vals = torch.tensor([dev_ms, e2e_ms, float(windows), float(read_windows)], dtype=torch.float64, device=device)
+    if dist is None:
+        return dev_ms, e2e_ms, float(windows), float(read_windows)
+    mx = vals.clone()
+    dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    sm = vals.clone()
+    dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+    return mx[0].item(), mx[1].item(), sm[2].item(), sm[3].item()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -175,7 +193,7 @@ def main():
 
     ctx = m.Context(local_rank)
     t0 = time.time()
-    batch = m.Batch.synthetic(n_transcripts=n_tx, coverage=cov, seed=SEED + rank, pin=True)
+    batch = m.Batch.synthetic(n_transcripts=n_tx, coverage=cov, seed=shard_seed(rank), pin=True)
     gen_s = time.time() - t0
     view = batch.view()
 
@@ -234,16 +252,7 @@ def main():
     e2e_step_ms = sum(e2e_ms) / len(e2e_ms)
 
     # ---- max over ranks
-    vals = torch.tensor([dev_ms, e2e_step_ms, float(windows), float(read_windows)], dtype=torch.float64, device="cuda:%d" % local_rank)
-    if dist is not None:
-        mx = vals.clone()
-        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        sm = vals.clone()
-        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        dev_ms_max, e2e_ms_max = mx[0].item(), mx[1].item()
-        windows_all, rw_all = sm[2].item(), sm[3].item()
-    else:
-        dev_ms_max, e2e_ms_max, windows_all, rw_all = dev_ms, e2e_step_ms, float(windows), float(read_windows)
+    dev_ms_max, e2e_ms_max, windows_all, rw_all = aggregate_over_ranks(dist, "cuda:%d" % local_rank, dev_ms, e2e_step_ms, windows, read_windows)
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()

@@ -170,6 +170,13 @@ int mph_run_somatic(mph_ctx* ctx, const char* bam_path, const char* ref_path, co
                     const char* fasta_out_path, const char* tsv_path, const char* normal_path, uint32_t window_len,
                     int unsupported_allele_warning_only);
 
+/* the same over several devices of one box: genes are split into n_ctx contiguous ranges balanced by
+ * read count, every context phases its range on its own host thread, records are concatenated in
+ * range order. No collective is involved (shards are independent). */
+int mph_run_somatic_multi(mph_ctx* const* ctxs, int n_ctx, const char* bam_path, const char* ref_path, const char* variants_path,
+                          const char* gtf_path, const char* fasta_out_path, const char* tsv_path, const char* normal_path,
+                          uint32_t window_len, int unsupported_allele_warning_only);
+
 /* ---- synthetic workload (bench only): packs an exome-shaped batch natively ------------------ */
 typedef struct {
   uint64_t seed;

@@ -55,7 +55,7 @@ class BatchView(C.Structure):
 EXPORTS = ["mph_ctx_create", "mph_ctx_destroy", "mph_last_error", "mph_packer_create", "mph_packer_destroy", "mph_packer_add_gene",
            "mph_packer_finish", "mph_batch_destroy", "mph_batch_get_view", "mph_phase_batch", "mph_batch_upload", "mph_phase_resident",
            "mph_phase_collect", "mph_ctx_timing", "mph_result_destroy", "mph_result_count", "mph_result_get", "mph_result_write",
-           "mph_run_somatic", "mph_synth_batch", "mph_synth_write_files"]
+           "mph_run_somatic", "mph_run_somatic_multi", "mph_synth_batch", "mph_synth_write_files"]
 
 _lib = None
 
@@ -89,6 +89,7 @@ def load():
     lib.mph_result_get.argtypes = [P, C.c_uint64, C.POINTER(Record)]
     lib.mph_result_write.argtypes = [P, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
     lib.mph_run_somatic.argtypes = [P] + [C.c_char_p] * 7 + [C.c_uint32, C.c_int]
+    lib.mph_run_somatic_multi.argtypes = [C.POINTER(P), C.c_int] + [C.c_char_p] * 7 + [C.c_uint32, C.c_int]
     lib.mph_synth_batch.argtypes = [C.POINTER(SynthParams), C.c_uint32, C.c_int, C.POINTER(P)]
     lib.mph_synth_write_files.argtypes = [C.POINTER(SynthParams), C.c_uint32, C.c_char_p]
     _lib = lib
@@ -153,6 +154,13 @@ class Context:
         t = Timing()
         _check(self.lib.mph_ctx_timing(self.h, C.byref(t)))
         return t.as_dict()
+
+
+def run_somatic_multi(contexts, bam, ref, variants, gtf, fasta_out, tsv, normal_out, window_len=27, warn_only=False):
+    """`microphaser somatic` sharded by gene range over several devices (one Context each); ordered concatenation, no collective."""
+    arr = (C.c_void_p * len(contexts))(*[c.h for c in contexts])
+    enc = [s.encode() for s in (bam, ref, variants, gtf, fasta_out, tsv, normal_out)]
+    _check(load().mph_run_somatic_multi(arr, len(contexts), *enc, window_len, int(warn_only)), contexts[0].h)
 
 
 class Batch:

@@ -576,60 +576,102 @@ int mph_result_write(const mph_result* r, int fd_fasta, int fd_tsv, int fd_norma
   });
 }
 
+// shared by the single- and multi-device file drivers
+static void run_somatic_files(const std::vector<mph_ctx*>& ctxs, const char* bam_path, const char* ref_path, const char* variants_path,
+                              const char* gtf_path, const char* fasta_out_path, const char* tsv_path, const char* normal_path,
+                              uint32_t window_len, int warn_only) {
+  mphio::BamFile bam(bam_path);
+  mphio::VcfFile vcf(variants_path);
+  mphio::FastaIndexed fasta(ref_path);
+  // the reference creates its output files before it starts phasing (src/main.rs:79-85)
+  auto open_out = [](const char* p) -> int {
+    if (std::string(p) == "-") return 1;
+    FILE* f = fopen(p, "wb");
+    if (!f) throw std::runtime_error(std::string("cannot create ") + p);
+    int fd = dup(fileno(f));
+    fclose(f);
+    return fd;
+  };
+  const int fd_fa = open_out(fasta_out_path), fd_tsv = open_out(tsv_path), fd_n = open_out(normal_path);
+  auto close_all = [&] {
+    if (fd_fa > 2) close(fd_fa);
+    if (fd_tsv > 2) close(fd_tsv);
+    if (fd_n > 2) close(fd_n);
+  };
+  try {
+    IngestOptions io;
+    io.window_len = window_len;
+    io.warn_only = warn_only != 0;
+    std::ifstream gf;
+    std::istream* gin = &std::cin;
+    if (std::string(gtf_path) != "-") {
+      gf.open(gtf_path);
+      if (!gf) throw std::runtime_error(std::string("cannot open ") + gtf_path);
+      gin = &gf;
+    }
+    ReadBuffer reads(bam);
+    std::vector<GeneInput> genes = ingest_genes(*gin, reads, vcf, fasta, io);
+    // one contiguous gene range per device, no exchange between shards
+    const size_t n_dev = ctxs.size();
+    const std::vector<size_t> cut = partition_genes(genes, n_dev);
+    std::vector<std::unique_ptr<mph_batch>> batches(n_dev);
+    std::vector<mph_result*> results(n_dev, nullptr);
+    std::vector<std::exception_ptr> errs(n_dev);
+    auto shard = [&](size_t k) {
+      try {
+        Packer packer(window_len);
+        pack_genes(genes, cut[k], cut[k + 1], packer);
+        batches[k].reset(new mph_batch);
+        batches[k]->b = std::move(packer.batch());
+        finish_batch(batches[k].get(), false);
+        upload(ctxs[k], batches[k].get());
+        run_kernels(ctxs[k]);
+        collect(ctxs[k], &results[k]);
+        ctxs[k]->cur = nullptr;
+      } catch (...) {
+        errs[k] = std::current_exception();
+      }
+    };
+    if (n_dev == 1) {
+      shard(0);
+    } else {
+      std::vector<std::thread> th;
+      for (size_t k = 0; k < n_dev; ++k) th.emplace_back(shard, k);
+      for (auto& t : th) t.join();
+    }
+    std::vector<std::unique_ptr<mph_result>> holders;
+    for (auto r : results) holders.emplace_back(r);
+    for (auto& e : errs)
+      if (e) std::rethrow_exception(e);
+    int hw = 0;
+    for (size_t k = 0; k < n_dev; ++k)  // ordered concatenation; the TSV header goes out with the first row only
+      if (mph_result_write(results[k], fd_fa, fd_tsv, fd_n, &hw) != MPH_OK) throw std::runtime_error(g_last_error);
+  } catch (...) {
+    close_all();
+    throw;
+  }
+  close_all();
+}
+
 int mph_run_somatic(mph_ctx* ctx, const char* bam_path, const char* ref_path, const char* variants_path, const char* gtf_path,
                     const char* fasta_out_path, const char* tsv_path, const char* normal_path, uint32_t window_len, int warn_only) {
   if (!ctx || !bam_path || !ref_path || !variants_path || !gtf_path || !fasta_out_path || !tsv_path || !normal_path)
     return fail(ctx, MPH_ERR_INPUT, "null argument");
   if (window_len == 0 || window_len % 3 != 0) return fail(ctx, MPH_ERR_UNSUPPORTED, "window length must be a positive multiple of 3");
   return guarded(ctx, [&] {
-    mphio::BamFile bam(bam_path);
-    mphio::VcfFile vcf(variants_path);
-    mphio::FastaIndexed fasta(ref_path);
-    // the reference creates its output files before it starts phasing (src/main.rs:79-85)
-    auto open_out = [](const char* p) -> int {
-      if (std::string(p) == "-") return 1;
-      FILE* f = fopen(p, "wb");
-      if (!f) throw std::runtime_error(std::string("cannot create ") + p);
-      int fd = dup(fileno(f));
-      fclose(f);
-      return fd;
-    };
-    const int fd_fa = open_out(fasta_out_path), fd_tsv = open_out(tsv_path), fd_n = open_out(normal_path);
-    auto close_all = [&] {
-      if (fd_fa > 2) close(fd_fa);
-      if (fd_tsv > 2) close(fd_tsv);
-      if (fd_n > 2) close(fd_n);
-    };
-    try {
-      IngestOptions io;
-      io.window_len = window_len;
-      io.warn_only = warn_only != 0;
-      Packer packer(window_len);
-      std::ifstream gf;
-      std::istream* gin = &std::cin;
-      if (std::string(gtf_path) != "-") {
-        gf.open(gtf_path);
-        if (!gf) throw std::runtime_error(std::string("cannot open ") + gtf_path);
-        gin = &gf;
-      }
-      ingest(*gin, bam, vcf, fasta, io, packer);
-      mph_batch mb;
-      mb.b = std::move(packer.batch());
-      finish_batch(&mb, false);
-      mph_result* res = nullptr;
-      upload(ctx, &mb);
-      run_kernels(ctx);
-      collect(ctx, &res);
-      std::unique_ptr<mph_result> holder(res);
-      ctx->cur = nullptr;
-      int hw = 0;
-      int rc = mph_result_write(res, fd_fa, fd_tsv, fd_n, &hw);
-      if (rc != MPH_OK) throw std::runtime_error(g_last_error);
-    } catch (...) {
-      close_all();
-      throw;
-    }
-    close_all();
+    run_somatic_files({ctx}, bam_path, ref_path, variants_path, gtf_path, fasta_out_path, tsv_path, normal_path, window_len, warn_only);
+  });
+}
+
+int mph_run_somatic_multi(mph_ctx* const* ctxs, int n_ctx, const char* bam_path, const char* ref_path, const char* variants_path,
+                          const char* gtf_path, const char* fasta_out_path, const char* tsv_path, const char* normal_path,
+                          uint32_t window_len, int warn_only) {
+  if (!ctxs || n_ctx < 1 || !bam_path || !ref_path || !variants_path || !gtf_path || !fasta_out_path || !tsv_path || !normal_path)
+    return fail(nullptr, MPH_ERR_INPUT, "null argument");
+  if (window_len == 0 || window_len % 3 != 0) return fail(ctxs[0], MPH_ERR_UNSUPPORTED, "window length must be a positive multiple of 3");
+  return guarded(ctxs[0], [&] {
+    run_somatic_files(std::vector<mph_ctx*>(ctxs, ctxs + n_ctx), bam_path, ref_path, variants_path, gtf_path, fasta_out_path, tsv_path,
+                      normal_path, window_len, warn_only);
   });
 }
 

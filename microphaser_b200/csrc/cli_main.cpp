@@ -52,15 +52,31 @@ int main(int argc, char** argv) {
   const std::string tsv = opt.count("tsv") ? opt["tsv"] : "info.tsv";
   const std::string nrm = opt.count("normal-output") ? opt["normal-output"] : "normal.fasta";
   const uint32_t wl = opt.count("window-len") ? uint32_t(strtoul(opt["window-len"].c_str(), nullptr, 10)) : 27;
-  const char* dev = getenv("MPH_DEVICE");
-  mph_ctx* ctx = nullptr;
-  int rc = mph_ctx_create(dev ? atoi(dev) : 0, &ctx);
-  if (rc != MPH_OK) { fprintf(stderr, "microphaser: %s\n", mph_last_error(nullptr)); return 1; }
-  rc = mph_run_somatic(ctx, pos[0].c_str(), opt["ref"].c_str(), opt["variants"].c_str(), "-", "-", tsv.c_str(), nrm.c_str(), wl, warn_only);
+  // device selection stays out of the (frozen) command line: MPH_DEVICES=0,1,2,3 shards the genes over several GPUs
+  std::vector<int> devices;
+  if (const char* dl = getenv("MPH_DEVICES")) {
+    for (const char* p = dl; *p;) {
+      devices.push_back(atoi(p));
+      while (*p && *p != ',') ++p;
+      if (*p == ',') ++p;
+    }
+  }
+  if (devices.empty()) devices.push_back(getenv("MPH_DEVICE") ? atoi(getenv("MPH_DEVICE")) : 0);
+  std::vector<mph_ctx*> ctxs;
+  int rc = MPH_OK;
+  for (int dv : devices) {
+    mph_ctx* c = nullptr;
+    rc = mph_ctx_create(dv, &c);
+    if (rc != MPH_OK) { fprintf(stderr, "microphaser: %s\n", mph_last_error(nullptr)); return 1; }
+    ctxs.push_back(c);
+  }
+  mph_ctx* ctx = ctxs[0];
+  rc = mph_run_somatic_multi(ctxs.data(), int(ctxs.size()), pos[0].c_str(), opt["ref"].c_str(), opt["variants"].c_str(), "-", "-", tsv.c_str(),
+                             nrm.c_str(), wl, warn_only);
   int status = 0;
   if (rc == MPH_ERR_PANIC) { fprintf(stderr, "thread 'main' panicked at '%s'\n", mph_last_error(ctx)); status = 101; }
   else if (rc == MPH_ERR_UNSUPPORTED) { fprintf(stderr, "microphaser: input needs the serial replay path, which is not implemented: %s\n", mph_last_error(ctx)); status = 3; }
   else if (rc != MPH_OK) { fprintf(stderr, "%s\n", mph_last_error(ctx)); status = 1; }
-  mph_ctx_destroy(ctx);
+  for (auto c : ctxs) mph_ctx_destroy(c);
   return status;
 }

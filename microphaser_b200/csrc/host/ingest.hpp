@@ -273,24 +273,32 @@ struct IngestOptions {
   uint32_t min_mapq = 5;  // somatic: rec.mapq() < 5 is skipped (:910); normal mode has no filter
 };
 
-// Builds the batch for every protein-coding gene of the GTF, in GTF order.
-inline void ingest(std::istream& gtf, mphio::BamFile& bam, mphio::VcfFile& vcf, mphio::FastaIndexed& fasta, const IngestOptions& opt,
-                   Packer& packer) {
+// Everything phase_gene fetches for one gene (:894-942), held until it is packed.
+struct GeneInput {
+  HostGene gene;
+  std::vector<HostRead> reads;  // point into records owned by the ReadBuffer
+  uint32_t max_read_len = 0;
+  std::vector<std::vector<HostVariant>> sites;
+  std::vector<uint8_t> refseq;
+};
+
+// Streams the GTF and fetches reads / variants / reference for every protein-coding gene, in GTF order.
+inline std::vector<GeneInput> ingest_genes(std::istream& gtf, ReadBuffer& reads, mphio::VcfFile& vcf, mphio::FastaIndexed& fasta,
+                                           const IngestOptions& opt) {
   std::vector<ParsedGene> genes = read_gtf(gtf);
-  ReadBuffer reads(bam);
   VariantBuffer variants(vcf);
+  std::vector<GeneInput> out;
   for (auto& pg : genes) {
     if (pg.biotype != "protein_coding") continue;  // :1964
-    const HostGene& g = pg.gene;
-    std::vector<uint8_t> refseq;
-    fasta.fetch(g.chrom, g.start, uint64_t(g.end) + 100, refseq);  // end_overflow (:895-901)
+    GeneInput gi;
+    gi.gene = std::move(pg.gene);
+    const HostGene& g = gi.gene;
+    fasta.fetch(g.chrom, g.start, uint64_t(g.end) + 100, gi.refseq);  // end_overflow (:895-901)
     const auto& rb = reads.fetch(g.chrom, g.start, g.end);
-    std::vector<HostRead> hr;
-    hr.reserve(rb.size());
-    uint32_t max_read_len = 0;
+    gi.reads.reserve(rb.size());
     for (auto& rec : rb) {
       if (rec->mapq < opt.min_mapq) continue;
-      if (rec->l_seq > max_read_len) max_read_len = rec->l_seq;
+      if (rec->l_seq > gi.max_read_len) gi.max_read_len = rec->l_seq;
       HostRead h;
       h.start = uint32_t(rec->pos);
       h.end = uint32_t(rec->end_pos());
@@ -300,16 +308,48 @@ inline void ingest(std::istream& gtf, mphio::BamFile& bam, mphio::VcfFile& vcf, 
       h.cigar = rec->cigar.data();
       h.n_cigar = uint32_t(rec->cigar.size());
       h.qname_hash = fnv1a(rec->qname);
-      hr.push_back(h);
+      gi.reads.push_back(h);
     }
     // variant_tree.insert(rec.pos(), Variant::new(rec)): a later record at the same position replaces the earlier (:937)
     std::map<uint32_t, std::vector<HostVariant>> tree;
     for (auto& rec : variants.fetch(g.chrom, g.start, g.end)) tree[uint32_t(rec.pos)] = alleles_of(vcf, rec, opt.warn_only);
-    std::vector<std::vector<HostVariant>> sites;
     for (auto& kv : tree)
-      if (!kv.second.empty()) sites.push_back(std::move(kv.second));
-    packer.add_gene(g, hr, max_read_len, sites, std::move(refseq));
+      if (!kv.second.empty()) gi.sites.push_back(std::move(kv.second));
+    out.push_back(std::move(gi));
   }
+  return out;
+}
+
+// Contiguous gene ranges balanced by read count, one per device: shard k is
+// genes [cut[k], cut[k+1]). Shards are independent; their records are concatenated in shard order.
+inline std::vector<size_t> partition_genes(const std::vector<GeneInput>& genes, size_t n_shards) {
+  std::vector<size_t> cut(n_shards + 1, genes.size());
+  cut[0] = 0;
+  uint64_t total = 0;
+  for (auto& g : genes) total += g.reads.size() + 1;
+  uint64_t acc = 0;
+  size_t k = 1;
+  for (size_t i = 0; i < genes.size() && k < n_shards; ++i) {
+    acc += genes[i].reads.size() + 1;
+    while (k < n_shards && acc * n_shards >= total * k) cut[k++] = i + 1;
+  }
+  return cut;
+}
+
+inline void pack_genes(std::vector<GeneInput>& genes, size_t lo, size_t hi, Packer& packer) {
+  for (size_t i = lo; i < hi; ++i) {
+    GeneInput& gi = genes[i];
+    packer.add_gene(gi.gene, gi.reads, gi.max_read_len, gi.sites, std::move(gi.refseq));
+    std::vector<HostRead>().swap(gi.reads);
+  }
+}
+
+// Builds the batch for every protein-coding gene of the GTF, in GTF order.
+inline void ingest(std::istream& gtf, mphio::BamFile& bam, mphio::VcfFile& vcf, mphio::FastaIndexed& fasta, const IngestOptions& opt,
+                   Packer& packer) {
+  ReadBuffer reads(bam);
+  std::vector<GeneInput> genes = ingest_genes(gtf, reads, vcf, fasta, opt);
+  pack_genes(genes, 0, genes.size(), packer);
 }
 
 }  // namespace mph

@@ -109,3 +109,31 @@ def test_wide_histogram_kernel_matches_golden(product, case, tmp_path, monkeypat
     assert res.returncode == 0, res.stderr.decode()
     for name in sorted(os.listdir(os.path.join(d, "expected"))):
         assert open(tmp_path / name, "rb").read() == open(os.path.join(d, "expected", name), "rb").read(), name
+
+
+def test_multi_device_sharding_matches_oracle(product, oracle_bin, tmp_path):
+    """mph_run_somatic_multi: genes split into contiguous ranges over several contexts (two GPUs when the box has
+    them, else two contexts on GPU 0); ordered concatenation must equal the oracle's single-process output."""
+    import torch
+    import microphaser_b200 as m
+    d = str(tmp_path / "in")
+    synth.generate(d, synth.Params(seed=4242, n_genes=7, coverage=30.0, indel_frac=0.1, multiallelic_frac=0.1))
+    o, p = tmp_path / "o", tmp_path / "p"
+    o.mkdir()
+    p.mkdir()
+    ro = run_cli(oracle_bin, d, str(o))
+    assert ro.returncode == 0, ro.stderr.decode()
+    devs = [0, 1, 0] if torch.cuda.device_count() >= 2 else [0, 0, 0]
+    ctxs = [m.Context(x) for x in devs]
+    try:
+        m.run_somatic_multi(ctxs, os.path.join(d, "reads.bam"), os.path.join(d, "ref.fa"), os.path.join(d, "variants.vcf"),
+                            os.path.join(d, "annotation.gtf"), str(p / "out.fa"), str(p / "out.tsv"), str(p / "out.normal.fa"))
+    except m.MphError as e:
+        if e.code == m.MPH_ERR_UNSUPPORTED:
+            pytest.skip(str(e))
+        raise
+    finally:
+        for c in ctxs:
+            c.close()
+    assert read_outputs(str(o)) == read_outputs(str(p))
+    assert len(read_outputs(str(o))["out.tsv"]) > 0
