@@ -1,0 +1,3 @@
+nvidia-smi -L
+python -m pytest tests -m gpu -x -q -k "multi_device or golden" 2>&1 | tail -3
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_exome_2gpu.json 2> gpurun_out/bench_exome_2gpu.err; echo rc=$?; tail -c 1500 gpurun_out/bench_exome_2gpu.json; tail -3 gpurun_out/bench_exome_2gpu.err

@@ -97,6 +97,7 @@ struct mph_ctx {
   DevBuf<unsigned long long> sums;
   mph_timing timing = {};
   bool have_h2d_time = false;
+  PhaseRaw raw;  // download buffers, reused across calls (no page faults after the first)
 };
 
 namespace {
@@ -222,7 +223,7 @@ void run_kernels(mph_ctx* c) {
 
 void collect(mph_ctx* c, mph_result** out) {
   const Batch& b = c->cur->b;
-  PhaseRaw raw;
+  PhaseRaw& raw = c->raw;
   uint32_t ctr[8];
   for (int attempt = 0;; ++attempt) {
     CU(cudaMemcpyAsync(ctr, c->counters.p, sizeof ctr, cudaMemcpyDeviceToHost, c->stream));
@@ -274,7 +275,9 @@ void collect(mph_ctx* c, mph_result** out) {
   std::unique_ptr<mph_result> res(new mph_result);
   ResidueStats st;
   const uint32_t n_tx = uint32_t(b.txs.size());
+  // host threads for the residue: MPH_HOST_THREADS, else all cores (a multi-GPU launcher gives every rank its share)
   unsigned n_thr = std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 32u);
+  if (const char* ht = getenv("MPH_HOST_THREADS")) n_thr = std::max(1, atoi(ht));
   if (n_tx < 256) n_thr = 1;
   std::vector<std::vector<OutRecord>> parts(n_thr);
   std::vector<ResidueStats> pstats(n_thr);

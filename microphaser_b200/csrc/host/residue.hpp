@@ -8,6 +8,7 @@
 // (:1465-1488), record construction (:720-837), the emission predicate (:839-875) and the
 // splice-junction merge (:1497-1908, src/common.rs:376-568).
 #pragma once
+#include <charconv>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -180,7 +181,13 @@ class Residue {
   using FrameFreqs = std::map<uint64_t, std::pair<double, bool>>;
   struct HapSeq {  // HaplotypeSeq (:141-145): only the record is ever read
     InfoRecord rec;
-    bool partial = false;  // sequences were not shipped (window is not at an exon boundary)
+    // A haplotype whose mutant and normal sequence are both the plain reference window cannot produce a
+    // merged record on its own (:1887 writes only mt != wt); its strings are built only if the other side
+    // of the junction carries a variant.
+    bool lazy = false;
+    const MphSegment* sg = nullptr;
+    const MphHap* h = nullptr;
+    uint32_t k = 0, va = 0, nv = 0;
   };
 
   struct Key {
@@ -203,7 +210,16 @@ class Residue {
   }
 
   // print_haplotypes (:353-879) with the matrix scan and the sequence walk replaced by device results
-  std::vector<HapSeq> print(uint32_t t, const MphSegment& sg, uint32_t k, size_t iwi, uint64_t frame_in, FrameFreqs& ff,
+  // what print_haplotypes hands back (:878): the haplotype list is materialised only for windows a
+  // splice merge can read (exon boundaries); elsewhere only its length matters (:1437)
+  struct HapList {
+    std::vector<HapSeq> v;
+    size_t n = 0;
+    bool partial = false;
+    bool empty() const { return n == 0; }
+  };
+
+  HapList print(uint32_t t, const MphSegment& sg, uint32_t k, size_t iwi, uint64_t frame_in, FrameFreqs& ff,
                             bool is_first_exon_window, std::vector<OutRecord>& out) {
     const TxMeta& tm = b_.txs[t];
     const GeneMeta& gm = b_.genes[tm.gene];
@@ -218,7 +234,10 @@ class Residue {
     const bool is_short_exon = (sg.flags & MPH_SF_SHORT) != 0;
     uint64_t frame = frame_in;
     // histogram for this frame (:383-411) from the fine keys (hap, obs.frame.0, obs.frame.1 != 0)
-    std::map<std::pair<uint64_t, uint64_t>, Key> keys;
+    // device keys arrive sorted by (hap, obs.frame.0, obs.frame.1 != 0); projecting them onto this frame's
+    // (hap, frame) key keeps the order, equal keys become adjacent -> a small sorted vector, no tree
+    Key keybuf[40];
+    size_t n_keys = 0;
     uint64_t frame_depth = 0;
     auto add = [&](uint64_t hap, uint32_t fr, uint64_t count, const MphHap* info) {
       const uint64_t f0 = fr & 0x7FFFFFFFu;
@@ -226,9 +245,12 @@ class Residue {
       if (frame > 0 && f0 != frame && f1nz) return;
       frame_depth += count;
       const uint64_t kf = frame > 0 ? frame : f0;
-      auto it = keys.find({hap, kf});
-      if (it == keys.end()) keys[{hap, kf}] = Key{hap, kf, count, info};
-      else it->second.count += count;
+      for (size_t q = n_keys; q-- > 0;) {
+        if (keybuf[q].hap == hap && keybuf[q].frame == kf) { keybuf[q].count += count; return; }
+        if (keybuf[q].hap != hap) break;
+      }
+      if (n_keys == 40) throw Unsupported("more than 40 haplotype keys in one window");
+      keybuf[n_keys++] = Key{hap, kf, count, info};
     };
     if (wo.c0 > 0) add(0, 0, wo.c0, &h0);
     for (uint32_t x = 0; x < wo.n_extra; ++x) {
@@ -236,20 +258,27 @@ class Residue {
       const MphHap* info = e.hap == 0 ? &h0 : &raw_.hapx[wo.extra_off + x];
       add(e.hap, e.frame, e.count, info);
     }
+    // within one hap the projected frames may be out of order only when frame > 0 collapses them (then they are equal)
+    for (size_t q = 1; q < n_keys; ++q) {
+      Key kq = keybuf[q];
+      size_t z = q;
+      while (z > 0 && (keybuf[z - 1].hap > kq.hap || (keybuf[z - 1].hap == kq.hap && keybuf[z - 1].frame > kq.frame))) { keybuf[z] = keybuf[z - 1]; --z; }
+      keybuf[z] = kq;
+    }
     const bool has_frameshift = frame > 0;
-    if (keys.empty()) keys[{0, 0}] = Key{0, 0, 0, &h0};
+    if (n_keys == 0) keybuf[n_keys++] = Key{0, 0, 0, &h0};
     if (trace_) {  // same line format as the oracle's MPH_ORACLE_TRACE
       fprintf(trace_, "W\t%s\t%llu\t%llu\t%llu\t%u\t%llu\t%u", tm.id.c_str(), (unsigned long long)g.s, (unsigned long long)g.e,
               (unsigned long long)frame_in, wo.depth, (unsigned long long)frame_depth, nv);
-      for (auto& kv : keys)
-        fprintf(trace_, "\t%llu:%llu:%llu", (unsigned long long)kv.second.hap, (unsigned long long)kv.second.frame, (unsigned long long)kv.second.count);
+      for (size_t q = 0; q < n_keys; ++q)
+        fprintf(trace_, "\t%llu:%llu:%llu", (unsigned long long)keybuf[q].hap, (unsigned long long)keybuf[q].frame, (unsigned long long)keybuf[q].count);
       fputc('\n', trace_);
     }
-    std::vector<HapSeq> haplotypes_vec;
+    HapList haplotypes_vec;
     uint64_t shift_in_window = 0;
     const bool boundary = is_boundary(sg, k);
-    for (auto& kv : keys) {
-      const Key& key = kv.second;
+    for (size_t q = 0; q < n_keys; ++q) {
+      const Key& key = keybuf[q];
       const MphHap& h = *key.info;
       const uint64_t haplotype_frame = key.frame;
       const bool indel = (h.flags & MPH_HF_INDEL) != 0, insertion = (h.flags & MPH_HF_INSERTION) != 0;
@@ -288,7 +317,9 @@ class Residue {
       const bool emit = (h.n_som > 0 || has_frameshift) && !is_short_exon && !seqs_equal && frame_frequency > 0.0 && (!stop_gain || has_frameshift);
       // bytes are needed for emitted records and for the windows a splice merge can read (:1497-1908);
       // an indel haplotype also needs them for the stop-codon side condition (:707)
-      const bool need_rec = emit || boundary;
+      // a boundary haplotype that is the plain reference on both streams is kept lazily (see HapSeq)
+      const bool lazy = boundary && !emit && (nv == 0 || key.hap == 0) && seqs_equal && !germ_cleared;
+      const bool need_rec = (emit || boundary) && !lazy;
       const bool want_seq = need_rec || (stop_gain && indel);
       std::string seq, germline_seq;
       if (want_seq) {
@@ -334,49 +365,36 @@ class Residue {
       // meta information (:720-769)
       InfoRecord rec;
       rec.tx = t;
-      if (need_rec) {
-        uint32_t n_variantsites = 0, n_som_variantsites = 0;
-        std::vector<std::string> s_pc, g_pc, s_pos, g_pos, sites;
-        for (uint32_t c = 0; c < nv; ++c) {
-          const MphVar& v = b_.vars[va + c];
-          if (c < h.n_prof && c < 32) {
-            const unsigned code = unsigned((h.profile >> (2 * c)) & 3);
-            if (code == 2) { s_pos.push_back(std::to_string(uint64_t(v.pos) + 1)); s_pc.push_back(b_.var_prot[va + c]); }
-            else if (code == 1) { g_pos.push_back(std::to_string(uint64_t(v.pos) + 1)); g_pc.push_back(b_.var_prot[va + c]); }
-          }
-          if (c == 0 || v.pos != b_.vars[va + c - 1].pos) {
-            ++n_variantsites;
-            sites.push_back(std::to_string(uint64_t(v.pos) + 1));
-            if (!(v.flags & MPH_VF_GERMLINE)) ++n_som_variantsites;
-          }
-        }
-        // the id of a record that is not written is never read (IDRecord::update derives a new one)
-        if (emit) rec.id = mphfmt::record_id(reinterpret_cast<const uint8_t*>(seq.data()), seq.size(), tm.id, g.s, rev ? 'R' : 'F');
+      if (need_rec || lazy) {
         rec.offset = g.spos == 0 ? uint64_t(g.s) + 1 : uint64_t(g.s) + 1 + g.gap;
         rec.frame = frame;
         rec.freq = frame_frequency;
         rec.depth = depth;
-        rec.nvar = h.n_var;
-        rec.nsomatic = h.n_som;
-        rec.nvariant_sites = n_variantsites;
-        rec.nsomvariant_sites = n_som_variantsites;
-        rec.variant_sites = detail::join_bar(sites);
-        rec.somatic_positions = detail::join_bar(s_pos);
-        rec.somatic_aa_change = detail::join_bar(s_pc);
-        rec.germline_positions = detail::join_bar(g_pos);
-        rec.germline_aa_change = detail::join_bar(g_pc);
+      }
+      if (need_rec) {
+        fill_meta(rec, va, nv, h);
+        // the id of a record that is not written is never read (IDRecord::update derives a new one)
+        if (emit) rec.id = mphfmt::record_id(reinterpret_cast<const uint8_t*>(seq.data()), seq.size(), tm.id, g.s, rev ? 'R' : 'F');
         rec.normal_sequence = normal_peptide;
         rec.mutant_sequence = neopeptide;
       }
       if (!remove_peptide || frame == 0) {
-        HapSeq hs;
-        hs.partial = !boundary;
+        InfoRecord rec_for_merge;
+        if (boundary) rec_for_merge = rec;
+        haplotypes_vec.n += 1;
         if (boundary) {
-          hs.rec = rec;
-          hs.rec.normal_sequence = germline_seq;
-          hs.rec.mutant_sequence = seq;
+          HapSeq hs;
+          hs.rec = std::move(rec_for_merge);
+          if (lazy) {
+            hs.lazy = true; hs.sg = &sg; hs.h = &h; hs.k = k; hs.va = va; hs.nv = nv;
+          } else {
+            hs.rec.normal_sequence = germline_seq;
+            hs.rec.mutant_sequence = seq;
+          }
+          haplotypes_vec.v.push_back(std::move(hs));
+        } else {
+          haplotypes_vec.partial = true;
         }
-        haplotypes_vec.push_back(std::move(hs));
       }
       if (emit) {
         OutRecord o;
@@ -386,12 +404,70 @@ class Residue {
           if (g.spos == 1) { o.wt = slice(germline_seq, g.gap, germline_seq.size()); o.has_wt = true; }
           else if (g.spos == 0) { o.wt = slice(germline_seq, 0, this_window_len); o.has_wt = true; }
         }
-        o.info = rec;
+        o.info = std::move(rec);
         out.push_back(std::move(o));
       }
     }
     (void)gm;
     return haplotypes_vec;
+  }
+
+  // variant-site metadata of one haplotype (:720-769)
+  void fill_meta(InfoRecord& rec, uint32_t va, uint32_t nv, const MphHap& h) const {
+    uint32_t n_variantsites = 0, n_som_variantsites = 0;
+    std::string s_pc, g_pc, s_pos, g_pos, sites;
+    bool fs = true, fg = true, fsite = true;
+    char buf[24];
+    auto put = [&](std::string& dst, bool& first, uint64_t v) {
+      if (!first) dst.push_back('|');
+      first = false;
+      auto r = std::to_chars(buf, buf + sizeof buf, v);
+      dst.append(buf, r.ptr);
+    };
+    bool fspc = true, fgpc = true;
+    for (uint32_t c = 0; c < nv; ++c) {
+      const MphVar& v = b_.vars[va + c];
+      if (c < h.n_prof && c < 32) {
+        const unsigned code = unsigned((h.profile >> (2 * c)) & 3);
+        if (code == 2) {
+          put(s_pos, fs, uint64_t(v.pos) + 1);
+          if (!fspc) s_pc.push_back('|');
+          fspc = false;
+          s_pc += b_.var_prot[va + c];
+        } else if (code == 1) {
+          put(g_pos, fg, uint64_t(v.pos) + 1);
+          if (!fgpc) g_pc.push_back('|');
+          fgpc = false;
+          g_pc += b_.var_prot[va + c];
+        }
+      }
+      if (c == 0 || v.pos != b_.vars[va + c - 1].pos) {
+        ++n_variantsites;
+        put(sites, fsite, uint64_t(v.pos) + 1);
+        if (!(v.flags & MPH_VF_GERMLINE)) ++n_som_variantsites;
+      }
+    }
+    rec.nvar = h.n_var;
+    rec.nsomatic = h.n_som;
+    rec.nvariant_sites = n_variantsites;
+    rec.nsomvariant_sites = n_som_variantsites;
+    rec.variant_sites = std::move(sites);
+    rec.somatic_positions = std::move(s_pos);
+    rec.somatic_aa_change = std::move(s_pc);
+    rec.germline_positions = std::move(g_pos);
+    rec.germline_aa_change = std::move(g_pc);
+  }
+
+  // builds the strings of a lazily kept boundary haplotype (plain reference window on both streams)
+  void materialize(HapSeq& hs) const {
+    if (!hs.lazy) return;
+    const MphSegment& sg = *hs.sg;
+    const MphGeom g = mph_geom(sg, hs.k);
+    if (g.s < sg.ref_pos0 || uint64_t(g.e) - sg.ref_pos0 > sg.ref_len) throw Fatal("slice index out of range: refseq");
+    fill_meta(hs.rec, hs.va, hs.nv, *hs.h);
+    hs.rec.mutant_sequence.assign(reinterpret_cast<const char*>(b_.ref.data()) + sg.ref_off + (g.s - sg.ref_pos0), g.e - g.s);
+    hs.rec.normal_sequence = hs.rec.mutant_sequence;
+    hs.lazy = false;
   }
 
   static bool is_boundary(const MphSegment& sg, uint32_t k) {
@@ -410,6 +486,7 @@ class Residue {
     if (fwd) frameshifts[0] = 0;
     else frameshifts[gm.end] = 0;
     std::vector<HapSeq> prev_hap_vec, hap_vec;
+    bool prev_partial = false, hap_partial = false;  // the list came from a window whose haplotypes were not materialised
     FrameFreqs ff;
     ff[0] = {1.0, false};
     uint64_t exon_rest = 0;
@@ -494,8 +571,8 @@ class Residue {
             }
             auto res = print(t, sg, k, iwi, frameshift, ff, is_first_exon_window, out);
             if (res.empty() || !ff.count(frameshift)) stopped_frameshift = key;
-            if (exon_rest < 3 && (!is_short_exon || is_first_exon) && !has_frameshift) prev_hap_vec = std::move(res);
-            else hap_vec = std::move(res);
+            if (exon_rest < 3 && (!is_short_exon || is_first_exon) && !has_frameshift) { prev_hap_vec = std::move(res.v); prev_partial = res.partial; }
+            else { hap_vec = std::move(res.v); hap_partial = res.partial; }
             if (frameshift != 0 && ff.count(frameshift) && ff.at(frameshift).first == 0.0) stopped_frameshift = key;
           }
         }
@@ -519,6 +596,10 @@ class Residue {
         }
         const bool at_splice_side = fwd ? offset - current_exon_offset == sg.exon_start
                                         : offset + exon_window_len + current_exon_offset == sg.exon_end;
+        if (at_splice_side && !is_first_exon) {
+          if (prev_partial || hap_partial) throw Unsupported("transcript " + tm.id + ": splice merge needs a window that is not at an exon boundary");
+          prev_partial = hap_partial = false;
+        }
         if (at_splice_side && !is_first_exon)
           splice_merge(t, sg, offset, is_short_exon, is_last_exon, is_last_exon_window, exon_rest, frameshifts, ff, hap_vec, prev_hap_vec, out);
         (void)window_len;
@@ -547,6 +628,18 @@ class Residue {
     const bool fwd = !tm.reverse;
     const uint64_t window_len = b_.window_len;
     const uint64_t exon_window_len = sg.ewl;
+    {
+      bool all_lazy = true;
+      for (auto& x : hap_vec) all_lazy = all_lazy && x.lazy;
+      for (auto& x : prev_hap_vec) all_lazy = all_lazy && x.lazy;
+      if (all_lazy && !(sg.flags & MPH_SF_HAS_FS) && !(is_short_exon && !is_last_exon)) {
+        // every combination has mt == wt: the window slide below writes nothing (:1801-1810,1887)
+        if (is_short_exon) prev_hap_vec.clear();
+        return;
+      }
+      for (auto& x : hap_vec) materialize(x);
+      for (auto& x : prev_hap_vec) materialize(x);
+    }
     const std::vector<HapSeq>& first_hap_vec = fwd ? hap_vec : prev_hap_vec;
     const std::vector<HapSeq>& sec_hap_vec = fwd ? prev_hap_vec : hap_vec;
     struct OutVal { std::string mt; InfoRecord rec; std::string wt; };
@@ -554,12 +647,10 @@ class Residue {
     std::vector<HapSeq> new_hap_vec;
     const double eps = std::numeric_limits<double>::epsilon();
     for (const HapSeq& hapseq : first_hap_vec) {
-      if (hapseq.partial) throw Unsupported("transcript " + tm.id + ": splice merge needs a window that is not at an exon boundary");
       const InfoRecord& record = hapseq.rec;
       const std::string& wt_sequence = record.normal_sequence;
       const std::string& mt_sequence = record.mutant_sequence;
       for (const HapSeq& prev_hapseq : sec_hap_vec) {
-        if (prev_hapseq.partial) throw Unsupported("transcript " + tm.id + ": splice merge needs a window that is not at an exon boundary");
         const InfoRecord& prev_record = prev_hapseq.rec;
         const std::string& prev_wt_sequence = prev_record.normal_sequence;
         const std::string& prev_mt_sequence = prev_record.mutant_sequence;
