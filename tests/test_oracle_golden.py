@@ -44,6 +44,15 @@ def test_oracle_somatic_matches_reference_golden(oracle_bin, case, tmp_path):
     assert_outputs(case, tmp_path)
 
 
+@pytest.mark.parametrize("case", ["forward_normal", "splice_forward_normal"])
+def test_oracle_normal_matches_reference_golden(oracle_bin, case, tmp_path):
+    """reference tests/lib.rs:237-249, 273-285 — only the FASTA is diffed by the reference's tests; its SHA-1
+    ids hash sequence + transcript + offset, so they also pin the reference bases filled in from the fixture."""
+    res = run_cli(oracle_bin, case, tmp_path)
+    assert res.returncode == 0, res.stderr.decode()
+    assert_outputs(case, tmp_path)
+
+
 def test_oracle_unsorted_gtf_is_fatal(oracle_bin, tmp_path):
     """reference tests/lib.rs:344-382 — unsorted GTF must exit non-zero, sorted must exit zero."""
     res = run_cli(oracle_bin, "unsorted_gtf", tmp_path, gtf="unsorted.gtf")
