@@ -59,3 +59,40 @@ def test_oracle_unsorted_gtf_is_fatal(oracle_bin, tmp_path):
     assert res.returncode != 0
     res = run_cli(oracle_bin, "unsorted_gtf", tmp_path, gtf="sorted.gtf")
     assert res.returncode == 0, res.stderr.decode()
+
+
+def test_oracle_build_reference_matches_golden(oracle_bin, tmp_path):
+    """reference tests/lib.rs:132-143 (only the peptide FASTA is diffed; the HashSet file order is arbitrary)."""
+    d = os.path.join(GOLDEN, "test_build")
+    with open(tmp_path / "ref.fasta", "wb") as fo:
+        r = subprocess.run([oracle_bin, "build_reference", "--reference", os.path.join(d, "reference.fa"), "-l4", "--output",
+                            str(tmp_path / "ref.bin")], stdout=fo, stderr=subprocess.PIPE)
+    assert r.returncode == 0, r.stderr.decode()
+    assert open(tmp_path / "ref.fasta", "rb").read() == open(os.path.join(d, "expected_output", "reference_peptides.fasta"), "rb").read()
+    # bincode layout of HashSet<Vec<u8>>: u64 count, then u64 length + bytes per item — same items as the reference's file
+    import struct
+
+    def items(path):
+        b = open(path, "rb").read()
+        n, o, out = struct.unpack_from("<Q", b, 0)[0], 8, set()
+        for _ in range(n):
+            ln = struct.unpack_from("<Q", b, o)[0]
+            out.add(b[o + 8:o + 8 + ln])
+            o += 8 + ln
+        assert o == len(b)
+        return out
+    assert items(tmp_path / "ref.bin") == items(os.path.join(d, "expected_output", "reference.binary"))
+
+
+@pytest.mark.parametrize("case,suffix", [("test_filter", "filtered"), ("test_filter_long", "filtered_long"), ("test_filter_fs", "filtered_fs")])
+def test_oracle_filter_matches_golden(oracle_bin, case, suffix, tmp_path):
+    """reference tests/lib.rs:145-209"""
+    d = os.path.join(GOLDEN, case)
+    with open(tmp_path / ("tumor.%s.fa" % suffix), "wb") as fo:
+        r = subprocess.run([oracle_bin, "filter", "--reference", os.path.join(d, "reference.binary"), "-l", "9", "--tsv", os.path.join(d, "info.tsv"),
+                            "--tsv-output", str(tmp_path / ("info.%s.tsv" % suffix)), "--normal-output", str(tmp_path / ("normal.%s.fa" % suffix)),
+                            "-s", str(tmp_path / "removed.tsv"), "-p", str(tmp_path / "removed.fa")], stdout=fo, stderr=subprocess.PIPE)
+    assert r.returncode == 0, r.stderr.decode()
+    for name in ("tumor.%s.fa", "normal.%s.fa", "info.%s.tsv"):
+        name = name % suffix
+        assert open(tmp_path / name, "rb").read() == open(os.path.join(d, "expected_output", name), "rb").read(), name
