@@ -177,6 +177,21 @@ int mph_run_somatic_multi(mph_ctx* const* ctxs, int n_ctx, const char* bam_path,
                           const char* gtf_path, const char* fasta_out_path, const char* tsv_path, const char* normal_path,
                           uint32_t window_len, int unsupported_allele_warning_only);
 
+/* ---- secondary path: `filter` / `build_reference` (src/peptides.rs) ------------------------------ */
+/* to_protein (:128-146): n nucleotide sequences nt[off[i]..off[i+1]); frame[i] = +1 (forward) or -1 (reverse complement
+ * first, :131-135). aa[aa_off[i]..aa_off[i+1]) receives floor(len/3) amino-acid letters ('X' = stop); bad[i] = 1 if a
+ * codon is not in the table (the reference unwraps an Err there, :141). Constant-memory codon table on the device. */
+int mph_translate(mph_ctx* ctx, const uint8_t* nt, const uint64_t* off, const int8_t* frame, uint64_t n, uint8_t* aa, const uint64_t* aa_off,
+                  uint8_t* bad);
+/* the normal peptidome as a device open-addressing hash set (deserialised HashSet<Vec<u8>> of :245): n peptides of k <= 12 letters */
+int mph_set_load(mph_ctx* ctx, const uint8_t* peptides, uint32_t k, uint64_t n);
+/* ref_set.contains(tumor_peptide) (:502, :684) for n queries of k letters; hit[i] = 1 if present */
+int mph_set_probe(mph_ctx* ctx, const uint8_t* queries, uint32_t k, uint64_t n, uint8_t* hit);
+/* peptides::filter (:234-709) and peptides::build (:148-186) end to end on files ("-" = stdout for the tumor / peptide FASTA) */
+int mph_run_filter(mph_ctx* ctx, const char* reference_bin, const char* tsv_in, const char* fasta_out_path, const char* normal_out,
+                   const char* tsv_out, const char* removed_tsv, const char* removed_fasta, uint32_t peptide_length);
+int mph_run_build_reference(mph_ctx* ctx, const char* reference_fasta, const char* binary_out, const char* fasta_out_path, uint32_t peptide_length);
+
 /* ---- synthetic workload (bench only): packs an exome-shaped batch natively ------------------ */
 typedef struct {
   uint64_t seed;

@@ -55,7 +55,8 @@ class BatchView(C.Structure):
 EXPORTS = ["mph_ctx_create", "mph_ctx_destroy", "mph_last_error", "mph_packer_create", "mph_packer_destroy", "mph_packer_add_gene",
            "mph_packer_finish", "mph_batch_destroy", "mph_batch_get_view", "mph_phase_batch", "mph_batch_upload", "mph_phase_resident",
            "mph_phase_collect", "mph_ctx_timing", "mph_result_destroy", "mph_result_count", "mph_result_get", "mph_result_write",
-           "mph_run_somatic", "mph_run_somatic_multi", "mph_synth_batch", "mph_synth_write_files"]
+           "mph_run_somatic", "mph_run_somatic_multi", "mph_translate", "mph_set_load", "mph_set_probe", "mph_run_filter",
+           "mph_run_build_reference", "mph_synth_batch", "mph_synth_write_files"]
 
 _lib = None
 
@@ -90,6 +91,11 @@ def load():
     lib.mph_result_write.argtypes = [P, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
     lib.mph_run_somatic.argtypes = [P] + [C.c_char_p] * 7 + [C.c_uint32, C.c_int]
     lib.mph_run_somatic_multi.argtypes = [C.POINTER(P), C.c_int] + [C.c_char_p] * 7 + [C.c_uint32, C.c_int]
+    lib.mph_translate.argtypes = [P, P, P, P, C.c_uint64, P, P, P]
+    lib.mph_set_load.argtypes = [P, P, C.c_uint32, C.c_uint64]
+    lib.mph_set_probe.argtypes = [P, P, C.c_uint32, C.c_uint64, P]
+    lib.mph_run_filter.argtypes = [P] + [C.c_char_p] * 7 + [C.c_uint32]
+    lib.mph_run_build_reference.argtypes = [P] + [C.c_char_p] * 3 + [C.c_uint32]
     lib.mph_synth_batch.argtypes = [C.POINTER(SynthParams), C.c_uint32, C.c_int, C.POINTER(P)]
     lib.mph_synth_write_files.argtypes = [C.POINTER(SynthParams), C.c_uint32, C.c_char_p]
     _lib = lib
@@ -133,6 +139,47 @@ class Context:
         """`microphaser somatic` on files (reference src/microphasing.rs:1943 `phase`)."""
         enc = [s.encode() for s in (bam, ref, variants, gtf, fasta_out, tsv, normal_out)]
         _check(self.lib.mph_run_somatic(self.h, *enc, window_len, int(warn_only)), self.h)
+
+    # ---- secondary path (reference src/peptides.rs)
+    def translate(self, seqs, frames):
+        """to_protein for a list of byte strings; returns (peptides, bad flags)."""
+        import numpy as np
+        n = len(seqs)
+        off = np.zeros(n + 1, dtype=np.uint64)
+        aoff = np.zeros(n + 1, dtype=np.uint64)
+        for i, s in enumerate(seqs):
+            off[i + 1] = off[i] + len(s)
+            aoff[i + 1] = aoff[i] + (len(s) // 3 if len(s) >= 2 else 0)
+        flat = np.frombuffer(b"".join(seqs) + b"\0", dtype=np.uint8).copy()
+        fr = np.asarray(frames, dtype=np.int8)
+        aa = np.zeros(int(aoff[n]) + 1, dtype=np.uint8)
+        bad = np.zeros(max(n, 1), dtype=np.uint8)
+        _check(self.lib.mph_translate(self.h, flat.ctypes.data, off.ctypes.data, fr.ctypes.data, n, aa.ctypes.data, aoff.ctypes.data, bad.ctypes.data), self.h)
+        raw = aa.tobytes()
+        return [raw[int(aoff[i]):int(aoff[i + 1])] for i in range(n)], bad[:n].tolist()
+
+    def set_load(self, peptides, k):
+        """peptides: numpy uint8 array of shape (n, k) or bytes of length n*k."""
+        import numpy as np
+        arr = np.ascontiguousarray(np.frombuffer(peptides, dtype=np.uint8) if isinstance(peptides, (bytes, bytearray)) else peptides, dtype=np.uint8)
+        n = arr.size // k
+        _check(self.lib.mph_set_load(self.h, arr.ctypes.data, k, n), self.h)
+
+    def set_probe(self, queries, k):
+        import numpy as np
+        arr = np.ascontiguousarray(np.frombuffer(queries, dtype=np.uint8) if isinstance(queries, (bytes, bytearray)) else queries, dtype=np.uint8)
+        n = arr.size // k
+        hit = np.zeros(max(n, 1), dtype=np.uint8)
+        _check(self.lib.mph_set_probe(self.h, arr.ctypes.data, k, n, hit.ctypes.data), self.h)
+        return hit[:n]
+
+    def run_filter(self, reference_bin, tsv_in, fasta_out, normal_out, tsv_out, removed_tsv, removed_fasta, peptide_length=9):
+        enc = [s.encode() for s in (reference_bin, tsv_in, fasta_out, normal_out, tsv_out, removed_tsv, removed_fasta)]
+        _check(self.lib.mph_run_filter(self.h, *enc, peptide_length), self.h)
+
+    def run_build_reference(self, reference_fasta, binary_out, fasta_out, peptide_length=9):
+        enc = [s.encode() for s in (reference_fasta, binary_out, fasta_out)]
+        _check(self.lib.mph_run_build_reference(self.h, *enc, peptide_length), self.h)
 
     def phase_batch(self, batch):
         res = C.c_void_p()

@@ -13,7 +13,9 @@
 
 #include "../../include/microphaser_gpu.h"
 #include "host/cli.hpp"
+#include "host/peptides_host.hpp"
 #include "host/synth_files.hpp"
+#include "kernels/peptide_kernels.cuh"
 #include "kernels/phase_kernels.cuh"
 
 using namespace mph;
@@ -98,6 +100,11 @@ struct mph_ctx {
   mph_timing timing = {};
   bool have_h2d_time = false;
   PhaseRaw raw;  // download buffers, reused across calls (no page faults after the first)
+  // secondary path: normal-peptidome hash set (open addressing, 5-bit packed peptides)
+  DevBuf<unsigned long long> set_table;
+  uint64_t set_mask = 0;
+  uint32_t set_k = 0;
+  uint64_t set_distinct = 0;
 };
 
 namespace {
@@ -347,6 +354,139 @@ void write_all(int fd, const std::string& s) {
 
 }  // namespace
 
+// ---- secondary path helpers (device translation / hash set) ---------------------------------
+namespace {
+
+void dev_translate(mph_ctx* c, const uint8_t* nt, const uint64_t* off, const int8_t* frame, uint64_t n, uint8_t* aa, const uint64_t* aa_off, uint8_t* bad) {
+  CU(cudaSetDevice(c->device));
+  if (n == 0) return;
+  DevBuf<uint8_t> d_nt, d_aa, d_bad;
+  DevBuf<uint64_t> d_off, d_aoff;
+  DevBuf<int8_t> d_fr;
+  d_nt.ensure(off[n] + 1); d_aa.ensure(aa_off[n] + 1); d_bad.ensure(n); d_off.ensure(n + 1); d_aoff.ensure(n + 1); d_fr.ensure(n);
+  try {
+    if (off[n]) CU(cudaMemcpyAsync(d_nt.p, nt, off[n], cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d_off.p, off, (n + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d_aoff.p, aa_off, (n + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d_fr.p, frame, n, cudaMemcpyHostToDevice, c->stream));
+    mphk::launch_translate(d_nt.p, d_off.p, d_fr.p, n, d_aa.p, d_aoff.p, d_bad.p, c->stream);
+    CU(cudaGetLastError());
+    if (aa_off[n]) CU(cudaMemcpyAsync(aa, d_aa.p, aa_off[n], cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(bad, d_bad.p, n, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+  } catch (...) {
+    d_nt.release(); d_aa.release(); d_bad.release(); d_off.release(); d_aoff.release(); d_fr.release();
+    throw;
+  }
+  d_nt.release(); d_aa.release(); d_bad.release(); d_off.release(); d_aoff.release(); d_fr.release();
+}
+
+void dev_set_load(mph_ctx* c, const uint8_t* peptides, uint32_t k, uint64_t n) {
+  CU(cudaSetDevice(c->device));
+  if (k == 0 || k > 12) throw Unsupported("peptide length must be 1..12 for the device hash set");
+  uint64_t slots = 1024;
+  while (slots < 2 * n + 16) slots <<= 1;
+  c->set_table.ensure(slots);
+  c->set_mask = slots - 1;
+  c->set_k = k;
+  CU(cudaMemsetAsync(c->set_table.p, 0, slots * 8, c->stream));
+  c->sums.ensure(2);
+  CU(cudaMemsetAsync(c->sums.p, 0, 16, c->stream));
+  if (n) {
+    DevBuf<uint8_t> d_p;
+    d_p.ensure(n * k);
+    try {
+      CU(cudaMemcpyAsync(d_p.p, peptides, n * k, cudaMemcpyHostToDevice, c->stream));
+      mphk::launch_set_insert(d_p.p, k, n, c->set_table.p, c->set_mask, c->sums.p, c->stream);
+      CU(cudaGetLastError());
+      CU(cudaStreamSynchronize(c->stream));
+    } catch (...) {
+      d_p.release();
+      throw;
+    }
+    d_p.release();
+  }
+  unsigned long long nd = 0;
+  CU(cudaMemcpyAsync(&nd, c->sums.p, 8, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  c->set_distinct = nd;
+}
+
+void dev_set_probe(mph_ctx* c, const uint8_t* queries, uint32_t k, uint64_t n, uint8_t* hit) {
+  CU(cudaSetDevice(c->device));
+  if (!c->set_table.p) throw std::runtime_error("no peptide set loaded");
+  if (n == 0) return;
+  if (k != c->set_k) {  // a peptide of another length cannot be in the set
+    memset(hit, 0, n);
+    return;
+  }
+  DevBuf<uint8_t> d_q, d_h;
+  d_q.ensure(n * k); d_h.ensure(n);
+  try {
+    CU(cudaMemcpyAsync(d_q.p, queries, n * k, cudaMemcpyHostToDevice, c->stream));
+    mphk::launch_set_probe(d_q.p, k, n, c->set_table.p, c->set_mask, d_h.p, c->stream);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(hit, d_h.p, n, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+  } catch (...) {
+    d_q.release(); d_h.release();
+    throw;
+  }
+  d_q.release(); d_h.release();
+}
+
+std::vector<std::string> dev_set_export(mph_ctx* c) {
+  std::vector<std::string> out;
+  if (!c->set_table.p || c->set_distinct == 0) return out;
+  const uint32_t k = c->set_k;
+  DevBuf<uint8_t> d_o;
+  d_o.ensure(c->set_distinct * k);
+  std::vector<uint8_t> host(c->set_distinct * k);
+  try {
+    CU(cudaMemsetAsync(c->sums.p, 0, 16, c->stream));
+    mphk::launch_set_export(c->set_table.p, c->set_mask + 1, k, d_o.p, c->sums.p, c->stream);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(host.data(), d_o.p, host.size(), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+  } catch (...) {
+    d_o.release();
+    throw;
+  }
+  d_o.release();
+  for (uint64_t i = 0; i < c->set_distinct; ++i) out.emplace_back(reinterpret_cast<const char*>(host.data() + i * k), k);
+  return out;
+}
+
+// adapters for host/peptides_host.hpp
+pep::TranslateFn make_translate(mph_ctx* c) {
+  return [c](const std::vector<std::string>& nt, const std::vector<int8_t>& frame, std::vector<std::string>& aa, std::vector<uint8_t>& bad) {
+    const uint64_t n = nt.size();
+    std::vector<uint64_t> off(n + 1, 0), aoff(n + 1, 0);
+    for (uint64_t i = 0; i < n; ++i) {
+      off[i + 1] = off[i] + nt[i].size();
+      aoff[i + 1] = aoff[i] + (nt[i].size() >= 2 ? nt[i].size() / 3 : 0);
+    }
+    std::vector<uint8_t> flat(off[n] + 1), out(aoff[n] + 1);
+    for (uint64_t i = 0; i < n; ++i) memcpy(flat.data() + off[i], nt[i].data(), nt[i].size());
+    bad.assign(n, 0);
+    dev_translate(c, flat.data(), off.data(), frame.data(), n, out.data(), aoff.data(), bad.data());
+    aa.resize(n);
+    for (uint64_t i = 0; i < n; ++i) aa[i].assign(reinterpret_cast<const char*>(out.data() + aoff[i]), size_t(aoff[i + 1] - aoff[i]));
+  };
+}
+
+std::vector<uint8_t> flatten_k(const std::vector<std::string>& v, uint32_t k, std::vector<uint64_t>& index) {
+  std::vector<uint8_t> flat;
+  for (uint64_t i = 0; i < v.size(); ++i)
+    if (v[i].size() == k) {
+      index.push_back(i);
+      flat.insert(flat.end(), v[i].begin(), v[i].end());
+    }
+  return flat;
+}
+
+}  // namespace
+
 extern "C" {
 
 int mph_ctx_create(int device, mph_ctx** out) {
@@ -375,7 +515,7 @@ void mph_ctx_destroy(mph_ctx* c) {
   c->read_start.release(); c->read_end.release(); c->read_vlo.release(); c->read_seq_off.release(); c->read_cig_off.release();
   c->cigars.release(); c->block_counts.release(); c->iw.release(); c->counters.release(); c->seg_live.release(); c->read_lseq.release();
   c->read_ncig.release(); c->read_nv.release(); c->read_flags.release(); c->bases.release(); c->ins_bytes.release(); c->ref.release();
-  c->ovf_list.release(); c->stopmap.release(); c->hist_win.release(); c->call_flags.release(); c->seq.release(); c->win_flag.release(); c->pairs.release(); c->vars.release(); c->segs.release();
+  c->ovf_list.release(); c->stopmap.release(); c->hist_win.release(); c->set_table.release(); c->call_flags.release(); c->seq.release(); c->win_flag.release(); c->pairs.release(); c->vars.release(); c->segs.release();
   c->chunks.release(); c->call_S.release(); c->call_B.release(); c->win_out.release(); c->iw_out.release(); c->hist.release();
   c->hap0.release(); c->hapx.release(); c->iw_hap0.release(); c->sums.release();
   for (auto& e : c->ev)
@@ -675,6 +815,82 @@ int mph_run_somatic_multi(mph_ctx* const* ctxs, int n_ctx, const char* bam_path,
   return guarded(ctxs[0], [&] {
     run_somatic_files(std::vector<mph_ctx*>(ctxs, ctxs + n_ctx), bam_path, ref_path, variants_path, gtf_path, fasta_out_path, tsv_path,
                       normal_path, window_len, warn_only);
+  });
+}
+
+int mph_translate(mph_ctx* ctx, const uint8_t* nt, const uint64_t* off, const int8_t* frame, uint64_t n, uint8_t* aa, const uint64_t* aa_off,
+                  uint8_t* bad) {
+  if (!ctx || !off || !aa_off || (n && (!nt || !frame || !aa || !bad))) return fail(ctx, MPH_ERR_INPUT, "null argument");
+  return guarded(ctx, [&] { dev_translate(ctx, nt, off, frame, n, aa, aa_off, bad); });
+}
+
+int mph_set_load(mph_ctx* ctx, const uint8_t* peptides, uint32_t k, uint64_t n) {
+  if (!ctx || (n && !peptides)) return fail(ctx, MPH_ERR_INPUT, "null argument");
+  return guarded(ctx, [&] { dev_set_load(ctx, peptides, k, n); });
+}
+
+int mph_set_probe(mph_ctx* ctx, const uint8_t* queries, uint32_t k, uint64_t n, uint8_t* hit) {
+  if (!ctx || (n && (!queries || !hit))) return fail(ctx, MPH_ERR_INPUT, "null argument");
+  return guarded(ctx, [&] { dev_set_probe(ctx, queries, k, n, hit); });
+}
+
+int mph_run_filter(mph_ctx* ctx, const char* reference_bin, const char* tsv_in, const char* fasta_out_path, const char* normal_out,
+                   const char* tsv_out, const char* removed_tsv, const char* removed_fasta, uint32_t peptide_length) {
+  if (!ctx || !reference_bin || !tsv_in || !fasta_out_path || !normal_out || !tsv_out || !removed_tsv || !removed_fasta)
+    return fail(ctx, MPH_ERR_INPUT, "null argument");
+  return guarded(ctx, [&] {
+    pep::FilterPaths io;
+    io.tsv_in = tsv_in; io.normal_out = normal_out; io.tsv_out = tsv_out; io.removed_tsv = removed_tsv; io.removed_fasta = removed_fasta;
+    FILE* fo = stdout;
+    if (std::string(fasta_out_path) != "-") {
+      fo = fopen(fasta_out_path, "wb");
+      if (!fo) throw std::runtime_error(std::string("cannot create ") + fasta_out_path);
+    }
+    io.fasta_out = fo;
+    try {
+      // the reference deserialises the whole set up front (:245); items of another length or with non-letter bytes can never match
+      std::vector<std::string> items = pep::read_peptide_set(reference_bin);
+      std::vector<uint64_t> idx;
+      std::vector<uint8_t> flat = flatten_k(items, peptide_length, idx);
+      dev_set_load(ctx, flat.data(), peptide_length, idx.size());
+      pep::ProbeFn probe = [&](const std::vector<std::string>& q, uint32_t k, std::vector<uint8_t>& hit) {
+        hit.assign(q.size(), 0);
+        std::vector<uint64_t> qi;
+        std::vector<uint8_t> qf = flatten_k(q, k, qi);
+        std::vector<uint8_t> h(qi.size() + 1, 0);
+        dev_set_probe(ctx, qf.data(), k, qi.size(), h.data());
+        for (size_t x = 0; x < qi.size(); ++x) hit[qi[x]] = h[x];
+      };
+      pep::run_filter(io, peptide_length, make_translate(ctx), probe);
+    } catch (...) {
+      if (fo != stdout) fclose(fo);
+      throw;
+    }
+    if (fo != stdout) fclose(fo);
+  });
+}
+
+int mph_run_build_reference(mph_ctx* ctx, const char* reference_fasta, const char* binary_out, const char* fasta_out_path, uint32_t peptide_length) {
+  if (!ctx || !reference_fasta || !binary_out || !fasta_out_path) return fail(ctx, MPH_ERR_INPUT, "null argument");
+  return guarded(ctx, [&] {
+    FILE* fo = stdout;
+    if (std::string(fasta_out_path) != "-") {
+      fo = fopen(fasta_out_path, "wb");
+      if (!fo) throw std::runtime_error(std::string("cannot create ") + fasta_out_path);
+    }
+    try {
+      pep::DedupeFn dedupe = [&](const std::vector<std::string>& peptides, uint32_t k) {
+        std::vector<uint64_t> idx;
+        std::vector<uint8_t> flat = flatten_k(peptides, k, idx);
+        dev_set_load(ctx, flat.data(), k, idx.size());
+        return dev_set_export(ctx);
+      };
+      pep::run_build_reference(reference_fasta, binary_out, fo, peptide_length, make_translate(ctx), dedupe);
+    } catch (...) {
+      if (fo != stdout) fclose(fo);
+      throw;
+    }
+    if (fo != stdout) fclose(fo);
   });
 }
 
