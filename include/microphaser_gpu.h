@@ -50,7 +50,10 @@ void mph_ctx_destroy(mph_ctx* ctx);
 const char* mph_last_error(const mph_ctx* ctx);
 
 /* ---- packer: replaces the per-gene set-up of phase_gene (src/microphasing.rs:894-942) ---- */
-/* mode 0 = somatic (reads with mapq < 5 are dropped by the caller, :910) */
+/* mode 0 = somatic (reads with mapq < 5 are dropped by the caller, :910);
+ * mode 1 = normal, the healthy-peptidome pass of src/normal_microphasing.rs:650-1279 (no mapq / base-quality
+ * filter, every window of a non-short exon yields a record; mph_record.mutant_sequence then holds the
+ * `peptide_sequence` column, normal_sequence is empty and offsets are 0-based as in the reference) */
 int mph_packer_create(uint32_t window_len, int mode, mph_packer** out);
 void mph_packer_destroy(mph_packer* p);
 
@@ -169,6 +172,10 @@ int mph_result_write(const mph_result* r, int fd_fasta, int fd_tsv, int fd_norma
 int mph_run_somatic(mph_ctx* ctx, const char* bam_path, const char* ref_path, const char* variants_path, const char* gtf_path,
                     const char* fasta_out_path, const char* tsv_path, const char* normal_path, uint32_t window_len,
                     int unsupported_allele_warning_only);
+
+/* `normal` sub-command (src/normal_microphasing.rs:1281-1440): FASTA of every window's haplotypes and the 20-column TSV */
+int mph_run_normal(mph_ctx* ctx, const char* bam_path, const char* ref_path, const char* variants_path, const char* gtf_path,
+                   const char* fasta_out_path, const char* tsv_path, uint32_t window_len, int unsupported_allele_warning_only);
 
 /* the same over several devices of one box: genes are split into n_ctx contiguous ranges balanced by
  * read count, every context phases its range on its own host thread, records are concatenated in

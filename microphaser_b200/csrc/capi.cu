@@ -73,6 +73,7 @@ struct mph_packer {
 };
 
 struct mph_result {
+  int mode = 0;
   std::vector<OutRecord> recs;
   std::vector<std::string> tx_id, gene_id, gene_name, chrom;
   std::vector<uint8_t> tx_reverse;
@@ -85,7 +86,7 @@ struct mph_ctx {
   std::string last_error;
   const mph_batch* cur = nullptr;
   mphk::DeviceBatch d;
-  DevBuf<uint32_t> read_start, read_end, read_vlo, read_seq_off, read_cig_off, cigars, block_counts, iw, counters, seg_live, ovf_list, stopmap, hist_win;
+  DevBuf<uint32_t> read_start, read_end, read_vlo, read_seq_off, read_cig_off, cigars, block_counts, iw, counters, seg_live, ovf_list, stopmap, hist_win, win_depth;
   DevBuf<uint16_t> read_lseq, read_ncig;
   DevBuf<uint8_t> read_nv, read_flags, bases, ins_bytes, ref, call_flags, seq, win_flag;
   DevBuf<uint2> pairs;
@@ -202,6 +203,8 @@ void upload(mph_ctx* c, const mph_batch* mb) {
   d.ovf_list = c->ovf_list.p;
   d.iw = c->iw.p; d.iw_out = c->iw_out.p; d.iw_hap0 = c->iw_hap0.p; d.counters = c->counters.p;
   d.sum_depth = c->sums.p; d.live_depth = c->sums.p + 1; d.seg_live = c->seg_live.p;
+  d.mode = uint32_t(b.mode);
+  if (b.mode == 1) { c->win_depth.ensure(nw + 1); d.win_depth = c->win_depth.p; }
   c->cur = mb;
   c->timing.h2d_bytes = mb->h2d_bytes;
   c->have_h2d_time = true;
@@ -268,18 +271,22 @@ void collect(mph_ctx* c, mph_result** out) {
     CU(cudaMemcpyAsync(raw.hapx.data(), c->hapx.p, n_hist * sizeof(MphHap), cudaMemcpyDeviceToHost, c->stream));
   }
   if (n_seq) CU(cudaMemcpyAsync(raw.seq.data(), c->seq.p, n_seq, cudaMemcpyDeviceToHost, c->stream));
+  const bool normal_mode = b.mode == 1;
+  raw.win_depth.resize(normal_mode ? size_t(b.n_windows) : 0);
+  if (normal_mode && b.n_windows) CU(cudaMemcpyAsync(raw.win_depth.data(), c->win_depth.p, size_t(b.n_windows) * 4, cudaMemcpyDeviceToHost, c->stream));
   unsigned long long sums[2];
   CU(cudaMemcpyAsync(sums, c->sums.p, sizeof sums, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaEventRecord(c->ev[1], c->stream));
   CU(cudaStreamSynchronize(c->stream));
   CU(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
   c->timing.d2h_ms = ms;
-  c->timing.d2h_bytes = sizeof ctr + sizeof sums + size_t(n_iw) * (4 + sizeof(MphWinOut) + sizeof(MphHap)) + size_t(n_hist) * (sizeof(MphHist) + sizeof(MphHap)) + n_seq;
+  c->timing.d2h_bytes = sizeof ctr + sizeof sums + size_t(n_iw) * (4 + sizeof(MphWinOut) + sizeof(MphHap)) + size_t(n_hist) * (sizeof(MphHist) + sizeof(MphHap)) + n_seq + raw.win_depth.size() * 4;
   raw.sum_depth = sums[0];
 
   // host residue: the serial part of the window loop, transcripts are independent
   const auto t0 = std::chrono::steady_clock::now();
   std::unique_ptr<mph_result> res(new mph_result);
+  res->mode = b.mode;
   ResidueStats st;
   const uint32_t n_tx = uint32_t(b.txs.size());
   // host threads for the residue: MPH_HOST_THREADS, else all cores (a multi-GPU launcher gives every rank its share)
@@ -292,8 +299,13 @@ void collect(mph_ctx* c, mph_result** out) {
   std::vector<std::exception_ptr> perr(n_thr);
   auto work = [&](unsigned ti) {
     try {
-      Residue r(b, raw);
       const uint32_t lo = uint32_t(uint64_t(n_tx) * ti / n_thr), hi = uint32_t(uint64_t(n_tx) * (ti + 1) / n_thr);
+      if (normal_mode) {
+        ResidueNormal r(b, raw);
+        r.run(lo, hi, parts[ti], pstats[ti]);
+        return;
+      }
+      Residue r(b, raw);
       r.run(lo, hi, parts[ti], pstats[ti]);
       plive[ti] = std::move(r.seg_live_);
     } catch (...) {
@@ -319,13 +331,17 @@ void collect(mph_ctx* c, mph_result** out) {
   }
   c->timing.residue_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   // statistics: depth summed on the device over the windows the reference reaches
-  std::vector<uint32_t> live(b.segs.size() + 1, 0);
-  for (auto& pl : plive)
-    for (auto& sl : pl) live[sl.first] = sl.second;
-  CU(cudaMemcpyAsync(c->seg_live.p, live.data(), live.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
-  mphk::launch_live_depth(c->d, c->stream);
-  CU(cudaMemcpyAsync(sums, c->sums.p, sizeof sums, cudaMemcpyDeviceToHost, c->stream));
-  CU(cudaStreamSynchronize(c->stream));
+  if (!normal_mode) {  // the normal-mode residue visits every window and sums the depth itself
+    std::vector<uint32_t> live(b.segs.size() + 1, 0);
+    for (auto& pl : plive)
+      for (auto& sl : pl) live[sl.first] = sl.second;
+    CU(cudaMemcpyAsync(c->seg_live.p, live.data(), live.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+    mphk::launch_live_depth(c->d, c->stream);
+    CU(cudaMemcpyAsync(sums, c->sums.p, sizeof sums, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+  } else {
+    sums[1] = 0;
+  }
   c->timing.windows = st.windows;
   c->timing.read_windows = st.read_windows + sums[1];
   c->timing.windows_enumerated = b.n_windows;
@@ -528,10 +544,10 @@ const char* mph_last_error(const mph_ctx* ctx) { return ctx ? ctx->last_error.c_
 
 int mph_packer_create(uint32_t window_len, int mode, mph_packer** out) {
   if (!out) return fail(nullptr, MPH_ERR_INPUT, "out is NULL");
-  if (mode != 0) return fail(nullptr, MPH_ERR_UNSUPPORTED, "only mode 0 (somatic) is implemented");
+  if (mode != 0 && mode != 1) return fail(nullptr, MPH_ERR_UNSUPPORTED, "mode must be 0 (somatic) or 1 (normal)");
   if (window_len == 0 || window_len % 3 != 0) return fail(nullptr, MPH_ERR_UNSUPPORTED, "window length must be a positive multiple of 3");
   *out = new mph_packer;
-  (*out)->p.reset(new Packer(window_len));
+  (*out)->p.reset(new Packer(window_len, mode));
   (*out)->mode = mode;
   return MPH_OK;
 }
@@ -693,13 +709,17 @@ int mph_result_write(const mph_result* r, int fd_fasta, int fd_tsv, int fd_norma
         "id\ttranscript\tgene_id\tgene_name\tchrom\toffset\tframe\tfreq\tdepth\tnvar\tnsomatic\tnvariant_sites\tnsomvariant_sites\t"
         "strand\tvariant_sites\tsomatic_positions\tsomatic_aa_change\tgermline_positions\tgermline_aa_change\tnormal_sequence\t"
         "mutant_sequence\n";
+    static const char* header_normal =
+        "id\ttranscript\tgene_id\tgene_name\tchrom\toffset\tframe\tfreq\tdepth\tnvar\tnsomatic\tnvariant_sites\tnsomvariant_sites\t"
+        "strand\tvariant_sites\tsomatic_positions\tsomatic_aa_change\tgermline_positions\tgermline_aa_change\tpeptide_sequence\n";
     std::string fa, tsv, nrm;
     int hw = header_written ? *header_written : 0;
+    const bool normal_mode = r->mode == 1;  // 20 columns, the last one is peptide_sequence (src/normal_microphasing.rs:80-102)
     for (const OutRecord& rec : r->recs) {
       const uint32_t t = rec.info.tx;
       if (rec.has_mt) { fa += '>'; fa += rec.info.id; fa += '\n'; fa += rec.mt; fa += '\n'; }
       if (rec.has_wt) { nrm += '>'; nrm += rec.info.id; nrm += '\n'; nrm += rec.wt; nrm += '\n'; }
-      if (!hw) { tsv += header; hw = 1; }
+      if (!hw) { tsv += normal_mode ? header_normal : header; hw = 1; }
       const std::string fields[21] = {rec.info.id, r->tx_id[t], r->gene_id[t], r->gene_name[t], r->chrom[t], std::to_string(rec.info.offset),
                                       std::to_string(rec.info.frame), mphfmt::format_f64(rec.info.freq), std::to_string(rec.info.depth),
                                       std::to_string(rec.info.nvar), std::to_string(rec.info.nsomatic), std::to_string(rec.info.nvariant_sites),
@@ -707,6 +727,7 @@ int mph_result_write(const mph_result* r, int fd_fasta, int fd_tsv, int fd_norma
                                       rec.info.variant_sites, rec.info.somatic_positions, rec.info.somatic_aa_change,
                                       rec.info.germline_positions, rec.info.germline_aa_change, rec.info.normal_sequence, rec.info.mutant_sequence};
       for (int i = 0; i < 21; ++i) {
+        if (normal_mode && i == 19) continue;
         if (i) tsv.push_back('\t');
         mphfmt::csv_field(fields[i], '\t', tsv);
       }
@@ -722,7 +743,7 @@ int mph_result_write(const mph_result* r, int fd_fasta, int fd_tsv, int fd_norma
 // shared by the single- and multi-device file drivers
 static void run_somatic_files(const std::vector<mph_ctx*>& ctxs, const char* bam_path, const char* ref_path, const char* variants_path,
                               const char* gtf_path, const char* fasta_out_path, const char* tsv_path, const char* normal_path,
-                              uint32_t window_len, int warn_only) {
+                              uint32_t window_len, int warn_only, int mode = 0) {
   mphio::BamFile bam(bam_path);
   mphio::VcfFile vcf(variants_path);
   mphio::FastaIndexed fasta(ref_path);
@@ -735,7 +756,7 @@ static void run_somatic_files(const std::vector<mph_ctx*>& ctxs, const char* bam
     fclose(f);
     return fd;
   };
-  const int fd_fa = open_out(fasta_out_path), fd_tsv = open_out(tsv_path), fd_n = open_out(normal_path);
+  const int fd_fa = open_out(fasta_out_path), fd_tsv = open_out(tsv_path), fd_n = normal_path ? open_out(normal_path) : -1;
   auto close_all = [&] {
     if (fd_fa > 2) close(fd_fa);
     if (fd_tsv > 2) close(fd_tsv);
@@ -745,6 +766,8 @@ static void run_somatic_files(const std::vector<mph_ctx*>& ctxs, const char* bam
     IngestOptions io;
     io.window_len = window_len;
     io.warn_only = warn_only != 0;
+    io.mode = mode;
+    if (mode == 1) io.min_mapq = 0;  // the normal mode keeps every read (src/normal_microphasing.rs:667-676)
     std::ifstream gf;
     std::istream* gin = &std::cin;
     if (std::string(gtf_path) != "-") {
@@ -762,7 +785,7 @@ static void run_somatic_files(const std::vector<mph_ctx*>& ctxs, const char* bam
     std::vector<std::exception_ptr> errs(n_dev);
     auto shard = [&](size_t k) {
       try {
-        Packer packer(window_len);
+        Packer packer(window_len, mode);
         pack_genes(genes, cut[k], cut[k + 1], packer);
         batches[k].reset(new mph_batch);
         batches[k]->b = std::move(packer.batch());
@@ -803,6 +826,15 @@ int mph_run_somatic(mph_ctx* ctx, const char* bam_path, const char* ref_path, co
   if (window_len == 0 || window_len % 3 != 0) return fail(ctx, MPH_ERR_UNSUPPORTED, "window length must be a positive multiple of 3");
   return guarded(ctx, [&] {
     run_somatic_files({ctx}, bam_path, ref_path, variants_path, gtf_path, fasta_out_path, tsv_path, normal_path, window_len, warn_only);
+  });
+}
+
+int mph_run_normal(mph_ctx* ctx, const char* bam_path, const char* ref_path, const char* variants_path, const char* gtf_path,
+                   const char* fasta_out_path, const char* tsv_path, uint32_t window_len, int warn_only) {
+  if (!ctx || !bam_path || !ref_path || !variants_path || !gtf_path || !fasta_out_path || !tsv_path) return fail(ctx, MPH_ERR_INPUT, "null argument");
+  if (window_len == 0 || window_len % 3 != 0) return fail(ctx, MPH_ERR_UNSUPPORTED, "window length must be a positive multiple of 3");
+  return guarded(ctx, [&] {
+    run_somatic_files({ctx}, bam_path, ref_path, variants_path, gtf_path, fasta_out_path, tsv_path, nullptr, window_len, warn_only, 1);
   });
 }
 

@@ -3,6 +3,7 @@
 // include/microphaser_gpu.h; the phasing itself runs on the GPU, there is no CPU fallback.
 //   microphaser somatic <tumor.bam> --ref genome.fasta --variants tumor.vcf [-w 27] [--tsv info.tsv]
 //                       [--normal-output normal.fasta] [-u] [-v]   < annotation.gtf > peptides.mt.fa
+//   microphaser normal <normal.bam> --ref genome.fasta --variants normal.vcf [-w 27] [--tsv info.tsv] [-u] [-v] < annotation.gtf > peptides.wt.fa
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -84,7 +85,8 @@ int main(int argc, char** argv) {
   if (argc < 2) return 0;
   const std::string sub = argv[1];
   if (sub == "filter" || sub == "build_reference") return run_secondary(sub, argc, argv);
-  if (sub != "somatic") {
+  const bool normal_mode = sub == "normal";  // src/main.rs `normal`: same arguments without --normal-output
+  if (sub != "somatic" && !normal_mode) {
     fprintf(stderr, "error: sub-command '%s' is not part of the GPU phasing path\n", sub.c_str());
     return 1;
   }
@@ -139,8 +141,11 @@ int main(int argc, char** argv) {
     ctxs.push_back(c);
   }
   mph_ctx* ctx = ctxs[0];
-  rc = mph_run_somatic_multi(ctxs.data(), int(ctxs.size()), pos[0].c_str(), opt["ref"].c_str(), opt["variants"].c_str(), "-", "-", tsv.c_str(),
-                             nrm.c_str(), wl, warn_only);
+  if (normal_mode)
+    rc = mph_run_normal(ctx, pos[0].c_str(), opt["ref"].c_str(), opt["variants"].c_str(), "-", "-", tsv.c_str(), wl, warn_only);
+  else
+    rc = mph_run_somatic_multi(ctxs.data(), int(ctxs.size()), pos[0].c_str(), opt["ref"].c_str(), opt["variants"].c_str(), "-", "-", tsv.c_str(),
+                               nrm.c_str(), wl, warn_only);
   int status = 0;
   if (rc == MPH_ERR_PANIC) { fprintf(stderr, "thread 'main' panicked at '%s'\n", mph_last_error(ctx)); status = 101; }
   else if (rc == MPH_ERR_UNSUPPORTED) { fprintf(stderr, "microphaser: input needs the serial replay path, which is not implemented: %s\n", mph_last_error(ctx)); status = 3; }

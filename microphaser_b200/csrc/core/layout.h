@@ -129,6 +129,7 @@ enum {
   MPH_HF_SEQ = 8,        // seq/germline_seq bytes were written to the sequence arena
   MPH_HF_GERM_EQ = 16,   // germline_seq == seq before any clearing (:624-631)
   MPH_HF_OVERFLOW = 32,  // assembled sequence longer than the per-haplotype arena slot
+  MPH_HF_REFRANGE = 64,  // the walk left the shipped reference slice: the reference panics if (and only if) it reaches this haplotype
 };
 typedef struct {
   uint32_t flags;      // MPH_HF_*

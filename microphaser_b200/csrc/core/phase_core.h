@@ -123,7 +123,7 @@ MPH_HD int mph_read_pos(const uint32_t* cig, uint32_t n_cig, uint32_t l_seq, uin
 // supports_variant / bad_quality for every variant with pos in [start, end) of one read.
 // `bases` points at the read's packed record: ceil(l_seq/2) B of 4-bit codes (high nibble first),
 // then ceil(l_seq/8) B with bit i set iff qual[i] < 10.
-MPH_HD MphCall mph_call_read(const MphRead& r, const uint8_t* bases, const uint32_t* cig, const MphVar* vars) {
+MPH_HD MphCall mph_call_read(const MphRead& r, const uint8_t* bases, const uint32_t* cig, const MphVar* vars, bool use_qual = true) {
   MphCall c;
   c.S = 0;
   c.B = 0;
@@ -136,7 +136,7 @@ MPH_HD MphCall mph_call_read(const MphRead& r, const uint8_t* bases, const uint3
     if (v.kind == MPH_SNV) {
       const uint32_t rel = v.pos - r.start;  // raw reference offset indexes the *query* qualities (:82-84,99-101)
       bool low = false;
-      if (rel < r.l_seq) low = (lowq[rel >> 3] >> (rel & 7u)) & 1u;
+      if (use_qual && rel < r.l_seq) low = (lowq[rel >> 3] >> (rel & 7u)) & 1u;  // normal mode has no base-quality test (normal_microphasing.rs:43-52)
       if (low) {
         c.B |= (uint64_t)1 << j;
       } else {
@@ -333,7 +333,7 @@ MPH_HD uint32_t mph_assemble(const MphSegment& g, const MphGeom& gk, const MphVa
 #define MPH_REF(i_, dst_)                                          \
   do {                                                             \
     const uint64_t ri_ = (uint64_t)(i_) - g.ref_pos0;              \
-    if ((i_) < g.ref_pos0 || ri_ >= g.ref_len) { err |= MPH_E_REF_RANGE; dst_ = 'N'; } \
+    if ((i_) < g.ref_pos0 || ri_ >= g.ref_len) { flags |= MPH_HF_REFRANGE; dst_ = 'N'; } \
     else dst_ = ref[ri_];                                          \
   } while (0)
 #define MPH_PUSH(buf_, len_, c_)           \
@@ -435,7 +435,7 @@ MPH_HD uint32_t mph_plain_hap(const MphSegment& g, const MphGeom& gk, const uint
   const uint32_t len = gk.e - gk.s;
   uint32_t flags = MPH_HF_GERM_EQ;
   if (gk.s < g.ref_pos0 || (uint64_t)gk.e - g.ref_pos0 > g.ref_len) {
-    err |= MPH_E_REF_RANGE;
+    flags |= MPH_HF_REFRANGE;
   } else {
     uint32_t a, b;
     mph_neo_slice(gk, len, g.ewl, false, &a, &b);
@@ -476,7 +476,7 @@ MPH_HD uint32_t mph_plain_window(const MphSegment& g, const MphGeom& gk, const u
   const uint32_t len = gk.e - gk.s;
   uint32_t flags = MPH_HF_GERM_EQ;
   if (gk.s < g.ref_pos0 || (uint64_t)gk.e - g.ref_pos0 > g.ref_len) {
-    err |= MPH_E_REF_RANGE;
+    flags |= MPH_HF_REFRANGE;
   } else {
     const uint8_t* p = ref_arena + g.ref_off + (gk.s - g.ref_pos0);
     uint32_t a, b;
@@ -491,4 +491,216 @@ MPH_HD uint32_t mph_plain_window(const MphSegment& g, const MphGeom& gk, const u
   out->profile = 0;
   out->pad2 = 0;
   return err;
+}
+
+// ================================================================================================
+// `normal` mode (reference src/normal_microphasing.rs; line numbers below refer to that file).
+// Same window geometry; what differs in the matrix: no quality / mapq filters, no
+// `contains`, push_read numbers the variants oldest-first (:317) while extend_right numbers the new
+// ones newest-first (:260), and on the reverse strand cleanup_reads(splice_side_offset) (:1001)
+// together with re-offering every read each iteration (:942-967) inserts a read once per iteration.
+// ================================================================================================
+
+// Number of copies of a read in the matrix at iteration k of a reverse-strand segment, and the first
+// iteration kc at which a copy was pushed (copies exist for every iteration kc..k).
+MPH_HD uint32_t mph_nrm_rev_copies(const MphSegment& g, uint32_t k, const MphGeom& gk, uint32_t start, uint32_t end, uint32_t* kc_out) {
+  *kc_out = k;
+  if (start > gk.s || end < gk.e) return 0;
+  const uint64_t lim = (uint64_t)start + g.K;
+  if (start == gk.s) return lim >= gk.s ? 1u : 0u;  // older copies were just removed (keys >= s, :275-278)
+  uint32_t kc = g.off0 > lim ? (uint32_t)(g.off0 - lim) : 0;
+  if (mph_geom(g, 0).e > end) {
+    const uint64_t t = (uint64_t)g.off0 + g.ewl;
+    const uint32_t k2 = t > end ? (uint32_t)(t - end) : 1;
+    if (k2 > kc) kc = k2;
+    if (kc == 0) kc = 1;
+  }
+  kc = kc >= 2 ? kc - 2 : 0;
+  for (; kc <= k; ++kc) {
+    const MphGeom gc = mph_geom(g, kc);
+    if (gc.s <= lim && gc.e <= end) break;
+  }
+  if (kc > k) return 0;
+  *kc_out = kc;
+  return k - kc + 1;
+}
+
+// obs.haplotype at iteration k of an observation pushed at iteration kp (:238-267,301-331).
+// Storage order of the variants is ascending position (ALT order reversed on the reverse strand);
+// the matrix adds them in ascending index order on the forward strand, descending on the reverse strand.
+MPH_HD uint64_t mph_nrm_hap(const MphSegment& g, const MphVar* vars, uint32_t kp, uint32_t k, uint32_t va, uint32_t vb, uint32_t vlo, uint64_t S) {
+  const bool rev = (g.flags & MPH_SF_REVERSE) != 0;
+  if (S == 0) return 0;
+  auto sbit = [&](uint32_t idx) -> uint64_t { return (idx >= vlo && idx - vlo < 64) ? ((S >> (idx - vlo)) & 1) : 0; };
+  // deque at the push: what the previous iteration held minus what has just left (empty at iteration 0)
+  uint32_t a0, b0;
+  if (kp == 0) {
+    a0 = b0 = rev ? mph_var_lb(vars, g.var_lo, g.var_hi, mph_geom(g, 0).e) : mph_var_lb(vars, g.var_lo, g.var_hi, mph_geom(g, 0).s);
+  } else {
+    const MphGeom gp = mph_geom(g, kp), gq = mph_geom(g, kp - 1);
+    a0 = mph_var_lb(vars, g.var_lo, g.var_hi, rev ? gq.s : gp.s);
+    b0 = mph_var_lb(vars, g.var_lo, g.var_hi, rev ? gp.e : gq.e);
+    if (b0 < a0) b0 = a0;
+  }
+  const uint32_t m = b0 - a0;
+  const uint32_t A = rev ? (a0 > va ? a0 - va : 0) : (vb > b0 ? vb - b0 : 0);
+  const uint32_t Del = rev ? (b0 > vb ? b0 - vb : 0) : (va > a0 ? va - a0 : 0);
+  uint64_t hap = 0;
+  // push-time columns: bit i <-> i-th oldest; it survives the masks while Del < m - i
+  for (uint32_t i = 0; i < m && i + Del < m; ++i) {
+    const uint32_t idx = rev ? b0 - 1 - i : a0 + i;
+    const uint32_t pos = i + A;
+    if (pos < 64 && sbit(idx)) hap |= (uint64_t)1 << pos;
+  }
+  // columns added afterwards: the j-th added sits at bit A - j and survives while Del < m + j
+  for (uint32_t j = 1; j <= A; ++j) {
+    if (Del >= m + j) continue;
+    const uint32_t idx = rev ? a0 - j : b0 + j - 1;
+    const uint32_t pos = A - j;
+    if (pos < 64 && sbit(idx)) hap |= (uint64_t)1 << pos;
+  }
+  return hap;
+}
+
+enum { MPH_NF_STOP = 1, MPH_NF_INSERTION = 4, MPH_NF_SEQ = 8, MPH_NF_OVERFLOW = 32, MPH_NF_REFRANGE = 64 };
+
+// Sequence walk of the normal-mode print_haplotypes (:403-507) for one haplotype; `all_reads` = the
+// haplotype is carried by every observation (freq == 1, :422). Fills seq (cap bytes) and out.
+MPH_HD uint32_t mph_nrm_assemble(const MphSegment& g, const MphGeom& gk, const MphVar* vars, uint32_t va, uint32_t vb, const uint8_t* ref_arena,
+                                 const uint8_t* ins_arena, uint64_t hap, bool all_reads, uint8_t* seq, uint32_t cap, MphHap* out) {
+  const bool rev = (g.flags & MPH_SF_REVERSE) != 0;
+  const uint32_t n = vb - va;
+  uint32_t err = 0, sl = 0, flags = 0, n_var = 0, n_som = 0, n_prof = 0;
+  uint64_t profile = 0;
+  const uint8_t* ref = ref_arena + g.ref_off;
+#define MPH_NREF(i_, dst_)                                                            \
+  do {                                                                                \
+    const uint64_t ri_ = (uint64_t)(i_) - g.ref_pos0;                                 \
+    if ((i_) < g.ref_pos0 || ri_ >= g.ref_len) { flags |= MPH_HF_REFRANGE; dst_ = 'N'; } \
+    else dst_ = ref[ri_];                                                             \
+  } while (0)
+#define MPH_NPUSH(c_)                        \
+  do {                                       \
+    if (sl < cap) seq[sl] = (c_);            \
+    else flags |= MPH_NF_OVERFLOW;           \
+    ++sl;                                    \
+  } while (0)
+  uint64_t i = gk.s, window_end = gk.e;
+  uint32_t j = 0;
+  if (n == 0) {
+    for (; i < window_end; ++i) { uint8_t r; MPH_NREF(i, r); MPH_NPUSH(r); }
+  } else {
+    while (i < window_end) {
+      while (j < n && i == vars[va + j].pos) {
+        if (all_reads && !(vars[va + j].flags & MPH_VF_GERMLINE)) {  // :422-426
+          ++j;
+          ++n_prof;
+          continue;
+        }
+        if ((hap >> (j & 63)) & 1) {
+          if (j + 1 < n && i == vars[va + j + 1].pos) ++j;  // :429-431
+          const MphVar v = vars[va + j];
+          uint8_t r;
+          MPH_NREF(i, r);
+          if (v.kind == MPH_SNV) {
+            MPH_NPUSH(mph_is_upper(r) ? mph_lower(v.alt) : v.alt);
+            i += 1;
+          } else if (v.kind == MPH_INS) {
+            const bool up = mph_is_upper(r);
+            for (uint32_t t = 0; t <= v.len; ++t) {
+              const uint8_t c0 = ins_arena[v.ins_off + t];
+              MPH_NPUSH(up ? mph_lower(c0) : mph_upper(c0));
+            }
+            flags |= MPH_NF_INSERTION;
+            i += 1;
+          } else {
+            MPH_NPUSH(r);
+            i += (uint64_t)v.len + 1;
+            window_end += (uint64_t)v.len + 1;  // :457
+          }
+          const uint64_t code = (v.flags & MPH_VF_GERMLINE) ? 1 : 2;
+          if (n_prof < 32) profile |= code << (2 * n_prof);
+          if (code == 2) ++n_som;
+          ++n_var;
+        }
+        ++n_prof;
+        ++j;
+      }
+      uint8_t r;
+      MPH_NREF(i, r);  // :476 — unconditional, also right after a variant at the last window position
+      MPH_NPUSH(r);
+      i += 1;
+    }
+  }
+#undef MPH_NREF
+#undef MPH_NPUSH
+  if (n_prof > 32) err |= MPH_E_VARS_PER_WINDOW;
+  // peptide slice (:485-492) and the first / last codon stop test (:493-507)
+  const uint32_t len = sl < cap ? sl : cap;
+  const uint32_t twl = len < g.ewl ? len : g.ewl;
+  uint32_t a = 0, b = len;
+  if (gk.spos == 1) a = gk.gap < len ? gk.gap : len;
+  else if (gk.spos == 0 && !(flags & MPH_NF_INSERTION)) b = twl;
+  if (b >= a + 3) {
+    const uint8_t* p = seq + a;
+    const uint32_t pl = b - a;
+    bool stop;
+    if (!rev) stop = p[0] == 'T' && ((p[1] == 'G' && p[2] == 'A') || (p[1] == 'A' && (p[2] == 'G' || p[2] == 'A')));
+    else stop = p[pl - 1] == 'A' && ((p[pl - 3] == 'T' && (p[pl - 2] == 'C' || p[pl - 2] == 'T')) || (p[pl - 3] == 'C' && p[pl - 2] == 'T'));
+    if (stop) flags |= MPH_NF_STOP;
+  }
+  out->flags = flags;
+  out->seq_len = (uint16_t)sl;
+  out->germ_len = 0;
+  out->n_var = (uint8_t)n_var;
+  out->n_som = (uint8_t)n_som;
+  out->n_prof = (uint8_t)(n_prof < 255 ? n_prof : 255);
+  out->brk = 0;
+  out->seq_off = 0xFFFFFFFFu;
+  out->profile = profile;
+  out->pad2 = 0;
+  return err;
+}
+
+// haplotype 0 of a window without variants in normal mode: seq = refseq[s..e) (:409-412), first / last codon stop test
+MPH_HD uint32_t mph_nrm_plain(const MphSegment& g, const MphGeom& gk, const uint8_t* ref_arena, uint32_t nv, MphHap* out) {
+  uint32_t err = 0, flags = 0;
+  const uint32_t len = gk.e - gk.s;
+  if (gk.s < g.ref_pos0 || (uint64_t)gk.e - g.ref_pos0 > g.ref_len) {
+    flags |= MPH_HF_REFRANGE;
+  } else {
+    const uint8_t* q = ref_arena + g.ref_off + (gk.s - g.ref_pos0);
+    const uint32_t twl = len < g.ewl ? len : g.ewl;
+    uint32_t a = 0, b = len;
+    if (gk.spos == 1) a = gk.gap < len ? gk.gap : len;
+    else if (gk.spos == 0) b = twl;
+    if (b >= a + 3) {
+      const uint8_t* p = q + a;
+      const uint32_t pl = b - a;
+      bool stop;
+      if (!(g.flags & MPH_SF_REVERSE)) stop = p[0] == 'T' && ((p[1] == 'G' && p[2] == 'A') || (p[1] == 'A' && (p[2] == 'G' || p[2] == 'A')));
+      else stop = p[pl - 1] == 'A' && ((p[pl - 3] == 'T' && (p[pl - 2] == 'C' || p[pl - 2] == 'T')) || (p[pl - 3] == 'C' && p[pl - 2] == 'T'));
+      if (stop) flags |= MPH_NF_STOP;
+    }
+  }
+  out->flags = flags;
+  out->seq_len = (uint16_t)len;
+  out->germ_len = 0;
+  out->n_var = 0; out->n_som = 0; out->brk = 0;
+  out->n_prof = (uint8_t)(nv < 255 ? nv : 255);  // every window variant is visited and left unset
+  out->seq_off = 0xFFFFFFFFu;
+  out->profile = 0;
+  out->pad2 = 0;
+  return err;
+}
+
+// Forward strand, normal mode: iteration at which the read is pushed (:974-1003) or 0xFFFFFFFF if it
+// is not an observation of window k. One copy only: s(k) grows strictly, a read is fetched once.
+MPH_HD uint32_t mph_nrm_fwd_entry(const MphSegment& g, uint32_t k, const MphGeom& gk, uint32_t start, uint32_t end) {
+  if (end < gk.e) return 0xFFFFFFFFu;
+  const uint32_t s0 = g.off0 - g.ceo;
+  if (start <= s0) return (int64_t)start < (int64_t)s0 - (int64_t)g.K ? 0xFFFFFFFFu : 0u;
+  if (start <= g.off0) return 0xFFFFFFFFu;  // starts in (s0, off0] are never fetched when ceo > 0
+  const uint32_t k_ins = start - g.off0;
+  return k_ins > k ? 0xFFFFFFFFu : k_ins;
 }

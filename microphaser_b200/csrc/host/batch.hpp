@@ -77,6 +77,7 @@ struct GeneMeta {
 
 struct Batch {
   uint32_t window_len = 27;
+  int mode = 0;  // 0 somatic (src/microphasing.rs), 1 normal (src/normal_microphasing.rs)
   // reads (SoA)
   std::vector<uint32_t> read_start, read_end, read_vlo, read_seq_off, read_cig_off;
   std::vector<uint16_t> read_lseq, read_ncig;
@@ -111,7 +112,10 @@ inline uint8_t base_code(uint8_t c) {
 
 class Packer {
  public:
-  explicit Packer(uint32_t window_len, uint32_t chunk_windows = 32) : chunk_windows_(chunk_windows) { b_.window_len = window_len; }
+  explicit Packer(uint32_t window_len, int mode = 0, uint32_t chunk_windows = 32) : chunk_windows_(chunk_windows) {
+    b_.window_len = window_len;
+    b_.mode = mode;
+  }
 
   // `reads`: the records bam::RecordBuffer holds for this gene after the mapq filter, in file order;
   // `max_read_len`: max seq().len() over them (:913-915); `sites`: variant_tree in ascending position
@@ -133,7 +137,7 @@ class Packer {
     }
     bool multi = false;
     gm.var_lo = uint32_t(b_.vars.size());
-    uint32_t max_del = 0, max_ins = 0;
+    uint32_t max_del = 0, max_ins = 0, n_del = 0;
     bool has_fs = false;
     for (auto& site : sites) {
       if (site.size() > 1) multi = true;
@@ -150,6 +154,7 @@ class Packer {
           if (hv.len + 1 > max_ins) max_ins = hv.len + 1;
         }
         if (hv.kind == MPH_DEL && hv.len > max_del) max_del = hv.len;
+        if (hv.kind == MPH_DEL) ++n_del;
         if (hv.fs()) has_fs = true;
         b_.vars.push_back(v);
         b_.var_prot.push_back(hv.prot_change);
@@ -160,6 +165,7 @@ class Packer {
     // assembled sequences can grow by insertions / deleted reference bases
     uint32_t need = wl + 8 + 2 * (max_ins + max_del);
     need = (need + 15u) & ~15u;
+    if (b_.mode == 1) need += 16;  // the extra reference base after every variant block (normal_microphasing.rs:476)
     if (need > b_.seq_cap) b_.seq_cap = need;
 
     // reads
@@ -203,7 +209,7 @@ class Packer {
         b_.read_cig_off.push_back(0);
         b_.read_ncig.push_back(0);
       }
-      if (strand == 1) {  // `contains` only bites on the reverse strand (keys are read starts, :328-331)
+      if (strand == 1 && b_.mode == 0) {  // `contains` only bites on the reverse strand (keys are read starts, :328-331); normal mode has none
         const uint64_t key = r.qname_hash * 0x9E3779B97F4A7C15ull ^ (uint64_t(r.start) << 1);
         auto it = seen.find(key);
         if (it == seen.end()) {
@@ -224,7 +230,9 @@ class Packer {
 
     // transcripts -> segments
     const uint32_t ref_end = g.start + uint32_t(refseq.size());
-    const uint32_t margin = max_del + 2;
+    // somatic: one deletion can pull the walk past the window end (:560-563); normal: every applied
+    // deletion moves window_end (normal_microphasing.rs:457), so the overhang adds up
+    const uint32_t margin = b_.mode == 1 ? (max_del + 1) * std::min<uint32_t>(n_del, wl) + 2 : max_del + 2;
     for (auto& t : g.transcripts) {
       if (t.exons.empty()) continue;  // is_coding (:947)
       TxMeta tm;
@@ -238,7 +246,8 @@ class Packer {
         if (ex.start > ex.end) continue;  // :981
         exon_count += 1;
         const uint64_t exon_len = ex.end - ex.start;
-        const uint64_t ceo = exon_count == 1 ? ex.frame : (exon_rest == 0 ? 0 : 3 - exon_rest);
+        // somatic: the first exon takes the GTF frame column (microphasing.rs:989-995); normal: exon_rest only (normal_microphasing.rs:739-742)
+        const uint64_t ceo = (exon_count == 1 && b_.mode == 0) ? ex.frame : (exon_rest == 0 ? 0 : 3 - exon_rest);
         const bool is_short = exon_len < 3 ? true : uint64_t(wl) >= exon_len - ceo - (3 - ceo) % 3;
         if (ceo > exon_len || ceo > 2) throw Unsupported("transcript " + t.id + ": exon offset " + std::to_string(ceo) + " does not fit the exon");
         uint64_t ewl = !is_short ? wl : (exon_len - ceo) - ((exon_len - ceo) % 3);
@@ -275,7 +284,7 @@ class Packer {
         sg.read_lo = gm.read_lo; sg.read_hi = gm.read_hi;
         sg.var_lo = gm.var_lo; sg.var_hi = gm.var_hi;
         sg.max_span = max_span;
-        if (exon_count == 1) {  // start-loss positions (:1305-1316)
+        if (exon_count == 1 && b_.mode == 0) {  // start-loss positions (:1305-1316); normal mode has none
           const uint32_t lo = t.reverse ? (ex.end >= 3 ? ex.end - 3 : 0) : ex.start;
           const uint32_t hi = t.reverse ? ex.end : ex.start + 3;
           sg.sl_va = mph_var_lb(b_.vars.data(), gm.var_lo, gm.var_hi, lo);

@@ -96,11 +96,48 @@ inline int run_somatic(int argc, char** argv, const PhaseFn& phase) {
   return 0;
 }
 
+// microphaser normal <normal.bam> -r REF -b VCF [-w 27] [-t info.tsv] [-u] [-v]  (src/main.rs, src/cli.yaml `normal`)
+inline int run_normal(int argc, char** argv, const PhaseFn& phase) {
+  CliArgs a = parse_cli(argc, argv, 2, {{"ref", 'r', true}, {"variants", 'b', true}, {"window-len", 'w', true}, {"tsv", 't', true},
+                                        {"unsupported-allele-warning-only", 'u', false}, {"verbose", 'v', false}});
+  if (a.pos.size() != 1 || !a.opt.count("ref") || !a.opt.count("variants"))
+    throw std::runtime_error("error: The following required arguments were not provided: <normal-sample> --ref <FILE> --variants <FILE>");
+  mphio::BamFile bam(a.pos[0]);
+  mphio::VcfFile vcf(a.opt["variants"]);
+  mphio::FastaIndexed fasta(a.opt["ref"]);
+  Outputs o;
+  o.fasta = stdout;
+  const std::string tsv = a.opt.count("tsv") ? a.opt["tsv"] : "info.tsv";
+  o.tsv = fopen(tsv.c_str(), "wb");
+  if (!o.tsv) throw std::runtime_error("cannot create " + tsv);
+  IngestOptions io;
+  io.window_len = a.opt.count("window-len") ? uint32_t(std::stoul(a.opt["window-len"])) : 27;
+  io.warn_only = a.flags.count("unsupported-allele-warning-only") != 0;
+  io.mode = 1;
+  io.min_mapq = 0;
+  Packer packer(io.window_len, 1);
+  ingest(std::cin, bam, vcf, fasta, io, packer);
+  Batch& b = packer.batch();
+  PhaseRaw raw = phase(b);
+  if (raw.err & MPH_E_REF_RANGE) throw Fatal("index out of bounds: refseq");
+  if (raw.err & MPH_E_VARS_PER_WINDOW) throw Unsupported("more than 32 variants in one window / 64 in one read");
+  if (raw.err) throw std::runtime_error("device error bits " + std::to_string(raw.err));
+  ResidueNormal res(b, raw);
+  std::vector<OutRecord> recs;
+  ResidueStats st;
+  res.run(0, uint32_t(b.txs.size()), recs, st);
+  write_records(b, recs, o);
+  fclose(o.tsv);
+  fflush(stdout);
+  return 0;
+}
+
 inline int cli_main(int argc, char** argv, const PhaseFn& phase) {
   try {
     if (argc < 2) return 0;
     const std::string sub = argv[1];
     if (sub == "somatic") return run_somatic(argc, argv, phase);
+    if (sub == "normal") return run_normal(argc, argv, phase);
     throw std::runtime_error("error: unknown subcommand " + sub);
   } catch (const Fatal& e) {
     fflush(stdout);

@@ -182,7 +182,7 @@ struct ParsedGene {
 };
 
 // GTF streaming rules of `phase` (:1982-2125): gene / transcript / CDS / start_codon / three_prime_utr
-inline std::vector<ParsedGene> read_gtf(std::istream& in) {
+inline std::vector<ParsedGene> read_gtf(std::istream& in, int mode = 0) {
   std::vector<ParsedGene> genes;
   bool start_codon_found = false, three_prime_found = false;
   std::string last_chrom = "not_yet_set";
@@ -252,7 +252,7 @@ inline std::vector<ParsedGene> read_gtf(std::istream& in) {
       if (t.exons.empty()) throw Fatal("no exon record before start codon in GTF");
       if (r.strand == '+') t.exons.back().start = uint32_t(r.start - 1);
       else t.exons.back().end = uint32_t(r.end);
-    } else if (r.feature == "three_prime_utr") {
+    } else if (r.feature == "three_prime_utr" && mode == 0) {  // normal mode ignores UTR rows (normal_microphasing.rs:1405-1432)
       HostTranscript& t = cur_tx("no gene record before exon in GTF", "no transcript record before exon in GTF");
       if (three_prime_found) {
         t.exons.push_back(HostExon{uint32_t(r.start - 1), uint32_t(r.end), frame_of(r.frame)});
@@ -271,6 +271,7 @@ struct IngestOptions {
   uint32_t window_len = 27;
   bool warn_only = false;
   uint32_t min_mapq = 5;  // somatic: rec.mapq() < 5 is skipped (:910); normal mode has no filter
+  int mode = 0;
 };
 
 // Everything phase_gene fetches for one gene (:894-942), held until it is packed.
@@ -285,7 +286,7 @@ struct GeneInput {
 // Streams the GTF and fetches reads / variants / reference for every protein-coding gene, in GTF order.
 inline std::vector<GeneInput> ingest_genes(std::istream& gtf, ReadBuffer& reads, mphio::VcfFile& vcf, mphio::FastaIndexed& fasta,
                                            const IngestOptions& opt) {
-  std::vector<ParsedGene> genes = read_gtf(gtf);
+  std::vector<ParsedGene> genes = read_gtf(gtf, opt.mode);
   VariantBuffer variants(vcf);
   std::vector<GeneInput> out;
   for (auto& pg : genes) {

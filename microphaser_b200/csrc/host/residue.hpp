@@ -30,7 +30,8 @@ struct PhaseRaw {
   std::vector<MphHap> iw_hap0;    // per interesting window: assembly of haplotype 0
   std::vector<MphHist> hist;      // extra histogram keys (whole arena)
   std::vector<MphHap> hapx;       // per extra key
-  std::vector<uint8_t> seq;       // sequence arena: slots of 2 * seq_cap bytes
+  std::vector<uint8_t> seq;       // sequence arena: slots of 2 * seq_cap bytes (normal mode: seq_cap bytes)
+  std::vector<uint32_t> win_depth;  // normal mode only, per enumerated window: depth | (plain window starts / ends with a stop codon) << 31
   uint32_t err = 0;
   uint64_t sum_depth = 0;         // over every enumerated window
 };
@@ -280,6 +281,7 @@ class Residue {
     for (size_t q = 0; q < n_keys; ++q) {
       const Key& key = keybuf[q];
       const MphHap& h = *key.info;
+      if (h.flags & MPH_HF_REFRANGE) throw Fatal("index out of bounds: refseq");  // the reference panics when it reaches this walk
       const uint64_t haplotype_frame = key.frame;
       const bool indel = (h.flags & MPH_HF_INDEL) != 0, insertion = (h.flags & MPH_HF_INSERTION) != 0;
       bool shift_is_set = false;

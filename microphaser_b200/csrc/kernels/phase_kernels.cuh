@@ -12,6 +12,7 @@ namespace mphk {
 struct DeviceBatch {
   // inputs
   uint32_t n_reads = 0, n_vars = 0, n_segs = 0, n_chunks = 0, n_windows = 0, seq_cap = 64, n_pairs = 0;
+  uint32_t mode = 0;        // 0 somatic, 1 normal (reference src/normal_microphasing.rs)
   uint32_t force_wide = 0;  // test hook (MPH_FORCE_WIDE=1): send every window with extra keys through k_window_hist_wide
   const uint32_t* read_start = nullptr;
   const uint32_t* read_end = nullptr;
@@ -57,6 +58,7 @@ struct DeviceBatch {
   unsigned long long* sum_depth = nullptr;
   unsigned long long* live_depth = nullptr;
   const uint32_t* seg_live = nullptr;  // per segment: number of windows the reference reaches
+  uint32_t* win_depth = nullptr;       // normal mode, per window: depth | (plain window begins / ends with a stop codon) << 31
 };
 
 enum { CTR_HIST = 0, CTR_SEQ = 1, CTR_NIW = 2, CTR_ERR = 3, CTR_OVF = 4 };

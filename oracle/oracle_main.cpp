@@ -113,8 +113,17 @@ int run(int argc, char** argv) {
     std::string tsv = a.opt.count("tsv") ? a.opt["tsv"] : "info.tsv";
     uint64_t wl = a.opt.count("window-len") ? std::stoull(a.opt["window-len"]) : 27;
     oracle::normal::Writers w{{stdout}, {open_out(tsv)}};
+    auto t1 = std::chrono::steady_clock::now();
     oracle::normal::phase(fasta, std::cin, vcf, bam, w, wl, a.flags.count("unsupported-allele-warning-only") != 0);
+    auto t2 = std::chrono::steady_clock::now();
     fclose(w.tsv.f);
+    if (st && *st) {
+      FILE* sf = fopen(st, "w");
+      auto& s = oracle::normal::stats();
+      fprintf(sf, "{\"windows\": %llu, \"read_windows\": %llu, \"load_s\": %.6f, \"phase_s\": %.6f}\n", (unsigned long long)s.windows,
+              (unsigned long long)s.read_windows, std::chrono::duration<double>(t1 - t0).count(), std::chrono::duration<double>(t2 - t1).count());
+      fclose(sf);
+    }
     return 0;
   }
   if (sub == "build_reference") {

@@ -106,8 +106,9 @@ def run_cli(binary, case_dir, out_dir, gtf="annotation.gtf", ref=None, subcomman
         return subprocess.run(cmd, stdin=gin, stdout=fout, stderr=subprocess.PIPE, timeout=900)
 
 
-def read_outputs(out_dir):
-    return {n: open(os.path.join(out_dir, n), "rb").read() for n in ("out.fa", "out.tsv", "out.normal.fa")}
+def read_outputs(out_dir, subcommand="somatic"):
+    names = ("out.fa", "out.tsv", "out.normal.fa") if subcommand == "somatic" else ("out.fa", "out.tsv")
+    return {n: open(os.path.join(out_dir, n), "rb").read() for n in names}
 
 
 @pytest.fixture(scope="session")

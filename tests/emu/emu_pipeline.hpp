@@ -20,7 +20,82 @@ inline uint32_t partner_of(const Batch& b, uint32_t r) {
   return 0xFFFFFFFFu;
 }
 
-inline PhaseRaw phase(const Batch& b) {
+// normal mode (reference src/normal_microphasing.rs)
+inline PhaseRaw phase_normal(const Batch& b) {
+  PhaseRaw raw;
+  const size_t nr = b.read_start.size();
+  std::vector<MphCall> calls(nr);
+  for (size_t r = 0; r < nr; ++r) {
+    MphRead rd{b.read_start[r], b.read_end[r], b.read_vlo[r], b.read_lseq[r], b.read_nv[r], b.read_ncig[r]};
+    const uint8_t* bases = rd.nv ? b.bases.data() + size_t(b.read_seq_off[r]) * 16 : nullptr;
+    calls[r] = mph_call_read(rd, bases, b.cigars.data() + b.read_cig_off[r], b.vars.data(), false);
+    if (b.read_flags[r] & MPH_RF_OVERFLOW) raw.err |= MPH_E_VARS_PER_WINDOW;
+  }
+  raw.win_depth.assign(b.n_windows, 0);
+  std::vector<uint8_t> seqbuf(b.seq_cap);
+  for (const MphChunk& ch : b.chunks) {
+    const MphSegment& sg = b.segs[ch.seg];
+    const bool rev = sg.flags & MPH_SF_REVERSE;
+    for (uint32_t i = ch.i_first; i < ch.i_first + ch.n; ++i) {
+      const uint32_t k = sg.k_first + i * sg.k_stride;
+      const uint32_t widx = sg.win_base + i;
+      const MphGeom g = mph_geom(sg, k);
+      const uint32_t va = mph_var_lb(b.vars.data(), sg.var_lo, sg.var_hi, g.s);
+      const uint32_t vb = mph_var_lb(b.vars.data(), sg.var_lo, sg.var_hi, g.e);
+      const uint32_t nv = vb - va;
+      if (nv > 64) raw.err |= MPH_E_VARS_PER_WINDOW;
+      uint32_t rlo, rhi;
+      mph_candidate_range(sg, b.read_start.data(), g, &rlo, &rhi);
+      uint32_t depth = 0;
+      std::map<uint64_t, uint32_t> hist;
+      for (uint32_t r = rlo; r < rhi; ++r) {
+        const uint32_t st = b.read_start[r], en = b.read_end[r], vlo = b.read_vlo[r];
+        if (!rev) {
+          const uint32_t kp = mph_nrm_fwd_entry(sg, k, g, st, en);
+          if (kp == 0xFFFFFFFFu) continue;
+          ++depth;
+          if (nv) hist[mph_nrm_hap(sg, b.vars.data(), kp, k, va, vb, vlo, calls[r].S)] += 1;
+        } else {
+          uint32_t kc;
+          const uint32_t copies = mph_nrm_rev_copies(sg, k, g, st, en, &kc);
+          if (!copies) continue;
+          depth += copies;
+          if (!nv) continue;
+          if (calls[r].S == 0) { hist[0] += copies; continue; }
+          for (uint32_t c = 0; c < copies; ++c) hist[mph_nrm_hap(sg, b.vars.data(), k - c, k, va, vb, vlo, calls[r].S)] += 1;
+        }
+      }
+      raw.sum_depth += depth;
+      MphHap h0;
+      raw.err |= mph_nrm_plain(sg, g, b.ref.data(), nv, &h0);
+      raw.win_depth[widx] = depth | ((nv == 0 && (h0.flags & MPH_NF_STOP)) ? 0x80000000u : 0u);
+      if (!nv) continue;
+      MphWinOut wo;
+      wo.depth = depth;
+      wo.c0 = 0;
+      wo.extra_off = uint32_t(raw.hist.size());
+      wo.n_extra = 0;
+      for (auto& kv : hist) {
+        if (kv.first == 0) { wo.c0 = kv.second; continue; }
+        MphHap hx;
+        raw.err |= mph_nrm_assemble(sg, g, b.vars.data(), va, vb, b.ref.data(), b.ins_bytes.data(), kv.first, kv.second == depth, seqbuf.data(), b.seq_cap, &hx);
+        hx.seq_off = uint32_t(raw.seq.size());
+        raw.seq.resize(raw.seq.size() + b.seq_cap, 0);
+        memcpy(&raw.seq[hx.seq_off], seqbuf.data(), std::min<uint32_t>(hx.seq_len, b.seq_cap));
+        hx.flags |= MPH_NF_SEQ;
+        raw.hist.push_back(MphHist{kv.first, kv.second, 0});
+        raw.hapx.push_back(hx);
+        ++wo.n_extra;
+      }
+      raw.iw.push_back(widx);
+      raw.iw_out.push_back(wo);
+      raw.iw_hap0.push_back(h0);
+    }
+  }
+  return raw;
+}
+
+inline PhaseRaw phase_somatic(const Batch& b) {
   PhaseRaw raw;
   const size_t nr = b.read_start.size();
   // K1
@@ -119,5 +194,7 @@ inline PhaseRaw phase(const Batch& b) {
   }
   return raw;
 }
+
+inline PhaseRaw phase(const Batch& b) { return b.mode == 1 ? phase_normal(b) : phase_somatic(b); }
 
 }  // namespace mphemu

@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Differential fuzzing: product host code + device logic (CPU emulator or CUDA CLI) vs the oracle
-on random synthetic inputs.  usage: fuzz_compare.py <binary> <n_seeds> [first_seed] [profile]"""
+on random synthetic inputs.  usage: fuzz_compare.py <binary> <n_seeds> [first_seed] [profile] [somatic|normal]"""
 import os
 import subprocess
 import sys
@@ -20,9 +20,10 @@ PROFILES = {
 }
 
 
-def run(binary, d, out):
-    cmd = [binary, "somatic", os.path.join(d, "reads.bam"), "-r", os.path.join(d, "ref.fa"), "-b", os.path.join(d, "variants.vcf"),
-           "-t", out + ".tsv", "-n", out + ".normal.fa"]
+def run(binary, d, out, sub="somatic"):
+    cmd = [binary, sub, os.path.join(d, "reads.bam"), "-r", os.path.join(d, "ref.fa"), "-b", os.path.join(d, "variants.vcf"), "-t", out + ".tsv"]
+    if sub == "somatic":
+        cmd += ["-n", out + ".normal.fa"]
     with open(os.path.join(d, "annotation.gtf")) as gin, open(out + ".fa", "wb") as fo:
         r = subprocess.run(cmd, stdin=gin, stdout=fo, stderr=subprocess.PIPE, timeout=600)
     return r.returncode, r.stderr.decode()[-400:]
@@ -32,7 +33,8 @@ def main():
     binary = sys.argv[1]
     n = int(sys.argv[2])
     first = int(sys.argv[3]) if len(sys.argv) > 3 else 1
-    profs = sys.argv[4].split(",") if len(sys.argv) > 4 else list(PROFILES)
+    profs = sys.argv[4].split(",") if len(sys.argv) > 4 and sys.argv[4] != "all" else list(PROFILES)
+    sub = sys.argv[5] if len(sys.argv) > 5 else "somatic"
     oracle = os.path.join(ROOT, "oracle", "_build", "mph_oracle")
     stats = dict(ok=0, both_fail=0, unsupported=0, mismatch=0, records=0)
     for seed in range(first, first + n):
@@ -41,8 +43,8 @@ def main():
         kw.update(seed=seed, n_genes=3, coverage=25.0)
         with tempfile.TemporaryDirectory() as d:
             synth.generate(d, synth.Params(**kw))
-            rc_o, err_o = run(oracle, d, os.path.join(d, "o"))
-            rc_p, err_p = run(binary, d, os.path.join(d, "p"))
+            rc_o, err_o = run(oracle, d, os.path.join(d, "o"), sub)
+            rc_p, err_p = run(binary, d, os.path.join(d, "p"), sub)
             if rc_o != 0 and rc_p != 0:
                 stats["both_fail"] += 1
                 continue
@@ -51,7 +53,7 @@ def main():
                 print("seed %d [%s]: unsupported: %s" % (seed, prof, err_p.strip().split("\n")[-1]))
                 continue
             same = rc_o == rc_p
-            for ext in (".fa", ".tsv", ".normal.fa"):
+            for ext in ((".fa", ".tsv", ".normal.fa") if sub == "somatic" else (".fa", ".tsv")):
                 a = open(os.path.join(d, "o") + ext, "rb").read()
                 b = open(os.path.join(d, "p") + ext, "rb").read()
                 same = same and a == b

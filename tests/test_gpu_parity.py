@@ -10,7 +10,7 @@ from conftest import GOLDEN, ROOT, materialize_reference, read_outputs, run_cli
 
 sys.path.insert(0, ROOT)
 from microphaser_b200 import synth  # noqa: E402
-from test_emu_parity import PROFILES, SOMATIC  # noqa: E402
+from test_emu_parity import NORMAL, PROFILES, SOMATIC  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 
@@ -137,3 +137,71 @@ def test_multi_device_sharding_matches_oracle(product, oracle_bin, tmp_path):
             c.close()
     assert read_outputs(str(o)) == read_outputs(str(p))
     assert len(read_outputs(str(o))["out.tsv"]) > 0
+
+
+# ---------------------------------------------------------------- `normal` mode (src/normal_microphasing.rs)
+@pytest.mark.parametrize("case", NORMAL)
+def test_cuda_normal_mode_matches_reference_golden(product, oracle_bin, case, tmp_path):
+    d = os.path.join(GOLDEN, case)
+    fa = materialize_reference(d, str(tmp_path))
+    res = run_cli(product[1], d, str(tmp_path), ref=fa, subcommand="normal")
+    assert res.returncode == 0, res.stderr.decode()
+    assert open(tmp_path / "out.fa", "rb").read() == open(os.path.join(d, "expected", "out.fa"), "rb").read()
+    o = tmp_path / "o"
+    o.mkdir()
+    assert run_cli(oracle_bin, d, str(o), ref=fa, subcommand="normal").returncode == 0
+    assert open(tmp_path / "out.tsv", "rb").read() == open(o / "out.tsv", "rb").read()
+
+
+@pytest.mark.parametrize("wide", [False, True])
+@pytest.mark.parametrize("profile,seed", [(p, s) for p in PROFILES for s in (41, 42, 43)])
+def test_cuda_normal_mode_matches_oracle_on_synthetic(product, oracle_bin, profile, seed, wide, tmp_path, monkeypatch):
+    if wide:
+        if seed != 41:
+            pytest.skip("the overflow kernel is exercised on one seed per profile")
+        monkeypatch.setenv("MPH_FORCE_WIDE", "1")
+    kw = dict(PROFILES[profile])
+    kw.update(seed=seed * 15485863 + len(profile), n_genes=4, coverage=30.0)
+    d = str(tmp_path / "in")
+    synth.generate(d, synth.Params(**kw))
+    o, p = tmp_path / "o", tmp_path / "p"
+    o.mkdir()
+    p.mkdir()
+    ro = run_cli(oracle_bin, d, str(o), subcommand="normal")
+    rp = run_cli(product[1], d, str(p), subcommand="normal")
+    if rp.returncode == 3:
+        pytest.skip("input needs the serial replay path: " + rp.stderr.decode().strip()[-120:])
+    assert (ro.returncode == 0) == (rp.returncode == 0), (ro.stderr.decode()[-300:], rp.stderr.decode()[-300:])
+    if ro.returncode == 0:
+        assert read_outputs(str(o), "normal") == read_outputs(str(p), "normal")
+
+
+def test_c_abi_run_normal_matches_oracle_with_statistics(product, oracle_bin, tmp_path):
+    """mph_run_normal through the binding; window and observation counts against the oracle's own counters."""
+    import json
+    import subprocess
+    import microphaser_b200 as m
+    d = str(tmp_path / "in")
+    synth.generate(d, synth.Params(seed=977, n_genes=12, coverage=30.0, indel_frac=0.1, multiallelic_frac=0.1))
+    o, p = tmp_path / "o", tmp_path / "p"
+    o.mkdir()
+    p.mkdir()
+    env = dict(os.environ, MPH_ORACLE_STATS=str(tmp_path / "stats.json"))
+    with open(os.path.join(d, "annotation.gtf")) as gin, open(o / "out.fa", "wb") as fo:
+        ro = subprocess.run([oracle_bin, "normal", os.path.join(d, "reads.bam"), "-r", os.path.join(d, "ref.fa"), "-b",
+                             os.path.join(d, "variants.vcf"), "-t", str(o / "out.tsv")], stdin=gin, stdout=fo, stderr=subprocess.PIPE, env=env)
+    assert ro.returncode == 0, ro.stderr.decode()
+    ctx = m.Context(0)
+    try:
+        ctx.run_normal(os.path.join(d, "reads.bam"), os.path.join(d, "ref.fa"), os.path.join(d, "variants.vcf"),
+                       os.path.join(d, "annotation.gtf"), str(p / "out.fa"), str(p / "out.tsv"))
+    except m.MphError as e:
+        if e.code == m.MPH_ERR_UNSUPPORTED:
+            pytest.skip(str(e))
+        raise
+    t = ctx.timing()
+    ctx.close()
+    assert read_outputs(str(o), "normal") == read_outputs(str(p), "normal")
+    if os.path.exists(tmp_path / "stats.json"):
+        st = json.load(open(tmp_path / "stats.json"))
+        assert t["windows"] == st["windows"] and t["read_windows"] == st["read_windows"]
