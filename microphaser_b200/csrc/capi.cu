@@ -86,9 +86,11 @@ struct mph_ctx {
   std::string last_error;
   const mph_batch* cur = nullptr;
   mphk::DeviceBatch d;
-  DevBuf<uint32_t> read_start, read_end, read_vlo, read_seq_off, read_cig_off, cigars, block_counts, iw, counters, seg_live, ovf_list, stopmap, hist_win, win_depth;
+  DevBuf<uint32_t> read_start, read_end, read_vlo, read_seq_off, read_cig_off, cigars, block_counts, iw, counters, seg_live, ovf_list, stopmap, hist_win, win_depth, seg_chunk0, o_read, o_frame, win_voff, vlist, iw_voff;
   DevBuf<uint16_t> read_lseq, read_ncig;
-  DevBuf<uint8_t> read_nv, read_flags, bases, ins_bytes, ref, call_flags, seq, win_flag;
+  DevBuf<uint8_t> read_nv, read_flags, bases, ins_bytes, ref, call_flags, seq, win_flag, o_flags, o_inmat;
+  DevBuf<MphReplayTx> replay;
+  DevBuf<uint64_t> o_hap;
   DevBuf<uint2> pairs;
   DevBuf<MphVar> vars;
   DevBuf<MphSegment> segs;
@@ -146,7 +148,8 @@ void finish_batch(mph_batch* mb, bool pin) {
   auto bytes = [](auto& v) { return v.size() * sizeof(v[0]); };
   mb->h2d_bytes = bytes(b.read_start) + bytes(b.read_end) + bytes(b.read_vlo) + bytes(b.read_seq_off) + bytes(b.read_cig_off) +
                   bytes(b.read_lseq) + bytes(b.read_ncig) + bytes(b.read_nv) + bytes(b.read_flags) + bytes(b.bases) + bytes(b.cigars) +
-                  bytes(b.vars) + bytes(b.ins_bytes) + bytes(b.segs) + bytes(b.chunks) + bytes(b.ref) + bytes(b.stopmap) + bytes(mb->pairs);
+                  bytes(b.vars) + bytes(b.ins_bytes) + bytes(b.segs) + bytes(b.chunks) + bytes(b.ref) + bytes(b.stopmap) + bytes(mb->pairs) +
+                  bytes(b.replay) + (b.replay.empty() ? 0 : bytes(b.seg_chunk0));
   if (pin) {
     auto reg = [&](auto& v) {
       if (v.empty()) return;
@@ -178,6 +181,7 @@ void upload(mph_ctx* c, const mph_batch* mb) {
   h2d(c, c->read_ncig, b.read_ncig); h2d(c, c->read_nv, b.read_nv); h2d(c, c->read_flags, b.read_flags); h2d(c, c->bases, b.bases);
   h2d(c, c->cigars, b.cigars); h2d(c, c->vars, b.vars); h2d(c, c->ins_bytes, b.ins_bytes); h2d(c, c->segs, b.segs);
   h2d(c, c->chunks, b.chunks); h2d(c, c->ref, b.ref); h2d(c, c->stopmap, b.stopmap); h2d(c, c->pairs, mb->pairs);
+  if (!b.replay.empty()) { h2d(c, c->replay, b.replay); h2d(c, c->seg_chunk0, b.seg_chunk0); }
   CU(cudaEventRecord(c->ev[1], c->stream));
   const size_t nr = b.n_reads(), nw = size_t(b.n_windows);
   c->call_S.ensure(nr + 1); c->call_B.ensure(nr + 1); c->call_flags.ensure(nr + 1);
@@ -203,6 +207,17 @@ void upload(mph_ctx* c, const mph_batch* mb) {
   d.ovf_list = c->ovf_list.p;
   d.iw = c->iw.p; d.iw_out = c->iw_out.p; d.iw_hap0 = c->iw_hap0.p; d.counters = c->counters.p;
   d.sum_depth = c->sums.p; d.live_depth = c->sums.p + 1; d.seg_live = c->seg_live.p;
+  d.n_replay = uint32_t(b.replay.size());
+  d.win_voff = nullptr; d.iw_voff = nullptr;
+  if (d.n_replay) {
+    const size_t no = size_t(b.replay_obs) + 1;
+    c->o_read.ensure(no); c->o_hap.ensure(no); c->o_frame.ensure(no); c->o_flags.ensure(no); c->o_inmat.ensure(no);
+    c->win_voff.ensure(nw + 1); c->iw_voff.ensure(nw + 1);
+    if (c->vlist.cap == 0) c->vlist.ensure(1 << 16);
+    d.replay = c->replay.p; d.seg_chunk0 = c->seg_chunk0.p;
+    d.o_read = c->o_read.p; d.o_hap = reinterpret_cast<uint64_t*>(c->o_hap.p); d.o_frame = c->o_frame.p; d.o_flags = c->o_flags.p; d.o_inmat = c->o_inmat.p;
+    d.win_voff = c->win_voff.p; d.iw_voff = c->iw_voff.p;
+  }
   d.mode = uint32_t(b.mode);
   if (b.mode == 1) { c->win_depth.ensure(nw + 1); d.win_depth = c->win_depth.p; }
   c->cur = mb;
@@ -219,10 +234,15 @@ void run_kernels(mph_ctx* c) {
   d.seq = c->seq.p; d.seq_cap_bytes = uint32_t(std::min<size_t>(c->seq.cap, 0xFFFFFF00u));
   CU(cudaMemsetAsync(c->counters.p, 0, 8 * sizeof(uint32_t), c->stream));
   CU(cudaMemsetAsync(c->sums.p, 0, 2 * sizeof(unsigned long long), c->stream));
+  if (d.n_replay) {
+    d.vlist = c->vlist.p; d.vlist_cap = uint32_t(std::min<size_t>(c->vlist.cap, 0xFFFFFF00u));
+    CU(cudaMemsetAsync(c->win_voff.p, 0xFF, (size_t(d.n_windows) + 1) * sizeof(uint32_t), c->stream));
+  }
   CU(cudaEventRecord(c->ev[2], c->stream));
   mphk::launch_allele_call(d, c->stream);
   CU(cudaEventRecord(c->ev[3], c->stream));
   mphk::launch_window_hist(d, c->stream);
+  mphk::launch_replay(d, c->stream);
   CU(cudaEventRecord(c->ev[4], c->stream));
   mphk::launch_assemble(d, c->stream);
   CU(cudaEventRecord(c->ev[5], c->stream));
@@ -239,7 +259,8 @@ void collect(mph_ctx* c, mph_result** out) {
     CU(cudaMemcpyAsync(ctr, c->counters.p, sizeof ctr, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     const uint32_t err = ctr[mphk::CTR_ERR];
-    if ((err & (MPH_E_HIST_OVERFLOW | MPH_E_SEQ_OVERFLOW)) && attempt < 6) {
+    if ((err & (MPH_E_HIST_OVERFLOW | MPH_E_SEQ_OVERFLOW | MPH_E_VLIST_OVERFLOW)) && attempt < 6) {
+      if (err & MPH_E_VLIST_OVERFLOW) c->vlist.ensure(size_t(ctr[mphk::CTR_VLIST]) * 2 + 1024);
       if (err & MPH_E_HIST_OVERFLOW) { c->hist.ensure(size_t(ctr[mphk::CTR_HIST]) * 2 + 1024); c->hapx.ensure(c->hist.cap); }
       if (err & MPH_E_SEQ_OVERFLOW) c->seq.ensure(size_t(ctr[mphk::CTR_SEQ]) * 2 + 4096);
       run_kernels(c);
@@ -257,6 +278,7 @@ void collect(mph_ctx* c, mph_result** out) {
   if (raw.err & MPH_E_REF_RANGE) throw Fatal("slice index out of range: refseq");
   if (raw.err & MPH_E_VARS_PER_WINDOW) throw Unsupported("more than 32 variants in one window / 64 inside one read");
   if (raw.err & MPH_E_KEYS_PER_WINDOW) throw Unsupported("more than 32 distinct haplotypes in one window");
+  if (raw.err & MPH_E_REPLAY_PANIC) throw Fatal("matrix replay: drain range out of bounds / read starts right of variant");
   if (raw.err) throw std::logic_error("device error bits " + std::to_string(raw.err));
   const uint32_t n_iw = ctr[mphk::CTR_NIW], n_hist = ctr[mphk::CTR_HIST], n_seq = ctr[mphk::CTR_SEQ];
   raw.iw.resize(n_iw); raw.iw_out.resize(n_iw); raw.iw_hap0.resize(n_iw); raw.hist.resize(n_hist); raw.hapx.resize(n_hist); raw.seq.resize(n_seq);
@@ -271,6 +293,11 @@ void collect(mph_ctx* c, mph_result** out) {
     CU(cudaMemcpyAsync(raw.hapx.data(), c->hapx.p, n_hist * sizeof(MphHap), cudaMemcpyDeviceToHost, c->stream));
   }
   if (n_seq) CU(cudaMemcpyAsync(raw.seq.data(), c->seq.p, n_seq, cudaMemcpyDeviceToHost, c->stream));
+  const uint32_t n_vl = c->d.n_replay ? std::min<uint32_t>(ctr[mphk::CTR_VLIST], c->d.vlist_cap) : 0;
+  raw.iw_voff.resize(c->d.n_replay ? n_iw : 0);
+  raw.vlist.resize(n_vl);
+  if (c->d.n_replay && n_iw) CU(cudaMemcpyAsync(raw.iw_voff.data(), c->iw_voff.p, n_iw * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  if (n_vl) CU(cudaMemcpyAsync(raw.vlist.data(), c->vlist.p, size_t(n_vl) * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
   const bool normal_mode = b.mode == 1;
   raw.win_depth.resize(normal_mode ? size_t(b.n_windows) : 0);
   if (normal_mode && b.n_windows) CU(cudaMemcpyAsync(raw.win_depth.data(), c->win_depth.p, size_t(b.n_windows) * 4, cudaMemcpyDeviceToHost, c->stream));
@@ -280,7 +307,7 @@ void collect(mph_ctx* c, mph_result** out) {
   CU(cudaStreamSynchronize(c->stream));
   CU(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
   c->timing.d2h_ms = ms;
-  c->timing.d2h_bytes = sizeof ctr + sizeof sums + size_t(n_iw) * (4 + sizeof(MphWinOut) + sizeof(MphHap)) + size_t(n_hist) * (sizeof(MphHist) + sizeof(MphHap)) + n_seq + raw.win_depth.size() * 4;
+  c->timing.d2h_bytes = sizeof ctr + sizeof sums + size_t(n_iw) * (4 + sizeof(MphWinOut) + sizeof(MphHap)) + size_t(n_hist) * (sizeof(MphHist) + sizeof(MphHap)) + n_seq + raw.win_depth.size() * 4 + (raw.iw_voff.size() + raw.vlist.size()) * 4;
   raw.sum_depth = sums[0];
 
   // host residue: the serial part of the window loop, transcripts are independent

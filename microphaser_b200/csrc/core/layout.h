@@ -44,6 +44,7 @@ enum {
   MPH_SF_FIRST_EXON = 4,  // exon_count == 1
   MPH_SF_LAST_EXON = 8,
   MPH_SF_HAS_FS = 16,     // the gene carries frameshifting variants: every iteration is a window
+  MPH_SF_REPLAY = 32,     // the transcript goes through the serial replay (core/replay_core.h), not the closed form
 };
 
 // One processed exon of one transcript, 96 B.
@@ -151,5 +152,8 @@ enum {
   MPH_E_SEQ_OVERFLOW = 2,    // sequence arena exhausted  -> host retries with a larger arena
   MPH_E_KEYS_PER_WINDOW = 4, // more distinct keys in one window than a warp table holds
   MPH_E_REF_RANGE = 8,       // reference index out of the shipped slice (reference: slice panic)
-  MPH_E_VARS_PER_WINDOW = 16 // > 64 variants in one window (reference: shift overflow)
+  MPH_E_VARS_PER_WINDOW = 16, // > 64 variants in one window (reference: shift overflow)
+  MPH_E_REPLAY_PANIC = 32,    // serial replay: the reference panics here (drain out of range, read right of a variant, inverted range)
+  MPH_E_VLIST_OVERFLOW = 64,  // column-list arena exhausted -> host retries with a larger arena
+  MPH_E_REPLAY_INPUT = 128    // serial replay: observation scratch too small or read bases not shipped (internal)
 };

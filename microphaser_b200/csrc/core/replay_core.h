@@ -1,0 +1,336 @@
+// replay_core.h — serial replay of the ObservationMatrix for transcripts the closed form of
+// phase_core.h does not cover (reference src/microphasing.rs; line numbers refer to that file):
+//   * an observation survives from one exon into the next (cleanup_reads :259-278 keeps it), e.g. a
+//     spliced read or an intron shorter than a read;
+//   * the "stale column" of reverse-strand exons: at the last iteration `offset == old_offset`
+//     (:1159) suppresses the removal of the variants at exon.start + window_len, which then stay in
+//     the matrix — shifted through every later shrink_left — for the rest of the transcript.
+// Both make the matrix state depend on the whole history of the transcript, so the replay runs the
+// reference's own sequence of matrix operations (cleanup_reads, shrink_left, push_read,
+// extend_right :220-343 in the order of the window loop :1119-1343) with one observation list per
+// transcript. It emits, for every enumerated window, what the closed-form kernel emits (depth and
+// the (haplotype, frame) histogram) plus the matrix's variant columns, which no longer equal the
+// variants inside the window.
+//
+// Shared by the CUDA kernel k_replay (one warp per transcript, csrc/kernels/phase_kernels.cu) and the
+// test-only CPU emulator. All functions are MPH_HD.
+#pragma once
+#include "phase_core.h"
+
+#define MPH_RP_MAXCOLS 64
+#define MPH_RP_KEYS 32
+
+// one replayed transcript, 32 B
+typedef struct {
+  uint32_t seg_lo, seg_hi;    // its segments
+  uint32_t read_lo, read_hi;  // the gene's reads
+  uint32_t obs_off, obs_cap;  // slice of the observation scratch arrays
+  uint32_t sl_va, sl_vb;      // start-loss variant range of the first exon (:1305-1316)
+} MphReplayTx;
+
+typedef struct {
+  // inputs (same arrays as the closed-form kernels)
+  const uint32_t* read_start; const uint32_t* read_end; const uint32_t* read_vlo; const uint32_t* read_seq_off; const uint32_t* read_cig_off;
+  const uint16_t* read_lseq; const uint16_t* read_ncig; const uint8_t* read_nv; const uint8_t* read_flags;
+  const uint8_t* bases; const uint32_t* cigars;
+  const uint64_t* call_S; const uint64_t* call_B;
+  const uint32_t* pairs; uint32_t n_pairs;  // (read, partner) interleaved, sorted by read
+  const MphVar* vars; const MphSegment* segs; const uint32_t* seg_chunk0;
+  const uint32_t* stopmap; const uint8_t* ref;
+  // scratch: observation list
+  uint32_t* o_read; uint64_t* o_hap; uint32_t* o_frame; uint8_t* o_flags;
+  uint8_t* o_inmat;  // per gene read (obs_off + read - read_lo): the read is an observation right now
+  // outputs
+  MphWinOut* win_out; MphHist* hist; uint32_t* hist_win; uint32_t hist_cap;
+  MphHap* hap0; uint8_t* win_flag;
+  uint32_t* win_voff;  // per window: offset of its column list in vlist (entry 0 = count), 0xFFFFFFFF = the window's own variants
+  uint32_t* vlist; uint32_t vlist_cap;
+  uint32_t* counters;  // CTR_* of phase_kernels.cuh
+  unsigned long long* sum_depth;
+} MphReplayCtx;
+
+enum { MPH_RP_CTR_HIST = 0, MPH_RP_CTR_ERR = 3, MPH_RP_CTR_VLIST = 5 };
+
+#ifdef __CUDA_ARCH__
+#define MPH_RP_ADD(p, v) atomicAdd((p), (v))
+#define MPH_RP_OR(p, v) atomicOr((p), (v))
+#define MPH_RP_ADD64(p, v) atomicAdd((p), (unsigned long long)(v))
+#else
+static inline uint32_t mph_rp_add_host(uint32_t* p, uint32_t v) { const uint32_t o = *p; *p += v; return o; }
+#define MPH_RP_ADD(p, v) mph_rp_add_host((p), (v))
+#define MPH_RP_OR(p, v) (*(p) |= (v))
+#define MPH_RP_ADD64(p, v) (*(p) += (unsigned long long)(v))
+#endif
+
+// supports_variant (:95-139) and bad_quality (:78-93) of one (read, variant) pair. Variants inside
+// the alignment come from the K1 masks; a matrix column outside it (stale column) is evaluated here.
+MPH_HD void mph_rp_eval(const MphReplayCtx& c, uint32_t r, uint32_t v, bool* sup, bool* bad, uint32_t* err) {
+  const uint32_t vlo = c.read_vlo[r], nv = c.read_nv[r];
+  if (v >= vlo && v - vlo < nv) {
+    *sup = (c.call_S[r] >> (v - vlo)) & 1;
+    *bad = (c.call_B[r] >> (v - vlo)) & 1;
+    return;
+  }
+  const MphVar var = c.vars[v];
+  const uint32_t start = c.read_start[r], l_seq = c.read_lseq[r];
+  *sup = false;
+  *bad = false;
+  if (start > var.pos) { *err |= MPH_E_REPLAY_PANIC; return; }  // "bug: read starts right of variant" (:160-167)
+  const uint32_t soff = c.read_seq_off[r];
+  const uint32_t ncig = c.read_ncig[r];
+  const uint32_t* cig = c.cigars + c.read_cig_off[r];
+  if (var.kind == MPH_SNV) {
+    if (soff == 0xFFFFFFFFu) { *err |= MPH_E_REPLAY_INPUT; return; }
+    const uint8_t* b = c.bases + (size_t)soff * 16;
+    const uint8_t* lowq = b + ((l_seq + 1u) >> 1);
+    const uint32_t rel = var.pos - start;
+    if (rel < l_seq && ((lowq[rel >> 3] >> (rel & 7u)) & 1u)) { *bad = true; return; }
+    uint32_t q;
+    if (mph_read_pos(cig, ncig, l_seq, start, var.pos, &q) && q < l_seq) {
+      const uint8_t x = b[q >> 1];
+      *sup = ((q & 1u) ? (x & 15u) : (x >> 4)) == var.alt4;
+    }
+  } else {
+    const uint32_t want = var.kind == MPH_INS ? 1u : 2u;
+    for (uint32_t i = 0; i < ncig; ++i)
+      if ((cig[i] & 15u) == want && (cig[i] >> 4) == var.len) { *sup = true; break; }
+  }
+}
+
+// Observation::update_haplotype (:157-183) on packed state: frame = frame.0 | (frame.1 != 0) << 31, flags = bad_qual | start_loss << 1
+MPH_HD void mph_rp_update(const MphReplayCtx& c, const MphReplayTx& t, uint32_t r, uint32_t i, uint32_t v, uint64_t* hap, uint32_t* frame,
+                          uint8_t* flags, uint32_t* err) {
+  const MphVar& var = c.vars[v];
+  const uint32_t fs = (var.flags & MPH_VF_FS_MASK) >> MPH_VF_FS_SHIFT;
+  bool sup, bad;
+  mph_rp_eval(c, r, v, &sup, &bad, err);
+  if (fs > 0 && var.pos != 0) *frame |= 0x80000000u;
+  if (sup) {
+    if (v >= t.sl_va && v < t.sl_vb) *flags |= 2;
+    *hap |= (uint64_t)1 << (i & 63u);
+    *frame = (*frame & 0x80000000u) | (((*frame & 0x7FFFFFFFu) + fs) & 0x7FFFFFFFu);
+  }
+  if (bad || (*flags & 3)) {
+    *hap = 0;
+    *flags |= 1;
+  }
+}
+
+MPH_HD uint32_t mph_rp_partner(const MphReplayCtx& c, uint32_t r) {
+  uint32_t lo = 0, hi = c.n_pairs;
+  while (lo < hi) {
+    const uint32_t mid = lo + ((hi - lo) >> 1);
+    if (c.pairs[2 * mid] < r) lo = mid + 1;
+    else hi = mid;
+  }
+  return (lo < c.n_pairs && c.pairs[2 * lo] == r) ? c.pairs[2 * lo + 1] : 0xFFFFFFFFu;
+}
+
+// histogram + outputs of one enumerated window (the part of print_haplotypes :383-411 that reads the matrix)
+MPH_HD void mph_rp_emit(const MphReplayCtx& c, const MphReplayTx& t, const MphSegment& sg, uint32_t si, uint32_t i, uint32_t k, const MphGeom& g,
+                        uint32_t n_obs, const uint32_t* dq, uint32_t ncols, uint32_t* err) {
+  const uint32_t widx = sg.win_base + i;
+  MphHist table[MPH_RP_KEYS];
+  uint32_t n_keys = 0, c0 = 0;
+  for (uint32_t o = 0; o < n_obs; ++o) {
+    if (c.o_flags[t.obs_off + o] & 1) continue;
+    const uint64_t hap = c.o_hap[t.obs_off + o];
+    const uint32_t fr = c.o_frame[t.obs_off + o];
+    if (hap == 0 && fr == 0) { ++c0; continue; }
+    uint32_t x = 0;
+    for (; x < n_keys; ++x)
+      if (table[x].hap == hap && table[x].frame == fr) break;
+    if (x == n_keys) {
+      if (n_keys == MPH_RP_KEYS) { *err |= MPH_E_KEYS_PER_WINDOW; continue; }
+      table[x].hap = hap; table[x].frame = fr; table[x].count = 0;
+      ++n_keys;
+    }
+    table[x].count += 1;
+  }
+  for (uint32_t a = 1; a < n_keys; ++a) {  // BTreeMap order (:383,434): haplotype, frame.0, frame.1 != 0
+    const MphHist key = table[a];
+    uint32_t b = a;
+    while (b > 0) {
+      const MphHist& p = table[b - 1];
+      const uint32_t fa = key.frame & 0x7FFFFFFFu, fb = p.frame & 0x7FFFFFFFu;
+      const bool less = key.hap != p.hap ? key.hap < p.hap : (fa != fb ? fa < fb : (key.frame >> 31) < (p.frame >> 31));
+      if (!less) break;
+      table[b] = table[b - 1];
+      --b;
+    }
+    table[b] = key;
+  }
+  MphWinOut wo;
+  wo.depth = n_obs;
+  wo.c0 = c0;
+  wo.n_extra = n_keys;
+  wo.extra_off = 0;
+  if (n_keys) {
+    const uint32_t off = MPH_RP_ADD(&c.counters[MPH_RP_CTR_HIST], n_keys);
+    if (off + n_keys <= c.hist_cap) {
+      wo.extra_off = off;
+      const uint32_t code = ((c.seg_chunk0[si] + (i >> 5)) << 5) | (i & 31u);
+      for (uint32_t a = 0; a < n_keys; ++a) {
+        c.hist[off + a] = table[a];
+        c.hist_win[off + a] = code;
+      }
+    } else {
+      *err |= MPH_E_HIST_OVERFLOW;
+      wo.n_extra = 0;
+    }
+  }
+  c.win_out[widx] = wo;
+  MPH_RP_ADD64(c.sum_depth, n_obs);
+  // the matrix columns in print_haplotypes order (:372-378): the deque, reversed on the reverse strand
+  const bool rev = (sg.flags & MPH_SF_REVERSE) != 0;
+  uint32_t n_walk = 0;
+  {
+    const uint32_t off = MPH_RP_ADD(&c.counters[MPH_RP_CTR_VLIST], ncols + 1);
+    if (off + ncols + 1 <= c.vlist_cap) {
+      c.vlist[off] = ncols;
+      for (uint32_t j = 0; j < ncols; ++j) c.vlist[off + 1 + j] = rev ? dq[ncols - 1 - j] : dq[j];
+      c.win_voff[widx] = off;
+    } else {
+      *err |= MPH_E_VLIST_OVERFLOW;
+    }
+    // variants the sequence walk visits (:473-476): j only advances while variants[j].pos == i
+    uint32_t j = 0;
+    for (uint32_t p = g.s; p < g.e && j < ncols; ++p)
+      while (j < ncols && c.vars[rev ? dq[ncols - 1 - j] : dq[j]].pos == p) ++j;
+    n_walk = j;
+  }
+  MphHap h0;
+  *err |= mph_plain_hap(sg, g, c.stopmap, c.ref, n_walk, &h0);
+  if (ncols > 32) *err |= MPH_E_VARS_PER_WINDOW;
+  c.hap0[widx] = h0;
+  c.win_flag[widx] = 1;
+  (void)k;
+}
+
+// the window loop of phase_gene (:944-1939) reduced to its matrix operations
+MPH_HD void mph_replay_tx(const MphReplayCtx& c, const MphReplayTx& t) {
+  uint32_t err = 0;
+  uint32_t dq[MPH_RP_MAXCOLS];
+  uint32_t ncols = 0, n_obs = 0;
+  uint64_t last_window_vars = 0;
+  uint32_t* o_read = c.o_read + t.obs_off;
+  uint64_t* o_hap = c.o_hap + t.obs_off;
+  uint32_t* o_frame = c.o_frame + t.obs_off;
+  uint8_t* o_flags = c.o_flags + t.obs_off;
+  uint8_t* in_mat = c.o_inmat + t.obs_off;
+  for (uint32_t x = 0; x < t.obs_cap; ++x) in_mat[x] = 0;
+  auto shrink_left = [&](uint64_t n) -> bool {  // :220-229
+    if (n > ncols) { err |= MPH_E_REPLAY_PANIC; return false; }  // drain(..k) out of range
+    for (uint32_t j = (uint32_t)n; j < ncols; ++j) dq[j - n] = dq[j];
+    ncols -= (uint32_t)n;
+    const uint64_t mask = ncols >= 64 ? ~(uint64_t)0 : (((uint64_t)1 << ncols) - 1);
+    for (uint32_t o = 0; o < n_obs; ++o) o_hap[o] &= mask;
+    return true;
+  };
+  for (uint32_t si = t.seg_lo; si < t.seg_hi && !(err & MPH_E_REPLAY_PANIC); ++si) {
+    const MphSegment& sg = c.segs[si];
+    const bool rev = (sg.flags & MPH_SF_REVERSE) != 0;
+    const bool is_short = (sg.flags & MPH_SF_SHORT) != 0;
+    if (!shrink_left(last_window_vars)) break;  // :1024
+    last_window_vars = 0;
+    uint64_t old_offset = sg.off0, old_end = (uint64_t)sg.off0 + sg.ewl;
+    bool reached_end = false;
+    for (uint32_t k = 0; k < sg.n_iter; ++k) {
+      const uint64_t offset = rev ? (uint64_t)sg.off0 - k : (uint64_t)sg.off0 + k;
+      const MphGeom g = mph_geom(sg, k);
+      const uint64_t rest = rev ? offset - sg.exon_start : sg.exon_end - (offset + sg.ewl);
+      const bool is_last_exon_window = rest < 3, is_first_exon_window = k == 0;
+      auto cnt = [&](uint64_t a, uint64_t b) -> uint64_t {  // variant_tree.range(a..b) (:1119-1170); a > b panics in the reference
+        if (a > b) { err |= MPH_E_REPLAY_PANIC; return 0; }
+        const uint32_t ia = mph_var_lb(c.vars, sg.var_lo, sg.var_hi, (uint32_t)a);
+        return mph_var_lb(c.vars, ia, sg.var_hi, (uint32_t)b) - ia;
+      };
+      const uint32_t va = mph_var_lb(c.vars, sg.var_lo, sg.var_hi, g.s);
+      const uint32_t vb = mph_var_lb(c.vars, va, sg.var_hi, g.e);
+      const uint64_t nvars = vb - va;
+      uint64_t added_vars, deleted_vars;
+      if (is_first_exon_window) added_vars = nvars;
+      else if (is_short || reached_end) added_vars = 0;
+      else if (g.s > old_offset) added_vars = cnt(old_end, g.e);
+      else added_vars = cnt(g.s, old_offset);
+      if (offset == old_offset || is_short) deleted_vars = 0;
+      else if (g.s > old_offset) deleted_vars = cnt(old_offset, g.s);
+      else deleted_vars = cnt(g.e, old_end);
+      if (is_last_exon_window) reached_end = true;
+      // cleanup_reads (:259-278, call sites :1255-1262)
+      {
+        uint32_t w = 0;
+        for (uint32_t o = 0; o < n_obs; ++o) {
+          const uint32_t r = o_read[o];
+          const bool keep = rev ? c.read_start[r] < g.s + 1u : c.read_end[r] >= g.e;
+          if (keep) {
+            if (w != o) { o_read[w] = r; o_hap[w] = o_hap[o]; o_frame[w] = o_frame[o]; o_flags[w] = o_flags[o]; }
+            ++w;
+          } else {
+            in_mat[r - t.read_lo] = 0;
+          }
+        }
+        n_obs = w;
+      }
+      if (!shrink_left(deleted_vars)) break;
+      // candidate reads (:1191-1249) and push_read (:297-343)
+      {
+        const bool wide = rev || offset == (uint64_t)sg.exon_start + sg.ceo;
+        const uint32_t lo = wide ? (g.s > sg.K ? g.s - sg.K : 0u) : g.s;
+        const uint32_t r0 = mph_u32_lb(c.read_start, t.read_lo, t.read_hi, lo);
+        const uint32_t r1 = mph_u32_lb(c.read_start, r0, t.read_hi, g.s + 1u);
+        for (uint32_t r = r0; r < r1; ++r) {
+          if (c.read_end[r] < g.e) continue;
+          if (rev) {
+            // `contains` (:281-294): an observation with the same start and qname is already in the matrix
+            bool dup = in_mat[r - t.read_lo] != 0;
+            if (!dup && (c.read_flags[r] & MPH_RF_PARTNER)) {
+              const uint32_t q = mph_rp_partner(c, r);
+              dup = q != 0xFFFFFFFFu && q >= t.read_lo && q < t.read_hi && in_mat[q - t.read_lo] != 0;
+            }
+            if (dup) continue;
+          }
+          uint64_t hap = 0;
+          uint32_t frame = 0;
+          uint8_t fl = 0;
+          for (uint32_t i = 0; i < ncols; ++i) mph_rp_update(c, t, r, i, dq[ncols - 1 - i], &hap, &frame, &fl, &err);
+          if (fl & 1) continue;  // rejected at push (:338)
+          if (n_obs >= t.obs_cap) { err |= MPH_E_REPLAY_INPUT; continue; }
+          o_read[n_obs] = r; o_hap[n_obs] = hap; o_frame[n_obs] = frame; o_flags[n_obs] = fl;
+          in_mat[r - t.read_lo] = 1;
+          ++n_obs;
+        }
+      }
+      // newly collected variants (:1280-1296): the window's variants in collection order minus the first nvars - added_vars
+      {
+        const uint64_t skip = nvars - added_vars;  // wraps like the release build: nothing is added then
+        const uint32_t n_new = skip <= nvars ? (uint32_t)(nvars - skip) : 0u;
+        if (n_new) {
+          if (ncols + n_new > MPH_RP_MAXCOLS) { err |= MPH_E_VARS_PER_WINDOW; break; }
+          // extend_right (:232-256)
+          for (uint32_t o = 0; o < n_obs; ++o) {
+            uint64_t hap = o_hap[o] << (n_new & 63u);
+            uint32_t frame = o_frame[o];
+            uint8_t fl = o_flags[o];
+            for (uint32_t i = 0; i < n_new; ++i) {
+              const uint32_t x = (uint32_t)skip + (n_new - 1 - i);  // new_variants.rev(): the newest first
+              const uint32_t v = rev ? vb - 1 - x : va + x;
+              mph_rp_update(c, t, o_read[o], i, v, &hap, &frame, &fl, &err);
+            }
+            o_hap[o] = hap; o_frame[o] = frame; o_flags[o] = fl;
+          }
+          for (uint32_t x = (uint32_t)skip; x < (uint32_t)nvars; ++x) dq[ncols++] = rev ? vb - 1 - x : va + x;
+        }
+      }
+      last_window_vars = nvars;
+      if (k >= sg.k_first && (k - sg.k_first) % sg.k_stride == 0) {
+        const uint32_t i = (k - sg.k_first) / sg.k_stride;
+        if (i < sg.n_win) mph_rp_emit(c, t, sg, si, i, k, g, n_obs, dq, ncols, &err);
+      }
+      old_offset = g.s;
+      old_end = g.e;
+      if (is_short) break;
+    }
+  }
+  if (err) MPH_RP_OR(&c.counters[MPH_RP_CTR_ERR], err);
+}

@@ -16,7 +16,7 @@
 #include <vector>
 
 #include "../core/layout.h"
-#include "../core/phase_core.h"
+#include "../core/replay_core.h"
 
 namespace mph {
 
@@ -96,6 +96,10 @@ struct Batch {
   std::vector<uint32_t> stopmap;  // 1 bit per ref byte: a stop codon (for the slice's strand) starts here; 2 words of slack
   uint64_t n_windows = 0;
   uint32_t seq_cap = 64;  // bytes per assembled sequence slot
+  // transcripts that go through the serial replay (core/replay_core.h) and the size of their observation scratch
+  std::vector<MphReplayTx> replay;
+  uint64_t replay_obs = 0;
+  std::vector<uint32_t> seg_chunk0;  // per segment: index of its first chunk
   // host-only
   std::vector<TxMeta> txs;
   std::vector<GeneMeta> genes;
@@ -172,6 +176,7 @@ class Packer {
     gm.read_lo = uint32_t(b_.read_start.size());
     uint32_t vcur = gm.var_lo, max_span = 0;
     std::unordered_map<uint64_t, uint32_t> seen;  // (start, qname) -> first read index
+    const size_t bases_mark = b_.bases.size(), cigars_mark = b_.cigars.size();
     for (auto& r : reads) {
       const uint32_t idx = uint32_t(b_.read_start.size());
       while (vcur < gm.var_hi && b_.vars[vcur].pos < r.start) ++vcur;
@@ -233,6 +238,7 @@ class Packer {
     // somatic: one deletion can pull the walk past the window end (:560-563); normal: every applied
     // deletion moves window_end (normal_microphasing.rs:457), so the overhang adds up
     const uint32_t margin = b_.mode == 1 ? (max_del + 1) * std::min<uint32_t>(n_del, wl) + 2 : max_del + 2;
+    bool gene_replay = false;
     for (auto& t : g.transcripts) {
       if (t.exons.empty()) continue;  // is_coding (:947)
       TxMeta tm;
@@ -242,6 +248,7 @@ class Packer {
       uint64_t exon_rest = 0;
       uint32_t exon_count = 0;
       const size_t exon_number = t.exons.size();
+      bool tx_replay = false;
       for (auto& ex : t.exons) {
         if (ex.start > ex.end) continue;  // :981
         exon_count += 1;
@@ -276,8 +283,7 @@ class Packer {
         if (t.reverse && !is_short && sg.n_iter >= 2) {
           const uint32_t pstar = ex.start + uint32_t(ewl);
           const uint32_t vi = mph_var_lb(b_.vars.data(), gm.var_lo, gm.var_hi, pstar);
-          if (vi < gm.var_hi && b_.vars[vi].pos == pstar)
-            throw Unsupported("transcript " + t.id + ": variant at exon.start + window_len on a reverse-strand exon (stale matrix column)");
+          if (vi < gm.var_hi && b_.vars[vi].pos == pstar) tx_replay = true;
         }
         sg.K = uint32_t(max_read_len - ewl);
         if (!t.reverse && uint64_t(sg.off0 - sg.ceo) < sg.K) throw Fatal("range start is greater than range end in BTreeMap");
@@ -332,8 +338,9 @@ class Packer {
         b_.n_windows += sg.n_win;
         const uint32_t si = uint32_t(b_.segs.size());
         // carry-over of observations from the previous exon needs the serial path
-        if (si > tm.seg_lo) check_carry_over(b_.segs[si - 1], sg, t.id);
+        if (si > tm.seg_lo && carries_over(b_.segs[si - 1], sg)) tx_replay = true;
         b_.segs.push_back(sg);
+        b_.seg_chunk0.push_back(uint32_t(b_.chunks.size()));
         for (uint32_t i = 0; i < sg.n_win; i += chunk_windows_) {
           MphChunk c;
           c.seg = si; c.i_first = i; c.n = std::min(chunk_windows_, sg.n_win - i); c.pad = 0;
@@ -351,7 +358,45 @@ class Packer {
         }
       }
       tm.seg_hi = uint32_t(b_.segs.size());
+      if (tx_replay && tm.seg_hi > tm.seg_lo) {
+        if (b_.mode != 0) throw Unsupported("transcript " + t.id + ": the normal mode has no serial replay (observation carry-over / stale matrix column)");
+        MphReplayTx rt;
+        rt.seg_lo = tm.seg_lo; rt.seg_hi = tm.seg_hi; rt.read_lo = gm.read_lo; rt.read_hi = gm.read_hi;
+        rt.obs_off = uint32_t(b_.replay_obs); rt.obs_cap = gm.read_hi - gm.read_lo;
+        rt.sl_va = b_.segs[tm.seg_lo].sl_va; rt.sl_vb = b_.segs[tm.seg_lo].sl_vb;
+        if (!(b_.segs[tm.seg_lo].flags & MPH_SF_FIRST_EXON)) rt.sl_va = rt.sl_vb = 0;
+        b_.replay_obs += rt.obs_cap;
+        if (b_.replay_obs > 0xFFFFFF00ull) throw Unsupported("batch too large: split it into gene ranges");
+        b_.replay.push_back(rt);
+        for (uint32_t si = tm.seg_lo; si < tm.seg_hi; ++si) b_.segs[si].flags |= MPH_SF_REPLAY;
+        gene_replay = true;
+      }
       b_.txs.push_back(std::move(tm));
+    }
+    if (gene_replay) {
+      // the replay evaluates matrix columns outside a read's own variant range: every read of the gene ships its bases and CIGAR
+      b_.bases.resize(bases_mark);
+      b_.cigars.resize(cigars_mark);
+      uint32_t idx = gm.read_lo;
+      for (auto& r : reads) {
+        const size_t off = (b_.bases.size() + 15u) & ~size_t(15);
+        const size_t nb = (r.l_seq + 1u) / 2, nq = (r.l_seq + 7u) / 8;
+        b_.bases.resize(off + nb + nq, 0);
+        memcpy(&b_.bases[off], r.seq4, nb);
+        for (uint32_t i = 0; i < r.l_seq; ++i)
+          if (r.qual[i] < 10) b_.bases[off + nb + (i >> 3)] |= uint8_t(1u << (i & 7));
+        b_.read_seq_off[idx] = uint32_t(off / 16);
+        const bool single_m = r.n_cigar == 1 && (r.cigar[0] & 15u) == 0 && (r.cigar[0] >> 4) == r.l_seq;
+        if (!single_m) {
+          b_.read_cig_off[idx] = uint32_t(b_.cigars.size());
+          b_.read_ncig[idx] = uint16_t(r.n_cigar);
+          b_.cigars.insert(b_.cigars.end(), r.cigar, r.cigar + r.n_cigar);
+        } else {
+          b_.read_cig_off[idx] = 0;
+          b_.read_ncig[idx] = 0;
+        }
+        ++idx;
+      }
     }
     b_.genes.push_back(std::move(gm));
   }
@@ -362,8 +407,8 @@ class Packer {
   // An observation survives into the next exon when it still passes cleanup_reads there
   // (:259-278); exome introns are longer than a read, so this is rare, and the closed form of
   // phase_core.h does not model it.
-  void check_carry_over(const MphSegment& a, const MphSegment& bseg, const std::string& tx) {
-    if (a.n_iter == 0) return;
+  bool carries_over(const MphSegment& a, const MphSegment& bseg) const {
+    if (a.n_iter == 0) return false;
     const MphGeom ga = mph_geom(a, a.n_iter - 1), gb = mph_geom(bseg, 0);
     const bool rev = (a.flags & MPH_SF_REVERSE) != 0;
     // a carried read encloses the last window of A and still passes B's first cleanup:
@@ -371,11 +416,11 @@ class Packer {
     const uint32_t need_end = rev ? ga.e : gb.e;
     const uint32_t max_start = rev ? std::min(ga.s, gb.s) : ga.s;
     const uint32_t min_start = need_end > a.max_span ? need_end - a.max_span : 0;
-    if (min_start > max_start) return;
+    if (min_start > max_start) return false;
     auto lo = std::lower_bound(b_.read_start.begin() + a.read_lo, b_.read_start.begin() + a.read_hi, min_start) - b_.read_start.begin();
     for (uint32_t r = uint32_t(lo); r < a.read_hi && b_.read_start[r] <= max_start; ++r)
-      if (b_.read_end[r] >= need_end && b_.read_end[r] >= ga.e)
-        throw Unsupported("transcript " + tx + ": a read spans two exons' windows (observation carry-over)");
+      if (b_.read_end[r] >= need_end && b_.read_end[r] >= ga.e) return true;
+    return false;
   }
 
   Batch b_;

@@ -31,6 +31,8 @@ struct PhaseRaw {
   std::vector<MphHist> hist;      // extra histogram keys (whole arena)
   std::vector<MphHap> hapx;       // per extra key
   std::vector<uint8_t> seq;       // sequence arena: slots of 2 * seq_cap bytes (normal mode: seq_cap bytes)
+  std::vector<uint32_t> iw_voff;  // per interesting window (empty without replayed transcripts): offset of its matrix columns in vlist, 0xFFFFFFFF = own variants
+  std::vector<uint32_t> vlist;    // column lists: count, then variant indices in print_haplotypes order
   std::vector<uint32_t> win_depth;  // normal mode only, per enumerated window: depth | (plain window starts / ends with a stop codon) << 31
   uint32_t err = 0;
   uint64_t sum_depth = 0;         // over every enumerated window
@@ -163,6 +165,14 @@ inline InfoRecord add_freq(const InfoRecord& r, double f) {
 
 }  // namespace detail
 
+// the variant columns print_haplotypes sees for one window: the window's own variants [va, va + n), or the
+// explicit list the serial replay recorded (stale columns, core/replay_core.h)
+struct WinVars {
+  const uint32_t* list = nullptr;
+  uint32_t va = 0, n = 0;
+  uint32_t at(uint32_t c) const { return list ? list[c] : va + c; }
+};
+
 class Residue {
  public:
   Residue(const Batch& b, const PhaseRaw& raw) : b_(b), raw_(raw) {
@@ -188,7 +198,8 @@ class Residue {
     bool lazy = false;
     const MphSegment* sg = nullptr;
     const MphHap* h = nullptr;
-    uint32_t k = 0, va = 0, nv = 0;
+    uint32_t k = 0;
+    WinVars wv;
   };
 
   struct Key {
@@ -226,9 +237,15 @@ class Residue {
     const GeneMeta& gm = b_.genes[tm.gene];
     const bool rev = tm.reverse;
     const MphGeom g = mph_geom(sg, k);
-    const uint32_t va = mph_var_lb(b_.vars.data(), sg.var_lo, sg.var_hi, g.s);
-    const uint32_t vb = mph_var_lb(b_.vars.data(), sg.var_lo, sg.var_hi, g.e);
-    const uint32_t nv = vb - va;
+    WinVars wv;
+    wv.va = mph_var_lb(b_.vars.data(), sg.var_lo, sg.var_hi, g.s);
+    wv.n = mph_var_lb(b_.vars.data(), sg.var_lo, sg.var_hi, g.e) - wv.va;
+    if (!raw_.iw_voff.empty() && raw_.iw_voff[iwi] != 0xFFFFFFFFu) {
+      const uint32_t off = raw_.iw_voff[iwi];
+      wv.n = raw_.vlist[off];
+      wv.list = raw_.vlist.data() + off + 1;
+    }
+    const uint32_t nv = wv.n;
     const MphWinOut& wo = raw_.iw_out[iwi];
     const MphHap& h0 = raw_.iw_hap0[iwi];
     const uint64_t window_len = sg.ewl;
@@ -290,7 +307,7 @@ class Residue {
       // replay of the frameshift side effects of the sequence walk (:482-502): the visited
       // variants are variants[0 .. n_prof) in order, profile != 0 <=> the haplotype carries it
       for (uint32_t c = 0; c < uint32_t(h.n_prof) + h.brk && c < 32; ++c) {
-        const MphVar& v = b_.vars[va + c];
+        const MphVar& v = b_.vars[wv.at(c)];
         const uint64_t vfs = (v.flags & MPH_VF_FS_MASK) >> MPH_VF_FS_SHIFT;
         shift_in_window = shift_in_window > 0 ? shift_in_window : vfs;
         if (c == h.n_prof || ((h.profile >> (2 * c)) & 3)) {  // c == n_prof: the variant the walk broke on
@@ -374,7 +391,7 @@ class Residue {
         rec.depth = depth;
       }
       if (need_rec) {
-        fill_meta(rec, va, nv, h);
+        fill_meta(rec, wv, h);
         // the id of a record that is not written is never read (IDRecord::update derives a new one)
         if (emit) rec.id = mphfmt::record_id(reinterpret_cast<const uint8_t*>(seq.data()), seq.size(), tm.id, g.s, rev ? 'R' : 'F');
         rec.normal_sequence = normal_peptide;
@@ -388,7 +405,7 @@ class Residue {
           HapSeq hs;
           hs.rec = std::move(rec_for_merge);
           if (lazy) {
-            hs.lazy = true; hs.sg = &sg; hs.h = &h; hs.k = k; hs.va = va; hs.nv = nv;
+            hs.lazy = true; hs.sg = &sg; hs.h = &h; hs.k = k; hs.wv = wv;
           } else {
             hs.rec.normal_sequence = germline_seq;
             hs.rec.mutant_sequence = seq;
@@ -415,7 +432,8 @@ class Residue {
   }
 
   // variant-site metadata of one haplotype (:720-769)
-  void fill_meta(InfoRecord& rec, uint32_t va, uint32_t nv, const MphHap& h) const {
+  void fill_meta(InfoRecord& rec, const WinVars& wv, const MphHap& h) const {
+    const uint32_t nv = wv.n;
     uint32_t n_variantsites = 0, n_som_variantsites = 0;
     std::string s_pc, g_pc, s_pos, g_pos, sites;
     bool fs = true, fg = true, fsite = true;
@@ -428,22 +446,22 @@ class Residue {
     };
     bool fspc = true, fgpc = true;
     for (uint32_t c = 0; c < nv; ++c) {
-      const MphVar& v = b_.vars[va + c];
+      const MphVar& v = b_.vars[wv.at(c)];
       if (c < h.n_prof && c < 32) {
         const unsigned code = unsigned((h.profile >> (2 * c)) & 3);
         if (code == 2) {
           put(s_pos, fs, uint64_t(v.pos) + 1);
           if (!fspc) s_pc.push_back('|');
           fspc = false;
-          s_pc += b_.var_prot[va + c];
+          s_pc += b_.var_prot[wv.at(c)];
         } else if (code == 1) {
           put(g_pos, fg, uint64_t(v.pos) + 1);
           if (!fgpc) g_pc.push_back('|');
           fgpc = false;
-          g_pc += b_.var_prot[va + c];
+          g_pc += b_.var_prot[wv.at(c)];
         }
       }
-      if (c == 0 || v.pos != b_.vars[va + c - 1].pos) {
+      if (c == 0 || v.pos != b_.vars[wv.at(c - 1)].pos) {
         ++n_variantsites;
         put(sites, fsite, uint64_t(v.pos) + 1);
         if (!(v.flags & MPH_VF_GERMLINE)) ++n_som_variantsites;
@@ -466,7 +484,7 @@ class Residue {
     const MphSegment& sg = *hs.sg;
     const MphGeom g = mph_geom(sg, hs.k);
     if (g.s < sg.ref_pos0 || uint64_t(g.e) - sg.ref_pos0 > sg.ref_len) throw Fatal("slice index out of range: refseq");
-    fill_meta(hs.rec, hs.va, hs.nv, *hs.h);
+    fill_meta(hs.rec, hs.wv, *hs.h);
     hs.rec.mutant_sequence.assign(reinterpret_cast<const char*>(b_.ref.data()) + sg.ref_off + (g.s - sg.ref_pos0), g.e - g.s);
     hs.rec.normal_sequence = hs.rec.mutant_sequence;
     hs.lazy = false;

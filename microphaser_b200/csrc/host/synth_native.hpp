@@ -166,9 +166,8 @@ inline void synth_generate(const SynthParams& sp, uint32_t window_len, bool all_
       const uint32_t ng = rng.poisson(kb * sp.germline_per_kb), ns = rng.poisson(kb * sp.somatic_per_kb);
       for (uint32_t x = 0; x < ng + ns; ++x) {
         const uint32_t vp = rng.range(e.start, e.end - 1);
-        // a variant exactly window_len after the start of a reverse-strand exon triggers the
-        // reference's stale-column quirk, which needs the serial replay path (not built yet)
-        if (reverse && vp == e.start + window_len) continue;
+        // (a variant exactly window_len after the start of a reverse-strand exon triggers the reference's
+        // stale-column quirk: such transcripts go through the serial replay kernel)
         const char r = char(ref[vp - gstart]);
         char a;
         do a = B[rng.below(4)]; while (a == r);

@@ -20,6 +20,7 @@
 #include "phase_kernels.cuh"
 
 #include "../core/phase_core.h"
+#include "../core/replay_core.h"
 
 namespace mphk {
 
@@ -242,6 +243,7 @@ __global__ void __launch_bounds__(K2_WARPS * 32) k_window_hist(const DeviceBatch
   if (lane < 2) s_add[warp][32 + lane] = 0;
   __syncwarp();
   const MphSegment& sg = s_seg[warp];
+  if (sg.flags & MPH_SF_REPLAY) return;  // the whole transcript goes through k_replay
   const bool rev = (sg.flags & MPH_SF_REVERSE) != 0;
   const bool has_fs = (sg.flags & MPH_SF_HAS_FS) != 0;
   const int n = (int)ch.n;
@@ -451,6 +453,25 @@ __global__ void __launch_bounds__(K2_WARPS * 32) k_window_hist(const DeviceBatch
   if (lane == 0 && dsum) atomicAdd(d.sum_depth, dsum);
 }
 
+// ------------------------------------------------------------------ serial replay
+// One warp per irregular transcript; the matrix operations of one transcript are a strict sequence
+// (core/replay_core.h), so lane 0 walks it while the other transcripts run in the other warps.
+__global__ void __launch_bounds__(128) k_replay(const DeviceBatch d) {
+  const uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (t >= d.n_replay || (threadIdx.x & 31)) return;
+  MphReplayCtx c;
+  c.read_start = d.read_start; c.read_end = d.read_end; c.read_vlo = d.read_vlo; c.read_seq_off = d.read_seq_off; c.read_cig_off = d.read_cig_off;
+  c.read_lseq = d.read_lseq; c.read_ncig = d.read_ncig; c.read_nv = d.read_nv; c.read_flags = d.read_flags;
+  c.bases = d.bases; c.cigars = d.cigars; c.call_S = d.call_S; c.call_B = d.call_B;
+  c.pairs = reinterpret_cast<const uint32_t*>(d.pairs); c.n_pairs = d.n_pairs;
+  c.vars = d.vars; c.segs = d.segs; c.seg_chunk0 = d.seg_chunk0; c.stopmap = d.stopmap; c.ref = d.ref;
+  c.o_read = d.o_read; c.o_hap = d.o_hap; c.o_frame = d.o_frame; c.o_flags = d.o_flags; c.o_inmat = d.o_inmat;
+  c.win_out = d.win_out; c.hist = d.hist; c.hist_win = d.hist_win; c.hist_cap = d.hist_cap;
+  c.hap0 = d.hap0; c.win_flag = d.win_flag; c.win_voff = d.win_voff; c.vlist = d.vlist; c.vlist_cap = d.vlist_cap;
+  c.counters = d.counters; c.sum_depth = d.sum_depth;
+  mph_replay_tx(c, d.replay[t]);
+}
+
 // ------------------------------------------------------------------ K3
 // One thread per extra histogram key (haplotype != 0): the sequence walk of print_haplotypes
 // (:458-603) into thread-local buffers, then the stop test; the bytes are kept only for haplotypes
@@ -470,9 +491,20 @@ __global__ void __launch_bounds__(128) k_assemble(const DeviceBatch d) {
     const MphGeom g = mph_geom(sg, k);
     const uint32_t va = mph_var_lb(d.vars, ch.va0, ch.vb1, g.s);
     const uint32_t vb = mph_var_lb(d.vars, va, ch.vb1, g.e);
-    const bool boundary = i == 0 || i + 1 == sg.n_win || (sg.flags & MPH_SF_HAS_FS);
+    const bool replayed = (sg.flags & MPH_SF_REPLAY) != 0;
+    const bool boundary = i == 0 || i + 1 == sg.n_win || (sg.flags & MPH_SF_HAS_FS) || replayed;
     MphHap out;
-    uint32_t err = mph_assemble(sg, g, d.vars, va, vb, d.ref, d.ins_bytes, hap, seq, germ, cap, &out);
+    uint32_t err;
+    if (!replayed) {
+      err = mph_assemble(sg, g, d.vars, va, vb, d.ref, d.ins_bytes, hap, seq, germ, cap, &out);
+    } else {
+      // the walk runs over the matrix columns the replay recorded, gathered into a dense array
+      MphVar cols[MPH_RP_MAXCOLS];
+      const uint32_t off = d.win_voff[sg.win_base + i];
+      const uint32_t ncol = off == NONE ? 0u : min(d.vlist[off], (uint32_t)MPH_RP_MAXCOLS);
+      for (uint32_t j = 0; j < ncol; ++j) cols[j] = d.vars[d.vlist[off + 1 + j]];
+      err = mph_assemble(sg, g, cols, 0, ncol, d.ref, d.ins_bytes, hap, seq, germ, cap, &out);
+    }
     if (boundary || out.n_som > 0) {
       const uint32_t off = atomicAdd(&d.counters[CTR_SEQ], 2 * cap);
       if (off + 2 * cap <= d.seq_cap_bytes) {
@@ -939,6 +971,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scatter(const DeviceBatch d) {
     d.iw[pos] = w;
     d.iw_out[pos] = d.win_out[w];
     d.iw_hap0[pos] = d.hap0[w];
+    if (d.win_voff) d.iw_voff[pos] = d.win_voff[w];
   }
 }
 
@@ -973,6 +1006,9 @@ void launch_window_hist(const DeviceBatch& d, cudaStream_t st) {
   k_window_hist<<<(d.n_chunks + K2_WARPS - 1) / K2_WARPS, K2_WARPS * 32, 0, st>>>(d);
   // windows with more distinct haplotypes than a lane table holds (rare): one warp per window
   k_window_hist_wide<<<148, K2_WARPS * 32, 0, st>>>(d);
+}
+void launch_replay(const DeviceBatch& d, cudaStream_t st) {
+  if (d.n_replay) k_replay<<<(d.n_replay * 32 + 127) / 128, 128, 0, st>>>(d);
 }
 void launch_assemble(const DeviceBatch& d, cudaStream_t st) {
   if (d.n_chunks && d.mode == 1) k_assemble_normal<<<148 * 8, 128, 0, st>>>(d);

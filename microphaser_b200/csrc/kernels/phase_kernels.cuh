@@ -5,6 +5,7 @@
 #include <stdint.h>
 
 #include "../core/layout.h"
+#include "../core/replay_core.h"
 
 namespace mphk {
 
@@ -58,13 +59,23 @@ struct DeviceBatch {
   unsigned long long* sum_depth = nullptr;
   unsigned long long* live_depth = nullptr;
   const uint32_t* seg_live = nullptr;  // per segment: number of windows the reference reaches
+  // serial replay of irregular transcripts (core/replay_core.h)
+  const MphReplayTx* replay = nullptr;
+  uint32_t n_replay = 0;
+  const uint32_t* seg_chunk0 = nullptr;
+  uint32_t* o_read = nullptr; uint64_t* o_hap = nullptr; uint32_t* o_frame = nullptr; uint8_t* o_flags = nullptr; uint8_t* o_inmat = nullptr;
+  uint32_t* win_voff = nullptr;  // per window: offset of the matrix column list in vlist, 0xFFFFFFFF = the window's own variants
+  uint32_t* vlist = nullptr;
+  uint32_t vlist_cap = 0;
+  uint32_t* iw_voff = nullptr;   // K4: win_voff of the interesting windows
   uint32_t* win_depth = nullptr;       // normal mode, per window: depth | (plain window begins / ends with a stop codon) << 31
 };
 
-enum { CTR_HIST = 0, CTR_SEQ = 1, CTR_NIW = 2, CTR_ERR = 3, CTR_OVF = 4 };
+enum { CTR_HIST = 0, CTR_SEQ = 1, CTR_NIW = 2, CTR_ERR = 3, CTR_OVF = 4, CTR_VLIST = 5 };
 
 void launch_allele_call(const DeviceBatch& d, cudaStream_t st);
 void launch_window_hist(const DeviceBatch& d, cudaStream_t st);
+void launch_replay(const DeviceBatch& d, cudaStream_t st);
 void launch_assemble(const DeviceBatch& d, cudaStream_t st);
 void launch_compact(const DeviceBatch& d, cudaStream_t st);
 void launch_live_depth(const DeviceBatch& d, cudaStream_t st);

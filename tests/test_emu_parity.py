@@ -39,6 +39,7 @@ PROFILES = {
     "dense": dict(germline_per_kb=15.0, somatic_per_kb=15.0, indel_frac=0.2, multiallelic_frac=0.1, lowq_frac=0.08),
     "fs": dict(indel_frac=0.3, frameshift_ok=True, somatic_per_kb=4.0),
     "multi": dict(transcripts_per_gene=3, indel_frac=0.1),
+    "carry": dict(intron_len=(15, 80), indel_frac=0.1, multiallelic_frac=0.05),  # introns shorter than a read: observations survive into the next exon
 }
 
 
