@@ -82,11 +82,13 @@ struct mph_result {
 struct mph_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;  // the serial replay of irregular transcripts runs beside the closed-form window kernel
+  cudaEvent_t ev_rp = nullptr;
   cudaEvent_t ev[8] = {};
   std::string last_error;
   const mph_batch* cur = nullptr;
   mphk::DeviceBatch d;
-  DevBuf<uint32_t> read_start, read_end, read_vlo, read_seq_off, read_cig_off, cigars, block_counts, iw, counters, seg_live, ovf_list, stopmap, hist_win, win_depth, seg_chunk0, o_read, o_frame, win_voff, vlist, iw_voff;
+  DevBuf<uint32_t> read_start, read_end, read_vlo, read_seq_off, read_cig_off, cigars, block_counts, iw, counters, seg_live, ovf_list, stopmap, hist_win, win_depth, seg_chunk0, dq_init, seg_err, o_read, o_key, o_frame, win_voff, vlist, iw_voff;
   DevBuf<uint16_t> read_lseq, read_ncig;
   DevBuf<uint8_t> read_nv, read_flags, bases, ins_bytes, ref, call_flags, seq, win_flag, o_flags, o_inmat;
   DevBuf<MphReplayTx> replay;
@@ -149,7 +151,7 @@ void finish_batch(mph_batch* mb, bool pin) {
   mb->h2d_bytes = bytes(b.read_start) + bytes(b.read_end) + bytes(b.read_vlo) + bytes(b.read_seq_off) + bytes(b.read_cig_off) +
                   bytes(b.read_lseq) + bytes(b.read_ncig) + bytes(b.read_nv) + bytes(b.read_flags) + bytes(b.bases) + bytes(b.cigars) +
                   bytes(b.vars) + bytes(b.ins_bytes) + bytes(b.segs) + bytes(b.chunks) + bytes(b.ref) + bytes(b.stopmap) + bytes(mb->pairs) +
-                  bytes(b.replay) + (b.replay.empty() ? 0 : bytes(b.seg_chunk0));
+                  bytes(b.replay) + bytes(b.replay_dq) + (b.replay.empty() ? 0 : bytes(b.seg_chunk0));
   if (pin) {
     auto reg = [&](auto& v) {
       if (v.empty()) return;
@@ -181,7 +183,7 @@ void upload(mph_ctx* c, const mph_batch* mb) {
   h2d(c, c->read_ncig, b.read_ncig); h2d(c, c->read_nv, b.read_nv); h2d(c, c->read_flags, b.read_flags); h2d(c, c->bases, b.bases);
   h2d(c, c->cigars, b.cigars); h2d(c, c->vars, b.vars); h2d(c, c->ins_bytes, b.ins_bytes); h2d(c, c->segs, b.segs);
   h2d(c, c->chunks, b.chunks); h2d(c, c->ref, b.ref); h2d(c, c->stopmap, b.stopmap); h2d(c, c->pairs, mb->pairs);
-  if (!b.replay.empty()) { h2d(c, c->replay, b.replay); h2d(c, c->seg_chunk0, b.seg_chunk0); }
+  if (!b.replay.empty()) { h2d(c, c->replay, b.replay); h2d(c, c->seg_chunk0, b.seg_chunk0); h2d(c, c->dq_init, b.replay_dq); }
   CU(cudaEventRecord(c->ev[1], c->stream));
   const size_t nr = b.n_reads(), nw = size_t(b.n_windows);
   c->call_S.ensure(nr + 1); c->call_B.ensure(nr + 1); c->call_flags.ensure(nr + 1);
@@ -211,12 +213,12 @@ void upload(mph_ctx* c, const mph_batch* mb) {
   d.win_voff = nullptr; d.iw_voff = nullptr;
   if (d.n_replay) {
     const size_t no = size_t(b.replay_obs) + 1;
-    c->o_read.ensure(no); c->o_hap.ensure(no); c->o_frame.ensure(no); c->o_flags.ensure(no); c->o_inmat.ensure(no);
-    c->win_voff.ensure(nw + 1); c->iw_voff.ensure(nw + 1);
+    c->o_read.ensure(no); c->o_key.ensure(no); c->o_hap.ensure(no); c->o_frame.ensure(no); c->o_flags.ensure(no); c->o_inmat.ensure(no);
+    c->win_voff.ensure(nw + 1); c->iw_voff.ensure(nw + 1); c->seg_err.ensure(b.segs.size() + 1);
     if (c->vlist.cap == 0) c->vlist.ensure(1 << 16);
-    d.replay = c->replay.p; d.seg_chunk0 = c->seg_chunk0.p;
-    d.o_read = c->o_read.p; d.o_hap = reinterpret_cast<uint64_t*>(c->o_hap.p); d.o_frame = c->o_frame.p; d.o_flags = c->o_flags.p; d.o_inmat = c->o_inmat.p;
-    d.win_voff = c->win_voff.p; d.iw_voff = c->iw_voff.p;
+    d.replay = c->replay.p; d.seg_chunk0 = c->seg_chunk0.p; d.dq_init = c->dq_init.p;
+    d.o_read = c->o_read.p; d.o_key = c->o_key.p; d.o_hap = reinterpret_cast<uint64_t*>(c->o_hap.p); d.o_frame = c->o_frame.p; d.o_flags = c->o_flags.p; d.o_inmat = c->o_inmat.p;
+    d.win_voff = c->win_voff.p; d.iw_voff = c->iw_voff.p; d.seg_err = c->seg_err.p;
   }
   d.mode = uint32_t(b.mode);
   if (b.mode == 1) { c->win_depth.ensure(nw + 1); d.win_depth = c->win_depth.p; }
@@ -237,12 +239,18 @@ void run_kernels(mph_ctx* c) {
   if (d.n_replay) {
     d.vlist = c->vlist.p; d.vlist_cap = uint32_t(std::min<size_t>(c->vlist.cap, 0xFFFFFF00u));
     CU(cudaMemsetAsync(c->win_voff.p, 0xFF, (size_t(d.n_windows) + 1) * sizeof(uint32_t), c->stream));
+    CU(cudaMemsetAsync(c->seg_err.p, 0, (size_t(d.n_segs) + 1) * sizeof(uint32_t), c->stream));
   }
   CU(cudaEventRecord(c->ev[2], c->stream));
   mphk::launch_allele_call(d, c->stream);
   CU(cudaEventRecord(c->ev[3], c->stream));
+  if (d.n_replay) {
+    CU(cudaStreamWaitEvent(c->stream2, c->ev[3], 0));
+    mphk::launch_replay(d, c->stream2);
+    CU(cudaEventRecord(c->ev_rp, c->stream2));
+  }
   mphk::launch_window_hist(d, c->stream);
-  mphk::launch_replay(d, c->stream);
+  if (d.n_replay) CU(cudaStreamWaitEvent(c->stream, c->ev_rp, 0));
   CU(cudaEventRecord(c->ev[4], c->stream));
   mphk::launch_assemble(d, c->stream);
   CU(cudaEventRecord(c->ev[5], c->stream));
@@ -278,7 +286,7 @@ void collect(mph_ctx* c, mph_result** out) {
   if (raw.err & MPH_E_REF_RANGE) throw Fatal("slice index out of range: refseq");
   if (raw.err & MPH_E_VARS_PER_WINDOW) throw Unsupported("more than 32 variants in one window / 64 inside one read");
   if (raw.err & MPH_E_KEYS_PER_WINDOW) throw Unsupported("more than 32 distinct haplotypes in one window");
-  if (raw.err & MPH_E_REPLAY_PANIC) throw Fatal("matrix replay: drain range out of bounds / read starts right of variant");
+  if (raw.err & MPH_E_REPLAY_PANIC) throw Fatal("bug: read starts right of variant");
   if (raw.err) throw std::logic_error("device error bits " + std::to_string(raw.err));
   const uint32_t n_iw = ctr[mphk::CTR_NIW], n_hist = ctr[mphk::CTR_HIST], n_seq = ctr[mphk::CTR_SEQ];
   raw.iw.resize(n_iw); raw.iw_out.resize(n_iw); raw.iw_hap0.resize(n_iw); raw.hist.resize(n_hist); raw.hapx.resize(n_hist); raw.seq.resize(n_seq);
@@ -298,6 +306,8 @@ void collect(mph_ctx* c, mph_result** out) {
   raw.vlist.resize(n_vl);
   if (c->d.n_replay && n_iw) CU(cudaMemcpyAsync(raw.iw_voff.data(), c->iw_voff.p, n_iw * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
   if (n_vl) CU(cudaMemcpyAsync(raw.vlist.data(), c->vlist.p, size_t(n_vl) * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  raw.seg_err.resize(c->d.n_replay ? b.segs.size() : 0);
+  if (!raw.seg_err.empty()) CU(cudaMemcpyAsync(raw.seg_err.data(), c->seg_err.p, raw.seg_err.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
   const bool normal_mode = b.mode == 1;
   raw.win_depth.resize(normal_mode ? size_t(b.n_windows) : 0);
   if (normal_mode && b.n_windows) CU(cudaMemcpyAsync(raw.win_depth.data(), c->win_depth.p, size_t(b.n_windows) * 4, cudaMemcpyDeviceToHost, c->stream));
@@ -307,7 +317,7 @@ void collect(mph_ctx* c, mph_result** out) {
   CU(cudaStreamSynchronize(c->stream));
   CU(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
   c->timing.d2h_ms = ms;
-  c->timing.d2h_bytes = sizeof ctr + sizeof sums + size_t(n_iw) * (4 + sizeof(MphWinOut) + sizeof(MphHap)) + size_t(n_hist) * (sizeof(MphHist) + sizeof(MphHap)) + n_seq + raw.win_depth.size() * 4 + (raw.iw_voff.size() + raw.vlist.size()) * 4;
+  c->timing.d2h_bytes = sizeof ctr + sizeof sums + size_t(n_iw) * (4 + sizeof(MphWinOut) + sizeof(MphHap)) + size_t(n_hist) * (sizeof(MphHist) + sizeof(MphHap)) + n_seq + raw.win_depth.size() * 4 + (raw.iw_voff.size() + raw.vlist.size() + raw.seg_err.size()) * 4;
   raw.sum_depth = sums[0];
 
   // host residue: the serial part of the window loop, transcripts are independent
@@ -544,6 +554,15 @@ int mph_ctx_create(int device, mph_ctx** out) {
     c->device = device;
     CU(cudaSetDevice(device));
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    {
+      // highest priority: the few long-running replay warps must get their SM slots while the closed-form kernel's
+      // many short CTAs are still being dispatched, otherwise the two kernels run back to back
+      int prio_lo = 0, prio_hi = 0;
+      CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+      const char* pe = getenv("MPH_REPLAY_PRIORITY");  // measurement hook: 0 = default priority
+      CU(cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, (pe && *pe == '0') ? prio_lo : prio_hi));
+    }
+    CU(cudaEventCreateWithFlags(&c->ev_rp, cudaEventDisableTiming));
     for (auto& e2 : c->ev) CU(cudaEventCreate(&e2));
   });
   if (rc != MPH_OK) return rc;
@@ -563,6 +582,8 @@ void mph_ctx_destroy(mph_ctx* c) {
   c->hap0.release(); c->hapx.release(); c->iw_hap0.release(); c->sums.release();
   for (auto& e : c->ev)
     if (e) cudaEventDestroy(e);
+  if (c->ev_rp) cudaEventDestroy(c->ev_rp);
+  if (c->stream2) cudaStreamDestroy(c->stream2);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }

@@ -44,6 +44,7 @@ enum {
   MPH_SF_FIRST_EXON = 4,  // exon_count == 1
   MPH_SF_LAST_EXON = 8,
   MPH_SF_HAS_FS = 16,     // the gene carries frameshifting variants: every iteration is a window
+  MPH_SF_KEEP_PENULT = 64,  // the next exon's only window is first and last: its junction merge reads this exon's last-but-one window (:1401-1405)
   MPH_SF_REPLAY = 32,     // the transcript goes through the serial replay (core/replay_core.h), not the closed form
 };
 

@@ -157,6 +157,15 @@ MPH_HD MphCall mph_call_read(const MphRead& r, const uint8_t* bases, const uint3
   return c;
 }
 
+// windows whose haplotype list a splice-junction merge can read (:1401-1405,1497-1510): the first and the last window
+// of an exon, every window when frameshifts keep several reading frames alive, and the last-but-one window when the
+// next exon stores its only window on the "previous exon" side
+MPH_HD bool mph_is_boundary(const MphSegment& g, uint32_t i) {
+  if (g.flags & MPH_SF_HAS_FS) return true;
+  if (i == 0 || i + 1 == g.n_win) return true;
+  return (g.flags & MPH_SF_KEEP_PENULT) && i + 2 == g.n_win;
+}
+
 // Reads that can be observations of window gk: start <= s, and start not further left than the
 // candidate range of the reference (:1191-1249) nor than the longest alignment allows.
 MPH_HD void mph_candidate_range(const MphSegment& g, const uint32_t* read_start, const MphGeom& gk, uint32_t* rlo, uint32_t* rhi) {

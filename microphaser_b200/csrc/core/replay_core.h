@@ -20,12 +20,17 @@
 #define MPH_RP_MAXCOLS 64
 #define MPH_RP_KEYS 32
 
-// one replayed transcript, 32 B
+// One replay unit, 48 B: a run of consecutive exons of one transcript that no observation crosses the
+// ends of. The matrix columns at its start do not depend on reads, so the packer computes them with a
+// read-free pass over the transcript and the units of one transcript replay in parallel.
 typedef struct {
   uint32_t seg_lo, seg_hi;    // its segments
   uint32_t read_lo, read_hi;  // the gene's reads
   uint32_t obs_off, obs_cap;  // slice of the observation scratch arrays
   uint32_t sl_va, sl_vb;      // start-loss variant range of the first exon (:1305-1316)
+  uint32_t dq_off, dq_n;      // matrix columns when the unit starts (variant indices, oldest first) in the dq arena
+  uint32_t last_vars;         // last_window_vars when the unit starts (:1024)
+  uint32_t pad;
 } MphReplayTx;
 
 typedef struct {
@@ -37,6 +42,7 @@ typedef struct {
   const uint32_t* pairs; uint32_t n_pairs;  // (read, partner) interleaved, sorted by read
   const MphVar* vars; const MphSegment* segs; const uint32_t* seg_chunk0;
   const uint32_t* stopmap; const uint8_t* ref;
+  const uint32_t* dq_init;  // arena of initial column lists
   // scratch: observation list
   uint32_t* o_read; uint64_t* o_hap; uint32_t* o_frame; uint8_t* o_flags;
   uint8_t* o_inmat;  // per gene read (obs_off + read - read_lo): the read is an observation right now
@@ -45,6 +51,7 @@ typedef struct {
   MphHap* hap0; uint8_t* win_flag;
   uint32_t* win_voff;  // per window: offset of its column list in vlist (entry 0 = count), 0xFFFFFFFF = the window's own variants
   uint32_t* vlist; uint32_t vlist_cap;
+  uint32_t* seg_err;   // per segment: 1 + iteration at which the reference panics (drain out of range, inverted range), 0 = none
   uint32_t* counters;  // CTR_* of phase_kernels.cuh
   unsigned long long* sum_depth;
 } MphReplayCtx;
@@ -211,16 +218,19 @@ MPH_HD void mph_rp_emit(const MphReplayCtx& c, const MphReplayTx& t, const MphSe
 MPH_HD void mph_replay_tx(const MphReplayCtx& c, const MphReplayTx& t) {
   uint32_t err = 0;
   uint32_t dq[MPH_RP_MAXCOLS];
-  uint32_t ncols = 0, n_obs = 0;
-  uint64_t last_window_vars = 0;
+  uint32_t ncols = t.dq_n <= MPH_RP_MAXCOLS ? t.dq_n : 0, n_obs = 0;
+  if (t.dq_n > MPH_RP_MAXCOLS) err |= MPH_E_VARS_PER_WINDOW;
+  for (uint32_t j = 0; j < ncols; ++j) dq[j] = c.dq_init[t.dq_off + j];
+  uint64_t last_window_vars = t.last_vars;
   uint32_t* o_read = c.o_read + t.obs_off;
   uint64_t* o_hap = c.o_hap + t.obs_off;
   uint32_t* o_frame = c.o_frame + t.obs_off;
   uint8_t* o_flags = c.o_flags + t.obs_off;
   uint8_t* in_mat = c.o_inmat + t.obs_off;
   for (uint32_t x = 0; x < t.obs_cap; ++x) in_mat[x] = 0;
+  bool panicked = false;
   auto shrink_left = [&](uint64_t n) -> bool {  // :220-229
-    if (n > ncols) { err |= MPH_E_REPLAY_PANIC; return false; }  // drain(..k) out of range
+    if (n > ncols) { panicked = true; return false; }  // drain(..k) out of range
     for (uint32_t j = (uint32_t)n; j < ncols; ++j) dq[j - n] = dq[j];
     ncols -= (uint32_t)n;
     const uint64_t mask = ncols >= 64 ? ~(uint64_t)0 : (((uint64_t)1 << ncols) - 1);
@@ -231,7 +241,7 @@ MPH_HD void mph_replay_tx(const MphReplayCtx& c, const MphReplayTx& t) {
     const MphSegment& sg = c.segs[si];
     const bool rev = (sg.flags & MPH_SF_REVERSE) != 0;
     const bool is_short = (sg.flags & MPH_SF_SHORT) != 0;
-    if (!shrink_left(last_window_vars)) break;  // :1024
+    if (!shrink_left(last_window_vars)) { c.seg_err[si] = 1; break; }  // :1024
     last_window_vars = 0;
     uint64_t old_offset = sg.off0, old_end = (uint64_t)sg.off0 + sg.ewl;
     bool reached_end = false;
@@ -241,7 +251,7 @@ MPH_HD void mph_replay_tx(const MphReplayCtx& c, const MphReplayTx& t) {
       const uint64_t rest = rev ? offset - sg.exon_start : sg.exon_end - (offset + sg.ewl);
       const bool is_last_exon_window = rest < 3, is_first_exon_window = k == 0;
       auto cnt = [&](uint64_t a, uint64_t b) -> uint64_t {  // variant_tree.range(a..b) (:1119-1170); a > b panics in the reference
-        if (a > b) { err |= MPH_E_REPLAY_PANIC; return 0; }
+        if (a > b) { panicked = true; return 0; }
         const uint32_t ia = mph_var_lb(c.vars, sg.var_lo, sg.var_hi, (uint32_t)a);
         return mph_var_lb(c.vars, ia, sg.var_hi, (uint32_t)b) - ia;
       };
@@ -257,6 +267,7 @@ MPH_HD void mph_replay_tx(const MphReplayCtx& c, const MphReplayTx& t) {
       else if (g.s > old_offset) deleted_vars = cnt(old_offset, g.s);
       else deleted_vars = cnt(g.e, old_end);
       if (is_last_exon_window) reached_end = true;
+      if (panicked) { c.seg_err[si] = k + 1; break; }
       // cleanup_reads (:259-278, call sites :1255-1262)
       {
         uint32_t w = 0;
@@ -272,7 +283,7 @@ MPH_HD void mph_replay_tx(const MphReplayCtx& c, const MphReplayTx& t) {
         }
         n_obs = w;
       }
-      if (!shrink_left(deleted_vars)) break;
+      if (!shrink_left(deleted_vars)) { c.seg_err[si] = k + 1; break; }
       // candidate reads (:1191-1249) and push_read (:297-343)
       {
         const bool wide = rev || offset == (uint64_t)sg.exon_start + sg.ceo;
@@ -331,6 +342,7 @@ MPH_HD void mph_replay_tx(const MphReplayCtx& c, const MphReplayTx& t) {
       old_end = g.e;
       if (is_short) break;
     }
+    if (panicked) break;
   }
   if (err) MPH_RP_OR(&c.counters[MPH_RP_CTR_ERR], err);
 }

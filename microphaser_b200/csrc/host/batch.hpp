@@ -98,6 +98,7 @@ struct Batch {
   uint32_t seq_cap = 64;  // bytes per assembled sequence slot
   // transcripts that go through the serial replay (core/replay_core.h) and the size of their observation scratch
   std::vector<MphReplayTx> replay;
+  std::vector<uint32_t> replay_dq;  // initial matrix columns of the replay units
   uint64_t replay_obs = 0;
   std::vector<uint32_t> seg_chunk0;  // per segment: index of its first chunk
   // host-only
@@ -284,6 +285,13 @@ class Packer {
           const uint32_t pstar = ex.start + uint32_t(ewl);
           const uint32_t vi = mph_var_lb(b_.vars.data(), gm.var_lo, gm.var_hi, pstar);
           if (vi < gm.var_hi && b_.vars[vi].pos == pstar) tx_replay = true;
+          // second quirk: when the first window is already a last window (rest < 3) the later iterations move the
+          // window start down to exon.start, but `reached_end` (:1136-1139) keeps the variants entering there out of
+          // the matrix while last_window_vars still counts them
+          if (sg.off0 - ex.start < 3) {
+            const uint32_t v0 = mph_var_lb(b_.vars.data(), gm.var_lo, gm.var_hi, ex.start);
+            if (v0 < gm.var_hi && b_.vars[v0].pos < sg.off0) tx_replay = true;
+          }
         }
         sg.K = uint32_t(max_read_len - ewl);
         if (!t.reverse && uint64_t(sg.off0 - sg.ceo) < sg.K) throw Fatal("range start is greater than range end in BTreeMap");
@@ -339,6 +347,7 @@ class Packer {
         const uint32_t si = uint32_t(b_.segs.size());
         // carry-over of observations from the previous exon needs the serial path
         if (si > tm.seg_lo && carries_over(b_.segs[si - 1], sg)) tx_replay = true;
+        if (si > tm.seg_lo && sg.n_win == 1 && !is_short) b_.segs[si - 1].flags |= MPH_SF_KEEP_PENULT;
         b_.segs.push_back(sg);
         b_.seg_chunk0.push_back(uint32_t(b_.chunks.size()));
         for (uint32_t i = 0; i < sg.n_win; i += chunk_windows_) {
@@ -360,14 +369,77 @@ class Packer {
       tm.seg_hi = uint32_t(b_.segs.size());
       if (tx_replay && tm.seg_hi > tm.seg_lo) {
         if (b_.mode != 0) throw Unsupported("transcript " + t.id + ": the normal mode has no serial replay (observation carry-over / stale matrix column)");
+        // split the transcript into units at the exon boundaries no observation crosses; the matrix columns at a
+        // unit start come from a read-free pass over the window loop's column bookkeeping (:1119-1178,1280-1296)
+        std::vector<uint32_t> dq;
+        uint64_t last_vars = 0;
+        bool broken = false;  // the reference panics in this transcript (drain out of range): keep the rest in one unit
         MphReplayTx rt;
-        rt.seg_lo = tm.seg_lo; rt.seg_hi = tm.seg_hi; rt.read_lo = gm.read_lo; rt.read_hi = gm.read_hi;
-        rt.obs_off = uint32_t(b_.replay_obs); rt.obs_cap = gm.read_hi - gm.read_lo;
-        rt.sl_va = b_.segs[tm.seg_lo].sl_va; rt.sl_vb = b_.segs[tm.seg_lo].sl_vb;
-        if (!(b_.segs[tm.seg_lo].flags & MPH_SF_FIRST_EXON)) rt.sl_va = rt.sl_vb = 0;
-        b_.replay_obs += rt.obs_cap;
-        if (b_.replay_obs > 0xFFFFFF00ull) throw Unsupported("batch too large: split it into gene ranges");
-        b_.replay.push_back(rt);
+        memset(&rt, 0, sizeof rt);
+        auto open_unit = [&](uint32_t si) {
+          rt.seg_lo = si; rt.read_lo = gm.read_lo; rt.read_hi = gm.read_hi;
+          rt.obs_off = uint32_t(b_.replay_obs); rt.obs_cap = gm.read_hi - gm.read_lo;
+          rt.sl_va = b_.segs[tm.seg_lo].sl_va; rt.sl_vb = b_.segs[tm.seg_lo].sl_vb;
+          if (!(b_.segs[tm.seg_lo].flags & MPH_SF_FIRST_EXON)) rt.sl_va = rt.sl_vb = 0;
+          rt.dq_off = uint32_t(b_.replay_dq.size()); rt.dq_n = uint32_t(dq.size()); rt.last_vars = uint32_t(last_vars);
+          b_.replay_dq.insert(b_.replay_dq.end(), dq.begin(), dq.end());
+          b_.replay_obs += rt.obs_cap;
+          if (b_.replay_obs > 0xFFFFFF00ull) throw Unsupported("batch too large: split it into gene ranges");
+        };
+        auto close_unit = [&](uint32_t si_end) {
+          rt.seg_hi = si_end;
+          b_.replay.push_back(rt);
+        };
+        open_unit(tm.seg_lo);
+        for (uint32_t si = tm.seg_lo; si < tm.seg_hi; ++si) {
+          const MphSegment& sg = b_.segs[si];
+          if (si > tm.seg_lo && !broken && !carries_over(b_.segs[si - 1], sg)) {
+            close_unit(si);
+            open_unit(si);
+          }
+          if (broken) continue;
+          const bool rev = (sg.flags & MPH_SF_REVERSE) != 0, is_short = (sg.flags & MPH_SF_SHORT) != 0;
+          auto shrink = [&](uint64_t n) {
+            if (n > dq.size()) { broken = true; return; }
+            dq.erase(dq.begin(), dq.begin() + long(n));
+          };
+          shrink(last_vars);
+          last_vars = 0;
+          uint64_t old_offset = sg.off0, old_end = uint64_t(sg.off0) + sg.ewl;
+          bool reached_end = false;
+          for (uint32_t k = 0; k < sg.n_iter && !broken; ++k) {
+            const uint64_t offset = rev ? uint64_t(sg.off0) - k : uint64_t(sg.off0) + k;
+            const MphGeom g = mph_geom(sg, k);
+            const uint64_t rest = rev ? offset - sg.exon_start : sg.exon_end - (offset + sg.ewl);
+            auto cnt = [&](uint64_t a, uint64_t c2) -> uint64_t {
+              if (a > c2) { broken = true; return 0; }
+              const uint32_t ia = mph_var_lb(b_.vars.data(), sg.var_lo, sg.var_hi, uint32_t(a));
+              return mph_var_lb(b_.vars.data(), ia, sg.var_hi, uint32_t(c2)) - ia;
+            };
+            const uint32_t va = mph_var_lb(b_.vars.data(), sg.var_lo, sg.var_hi, g.s);
+            const uint32_t vb = mph_var_lb(b_.vars.data(), va, sg.var_hi, g.e);
+            const uint64_t nvars = vb - va;
+            uint64_t added, deleted;
+            if (k == 0) added = nvars;
+            else if (is_short || reached_end) added = 0;
+            else if (g.s > old_offset) added = cnt(old_end, g.e);
+            else added = cnt(g.s, old_offset);
+            if (offset == old_offset || is_short) deleted = 0;
+            else if (g.s > old_offset) deleted = cnt(old_offset, g.s);
+            else deleted = cnt(g.e, old_end);
+            if (rest < 3) reached_end = true;
+            if (broken) break;
+            shrink(deleted);
+            const uint64_t skip = nvars - added;
+            if (skip <= nvars)
+              for (uint64_t x = skip; x < nvars; ++x) dq.push_back(rev ? vb - 1 - uint32_t(x) : va + uint32_t(x));
+            last_vars = nvars;
+            old_offset = g.s;
+            old_end = g.e;
+            if (is_short) break;
+          }
+        }
+        close_unit(tm.seg_hi);
         for (uint32_t si = tm.seg_lo; si < tm.seg_hi; ++si) b_.segs[si].flags |= MPH_SF_REPLAY;
         gene_replay = true;
       }

@@ -32,6 +32,7 @@ struct PhaseRaw {
   std::vector<MphHap> hapx;       // per extra key
   std::vector<uint8_t> seq;       // sequence arena: slots of 2 * seq_cap bytes (normal mode: seq_cap bytes)
   std::vector<uint32_t> iw_voff;  // per interesting window (empty without replayed transcripts): offset of its matrix columns in vlist, 0xFFFFFFFF = own variants
+  std::vector<uint32_t> seg_err;  // per segment (empty without replayed transcripts): 1 + iteration at which the reference panics
   std::vector<uint32_t> vlist;    // column lists: count, then variant indices in print_haplotypes order
   std::vector<uint32_t> win_depth;  // normal mode only, per enumerated window: depth | (plain window starts / ends with a stop codon) << 31
   uint32_t err = 0;
@@ -492,9 +493,9 @@ class Residue {
 
   static bool is_boundary(const MphSegment& sg, uint32_t k) {
     if (sg.n_win == 0) return false;
-    if (k == sg.k_first) return true;
     if (sg.flags & MPH_SF_HAS_FS) return true;
-    return k == sg.k_first + (sg.n_win - 1) * sg.k_stride;
+    if (k < sg.k_first || (k - sg.k_first) % sg.k_stride) return false;
+    return mph_is_boundary(sg, (k - sg.k_first) / sg.k_stride);
   }
 
   void run_transcript(uint32_t t, std::vector<OutRecord>& out, ResidueStats& stats) {
@@ -535,8 +536,12 @@ class Residue {
       bool fs_init = false;
       uint64_t live_windows_end = sg.n_win;  // windows of this segment the reference reaches
       bool stopped = false;
+      // the replay found an iteration at which the reference panics (shrink_left past the matrix columns :220-222,
+      // inverted BTreeMap range): the loop gets there unless the ORF has ended before
+      const uint32_t panic_k = raw_.seg_err.empty() ? 0xFFFFFFFFu : raw_.seg_err[si] - 1u;
       for (uint32_t k : ks) {
         if (frameshifts.empty()) { stopped = true; break; }
+        if (k >= panic_k) throw Fatal("drain: range end out of bounds");
         const MphGeom g = mph_geom(sg, k);
         const uint64_t offset = fwd ? uint64_t(sg.off0) + k : uint64_t(sg.off0) - k;
         const bool is_first_exon_window = k == 0;
@@ -624,6 +629,7 @@ class Residue {
           splice_merge(t, sg, offset, is_short_exon, is_last_exon, is_last_exon_window, exon_rest, frameshifts, ff, hap_vec, prev_hap_vec, out);
         (void)window_len;
       }
+      if (!stopped && !frameshifts.empty() && panic_k != 0xFFFFFFFFu) throw Fatal("drain: range end out of bounds");
       // statistics: main-ORF windows the reference evaluates in this segment (depth is summed on the
       // device over exactly these windows)
       if (!has_fs) {

@@ -63,11 +63,13 @@ struct DeviceBatch {
   const MphReplayTx* replay = nullptr;
   uint32_t n_replay = 0;
   const uint32_t* seg_chunk0 = nullptr;
-  uint32_t* o_read = nullptr; uint64_t* o_hap = nullptr; uint32_t* o_frame = nullptr; uint8_t* o_flags = nullptr; uint8_t* o_inmat = nullptr;
+  const uint32_t* dq_init = nullptr;  // initial matrix columns of the replay units
+  uint32_t* o_read = nullptr; uint32_t* o_key = nullptr; uint64_t* o_hap = nullptr; uint32_t* o_frame = nullptr; uint8_t* o_flags = nullptr; uint8_t* o_inmat = nullptr;
   uint32_t* win_voff = nullptr;  // per window: offset of the matrix column list in vlist, 0xFFFFFFFF = the window's own variants
   uint32_t* vlist = nullptr;
   uint32_t vlist_cap = 0;
   uint32_t* iw_voff = nullptr;   // K4: win_voff of the interesting windows
+  uint32_t* seg_err = nullptr;   // per segment: 1 + iteration at which the reference panics, 0 = none
   uint32_t* win_depth = nullptr;       // normal mode, per window: depth | (plain window begins / ends with a stop codon) << 31
 };
 

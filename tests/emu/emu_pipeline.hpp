@@ -129,12 +129,14 @@ inline PhaseRaw phase_somatic(const Batch& b) {
     rp_vlist.resize(size_t(b.n_windows) * 66 + 1024);
     uint32_t counters[8] = {0};
     unsigned long long sum_depth = 0;
+    raw.seg_err.assign(b.segs.size(), 0);
     MphReplayCtx c;
+    c.seg_err = raw.seg_err.data();
     c.read_start = b.read_start.data(); c.read_end = b.read_end.data(); c.read_vlo = b.read_vlo.data(); c.read_seq_off = b.read_seq_off.data();
     c.read_cig_off = b.read_cig_off.data(); c.read_lseq = b.read_lseq.data(); c.read_ncig = b.read_ncig.data(); c.read_nv = b.read_nv.data();
     c.read_flags = b.read_flags.data(); c.bases = b.bases.data(); c.cigars = b.cigars.data(); c.call_S = S.data(); c.call_B = B.data();
     c.pairs = pairs.data(); c.n_pairs = uint32_t(pairs.size() / 2); c.vars = b.vars.data(); c.segs = b.segs.data(); c.seg_chunk0 = b.seg_chunk0.data();
-    c.stopmap = b.stopmap.data(); c.ref = b.ref.data();
+    c.stopmap = b.stopmap.data(); c.ref = b.ref.data(); c.dq_init = b.replay_dq.data();
     c.o_read = o_read.data(); c.o_hap = o_hap.data(); c.o_frame = o_frame.data(); c.o_flags = o_flags.data(); c.o_inmat = o_inmat.data();
     c.win_out = rp_out.data(); c.hist = rp_hist.data(); c.hist_win = rp_histwin.data(); c.hist_cap = uint32_t(rp_hist.size());
     c.hap0 = rp_hap0.data(); c.win_flag = rp_flag.data(); c.win_voff = rp_voff.data(); c.vlist = rp_vlist.data(); c.vlist_cap = uint32_t(rp_vlist.size());
@@ -231,7 +233,7 @@ inline PhaseRaw phase_somatic(const Batch& b) {
       }
       wo.n_extra = uint32_t(extras.size());
       // K3
-      const bool boundary = i == 0 || i + 1 == sg.n_win || (sg.flags & MPH_SF_HAS_FS);
+      const bool boundary = mph_is_boundary(sg, i);
       auto assemble = [&](uint64_t hap, MphHap* out) {
         if (hap == 0) {
           raw.err |= mph_plain_hap(sg, g, b.stopmap.data(), b.ref.data(), vb - va, out);
