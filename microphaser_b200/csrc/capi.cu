@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <unistd.h>
 
+#include <atomic>
 #include <chrono>
 #include <cstdarg>
 #include <fstream>
@@ -74,7 +75,14 @@ struct mph_packer {
 
 struct mph_result {
   int mode = 0;
-  std::vector<OutRecord> recs;
+  // records in the reference's order: the transcript ranges of the residue threads, kept as they were produced
+  std::vector<std::vector<OutRecord>> parts;
+  std::vector<uint64_t> part_base;  // prefix counts, parts.size() + 1 entries
+  uint64_t size() const { return part_base.empty() ? 0 : part_base.back(); }
+  const OutRecord& at(uint64_t i) const {
+    size_t p = size_t(std::upper_bound(part_base.begin(), part_base.end(), i) - part_base.begin()) - 1;
+    return parts[p][size_t(i - part_base[p])];
+  }
   std::vector<std::string> tx_id, gene_id, gene_name, chrom;
   std::vector<uint8_t> tx_reverse;
 };
@@ -82,14 +90,13 @@ struct mph_result {
 struct mph_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
-  cudaStream_t stream2 = nullptr;  // the serial replay of irregular transcripts runs beside the closed-form window kernel
-  cudaEvent_t ev_rp = nullptr;
   cudaEvent_t ev[8] = {};
   std::string last_error;
   const mph_batch* cur = nullptr;
   mphk::DeviceBatch d;
-  DevBuf<uint32_t> read_start, read_end, read_vlo, read_seq_off, read_cig_off, cigars, block_counts, iw, counters, seg_live, ovf_list, stopmap, hist_win, win_depth, seg_chunk0, dq_init, seg_err, o_read, o_key, o_frame, win_voff, vlist, iw_voff;
+  DevBuf<uint32_t> read_start, read_end, read_vlo, read_seq_off, read_cig_off, cigars, block_counts, iw, counters, seg_live, ovf_list, stopmap, hist_win, win_depth, seg_chunk0, dq_init, seg_err, tx_id_off, o_read, o_key, o_frame, win_voff, vlist, iw_voff;
   DevBuf<uint16_t> read_lseq, read_ncig;
+  DevBuf<uint8_t> tx_id_bytes;
   DevBuf<uint8_t> read_nv, read_flags, bases, ins_bytes, ref, call_flags, seq, win_flag, o_flags, o_inmat;
   DevBuf<MphReplayTx> replay;
   DevBuf<uint64_t> o_hap;
@@ -101,7 +108,7 @@ struct mph_ctx {
   DevBuf<MphWinOut> win_out, iw_out;
   DevBuf<MphHist> hist;
   DevBuf<MphHap> hap0, hapx, iw_hap0;
-  DevBuf<unsigned long long> sums;
+  DevBuf<unsigned long long> sums, win_id;
   mph_timing timing = {};
   bool have_h2d_time = false;
   PhaseRaw raw;  // download buffers, reused across calls (no page faults after the first)
@@ -151,7 +158,7 @@ void finish_batch(mph_batch* mb, bool pin) {
   mb->h2d_bytes = bytes(b.read_start) + bytes(b.read_end) + bytes(b.read_vlo) + bytes(b.read_seq_off) + bytes(b.read_cig_off) +
                   bytes(b.read_lseq) + bytes(b.read_ncig) + bytes(b.read_nv) + bytes(b.read_flags) + bytes(b.bases) + bytes(b.cigars) +
                   bytes(b.vars) + bytes(b.ins_bytes) + bytes(b.segs) + bytes(b.chunks) + bytes(b.ref) + bytes(b.stopmap) + bytes(mb->pairs) +
-                  bytes(b.replay) + bytes(b.replay_dq) + (b.replay.empty() ? 0 : bytes(b.seg_chunk0));
+                  bytes(b.tx_id_bytes) + bytes(b.tx_id_off) + bytes(b.replay) + bytes(b.replay_dq) + (b.replay.empty() ? 0 : bytes(b.seg_chunk0));
   if (pin) {
     auto reg = [&](auto& v) {
       if (v.empty()) return;
@@ -183,6 +190,7 @@ void upload(mph_ctx* c, const mph_batch* mb) {
   h2d(c, c->read_ncig, b.read_ncig); h2d(c, c->read_nv, b.read_nv); h2d(c, c->read_flags, b.read_flags); h2d(c, c->bases, b.bases);
   h2d(c, c->cigars, b.cigars); h2d(c, c->vars, b.vars); h2d(c, c->ins_bytes, b.ins_bytes); h2d(c, c->segs, b.segs);
   h2d(c, c->chunks, b.chunks); h2d(c, c->ref, b.ref); h2d(c, c->stopmap, b.stopmap); h2d(c, c->pairs, mb->pairs);
+  h2d(c, c->tx_id_bytes, b.tx_id_bytes); h2d(c, c->tx_id_off, b.tx_id_off);
   if (!b.replay.empty()) { h2d(c, c->replay, b.replay); h2d(c, c->seg_chunk0, b.seg_chunk0); h2d(c, c->dq_init, b.replay_dq); }
   CU(cudaEventRecord(c->ev[1], c->stream));
   const size_t nr = b.n_reads(), nw = size_t(b.n_windows);
@@ -209,6 +217,7 @@ void upload(mph_ctx* c, const mph_batch* mb) {
   d.ovf_list = c->ovf_list.p;
   d.iw = c->iw.p; d.iw_out = c->iw_out.p; d.iw_hap0 = c->iw_hap0.p; d.counters = c->counters.p;
   d.sum_depth = c->sums.p; d.live_depth = c->sums.p + 1; d.seg_live = c->seg_live.p;
+  d.tx_id_bytes = c->tx_id_bytes.p; d.tx_id_off = c->tx_id_off.p;
   d.n_replay = uint32_t(b.replay.size());
   d.win_voff = nullptr; d.iw_voff = nullptr;
   if (d.n_replay) {
@@ -221,7 +230,7 @@ void upload(mph_ctx* c, const mph_batch* mb) {
     d.win_voff = c->win_voff.p; d.iw_voff = c->iw_voff.p; d.seg_err = c->seg_err.p;
   }
   d.mode = uint32_t(b.mode);
-  if (b.mode == 1) { c->win_depth.ensure(nw + 1); d.win_depth = c->win_depth.p; }
+  if (b.mode == 1) { c->win_depth.ensure(nw + 1); d.win_depth = c->win_depth.p; c->win_id.ensure(nw + 1); d.win_id = c->win_id.p; }
   c->cur = mb;
   c->timing.h2d_bytes = mb->h2d_bytes;
   c->have_h2d_time = true;
@@ -244,13 +253,10 @@ void run_kernels(mph_ctx* c) {
   CU(cudaEventRecord(c->ev[2], c->stream));
   mphk::launch_allele_call(d, c->stream);
   CU(cudaEventRecord(c->ev[3], c->stream));
-  if (d.n_replay) {
-    CU(cudaStreamWaitEvent(c->stream2, c->ev[3], 0));
-    mphk::launch_replay(d, c->stream2);
-    CU(cudaEventRecord(c->ev_rp, c->stream2));
-  }
+  // measured on B200: the replay warps are latency-bound; sharing the SMs with the closed-form kernel (second stream,
+  // either priority) slows both by more than the overlap gains, so the two kernels run back to back
+  mphk::launch_replay(d, c->stream);
   mphk::launch_window_hist(d, c->stream);
-  if (d.n_replay) CU(cudaStreamWaitEvent(c->stream, c->ev_rp, 0));
   CU(cudaEventRecord(c->ev[4], c->stream));
   mphk::launch_assemble(d, c->stream);
   CU(cudaEventRecord(c->ev[5], c->stream));
@@ -310,14 +316,18 @@ void collect(mph_ctx* c, mph_result** out) {
   if (!raw.seg_err.empty()) CU(cudaMemcpyAsync(raw.seg_err.data(), c->seg_err.p, raw.seg_err.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
   const bool normal_mode = b.mode == 1;
   raw.win_depth.resize(normal_mode ? size_t(b.n_windows) : 0);
-  if (normal_mode && b.n_windows) CU(cudaMemcpyAsync(raw.win_depth.data(), c->win_depth.p, size_t(b.n_windows) * 4, cudaMemcpyDeviceToHost, c->stream));
+  raw.win_id.resize(normal_mode ? size_t(b.n_windows) : 0);
+  if (normal_mode && b.n_windows) {
+    CU(cudaMemcpyAsync(raw.win_depth.data(), c->win_depth.p, size_t(b.n_windows) * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(raw.win_id.data(), c->win_id.p, size_t(b.n_windows) * 8, cudaMemcpyDeviceToHost, c->stream));
+  }
   unsigned long long sums[2];
   CU(cudaMemcpyAsync(sums, c->sums.p, sizeof sums, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaEventRecord(c->ev[1], c->stream));
   CU(cudaStreamSynchronize(c->stream));
   CU(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
   c->timing.d2h_ms = ms;
-  c->timing.d2h_bytes = sizeof ctr + sizeof sums + size_t(n_iw) * (4 + sizeof(MphWinOut) + sizeof(MphHap)) + size_t(n_hist) * (sizeof(MphHist) + sizeof(MphHap)) + n_seq + raw.win_depth.size() * 4 + (raw.iw_voff.size() + raw.vlist.size() + raw.seg_err.size()) * 4;
+  c->timing.d2h_bytes = sizeof ctr + sizeof sums + size_t(n_iw) * (4 + sizeof(MphWinOut) + sizeof(MphHap)) + size_t(n_hist) * (sizeof(MphHist) + sizeof(MphHap)) + n_seq + raw.win_depth.size() * 12 + (raw.iw_voff.size() + raw.vlist.size() + raw.seg_err.size()) * 4;
   raw.sum_depth = sums[0];
 
   // host residue: the serial part of the window loop, transcripts are independent
@@ -330,21 +340,27 @@ void collect(mph_ctx* c, mph_result** out) {
   unsigned n_thr = std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 32u);
   if (const char* ht = getenv("MPH_HOST_THREADS")) n_thr = std::max(1, atoi(ht));
   if (n_tx < 256) n_thr = 1;
-  std::vector<std::vector<OutRecord>> parts(n_thr);
+  // transcripts are handed out in blocks of 128 (dynamic: blocks differ a lot in the number of interesting windows);
+  // every block keeps its own record vector so that the reference's order needs no copy afterwards
+  const uint32_t blk = 128;
+  const uint32_t n_blk = (n_tx + blk - 1) / blk;
+  std::vector<std::vector<OutRecord>> parts(n_blk);
   std::vector<ResidueStats> pstats(n_thr);
   std::vector<std::vector<std::pair<uint32_t, uint32_t>>> plive(n_thr);
   std::vector<std::exception_ptr> perr(n_thr);
+  std::atomic<uint32_t> next_blk{0};
   auto work = [&](unsigned ti) {
     try {
-      const uint32_t lo = uint32_t(uint64_t(n_tx) * ti / n_thr), hi = uint32_t(uint64_t(n_tx) * (ti + 1) / n_thr);
-      if (normal_mode) {
-        ResidueNormal r(b, raw);
-        r.run(lo, hi, parts[ti], pstats[ti]);
-        return;
+      Residue rs(b, raw);
+      ResidueNormal rn(b, raw);
+      for (;;) {
+        const uint32_t bi = next_blk.fetch_add(1);
+        if (bi >= n_blk) break;
+        const uint32_t lo = bi * blk, hi = std::min(n_tx, lo + blk);
+        if (normal_mode) rn.run(lo, hi, parts[bi], pstats[ti]);
+        else rs.run(lo, hi, parts[bi], pstats[ti]);
       }
-      Residue r(b, raw);
-      r.run(lo, hi, parts[ti], pstats[ti]);
-      plive[ti] = std::move(r.seg_live_);
+      plive[ti] = std::move(rs.seg_live_);
     } catch (...) {
       perr[ti] = std::current_exception();
     }
@@ -358,11 +374,9 @@ void collect(mph_ctx* c, mph_result** out) {
   }
   for (auto& e : perr)
     if (e) std::rethrow_exception(e);
-  size_t total = 0;
-  for (auto& p : parts) total += p.size();
-  res->recs.reserve(total);
+  res->part_base.assign(1, 0);
+  for (auto& p : parts) res->part_base.push_back(res->part_base.back() + p.size());
   for (unsigned ti = 0; ti < n_thr; ++ti) {
-    for (auto& r : parts[ti]) res->recs.push_back(std::move(r));
     st.windows += pstats[ti].windows;
     st.read_windows += pstats[ti].read_windows;
   }
@@ -383,7 +397,8 @@ void collect(mph_ctx* c, mph_result** out) {
   c->timing.read_windows = st.read_windows + sums[1];
   c->timing.windows_enumerated = b.n_windows;
   c->timing.n_interesting = n_iw;
-  c->timing.n_records = res->recs.size();
+  res->parts = std::move(parts);
+  c->timing.n_records = res->size();
   c->timing.kernel_launches = uint32_t(mphk::kernel_launch_count());
   c->timing.total_ms = c->timing.h2d_ms + c->timing.k1_ms + c->timing.k2_ms + c->timing.k3_ms + c->timing.k4_ms + c->timing.d2h_ms + c->timing.residue_ms;
   for (auto& t : b.txs) {
@@ -554,15 +569,6 @@ int mph_ctx_create(int device, mph_ctx** out) {
     c->device = device;
     CU(cudaSetDevice(device));
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    {
-      // highest priority: the few long-running replay warps must get their SM slots while the closed-form kernel's
-      // many short CTAs are still being dispatched, otherwise the two kernels run back to back
-      int prio_lo = 0, prio_hi = 0;
-      CU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-      const char* pe = getenv("MPH_REPLAY_PRIORITY");  // measurement hook: 0 = default priority
-      CU(cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, (pe && *pe == '0') ? prio_lo : prio_hi));
-    }
-    CU(cudaEventCreateWithFlags(&c->ev_rp, cudaEventDisableTiming));
     for (auto& e2 : c->ev) CU(cudaEventCreate(&e2));
   });
   if (rc != MPH_OK) return rc;
@@ -582,8 +588,6 @@ void mph_ctx_destroy(mph_ctx* c) {
   c->hap0.release(); c->hapx.release(); c->iw_hap0.release(); c->sums.release();
   for (auto& e : c->ev)
     if (e) cudaEventDestroy(e);
-  if (c->ev_rp) cudaEventDestroy(c->ev_rp);
-  if (c->stream2) cudaStreamDestroy(c->stream2);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -729,11 +733,11 @@ int mph_ctx_timing(const mph_ctx* ctx, mph_timing* out) {
 }
 
 void mph_result_destroy(mph_result* r) { delete r; }
-uint64_t mph_result_count(const mph_result* r) { return r ? r->recs.size() : 0; }
+uint64_t mph_result_count(const mph_result* r) { return r ? r->size() : 0; }
 
 int mph_result_get(const mph_result* r, uint64_t i, mph_record* o) {
-  if (!r || !o || i >= r->recs.size()) return fail(nullptr, MPH_ERR_INPUT, "record index out of range");
-  const OutRecord& rec = r->recs[i];
+  if (!r || !o || i >= r->size()) return fail(nullptr, MPH_ERR_INPUT, "record index out of range");
+  const OutRecord& rec = r->at(i);
   const uint32_t t = rec.info.tx;
   o->id = rec.info.id.c_str();
   o->transcript = r->tx_id[t].c_str(); o->gene_id = r->gene_id[t].c_str(); o->gene_name = r->gene_name[t].c_str(); o->chrom = r->chrom[t].c_str();
@@ -763,7 +767,8 @@ int mph_result_write(const mph_result* r, int fd_fasta, int fd_tsv, int fd_norma
     std::string fa, tsv, nrm;
     int hw = header_written ? *header_written : 0;
     const bool normal_mode = r->mode == 1;  // 20 columns, the last one is peptide_sequence (src/normal_microphasing.rs:80-102)
-    for (const OutRecord& rec : r->recs) {
+    for (const auto& part : r->parts)
+    for (const OutRecord& rec : part) {
       const uint32_t t = rec.info.tx;
       if (rec.has_mt) { fa += '>'; fa += rec.info.id; fa += '\n'; fa += rec.mt; fa += '\n'; }
       if (rec.has_wt) { nrm += '>'; nrm += rec.info.id; nrm += '\n'; nrm += rec.wt; nrm += '\n'; }

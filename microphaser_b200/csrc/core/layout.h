@@ -131,6 +131,7 @@ enum {
   MPH_HF_SEQ = 8,        // seq/germline_seq bytes were written to the sequence arena
   MPH_HF_GERM_EQ = 16,   // germline_seq == seq before any clearing (:624-631)
   MPH_HF_OVERFLOW = 32,  // assembled sequence longer than the per-haplotype arena slot
+  MPH_HF_ID = 128,       // id64 holds the leading 64 bits of the record id's SHA-1 (:667-675)
   MPH_HF_REFRANGE = 64,  // the walk left the shipped reference slice: the reference panics if (and only if) it reaches this haplotype
 };
 typedef struct {
@@ -144,7 +145,7 @@ typedef struct {
                        //    (its frameshift side effects :482-502 happened, its profile entry did not)
   uint32_t seq_off;    // byte offset into the sequence arena: seq then germline_seq
   uint64_t profile;    // 2 bits per visited variant: 0 absent, 1 germline, 2 somatic (:583-590)
-  uint64_t pad2;
+  uint64_t id64;       // MPH_HF_ID: sha1(format!("{:?}{}{}", seq, transcript.id, offset)) bits 159..96; the id is its first 15 hex digits + strand initial
 } MphHap;
 
 // device error bits (sticky, OR-ed into one word)

@@ -299,6 +299,96 @@ MPH_HD MphPair mph_rev_state(const MphSegment& g, const MphVar* vars, uint32_t k
   return o;
 }
 
+// ------------------------------------------------------------------ record ids (SHA-1, FIPS 180-1)
+// The reference names a record by the first 15 hex digits of sha1(format!("{:?}{}{}", seq, transcript.id, offset))
+// (:667-675; `{:?}` of a byte vector prints "[65, 84, 71]"). The message is generated and hashed on the fly,
+// 64 bytes at a time, so that no per-thread message buffer is needed.
+typedef struct {
+  uint32_t h[5];
+  uint32_t w[16];
+  uint32_t fill;
+  uint32_t len;
+} MphSha1;
+
+MPH_HD uint32_t mph_rol(uint32_t v, int s) { return (v << s) | (v >> (32 - s)); }
+
+MPH_HD void mph_sha1_init(MphSha1* s) {
+  s->h[0] = 0x67452301u; s->h[1] = 0xEFCDAB89u; s->h[2] = 0x98BADCFEu; s->h[3] = 0x10325476u; s->h[4] = 0xC3D2E1F0u;
+  for (int i = 0; i < 16; ++i) s->w[i] = 0;
+  s->fill = 0;
+  s->len = 0;
+}
+
+MPH_HD void mph_sha1_block(MphSha1* s) {
+  uint32_t w[16];
+  for (int i = 0; i < 16; ++i) w[i] = s->w[i];
+  uint32_t a = s->h[0], b = s->h[1], c = s->h[2], d = s->h[3], e = s->h[4];
+#define MPH_SHA1_ROUND(i_, f_, k_)                                                                      \
+  do {                                                                                                  \
+    uint32_t wi_;                                                                                       \
+    if ((i_) < 16) wi_ = w[(i_)];                                                                       \
+    else {                                                                                              \
+      wi_ = mph_rol(w[((i_) + 13) & 15] ^ w[((i_) + 8) & 15] ^ w[((i_) + 2) & 15] ^ w[(i_) & 15], 1);   \
+      w[(i_) & 15] = wi_;                                                                               \
+    }                                                                                                   \
+    const uint32_t t_ = mph_rol(a, 5) + (f_) + e + (k_) + wi_;                                          \
+    e = d; d = c; c = mph_rol(b, 30); b = a; a = t_;                                                    \
+  } while (0)
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+  for (int i = 0; i < 20; ++i) MPH_SHA1_ROUND(i, (b & c) | (~b & d), 0x5A827999u);
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+  for (int i = 20; i < 40; ++i) MPH_SHA1_ROUND(i, b ^ c ^ d, 0x6ED9EBA1u);
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+  for (int i = 40; i < 60; ++i) MPH_SHA1_ROUND(i, (b & c) | (b & d) | (c & d), 0x8F1BBCDCu);
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+  for (int i = 60; i < 80; ++i) MPH_SHA1_ROUND(i, b ^ c ^ d, 0xCA62C1D6u);
+#undef MPH_SHA1_ROUND
+  s->h[0] += a; s->h[1] += b; s->h[2] += c; s->h[3] += d; s->h[4] += e;
+  for (int i = 0; i < 16; ++i) s->w[i] = 0;
+  s->fill = 0;
+}
+
+MPH_HD void mph_sha1_byte(MphSha1* s, uint8_t v) {
+  s->w[s->fill >> 2] |= (uint32_t)v << (24 - 8 * (s->fill & 3u));
+  s->len += 1;
+  if (++s->fill == 64) mph_sha1_block(s);
+}
+
+MPH_HD void mph_sha1_decimal(MphSha1* s, uint32_t v) {
+  uint8_t dig[10];
+  int n = 0;
+  do { dig[n++] = (uint8_t)('0' + v % 10u); v /= 10u; } while (v);
+  while (n) mph_sha1_byte(s, dig[--n]);
+}
+
+// leading 64 bits of sha1(format!("{:?}{}{}", seq, transcript_id, offset))
+MPH_HD uint64_t mph_record_id64(const uint8_t* seq, uint32_t n, const uint8_t* tx_id, uint32_t tx_len, uint32_t offset) {
+  MphSha1 s;
+  mph_sha1_init(&s);
+  mph_sha1_byte(&s, '[');
+  for (uint32_t i = 0; i < n; ++i) {
+    if (i) { mph_sha1_byte(&s, ','); mph_sha1_byte(&s, ' '); }
+    mph_sha1_decimal(&s, seq[i]);
+  }
+  mph_sha1_byte(&s, ']');
+  for (uint32_t i = 0; i < tx_len; ++i) mph_sha1_byte(&s, tx_id[i]);
+  mph_sha1_decimal(&s, offset);
+  const uint32_t bits = s.len * 8u;
+  mph_sha1_byte(&s, 0x80);
+  while (s.fill != 56) mph_sha1_byte(&s, 0);
+  s.w[15] = bits;  // 64-bit big-endian length; messages are far below 2^29 bytes
+  mph_sha1_block(&s);
+  return ((uint64_t)s.h[0] << 32) | s.h[1];
+}
+
 // ------------------------------------------------------------------ K3: haplotype assembly
 MPH_HD bool mph_is_upper(uint8_t c) { return c >= 'A' && c <= 'Z'; }
 MPH_HD uint8_t mph_lower(uint8_t c) { return (c >= 'A' && c <= 'Z') ? (uint8_t)(c + 32) : c; }
@@ -430,7 +520,7 @@ MPH_HD uint32_t mph_assemble(const MphSegment& g, const MphGeom& gk, const MphVa
   out->brk = (uint8_t)brk;
   out->seq_off = 0xFFFFFFFFu;
   out->profile = profile;
-  out->pad2 = 0;
+  out->id64 = 0;
   return err;
 }
 
@@ -474,7 +564,7 @@ MPH_HD uint32_t mph_plain_hap(const MphSegment& g, const MphGeom& gk, const uint
   out->n_var = 0; out->n_som = 0; out->n_prof = (uint8_t)(nvar < 255 ? nvar : 255); out->brk = 0;
   out->seq_off = 0xFFFFFFFFu;
   out->profile = 0;
-  out->pad2 = 0;
+  out->id64 = 0;
   if (nvar > 32) err |= MPH_E_VARS_PER_WINDOW;
   return err;
 }
@@ -498,7 +588,7 @@ MPH_HD uint32_t mph_plain_window(const MphSegment& g, const MphGeom& gk, const u
   out->n_var = 0; out->n_som = 0; out->n_prof = 0; out->brk = 0;
   out->seq_off = 0xFFFFFFFFu;
   out->profile = 0;
-  out->pad2 = 0;
+  out->id64 = 0;
   return err;
 }
 
@@ -571,7 +661,7 @@ MPH_HD uint64_t mph_nrm_hap(const MphSegment& g, const MphVar* vars, uint32_t kp
   return hap;
 }
 
-enum { MPH_NF_STOP = 1, MPH_NF_INSERTION = 4, MPH_NF_SEQ = 8, MPH_NF_OVERFLOW = 32, MPH_NF_REFRANGE = 64 };
+enum { MPH_NF_STOP = 1, MPH_NF_INSERTION = 4, MPH_NF_SEQ = 8, MPH_NF_OVERFLOW = 32, MPH_NF_REFRANGE = 64, MPH_NF_ID = 128 };
 
 // Sequence walk of the normal-mode print_haplotypes (:403-507) for one haplotype; `all_reads` = the
 // haplotype is carried by every observation (freq == 1, :422). Fills seq (cap bytes) and out.
@@ -667,7 +757,7 @@ MPH_HD uint32_t mph_nrm_assemble(const MphSegment& g, const MphGeom& gk, const M
   out->brk = 0;
   out->seq_off = 0xFFFFFFFFu;
   out->profile = profile;
-  out->pad2 = 0;
+  out->id64 = 0;
   return err;
 }
 
@@ -699,7 +789,7 @@ MPH_HD uint32_t mph_nrm_plain(const MphSegment& g, const MphGeom& gk, const uint
   out->n_prof = (uint8_t)(nv < 255 ? nv : 255);  // every window variant is visited and left unset
   out->seq_off = 0xFFFFFFFFu;
   out->profile = 0;
-  out->pad2 = 0;
+  out->id64 = 0;
   return err;
 }
 

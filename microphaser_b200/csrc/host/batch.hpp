@@ -101,6 +101,9 @@ struct Batch {
   std::vector<uint32_t> replay_dq;  // initial matrix columns of the replay units
   uint64_t replay_obs = 0;
   std::vector<uint32_t> seg_chunk0;  // per segment: index of its first chunk
+  // transcript ids for the record ids hashed on the device (:667-675): byte arena + n_tx + 1 offsets
+  std::vector<uint8_t> tx_id_bytes;
+  std::vector<uint32_t> tx_id_off{0};
   // host-only
   std::vector<TxMeta> txs;
   std::vector<GeneMeta> genes;
@@ -443,6 +446,8 @@ class Packer {
         for (uint32_t si = tm.seg_lo; si < tm.seg_hi; ++si) b_.segs[si].flags |= MPH_SF_REPLAY;
         gene_replay = true;
       }
+      b_.tx_id_bytes.insert(b_.tx_id_bytes.end(), tm.id.begin(), tm.id.end());
+      b_.tx_id_off.push_back(uint32_t(b_.tx_id_bytes.size()));
       b_.txs.push_back(std::move(tm));
     }
     if (gene_replay) {

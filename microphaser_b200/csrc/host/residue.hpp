@@ -34,6 +34,7 @@ struct PhaseRaw {
   std::vector<uint32_t> iw_voff;  // per interesting window (empty without replayed transcripts): offset of its matrix columns in vlist, 0xFFFFFFFF = own variants
   std::vector<uint32_t> seg_err;  // per segment (empty without replayed transcripts): 1 + iteration at which the reference panics
   std::vector<uint32_t> vlist;    // column lists: count, then variant indices in print_haplotypes order
+  std::vector<uint64_t> win_id;   // normal mode only, per enumerated window: leading 64 bits of the record id of the reference window (0 = not hashed)
   std::vector<uint32_t> win_depth;  // normal mode only, per enumerated window: depth | (plain window starts / ends with a stop codon) << 31
   uint32_t err = 0;
   uint64_t sum_depth = 0;         // over every enumerated window
@@ -394,7 +395,16 @@ class Residue {
       if (need_rec) {
         fill_meta(rec, wv, h);
         // the id of a record that is not written is never read (IDRecord::update derives a new one)
-        if (emit) rec.id = mphfmt::record_id(reinterpret_cast<const uint8_t*>(seq.data()), seq.size(), tm.id, g.s, rev ? 'R' : 'F');
+        if (emit) {
+          if ((h.flags & MPH_HF_ID) && key.hap != 0) {  // hashed on the device next to the sequence walk
+            static const char* hx = "0123456789abcdef";
+            rec.id.resize(16);
+            for (int q = 0; q < 15; ++q) rec.id[q] = hx[(h.id64 >> (60 - 4 * q)) & 15];
+            rec.id[15] = rev ? 'R' : 'F';
+          } else {
+            rec.id = mphfmt::record_id(reinterpret_cast<const uint8_t*>(seq.data()), seq.size(), tm.id, g.s, rev ? 'R' : 'F');
+          }
+        }
         rec.normal_sequence = normal_peptide;
         rec.mutant_sequence = neopeptide;
       }
@@ -524,7 +534,8 @@ class Residue {
       // Iterations the serial loop has to visit: every iteration when frameshifting variants can
       // open further reading frames, otherwise only the interesting main-ORF windows (all other
       // iterations leave the state untouched).
-      std::vector<uint32_t> ks;
+      std::vector<uint32_t>& ks = ks_scratch_;
+      ks.clear();
       if (has_fs) {
         for (uint32_t k = 0; k < sg.n_iter; ++k) ks.push_back(k);
       } else {
@@ -570,7 +581,8 @@ class Residue {
           else for (uint32_t j = nb; j > na; --j) handle(b_.vars[j - 1]);
         }
         uint64_t stopped_frameshift = 3;
-        std::vector<std::pair<uint64_t, uint64_t>> active;
+        std::vector<std::pair<uint64_t, uint64_t>>& active = active_scratch_;  // snapshot: the map is not mutated while iterating (:1347-1350)
+        active.clear();
         if (fwd) { for (auto it = frameshifts.begin(); it != frameshifts.end() && it->first < offset; ++it) active.push_back(*it); }
         else { for (auto it = frameshifts.lower_bound(offset + exon_window_len); it != frameshifts.end(); ++it) active.push_back(*it); }
         uint64_t frameshift_count = 0;
@@ -795,6 +807,8 @@ class Residue {
   const Batch& b_;
   const PhaseRaw& raw_;
   FILE* trace_ = nullptr;
+  std::vector<std::pair<uint64_t, uint64_t>> active_scratch_;
+  std::vector<uint32_t> ks_scratch_;
 };
 
 }  // namespace mph

@@ -169,7 +169,21 @@ class ResidueNormal {
       if (g.spos == 1) rec.mutant_sequence = slice(g.gap, seq.size());
       else if (g.spos == 0) rec.mutant_sequence = insertion ? seq : slice(0, this_window_len);
       else rec.mutant_sequence = seq;
-      rec.id = mphfmt::record_id(reinterpret_cast<const uint8_t*>(seq.data()), seq.size(), tm.id, g.s, rev ? 'R' : 'F');
+      {
+        // ids are hashed on the device: per window for the reference haplotype, per key for the others
+        uint64_t id64 = 0;
+        bool have = false;
+        if (key.hap == 0) { have = !raw_.win_id.empty() && raw_.win_id[widx] != 0; if (have) id64 = raw_.win_id[widx]; }
+        else if (h.flags & MPH_NF_ID) { have = true; id64 = h.id64; }
+        if (have) {
+          static const char* hx = "0123456789abcdef";
+          rec.id.resize(16);
+          for (int q2 = 0; q2 < 15; ++q2) rec.id[q2] = hx[(id64 >> (60 - 4 * q2)) & 15];
+          rec.id[15] = rev ? 'R' : 'F';
+        } else {
+          rec.id = mphfmt::record_id(reinterpret_cast<const uint8_t*>(seq.data()), seq.size(), tm.id, g.s, rev ? 'R' : 'F');
+        }
+      }
       rec.tx = t;
       rec.offset = g.s;
       rec.frame = frame;

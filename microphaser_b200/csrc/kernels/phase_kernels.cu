@@ -913,6 +913,12 @@ __global__ void __launch_bounds__(128) k_assemble(const DeviceBatch d) {
       for (uint32_t j = 0; j < ncol; ++j) cols[j] = d.vars[d.vlist[off + 1 + j]];
       err = mph_assemble(sg, g, cols, 0, ncol, d.ref, d.ins_bytes, hap, seq, germ, cap, &out);
     }
+    // record id (:667-675): SHA-1 over the debug rendering of the assembled bytes, hashed while they are in registers / L1
+    if ((out.n_som > 0 || (sg.flags & MPH_SF_HAS_FS)) && out.seq_len <= cap) {
+      const uint32_t t0 = d.tx_id_off[sg.tx];
+      out.id64 = mph_record_id64(seq, out.seq_len, d.tx_id_bytes + t0, d.tx_id_off[sg.tx + 1] - t0, g.s);
+      out.flags |= MPH_HF_ID;
+    }
     if (boundary || out.n_som > 0) {
       const uint32_t off = atomicAdd(&d.counters[CTR_SEQ], 2 * cap);
       if (off + 2 * cap <= d.seq_cap_bytes) {
@@ -943,6 +949,13 @@ __device__ __forceinline__ void normal_window_out(const DeviceBatch& d, const Mp
   MphHap h0;
   const uint32_t err = mph_nrm_plain(sg, g, d.ref, nvar, &h0);
   d.win_depth[widx] = depth | ((nvar == 0 && (h0.flags & MPH_NF_STOP)) ? 0x80000000u : 0u);
+  // every window's reference haplotype is written by the host (:509-645): its record id is hashed here
+  unsigned long long id = 0;
+  if (!(h0.flags & MPH_NF_REFRANGE)) {
+    const uint32_t t0 = d.tx_id_off[sg.tx];
+    id = mph_record_id64(d.ref + sg.ref_off + (g.s - sg.ref_pos0), g.e - g.s, d.tx_id_bytes + t0, d.tx_id_off[sg.tx + 1] - t0, g.s);
+  }
+  d.win_id[widx] = id;
   d.win_flag[widx] = nvar > 0 ? 1 : 0;
   if (nvar) d.hap0[widx] = h0;
   raise(d, err);
@@ -1298,6 +1311,11 @@ __global__ void __launch_bounds__(128) k_assemble_normal(const DeviceBatch d) {
     const uint32_t depth = d.win_out[sg.win_base + i].depth;
     MphHap out;
     uint32_t err = mph_nrm_assemble(sg, g, d.vars, va, vb, d.ref, d.ins_bytes, key.hap, key.count == depth, seq, cap, &out);
+    if (out.seq_len <= cap) {
+      const uint32_t t0 = d.tx_id_off[sg.tx];
+      out.id64 = mph_record_id64(seq, out.seq_len, d.tx_id_bytes + t0, d.tx_id_off[sg.tx + 1] - t0, g.s);
+      out.flags |= MPH_NF_ID;
+    }
     const uint32_t off = atomicAdd(&d.counters[CTR_SEQ], cap);
     if (off + cap <= d.seq_cap_bytes) {
       const uint32_t sl = out.seq_len < cap ? out.seq_len : cap;

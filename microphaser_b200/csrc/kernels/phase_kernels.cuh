@@ -33,6 +33,8 @@ struct DeviceBatch {
   const MphChunk* chunks = nullptr;
   const uint8_t* ref = nullptr;
   const uint32_t* stopmap = nullptr;  // 1 bit per ref byte: a stop codon starts here
+  const uint8_t* tx_id_bytes = nullptr;  // transcript ids (record ids are hashed on the device)
+  const uint32_t* tx_id_off = nullptr;
   // K1 output
   uint64_t* call_S = nullptr;
   uint64_t* call_B = nullptr;
@@ -70,6 +72,7 @@ struct DeviceBatch {
   uint32_t vlist_cap = 0;
   uint32_t* iw_voff = nullptr;   // K4: win_voff of the interesting windows
   uint32_t* seg_err = nullptr;   // per segment: 1 + iteration at which the reference panics, 0 = none
+  unsigned long long* win_id = nullptr;  // normal mode, per window: leading 64 bits of the record id of the unmodified reference window
   uint32_t* win_depth = nullptr;       // normal mode, per window: depth | (plain window begins / ends with a stop codon) << 31
 };
 

@@ -32,6 +32,7 @@ inline PhaseRaw phase_normal(const Batch& b) {
     if (b.read_flags[r] & MPH_RF_OVERFLOW) raw.err |= MPH_E_VARS_PER_WINDOW;
   }
   raw.win_depth.assign(b.n_windows, 0);
+  raw.win_id.assign(b.n_windows, 0);
   std::vector<uint8_t> seqbuf(b.seq_cap);
   for (const MphChunk& ch : b.chunks) {
     const MphSegment& sg = b.segs[ch.seg];
@@ -69,6 +70,9 @@ inline PhaseRaw phase_normal(const Batch& b) {
       MphHap h0;
       raw.err |= mph_nrm_plain(sg, g, b.ref.data(), nv, &h0);
       raw.win_depth[widx] = depth | ((nv == 0 && (h0.flags & MPH_NF_STOP)) ? 0x80000000u : 0u);
+      if (!(h0.flags & MPH_NF_REFRANGE))
+        raw.win_id[widx] = mph_record_id64(b.ref.data() + sg.ref_off + (g.s - sg.ref_pos0), g.e - g.s, b.tx_id_bytes.data() + b.tx_id_off[sg.tx],
+                                          b.tx_id_off[sg.tx + 1] - b.tx_id_off[sg.tx], g.s);
       if (!nv) continue;
       MphWinOut wo;
       wo.depth = depth;
@@ -79,6 +83,10 @@ inline PhaseRaw phase_normal(const Batch& b) {
         if (kv.first == 0) { wo.c0 = kv.second; continue; }
         MphHap hx;
         raw.err |= mph_nrm_assemble(sg, g, b.vars.data(), va, vb, b.ref.data(), b.ins_bytes.data(), kv.first, kv.second == depth, seqbuf.data(), b.seq_cap, &hx);
+        if (hx.seq_len <= b.seq_cap) {
+          hx.id64 = mph_record_id64(seqbuf.data(), hx.seq_len, b.tx_id_bytes.data() + b.tx_id_off[sg.tx], b.tx_id_off[sg.tx + 1] - b.tx_id_off[sg.tx], g.s);
+          hx.flags |= MPH_NF_ID;
+        }
         hx.seq_off = uint32_t(raw.seq.size());
         raw.seq.resize(raw.seq.size() + b.seq_cap, 0);
         memcpy(&raw.seq[hx.seq_off], seqbuf.data(), std::min<uint32_t>(hx.seq_len, b.seq_cap));
@@ -169,6 +177,10 @@ inline PhaseRaw phase_somatic(const Batch& b) {
           memset(&hx, 0, sizeof hx);
           if (e.hap != 0) {
             raw.err |= mph_assemble(sg, g, gathered.data(), 0, ncol, b.ref.data(), b.ins_bytes.data(), e.hap, seqbuf.data(), germbuf.data(), b.seq_cap, &hx);
+            if ((hx.n_som > 0 || (sg.flags & MPH_SF_HAS_FS)) && hx.seq_len <= b.seq_cap) {
+              hx.id64 = mph_record_id64(seqbuf.data(), hx.seq_len, b.tx_id_bytes.data() + b.tx_id_off[sg.tx], b.tx_id_off[sg.tx + 1] - b.tx_id_off[sg.tx], g.s);
+              hx.flags |= MPH_HF_ID;
+            }
             hx.seq_off = uint32_t(raw.seq.size());
             raw.seq.resize(raw.seq.size() + 2 * b.seq_cap, 0);
             memcpy(&raw.seq[hx.seq_off], seqbuf.data(), std::min<uint32_t>(hx.seq_len, b.seq_cap));
@@ -240,6 +252,10 @@ inline PhaseRaw phase_somatic(const Batch& b) {
           return;
         }
         raw.err |= mph_assemble(sg, g, b.vars.data(), va, vb, b.ref.data(), b.ins_bytes.data(), hap, seqbuf.data(), germbuf.data(), b.seq_cap, out);
+        if ((out->n_som > 0 || (sg.flags & MPH_SF_HAS_FS)) && out->seq_len <= b.seq_cap) {
+          out->id64 = mph_record_id64(seqbuf.data(), out->seq_len, b.tx_id_bytes.data() + b.tx_id_off[sg.tx], b.tx_id_off[sg.tx + 1] - b.tx_id_off[sg.tx], g.s);
+          out->flags |= MPH_HF_ID;
+        }
         if (boundary || out->n_som > 0) {
           out->seq_off = uint32_t(raw.seq.size());
           raw.seq.resize(raw.seq.size() + 2 * b.seq_cap, 0);
