@@ -4,6 +4,9 @@
 #include <cuda_runtime.h>
 #include <unistd.h>
 
+#include <condition_variable>
+#include <deque>
+#include <mutex>
 #include <atomic>
 #include <chrono>
 #include <cstdarg>
@@ -53,6 +56,7 @@ struct DevBuf {
     p = nullptr;
     cap = 0;
   }
+  ~DevBuf() { release(); }
 };
 
 }  // namespace
@@ -89,7 +93,11 @@ struct mph_result {
 
 struct mph_ctx {
   int device = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;       // compute + device -> host
+  cudaStream_t copy_stream = nullptr;  // host -> device of the next stage
+  std::vector<cudaEvent_t> ev_copy;
+  uint32_t stage_seg_lo = 0, stage_seg_hi = 0;
+  bool kernels_done = false;           // mph_phase_resident ran for the uploaded batch: mph_phase_collect only downloads
   cudaEvent_t ev[8] = {};
   std::string last_error;
   const mph_batch* cur = nullptr;
@@ -110,8 +118,7 @@ struct mph_ctx {
   DevBuf<MphHap> hap0, hapx, iw_hap0;
   DevBuf<unsigned long long> sums, win_id;
   mph_timing timing = {};
-  bool have_h2d_time = false;
-  PhaseRaw raw;  // download buffers, reused across calls (no page faults after the first)
+  std::vector<PhaseRaw> raws;  // download buffers per stage, reused across calls (no page faults after the first)
   // secondary path: normal-peptidome hash set (open addressing, 5-bit packed peptides)
   DevBuf<unsigned long long> set_table;
   uint64_t set_mask = 0;
@@ -170,35 +177,66 @@ void finish_batch(mph_batch* mb, bool pin) {
     reg(b.read_start); reg(b.read_end); reg(b.read_vlo); reg(b.read_seq_off); reg(b.read_cig_off); reg(b.read_lseq); reg(b.read_ncig);
     reg(b.read_nv); reg(b.read_flags); reg(b.bases); reg(b.cigars); reg(b.vars); reg(b.ins_bytes); reg(b.segs); reg(b.chunks); reg(b.ref); reg(b.stopmap);
     reg(mb->pairs);
+    reg(b.tx_id_bytes); reg(b.tx_id_off); reg(b.replay); reg(b.replay_dq); reg(b.seg_chunk0);
     mb->pinned = true;
   }
 }
 
-template <class T, class V>
-void h2d(mph_ctx* c, DevBuf<T>& dst, const V& src) {
-  dst.ensure(src.size() ? src.size() : 1);
-  if (!src.empty()) CU(cudaMemcpyAsync(dst.p, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+// ---- stages ---------------------------------------------------------------------------------
+// A batch is cut at gene boundaries into stages. mph_phase_batch copies stage s + 1 to the device on the copy stream
+// while the kernels and the download of stage s run on the compute stream and the host threads work on the residue of
+// the stages already downloaded. The resident entry points (upload / phase_resident / collect) use one stage = everything.
+struct Stage {
+  GeneMark lo, hi;
+  uint32_t pair_lo = 0, pair_hi = 0;  // slice of mb->pairs (sorted by read)
+};
+
+std::vector<Stage> plan_stages(const mph_batch* mb, unsigned want) {
+  const Batch& b = mb->b;
+  const size_t n_genes = b.marks.size() - 1;
+  std::vector<Stage> out;
+  if (want < 1) want = 1;
+  size_t g = 0;
+  for (unsigned s = 0; s < want && g < n_genes; ++s) {
+    const uint64_t target = b.marks.back().reads * (s + 1) / want;
+    size_t ge = g + 1;
+    while (ge < n_genes && b.marks[ge].reads < target) ++ge;
+    if (s + 1 == want) ge = n_genes;
+    Stage st;
+    st.lo = b.marks[g];
+    st.hi = b.marks[ge];
+    auto by_read = [](const uint2& a, uint64_t r) { return a.x < r; };
+    st.pair_lo = uint32_t(std::lower_bound(mb->pairs.begin(), mb->pairs.end(), st.lo.reads, by_read) - mb->pairs.begin());
+    st.pair_hi = uint32_t(std::lower_bound(mb->pairs.begin(), mb->pairs.end(), st.hi.reads, by_read) - mb->pairs.begin());
+    out.push_back(st);
+    g = ge;
+  }
+  if (out.empty()) {
+    Stage st;
+    st.lo = b.marks.front();
+    st.hi = b.marks.back();
+    st.pair_hi = uint32_t(mb->pairs.size());
+    out.push_back(st);
+  }
+  return out;
 }
 
-void upload(mph_ctx* c, const mph_batch* mb) {
+// device buffers for the whole batch and the pointers of the kernel argument; nothing is copied here
+void prepare(mph_ctx* c, const mph_batch* mb) {
   const Batch& b = mb->b;
   CU(cudaSetDevice(c->device));
   if (b.n_windows > 0xFFFFFF00ull || b.n_reads() > 0xFFFFFF00ull) throw Unsupported("batch too large: split it into gene ranges");
-  CU(cudaEventRecord(c->ev[0], c->stream));
-  h2d(c, c->read_start, b.read_start); h2d(c, c->read_end, b.read_end); h2d(c, c->read_vlo, b.read_vlo);
-  h2d(c, c->read_seq_off, b.read_seq_off); h2d(c, c->read_cig_off, b.read_cig_off); h2d(c, c->read_lseq, b.read_lseq);
-  h2d(c, c->read_ncig, b.read_ncig); h2d(c, c->read_nv, b.read_nv); h2d(c, c->read_flags, b.read_flags); h2d(c, c->bases, b.bases);
-  h2d(c, c->cigars, b.cigars); h2d(c, c->vars, b.vars); h2d(c, c->ins_bytes, b.ins_bytes); h2d(c, c->segs, b.segs);
-  h2d(c, c->chunks, b.chunks); h2d(c, c->ref, b.ref); h2d(c, c->stopmap, b.stopmap); h2d(c, c->pairs, mb->pairs);
-  h2d(c, c->tx_id_bytes, b.tx_id_bytes); h2d(c, c->tx_id_off, b.tx_id_off);
-  if (!b.replay.empty()) { h2d(c, c->replay, b.replay); h2d(c, c->seg_chunk0, b.seg_chunk0); h2d(c, c->dq_init, b.replay_dq); }
-  CU(cudaEventRecord(c->ev[1], c->stream));
+  if (b.chunks.size() >= (1u << 27)) throw Unsupported("batch too large: split it into gene ranges");
   const size_t nr = b.n_reads(), nw = size_t(b.n_windows);
+  c->read_start.ensure(nr + 1); c->read_end.ensure(nr + 1); c->read_vlo.ensure(nr + 1); c->read_seq_off.ensure(nr + 1); c->read_cig_off.ensure(nr + 1);
+  c->read_lseq.ensure(nr + 1); c->read_ncig.ensure(nr + 1); c->read_nv.ensure(nr + 1); c->read_flags.ensure(nr + 1);
+  c->bases.ensure(b.bases.size() + 1); c->cigars.ensure(b.cigars.size() + 1); c->vars.ensure(b.vars.size() + 1); c->ins_bytes.ensure(b.ins_bytes.size() + 1);
+  c->segs.ensure(b.segs.size() + 1); c->chunks.ensure(b.chunks.size() + 1); c->ref.ensure(b.ref.size() + 1); c->stopmap.ensure(b.stopmap.size() + 1);
+  c->pairs.ensure(mb->pairs.size() + 1); c->tx_id_bytes.ensure(b.tx_id_bytes.size() + 1); c->tx_id_off.ensure(b.tx_id_off.size() + 1);
   c->call_S.ensure(nr + 1); c->call_B.ensure(nr + 1); c->call_flags.ensure(nr + 1);
   c->win_out.ensure(nw + 1); c->hap0.ensure(nw + 1); c->win_flag.ensure(nw + 1);
   c->block_counts.ensure(nw / 1024 + 2);
   c->iw.ensure(nw + 1); c->iw_out.ensure(nw + 1); c->iw_hap0.ensure(nw + 1); c->ovf_list.ensure(nw + 1);
-  if (b.chunks.size() >= (1u << 27)) throw Unsupported("batch too large: split it into gene ranges");
   c->counters.ensure(8); c->sums.ensure(2); c->seg_live.ensure(b.segs.size() + 1);
   if (c->hist.cap == 0) { c->hist.ensure(std::max<size_t>(nw / 2, 1 << 16)); c->hapx.ensure(c->hist.cap); }
   if (c->hapx.cap < c->hist.cap) c->hapx.ensure(c->hist.cap);
@@ -207,10 +245,10 @@ void upload(mph_ctx* c, const mph_batch* mb) {
   if (c->seq.cap < seq_want) c->seq.ensure(seq_want);
   mphk::DeviceBatch& d = c->d;
   d.n_reads = uint32_t(nr); d.n_vars = uint32_t(b.vars.size()); d.n_segs = uint32_t(b.segs.size()); d.n_chunks = uint32_t(b.chunks.size());
-  d.n_windows = uint32_t(nw); d.seq_cap = b.seq_cap; d.n_pairs = uint32_t(mb->pairs.size());
+  d.n_windows = uint32_t(nw); d.seq_cap = b.seq_cap;
   d.read_start = c->read_start.p; d.read_end = c->read_end.p; d.read_vlo = c->read_vlo.p; d.read_seq_off = c->read_seq_off.p;
   d.read_cig_off = c->read_cig_off.p; d.read_lseq = c->read_lseq.p; d.read_ncig = c->read_ncig.p; d.read_nv = c->read_nv.p;
-  d.read_flags = c->read_flags.p; d.pairs = c->pairs.p; d.bases = c->bases.p; d.cigars = c->cigars.p; d.vars = c->vars.p;
+  d.read_flags = c->read_flags.p; d.bases = c->bases.p; d.cigars = c->cigars.p; d.vars = c->vars.p;
   d.ins_bytes = c->ins_bytes.p; d.segs = c->segs.p; d.chunks = c->chunks.p; d.ref = c->ref.p; d.stopmap = c->stopmap.p;
   d.call_S = reinterpret_cast<uint64_t*>(c->call_S.p); d.call_B = reinterpret_cast<uint64_t*>(c->call_B.p); d.call_flags = c->call_flags.p;
   d.win_out = c->win_out.p; d.hap0 = c->hap0.p; d.win_flag = c->win_flag.p; d.block_counts = c->block_counts.p;
@@ -222,6 +260,7 @@ void upload(mph_ctx* c, const mph_batch* mb) {
   d.win_voff = nullptr; d.iw_voff = nullptr;
   if (d.n_replay) {
     const size_t no = size_t(b.replay_obs) + 1;
+    c->replay.ensure(b.replay.size() + 1); c->seg_chunk0.ensure(b.seg_chunk0.size() + 1); c->dq_init.ensure(b.replay_dq.size() + 1);
     c->o_read.ensure(no); c->o_key.ensure(no); c->o_hap.ensure(no); c->o_frame.ensure(no); c->o_flags.ensure(no); c->o_inmat.ensure(no);
     c->win_voff.ensure(nw + 1); c->iw_voff.ensure(nw + 1); c->seg_err.ensure(b.segs.size() + 1);
     if (c->vlist.cap == 0) c->vlist.ensure(1 << 16);
@@ -232,10 +271,47 @@ void upload(mph_ctx* c, const mph_batch* mb) {
   d.mode = uint32_t(b.mode);
   if (b.mode == 1) { c->win_depth.ensure(nw + 1); d.win_depth = c->win_depth.p; c->win_id.ensure(nw + 1); d.win_id = c->win_id.p; }
   c->cur = mb;
+  c->timing = mph_timing{};
   c->timing.h2d_bytes = mb->h2d_bytes;
-  c->have_h2d_time = true;
 }
 
+template <class T, class V>
+void h2d_range(cudaStream_t st, DevBuf<T>& dst, const V& src, size_t lo, size_t hi) {
+  if (hi > src.size()) hi = src.size();
+  if (hi > lo) CU(cudaMemcpyAsync(dst.p + lo, src.data() + lo, (hi - lo) * sizeof(T), cudaMemcpyHostToDevice, st));
+}
+
+// host -> device copy of one stage's slices
+void copy_stage(mph_ctx* c, const mph_batch* mb, const Stage& s, bool first, cudaStream_t st) {
+  const Batch& b = mb->b;
+  const size_t r0 = s.lo.reads, r1 = s.hi.reads;
+  h2d_range(st, c->read_start, b.read_start, r0, r1); h2d_range(st, c->read_end, b.read_end, r0, r1); h2d_range(st, c->read_vlo, b.read_vlo, r0, r1);
+  h2d_range(st, c->read_seq_off, b.read_seq_off, r0, r1); h2d_range(st, c->read_cig_off, b.read_cig_off, r0, r1);
+  h2d_range(st, c->read_lseq, b.read_lseq, r0, r1); h2d_range(st, c->read_ncig, b.read_ncig, r0, r1); h2d_range(st, c->read_nv, b.read_nv, r0, r1);
+  h2d_range(st, c->read_flags, b.read_flags, r0, r1);
+  h2d_range(st, c->bases, b.bases, s.lo.bases, s.hi.bases); h2d_range(st, c->cigars, b.cigars, s.lo.cigars, s.hi.cigars);
+  h2d_range(st, c->vars, b.vars, s.lo.vars, s.hi.vars); h2d_range(st, c->ins_bytes, b.ins_bytes, s.lo.ins, s.hi.ins);
+  h2d_range(st, c->segs, b.segs, s.lo.segs, s.hi.segs); h2d_range(st, c->chunks, b.chunks, s.lo.chunks, s.hi.chunks);
+  h2d_range(st, c->ref, b.ref, s.lo.ref, s.hi.ref);
+  h2d_range(st, c->stopmap, b.stopmap, s.lo.ref / 32, s.hi.ref / 32 + 4);  // whole words; neighbouring stages rewrite the shared word with the same bits
+  h2d_range(st, c->pairs, mb->pairs, s.pair_lo, s.pair_hi);
+  if (first) { h2d_range(st, c->tx_id_bytes, b.tx_id_bytes, 0, b.tx_id_bytes.size()); h2d_range(st, c->tx_id_off, b.tx_id_off, 0, b.tx_id_off.size()); }
+  if (!b.replay.empty()) {
+    h2d_range(st, c->replay, b.replay, s.lo.replay, s.hi.replay); h2d_range(st, c->dq_init, b.replay_dq, s.lo.dq, s.hi.dq);
+    h2d_range(st, c->seg_chunk0, b.seg_chunk0, s.lo.segs, s.hi.segs);
+  }
+}
+
+void set_ranges(mph_ctx* c, const Stage& s) {
+  mphk::DeviceBatch& d = c->d;
+  d.r0 = uint32_t(s.lo.reads); d.r1 = uint32_t(s.hi.reads);
+  d.c0 = uint32_t(s.lo.chunks); d.c1 = uint32_t(s.hi.chunks);
+  d.w0 = uint32_t(s.lo.windows); d.w1 = uint32_t(s.hi.windows);
+  d.rp0 = uint32_t(s.lo.replay); d.rp1 = uint32_t(s.hi.replay);
+  d.pairs = c->pairs.p + s.pair_lo; d.n_pairs = s.pair_hi - s.pair_lo;
+}
+
+// kernels K1-K4 over the slice set by set_ranges, on the compute stream
 void run_kernels(mph_ctx* c) {
   if (!c->cur) throw std::runtime_error("no batch uploaded");
   mphk::DeviceBatch& d = c->d;
@@ -244,11 +320,13 @@ void run_kernels(mph_ctx* c) {
   d.hist = c->hist.p; d.hapx = c->hapx.p; d.hist_win = c->hist_win.p; d.hist_cap = uint32_t(std::min<size_t>(c->hist.cap, 0xFFFFFFF0u));
   d.seq = c->seq.p; d.seq_cap_bytes = uint32_t(std::min<size_t>(c->seq.cap, 0xFFFFFF00u));
   CU(cudaMemsetAsync(c->counters.p, 0, 8 * sizeof(uint32_t), c->stream));
-  CU(cudaMemsetAsync(c->sums.p, 0, 2 * sizeof(unsigned long long), c->stream));
-  if (d.n_replay) {
+  if (d.rp1 > d.rp0) {
     d.vlist = c->vlist.p; d.vlist_cap = uint32_t(std::min<size_t>(c->vlist.cap, 0xFFFFFF00u));
-    CU(cudaMemsetAsync(c->win_voff.p, 0xFF, (size_t(d.n_windows) + 1) * sizeof(uint32_t), c->stream));
-    CU(cudaMemsetAsync(c->seg_err.p, 0, (size_t(d.n_segs) + 1) * sizeof(uint32_t), c->stream));
+    CU(cudaMemsetAsync(c->win_voff.p + d.w0, 0xFF, size_t(d.w1 - d.w0) * sizeof(uint32_t), c->stream));
+    const uint32_t s0 = c->stage_seg_lo, s1 = c->stage_seg_hi;
+    CU(cudaMemsetAsync(c->seg_err.p + s0, 0, size_t(s1 - s0) * sizeof(uint32_t), c->stream));
+  } else if (d.n_replay) {
+    CU(cudaMemsetAsync(c->win_voff.p + d.w0, 0xFF, size_t(d.w1 - d.w0) * sizeof(uint32_t), c->stream));
   }
   CU(cudaEventRecord(c->ev[2], c->stream));
   mphk::launch_allele_call(d, c->stream);
@@ -265,9 +343,9 @@ void run_kernels(mph_ctx* c) {
   CU(cudaGetLastError());
 }
 
-void collect(mph_ctx* c, mph_result** out) {
+// device -> host copy of what the kernels produced for the current slice; re-runs the kernels when an arena was too small
+void fetch_stage(mph_ctx* c, const Stage& s, PhaseRaw& raw, uint64_t* n_iw_total) {
   const Batch& b = c->cur->b;
-  PhaseRaw& raw = c->raw;
   uint32_t ctr[8];
   for (int attempt = 0;; ++attempt) {
     CU(cudaMemcpyAsync(ctr, c->counters.p, sizeof ctr, cudaMemcpyDeviceToHost, c->stream));
@@ -283,11 +361,10 @@ void collect(mph_ctx* c, mph_result** out) {
     break;
   }
   float ms;
-  if (c->have_h2d_time) { CU(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1])); c->timing.h2d_ms = ms; }
-  CU(cudaEventElapsedTime(&ms, c->ev[2], c->ev[3])); c->timing.k1_ms = ms;
-  CU(cudaEventElapsedTime(&ms, c->ev[3], c->ev[4])); c->timing.k2_ms = ms;
-  CU(cudaEventElapsedTime(&ms, c->ev[4], c->ev[5])); c->timing.k3_ms = ms;
-  CU(cudaEventElapsedTime(&ms, c->ev[5], c->ev[6])); c->timing.k4_ms = ms;
+  CU(cudaEventElapsedTime(&ms, c->ev[2], c->ev[3])); c->timing.k1_ms += ms;
+  CU(cudaEventElapsedTime(&ms, c->ev[3], c->ev[4])); c->timing.k2_ms += ms;
+  CU(cudaEventElapsedTime(&ms, c->ev[4], c->ev[5])); c->timing.k3_ms += ms;
+  CU(cudaEventElapsedTime(&ms, c->ev[5], c->ev[6])); c->timing.k4_ms += ms;
   raw.err = ctr[mphk::CTR_ERR];
   if (raw.err & MPH_E_REF_RANGE) throw Fatal("slice index out of range: refseq");
   if (raw.err & MPH_E_VARS_PER_WINDOW) throw Unsupported("more than 32 variants in one window / 64 inside one read");
@@ -307,100 +384,217 @@ void collect(mph_ctx* c, mph_result** out) {
     CU(cudaMemcpyAsync(raw.hapx.data(), c->hapx.p, n_hist * sizeof(MphHap), cudaMemcpyDeviceToHost, c->stream));
   }
   if (n_seq) CU(cudaMemcpyAsync(raw.seq.data(), c->seq.p, n_seq, cudaMemcpyDeviceToHost, c->stream));
-  const uint32_t n_vl = c->d.n_replay ? std::min<uint32_t>(ctr[mphk::CTR_VLIST], c->d.vlist_cap) : 0;
-  raw.iw_voff.resize(c->d.n_replay ? n_iw : 0);
+  const bool has_replay = c->d.n_replay != 0;
+  const uint32_t n_vl = (c->d.rp1 > c->d.rp0) ? std::min<uint32_t>(ctr[mphk::CTR_VLIST], c->d.vlist_cap) : 0;
+  raw.iw_voff.resize(has_replay ? n_iw : 0);
   raw.vlist.resize(n_vl);
-  if (c->d.n_replay && n_iw) CU(cudaMemcpyAsync(raw.iw_voff.data(), c->iw_voff.p, n_iw * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  if (has_replay && n_iw) CU(cudaMemcpyAsync(raw.iw_voff.data(), c->iw_voff.p, n_iw * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
   if (n_vl) CU(cudaMemcpyAsync(raw.vlist.data(), c->vlist.p, size_t(n_vl) * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-  raw.seg_err.resize(c->d.n_replay ? b.segs.size() : 0);
-  if (!raw.seg_err.empty()) CU(cudaMemcpyAsync(raw.seg_err.data(), c->seg_err.p, raw.seg_err.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-  const bool normal_mode = b.mode == 1;
-  raw.win_depth.resize(normal_mode ? size_t(b.n_windows) : 0);
-  raw.win_id.resize(normal_mode ? size_t(b.n_windows) : 0);
-  if (normal_mode && b.n_windows) {
-    CU(cudaMemcpyAsync(raw.win_depth.data(), c->win_depth.p, size_t(b.n_windows) * 4, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaMemcpyAsync(raw.win_id.data(), c->win_id.p, size_t(b.n_windows) * 8, cudaMemcpyDeviceToHost, c->stream));
+  raw.seg_base = uint32_t(s.lo.segs);
+  if (c->d.rp1 > c->d.rp0) {
+    raw.seg_err.resize(size_t(s.hi.segs - s.lo.segs));
+    if (!raw.seg_err.empty()) CU(cudaMemcpyAsync(raw.seg_err.data(), c->seg_err.p + s.lo.segs, raw.seg_err.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  } else {
+    raw.seg_err.clear();
   }
-  unsigned long long sums[2];
-  CU(cudaMemcpyAsync(sums, c->sums.p, sizeof sums, cudaMemcpyDeviceToHost, c->stream));
+  const bool normal_mode = b.mode == 1;
+  const size_t nw = size_t(s.hi.windows - s.lo.windows);
+  raw.win_base = uint32_t(s.lo.windows);
+  raw.win_depth.resize(normal_mode ? nw : 0);
+  raw.win_id.resize(normal_mode ? nw : 0);
+  if (normal_mode && nw) {
+    CU(cudaMemcpyAsync(raw.win_depth.data(), c->win_depth.p + s.lo.windows, nw * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(raw.win_id.data(), c->win_id.p + s.lo.windows, nw * 8, cudaMemcpyDeviceToHost, c->stream));
+  }
   CU(cudaEventRecord(c->ev[1], c->stream));
   CU(cudaStreamSynchronize(c->stream));
   CU(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
-  c->timing.d2h_ms = ms;
-  c->timing.d2h_bytes = sizeof ctr + sizeof sums + size_t(n_iw) * (4 + sizeof(MphWinOut) + sizeof(MphHap)) + size_t(n_hist) * (sizeof(MphHist) + sizeof(MphHap)) + n_seq + raw.win_depth.size() * 12 + (raw.iw_voff.size() + raw.vlist.size() + raw.seg_err.size()) * 4;
-  raw.sum_depth = sums[0];
+  c->timing.d2h_ms += ms;
+  c->timing.d2h_bytes += sizeof ctr + size_t(n_iw) * (4 + sizeof(MphWinOut) + sizeof(MphHap)) + size_t(n_hist) * (sizeof(MphHist) + sizeof(MphHap)) + n_seq +
+                         raw.win_depth.size() * 12 + (raw.iw_voff.size() + raw.vlist.size() + raw.seg_err.size()) * 4;
+  *n_iw_total += n_iw;
+}
 
-  // host residue: the serial part of the window loop, transcripts are independent
-  const auto t0 = std::chrono::steady_clock::now();
-  std::unique_ptr<mph_result> res(new mph_result);
-  res->mode = b.mode;
-  ResidueStats st;
-  const uint32_t n_tx = uint32_t(b.txs.size());
+// host residue workers: transcripts are independent, blocks of them are taken from a queue that the stage loop fills
+struct ResiduePool {
+  struct Task { const PhaseRaw* raw; uint32_t tx_lo, tx_hi; size_t part; };
+  const Batch& b;
+  std::vector<std::vector<OutRecord>>& parts;
+  std::vector<std::thread> threads;
+  std::mutex mu;
+  std::condition_variable cv;
+  std::deque<Task> queue;
+  bool closed = false;
+  std::vector<ResidueStats> stats;
+  std::vector<std::vector<std::pair<uint32_t, uint32_t>>> live;
+  std::vector<std::exception_ptr> errs;
+  std::vector<double> busy_ms;
+
+  ResiduePool(const Batch& batch, std::vector<std::vector<OutRecord>>& out, unsigned n_thr)
+      : b(batch), parts(out), stats(n_thr), live(n_thr), errs(n_thr), busy_ms(n_thr, 0.0) {
+    for (unsigned ti = 0; ti < n_thr; ++ti) threads.emplace_back([this, ti] { run(ti); });
+  }
+  void run(unsigned ti) {
+    for (;;) {
+      Task t;
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return closed || !queue.empty(); });
+        if (queue.empty()) return;
+        t = queue.front();
+        queue.pop_front();
+      }
+      if (errs[ti]) continue;  // keep draining so that finish() returns
+      const auto t0 = std::chrono::steady_clock::now();
+      try {
+        if (b.mode == 1) {
+          ResidueNormal r(b, *t.raw);
+          r.run(t.tx_lo, t.tx_hi, parts[t.part], stats[ti]);
+        } else {
+          Residue r(b, *t.raw);
+          r.run(t.tx_lo, t.tx_hi, parts[t.part], stats[ti]);
+          live[ti].insert(live[ti].end(), r.seg_live_.begin(), r.seg_live_.end());
+        }
+      } catch (...) {
+        errs[ti] = std::current_exception();
+      }
+      busy_ms[ti] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
+  }
+  void push(const PhaseRaw* raw, uint32_t tx_lo, uint32_t tx_hi, size_t part) {
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      queue.push_back(Task{raw, tx_lo, tx_hi, part});
+    }
+    cv.notify_one();
+  }
+  void finish() {
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      closed = true;
+    }
+    cv.notify_all();
+    for (auto& t : threads) t.join();
+    threads.clear();
+  }
+  ~ResiduePool() {
+    if (!threads.empty()) finish();
+  }
+};
+
+unsigned residue_threads(uint32_t n_tx) {
   // host threads for the residue: MPH_HOST_THREADS, else all cores (a multi-GPU launcher gives every rank its share)
   unsigned n_thr = std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 32u);
   if (const char* ht = getenv("MPH_HOST_THREADS")) n_thr = std::max(1, atoi(ht));
   if (n_tx < 256) n_thr = 1;
-  // transcripts are handed out in blocks of 128 (dynamic: blocks differ a lot in the number of interesting windows);
-  // every block keeps its own record vector so that the reference's order needs no copy afterwards
-  const uint32_t blk = 128;
-  const uint32_t n_blk = (n_tx + blk - 1) / blk;
-  std::vector<std::vector<OutRecord>> parts(n_blk);
-  std::vector<ResidueStats> pstats(n_thr);
-  std::vector<std::vector<std::pair<uint32_t, uint32_t>>> plive(n_thr);
-  std::vector<std::exception_ptr> perr(n_thr);
-  std::atomic<uint32_t> next_blk{0};
-  auto work = [&](unsigned ti) {
-    try {
-      Residue rs(b, raw);
-      ResidueNormal rn(b, raw);
-      for (;;) {
-        const uint32_t bi = next_blk.fetch_add(1);
-        if (bi >= n_blk) break;
-        const uint32_t lo = bi * blk, hi = std::min(n_tx, lo + blk);
-        if (normal_mode) rn.run(lo, hi, parts[bi], pstats[ti]);
-        else rs.run(lo, hi, parts[bi], pstats[ti]);
-      }
-      plive[ti] = std::move(rs.seg_live_);
-    } catch (...) {
-      perr[ti] = std::current_exception();
+  return n_thr;
+}
+
+// kernels + download + residue for the stages; `copied` tells whether the inputs are already on the device
+void phase_stages(mph_ctx* c, const std::vector<Stage>& stages, bool copied, mph_result** out) {
+  const mph_batch* mb = c->cur;
+  const Batch& b = mb->b;
+  const auto wall0 = std::chrono::steady_clock::now();
+  const size_t ns = stages.size();
+  if (c->raws.size() < ns) c->raws.resize(ns);
+  if (c->ev_copy.size() < ns + 1) {
+    const size_t old = c->ev_copy.size();
+    c->ev_copy.resize(ns + 1);
+    for (size_t i = old; i < c->ev_copy.size(); ++i) CU(cudaEventCreate(&c->ev_copy[i]));
+  }
+  CU(cudaMemsetAsync(c->sums.p, 0, 2 * sizeof(unsigned long long), c->stream));
+  // Host -> device copies go to the copy stream, the compute stream waits per stage. From pinned buffers they are all
+  // queued now (asynchronous, back to back at link speed); from pageable buffers cudaMemcpyAsync blocks the caller, so
+  // stage s + 1 is queued after the kernels of stage s have been launched.
+  size_t copies_queued = 0;
+  auto queue_copies = [&](size_t upto) {
+    for (; copies_queued < upto && copies_queued < ns; ++copies_queued) {
+      copy_stage(c, mb, stages[copies_queued], copies_queued == 0, c->copy_stream);
+      CU(cudaEventRecord(c->ev_copy[copies_queued], c->copy_stream));
     }
   };
-  if (n_thr == 1) {
-    work(0);
-  } else {
-    std::vector<std::thread> th;
-    for (unsigned ti = 0; ti < n_thr; ++ti) th.emplace_back(work, ti);
-    for (auto& t : th) t.join();
+  if (!copied) {
+    CU(cudaEventRecord(c->ev_copy[ns], c->copy_stream));
+    queue_copies(mb->pinned ? ns : 1);
   }
-  for (auto& e : perr)
-    if (e) std::rethrow_exception(e);
+  std::unique_ptr<mph_result> res(new mph_result);
+  res->mode = b.mode;
+  const uint32_t n_tx = uint32_t(b.txs.size());
+  const uint32_t blk = 128;
+  // record blocks in transcript order: every stage contributes ceil(n / 128) of them
+  std::vector<size_t> part0(ns + 1, 0);
+  for (size_t s = 0; s < ns; ++s) part0[s + 1] = part0[s] + size_t((stages[s].hi.txs - stages[s].lo.txs + blk - 1) / blk);
+  std::vector<std::vector<OutRecord>> parts(part0[ns]);
+  const unsigned n_thr = residue_threads(n_tx);
+  uint64_t n_iw_total = 0;
+  const bool timeline = getenv("MPH_TIMELINE") != nullptr;  // measurement hook
+  {
+    ResiduePool pool(b, parts, n_thr);
+    try {
+      for (size_t s = 0; s < ns; ++s) {
+        const Stage& st = stages[s];
+        if (!copied) CU(cudaStreamWaitEvent(c->stream, c->ev_copy[s], 0));
+        set_ranges(c, st);
+        c->stage_seg_lo = uint32_t(st.lo.segs);
+        c->stage_seg_hi = uint32_t(st.hi.segs);
+        if (!(copied && c->kernels_done)) run_kernels(c);
+        if (!copied) queue_copies(s + 2);
+        fetch_stage(c, st, c->raws[s], &n_iw_total);
+        if (timeline) fprintf(stderr, "[mph] stage %zu downloaded at %.2f ms\n", s, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count());
+        size_t part = part0[s];
+        for (uint32_t lo = uint32_t(st.lo.txs); lo < uint32_t(st.hi.txs); lo += blk, ++part)
+          pool.push(&c->raws[s], lo, std::min<uint32_t>(uint32_t(st.hi.txs), lo + blk), part);
+      }
+    } catch (...) {
+      pool.finish();
+      throw;
+    }
+    if (timeline) fprintf(stderr, "[mph] last stage queued at %.2f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count());
+    pool.finish();
+    if (timeline) fprintf(stderr, "[mph] residue finished at %.2f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count());
+    for (auto& e : pool.errs)
+      if (e) std::rethrow_exception(e);
+    ResidueStats stt;
+    double busy = 0;
+    for (unsigned ti = 0; ti < n_thr; ++ti) {
+      stt.windows += pool.stats[ti].windows;
+      stt.read_windows += pool.stats[ti].read_windows;
+      busy += pool.busy_ms[ti];
+    }
+    c->timing.residue_ms = busy / n_thr;
+    c->timing.windows = stt.windows;
+    c->timing.read_windows = stt.read_windows;
+    // statistics: depth summed on the device over the windows the reference reaches (the normal-mode residue visits
+    // every window and sums the depth itself)
+    if (b.mode != 1) {
+      std::vector<uint32_t> live(b.segs.size() + 1, 0);
+      for (auto& pl : pool.live)
+        for (auto& sl : pl) live[sl.first] = sl.second;
+      CU(cudaMemcpyAsync(c->seg_live.p, live.data(), live.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+      Stage all;
+      all.lo = b.marks.front();
+      all.hi = b.marks.back();
+      all.pair_hi = uint32_t(mb->pairs.size());
+      set_ranges(c, all);
+      mphk::launch_live_depth(c->d, c->stream);
+      unsigned long long sums[2];
+      CU(cudaMemcpyAsync(sums, c->sums.p, sizeof sums, cudaMemcpyDeviceToHost, c->stream));
+      CU(cudaStreamSynchronize(c->stream));
+      c->timing.read_windows += sums[1];
+    }
+  }
+  if (!copied) {
+    float ms;
+    CU(cudaEventElapsedTime(&ms, c->ev_copy[ns], c->ev_copy[ns - 1]));
+    c->timing.h2d_ms = ms;
+  }
   res->part_base.assign(1, 0);
   for (auto& p : parts) res->part_base.push_back(res->part_base.back() + p.size());
-  for (unsigned ti = 0; ti < n_thr; ++ti) {
-    st.windows += pstats[ti].windows;
-    st.read_windows += pstats[ti].read_windows;
-  }
-  c->timing.residue_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-  // statistics: depth summed on the device over the windows the reference reaches
-  if (!normal_mode) {  // the normal-mode residue visits every window and sums the depth itself
-    std::vector<uint32_t> live(b.segs.size() + 1, 0);
-    for (auto& pl : plive)
-      for (auto& sl : pl) live[sl.first] = sl.second;
-    CU(cudaMemcpyAsync(c->seg_live.p, live.data(), live.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
-    mphk::launch_live_depth(c->d, c->stream);
-    CU(cudaMemcpyAsync(sums, c->sums.p, sizeof sums, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
-  } else {
-    sums[1] = 0;
-  }
-  c->timing.windows = st.windows;
-  c->timing.read_windows = st.read_windows + sums[1];
-  c->timing.windows_enumerated = b.n_windows;
-  c->timing.n_interesting = n_iw;
   res->parts = std::move(parts);
+  c->timing.windows_enumerated = b.n_windows;
+  c->timing.n_interesting = n_iw_total;
   c->timing.n_records = res->size();
-  c->timing.kernel_launches = uint32_t(mphk::kernel_launch_count());
-  c->timing.total_ms = c->timing.h2d_ms + c->timing.k1_ms + c->timing.k2_ms + c->timing.k3_ms + c->timing.k4_ms + c->timing.d2h_ms + c->timing.residue_ms;
+  c->timing.kernel_launches = uint32_t(mphk::kernel_launch_count()) * uint32_t(ns);
   for (auto& t : b.txs) {
     res->tx_id.push_back(t.id);
     res->gene_id.push_back(b.genes[t.gene].id);
@@ -408,7 +602,22 @@ void collect(mph_ctx* c, mph_result** out) {
     res->chrom.push_back(b.genes[t.gene].chrom);
     res->tx_reverse.push_back(t.reverse ? 1 : 0);
   }
+  c->timing.total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
+  if (timeline) fprintf(stderr, "[mph] call finished at %.2f ms\n", c->timing.total_ms);
   *out = res.release();
+}
+
+// host buffers in, records out: the pipelined path
+void phase_batch_impl(mph_ctx* c, const mph_batch* mb, mph_result** out) {
+  prepare(c, mb);
+  // stages of about 4 M reads: long enough to keep the copy engine at full rate, short enough to hide all but the first
+  // copy and the last residue
+  unsigned want = unsigned(std::min<uint64_t>(12, std::max<uint64_t>(1, mb->b.n_reads() / 4000000)));
+  if (const char* e = getenv("MPH_STAGES")) want = unsigned(std::max(1, atoi(e)));
+  const std::vector<Stage> stages = plan_stages(mb, want);
+  c->kernels_done = false;
+  phase_stages(c, stages, false, out);
+  c->cur = nullptr;
 }
 
 void write_all(int fd, const std::string& s) {
@@ -569,6 +778,7 @@ int mph_ctx_create(int device, mph_ctx** out) {
     c->device = device;
     CU(cudaSetDevice(device));
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     for (auto& e2 : c->ev) CU(cudaEventCreate(&e2));
   });
   if (rc != MPH_OK) return rc;
@@ -588,8 +798,11 @@ void mph_ctx_destroy(mph_ctx* c) {
   c->hap0.release(); c->hapx.release(); c->iw_hap0.release(); c->sums.release();
   for (auto& e : c->ev)
     if (e) cudaEventDestroy(e);
+  for (auto& e : c->ev_copy)
+    if (e) cudaEventDestroy(e);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->stream) cudaStreamDestroy(c->stream);
-  delete c;
+  delete c;  // the remaining device buffers are released by ~DevBuf
 }
 
 const char* mph_last_error(const mph_ctx* ctx) { return ctx ? ctx->last_error.c_str() : g_last_error.c_str(); }
@@ -686,17 +899,29 @@ int mph_batch_get_view(const mph_batch* mb, mph_batch_view* v) {
 int mph_batch_upload(mph_ctx* ctx, const mph_batch* batch) {
   if (!ctx || !batch) return fail(ctx, MPH_ERR_INPUT, "null argument");
   return guarded(ctx, [&] {
-    upload(ctx, batch);
+    prepare(ctx, batch);
+    const std::vector<Stage> all = plan_stages(batch, 1);
+    CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+    copy_stage(ctx, batch, all[0], true, ctx->stream);
+    CU(cudaEventRecord(ctx->ev[1], ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
+    float ms;
+    CU(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+    ctx->timing.h2d_ms = ms;
+    ctx->kernels_done = false;
   });
 }
 
 int mph_phase_resident(mph_ctx* ctx) {
   if (!ctx) return fail(ctx, MPH_ERR_INPUT, "null argument");
   return guarded(ctx, [&] {
+    if (!ctx->cur) throw std::runtime_error("no batch uploaded");
     CU(cudaSetDevice(ctx->device));
-    ctx->have_h2d_time = false;
-    ctx->timing.h2d_ms = 0;
+    const std::vector<Stage> all = plan_stages(ctx->cur, 1);
+    set_ranges(ctx, all[0]);
+    ctx->stage_seg_lo = 0;
+    ctx->stage_seg_hi = uint32_t(all[0].hi.segs);
+    CU(cudaMemsetAsync(ctx->sums.p, 0, 2 * sizeof(unsigned long long), ctx->stream));
     run_kernels(ctx);
     CU(cudaStreamSynchronize(ctx->stream));
     float ms;
@@ -704,6 +929,7 @@ int mph_phase_resident(mph_ctx* ctx) {
     CU(cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4])); ctx->timing.k2_ms = ms;
     CU(cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5])); ctx->timing.k3_ms = ms;
     CU(cudaEventElapsedTime(&ms, ctx->ev[5], ctx->ev[6])); ctx->timing.k4_ms = ms;
+    ctx->kernels_done = true;
   });
 }
 
@@ -712,18 +938,19 @@ int mph_phase_collect(mph_ctx* ctx, mph_result** out) {
   *out = nullptr;
   return guarded(ctx, [&] {
     if (!ctx->cur) throw std::runtime_error("no resident run to collect");
-    collect(ctx, out);
+    CU(cudaSetDevice(ctx->device));
+    const std::vector<Stage> all = plan_stages(ctx->cur, 1);
+    ctx->timing.k1_ms = ctx->timing.k2_ms = ctx->timing.k3_ms = ctx->timing.k4_ms = 0;
+    ctx->timing.d2h_ms = 0;
+    ctx->timing.d2h_bytes = 0;
+    phase_stages(ctx, all, true, out);
   });
 }
 
 int mph_phase_batch(mph_ctx* ctx, const mph_batch* batch, mph_result** out) {
   if (!ctx || !batch || !out) return fail(ctx, MPH_ERR_INPUT, "null argument");
   *out = nullptr;
-  return guarded(ctx, [&] {
-    upload(ctx, batch);
-    run_kernels(ctx);
-    collect(ctx, out);
-  });
+  return guarded(ctx, [&] { phase_batch_impl(ctx, batch, out); });
 }
 
 int mph_ctx_timing(const mph_ctx* ctx, mph_timing* out) {
@@ -843,10 +1070,7 @@ static void run_somatic_files(const std::vector<mph_ctx*>& ctxs, const char* bam
         batches[k].reset(new mph_batch);
         batches[k]->b = std::move(packer.batch());
         finish_batch(batches[k].get(), false);
-        upload(ctxs[k], batches[k].get());
-        run_kernels(ctxs[k]);
-        collect(ctxs[k], &results[k]);
-        ctxs[k]->cur = nullptr;
+        phase_batch_impl(ctxs[k], batches[k].get(), &results[k]);
       } catch (...) {
         errs[k] = std::current_exception();
       }

@@ -75,8 +75,14 @@ struct GeneMeta {
   uint32_t var_lo, var_hi, read_lo, read_hi;
 };
 
+// sizes of every per-gene-contiguous array after a gene has been packed: a batch can be cut at any gene boundary
+struct GeneMark {
+  uint64_t reads = 0, bases = 0, cigars = 0, vars = 0, ins = 0, segs = 0, chunks = 0, ref = 0, windows = 0, txs = 0, replay = 0, dq = 0, partners = 0;
+};
+
 struct Batch {
   uint32_t window_len = 27;
+  std::vector<GeneMark> marks{GeneMark{}};  // marks[g + 1]: sizes after gene g
   int mode = 0;  // 0 somatic (src/microphasing.rs), 1 normal (src/normal_microphasing.rs)
   // reads (SoA)
   std::vector<uint32_t> read_start, read_end, read_vlo, read_seq_off, read_cig_off;
@@ -476,6 +482,11 @@ class Packer {
       }
     }
     b_.genes.push_back(std::move(gm));
+    GeneMark mk;
+    mk.reads = b_.read_start.size(); mk.bases = b_.bases.size(); mk.cigars = b_.cigars.size(); mk.vars = b_.vars.size(); mk.ins = b_.ins_bytes.size();
+    mk.segs = b_.segs.size(); mk.chunks = b_.chunks.size(); mk.ref = b_.ref.size(); mk.windows = b_.n_windows; mk.txs = b_.txs.size();
+    mk.replay = b_.replay.size(); mk.dq = b_.replay_dq.size(); mk.partners = b_.partner_a.size();
+    b_.marks.push_back(mk);
   }
 
   Batch& batch() { return b_; }

@@ -36,6 +36,8 @@ struct PhaseRaw {
   std::vector<uint32_t> vlist;    // column lists: count, then variant indices in print_haplotypes order
   std::vector<uint64_t> win_id;   // normal mode only, per enumerated window: leading 64 bits of the record id of the reference window (0 = not hashed)
   std::vector<uint32_t> win_depth;  // normal mode only, per enumerated window: depth | (plain window starts / ends with a stop codon) << 31
+  uint32_t seg_base = 0;          // seg_err[0] belongs to this segment
+  uint32_t win_base = 0;          // win_depth[0] / win_id[0] belong to this window
   uint32_t err = 0;
   uint64_t sum_depth = 0;         // over every enumerated window
 };
@@ -549,7 +551,7 @@ class Residue {
       bool stopped = false;
       // the replay found an iteration at which the reference panics (shrink_left past the matrix columns :220-222,
       // inverted BTreeMap range): the loop gets there unless the ORF has ended before
-      const uint32_t panic_k = raw_.seg_err.empty() ? 0xFFFFFFFFu : raw_.seg_err[si] - 1u;
+      const uint32_t panic_k = raw_.seg_err.empty() ? 0xFFFFFFFFu : raw_.seg_err[si - raw_.seg_base] - 1u;
       for (uint32_t k : ks) {
         if (frameshifts.empty()) { stopped = true; break; }
         if (k >= panic_k) throw Fatal("drain: range end out of bounds");

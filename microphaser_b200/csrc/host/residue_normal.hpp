@@ -117,7 +117,7 @@ class ResidueNormal {
     const uint32_t nv = vb - va;
     const bool is_short_exon = (sg.flags & MPH_SF_SHORT) != 0;
     const uint64_t window_len = sg.ewl;
-    const uint32_t wd = raw_.win_depth[widx];
+    const uint32_t wd = raw_.win_depth[widx - raw_.win_base];
     const uint32_t depth = wd & 0x7FFFFFFFu;
     struct Key { uint64_t hap; uint64_t count; const MphHap* info; };
     Key keybuf[64];
@@ -173,7 +173,7 @@ class ResidueNormal {
         // ids are hashed on the device: per window for the reference haplotype, per key for the others
         uint64_t id64 = 0;
         bool have = false;
-        if (key.hap == 0) { have = !raw_.win_id.empty() && raw_.win_id[widx] != 0; if (have) id64 = raw_.win_id[widx]; }
+        if (key.hap == 0) { have = !raw_.win_id.empty() && raw_.win_id[widx - raw_.win_base] != 0; if (have) id64 = raw_.win_id[widx - raw_.win_base]; }
         else if (h.flags & MPH_NF_ID) { have = true; id64 = h.id64; }
         if (have) {
           static const char* hx = "0123456789abcdef";
@@ -292,7 +292,7 @@ class ResidueNormal {
             const uint32_t widx = sg.win_base + (k - sg.k_first) / sg.k_stride;
             if (frameshift == 0) {
               stats.windows += 1;
-              stats.read_windows += raw_.win_depth[widx] & 0x7FFFFFFFu;
+              stats.read_windows += raw_.win_depth[widx - raw_.win_base] & 0x7FFFFFFFu;
             }
             size_t n_res = 0;
             auto res = print(t, sg, k, widx, frameshift, is_boundary(sg, k), out, &n_res);

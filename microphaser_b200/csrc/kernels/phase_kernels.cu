@@ -38,8 +38,8 @@ __device__ __forceinline__ void raise(const DeviceBatch& d, uint32_t bits) {
 
 // ------------------------------------------------------------------ K1
 __global__ void __launch_bounds__(256) k_allele_call(const DeviceBatch d) {
-  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= d.n_reads) return;
+  const uint32_t r = d.r0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= d.r1) return;
   const uint32_t nv = d.read_nv[r];
   const uint32_t hf = d.read_flags[r];
   MphCall c;
@@ -235,8 +235,8 @@ __global__ void __launch_bounds__(K2_WARPS * 32) k_window_hist(const DeviceBatch
   __shared__ int s_add[K2_WARPS][34];
   __shared__ uint32_t s_list[K2_WARPS][K2_LIST];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t chunk = blockIdx.x * K2_WARPS + warp;
-  if (chunk >= d.n_chunks) return;
+  const uint32_t chunk = d.c0 + blockIdx.x * K2_WARPS + warp;
+  if (chunk >= d.c1) return;
   const MphChunk ch = d.chunks[chunk];
   if (lane < (int)(sizeof(MphSegment) / 4)) reinterpret_cast<uint32_t*>(&s_seg[warp])[lane] = reinterpret_cast<const uint32_t*>(&d.segs[ch.seg])[lane];
   s_add[warp][lane] = 0;
@@ -497,8 +497,8 @@ __device__ __forceinline__ void warp_lb2(const uint32_t* __restrict__ a, uint32_
 __global__ void __launch_bounds__(RP_WARPS * 32) k_replay(const DeviceBatch d) {
   __shared__ RpShared sh_all[RP_WARPS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t ti = blockIdx.x * RP_WARPS + warp;
-  if (ti >= d.n_replay) return;
+  const uint32_t ti = d.rp0 + blockIdx.x * RP_WARPS + warp;
+  if (ti >= d.rp1) return;
   RpShared& sh = sh_all[warp];
   const MphReplayTx t = d.replay[ti];
   MphReplayCtx c;
@@ -1099,8 +1099,8 @@ __global__ void __launch_bounds__(K2_WARPS * 32) k_window_hist_normal(const Devi
   __shared__ int s_add[K2_WARPS][34], s_slope[K2_WARPS][34];
   __shared__ uint32_t s_list[K2_WARPS][K2_LIST];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t chunk = blockIdx.x * K2_WARPS + warp;
-  if (chunk >= d.n_chunks) return;
+  const uint32_t chunk = d.c0 + blockIdx.x * K2_WARPS + warp;
+  if (chunk >= d.c1) return;
   const MphChunk ch = d.chunks[chunk];
   if (lane < (int)(sizeof(MphSegment) / 4)) reinterpret_cast<uint32_t*>(&s_seg[warp])[lane] = reinterpret_cast<const uint32_t*>(&d.segs[ch.seg])[lane];
   s_add[warp][lane] = 0;
@@ -1334,8 +1334,8 @@ __global__ void __launch_bounds__(128) k_assemble_normal(const DeviceBatch d) {
 constexpr int SCAN_THREADS = 1024;
 
 __global__ void __launch_bounds__(SCAN_THREADS) k_flag_count(const DeviceBatch d) {
-  const uint32_t w = blockIdx.x * SCAN_THREADS + threadIdx.x;
-  const int f = (w < d.n_windows) ? d.win_flag[w] : 0;
+  const uint32_t w = d.w0 + blockIdx.x * SCAN_THREADS + threadIdx.x;
+  const int f = (w < d.w1) ? d.win_flag[w] : 0;
   const int n = __syncthreads_count(f);
   if (threadIdx.x == 0) d.block_counts[blockIdx.x] = (uint32_t)n;
 }
@@ -1377,9 +1377,9 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_block_scan(const DeviceBatch d
 
 __global__ void __launch_bounds__(SCAN_THREADS) k_scatter(const DeviceBatch d) {
   __shared__ uint32_t warp_sums[32];
-  const uint32_t w = blockIdx.x * SCAN_THREADS + threadIdx.x;
+  const uint32_t w = d.w0 + blockIdx.x * SCAN_THREADS + threadIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const bool f = (w < d.n_windows) && d.win_flag[w];
+  const bool f = (w < d.w1) && d.win_flag[w];
   const unsigned bal = __ballot_sync(FULL, f);
   if (lane == 0) warp_sums[warp] = __popc(bal);
   __syncthreads();
@@ -1403,10 +1403,10 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scatter(const DeviceBatch d) {
 
 // ------------------------------------------------------------------ K5: statistics
 __global__ void __launch_bounds__(256) k_live_depth(const DeviceBatch d) {
-  const uint32_t chunk = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const uint32_t chunk = d.c0 + blockIdx.x * 8 + (threadIdx.x >> 5);
   const uint32_t lane = threadIdx.x & 31;
   unsigned long long v = 0;
-  if (chunk < d.n_chunks) {
+  if (chunk < d.c1) {
     const MphChunk ch = d.chunks[chunk];
     if (lane < ch.n) {
       const uint32_t i = ch.i_first + lane;
@@ -1420,34 +1420,35 @@ __global__ void __launch_bounds__(256) k_live_depth(const DeviceBatch d) {
 }  // namespace
 
 void launch_allele_call(const DeviceBatch& d, cudaStream_t st) {
-  if (d.n_reads) k_allele_call<<<(d.n_reads + 255) / 256, 256, 0, st>>>(d);
+  if (d.r1 > d.r0) k_allele_call<<<(d.r1 - d.r0 + 255) / 256, 256, 0, st>>>(d);
 }
 void launch_window_hist(const DeviceBatch& d, cudaStream_t st) {
-  if (!d.n_chunks) return;
+  if (d.c1 <= d.c0) return;
+  const uint32_t nc = d.c1 - d.c0;
   if (d.mode == 1) {
-    k_window_hist_normal<<<(d.n_chunks + K2_WARPS - 1) / K2_WARPS, K2_WARPS * 32, 0, st>>>(d);
+    k_window_hist_normal<<<(nc + K2_WARPS - 1) / K2_WARPS, K2_WARPS * 32, 0, st>>>(d);
     k_window_hist_wide_normal<<<148, K2_WARPS * 32, 0, st>>>(d);
     return;
   }
-  k_window_hist<<<(d.n_chunks + K2_WARPS - 1) / K2_WARPS, K2_WARPS * 32, 0, st>>>(d);
+  k_window_hist<<<(nc + K2_WARPS - 1) / K2_WARPS, K2_WARPS * 32, 0, st>>>(d);
   // windows with more distinct haplotypes than a lane table holds (rare): one warp per window
   k_window_hist_wide<<<148, K2_WARPS * 32, 0, st>>>(d);
 }
 void launch_replay(const DeviceBatch& d, cudaStream_t st) {
-  if (d.n_replay) k_replay<<<(d.n_replay + RP_WARPS - 1) / RP_WARPS, RP_WARPS * 32, 0, st>>>(d);
+  if (d.rp1 > d.rp0) k_replay<<<(d.rp1 - d.rp0 + RP_WARPS - 1) / RP_WARPS, RP_WARPS * 32, 0, st>>>(d);
 }
 void launch_assemble(const DeviceBatch& d, cudaStream_t st) {
-  if (d.n_chunks && d.mode == 1) k_assemble_normal<<<148 * 8, 128, 0, st>>>(d);
-  else if (d.n_chunks) k_assemble<<<148 * 8, 128, 0, st>>>(d);  // grid-stride over the key arena (its size lives on the device)
+  if (d.c1 > d.c0 && d.mode == 1) k_assemble_normal<<<148 * 8, 128, 0, st>>>(d);
+  else if (d.c1 > d.c0) k_assemble<<<148 * 8, 128, 0, st>>>(d);  // grid-stride over the key arena (its size lives on the device)
 }
 void launch_compact(const DeviceBatch& d, cudaStream_t st) {
-  const uint32_t nb = (d.n_windows + SCAN_THREADS - 1) / SCAN_THREADS;
+  const uint32_t nb = (d.w1 - d.w0 + SCAN_THREADS - 1) / SCAN_THREADS;
   if (nb) k_flag_count<<<nb, SCAN_THREADS, 0, st>>>(d);
   k_block_scan<<<1, SCAN_THREADS, 0, st>>>(d, nb);
   if (nb) k_scatter<<<nb, SCAN_THREADS, 0, st>>>(d);
 }
 void launch_live_depth(const DeviceBatch& d, cudaStream_t st) {
-  if (d.n_chunks) k_live_depth<<<(d.n_chunks + 7) / 8, 256, 0, st>>>(d);
+  if (d.c1 > d.c0) k_live_depth<<<(d.c1 - d.c0 + 7) / 8, 256, 0, st>>>(d);
 }
 int kernel_launch_count() { return 7; }
 

@@ -13,6 +13,11 @@ namespace mphk {
 struct DeviceBatch {
   // inputs
   uint32_t n_reads = 0, n_vars = 0, n_segs = 0, n_chunks = 0, n_windows = 0, seq_cap = 64, n_pairs = 0;
+  // the slice of the batch one launch sequence works on (a stage of the copy / compute / residue pipeline, or everything)
+  uint32_t r0 = 0, r1 = 0;    // reads (K1)
+  uint32_t c0 = 0, c1 = 0;    // chunks (K2, K5)
+  uint32_t w0 = 0, w1 = 0;    // windows (K4)
+  uint32_t rp0 = 0, rp1 = 0;  // replay units
   uint32_t mode = 0;        // 0 somatic, 1 normal (reference src/normal_microphasing.rs)
   uint32_t force_wide = 0;  // test hook (MPH_FORCE_WIDE=1): send every window with extra keys through k_window_hist_wide
   const uint32_t* read_start = nullptr;
@@ -24,7 +29,7 @@ struct DeviceBatch {
   const uint16_t* read_ncig = nullptr;
   const uint8_t* read_nv = nullptr;
   const uint8_t* read_flags = nullptr;
-  const uint2* pairs = nullptr;  // (read, partner) sorted by read — both directions
+  const uint2* pairs = nullptr;  // (read, partner) sorted by read — both directions; the current slice's pairs, n_pairs of them
   const uint8_t* bases = nullptr;
   const uint32_t* cigars = nullptr;
   const MphVar* vars = nullptr;
