@@ -136,12 +136,16 @@ int mph_phase_resident(mph_ctx* ctx);                     /* kernels K1-K4 only,
 int mph_phase_collect(mph_ctx* ctx, mph_result** out);    /* D2H + residue of the last resident run */
 
 typedef struct {
-  double h2d_ms, k1_ms, k2_ms, k3_ms, k4_ms, d2h_ms, residue_ms, total_ms; /* CUDA events on the stream; residue: host clock */
+  /* CUDA events on the library's streams, summed over the pipeline stages of one call; residue_ms: busy time of the
+   * host threads / thread count; total_ms: wall clock of the call (the stages overlap, so it is less than the sum) */
+  double h2d_ms, k1_ms, k2_ms, k3_ms, k4_ms, d2h_ms, residue_ms, total_ms;
   uint64_t h2d_bytes, d2h_bytes;
   uint64_t windows;       /* main-ORF windows the reference evaluates (print_haplotypes calls, frame 0) */
   uint64_t read_windows;  /* sum of depth over them */
   uint64_t windows_enumerated, n_interesting, n_records;
   uint32_t kernel_launches;
+  uint32_t n_replay_units; /* replay units (runs of exons of irregular transcripts) that went through k_replay */
+  double replay_ms;        /* k_replay, CUDA events; k2_ms is the closed-form window kernel alone */
 } mph_timing;
 int mph_ctx_timing(const mph_ctx* ctx, mph_timing* out);
 

@@ -98,7 +98,7 @@ struct mph_ctx {
   std::vector<cudaEvent_t> ev_copy;
   uint32_t stage_seg_lo = 0, stage_seg_hi = 0;
   bool kernels_done = false;           // mph_phase_resident ran for the uploaded batch: mph_phase_collect only downloads
-  cudaEvent_t ev[8] = {};
+  cudaEvent_t ev[9] = {};
   std::string last_error;
   const mph_batch* cur = nullptr;
   mphk::DeviceBatch d;
@@ -334,6 +334,7 @@ void run_kernels(mph_ctx* c) {
   // measured on B200: the replay warps are latency-bound; sharing the SMs with the closed-form kernel (second stream,
   // either priority) slows both by more than the overlap gains, so the two kernels run back to back
   mphk::launch_replay(d, c->stream);
+  CU(cudaEventRecord(c->ev[8], c->stream));
   mphk::launch_window_hist(d, c->stream);
   CU(cudaEventRecord(c->ev[4], c->stream));
   mphk::launch_assemble(d, c->stream);
@@ -362,7 +363,8 @@ void fetch_stage(mph_ctx* c, const Stage& s, PhaseRaw& raw, uint64_t* n_iw_total
   }
   float ms;
   CU(cudaEventElapsedTime(&ms, c->ev[2], c->ev[3])); c->timing.k1_ms += ms;
-  CU(cudaEventElapsedTime(&ms, c->ev[3], c->ev[4])); c->timing.k2_ms += ms;
+  CU(cudaEventElapsedTime(&ms, c->ev[3], c->ev[8])); c->timing.replay_ms += ms;
+  CU(cudaEventElapsedTime(&ms, c->ev[8], c->ev[4])); c->timing.k2_ms += ms;
   CU(cudaEventElapsedTime(&ms, c->ev[4], c->ev[5])); c->timing.k3_ms += ms;
   CU(cudaEventElapsedTime(&ms, c->ev[5], c->ev[6])); c->timing.k4_ms += ms;
   raw.err = ctr[mphk::CTR_ERR];
@@ -594,7 +596,8 @@ void phase_stages(mph_ctx* c, const std::vector<Stage>& stages, bool copied, mph
   c->timing.windows_enumerated = b.n_windows;
   c->timing.n_interesting = n_iw_total;
   c->timing.n_records = res->size();
-  c->timing.kernel_launches = uint32_t(mphk::kernel_launch_count()) * uint32_t(ns);
+  c->timing.kernel_launches = (uint32_t(mphk::kernel_launch_count()) + (b.replay.empty() ? 0u : 1u)) * uint32_t(ns);
+  c->timing.n_replay_units = uint32_t(b.replay.size());
   for (auto& t : b.txs) {
     res->tx_id.push_back(t.id);
     res->gene_id.push_back(b.genes[t.gene].id);
@@ -926,7 +929,8 @@ int mph_phase_resident(mph_ctx* ctx) {
     CU(cudaStreamSynchronize(ctx->stream));
     float ms;
     CU(cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3])); ctx->timing.k1_ms = ms;
-    CU(cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4])); ctx->timing.k2_ms = ms;
+    CU(cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[8])); ctx->timing.replay_ms = ms;
+    CU(cudaEventElapsedTime(&ms, ctx->ev[8], ctx->ev[4])); ctx->timing.k2_ms = ms;
     CU(cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5])); ctx->timing.k3_ms = ms;
     CU(cudaEventElapsedTime(&ms, ctx->ev[5], ctx->ev[6])); ctx->timing.k4_ms = ms;
     ctx->kernels_done = true;
@@ -940,7 +944,7 @@ int mph_phase_collect(mph_ctx* ctx, mph_result** out) {
     if (!ctx->cur) throw std::runtime_error("no resident run to collect");
     CU(cudaSetDevice(ctx->device));
     const std::vector<Stage> all = plan_stages(ctx->cur, 1);
-    ctx->timing.k1_ms = ctx->timing.k2_ms = ctx->timing.k3_ms = ctx->timing.k4_ms = 0;
+    ctx->timing.k1_ms = ctx->timing.k2_ms = ctx->timing.k3_ms = ctx->timing.k4_ms = ctx->timing.replay_ms = 0;
     ctx->timing.d2h_ms = 0;
     ctx->timing.d2h_bytes = 0;
     phase_stages(ctx, all, true, out);
