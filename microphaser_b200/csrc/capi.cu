@@ -1211,7 +1211,8 @@ int mph_synth_batch(const mph_synth_params* sp, uint32_t window_len, int pin, mp
   if (!sp || !out) return fail(nullptr, MPH_ERR_INPUT, "null argument");
   std::unique_ptr<mph_batch> mb(new mph_batch);
   int rc = guarded(nullptr, [&] {
-    Packer packer(window_len);
+    const char* me = getenv("MPH_SYNTH_MODE");  // measurement hook: 1 packs the same workload for the normal mode
+    Packer packer(window_len, (me && *me == '1') ? 1 : 0);
     SynthParams p;
     p.seed = sp->seed; p.n_transcripts = sp->n_transcripts; p.exons = sp->exons_per_transcript; p.exon_min = sp->exon_len_min;
     p.exon_max = sp->exon_len_max; p.read_len = sp->read_len; p.coverage = sp->coverage; p.germline_per_kb = sp->germline_per_kb;

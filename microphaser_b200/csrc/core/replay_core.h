@@ -43,6 +43,10 @@ typedef struct {
   const MphVar* vars; const MphSegment* segs; const uint32_t* seg_chunk0;
   const uint32_t* stopmap; const uint8_t* ref;
   const uint32_t* dq_init;  // arena of initial column lists
+  uint32_t mode;            // 0 somatic, 1 normal (src/normal_microphasing.rs: every re-offered copy of a read is kept, no quality test)
+  const uint8_t* tx_id_bytes; const uint32_t* tx_id_off;  // normal mode: record id of the reference window
+  uint32_t* win_depth; unsigned long long* win_id;        // normal mode outputs
+  uint32_t* o_last;         // normal mode, per gene read: index of its latest entry (entries are (read, haplotype, copies))
   // scratch: observation list
   uint32_t* o_read; uint64_t* o_hap; uint32_t* o_frame; uint8_t* o_flags;
   uint8_t* o_inmat;  // per gene read (obs_off + read - read_lo): the read is an observation right now
@@ -91,7 +95,7 @@ MPH_HD void mph_rp_eval(const MphReplayCtx& c, uint32_t r, uint32_t v, bool* sup
     const uint8_t* b = c.bases + (size_t)soff * 16;
     const uint8_t* lowq = b + ((l_seq + 1u) >> 1);
     const uint32_t rel = var.pos - start;
-    if (rel < l_seq && ((lowq[rel >> 3] >> (rel & 7u)) & 1u)) { *bad = true; return; }
+    if (c.mode == 0 && rel < l_seq && ((lowq[rel >> 3] >> (rel & 7u)) & 1u)) { *bad = true; return; }
     uint32_t q;
     if (mph_read_pos(cig, ncig, l_seq, start, var.pos, &q) && q < l_seq) {
       const uint8_t x = b[q >> 1];
@@ -111,6 +115,10 @@ MPH_HD void mph_rp_update(const MphReplayCtx& c, const MphReplayTx& t, uint32_t 
   const uint32_t fs = (var.flags & MPH_VF_FS_MASK) >> MPH_VF_FS_SHIFT;
   bool sup, bad;
   mph_rp_eval(c, r, v, &sup, &bad, err);
+  if (c.mode == 1) {  // normal_microphasing.rs:195-215: only the supported bit
+    if (sup) *hap |= (uint64_t)1 << (i & 63u);
+    return;
+  }
   if (fs > 0 && var.pos != 0) *frame |= 0x80000000u;
   if (sup) {
     if (v >= t.sl_va && v < t.sl_vb) *flags |= 2;
@@ -139,11 +147,15 @@ MPH_HD void mph_rp_emit(const MphReplayCtx& c, const MphReplayTx& t, const MphSe
   const uint32_t widx = sg.win_base + i;
   MphHist table[MPH_RP_KEYS];
   uint32_t n_keys = 0, c0 = 0;
+  const bool normal = c.mode == 1;
+  uint32_t depth = normal ? 0u : n_obs;
   for (uint32_t o = 0; o < n_obs; ++o) {
     if (c.o_flags[t.obs_off + o] & 1) continue;
     const uint64_t hap = c.o_hap[t.obs_off + o];
-    const uint32_t fr = c.o_frame[t.obs_off + o];
-    if (hap == 0 && fr == 0) { ++c0; continue; }
+    const uint32_t wgt = normal ? c.o_frame[t.obs_off + o] : 1u;  // normal mode: copies of the read with this haplotype
+    const uint32_t fr = normal ? 0u : c.o_frame[t.obs_off + o];
+    if (normal) depth += wgt;
+    if (hap == 0 && fr == 0) { c0 += wgt; continue; }
     uint32_t x = 0;
     for (; x < n_keys; ++x)
       if (table[x].hap == hap && table[x].frame == fr) break;
@@ -152,7 +164,7 @@ MPH_HD void mph_rp_emit(const MphReplayCtx& c, const MphReplayTx& t, const MphSe
       table[x].hap = hap; table[x].frame = fr; table[x].count = 0;
       ++n_keys;
     }
-    table[x].count += 1;
+    table[x].count += wgt;
   }
   for (uint32_t a = 1; a < n_keys; ++a) {  // BTreeMap order (:383,434): haplotype, frame.0, frame.1 != 0
     const MphHist key = table[a];
@@ -168,7 +180,7 @@ MPH_HD void mph_rp_emit(const MphReplayCtx& c, const MphReplayTx& t, const MphSe
     table[b] = key;
   }
   MphWinOut wo;
-  wo.depth = n_obs;
+  wo.depth = depth;
   wo.c0 = c0;
   wo.n_extra = n_keys;
   wo.extra_off = 0;
@@ -187,7 +199,7 @@ MPH_HD void mph_rp_emit(const MphReplayCtx& c, const MphReplayTx& t, const MphSe
     }
   }
   c.win_out[widx] = wo;
-  MPH_RP_ADD64(c.sum_depth, n_obs);
+  MPH_RP_ADD64(c.sum_depth, depth);
   // the matrix columns in print_haplotypes order (:372-378): the deque, reversed on the reverse strand
   const bool rev = (sg.flags & MPH_SF_REVERSE) != 0;
   uint32_t n_walk = 0;
@@ -207,10 +219,22 @@ MPH_HD void mph_rp_emit(const MphReplayCtx& c, const MphReplayTx& t, const MphSe
     n_walk = j;
   }
   MphHap h0;
-  *err |= mph_plain_hap(sg, g, c.stopmap, c.ref, n_walk, &h0);
+  if (normal) {
+    *err |= mph_nrm_plain(sg, g, c.ref, n_walk, &h0);
+    c.win_depth[widx] = depth | ((ncols == 0 && (h0.flags & MPH_NF_STOP)) ? 0x80000000u : 0u);
+    unsigned long long id = 0;
+    if (!(h0.flags & MPH_NF_REFRANGE)) {
+      const uint32_t t0 = c.tx_id_off[sg.tx];
+      id = mph_record_id64(c.ref + sg.ref_off + (g.s - sg.ref_pos0), g.e - g.s, c.tx_id_bytes + t0, c.tx_id_off[sg.tx + 1] - t0, g.s);
+    }
+    c.win_id[widx] = id;
+    c.win_flag[widx] = ncols > 0 ? 1 : 0;  // the residue reads a window without columns from win_depth / win_id alone
+  } else {
+    *err |= mph_plain_hap(sg, g, c.stopmap, c.ref, n_walk, &h0);
+    c.win_flag[widx] = 1;
+  }
   if (ncols > 32) *err |= MPH_E_VARS_PER_WINDOW;
   c.hap0[widx] = h0;
-  c.win_flag[widx] = 1;
   (void)k;
 }
 
@@ -227,7 +251,11 @@ MPH_HD void mph_replay_tx(const MphReplayCtx& c, const MphReplayTx& t) {
   uint32_t* o_frame = c.o_frame + t.obs_off;
   uint8_t* o_flags = c.o_flags + t.obs_off;
   uint8_t* in_mat = c.o_inmat + t.obs_off;
-  for (uint32_t x = 0; x < t.obs_cap; ++x) in_mat[x] = 0;
+  const bool normal = c.mode == 1;
+  uint32_t* o_last = normal ? c.o_last + t.obs_off : nullptr;  // indexed by read - read_lo (obs_cap >= number of gene reads)
+  const uint32_t n_gene_reads = t.read_hi - t.read_lo;
+  if (normal) { for (uint32_t x = 0; x < n_gene_reads; ++x) o_last[x] = 0xFFFFFFFFu; }
+  else { for (uint32_t x = 0; x < t.obs_cap; ++x) in_mat[x] = 0; }
   bool panicked = false;
   auto shrink_left = [&](uint64_t n) -> bool {  // :220-229
     if (n > ncols) { panicked = true; return false; }  // drain(..k) out of range
@@ -273,10 +301,14 @@ MPH_HD void mph_replay_tx(const MphReplayCtx& c, const MphReplayTx& t) {
         uint32_t w = 0;
         for (uint32_t o = 0; o < n_obs; ++o) {
           const uint32_t r = o_read[o];
-          const bool keep = rev ? c.read_start[r] < g.s + 1u : c.read_end[r] >= g.e;
+          // somatic: cleanup_reads(splice_side_offset + 1) (:1257); normal: cleanup_reads(splice_side_offset) (normal_microphasing.rs:1001)
+          const bool keep = rev ? c.read_start[r] < g.s + (normal ? 0u : 1u) : c.read_end[r] >= g.e;
           if (keep) {
             if (w != o) { o_read[w] = r; o_hap[w] = o_hap[o]; o_frame[w] = o_frame[o]; o_flags[w] = o_flags[o]; }
+            if (normal) o_last[r - t.read_lo] = w;  // entries of one read keep their order
             ++w;
+          } else if (normal) {
+            o_last[r - t.read_lo] = 0xFFFFFFFFu;
           } else {
             in_mat[r - t.read_lo] = 0;
           }
@@ -292,6 +324,21 @@ MPH_HD void mph_replay_tx(const MphReplayCtx& c, const MphReplayTx& t) {
         const uint32_t r1 = mph_u32_lb(c.read_start, r0, t.read_hi, g.s + 1u);
         for (uint32_t r = r0; r < r1; ++r) {
           if (c.read_end[r] < g.e) continue;
+          if (normal) {
+            // push_read of the normal mode (:301-331): no `contains`, columns numbered oldest-first, nothing is rejected;
+            // consecutive copies of a read with the same haplotype share one entry
+            uint64_t hap = 0;
+            uint32_t fr0 = 0;
+            uint8_t fl0 = 0;
+            for (uint32_t i = 0; i < ncols; ++i) mph_rp_update(c, t, r, i, dq[i], &hap, &fr0, &fl0, &err);
+            const uint32_t e = o_last[r - t.read_lo];
+            if (e != 0xFFFFFFFFu && o_hap[e] == hap) { o_frame[e] += 1; continue; }
+            if (n_obs >= t.obs_cap) { err |= MPH_E_REPLAY_INPUT; continue; }
+            o_read[n_obs] = r; o_hap[n_obs] = hap; o_frame[n_obs] = 1; o_flags[n_obs] = 0;
+            o_last[r - t.read_lo] = n_obs;
+            ++n_obs;
+            continue;
+          }
           if (rev) {
             // `contains` (:281-294): an observation with the same start and qname is already in the matrix
             bool dup = in_mat[r - t.read_lo] != 0;

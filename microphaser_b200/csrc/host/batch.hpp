@@ -377,7 +377,6 @@ class Packer {
       }
       tm.seg_hi = uint32_t(b_.segs.size());
       if (tx_replay && tm.seg_hi > tm.seg_lo) {
-        if (b_.mode != 0) throw Unsupported("transcript " + t.id + ": the normal mode has no serial replay (observation carry-over / stale matrix column)");
         // split the transcript into units at the exon boundaries no observation crosses; the matrix columns at a
         // unit start come from a read-free pass over the window loop's column bookkeeping (:1119-1178,1280-1296)
         std::vector<uint32_t> dq;
@@ -387,7 +386,8 @@ class Packer {
         memset(&rt, 0, sizeof rt);
         auto open_unit = [&](uint32_t si) {
           rt.seg_lo = si; rt.read_lo = gm.read_lo; rt.read_hi = gm.read_hi;
-          rt.obs_off = uint32_t(b_.replay_obs); rt.obs_cap = gm.read_hi - gm.read_lo;
+          // normal mode keeps every copy of a re-offered read; copies with equal haplotypes share an entry
+          rt.obs_off = uint32_t(b_.replay_obs); rt.obs_cap = b_.mode == 1 ? 4 * (gm.read_hi - gm.read_lo) + 1024 : gm.read_hi - gm.read_lo;
           rt.sl_va = b_.segs[tm.seg_lo].sl_va; rt.sl_vb = b_.segs[tm.seg_lo].sl_vb;
           if (!(b_.segs[tm.seg_lo].flags & MPH_SF_FIRST_EXON)) rt.sl_va = rt.sl_vb = 0;
           rt.dq_off = uint32_t(b_.replay_dq.size()); rt.dq_n = uint32_t(dq.size()); rt.last_vars = uint32_t(last_vars);

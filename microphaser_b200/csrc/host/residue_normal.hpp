@@ -64,7 +64,8 @@ class ResidueNormal {
 
   // variant-site metadata (:509-560): 0-based positions; sites are only counted while the walk
   // produced a profile entry for the variant
-  void fill_meta(InfoRecord& rec, uint32_t va, uint32_t nv, const MphHap& h) const {
+  void fill_meta(InfoRecord& rec, const WinVars& wv, const MphHap& h) const {
+    const uint32_t nv = wv.n;
     uint32_t n_sites = 0, n_som_sites = 0;
     std::string s_pc, g_pc, s_pos, g_pos, sites;
     bool fs = true, fg = true, fsite = true, fspc = true, fgpc = true;
@@ -76,20 +77,20 @@ class ResidueNormal {
       dst.append(buf, r.ptr);
     };
     for (uint32_t c = 0; c < nv && c < h.n_prof; ++c) {
-      const MphVar& v = b_.vars[va + c];
+      const MphVar& v = b_.vars[wv.at(c)];
       const unsigned code = c < 32 ? unsigned((h.profile >> (2 * c)) & 3) : 0;
       if (code == 2) {
         put(s_pos, fs, v.pos);
         if (!fspc) s_pc.push_back('|');
         fspc = false;
-        s_pc += b_.var_prot[va + c];
+        s_pc += b_.var_prot[wv.at(c)];
       } else if (code == 1) {
         put(g_pos, fg, v.pos);
         if (!fgpc) g_pc.push_back('|');
         fgpc = false;
-        g_pc += b_.var_prot[va + c];
+        g_pc += b_.var_prot[wv.at(c)];
       }
-      if (c == 0 || v.pos != b_.vars[va + c - 1].pos) {
+      if (c == 0 || v.pos != b_.vars[wv.at(c - 1)].pos) {
         ++n_sites;
         put(sites, fsite, v.pos);
         if (!(v.flags & MPH_VF_GERMLINE)) ++n_som_sites;
@@ -112,9 +113,21 @@ class ResidueNormal {
     const TxMeta& tm = b_.txs[t];
     const bool rev = tm.reverse;
     const MphGeom g = mph_geom(sg, k);
-    const uint32_t va = mph_var_lb(b_.vars.data(), sg.var_lo, sg.var_hi, g.s);
-    const uint32_t vb = mph_var_lb(b_.vars.data(), sg.var_lo, sg.var_hi, g.e);
-    const uint32_t nv = vb - va;
+    WinVars wv;
+    wv.va = mph_var_lb(b_.vars.data(), sg.var_lo, sg.var_hi, g.s);
+    wv.n = mph_var_lb(b_.vars.data(), sg.var_lo, sg.var_hi, g.e) - wv.va;
+    size_t iwi = SIZE_MAX;
+    if (sg.flags & MPH_SF_REPLAY) {
+      // replayed transcript: the matrix columns are what the replay recorded, not the variants inside the window
+      iwi = find_iw(widx);
+      wv.n = 0;
+      if (iwi != SIZE_MAX && !raw_.iw_voff.empty() && raw_.iw_voff[iwi] != 0xFFFFFFFFu) {
+        const uint32_t off = raw_.iw_voff[iwi];
+        wv.n = raw_.vlist[off];
+        wv.list = raw_.vlist.data() + off + 1;
+      }
+    }
+    const uint32_t nv = wv.n;
     const bool is_short_exon = (sg.flags & MPH_SF_SHORT) != 0;
     const uint64_t window_len = sg.ewl;
     const uint32_t wd = raw_.win_depth[widx - raw_.win_base];
@@ -129,7 +142,7 @@ class ResidueNormal {
       plain.seq_len = uint16_t(g.e - g.s);
       keybuf[n_keys++] = Key{0, depth, &plain};
     } else {
-      const size_t iwi = find_iw(widx);
+      if (iwi == SIZE_MAX) iwi = find_iw(widx);
       if (iwi == SIZE_MAX) throw std::logic_error("internal: window summary missing");
       const MphWinOut& wo = raw_.iw_out[iwi];
       if (wo.c0 > 0) keybuf[n_keys++] = Key{0, wo.c0, &raw_.iw_hap0[iwi]};
@@ -189,7 +202,7 @@ class ResidueNormal {
       rec.frame = frame;
       rec.freq = freq;
       rec.depth = depth;
-      if (nv) fill_meta(rec, va, nv, h);
+      if (nv) fill_meta(rec, wv, h);
       ++*n_res;
       if (keep) {
         HapSeq hs;
@@ -243,9 +256,13 @@ class ResidueNormal {
       uint32_t prev_vb_fs = 0, prev_va_fs = 0;
       bool fs_init = false;
       const uint32_t n_steps = has_fs ? sg.n_iter : sg.n_win;
+      // iteration at which the reference panics (found by the replay); reached unless the ORF ended before
+      const uint32_t panic_k = raw_.seg_err.empty() ? 0xFFFFFFFFu : raw_.seg_err[si - raw_.seg_base] - 1u;
+      bool left_early = false;
       for (uint32_t step = 0; step < n_steps; ++step) {
-        if (frameshifts.empty()) break;
+        if (frameshifts.empty()) { left_early = true; break; }
         const uint32_t k = has_fs ? step : sg.k_first + step * sg.k_stride;
+        if (k >= panic_k) throw Fatal("drain: range end out of bounds");
         const MphGeom g = mph_geom(sg, k);
         const uint64_t offset = fwd ? uint64_t(sg.off0) + k : uint64_t(sg.off0) - k;
         const uint64_t rest = fwd ? sg.exon_end - (offset + exon_window_len) : offset - sg.exon_start;
@@ -303,16 +320,18 @@ class ResidueNormal {
         }
         if (frameshift_count == 0 || !main_orf) {
           frameshifts.clear();
+          left_early = true;
           break;
         }
         frameshifts.erase(stopped_frameshift);  // :1130 — unconditional
-        if (frameshifts.empty()) break;
+        if (frameshifts.empty()) { left_early = true; break; }
         const bool at_splice_side = fwd ? offset - current_exon_offset == sg.exon_start
                                         : offset + exon_window_len + current_exon_offset == sg.exon_end;
         if (at_splice_side && !is_first_exon)
           splice_merge(t, fwd, is_short_exon, is_last_exon, is_last_exon_window, exon_rest, window_len, hap_vec, prev_hap_vec, out);
         if (is_short_exon) break;
       }
+      if (!left_early && !frameshifts.empty() && panic_k != 0xFFFFFFFFu) throw Fatal("drain: range end out of bounds");
     }
   }
 

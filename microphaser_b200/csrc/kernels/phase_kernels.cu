@@ -508,6 +508,7 @@ __global__ void __launch_bounds__(RP_WARPS * 32) k_replay(const DeviceBatch d) {
   c.pairs = reinterpret_cast<const uint32_t*>(d.pairs); c.n_pairs = d.n_pairs;
   c.vars = d.vars; c.segs = d.segs; c.seg_chunk0 = d.seg_chunk0; c.stopmap = d.stopmap; c.ref = d.ref;
   c.dq_init = d.dq_init;
+  c.mode = 0; c.tx_id_bytes = nullptr; c.tx_id_off = nullptr; c.win_depth = nullptr; c.win_id = nullptr; c.o_last = nullptr; c.seg_err = d.seg_err;
   c.o_read = nullptr; c.o_hap = nullptr; c.o_frame = nullptr; c.o_flags = nullptr; c.o_inmat = d.o_inmat;
   c.win_out = d.win_out; c.hist = d.hist; c.hist_win = d.hist_win; c.hist_cap = d.hist_cap;
   c.hap0 = d.hap0; c.win_flag = d.win_flag; c.win_voff = d.win_voff; c.vlist = d.vlist; c.vlist_cap = d.vlist_cap;
@@ -880,6 +881,26 @@ __global__ void __launch_bounds__(RP_WARPS * 32) k_replay(const DeviceBatch d) {
   raise(d, err);
 }
 
+// Normal mode: the same replay with the normal-mode matrix (every re-offered copy is kept, entries are
+// (read, haplotype, copies)). The normal-mode residue writes a record for every window, so this path is far from the
+// critical one; lane 0 of a warp runs the single-threaded statement of core/replay_core.h per unit.
+__global__ void __launch_bounds__(64) k_replay_normal(const DeviceBatch d) {
+  const uint32_t ti = d.rp0 + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (ti >= d.rp1 || (threadIdx.x & 31)) return;
+  MphReplayCtx c;
+  c.read_start = d.read_start; c.read_end = d.read_end; c.read_vlo = d.read_vlo; c.read_seq_off = d.read_seq_off; c.read_cig_off = d.read_cig_off;
+  c.read_lseq = d.read_lseq; c.read_ncig = d.read_ncig; c.read_nv = d.read_nv; c.read_flags = d.read_flags;
+  c.bases = d.bases; c.cigars = d.cigars; c.call_S = d.call_S; c.call_B = d.call_B;
+  c.pairs = reinterpret_cast<const uint32_t*>(d.pairs); c.n_pairs = d.n_pairs;
+  c.vars = d.vars; c.segs = d.segs; c.seg_chunk0 = d.seg_chunk0; c.stopmap = d.stopmap; c.ref = d.ref; c.dq_init = d.dq_init;
+  c.mode = 1; c.tx_id_bytes = d.tx_id_bytes; c.tx_id_off = d.tx_id_off; c.win_depth = d.win_depth; c.win_id = d.win_id; c.o_last = d.o_key;
+  c.o_read = d.o_read; c.o_hap = d.o_hap; c.o_frame = d.o_frame; c.o_flags = d.o_flags; c.o_inmat = d.o_inmat;
+  c.win_out = d.win_out; c.hist = d.hist; c.hist_win = d.hist_win; c.hist_cap = d.hist_cap;
+  c.hap0 = d.hap0; c.win_flag = d.win_flag; c.win_voff = d.win_voff; c.vlist = d.vlist; c.vlist_cap = d.vlist_cap;
+  c.seg_err = d.seg_err; c.counters = d.counters; c.sum_depth = d.sum_depth;
+  mph_replay_tx(c, d.replay[ti]);
+}
+
 // ------------------------------------------------------------------ K3
 // One thread per extra histogram key (haplotype != 0): the sequence walk of print_haplotypes
 // (:458-603) into thread-local buffers, then the stop test; the bytes are kept only for haplotypes
@@ -1108,6 +1129,7 @@ __global__ void __launch_bounds__(K2_WARPS * 32) k_window_hist_normal(const Devi
   if (lane < 2) { s_add[warp][32 + lane] = 0; s_slope[warp][32 + lane] = 0; }
   __syncwarp();
   const MphSegment& sg = s_seg[warp];
+  if (sg.flags & MPH_SF_REPLAY) return;  // the whole transcript goes through k_replay_normal
   const bool rev = (sg.flags & MPH_SF_REVERSE) != 0;
   const int n = (int)ch.n;
   const bool active = lane < n;
@@ -1310,7 +1332,16 @@ __global__ void __launch_bounds__(128) k_assemble_normal(const DeviceBatch d) {
     const uint32_t vb = mph_var_lb(d.vars, va, ch.vb1, g.e);
     const uint32_t depth = d.win_out[sg.win_base + i].depth;
     MphHap out;
-    uint32_t err = mph_nrm_assemble(sg, g, d.vars, va, vb, d.ref, d.ins_bytes, key.hap, key.count == depth, seq, cap, &out);
+    uint32_t err;
+    if (!(sg.flags & MPH_SF_REPLAY)) {
+      err = mph_nrm_assemble(sg, g, d.vars, va, vb, d.ref, d.ins_bytes, key.hap, key.count == depth, seq, cap, &out);
+    } else {
+      MphVar cols[MPH_RP_MAXCOLS];
+      const uint32_t off = d.win_voff[sg.win_base + i];
+      const uint32_t ncol = off == NONE ? 0u : min(d.vlist[off], (uint32_t)MPH_RP_MAXCOLS);
+      for (uint32_t j = 0; j < ncol; ++j) cols[j] = d.vars[d.vlist[off + 1 + j]];
+      err = mph_nrm_assemble(sg, g, cols, 0, ncol, d.ref, d.ins_bytes, key.hap, key.count == depth, seq, cap, &out);
+    }
     if (out.seq_len <= cap) {
       const uint32_t t0 = d.tx_id_off[sg.tx];
       out.id64 = mph_record_id64(seq, out.seq_len, d.tx_id_bytes + t0, d.tx_id_off[sg.tx + 1] - t0, g.s);
@@ -1435,7 +1466,8 @@ void launch_window_hist(const DeviceBatch& d, cudaStream_t st) {
   k_window_hist_wide<<<148, K2_WARPS * 32, 0, st>>>(d);
 }
 void launch_replay(const DeviceBatch& d, cudaStream_t st) {
-  if (d.rp1 > d.rp0) k_replay<<<(d.rp1 - d.rp0 + RP_WARPS - 1) / RP_WARPS, RP_WARPS * 32, 0, st>>>(d);
+  if (d.rp1 > d.rp0 && d.mode == 1) k_replay_normal<<<(d.rp1 - d.rp0 + 1) / 2, 64, 0, st>>>(d);
+  else if (d.rp1 > d.rp0) k_replay<<<(d.rp1 - d.rp0 + RP_WARPS - 1) / RP_WARPS, RP_WARPS * 32, 0, st>>>(d);
 }
 void launch_assemble(const DeviceBatch& d, cudaStream_t st) {
   if (d.c1 > d.c0 && d.mode == 1) k_assemble_normal<<<148 * 8, 128, 0, st>>>(d);

@@ -20,6 +20,56 @@ inline uint32_t partner_of(const Batch& b, uint32_t r) {
   return 0xFFFFFFFFu;
 }
 
+// serial replay of the irregular transcripts (core/replay_core.h) into per-window staging arrays
+struct ReplayStage {
+  std::vector<MphWinOut> out;
+  std::vector<MphHap> hap0;
+  std::vector<uint8_t> flag;
+  std::vector<uint32_t> voff, vlist, histwin;
+  std::vector<MphHist> hist;
+};
+
+inline void run_replay(const Batch& b, const std::vector<MphCall>& calls, int mode, PhaseRaw& raw, ReplayStage& st) {
+  if (b.replay.empty()) return;
+  const size_t nr = b.read_start.size();
+  st.out.resize(b.n_windows); st.hap0.resize(b.n_windows); st.flag.resize(b.n_windows); st.voff.assign(b.n_windows, 0xFFFFFFFFu);
+  std::vector<uint64_t> S(nr), B(nr);
+  for (size_t r = 0; r < nr; ++r) { S[r] = calls[r].S; B[r] = calls[r].B; }
+  std::vector<std::pair<uint32_t, uint32_t>> pr;
+  for (size_t i = 0; i < b.partner_a.size(); ++i) { pr.push_back({b.partner_a[i], b.partner_b[i]}); pr.push_back({b.partner_b[i], b.partner_a[i]}); }
+  std::sort(pr.begin(), pr.end());
+  std::vector<uint32_t> pairs;
+  for (auto& x : pr) { pairs.push_back(x.first); pairs.push_back(x.second); }
+  std::vector<uint32_t> o_read(b.replay_obs + 1), o_frame(b.replay_obs + 1), o_last(b.replay_obs + 1);
+  std::vector<uint64_t> o_hap(b.replay_obs + 1);
+  std::vector<uint8_t> o_flags(b.replay_obs + 1), o_inmat(b.replay_obs + 1);
+  st.hist.resize(size_t(b.n_windows) * 8 + 1024);
+  st.histwin.resize(st.hist.size());
+  st.vlist.resize(size_t(b.n_windows) * 66 + 1024);
+  uint32_t counters[8] = {0};
+  unsigned long long sum_depth = 0;
+  raw.seg_err.assign(b.segs.size(), 0);
+  if (mode == 1 && raw.win_depth.size() != b.n_windows) { raw.win_depth.assign(b.n_windows, 0); raw.win_id.assign(b.n_windows, 0); }
+  MphReplayCtx c;
+  c.seg_err = raw.seg_err.data();
+  c.read_start = b.read_start.data(); c.read_end = b.read_end.data(); c.read_vlo = b.read_vlo.data(); c.read_seq_off = b.read_seq_off.data();
+  c.read_cig_off = b.read_cig_off.data(); c.read_lseq = b.read_lseq.data(); c.read_ncig = b.read_ncig.data(); c.read_nv = b.read_nv.data();
+  c.read_flags = b.read_flags.data(); c.bases = b.bases.data(); c.cigars = b.cigars.data(); c.call_S = S.data(); c.call_B = B.data();
+  c.pairs = pairs.data(); c.n_pairs = uint32_t(pairs.size() / 2); c.vars = b.vars.data(); c.segs = b.segs.data(); c.seg_chunk0 = b.seg_chunk0.data();
+  c.stopmap = b.stopmap.data(); c.ref = b.ref.data(); c.dq_init = b.replay_dq.data();
+  c.mode = uint32_t(mode); c.tx_id_bytes = b.tx_id_bytes.data(); c.tx_id_off = b.tx_id_off.data();
+  c.win_depth = mode == 1 ? raw.win_depth.data() : nullptr;
+  c.win_id = mode == 1 ? reinterpret_cast<unsigned long long*>(raw.win_id.data()) : nullptr;
+  c.o_last = o_last.data();
+  c.o_read = o_read.data(); c.o_hap = o_hap.data(); c.o_frame = o_frame.data(); c.o_flags = o_flags.data(); c.o_inmat = o_inmat.data();
+  c.win_out = st.out.data(); c.hist = st.hist.data(); c.hist_win = st.histwin.data(); c.hist_cap = uint32_t(st.hist.size());
+  c.hap0 = st.hap0.data(); c.win_flag = st.flag.data(); c.win_voff = st.voff.data(); c.vlist = st.vlist.data(); c.vlist_cap = uint32_t(st.vlist.size());
+  c.counters = counters; c.sum_depth = &sum_depth;
+  for (const MphReplayTx& t : b.replay) mph_replay_tx(c, t);
+  raw.err |= counters[MPH_RP_CTR_ERR];
+  raw.sum_depth += sum_depth;
+}
+
 // normal mode (reference src/normal_microphasing.rs)
 inline PhaseRaw phase_normal(const Batch& b) {
   PhaseRaw raw;
@@ -33,6 +83,8 @@ inline PhaseRaw phase_normal(const Batch& b) {
   }
   raw.win_depth.assign(b.n_windows, 0);
   raw.win_id.assign(b.n_windows, 0);
+  ReplayStage rp;
+  run_replay(b, calls, 1, raw, rp);
   std::vector<uint8_t> seqbuf(b.seq_cap);
   for (const MphChunk& ch : b.chunks) {
     const MphSegment& sg = b.segs[ch.seg];
@@ -41,6 +93,41 @@ inline PhaseRaw phase_normal(const Batch& b) {
       const uint32_t k = sg.k_first + i * sg.k_stride;
       const uint32_t widx = sg.win_base + i;
       const MphGeom g = mph_geom(sg, k);
+      if (sg.flags & MPH_SF_REPLAY) {
+        // win_depth / win_id were written by the replay; windows with matrix columns also get their haplotypes assembled
+        if (!rp.flag[widx]) continue;
+        MphWinOut wo = rp.out[widx];
+        const uint32_t* list = rp.voff[widx] == 0xFFFFFFFFu ? nullptr : &rp.vlist[rp.voff[widx]];
+        const uint32_t ncol = list ? list[0] : 0;
+        std::vector<MphVar> gathered(ncol + 1);
+        for (uint32_t j = 0; j < ncol; ++j) gathered[j] = b.vars[list[1 + j]];
+        const uint32_t src = wo.extra_off;
+        wo.extra_off = uint32_t(raw.hist.size());
+        for (uint32_t x = 0; x < wo.n_extra; ++x) {
+          const MphHist e = rp.hist[src + x];
+          MphHap hx;
+          raw.err |= mph_nrm_assemble(sg, g, gathered.data(), 0, ncol, b.ref.data(), b.ins_bytes.data(), e.hap, e.count == wo.depth, seqbuf.data(), b.seq_cap, &hx);
+          if (hx.seq_len <= b.seq_cap) {
+            hx.id64 = mph_record_id64(seqbuf.data(), hx.seq_len, b.tx_id_bytes.data() + b.tx_id_off[sg.tx], b.tx_id_off[sg.tx + 1] - b.tx_id_off[sg.tx], g.s);
+            hx.flags |= MPH_NF_ID;
+          }
+          hx.seq_off = uint32_t(raw.seq.size());
+          raw.seq.resize(raw.seq.size() + b.seq_cap, 0);
+          memcpy(&raw.seq[hx.seq_off], seqbuf.data(), std::min<uint32_t>(hx.seq_len, b.seq_cap));
+          hx.flags |= MPH_NF_SEQ;
+          raw.hist.push_back(e);
+          raw.hapx.push_back(hx);
+        }
+        raw.iw.push_back(widx);
+        raw.iw_out.push_back(wo);
+        raw.iw_hap0.push_back(rp.hap0[widx]);
+        raw.iw_voff.resize(raw.iw.size(), 0xFFFFFFFFu);
+        if (list) {
+          raw.iw_voff.back() = uint32_t(raw.vlist.size());
+          raw.vlist.insert(raw.vlist.end(), list, list + 1 + ncol);
+        }
+        continue;
+      }
       const uint32_t va = mph_var_lb(b.vars.data(), sg.var_lo, sg.var_hi, g.s);
       const uint32_t vb = mph_var_lb(b.vars.data(), sg.var_lo, sg.var_hi, g.e);
       const uint32_t nv = vb - va;
@@ -100,6 +187,7 @@ inline PhaseRaw phase_normal(const Batch& b) {
       raw.iw_hap0.push_back(h0);
     }
   }
+  if (!b.replay.empty()) raw.iw_voff.resize(raw.iw.size(), 0xFFFFFFFFu);
   return raw;
 }
 
@@ -115,44 +203,12 @@ inline PhaseRaw phase_somatic(const Batch& b) {
     calls[r] = mph_call_read(rd, bases, cig, b.vars.data());
     if (b.read_flags[r] & MPH_RF_OVERFLOW) raw.err |= MPH_E_VARS_PER_WINDOW;
   }
-  // serial replay of the irregular transcripts (core/replay_core.h) into per-window staging arrays
-  std::vector<MphWinOut> rp_out(b.replay.empty() ? 0 : b.n_windows);
-  std::vector<MphHap> rp_hap0(rp_out.size());
-  std::vector<uint8_t> rp_flag(rp_out.size());
-  std::vector<uint32_t> rp_voff(rp_out.size(), 0xFFFFFFFFu), rp_vlist, rp_histwin;
-  std::vector<MphHist> rp_hist;
-  if (!b.replay.empty()) {
-    std::vector<uint64_t> S(nr), B(nr);
-    for (size_t r = 0; r < nr; ++r) { S[r] = calls[r].S; B[r] = calls[r].B; }
-    std::vector<std::pair<uint32_t, uint32_t>> pr;
-    for (size_t i = 0; i < b.partner_a.size(); ++i) { pr.push_back({b.partner_a[i], b.partner_b[i]}); pr.push_back({b.partner_b[i], b.partner_a[i]}); }
-    std::sort(pr.begin(), pr.end());
-    std::vector<uint32_t> pairs;
-    for (auto& x : pr) { pairs.push_back(x.first); pairs.push_back(x.second); }
-    std::vector<uint32_t> o_read(b.replay_obs + 1), o_frame(b.replay_obs + 1);
-    std::vector<uint64_t> o_hap(b.replay_obs + 1);
-    std::vector<uint8_t> o_flags(b.replay_obs + 1), o_inmat(b.replay_obs + 1);
-    rp_hist.resize(size_t(b.n_windows) * 8 + 1024);
-    rp_histwin.resize(rp_hist.size());
-    rp_vlist.resize(size_t(b.n_windows) * 66 + 1024);
-    uint32_t counters[8] = {0};
-    unsigned long long sum_depth = 0;
-    raw.seg_err.assign(b.segs.size(), 0);
-    MphReplayCtx c;
-    c.seg_err = raw.seg_err.data();
-    c.read_start = b.read_start.data(); c.read_end = b.read_end.data(); c.read_vlo = b.read_vlo.data(); c.read_seq_off = b.read_seq_off.data();
-    c.read_cig_off = b.read_cig_off.data(); c.read_lseq = b.read_lseq.data(); c.read_ncig = b.read_ncig.data(); c.read_nv = b.read_nv.data();
-    c.read_flags = b.read_flags.data(); c.bases = b.bases.data(); c.cigars = b.cigars.data(); c.call_S = S.data(); c.call_B = B.data();
-    c.pairs = pairs.data(); c.n_pairs = uint32_t(pairs.size() / 2); c.vars = b.vars.data(); c.segs = b.segs.data(); c.seg_chunk0 = b.seg_chunk0.data();
-    c.stopmap = b.stopmap.data(); c.ref = b.ref.data(); c.dq_init = b.replay_dq.data();
-    c.o_read = o_read.data(); c.o_hap = o_hap.data(); c.o_frame = o_frame.data(); c.o_flags = o_flags.data(); c.o_inmat = o_inmat.data();
-    c.win_out = rp_out.data(); c.hist = rp_hist.data(); c.hist_win = rp_histwin.data(); c.hist_cap = uint32_t(rp_hist.size());
-    c.hap0 = rp_hap0.data(); c.win_flag = rp_flag.data(); c.win_voff = rp_voff.data(); c.vlist = rp_vlist.data(); c.vlist_cap = uint32_t(rp_vlist.size());
-    c.counters = counters; c.sum_depth = &sum_depth;
-    for (const MphReplayTx& t : b.replay) mph_replay_tx(c, t);
-    raw.err |= counters[MPH_RP_CTR_ERR];
-    raw.sum_depth += sum_depth;
-  }
+  ReplayStage rp;
+  run_replay(b, calls, 0, raw, rp);
+  std::vector<MphWinOut>& rp_out = rp.out;
+  std::vector<MphHap>& rp_hap0 = rp.hap0;
+  std::vector<uint32_t>&rp_voff = rp.voff, &rp_vlist = rp.vlist;
+  std::vector<MphHist>& rp_hist = rp.hist;
   // K2 + K3 + K4
   std::vector<uint8_t> seqbuf(b.seq_cap), germbuf(b.seq_cap);
   for (const MphChunk& ch : b.chunks) {
