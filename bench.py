@@ -268,9 +268,11 @@ def main():
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     n_reads, n_win, n_seg, n_chunk = view.n_reads, view.n_windows, view.n_segments, view.n_chunks
-    n_special = view.bases_bytes / 96.0  # reads that ship bases (overlap a variant)
+    n_special = float(view.n_variant_reads)  # side-table entries: reads that overlap a variant
     alg = {
-        "k1_ms": n_reads * (26 + 17) + n_special * 64 + view.n_vars * 16,
+        # zero-fill of S / B / flag / nv for every read, then per side-table entry: entry in (21 B), start / end (8 B), one base
+        # sector + one quality sector (64 B), S / B / flag / vlo / nv / index out (26 B)
+        "k1_ms": n_reads * 18 + n_special * (21 + 8 + 64 + 26) + view.n_vars * 16,
         "k2_ms": n_reads * 9 + n_special * 20 + n_win * 16 + t_res["d2h_bytes"] * 0.3 + n_seg * 96 + n_chunk * 32,
         "k3_ms": n_win * (16 + 32 + 1) + view.ref_bytes + n_seg * 96 + n_chunk * 32,
         "k4_ms": n_win * 2 + t_res["n_interesting"] * (4 + 2 * 48),

@@ -108,16 +108,20 @@ void mph_batch_destroy(mph_batch* b);
 typedef struct {
   uint32_t window_len;
   uint64_t n_reads, n_vars, n_segments, n_chunks, n_windows, n_transcripts, n_genes;
-  const uint32_t* read_start;
+  const uint32_t* read_start;   /* per read, sorted by start within a gene */
   const uint32_t* read_end;
-  const uint32_t* read_vlo;
-  const uint32_t* read_seq_off;
-  const uint32_t* read_cig_off;
-  const uint16_t* read_lseq;
-  const uint16_t* read_ncig;
-  const uint8_t* read_nv;
   const uint8_t* read_flags;
-  const uint8_t* bases;   uint64_t bases_bytes;   /* 4-bit bases + (qual < 10) bitmask per read with variants */
+  /* compact side table: one entry per read that overlaps a variant (every read of a gene whose transcripts need the
+   * serial replay): read index, first variant index, offset of its packed bases (16-B units) / CIGAR, lengths */
+  uint64_t n_variant_reads;
+  const uint32_t* vr_read;
+  const uint32_t* vr_vlo;
+  const uint32_t* vr_seq_off;
+  const uint32_t* vr_cig_off;
+  const uint16_t* vr_lseq;
+  const uint16_t* vr_ncig;
+  const uint8_t* vr_nv;
+  const uint8_t* bases;   uint64_t bases_bytes;   /* 4-bit bases + (qual < 10) bitmask per side-table entry */
   const uint32_t* cigars; uint64_t n_cigar_ops;
   const void* vars;       /* MphVar[n_vars], 16 B each (csrc/core/layout.h) */
   const void* segments;   /* MphSegment[n_segments], 96 B each */

@@ -46,7 +46,8 @@ class Record(C.Structure):
 
 class BatchView(C.Structure):
     _fields_ = [("window_len", C.c_uint32)] + [(n, C.c_uint64) for n in ("n_reads", "n_vars", "n_segments", "n_chunks", "n_windows", "n_transcripts", "n_genes")] + \
-               [(n, C.c_void_p) for n in ("read_start", "read_end", "read_vlo", "read_seq_off", "read_cig_off", "read_lseq", "read_ncig", "read_nv", "read_flags")] + \
+               [(n, C.c_void_p) for n in ("read_start", "read_end", "read_flags")] + [("n_variant_reads", C.c_uint64)] + \
+               [(n, C.c_void_p) for n in ("vr_read", "vr_vlo", "vr_seq_off", "vr_cig_off", "vr_lseq", "vr_ncig", "vr_nv")] + \
                [("bases", C.c_void_p), ("bases_bytes", C.c_uint64), ("cigars", C.c_void_p), ("n_cigar_ops", C.c_uint64), ("vars", C.c_void_p),
                 ("segments", C.c_void_p), ("chunks", C.c_void_p), ("ref", C.c_void_p), ("ref_bytes", C.c_uint64), ("h2d_bytes", C.c_uint64)]
 

@@ -102,10 +102,10 @@ struct mph_ctx {
   std::string last_error;
   const mph_batch* cur = nullptr;
   mphk::DeviceBatch d;
-  DevBuf<uint32_t> read_start, read_end, read_vlo, read_seq_off, read_cig_off, cigars, block_counts, iw, counters, seg_live, ovf_list, stopmap, hist_win, win_depth, seg_chunk0, dq_init, seg_err, tx_id_off, o_read, o_key, o_frame, win_voff, vlist, iw_voff;
-  DevBuf<uint16_t> read_lseq, read_ncig;
+  DevBuf<uint32_t> read_start, read_end, read_vlo, read_vr, vr_read, vr_vlo, vr_seq_off, vr_cig_off, cigars, block_counts, iw, counters, seg_live, ovf_list, stopmap, hist_win, win_depth, seg_chunk0, dq_init, seg_err, tx_id_off, o_read, o_key, o_frame, win_voff, vlist, iw_voff;
+  DevBuf<uint16_t> vr_lseq, vr_ncig;
   DevBuf<uint8_t> tx_id_bytes;
-  DevBuf<uint8_t> read_nv, read_flags, bases, ins_bytes, ref, call_flags, seq, win_flag, o_flags, o_inmat;
+  DevBuf<uint8_t> read_nv, vr_nv, read_flags, bases, ins_bytes, ref, call_flags, seq, win_flag, o_flags, o_inmat;
   DevBuf<MphReplayTx> replay;
   DevBuf<uint64_t> o_hap;
   DevBuf<uint2> pairs;
@@ -162,8 +162,8 @@ void finish_batch(mph_batch* mb, bool pin) {
   }
   std::sort(mb->pairs.begin(), mb->pairs.end(), [](const uint2& a, const uint2& c) { return a.x < c.x; });
   auto bytes = [](auto& v) { return v.size() * sizeof(v[0]); };
-  mb->h2d_bytes = bytes(b.read_start) + bytes(b.read_end) + bytes(b.read_vlo) + bytes(b.read_seq_off) + bytes(b.read_cig_off) +
-                  bytes(b.read_lseq) + bytes(b.read_ncig) + bytes(b.read_nv) + bytes(b.read_flags) + bytes(b.bases) + bytes(b.cigars) +
+  mb->h2d_bytes = bytes(b.read_start) + bytes(b.read_end) + bytes(b.read_flags) + bytes(b.vr_read) + bytes(b.vr_vlo) + bytes(b.vr_seq_off) +
+                  bytes(b.vr_cig_off) + bytes(b.vr_lseq) + bytes(b.vr_ncig) + bytes(b.vr_nv) + bytes(b.bases) + bytes(b.cigars) +
                   bytes(b.vars) + bytes(b.ins_bytes) + bytes(b.segs) + bytes(b.chunks) + bytes(b.ref) + bytes(b.stopmap) + bytes(mb->pairs) +
                   bytes(b.tx_id_bytes) + bytes(b.tx_id_off) + bytes(b.replay) + bytes(b.replay_dq) + (b.replay.empty() ? 0 : bytes(b.seg_chunk0));
   if (pin) {
@@ -174,8 +174,8 @@ void finish_batch(mph_batch* mb, bool pin) {
       else
         cudaGetLastError();
     };
-    reg(b.read_start); reg(b.read_end); reg(b.read_vlo); reg(b.read_seq_off); reg(b.read_cig_off); reg(b.read_lseq); reg(b.read_ncig);
-    reg(b.read_nv); reg(b.read_flags); reg(b.bases); reg(b.cigars); reg(b.vars); reg(b.ins_bytes); reg(b.segs); reg(b.chunks); reg(b.ref); reg(b.stopmap);
+    reg(b.read_start); reg(b.read_end); reg(b.read_flags); reg(b.vr_read); reg(b.vr_vlo); reg(b.vr_seq_off); reg(b.vr_cig_off); reg(b.vr_lseq);
+    reg(b.vr_ncig); reg(b.vr_nv); reg(b.bases); reg(b.cigars); reg(b.vars); reg(b.ins_bytes); reg(b.segs); reg(b.chunks); reg(b.ref); reg(b.stopmap);
     reg(mb->pairs);
     reg(b.tx_id_bytes); reg(b.tx_id_off); reg(b.replay); reg(b.replay_dq); reg(b.seg_chunk0);
     mb->pinned = true;
@@ -228,8 +228,11 @@ void prepare(mph_ctx* c, const mph_batch* mb) {
   if (b.n_windows > 0xFFFFFF00ull || b.n_reads() > 0xFFFFFF00ull) throw Unsupported("batch too large: split it into gene ranges");
   if (b.chunks.size() >= (1u << 27)) throw Unsupported("batch too large: split it into gene ranges");
   const size_t nr = b.n_reads(), nw = size_t(b.n_windows);
-  c->read_start.ensure(nr + 1); c->read_end.ensure(nr + 1); c->read_vlo.ensure(nr + 1); c->read_seq_off.ensure(nr + 1); c->read_cig_off.ensure(nr + 1);
-  c->read_lseq.ensure(nr + 1); c->read_ncig.ensure(nr + 1); c->read_nv.ensure(nr + 1); c->read_flags.ensure(nr + 1);
+  const size_t nvr = b.vr_read.size();
+  c->read_start.ensure(nr + 1); c->read_end.ensure(nr + 1); c->read_flags.ensure(nr + 1);
+  c->read_vlo.ensure(nr + 1); c->read_nv.ensure(nr + 1); c->read_vr.ensure(nr + 1);  // expanded on the device by K1
+  c->vr_read.ensure(nvr + 1); c->vr_vlo.ensure(nvr + 1); c->vr_seq_off.ensure(nvr + 1); c->vr_cig_off.ensure(nvr + 1);
+  c->vr_lseq.ensure(nvr + 1); c->vr_ncig.ensure(nvr + 1); c->vr_nv.ensure(nvr + 1);
   c->bases.ensure(b.bases.size() + 1); c->cigars.ensure(b.cigars.size() + 1); c->vars.ensure(b.vars.size() + 1); c->ins_bytes.ensure(b.ins_bytes.size() + 1);
   c->segs.ensure(b.segs.size() + 1); c->chunks.ensure(b.chunks.size() + 1); c->ref.ensure(b.ref.size() + 1); c->stopmap.ensure(b.stopmap.size() + 1);
   c->pairs.ensure(mb->pairs.size() + 1); c->tx_id_bytes.ensure(b.tx_id_bytes.size() + 1); c->tx_id_off.ensure(b.tx_id_off.size() + 1);
@@ -246,9 +249,11 @@ void prepare(mph_ctx* c, const mph_batch* mb) {
   mphk::DeviceBatch& d = c->d;
   d.n_reads = uint32_t(nr); d.n_vars = uint32_t(b.vars.size()); d.n_segs = uint32_t(b.segs.size()); d.n_chunks = uint32_t(b.chunks.size());
   d.n_windows = uint32_t(nw); d.seq_cap = b.seq_cap;
-  d.read_start = c->read_start.p; d.read_end = c->read_end.p; d.read_vlo = c->read_vlo.p; d.read_seq_off = c->read_seq_off.p;
-  d.read_cig_off = c->read_cig_off.p; d.read_lseq = c->read_lseq.p; d.read_ncig = c->read_ncig.p; d.read_nv = c->read_nv.p;
-  d.read_flags = c->read_flags.p; d.bases = c->bases.p; d.cigars = c->cigars.p; d.vars = c->vars.p;
+  d.read_start = c->read_start.p; d.read_end = c->read_end.p; d.read_flags = c->read_flags.p;
+  d.read_vlo = c->read_vlo.p; d.read_nv = c->read_nv.p; d.read_vr = c->read_vr.p;
+  d.vr_read = c->vr_read.p; d.vr_vlo = c->vr_vlo.p; d.vr_seq_off = c->vr_seq_off.p; d.vr_cig_off = c->vr_cig_off.p;
+  d.vr_lseq = c->vr_lseq.p; d.vr_ncig = c->vr_ncig.p; d.vr_nv = c->vr_nv.p;
+  d.bases = c->bases.p; d.cigars = c->cigars.p; d.vars = c->vars.p;
   d.ins_bytes = c->ins_bytes.p; d.segs = c->segs.p; d.chunks = c->chunks.p; d.ref = c->ref.p; d.stopmap = c->stopmap.p;
   d.call_S = reinterpret_cast<uint64_t*>(c->call_S.p); d.call_B = reinterpret_cast<uint64_t*>(c->call_B.p); d.call_flags = c->call_flags.p;
   d.win_out = c->win_out.p; d.hap0 = c->hap0.p; d.win_flag = c->win_flag.p; d.block_counts = c->block_counts.p;
@@ -285,10 +290,11 @@ void h2d_range(cudaStream_t st, DevBuf<T>& dst, const V& src, size_t lo, size_t 
 void copy_stage(mph_ctx* c, const mph_batch* mb, const Stage& s, bool first, cudaStream_t st) {
   const Batch& b = mb->b;
   const size_t r0 = s.lo.reads, r1 = s.hi.reads;
-  h2d_range(st, c->read_start, b.read_start, r0, r1); h2d_range(st, c->read_end, b.read_end, r0, r1); h2d_range(st, c->read_vlo, b.read_vlo, r0, r1);
-  h2d_range(st, c->read_seq_off, b.read_seq_off, r0, r1); h2d_range(st, c->read_cig_off, b.read_cig_off, r0, r1);
-  h2d_range(st, c->read_lseq, b.read_lseq, r0, r1); h2d_range(st, c->read_ncig, b.read_ncig, r0, r1); h2d_range(st, c->read_nv, b.read_nv, r0, r1);
-  h2d_range(st, c->read_flags, b.read_flags, r0, r1);
+  h2d_range(st, c->read_start, b.read_start, r0, r1); h2d_range(st, c->read_end, b.read_end, r0, r1); h2d_range(st, c->read_flags, b.read_flags, r0, r1);
+  const size_t e0 = s.lo.vr, e1 = s.hi.vr;
+  h2d_range(st, c->vr_read, b.vr_read, e0, e1); h2d_range(st, c->vr_vlo, b.vr_vlo, e0, e1); h2d_range(st, c->vr_seq_off, b.vr_seq_off, e0, e1);
+  h2d_range(st, c->vr_cig_off, b.vr_cig_off, e0, e1); h2d_range(st, c->vr_lseq, b.vr_lseq, e0, e1); h2d_range(st, c->vr_ncig, b.vr_ncig, e0, e1);
+  h2d_range(st, c->vr_nv, b.vr_nv, e0, e1);
   h2d_range(st, c->bases, b.bases, s.lo.bases, s.hi.bases); h2d_range(st, c->cigars, b.cigars, s.lo.cigars, s.hi.cigars);
   h2d_range(st, c->vars, b.vars, s.lo.vars, s.hi.vars); h2d_range(st, c->ins_bytes, b.ins_bytes, s.lo.ins, s.hi.ins);
   h2d_range(st, c->segs, b.segs, s.lo.segs, s.hi.segs); h2d_range(st, c->chunks, b.chunks, s.lo.chunks, s.hi.chunks);
@@ -305,6 +311,7 @@ void copy_stage(mph_ctx* c, const mph_batch* mb, const Stage& s, bool first, cud
 void set_ranges(mph_ctx* c, const Stage& s) {
   mphk::DeviceBatch& d = c->d;
   d.r0 = uint32_t(s.lo.reads); d.r1 = uint32_t(s.hi.reads);
+  d.vr0 = uint32_t(s.lo.vr); d.vr1 = uint32_t(s.hi.vr);
   d.c0 = uint32_t(s.lo.chunks); d.c1 = uint32_t(s.hi.chunks);
   d.w0 = uint32_t(s.lo.windows); d.w1 = uint32_t(s.hi.windows);
   d.rp0 = uint32_t(s.lo.replay); d.rp1 = uint32_t(s.hi.replay);
@@ -320,6 +327,15 @@ void run_kernels(mph_ctx* c) {
   d.hist = c->hist.p; d.hapx = c->hapx.p; d.hist_win = c->hist_win.p; d.hist_cap = uint32_t(std::min<size_t>(c->hist.cap, 0xFFFFFFF0u));
   d.seq = c->seq.p; d.seq_cap_bytes = uint32_t(std::min<size_t>(c->seq.cap, 0xFFFFFF00u));
   CU(cudaMemsetAsync(c->counters.p, 0, 8 * sizeof(uint32_t), c->stream));
+  CU(cudaEventRecord(c->ev[2], c->stream));  // k1_ms covers the zero-fill below: it is the allele call of the reads without variants
+  if (d.r1 > d.r0) {
+    // reads without an entry in the side table: no allele call, no bad base, no variant inside
+    const size_t n = size_t(d.r1 - d.r0);
+    CU(cudaMemsetAsync(c->call_S.p + d.r0, 0, n * 8, c->stream));
+    CU(cudaMemsetAsync(c->call_B.p + d.r0, 0, n * 8, c->stream));
+    CU(cudaMemsetAsync(c->call_flags.p + d.r0, 0, n, c->stream));
+    CU(cudaMemsetAsync(c->read_nv.p + d.r0, 0, n, c->stream));
+  }
   if (d.rp1 > d.rp0) {
     d.vlist = c->vlist.p; d.vlist_cap = uint32_t(std::min<size_t>(c->vlist.cap, 0xFFFFFF00u));
     CU(cudaMemsetAsync(c->win_voff.p + d.w0, 0xFF, size_t(d.w1 - d.w0) * sizeof(uint32_t), c->stream));
@@ -328,11 +344,11 @@ void run_kernels(mph_ctx* c) {
   } else if (d.n_replay) {
     CU(cudaMemsetAsync(c->win_voff.p + d.w0, 0xFF, size_t(d.w1 - d.w0) * sizeof(uint32_t), c->stream));
   }
-  CU(cudaEventRecord(c->ev[2], c->stream));
   mphk::launch_allele_call(d, c->stream);
   CU(cudaEventRecord(c->ev[3], c->stream));
-  // measured on B200: the replay warps are latency-bound; sharing the SMs with the closed-form kernel (second stream,
-  // either priority) slows both by more than the overlap gains, so the two kernels run back to back
+  // measured on B200: on a second stream (any priority, with or without a dispatch head start) the replay and the
+  // closed-form kernel still take the sum of their times - the replay's shared-memory footprint keeps the window
+  // kernel's CTAs off the SMs it occupies - so the two kernels simply run back to back
   mphk::launch_replay(d, c->stream);
   CU(cudaEventRecord(c->ev[8], c->stream));
   mphk::launch_window_hist(d, c->stream);
@@ -793,12 +809,6 @@ void mph_ctx_destroy(mph_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
-  c->read_start.release(); c->read_end.release(); c->read_vlo.release(); c->read_seq_off.release(); c->read_cig_off.release();
-  c->cigars.release(); c->block_counts.release(); c->iw.release(); c->counters.release(); c->seg_live.release(); c->read_lseq.release();
-  c->read_ncig.release(); c->read_nv.release(); c->read_flags.release(); c->bases.release(); c->ins_bytes.release(); c->ref.release();
-  c->ovf_list.release(); c->stopmap.release(); c->hist_win.release(); c->set_table.release(); c->call_flags.release(); c->seq.release(); c->win_flag.release(); c->pairs.release(); c->vars.release(); c->segs.release();
-  c->chunks.release(); c->call_S.release(); c->call_B.release(); c->win_out.release(); c->iw_out.release(); c->hist.release();
-  c->hap0.release(); c->hapx.release(); c->iw_hap0.release(); c->sums.release();
   for (auto& e : c->ev)
     if (e) cudaEventDestroy(e);
   for (auto& e : c->ev_copy)
@@ -890,9 +900,10 @@ int mph_batch_get_view(const mph_batch* mb, mph_batch_view* v) {
   v->window_len = b.window_len;
   v->n_reads = b.n_reads(); v->n_vars = b.vars.size(); v->n_segments = b.segs.size(); v->n_chunks = b.chunks.size();
   v->n_windows = b.n_windows; v->n_transcripts = b.txs.size(); v->n_genes = b.genes.size();
-  v->read_start = b.read_start.data(); v->read_end = b.read_end.data(); v->read_vlo = b.read_vlo.data();
-  v->read_seq_off = b.read_seq_off.data(); v->read_cig_off = b.read_cig_off.data(); v->read_lseq = b.read_lseq.data();
-  v->read_ncig = b.read_ncig.data(); v->read_nv = b.read_nv.data(); v->read_flags = b.read_flags.data();
+  v->read_start = b.read_start.data(); v->read_end = b.read_end.data(); v->read_flags = b.read_flags.data();
+  v->n_variant_reads = b.vr_read.size();
+  v->vr_read = b.vr_read.data(); v->vr_vlo = b.vr_vlo.data(); v->vr_seq_off = b.vr_seq_off.data(); v->vr_cig_off = b.vr_cig_off.data();
+  v->vr_lseq = b.vr_lseq.data(); v->vr_ncig = b.vr_ncig.data(); v->vr_nv = b.vr_nv.data();
   v->bases = b.bases.data(); v->bases_bytes = b.bases.size(); v->cigars = b.cigars.data(); v->n_cigar_ops = b.cigars.size();
   v->vars = b.vars.data(); v->segments = b.segs.data(); v->chunks = b.chunks.data(); v->ref = b.ref.data(); v->ref_bytes = b.ref.size();
   v->h2d_bytes = mb->h2d_bytes;

@@ -35,8 +35,9 @@ typedef struct {
 
 typedef struct {
   // inputs (same arrays as the closed-form kernels)
-  const uint32_t* read_start; const uint32_t* read_end; const uint32_t* read_vlo; const uint32_t* read_seq_off; const uint32_t* read_cig_off;
-  const uint16_t* read_lseq; const uint16_t* read_ncig; const uint8_t* read_nv; const uint8_t* read_flags;
+  const uint32_t* read_start; const uint32_t* read_end; const uint8_t* read_flags;
+  const uint32_t* read_vlo; const uint8_t* read_nv; const uint32_t* read_vr;  // per read, expanded by K1 from the compact side table (read_vr = its entry)
+  const uint32_t* vr_seq_off; const uint32_t* vr_cig_off; const uint16_t* vr_lseq; const uint16_t* vr_ncig;
   const uint8_t* bases; const uint32_t* cigars;
   const uint64_t* call_S; const uint64_t* call_B;
   const uint32_t* pairs; uint32_t n_pairs;  // (read, partner) interleaved, sorted by read
@@ -83,15 +84,17 @@ MPH_HD void mph_rp_eval(const MphReplayCtx& c, uint32_t r, uint32_t v, bool* sup
     return;
   }
   const MphVar var = c.vars[v];
-  const uint32_t start = c.read_start[r], l_seq = c.read_lseq[r];
+  const uint32_t start = c.read_start[r];
   *sup = false;
   *bad = false;
   if (start > var.pos) { *err |= MPH_E_REPLAY_PANIC; return; }  // "bug: read starts right of variant" (:160-167)
-  const uint32_t soff = c.read_seq_off[r];
-  const uint32_t ncig = c.read_ncig[r];
-  const uint32_t* cig = c.cigars + c.read_cig_off[r];
+  // every read of a gene with replayed transcripts has an entry in the side table
+  const uint32_t e = c.read_vr[r];
+  const uint32_t l_seq = c.vr_lseq[e];
+  const uint32_t soff = c.vr_seq_off[e];
+  const uint32_t ncig = c.vr_ncig[e];
+  const uint32_t* cig = c.cigars + c.vr_cig_off[e];
   if (var.kind == MPH_SNV) {
-    if (soff == 0xFFFFFFFFu) { *err |= MPH_E_REPLAY_INPUT; return; }
     const uint8_t* b = c.bases + (size_t)soff * 16;
     const uint8_t* lowq = b + ((l_seq + 1u) >> 1);
     const uint32_t rel = var.pos - start;

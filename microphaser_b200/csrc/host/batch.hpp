@@ -77,7 +77,7 @@ struct GeneMeta {
 
 // sizes of every per-gene-contiguous array after a gene has been packed: a batch can be cut at any gene boundary
 struct GeneMark {
-  uint64_t reads = 0, bases = 0, cigars = 0, vars = 0, ins = 0, segs = 0, chunks = 0, ref = 0, windows = 0, txs = 0, replay = 0, dq = 0, partners = 0;
+  uint64_t reads = 0, vr = 0, bases = 0, cigars = 0, vars = 0, ins = 0, segs = 0, chunks = 0, ref = 0, windows = 0, txs = 0, replay = 0, dq = 0, partners = 0;
 };
 
 struct Batch {
@@ -85,9 +85,13 @@ struct Batch {
   std::vector<GeneMark> marks{GeneMark{}};  // marks[g + 1]: sizes after gene g
   int mode = 0;  // 0 somatic (src/microphasing.rs), 1 normal (src/normal_microphasing.rs)
   // reads (SoA)
-  std::vector<uint32_t> read_start, read_end, read_vlo, read_seq_off, read_cig_off;
-  std::vector<uint16_t> read_lseq, read_ncig;
-  std::vector<uint8_t> read_nv, read_flags;
+  std::vector<uint32_t> read_start, read_end;
+  std::vector<uint8_t> read_flags;
+  // compact side table of the reads K1 has work for (variants inside the alignment; every read of a gene with replayed
+  // transcripts): read index, first variant index, offsets of the packed bases / CIGAR, lengths, variant count
+  std::vector<uint32_t> vr_read, vr_vlo, vr_seq_off, vr_cig_off;
+  std::vector<uint16_t> vr_lseq, vr_ncig;
+  std::vector<uint8_t> vr_nv;
   std::vector<uint32_t> partner_a, partner_b;  // sorted pairs (a < b) of reads with identical (start, qname)
   std::vector<uint8_t> bases;                  // 16-B aligned packed records: 4-bit bases + (qual<10) bits
   std::vector<uint32_t> cigars;
@@ -186,7 +190,32 @@ class Packer {
     gm.read_lo = uint32_t(b_.read_start.size());
     uint32_t vcur = gm.var_lo, max_span = 0;
     std::unordered_map<uint64_t, uint32_t> seen;  // (start, qname) -> first read index
-    const size_t bases_mark = b_.bases.size(), cigars_mark = b_.cigars.size();
+    const size_t bases_mark = b_.bases.size(), cigars_mark = b_.cigars.size(), vr_mark = b_.vr_read.size();
+    auto add_vr = [&](uint32_t idx, uint32_t vlo, uint32_t nv, const HostRead& r) {
+      // packed record: 4-bit bases then (qual < 10) bits, 16-B aligned
+      const size_t off = (b_.bases.size() + 15u) & ~size_t(15);
+      const size_t nb = (r.l_seq + 1u) / 2, nq = (r.l_seq + 7u) / 8;
+      b_.bases.resize(off + nb + nq, 0);
+      memcpy(&b_.bases[off], r.seq4, nb);
+      for (uint32_t i = 0; i < r.l_seq; ++i)
+        if (r.qual[i] < 10) b_.bases[off + nb + (i >> 3)] |= uint8_t(1u << (i & 7));
+      b_.vr_read.push_back(idx);
+      b_.vr_vlo.push_back(vlo);
+      b_.vr_seq_off.push_back(uint32_t(off / 16));
+      b_.vr_lseq.push_back(uint16_t(r.l_seq));
+      b_.vr_nv.push_back(uint8_t(nv));
+      const bool single_m = r.n_cigar == 1 && (r.cigar[0] & 15u) == 0 && (r.cigar[0] >> 4) == r.l_seq;
+      if (!single_m) {
+        b_.vr_cig_off.push_back(uint32_t(b_.cigars.size()));
+        b_.vr_ncig.push_back(uint16_t(r.n_cigar));
+        b_.cigars.insert(b_.cigars.end(), r.cigar, r.cigar + r.n_cigar);
+      } else {
+        b_.vr_cig_off.push_back(0);
+        b_.vr_ncig.push_back(0);
+      }
+    };
+    std::vector<std::pair<uint32_t, uint32_t>> read_vrange;  // (vlo, nv) of every read of this gene, for the re-pack of replay genes
+    read_vrange.reserve(reads.size());
     for (auto& r : reads) {
       const uint32_t idx = uint32_t(b_.read_start.size());
       while (vcur < gm.var_hi && b_.vars[vcur].pos < r.start) ++vcur;
@@ -195,35 +224,11 @@ class Packer {
       uint32_t nv = ve - vcur;
       uint8_t flags = 0;
       if (nv > 64) { nv = 64; flags |= MPH_RF_OVERFLOW; }
-      const bool single_m = r.n_cigar == 1 && (r.cigar[0] & 15u) == 0 && (r.cigar[0] >> 4) == r.l_seq;
+      read_vrange.emplace_back(vcur, nv);
       b_.read_start.push_back(r.start);
       b_.read_end.push_back(r.end);
-      b_.read_vlo.push_back(vcur);
-      b_.read_lseq.push_back(uint16_t(r.l_seq));
-      b_.read_nv.push_back(uint8_t(nv));
       if (r.l_seq > 0xFFFF) throw Unsupported("read longer than 65535 bases");
-      if (nv > 0) {
-        // packed record: 4-bit bases then (qual < 10) bits, 16-B aligned
-        const size_t off = (b_.bases.size() + 15u) & ~size_t(15);
-        const size_t nb = (r.l_seq + 1u) / 2, nq = (r.l_seq + 7u) / 8;
-        b_.bases.resize(off + nb + nq, 0);
-        memcpy(&b_.bases[off], r.seq4, nb);
-        for (uint32_t i = 0; i < r.l_seq; ++i)
-          if (r.qual[i] < 10) b_.bases[off + nb + (i >> 3)] |= uint8_t(1u << (i & 7));
-        b_.read_seq_off.push_back(uint32_t(off / 16));
-        if (!single_m) {
-          b_.read_cig_off.push_back(uint32_t(b_.cigars.size()));
-          b_.read_ncig.push_back(uint16_t(r.n_cigar));
-          b_.cigars.insert(b_.cigars.end(), r.cigar, r.cigar + r.n_cigar);
-        } else {
-          b_.read_cig_off.push_back(0);
-          b_.read_ncig.push_back(0);
-        }
-      } else {
-        b_.read_seq_off.push_back(0xFFFFFFFFu);
-        b_.read_cig_off.push_back(0);
-        b_.read_ncig.push_back(0);
-      }
+      if (nv > 0) add_vr(idx, vcur, nv, r);
       if (strand == 1 && b_.mode == 0) {  // `contains` only bites on the reverse strand (keys are read starts, :328-331); normal mode has none
         const uint64_t key = r.qname_hash * 0x9E3779B97F4A7C15ull ^ (uint64_t(r.start) << 1);
         auto it = seen.find(key);
@@ -460,30 +465,19 @@ class Packer {
       // the replay evaluates matrix columns outside a read's own variant range: every read of the gene ships its bases and CIGAR
       b_.bases.resize(bases_mark);
       b_.cigars.resize(cigars_mark);
+      b_.vr_read.resize(vr_mark); b_.vr_vlo.resize(vr_mark); b_.vr_seq_off.resize(vr_mark); b_.vr_cig_off.resize(vr_mark);
+      b_.vr_lseq.resize(vr_mark); b_.vr_ncig.resize(vr_mark); b_.vr_nv.resize(vr_mark);
       uint32_t idx = gm.read_lo;
+      size_t q = 0;
       for (auto& r : reads) {
-        const size_t off = (b_.bases.size() + 15u) & ~size_t(15);
-        const size_t nb = (r.l_seq + 1u) / 2, nq = (r.l_seq + 7u) / 8;
-        b_.bases.resize(off + nb + nq, 0);
-        memcpy(&b_.bases[off], r.seq4, nb);
-        for (uint32_t i = 0; i < r.l_seq; ++i)
-          if (r.qual[i] < 10) b_.bases[off + nb + (i >> 3)] |= uint8_t(1u << (i & 7));
-        b_.read_seq_off[idx] = uint32_t(off / 16);
-        const bool single_m = r.n_cigar == 1 && (r.cigar[0] & 15u) == 0 && (r.cigar[0] >> 4) == r.l_seq;
-        if (!single_m) {
-          b_.read_cig_off[idx] = uint32_t(b_.cigars.size());
-          b_.read_ncig[idx] = uint16_t(r.n_cigar);
-          b_.cigars.insert(b_.cigars.end(), r.cigar, r.cigar + r.n_cigar);
-        } else {
-          b_.read_cig_off[idx] = 0;
-          b_.read_ncig[idx] = 0;
-        }
+        add_vr(idx, read_vrange[q].first, read_vrange[q].second, r);
         ++idx;
+        ++q;
       }
     }
     b_.genes.push_back(std::move(gm));
     GeneMark mk;
-    mk.reads = b_.read_start.size(); mk.bases = b_.bases.size(); mk.cigars = b_.cigars.size(); mk.vars = b_.vars.size(); mk.ins = b_.ins_bytes.size();
+    mk.reads = b_.read_start.size(); mk.vr = b_.vr_read.size(); mk.bases = b_.bases.size(); mk.cigars = b_.cigars.size(); mk.vars = b_.vars.size(); mk.ins = b_.ins_bytes.size();
     mk.segs = b_.segs.size(); mk.chunks = b_.chunks.size(); mk.ref = b_.ref.size(); mk.windows = b_.n_windows; mk.txs = b_.txs.size();
     mk.replay = b_.replay.size(); mk.dq = b_.replay_dq.size(); mk.partners = b_.partner_a.size();
     b_.marks.push_back(mk);

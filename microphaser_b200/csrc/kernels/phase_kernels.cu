@@ -38,29 +38,26 @@ __device__ __forceinline__ void raise(const DeviceBatch& d, uint32_t bits) {
 
 // ------------------------------------------------------------------ K1
 __global__ void __launch_bounds__(256) k_allele_call(const DeviceBatch d) {
-  const uint32_t r = d.r0 + blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= d.r1) return;
-  const uint32_t nv = d.read_nv[r];
-  const uint32_t hf = d.read_flags[r];
-  MphCall c;
-  c.S = 0;
-  c.B = 0;
-  if (nv) {
-    MphRead rd;
-    rd.start = d.read_start[r];
-    rd.end = d.read_end[r];
-    rd.vlo = d.read_vlo[r];
-    rd.l_seq = d.read_lseq[r];
-    rd.nv = nv;
-    rd.n_cig = d.read_ncig[r];
-    const uint8_t* bases = d.bases + (size_t)d.read_seq_off[r] * 16;
-    const uint32_t* cig = d.cigars + d.read_cig_off[r];
-    c = mph_call_read(rd, bases, cig, d.vars, d.mode == 0);
-  }
+  const uint32_t e = d.vr0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= d.vr1) return;
+  const uint32_t r = d.vr_read[e];
+  MphRead rd;
+  rd.start = d.read_start[r];
+  rd.end = d.read_end[r];
+  rd.vlo = d.vr_vlo[e];
+  rd.l_seq = d.vr_lseq[e];
+  rd.nv = d.vr_nv[e];
+  rd.n_cig = d.vr_ncig[e];
+  const uint8_t* bases = d.bases + (size_t)d.vr_seq_off[e] * 16;
+  const uint32_t* cig = d.cigars + d.vr_cig_off[e];
+  const MphCall c = mph_call_read(rd, bases, cig, d.vars, d.mode == 0);
   d.call_S[r] = c.S;
   d.call_B[r] = c.B;
-  d.call_flags[r] = (uint8_t)((((c.S | c.B) != 0) ? 1u : 0u) | ((hf & MPH_RF_PARTNER) ? 2u : 0u));
-  if (hf & MPH_RF_OVERFLOW) raise(d, MPH_E_VARS_PER_WINDOW);
+  d.call_flags[r] = (uint8_t)(((c.S | c.B) != 0) ? 1u : 0u);  // bit0: the read needs the full pair evaluation
+  d.read_vlo[r] = rd.vlo;
+  d.read_nv[r] = (uint8_t)rd.nv;
+  d.read_vr[r] = e;
+  if (d.read_flags[r] & MPH_RF_OVERFLOW) raise(d, MPH_E_VARS_PER_WINDOW);
 }
 
 // ------------------------------------------------------------------ K2
@@ -126,7 +123,8 @@ __device__ void window_hist_warp(const DeviceBatch& d, const MphSegment& sg, uin
     if (r < rhi) {
       const uint32_t st = d.read_start[r], en = d.read_end[r];
       if (en >= g.e) {
-        const MphPair p = eval_flagged(d, sg, rev, k, g, va, vb, r, st, en, d.call_flags[r], d.read_vlo[r], d.call_S[r], d.call_B[r]);
+        const uint32_t cf = d.call_flags[r] | ((d.read_flags[r] & MPH_RF_PARTNER) ? 2u : 0u);
+        const MphPair p = eval_flagged(d, sg, rev, k, g, va, vb, r, st, en, cf, d.read_vlo[r], d.call_S[r], d.call_B[r]);
         member = p.member != 0;
         counted = member && !p.bad;
         hap = p.hap;
@@ -301,7 +299,8 @@ __global__ void __launch_bounds__(K2_WARPS * 32) k_window_hist(const DeviceBatch
           add_key(hap, 0);
         }
       } else if (en >= my_e && st <= my_s) {
-        const MphPair p = eval_flagged(d, sg, rev, k, g, va, vb, r, st, en, d.call_flags[r], vlo, S, d.call_B[r]);
+        const uint32_t cf = d.call_flags[r] | ((d.read_flags[r] & MPH_RF_PARTNER) ? 2u : 0u);
+        const MphPair p = eval_flagged(d, sg, rev, k, g, va, vb, r, st, en, cf, vlo, S, d.call_B[r]);
         depth_x += p.member;
         if (p.member && !p.bad) {
           if (p.hap == 0 && p.frame == 0) c0_adj += 1;
@@ -318,7 +317,8 @@ __global__ void __launch_bounds__(K2_WARPS * 32) k_window_hist(const DeviceBatch
     const uint32_t r = base + lane;
     int cls = 0, ilo = 1, ihi = 0;
     if (r < rhi) {
-      const uint32_t st = d.read_start[r], en = d.read_end[r], cf = d.call_flags[r];
+      const uint32_t st = d.read_start[r], en = d.read_end[r];
+      const uint32_t cf = d.call_flags[r] | ((d.read_flags[r] & MPH_RF_PARTNER) ? 2u : 0u);
       if (cf == 0 && !has_fs) {
         cls = 1;
       } else {
@@ -502,8 +502,9 @@ __global__ void __launch_bounds__(RP_WARPS * 32) k_replay(const DeviceBatch d) {
   RpShared& sh = sh_all[warp];
   const MphReplayTx t = d.replay[ti];
   MphReplayCtx c;
-  c.read_start = d.read_start; c.read_end = d.read_end; c.read_vlo = d.read_vlo; c.read_seq_off = d.read_seq_off; c.read_cig_off = d.read_cig_off;
-  c.read_lseq = d.read_lseq; c.read_ncig = d.read_ncig; c.read_nv = d.read_nv; c.read_flags = d.read_flags;
+  c.read_start = d.read_start; c.read_end = d.read_end; c.read_flags = d.read_flags;
+  c.read_vlo = d.read_vlo; c.read_nv = d.read_nv; c.read_vr = d.read_vr;
+  c.vr_seq_off = d.vr_seq_off; c.vr_cig_off = d.vr_cig_off; c.vr_lseq = d.vr_lseq; c.vr_ncig = d.vr_ncig;
   c.bases = d.bases; c.cigars = d.cigars; c.call_S = d.call_S; c.call_B = d.call_B;
   c.pairs = reinterpret_cast<const uint32_t*>(d.pairs); c.n_pairs = d.n_pairs;
   c.vars = d.vars; c.segs = d.segs; c.seg_chunk0 = d.seg_chunk0; c.stopmap = d.stopmap; c.ref = d.ref;
@@ -888,8 +889,9 @@ __global__ void __launch_bounds__(64) k_replay_normal(const DeviceBatch d) {
   const uint32_t ti = d.rp0 + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   if (ti >= d.rp1 || (threadIdx.x & 31)) return;
   MphReplayCtx c;
-  c.read_start = d.read_start; c.read_end = d.read_end; c.read_vlo = d.read_vlo; c.read_seq_off = d.read_seq_off; c.read_cig_off = d.read_cig_off;
-  c.read_lseq = d.read_lseq; c.read_ncig = d.read_ncig; c.read_nv = d.read_nv; c.read_flags = d.read_flags;
+  c.read_start = d.read_start; c.read_end = d.read_end; c.read_flags = d.read_flags;
+  c.read_vlo = d.read_vlo; c.read_nv = d.read_nv; c.read_vr = d.read_vr;
+  c.vr_seq_off = d.vr_seq_off; c.vr_cig_off = d.vr_cig_off; c.vr_lseq = d.vr_lseq; c.vr_ncig = d.vr_ncig;
   c.bases = d.bases; c.cigars = d.cigars; c.call_S = d.call_S; c.call_B = d.call_B;
   c.pairs = reinterpret_cast<const uint32_t*>(d.pairs); c.n_pairs = d.n_pairs;
   c.vars = d.vars; c.segs = d.segs; c.seg_chunk0 = d.seg_chunk0; c.stopmap = d.stopmap; c.ref = d.ref; c.dq_init = d.dq_init;
@@ -1451,7 +1453,7 @@ __global__ void __launch_bounds__(256) k_live_depth(const DeviceBatch d) {
 }  // namespace
 
 void launch_allele_call(const DeviceBatch& d, cudaStream_t st) {
-  if (d.r1 > d.r0) k_allele_call<<<(d.r1 - d.r0 + 255) / 256, 256, 0, st>>>(d);
+  if (d.vr1 > d.vr0) k_allele_call<<<(d.vr1 - d.vr0 + 255) / 256, 256, 0, st>>>(d);
 }
 void launch_window_hist(const DeviceBatch& d, cudaStream_t st) {
   if (d.c1 <= d.c0) return;

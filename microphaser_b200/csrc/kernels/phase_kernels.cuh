@@ -14,7 +14,8 @@ struct DeviceBatch {
   // inputs
   uint32_t n_reads = 0, n_vars = 0, n_segs = 0, n_chunks = 0, n_windows = 0, seq_cap = 64, n_pairs = 0;
   // the slice of the batch one launch sequence works on (a stage of the copy / compute / residue pipeline, or everything)
-  uint32_t r0 = 0, r1 = 0;    // reads (K1)
+  uint32_t r0 = 0, r1 = 0;    // reads
+  uint32_t vr0 = 0, vr1 = 0;  // entries of the variant-read side table (K1)
   uint32_t c0 = 0, c1 = 0;    // chunks (K2, K5)
   uint32_t w0 = 0, w1 = 0;    // windows (K4)
   uint32_t rp0 = 0, rp1 = 0;  // replay units
@@ -22,13 +23,19 @@ struct DeviceBatch {
   uint32_t force_wide = 0;  // test hook (MPH_FORCE_WIDE=1): send every window with extra keys through k_window_hist_wide
   const uint32_t* read_start = nullptr;
   const uint32_t* read_end = nullptr;
-  const uint32_t* read_vlo = nullptr;
-  const uint32_t* read_seq_off = nullptr;
-  const uint32_t* read_cig_off = nullptr;
-  const uint16_t* read_lseq = nullptr;
-  const uint16_t* read_ncig = nullptr;
-  const uint8_t* read_nv = nullptr;
   const uint8_t* read_flags = nullptr;
+  // compact side table: the reads K1 has work for
+  const uint32_t* vr_read = nullptr;
+  const uint32_t* vr_vlo = nullptr;
+  const uint32_t* vr_seq_off = nullptr;
+  const uint32_t* vr_cig_off = nullptr;
+  const uint16_t* vr_lseq = nullptr;
+  const uint16_t* vr_ncig = nullptr;
+  const uint8_t* vr_nv = nullptr;
+  // per read, expanded by K1 (read_nv is zeroed first; read_vlo / read_vr are only defined where read_nv != 0)
+  uint32_t* read_vlo = nullptr;
+  uint8_t* read_nv = nullptr;
+  uint32_t* read_vr = nullptr;
   const uint2* pairs = nullptr;  // (read, partner) sorted by read — both directions; the current slice's pairs, n_pairs of them
   const uint8_t* bases = nullptr;
   const uint32_t* cigars = nullptr;

@@ -20,6 +20,26 @@ inline uint32_t partner_of(const Batch& b, uint32_t r) {
   return 0xFFFFFFFFu;
 }
 
+// what K1 expands on the device: per-read (vlo, nv, side-table entry) from the compact table
+struct PerRead {
+  std::vector<uint32_t> vlo, vr;
+  std::vector<uint8_t> nv;
+  explicit PerRead(const Batch& b) : vlo(b.read_start.size(), 0), vr(b.read_start.size(), 0xFFFFFFFFu), nv(b.read_start.size(), 0) {
+    for (size_t e = 0; e < b.vr_read.size(); ++e) { vlo[b.vr_read[e]] = b.vr_vlo[e]; nv[b.vr_read[e]] = b.vr_nv[e]; vr[b.vr_read[e]] = uint32_t(e); }
+  }
+};
+
+inline std::vector<MphCall> allele_calls(const Batch& b, bool use_qual) {
+  std::vector<MphCall> calls(b.read_start.size());
+  for (auto& c : calls) { c.S = 0; c.B = 0; }
+  for (size_t e = 0; e < b.vr_read.size(); ++e) {
+    const uint32_t r = b.vr_read[e];
+    MphRead rd{b.read_start[r], b.read_end[r], b.vr_vlo[e], b.vr_lseq[e], b.vr_nv[e], b.vr_ncig[e]};
+    calls[r] = mph_call_read(rd, b.bases.data() + size_t(b.vr_seq_off[e]) * 16, b.cigars.data() + b.vr_cig_off[e], b.vars.data(), use_qual);
+  }
+  return calls;
+}
+
 // serial replay of the irregular transcripts (core/replay_core.h) into per-window staging arrays
 struct ReplayStage {
   std::vector<MphWinOut> out;
@@ -29,7 +49,7 @@ struct ReplayStage {
   std::vector<MphHist> hist;
 };
 
-inline void run_replay(const Batch& b, const std::vector<MphCall>& calls, int mode, PhaseRaw& raw, ReplayStage& st) {
+inline void run_replay(const Batch& b, const std::vector<MphCall>& calls, const PerRead& pr_, int mode, PhaseRaw& raw, ReplayStage& st) {
   if (b.replay.empty()) return;
   const size_t nr = b.read_start.size();
   st.out.resize(b.n_windows); st.hap0.resize(b.n_windows); st.flag.resize(b.n_windows); st.voff.assign(b.n_windows, 0xFFFFFFFFu);
@@ -52,8 +72,8 @@ inline void run_replay(const Batch& b, const std::vector<MphCall>& calls, int mo
   if (mode == 1 && raw.win_depth.size() != b.n_windows) { raw.win_depth.assign(b.n_windows, 0); raw.win_id.assign(b.n_windows, 0); }
   MphReplayCtx c;
   c.seg_err = raw.seg_err.data();
-  c.read_start = b.read_start.data(); c.read_end = b.read_end.data(); c.read_vlo = b.read_vlo.data(); c.read_seq_off = b.read_seq_off.data();
-  c.read_cig_off = b.read_cig_off.data(); c.read_lseq = b.read_lseq.data(); c.read_ncig = b.read_ncig.data(); c.read_nv = b.read_nv.data();
+  c.read_start = b.read_start.data(); c.read_end = b.read_end.data(); c.read_vlo = pr_.vlo.data(); c.read_nv = pr_.nv.data(); c.read_vr = pr_.vr.data();
+  c.vr_seq_off = b.vr_seq_off.data(); c.vr_cig_off = b.vr_cig_off.data(); c.vr_lseq = b.vr_lseq.data(); c.vr_ncig = b.vr_ncig.data();
   c.read_flags = b.read_flags.data(); c.bases = b.bases.data(); c.cigars = b.cigars.data(); c.call_S = S.data(); c.call_B = B.data();
   c.pairs = pairs.data(); c.n_pairs = uint32_t(pairs.size() / 2); c.vars = b.vars.data(); c.segs = b.segs.data(); c.seg_chunk0 = b.seg_chunk0.data();
   c.stopmap = b.stopmap.data(); c.ref = b.ref.data(); c.dq_init = b.replay_dq.data();
@@ -74,17 +94,15 @@ inline void run_replay(const Batch& b, const std::vector<MphCall>& calls, int mo
 inline PhaseRaw phase_normal(const Batch& b) {
   PhaseRaw raw;
   const size_t nr = b.read_start.size();
-  std::vector<MphCall> calls(nr);
-  for (size_t r = 0; r < nr; ++r) {
-    MphRead rd{b.read_start[r], b.read_end[r], b.read_vlo[r], b.read_lseq[r], b.read_nv[r], b.read_ncig[r]};
-    const uint8_t* bases = rd.nv ? b.bases.data() + size_t(b.read_seq_off[r]) * 16 : nullptr;
-    calls[r] = mph_call_read(rd, bases, b.cigars.data() + b.read_cig_off[r], b.vars.data(), false);
+  const std::vector<MphCall> calls = allele_calls(b, false);
+  const PerRead per_read(b);
+  const std::vector<uint32_t>& read_vlo = per_read.vlo;
+  for (size_t r = 0; r < nr; ++r)
     if (b.read_flags[r] & MPH_RF_OVERFLOW) raw.err |= MPH_E_VARS_PER_WINDOW;
-  }
   raw.win_depth.assign(b.n_windows, 0);
   raw.win_id.assign(b.n_windows, 0);
   ReplayStage rp;
-  run_replay(b, calls, 1, raw, rp);
+  run_replay(b, calls, per_read, 1, raw, rp);
   std::vector<uint8_t> seqbuf(b.seq_cap);
   for (const MphChunk& ch : b.chunks) {
     const MphSegment& sg = b.segs[ch.seg];
@@ -137,7 +155,7 @@ inline PhaseRaw phase_normal(const Batch& b) {
       uint32_t depth = 0;
       std::map<uint64_t, uint32_t> hist;
       for (uint32_t r = rlo; r < rhi; ++r) {
-        const uint32_t st = b.read_start[r], en = b.read_end[r], vlo = b.read_vlo[r];
+        const uint32_t st = b.read_start[r], en = b.read_end[r], vlo = read_vlo[r];
         if (!rev) {
           const uint32_t kp = mph_nrm_fwd_entry(sg, k, g, st, en);
           if (kp == 0xFFFFFFFFu) continue;
@@ -195,16 +213,13 @@ inline PhaseRaw phase_somatic(const Batch& b) {
   PhaseRaw raw;
   const size_t nr = b.read_start.size();
   // K1
-  std::vector<MphCall> calls(nr);
-  for (size_t r = 0; r < nr; ++r) {
-    MphRead rd{b.read_start[r], b.read_end[r], b.read_vlo[r], b.read_lseq[r], b.read_nv[r], b.read_ncig[r]};
-    const uint8_t* bases = rd.nv ? b.bases.data() + size_t(b.read_seq_off[r]) * 16 : nullptr;
-    const uint32_t* cig = b.cigars.data() + b.read_cig_off[r];
-    calls[r] = mph_call_read(rd, bases, cig, b.vars.data());
+  const std::vector<MphCall> calls = allele_calls(b, true);
+  const PerRead per_read(b);
+  const std::vector<uint32_t>& read_vlo = per_read.vlo;
+  for (size_t r = 0; r < nr; ++r)
     if (b.read_flags[r] & MPH_RF_OVERFLOW) raw.err |= MPH_E_VARS_PER_WINDOW;
-  }
   ReplayStage rp;
-  run_replay(b, calls, 0, raw, rp);
+  run_replay(b, calls, per_read, 0, raw, rp);
   std::vector<MphWinOut>& rp_out = rp.out;
   std::vector<MphHap>& rp_hap0 = rp.hap0;
   std::vector<uint32_t>&rp_voff = rp.voff, &rp_vlist = rp.vlist;
@@ -265,7 +280,7 @@ inline PhaseRaw phase_somatic(const Batch& b) {
       std::map<std::tuple<uint64_t, uint32_t, uint32_t>, uint32_t> hist;  // (hap, frame0, f1nz) -> count
       for (uint32_t r = rlo; r < rhi; ++r) {
         MphPair p;
-        const uint32_t st = b.read_start[r], en = b.read_end[r], vlo = b.read_vlo[r];
+        const uint32_t st = b.read_start[r], en = b.read_end[r], vlo = read_vlo[r];
         if (!rev) {
           p = mph_fwd_state(sg, b.vars.data(), k, g, va, vb, st, en, vlo, calls[r].S, calls[r].B);
         } else {
@@ -275,9 +290,9 @@ inline PhaseRaw phase_somatic(const Batch& b) {
             uint32_t ke = mph_rev_entry(sg, b.vars.data(), k, st, en, vlo, Bx);
             if (ke != 0xFFFFFFFFu && (b.read_flags[r] & MPH_RF_PARTNER)) {
               const uint32_t q = partner_of(b, r);
-              const uint64_t Bq = calls[q].B | (calls[q].S & mph_range_mask(sg.sl_va, sg.sl_vb, b.read_vlo[q]));
+              const uint64_t Bq = calls[q].B | (calls[q].S & mph_range_mask(sg.sl_va, sg.sl_vb, read_vlo[q]));
               uint32_t kq = 0xFFFFFFFFu;
-              if (b.read_start[q] <= g.s && b.read_end[q] >= g.e) kq = mph_rev_entry(sg, b.vars.data(), k, b.read_start[q], b.read_end[q], b.read_vlo[q], Bq);
+              if (b.read_start[q] <= g.s && b.read_end[q] >= g.e) kq = mph_rev_entry(sg, b.vars.data(), k, b.read_start[q], b.read_end[q], read_vlo[q], Bq);
               if (kq != 0xFFFFFFFFu && (kq < ke || (kq == ke && q < r))) ke = 0xFFFFFFFFu;
             }
             if (ke != 0xFFFFFFFFu) p = mph_rev_state(sg, b.vars.data(), k, g, va, vb, st, en, vlo, calls[r].S, calls[r].B, ke);
