@@ -991,8 +991,8 @@ int mph_result_get(const mph_result* r, uint64_t i, mph_record* o) {
   o->somatic_aa_change = rec.info.somatic_aa_change.c_str(); o->germline_positions = rec.info.germline_positions.c_str();
   o->germline_aa_change = rec.info.germline_aa_change.c_str(); o->normal_sequence = rec.info.normal_sequence.c_str();
   o->mutant_sequence = rec.info.mutant_sequence.c_str();
-  o->fasta_mutant = rec.has_mt ? rec.mt.c_str() : nullptr;
-  o->fasta_normal = rec.has_wt ? rec.wt.c_str() : nullptr;
+  o->fasta_mutant = rec.has_mt ? rec.mt_str().c_str() : nullptr;
+  o->fasta_normal = rec.has_wt ? rec.wt_str().c_str() : nullptr;
   return MPH_OK;
 }
 
@@ -1012,8 +1012,8 @@ int mph_result_write(const mph_result* r, int fd_fasta, int fd_tsv, int fd_norma
     for (const auto& part : r->parts)
     for (const OutRecord& rec : part) {
       const uint32_t t = rec.info.tx;
-      if (rec.has_mt) { fa += '>'; fa += rec.info.id; fa += '\n'; fa += rec.mt; fa += '\n'; }
-      if (rec.has_wt) { nrm += '>'; nrm += rec.info.id; nrm += '\n'; nrm += rec.wt; nrm += '\n'; }
+      if (rec.has_mt) { fa += '>'; fa += rec.info.id; fa += '\n'; fa += rec.mt_str(); fa += '\n'; }
+      if (rec.has_wt) { nrm += '>'; nrm += rec.info.id; nrm += '\n'; nrm += rec.wt_str(); nrm += '\n'; }
       if (!hw) { tsv += normal_mode ? header_normal : header; hw = 1; }
       const std::string fields[21] = {rec.info.id, r->tx_id[t], r->gene_id[t], r->gene_name[t], r->chrom[t], std::to_string(rec.info.offset),
                                       std::to_string(rec.info.frame), mphfmt::format_f64(rec.info.freq), std::to_string(rec.info.depth),

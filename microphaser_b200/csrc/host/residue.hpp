@@ -15,6 +15,7 @@
 #include <limits>
 #include <map>
 #include <string>
+#include <string_view>
 #include <tuple>
 #include <vector>
 
@@ -55,9 +56,13 @@ struct InfoRecord {
 
 struct OutRecord {
   InfoRecord info;       // the TSV row
-  std::string mt;        // mutant FASTA sequence (stdout), valid if has_mt
-  std::string wt;        // normal FASTA sequence (--normal-output), valid if has_wt
+  std::string mt;        // mutant FASTA sequence (stdout), valid if has_mt && !mt_same
+  std::string wt;        // normal FASTA sequence (--normal-output), valid if has_wt && !wt_same
   bool has_mt = false, has_wt = false;
+  // the FASTA line is byte-identical to the TSV column (the common case): it is not stored twice
+  bool mt_same = false, wt_same = false;
+  const std::string& mt_str() const { return mt_same ? info.mutant_sequence : mt; }
+  const std::string& wt_str() const { return wt_same ? info.normal_sequence : wt; }
 };
 
 struct ResidueStats {
@@ -344,28 +349,31 @@ class Residue {
       const bool lazy = boundary && !emit && (nv == 0 || key.hap == 0) && seqs_equal && !germ_cleared;
       const bool need_rec = (emit || boundary) && !lazy;
       const bool want_seq = need_rec || (stop_gain && indel);
-      std::string seq, germline_seq;
+      // views into the reference arena / the downloaded sequence arena: nothing is copied until a record is built
+      std::string_view seq, germline_seq;
       if (want_seq) {
         if (nv == 0 || key.hap == 0) {
           // no variant applied: seq == germline_seq == refseq[s..e) (:464-471,594-599), the host has those bytes
           if (g.s < sg.ref_pos0 || uint64_t(g.e) - sg.ref_pos0 > sg.ref_len) throw Fatal("slice index out of range: refseq");
-          seq.assign(reinterpret_cast<const char*>(b_.ref.data()) + sg.ref_off + (g.s - sg.ref_pos0), g.e - g.s);
+          seq = std::string_view(reinterpret_cast<const char*>(b_.ref.data()) + sg.ref_off + (g.s - sg.ref_pos0), g.e - g.s);
           if (!germ_cleared) germline_seq = seq;
         } else {
           if (!(h.flags & MPH_HF_SEQ)) throw std::logic_error("internal: sequence not shipped for an emitted / boundary haplotype");
-          seq = arena(h, false);
-          if (!germ_cleared) germline_seq = arena(h, true);
+          if (h.flags & MPH_HF_OVERFLOW) throw Unsupported("assembled haplotype longer than the sequence slot");
+          const char* base = reinterpret_cast<const char*>(raw_.seq.data()) + h.seq_off;
+          seq = std::string_view(base, h.seq_len);
+          if (!germ_cleared) germline_seq = std::string_view(base + b_.seq_cap, h.germ_len);
         }
       }
       const bool have_seq = want_seq;
-      auto slice = [](const std::string& s, uint64_t a, uint64_t e) -> std::string {
+      auto slice = [](std::string_view s, uint64_t a, uint64_t e) -> std::string_view {
         if (a > e || e > s.size()) throw Fatal("slice index out of range");
         return s.substr(size_t(a), size_t(e - a));
       };
-      std::string normal_peptide, neopeptide;
+      std::string_view normal_peptide, neopeptide;
       bool peptides_differ;  // normal_peptide != neopeptide (:707)
       if (have_seq) {
-        if (germline_seq.empty()) normal_peptide = "";
+        if (germline_seq.empty()) normal_peptide = std::string_view();
         else if (g.spos == 1) normal_peptide = slice(germline_seq, g.gap, germline_seq.size());
         else if (g.spos == 0) normal_peptide = slice(germline_seq, 0, normal_window_len);
         else normal_peptide = germline_seq;
@@ -407,8 +415,8 @@ class Residue {
             rec.id = mphfmt::record_id(reinterpret_cast<const uint8_t*>(seq.data()), seq.size(), tm.id, g.s, rev ? 'R' : 'F');
           }
         }
-        rec.normal_sequence = normal_peptide;
-        rec.mutant_sequence = neopeptide;
+        rec.normal_sequence.assign(normal_peptide);
+        rec.mutant_sequence.assign(neopeptide);
       }
       if (!remove_peptide || frame == 0) {
         InfoRecord rec_for_merge;
@@ -420,8 +428,8 @@ class Residue {
           if (lazy) {
             hs.lazy = true; hs.sg = &sg; hs.h = &h; hs.k = k; hs.wv = wv;
           } else {
-            hs.rec.normal_sequence = germline_seq;
-            hs.rec.mutant_sequence = seq;
+            hs.rec.normal_sequence.assign(germline_seq);
+            hs.rec.mutant_sequence.assign(seq);
           }
           haplotypes_vec.v.push_back(std::move(hs));
         } else {
@@ -430,11 +438,16 @@ class Residue {
       }
       if (emit) {
         OutRecord o;
-        if (g.spos == 1) { o.mt = slice(seq, g.gap, seq.size()); o.has_mt = true; }
-        else if (g.spos == 0) { o.mt = slice(seq, 0, this_window_len); o.has_mt = true; }
+        // the FASTA lines (:846-873) are the TSV columns again unless an insertion / indel changed the slice bounds
+        auto put = [](std::string_view line, std::string_view column, std::string& dst, bool& same) {
+          same = line.data() == column.data() && line.size() == column.size();
+          if (!same) dst.assign(line);
+        };
+        if (g.spos == 1) { put(slice(seq, g.gap, seq.size()), neopeptide, o.mt, o.mt_same); o.has_mt = true; }
+        else if (g.spos == 0) { put(slice(seq, 0, this_window_len), neopeptide, o.mt, o.mt_same); o.has_mt = true; }
         if (!germline_seq.empty()) {
-          if (g.spos == 1) { o.wt = slice(germline_seq, g.gap, germline_seq.size()); o.has_wt = true; }
-          else if (g.spos == 0) { o.wt = slice(germline_seq, 0, this_window_len); o.has_wt = true; }
+          if (g.spos == 1) { put(slice(germline_seq, g.gap, germline_seq.size()), normal_peptide, o.wt, o.wt_same); o.has_wt = true; }
+          else if (g.spos == 0) { put(slice(germline_seq, 0, this_window_len), normal_peptide, o.wt, o.wt_same); o.has_wt = true; }
         }
         o.info = std::move(rec);
         out.push_back(std::move(o));

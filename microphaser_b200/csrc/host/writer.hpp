@@ -34,7 +34,7 @@ inline void write_records_normal(const Batch& b, const std::vector<OutRecord>& r
       "strand\tvariant_sites\tsomatic_positions\tsomatic_aa_change\tgermline_positions\tgermline_aa_change\tpeptide_sequence\n";
   std::string line;
   for (const OutRecord& r : recs) {
-    if (r.has_mt) write_fasta(o.fasta, r.info.id, r.mt);
+    if (r.has_mt) write_fasta(o.fasta, r.info.id, r.mt_str());
     if (!o.header_written) {
       fputs(header, o.tsv);
       o.header_written = true;
@@ -65,8 +65,8 @@ inline void write_records(const Batch& b, const std::vector<OutRecord>& recs, Ou
       "mutant_sequence\n";
   std::string line;
   for (const OutRecord& r : recs) {
-    if (r.has_mt) write_fasta(o.fasta, r.info.id, r.mt);
-    if (r.has_wt) write_fasta(o.normal, r.info.id, r.wt);
+    if (r.has_mt) write_fasta(o.fasta, r.info.id, r.mt_str());
+    if (r.has_wt) write_fasta(o.normal, r.info.id, r.wt_str());
     if (!o.header_written) {
       fputs(header, o.tsv);
       o.header_written = true;
