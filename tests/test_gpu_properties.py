@@ -51,3 +51,27 @@ def test_whole_exome_shape_resident_run(product):
     assert t_one["windows"] == t_two["windows"] and t_one["read_windows"] == t_two["read_windows"]
     assert t_one["read_windows"] > 50 * t_one["windows"]  # ~100x * (150-27)/150 reads per window
     ctx.close()
+
+
+@pytest.mark.parametrize("mode", ["somatic", "normal"])
+def test_pipelined_stages_match_single_stage(product, mode, monkeypatch):
+    """mph_phase_batch cuts a batch at gene boundaries into stages (copy / kernels / residue overlap); the records must not
+    depend on where the cuts fall. MPH_STAGES forces the stage count (large batches pick it from the read count)."""
+    import microphaser_b200 as m
+    if mode == "normal":
+        monkeypatch.setenv("MPH_SYNTH_MODE", "1")
+    ctx = m.Context(0)
+    batch = m.Batch.synthetic(n_transcripts=600 if mode == "normal" else 2000, coverage=60.0, seed=0x4D500004)
+    monkeypatch.setenv("MPH_STAGES", "1")
+    one = ctx.phase_batch(batch)
+    t_one = ctx.timing()
+    monkeypatch.setenv("MPH_STAGES", "7")
+    many = ctx.phase_batch(batch)
+    t_many = ctx.timing()
+    assert len(one) == len(many) > 1000
+    assert records(one) == records(many)
+    assert t_one["windows"] == t_many["windows"] and t_one["read_windows"] == t_many["read_windows"]
+    assert t_many["kernel_launches"] >= 7 * t_one["kernel_launches"]
+    if mode == "somatic":
+        assert t_one["n_replay_units"] > 0, "the synthetic workload is expected to contain irregular transcripts"
+    ctx.close()
