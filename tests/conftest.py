@@ -95,6 +95,19 @@ def build_product():
     return build.build_all()
 
 
+def build_abi_host():
+    """tests/abi_host/abi_host.cpp: a host that reaches the library through the C ABI's packer entry points only."""
+    lib, _ = build_product()
+    out = os.path.join(ROOT, "tests", "abi_host", "_build")
+    os.makedirs(out, exist_ok=True)
+    exe = os.path.join(out, "abi_host")
+    src = os.path.join(ROOT, "tests", "abi_host", "abi_host.cpp")
+    if not os.path.exists(exe) or os.path.getmtime(exe) < max(os.path.getmtime(src), os.path.getmtime(lib)):
+        subprocess.run(["g++", "-std=c++17", "-O2", "-o", exe, src, "-L" + os.path.dirname(lib), "-lmicrophaser_gpu", "-lz",
+                        "-Wl,-rpath," + os.path.dirname(lib)], check=True)
+    return exe
+
+
 def run_cli(binary, case_dir, out_dir, gtf="annotation.gtf", ref=None, subcommand="somatic"):
     """Run `<binary> somatic ...` the way the reference's tests do (tests/lib.rs:23-35); returns CompletedProcess."""
     ref = ref or os.path.join(case_dir, "ref.fa")
@@ -109,6 +122,11 @@ def run_cli(binary, case_dir, out_dir, gtf="annotation.gtf", ref=None, subcomman
 def read_outputs(out_dir, subcommand="somatic"):
     names = ("out.fa", "out.tsv", "out.normal.fa") if subcommand == "somatic" else ("out.fa", "out.tsv")
     return {n: open(os.path.join(out_dir, n), "rb").read() for n in names}
+
+
+@pytest.fixture(scope="session")
+def abi_host():
+    return build_abi_host()
 
 
 @pytest.fixture(scope="session")

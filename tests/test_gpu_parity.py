@@ -205,3 +205,36 @@ def test_c_abi_run_normal_matches_oracle_with_statistics(product, oracle_bin, tm
     if os.path.exists(tmp_path / "stats.json"):
         st = json.load(open(tmp_path / "stats.json"))
         assert t["windows"] == st["windows"] and t["read_windows"] == st["read_windows"]
+
+
+# ---------------------------------------------------------------- the packer entry points of the C ABI
+@pytest.mark.parametrize("case,sub", [("reverse_somatic", "somatic"), ("splice_forward_somatic", "somatic"), ("forward_normal", "normal")])
+def test_c_abi_packer_entry_points_match_golden(abi_host, case, sub, tmp_path):
+    """A host that flattens every gene into `mph_gene_in` arrays and calls mph_packer_add_gene / mph_phase_batch /
+    mph_result_write (what the Rust binding of INTEGRATION.md does) must produce the reference's bytes."""
+    import subprocess
+    d = os.path.join(GOLDEN, case)
+    fa = materialize_reference(d, str(tmp_path))
+    cmd = [abi_host, sub, os.path.join(d, "reads.bam"), fa, os.path.join(d, "variants.vcf"), os.path.join(d, "annotation.gtf"),
+           str(tmp_path / "out.fa"), str(tmp_path / "out.tsv")]
+    if sub == "somatic":
+        cmd.append(str(tmp_path / "out.normal.fa"))
+    r = subprocess.run(cmd, stderr=subprocess.PIPE, timeout=600)
+    assert r.returncode == 0, r.stderr.decode()
+    names = sorted(os.listdir(os.path.join(d, "expected")))
+    for name in names:
+        assert open(tmp_path / name, "rb").read() == open(os.path.join(d, "expected", name), "rb").read(), name
+
+
+def test_c_abi_packer_entry_points_match_oracle_on_synthetic(abi_host, oracle_bin, tmp_path):
+    import subprocess
+    d = str(tmp_path / "in")
+    synth.generate(d, synth.Params(seed=31337, n_genes=6, coverage=30.0, indel_frac=0.2, multiallelic_frac=0.1, intron_len=(20, 400)))
+    o, p = tmp_path / "o", tmp_path / "p"
+    o.mkdir()
+    p.mkdir()
+    assert run_cli(oracle_bin, d, str(o)).returncode == 0
+    r = subprocess.run([abi_host, "somatic", os.path.join(d, "reads.bam"), os.path.join(d, "ref.fa"), os.path.join(d, "variants.vcf"),
+                        os.path.join(d, "annotation.gtf"), str(p / "out.fa"), str(p / "out.tsv"), str(p / "out.normal.fa")], stderr=subprocess.PIPE, timeout=600)
+    assert r.returncode == 0, r.stderr.decode()
+    assert read_outputs(str(o)) == read_outputs(str(p))
