@@ -1,0 +1,32 @@
+// kernel_common.cuh — constants and small device helpers shared by the phasing kernels (internal to csrc/kernels).
+#pragma once
+#include "phase_kernels.cuh"
+
+#include "../core/phase_core.h"
+#include "../core/replay_core.h"
+
+namespace mphk {
+namespace detail {
+
+constexpr unsigned FULL = 0xFFFFFFFFu;
+constexpr uint32_t NONE = 0xFFFFFFFFu;
+constexpr int K2_WARPS = 4;
+constexpr int K2_TABLE = 32;
+constexpr int MAX_SEQ_CAP = 256;  // bytes per assembled sequence kept in local memory
+
+__device__ __forceinline__ void raise(const DeviceBatch& d, uint32_t bits) {
+  if (bits) atomicOr(&d.counters[CTR_ERR], bits);
+}
+
+constexpr int K2_LIST = 64;  // listed reads per warp between two flushes (phase B of the window kernels)
+
+// order of the reference's BTreeMap<(haplotype, frame), count> (:383,434) on the packed key
+__device__ __forceinline__ bool hist_less(const MphHist& a, const MphHist& b) {
+  if (a.hap != b.hap) return a.hap < b.hap;
+  const uint32_t fa = a.frame & 0x7FFFFFFFu, fb = b.frame & 0x7FFFFFFFu;
+  if (fa != fb) return fa < fb;
+  return (a.frame >> 31) < (b.frame >> 31);
+}
+
+}  // namespace detail
+}  // namespace mphk

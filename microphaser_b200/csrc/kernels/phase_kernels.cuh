@@ -92,7 +92,9 @@ enum { CTR_HIST = 0, CTR_SEQ = 1, CTR_NIW = 2, CTR_ERR = 3, CTR_OVF = 4, CTR_VLI
 
 void launch_allele_call(const DeviceBatch& d, cudaStream_t st);
 void launch_window_hist(const DeviceBatch& d, cudaStream_t st);
-void launch_replay(const DeviceBatch& d, cudaStream_t st);
+void launch_replay(const DeviceBatch& d, cudaStream_t st);                // replay_kernels.cu
+void launch_window_hist_normal(const DeviceBatch& d, cudaStream_t st);    // normal_kernels.cu (called by launch_window_hist in mode 1)
+void launch_assemble_normal(const DeviceBatch& d, cudaStream_t st);
 void launch_assemble(const DeviceBatch& d, cudaStream_t st);
 void launch_compact(const DeviceBatch& d, cudaStream_t st);
 void launch_live_depth(const DeviceBatch& d, cudaStream_t st);
