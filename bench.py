@@ -273,7 +273,9 @@ def main():
         # zero-fill of S / B / flag / nv for every read, then per side-table entry: entry in (21 B), start / end (8 B), one base
         # sector + one quality sector (64 B), S / B / flag / vlo / nv / index out (26 B)
         "k1_ms": n_reads * 18 + n_special * (21 + 8 + 64 + 26) + view.n_vars * 16,
-        "k2_ms": n_reads * 9 + n_special * 20 + n_win * 16 + t_res["d2h_bytes"] * 0.3 + n_seg * 96 + n_chunk * 32,
+        # per read: start, end, call flag, host flag (10 B); per listed read: S + vlo + B (20 B); per window: summary + flag out (17 B);
+        # per interesting window: haplotype-0 record (32 B); per extra key (about two per record): key + window code (20 B)
+        "k2_ms": n_reads * 10 + n_special * 20 + n_win * 17 + t_res["n_interesting"] * 32 + n_records * 2 * 20 + n_seg * 96 + n_chunk * 32,
         "k3_ms": n_win * (16 + 32 + 1) + view.ref_bytes + n_seg * 96 + n_chunk * 32,
         "k4_ms": n_win * 2 + t_res["n_interesting"] * (4 + 2 * 48),
     }

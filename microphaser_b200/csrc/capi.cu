@@ -197,8 +197,13 @@ std::vector<Stage> plan_stages(const mph_batch* mb, unsigned want) {
   std::vector<Stage> out;
   if (want < 1) want = 1;
   size_t g = 0;
+  // the first two stages are shorter (0.35 and 0.7 of a regular one): the host residue can start earlier
+  auto weight = [](unsigned s) { return s == 0 ? 0.35 : (s == 1 ? 0.7 : 1.0); };
+  double total_w = 0, acc_w = 0;
+  for (unsigned s = 0; s < want; ++s) total_w += weight(s);
   for (unsigned s = 0; s < want && g < n_genes; ++s) {
-    const uint64_t target = b.marks.back().reads * (s + 1) / want;
+    acc_w += weight(s);
+    const uint64_t target = want > 2 ? uint64_t(double(b.marks.back().reads) * acc_w / total_w) : b.marks.back().reads * (s + 1) / want;
     size_t ge = g + 1;
     while (ge < n_genes && b.marks[ge].reads < target) ++ge;
     if (s + 1 == want) ge = n_genes;
@@ -614,6 +619,8 @@ void phase_stages(mph_ctx* c, const std::vector<Stage>& stages, bool copied, mph
   c->timing.n_records = res->size();
   c->timing.kernel_launches = (uint32_t(mphk::kernel_launch_count()) + (b.replay.empty() ? 0u : 1u)) * uint32_t(ns);
   c->timing.n_replay_units = uint32_t(b.replay.size());
+  res->tx_id.reserve(b.txs.size()); res->gene_id.reserve(b.txs.size()); res->gene_name.reserve(b.txs.size()); res->chrom.reserve(b.txs.size());
+  res->tx_reverse.reserve(b.txs.size());
   for (auto& t : b.txs) {
     res->tx_id.push_back(t.id);
     res->gene_id.push_back(b.genes[t.gene].id);
