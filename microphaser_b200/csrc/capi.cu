@@ -1046,7 +1046,10 @@ int mph_result_write(const mph_result* r, int fd_fasta, int fd_tsv, int fd_norma
 static void run_somatic_files(const std::vector<mph_ctx*>& ctxs, const char* bam_path, const char* ref_path, const char* variants_path,
                               const char* gtf_path, const char* fasta_out_path, const char* tsv_path, const char* normal_path,
                               uint32_t window_len, int warn_only, int mode = 0) {
-  mphio::BamFile bam(bam_path);
+  // BGZF inflate of the alignment file runs on a few host threads (MPH_IO_THREADS, default min(cores, 8))
+  unsigned io_threads = std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 8u);
+  if (const char* e = getenv("MPH_IO_THREADS")) io_threads = unsigned(std::max(1, atoi(e)));
+  mphio::BamFile bam(bam_path, io_threads);
   mphio::VcfFile vcf(variants_path);
   mphio::FastaIndexed fasta(ref_path);
   // the reference creates its output files before it starts phasing (src/main.rs:79-85)

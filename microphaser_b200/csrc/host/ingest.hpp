@@ -22,18 +22,41 @@ inline uint64_t fnv1a(const std::string& s) {
 // bam::RecordBuffer::fetch over a coordinate-sorted BAM held in memory per contig
 class ReadBuffer {
  public:
+  // one alignment record; sequence / quality / CIGAR live in the buffer's arenas (no allocation per record)
+  struct Rec {
+    int32_t tid, pos;
+    uint32_t end;  // CigarStringView::end_pos()
+    uint32_t l_seq, n_cigar;
+    uint16_t flag;
+    uint8_t mapq;
+    uint64_t qname_hash;
+    size_t seq_off, qual_off, cig_off;
+    bool is_unmapped() const { return flag & 4; }
+  };
+
   explicit ReadBuffer(mphio::BamFile& bam) : bam_(bam) {
     by_tid_.resize(bam.ref_names.size());
     mphio::BamRecord r;
     while (bam.next(r)) {
       if (r.tid < 0 || size_t(r.tid) >= by_tid_.size()) continue;
-      r.aux.clear();
-      by_tid_[r.tid].push_back(std::make_shared<mphio::BamRecord>(std::move(r)));
+      Rec x;
+      x.tid = r.tid; x.pos = int32_t(r.pos); x.end = uint32_t(r.end_pos()); x.l_seq = r.l_seq; x.n_cigar = uint32_t(r.cigar.size());
+      x.flag = r.flag; x.mapq = r.mapq; x.qname_hash = fnv1a_bytes(r.qname.data(), r.qname.size());
+      x.seq_off = seq_.size(); x.qual_off = qual_.size(); x.cig_off = cig_.size();
+      seq_.insert(seq_.end(), r.seq4.begin(), r.seq4.end());
+      qual_.insert(qual_.end(), r.qual.begin(), r.qual.end());
+      cig_.insert(cig_.end(), r.cigar.begin(), r.cigar.end());
+      by_tid_[r.tid].push_back(x);
     }
   }
-  using Ptr = std::shared_ptr<const mphio::BamRecord>;
-  const std::deque<Ptr>& fetch(const std::string& chrom, uint64_t start, uint64_t end) {
-    if (overflow_) { inner_.push_back(overflow_); overflow_.reset(); }
+  const uint8_t* seq4(const Rec& r) const { return seq_.data() + r.seq_off; }
+  const uint8_t* qual(const Rec& r) const { return qual_.data() + r.qual_off; }
+  const uint32_t* cigar(const Rec& r) const { return cig_.data() + r.cig_off; }
+
+  // bam::RecordBuffer::fetch (rust-htslib 0.36) over the in-memory records: the window of records with
+  // start <= pos < end, kept across calls for overlapping / adjacent queries
+  const std::deque<const Rec*>& fetch(const std::string& chrom, uint64_t start, uint64_t end) {
+    if (overflow_) { inner_.push_back(overflow_); overflow_ = nullptr; }
     auto it = bam_.tid_of.find(chrom);
     if (it == bam_.tid_of.end()) throw std::runtime_error("sequence " + chrom + " not found in BAM header");
     const int tid = it->second;
@@ -45,12 +68,12 @@ class ReadBuffer {
       tid_ = tid;
       cur_ = 0;
       // an index query starts at the first record overlapping `start`
-      while (cur_ < v.size() && uint64_t(v[cur_]->pos) < start && (v[cur_]->is_unmapped() || uint64_t(v[cur_]->end_pos()) <= start)) ++cur_;
+      while (cur_ < v.size() && uint64_t(v[cur_].pos) < start && (v[cur_].is_unmapped() || uint64_t(v[cur_].end) <= start)) ++cur_;
     } else {
       while (!inner_.empty() && uint64_t(inner_.front()->pos) < start) inner_.pop_front();
     }
     while (tid_ == tid && cur_ < v.size()) {
-      const Ptr& r = v[cur_++];
+      const Rec* r = &v[cur_++];
       if (r->is_unmapped()) continue;
       const uint64_t pos = uint64_t(r->pos);
       if (pos >= end) { overflow_ = r; break; }
@@ -60,10 +83,17 @@ class ReadBuffer {
   }
 
  private:
+  static uint64_t fnv1a_bytes(const char* p, size_t n) {
+    uint64_t h = 1469598103934665603ull;
+    for (size_t i = 0; i < n; ++i) { h ^= uint8_t(p[i]); h *= 1099511628211ull; }
+    return h;
+  }
   mphio::BamFile& bam_;
-  std::vector<std::vector<Ptr>> by_tid_;
-  std::deque<Ptr> inner_;
-  Ptr overflow_;
+  std::vector<std::vector<Rec>> by_tid_;
+  std::vector<uint8_t> seq_, qual_;
+  std::vector<uint32_t> cig_;
+  std::deque<const Rec*> inner_;
+  const Rec* overflow_ = nullptr;
   int tid_ = -1;
   size_t cur_ = 0;
 };
@@ -302,13 +332,13 @@ inline std::vector<GeneInput> ingest_genes(std::istream& gtf, ReadBuffer& reads,
       if (rec->l_seq > gi.max_read_len) gi.max_read_len = rec->l_seq;
       HostRead h;
       h.start = uint32_t(rec->pos);
-      h.end = uint32_t(rec->end_pos());
+      h.end = rec->end;
       h.l_seq = rec->l_seq;
-      h.seq4 = rec->seq4.data();
-      h.qual = rec->qual.data();
-      h.cigar = rec->cigar.data();
-      h.n_cigar = uint32_t(rec->cigar.size());
-      h.qname_hash = fnv1a(rec->qname);
+      h.seq4 = reads.seq4(*rec);
+      h.qual = reads.qual(*rec);
+      h.cigar = reads.cigar(*rec);
+      h.n_cigar = rec->n_cigar;
+      h.qname_hash = rec->qname_hash;
       gi.reads.push_back(h);
     }
     // variant_tree.insert(rec.pos(), Variant::new(rec)): a later record at the same position replaces the earlier (:937)

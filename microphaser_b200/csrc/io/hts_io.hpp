@@ -13,6 +13,11 @@
 #pragma once
 #include <zlib.h>
 
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
+#include <exception>
 #include <algorithm>
 #include <cstdint>
 #include <cstdio>
@@ -49,13 +54,25 @@ inline std::vector<uint8_t> read_file(const std::string& path) {
 // ---------------------------------------------------------------- BGZF
 // Streaming BGZF block reader: each block is an independent gzip member with a BC extra
 // subfield holding the block size. inflate is done with raw deflate (windowBits -15).
+// BGZF: a series of gzip members of <= 64 KiB each. With threads > 1 a producer thread reads batches of raw blocks
+// and inflates them with a small pool while the consumer parses the previous batch (rank 3 of SURVEY.md §8(f):
+// BGZF inflate is the first end-to-end bottleneck of the file drivers). threads == 1 is the plain sequential reader.
 class BgzfReader {
  public:
-  explicit BgzfReader(const std::string& path) : path_(path) {
+  explicit BgzfReader(const std::string& path, unsigned threads = 1) : path_(path), threads_(threads ? threads : 1) {
     f_ = fopen(path.c_str(), "rb");
     if (!f_) throw IoError("cannot open " + path);
+    if (threads_ > 1) producer_ = std::thread([this] { produce(); });
   }
   ~BgzfReader() {
+    if (producer_.joinable()) {
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        stop_ = true;
+      }
+      cv_.notify_all();
+      producer_.join();
+    }
     if (f_) fclose(f_);
   }
   BgzfReader(const BgzfReader&) = delete;
@@ -67,7 +84,7 @@ class BgzfReader {
     size_t got = 0;
     while (got < n) {
       if (pos_ == block_.size()) {
-        if (!next_block()) {
+        if (!(threads_ > 1 ? next_batch() : next_block())) {
           if (got == 0) return false;
           throw IoError("truncated BGZF stream in " + path_);
         }
@@ -82,51 +99,149 @@ class BgzfReader {
   }
 
  private:
+  struct Raw {
+    size_t coff, clen, ooff, isize;
+  };
+  // reads one raw block (compressed payload appended to cbuf); false at end of file
+  bool read_raw(std::vector<uint8_t>& cbuf, Raw& r) {
+    uint8_t hdr[18];
+    size_t n = fread(hdr, 1, 18, f_);
+    if (n == 0) return false;
+    if (n != 18 || hdr[0] != 31 || hdr[1] != 139 || hdr[2] != 8 || !(hdr[3] & 4)) throw IoError("not a BGZF file: " + path_);
+    uint16_t xlen = hdr[10] | (hdr[11] << 8);
+    // the BC subfield is normally the first (and only) one
+    std::vector<uint8_t> extra(xlen);
+    memcpy(extra.data(), hdr + 12, std::min<size_t>(6, xlen));
+    if (xlen > 6 && fread(extra.data() + 6, 1, xlen - 6, f_) != size_t(xlen - 6)) throw IoError("truncated BGZF header in " + path_);
+    int bsize = -1;
+    for (size_t o = 0; o + 4 <= extra.size();) {
+      uint16_t slen = extra[o + 2] | (extra[o + 3] << 8);
+      if (extra[o] == 'B' && extra[o + 1] == 'C' && slen == 2) bsize = extra[o + 4] | (extra[o + 5] << 8);
+      o += 4 + slen;
+    }
+    if (bsize < 0) throw IoError("BGZF block without BC field in " + path_);
+    const size_t clen = size_t(bsize) + 1 - 12 - xlen - 8;  // compressed payload
+    const size_t off = cbuf.size();
+    cbuf.resize(off + clen + 8);
+    if (fread(cbuf.data() + off, 1, clen + 8, f_) != clen + 8) throw IoError("truncated BGZF block in " + path_);
+    uint32_t isize;
+    memcpy(&isize, cbuf.data() + off + clen + 4, 4);
+    r.coff = off; r.clen = clen; r.isize = isize; r.ooff = 0;
+    return true;
+  }
+  void inflate_one(const uint8_t* in, size_t clen, uint8_t* out, size_t isize) const {
+    if (isize == 0) return;
+    z_stream zs;
+    memset(&zs, 0, sizeof zs);
+    if (inflateInit2(&zs, -15) != Z_OK) throw IoError("zlib init failed");
+    zs.next_in = const_cast<uint8_t*>(in);
+    zs.avail_in = uInt(clen);
+    zs.next_out = out;
+    zs.avail_out = uInt(isize);
+    int rc = inflate(&zs, Z_FINISH);
+    inflateEnd(&zs);
+    if (rc != Z_STREAM_END) throw IoError("BGZF inflate failed in " + path_);
+  }
   bool next_block() {
     for (;;) {
-      uint8_t hdr[18];
-      size_t n = fread(hdr, 1, 18, f_);
-      if (n == 0) return false;
-      if (n != 18 || hdr[0] != 31 || hdr[1] != 139 || hdr[2] != 8 || !(hdr[3] & 4))
-        throw IoError("not a BGZF file: " + path_);
-      uint16_t xlen = hdr[10] | (hdr[11] << 8);
-      // the BC subfield is normally the first (and only) one
-      std::vector<uint8_t> extra(xlen);
-      memcpy(extra.data(), hdr + 12, std::min<size_t>(6, xlen));
-      if (xlen > 6 && fread(extra.data() + 6, 1, xlen - 6, f_) != size_t(xlen - 6))
-        throw IoError("truncated BGZF header in " + path_);
-      int bsize = -1;
-      for (size_t o = 0; o + 4 <= extra.size();) {
-        uint16_t slen = extra[o + 2] | (extra[o + 3] << 8);
-        if (extra[o] == 'B' && extra[o + 1] == 'C' && slen == 2) bsize = extra[o + 4] | (extra[o + 5] << 8);
-        o += 4 + slen;
-      }
-      if (bsize < 0) throw IoError("BGZF block without BC field in " + path_);
-      size_t clen = size_t(bsize) + 1 - 12 - xlen - 8;  // compressed payload
-      cbuf_.resize(clen + 8);
-      if (fread(cbuf_.data(), 1, clen + 8, f_) != clen + 8) throw IoError("truncated BGZF block in " + path_);
-      uint32_t isize;
-      memcpy(&isize, cbuf_.data() + clen + 4, 4);
-      block_.resize(isize);
+      cbuf_.clear();
+      Raw r;
+      if (!read_raw(cbuf_, r)) return false;
+      block_.resize(r.isize);
       pos_ = 0;
-      if (isize == 0) continue;  // EOF marker / empty block
-      z_stream zs;
-      memset(&zs, 0, sizeof zs);
-      if (inflateInit2(&zs, -15) != Z_OK) throw IoError("zlib init failed");
-      zs.next_in = cbuf_.data();
-      zs.avail_in = uInt(clen);
-      zs.next_out = block_.data();
-      zs.avail_out = isize;
-      int rc = inflate(&zs, Z_FINISH);
-      inflateEnd(&zs);
-      if (rc != Z_STREAM_END) throw IoError("BGZF inflate failed in " + path_);
+      if (r.isize == 0) continue;  // EOF marker / empty block
+      inflate_one(cbuf_.data() + r.coff, r.clen, block_.data(), r.isize);
       return true;
     }
   }
+
+  // ---- threaded path: producer fills `ready_` (at most two batches ahead), consumer swaps them into block_
+  struct Batch {
+    std::vector<uint8_t> data;
+    bool eof = false;
+    std::exception_ptr err;
+  };
+  void produce() {
+    std::vector<uint8_t> cbuf;
+    std::vector<Raw> raws;
+    for (;;) {
+      Batch b;
+      try {
+        cbuf.clear();
+        raws.clear();
+        size_t total = 0;
+        while (raws.size() < 256) {
+          Raw r;
+          if (!read_raw(cbuf, r)) { b.eof = true; break; }
+          r.ooff = total;
+          total += r.isize;
+          raws.push_back(r);
+        }
+        b.data.resize(total);
+        std::atomic<size_t> next{0};
+        std::vector<std::exception_ptr> errs(threads_);
+        auto work = [&](unsigned ti) {
+          try {
+            for (;;) {
+              const size_t i = next.fetch_add(1);
+              if (i >= raws.size()) break;
+              inflate_one(cbuf.data() + raws[i].coff, raws[i].clen, b.data.data() + raws[i].ooff, raws[i].isize);
+            }
+          } catch (...) {
+            errs[ti] = std::current_exception();
+          }
+        };
+        std::vector<std::thread> pool;
+        for (unsigned ti = 1; ti < threads_; ++ti) pool.emplace_back(work, ti);
+        work(0);
+        for (auto& t : pool) t.join();
+        for (auto& e : errs)
+          if (e) std::rethrow_exception(e);
+      } catch (...) {
+        b.err = std::current_exception();
+        b.eof = true;
+      }
+      const bool last = b.eof;
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return stop_ || ready_.size() < 2; });
+        if (stop_) return;
+        ready_.push_back(std::move(b));
+      }
+      cv_.notify_all();
+      if (last) return;
+    }
+  }
+  bool next_batch() {
+    for (;;) {
+      Batch b;
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        if (drained_) return false;
+        cv_.wait(lk, [&] { return !ready_.empty(); });
+        b = std::move(ready_.front());
+        ready_.pop_front();
+        if (b.eof) drained_ = true;
+      }
+      cv_.notify_all();
+      if (b.err) std::rethrow_exception(b.err);
+      block_ = std::move(b.data);
+      pos_ = 0;
+      if (!block_.empty()) return true;
+      if (drained_) return false;
+    }
+  }
+
   std::string path_;
   FILE* f_ = nullptr;
   std::vector<uint8_t> cbuf_, block_;
   size_t pos_ = 0;
+  unsigned threads_ = 1;
+  std::thread producer_;
+  std::mutex mu_;
+  std::condition_variable cv_;
+  std::deque<Batch> ready_;
+  bool stop_ = false, drained_ = false;
 };
 
 // ---------------------------------------------------------------- BAM
@@ -227,7 +342,7 @@ struct BamFile {
   std::vector<int64_t> ref_lens;
   std::unordered_map<std::string, int> tid_of;
 
-  explicit BamFile(const std::string& path) : rd_(path) {
+  explicit BamFile(const std::string& path, unsigned inflate_threads = 1) : rd_(path, inflate_threads) {
     char magic[4];
     if (!rd_.read(magic, 4) || memcmp(magic, "BAM\1", 4) != 0) throw IoError("not a BAM file: " + path);
     int32_t l_text;
