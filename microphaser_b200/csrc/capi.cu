@@ -1082,12 +1082,28 @@ static void run_somatic_files(const std::vector<mph_ctx*>& ctxs, const char* bam
     }
     ReadBuffer reads(bam);
     std::vector<GeneInput> genes = ingest_genes(*gin, reads, vcf, fasta, io);
-    // one contiguous gene range per device, no exchange between shards
+    // one contiguous gene range per device, no exchange between shards; a device's range is cut
+    // further so that several host threads pack in parallel, while its phase calls run one after the other
     const size_t n_dev = ctxs.size();
-    const std::vector<size_t> cut = partition_genes(genes, n_dev);
-    std::vector<std::unique_ptr<mph_batch>> batches(n_dev);
-    std::vector<mph_result*> results(n_dev, nullptr);
-    std::vector<std::exception_ptr> errs(n_dev);
+    uint64_t total_reads = 0;
+    for (auto& g : genes) total_reads += g.reads.size();
+    size_t per_dev = 1;
+    if (total_reads > 500000 * n_dev)
+      per_dev = std::min<size_t>(4, std::max<size_t>(1, std::thread::hardware_concurrency() / n_dev));
+    if (const char* e = getenv("MPH_PACK_THREADS")) per_dev = size_t(std::max(1, atoi(e)));
+    const size_t n_shards = n_dev * per_dev;
+    const std::vector<size_t> cut = partition_genes(genes, n_shards);
+    std::vector<std::unique_ptr<mph_batch>> batches(n_shards);
+    std::vector<mph_result*> results(n_shards, nullptr);
+    std::vector<std::exception_ptr> errs(n_shards);
+    std::vector<std::mutex> dev_mu(n_dev);
+    std::vector<mph_timing> acc(n_dev, mph_timing{});  // a device's timing is the sum over its shards
+    auto add_timing = [](mph_timing& a, const mph_timing& t) {
+      a.h2d_ms += t.h2d_ms; a.k1_ms += t.k1_ms; a.k2_ms += t.k2_ms; a.k3_ms += t.k3_ms; a.k4_ms += t.k4_ms; a.d2h_ms += t.d2h_ms;
+      a.residue_ms += t.residue_ms; a.total_ms += t.total_ms; a.replay_ms += t.replay_ms; a.h2d_bytes += t.h2d_bytes; a.d2h_bytes += t.d2h_bytes;
+      a.windows += t.windows; a.read_windows += t.read_windows; a.windows_enumerated += t.windows_enumerated; a.n_interesting += t.n_interesting;
+      a.n_records += t.n_records; a.kernel_launches += t.kernel_launches; a.n_replay_units += t.n_replay_units;
+    };
     auto shard = [&](size_t k) {
       try {
         Packer packer(window_len, mode);
@@ -1095,24 +1111,28 @@ static void run_somatic_files(const std::vector<mph_ctx*>& ctxs, const char* bam
         batches[k].reset(new mph_batch);
         batches[k]->b = std::move(packer.batch());
         finish_batch(batches[k].get(), false);
-        phase_batch_impl(ctxs[k], batches[k].get(), &results[k]);
+        std::lock_guard<std::mutex> lk(dev_mu[k / per_dev]);  // a context is not re-entrant
+        phase_batch_impl(ctxs[k / per_dev], batches[k].get(), &results[k]);
+        add_timing(acc[k / per_dev], ctxs[k / per_dev]->timing);
+        batches[k].reset();
       } catch (...) {
         errs[k] = std::current_exception();
       }
     };
-    if (n_dev == 1) {
+    if (n_shards == 1) {
       shard(0);
     } else {
       std::vector<std::thread> th;
-      for (size_t k = 0; k < n_dev; ++k) th.emplace_back(shard, k);
+      for (size_t k = 0; k < n_shards; ++k) th.emplace_back(shard, k);
       for (auto& t : th) t.join();
     }
+    for (size_t dv = 0; dv < n_dev; ++dv) ctxs[dv]->timing = acc[dv];
     std::vector<std::unique_ptr<mph_result>> holders;
     for (auto r : results) holders.emplace_back(r);
     for (auto& e : errs)
       if (e) std::rethrow_exception(e);
     int hw = 0;
-    for (size_t k = 0; k < n_dev; ++k)  // ordered concatenation; the TSV header goes out with the first row only
+    for (size_t k = 0; k < n_shards; ++k)  // ordered concatenation; the TSV header goes out with the first row only
       if (mph_result_write(results[k], fd_fa, fd_tsv, fd_n, &hw) != MPH_OK) throw std::runtime_error(g_last_error);
   } catch (...) {
     close_all();
