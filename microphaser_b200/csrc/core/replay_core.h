@@ -44,6 +44,7 @@ typedef struct {
   const MphVar* vars; const MphSegment* segs; const uint32_t* seg_chunk0;
   const uint32_t* stopmap; const uint8_t* ref;
   const uint32_t* dq_init;  // arena of initial column lists
+  uint32_t batch;           // somatic only: iterations that neither change the columns nor emit a window are folded into the next one that does
   uint32_t mode;            // 0 somatic, 1 normal (src/normal_microphasing.rs: every re-offered copy of a read is kept, no quality test)
   const uint8_t* tx_id_bytes; const uint32_t* tx_id_off;  // normal mode: record id of the reference window
   uint32_t* win_depth; unsigned long long* win_id;        // normal mode outputs
@@ -276,6 +277,69 @@ MPH_HD void mph_replay_tx(const MphReplayCtx& c, const MphReplayTx& t) {
     last_window_vars = 0;
     uint64_t old_offset = sg.off0, old_end = (uint64_t)sg.off0 + sg.ewl;
     bool reached_end = false;
+    bool deferred = false;   // folded iterations are waiting to be offered
+    uint32_t pushed_s = 0;   // forward strand: window start of the last iteration whose reads were offered
+    MphGeom g_prev = mph_geom(sg, 0);
+    // cleanup_reads (:259-278, call sites :1255-1262)
+    auto do_cleanup = [&](const MphGeom& gg) {
+      uint32_t w = 0;
+      for (uint32_t o = 0; o < n_obs; ++o) {
+        const uint32_t r = o_read[o];
+        // somatic: cleanup_reads(splice_side_offset + 1) (:1257); normal: cleanup_reads(splice_side_offset) (normal_microphasing.rs:1001)
+        const bool keep = rev ? c.read_start[r] < gg.s + (normal ? 0u : 1u) : c.read_end[r] >= gg.e;
+        if (keep) {
+          if (w != o) { o_read[w] = r; o_hap[w] = o_hap[o]; o_frame[w] = o_frame[o]; o_flags[w] = o_flags[o]; }
+          if (normal) o_last[r - t.read_lo] = w;  // entries of one read keep their order
+          ++w;
+        } else if (normal) {
+          o_last[r - t.read_lo] = 0xFFFFFFFFu;
+        } else {
+          in_mat[r - t.read_lo] = 0;
+        }
+      }
+      n_obs = w;
+    };
+    // candidate reads (:1191-1249) and push_read (:297-343); `lo` = smallest start that is offered
+    auto do_push = [&](const MphGeom& gg, uint32_t lo) {
+      const uint32_t r0 = mph_u32_lb(c.read_start, t.read_lo, t.read_hi, lo);
+      const uint32_t r1 = mph_u32_lb(c.read_start, r0, t.read_hi, gg.s + 1u);
+      for (uint32_t r = r0; r < r1; ++r) {
+        if (c.read_end[r] < gg.e) continue;
+        if (normal) {
+          // push_read of the normal mode (:301-331): no `contains`, columns numbered oldest-first, nothing is rejected;
+          // consecutive copies of a read with the same haplotype share one entry
+          uint64_t hap = 0;
+          uint32_t fr0 = 0;
+          uint8_t fl0 = 0;
+          for (uint32_t i = 0; i < ncols; ++i) mph_rp_update(c, t, r, i, dq[i], &hap, &fr0, &fl0, &err);
+          const uint32_t e = o_last[r - t.read_lo];
+          if (e != 0xFFFFFFFFu && o_hap[e] == hap) { o_frame[e] += 1; continue; }
+          if (n_obs >= t.obs_cap) { err |= MPH_E_REPLAY_INPUT; continue; }
+          o_read[n_obs] = r; o_hap[n_obs] = hap; o_frame[n_obs] = 1; o_flags[n_obs] = 0;
+          o_last[r - t.read_lo] = n_obs;
+          ++n_obs;
+          continue;
+        }
+        if (rev) {
+          // `contains` (:281-294): an observation with the same start and qname is already in the matrix
+          bool dup = in_mat[r - t.read_lo] != 0;
+          if (!dup && (c.read_flags[r] & MPH_RF_PARTNER)) {
+            const uint32_t q = mph_rp_partner(c, r);
+            dup = q != 0xFFFFFFFFu && q >= t.read_lo && q < t.read_hi && in_mat[q - t.read_lo] != 0;
+          }
+          if (dup) continue;
+        }
+        uint64_t hap = 0;
+        uint32_t frame = 0;
+        uint8_t fl = 0;
+        for (uint32_t i = 0; i < ncols; ++i) mph_rp_update(c, t, r, i, dq[ncols - 1 - i], &hap, &frame, &fl, &err);
+        if (fl & 1) continue;  // rejected at push (:338)
+        if (n_obs >= t.obs_cap) { err |= MPH_E_REPLAY_INPUT; continue; }
+        o_read[n_obs] = r; o_hap[n_obs] = hap; o_frame[n_obs] = frame; o_flags[n_obs] = fl;
+        in_mat[r - t.read_lo] = 1;
+        ++n_obs;
+      }
+    };
     for (uint32_t k = 0; k < sg.n_iter; ++k) {
       const uint64_t offset = rev ? (uint64_t)sg.off0 - k : (uint64_t)sg.off0 + k;
       const MphGeom g = mph_geom(sg, k);
@@ -299,68 +363,36 @@ MPH_HD void mph_replay_tx(const MphReplayCtx& c, const MphReplayTx& t) {
       else deleted_vars = cnt(g.e, old_end);
       if (is_last_exon_window) reached_end = true;
       if (panicked) { c.seg_err[si] = k + 1; break; }
-      // cleanup_reads (:259-278, call sites :1255-1262)
-      {
-        uint32_t w = 0;
-        for (uint32_t o = 0; o < n_obs; ++o) {
-          const uint32_t r = o_read[o];
-          // somatic: cleanup_reads(splice_side_offset + 1) (:1257); normal: cleanup_reads(splice_side_offset) (normal_microphasing.rs:1001)
-          const bool keep = rev ? c.read_start[r] < g.s + (normal ? 0u : 1u) : c.read_end[r] >= g.e;
-          if (keep) {
-            if (w != o) { o_read[w] = r; o_hap[w] = o_hap[o]; o_frame[w] = o_frame[o]; o_flags[w] = o_flags[o]; }
-            if (normal) o_last[r - t.read_lo] = w;  // entries of one read keep their order
-            ++w;
-          } else if (normal) {
-            o_last[r - t.read_lo] = 0xFFFFFFFFu;
-          } else {
-            in_mat[r - t.read_lo] = 0;
-          }
-        }
-        n_obs = w;
+      // Folding (somatic mode): an iteration that neither adds nor removes a column and is not an enumerated window only
+      // offers reads; offering them later - all at once, just before the next iteration that does something - gives the
+      // same matrix, because a read offered at a folded iteration and still alive afterwards passes the same tests against
+      // the same columns. The first two iterations are never folded (the candidate range changes shape there).
+      const uint64_t skip_cnt = nvars - added_vars;  // wraps like the release build: nothing is added then
+      const uint32_t n_new_now = skip_cnt <= nvars ? (uint32_t)(nvars - skip_cnt) : 0u;
+      const bool emit_now = k >= sg.k_first && (k - sg.k_first) % sg.k_stride == 0 && (k - sg.k_first) / sg.k_stride < sg.n_win;
+      const bool fold = c.batch && !normal && k >= 2 && !emit_now && n_new_now == 0 && deleted_vars == 0 && !is_short;
+      if (fold) {
+        deferred = true;
+        g_prev = g;
+        last_window_vars = nvars;
+        old_offset = g.s;
+        old_end = g.e;
+        continue;
       }
+      if (deferred && deleted_vars > 0) {  // the folded reads must meet the columns as they were before this iteration's shrink_left
+        do_cleanup(g_prev);
+        do_push(g_prev, rev ? (g_prev.s > sg.K ? g_prev.s - sg.K : 0u) : pushed_s + 1u);
+        pushed_s = g_prev.s;
+      }
+      deferred = false;
+      do_cleanup(g);
       if (!shrink_left(deleted_vars)) { c.seg_err[si] = k + 1; break; }
-      // candidate reads (:1191-1249) and push_read (:297-343)
       {
         const bool wide = rev || offset == (uint64_t)sg.exon_start + sg.ceo;
-        const uint32_t lo = wide ? (g.s > sg.K ? g.s - sg.K : 0u) : g.s;
-        const uint32_t r0 = mph_u32_lb(c.read_start, t.read_lo, t.read_hi, lo);
-        const uint32_t r1 = mph_u32_lb(c.read_start, r0, t.read_hi, g.s + 1u);
-        for (uint32_t r = r0; r < r1; ++r) {
-          if (c.read_end[r] < g.e) continue;
-          if (normal) {
-            // push_read of the normal mode (:301-331): no `contains`, columns numbered oldest-first, nothing is rejected;
-            // consecutive copies of a read with the same haplotype share one entry
-            uint64_t hap = 0;
-            uint32_t fr0 = 0;
-            uint8_t fl0 = 0;
-            for (uint32_t i = 0; i < ncols; ++i) mph_rp_update(c, t, r, i, dq[i], &hap, &fr0, &fl0, &err);
-            const uint32_t e = o_last[r - t.read_lo];
-            if (e != 0xFFFFFFFFu && o_hap[e] == hap) { o_frame[e] += 1; continue; }
-            if (n_obs >= t.obs_cap) { err |= MPH_E_REPLAY_INPUT; continue; }
-            o_read[n_obs] = r; o_hap[n_obs] = hap; o_frame[n_obs] = 1; o_flags[n_obs] = 0;
-            o_last[r - t.read_lo] = n_obs;
-            ++n_obs;
-            continue;
-          }
-          if (rev) {
-            // `contains` (:281-294): an observation with the same start and qname is already in the matrix
-            bool dup = in_mat[r - t.read_lo] != 0;
-            if (!dup && (c.read_flags[r] & MPH_RF_PARTNER)) {
-              const uint32_t q = mph_rp_partner(c, r);
-              dup = q != 0xFFFFFFFFu && q >= t.read_lo && q < t.read_hi && in_mat[q - t.read_lo] != 0;
-            }
-            if (dup) continue;
-          }
-          uint64_t hap = 0;
-          uint32_t frame = 0;
-          uint8_t fl = 0;
-          for (uint32_t i = 0; i < ncols; ++i) mph_rp_update(c, t, r, i, dq[ncols - 1 - i], &hap, &frame, &fl, &err);
-          if (fl & 1) continue;  // rejected at push (:338)
-          if (n_obs >= t.obs_cap) { err |= MPH_E_REPLAY_INPUT; continue; }
-          o_read[n_obs] = r; o_hap[n_obs] = hap; o_frame[n_obs] = frame; o_flags[n_obs] = fl;
-          in_mat[r - t.read_lo] = 1;
-          ++n_obs;
-        }
+        uint32_t lo = wide ? (g.s > sg.K ? g.s - sg.K : 0u) : g.s;
+        if (!wide && c.batch && !normal && k >= 2) lo = pushed_s + 1u;  // everything since the last offered start
+        do_push(g, lo);
+        pushed_s = g.s;
       }
       // newly collected variants (:1280-1296): the window's variants in collection order minus the first nvars - added_vars
       {
@@ -393,6 +425,10 @@ MPH_HD void mph_replay_tx(const MphReplayCtx& c, const MphReplayTx& t) {
       if (is_short) break;
     }
     if (panicked) break;
+    if (deferred) {  // folded iterations at the end of the exon: their reads may survive into the next one
+      do_cleanup(g_prev);
+      do_push(g_prev, rev ? (g_prev.s > sg.K ? g_prev.s - sg.K : 0u) : pushed_s + 1u);
+    }
   }
   if (err) MPH_RP_OR(&c.counters[MPH_RP_CTR_ERR], err);
 }

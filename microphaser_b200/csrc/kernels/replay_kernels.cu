@@ -171,6 +171,116 @@ __global__ void __launch_bounds__(RP_WARPS * 32) k_replay(const DeviceBatch d) {
     bool reached_end = false;
     uint32_t prev_va = vs_lo, prev_vb = vs_lo;
     uint32_t emit_k = sg.k_first, emit_i = 0;  // next enumerated window
+    bool deferred = false;            // folded iterations are waiting to be offered
+    uint32_t pushed_s = 0;            // forward strand: window start of the last iteration whose reads were offered
+    uint32_t prev_s = 0, prev_e = 0;  // geometry of the last folded iteration
+    // cleanup_reads (:259-278): in-place compaction, a tile is read completely before it is written
+    auto do_cleanup = [&](uint32_t gs, uint32_t ge) {
+     if (n_obs && (rev ? key_bound > gs : key_bound < ge)) {
+      uint32_t w = 0, kb = rev ? 0u : 0xFFFFFFFFu;
+      for (uint32_t base = 0; base < n_obs; base += 32) {
+        const uint32_t o = base + lane;
+        const bool valid = o < n_obs;
+        uint32_t r = 0, key = 0, fr = 0;
+        uint64_t hp = 0;
+        uint8_t fl = 0;
+        if (valid) { r = o_read[o]; key = o_key[o]; hp = o_hap[o]; fr = o_frame[o]; fl = o_flags[o]; }
+        const bool keep = valid && (rev ? key < gs + 1u : key >= ge);
+        if (valid && !keep) in_mat[r] = 0;
+        const unsigned bal = __ballot_sync(FULL, keep);
+        __syncwarp();
+        if (keep) {
+          const uint32_t p = w + __popc(bal & ((1u << lane) - 1));
+          o_read[p] = r; o_key[p] = key; o_hap[p] = hp; o_frame[p] = fr; o_flags[p] = fl;
+          kb = rev ? max(kb, key) : min(kb, key);
+        }
+        w += __popc(bal);
+        __syncwarp();
+      }
+      n_obs = w;
+      key_bound = rev ? __reduce_max_sync(FULL, kb) : __reduce_min_sync(FULL, kb);
+    }
+    };
+    // candidate reads (:1191-1249) and push_read (:297-343); `lo` = smallest start that is offered
+    auto do_push = [&](uint32_t gs, uint32_t ge, uint32_t lo) {
+      warp_lb2(rs, r_lo, r_hi, lo, gs + 1u, &cur_lo, &cur_hi, lane);
+      if (cur_hi < cur_lo) cur_hi = cur_lo;
+      for (uint32_t base4 = cur_lo; base4 < cur_hi; base4 += 128) {
+       // the loads of four tiles are issued before any of them is processed
+       uint32_t en4[4];
+       uint8_t im4[4], rf4[4];
+#pragma unroll
+       for (int j = 0; j < 4; ++j) {
+         const uint32_t rj = base4 + 32 * j + lane;
+         const bool in = rj < cur_hi;
+         en4[j] = in ? re[rj] : 0u;
+         im4[j] = (in && rev) ? in_mat[rj] : (uint8_t)0;
+         rf4[j] = (in && rev) ? rf[rj] : (uint8_t)0;
+       }
+#pragma unroll
+       for (int j = 0; j < 4; ++j) {
+        const uint32_t base = base4 + 32 * j;
+        if (base >= cur_hi) break;
+        const uint32_t r = base + lane;
+        bool cand = r < cur_hi && en4[j] >= ge;
+        if (cand && rev) {
+          // `contains` (:281-294): the read itself or the read sharing its (start, qname) is in the matrix already
+          bool dup = im4[j] != 0;
+          if (!dup && (rf4[j] & MPH_RF_PARTNER)) {
+            const uint32_t q = mph_rp_partner(c, r);
+            if (q != NONE && q >= r_lo && q < r_hi) {
+              dup = in_mat[q] != 0;
+              if (!dup && q < r && q >= cur_lo && re[q] >= ge) {  // offered just before r in this same iteration
+                uint64_t hq = 0;
+                uint32_t fq = 0;
+                uint8_t lq = 0;
+                for (uint32_t i = 0; i < ncols; ++i) mph_rp_update(c, t, q, i, sh.dq[ncols - 1 - i], &hq, &fq, &lq, &err);
+                dup = !(lq & 1);
+              }
+            }
+          }
+          cand = !dup;
+        }
+        uint64_t hap = 0;
+        uint32_t frame = 0;
+        uint8_t fl = 0;
+        if (cand) {
+          for (uint32_t i = 0; i < ncols; ++i) mph_rp_update(c, t, r, i, sh.dq[ncols - 1 - i], &hap, &frame, &fl, &err);
+          if (fl & 1) cand = false;  // rejected at push (:338)
+        }
+        const unsigned bal = __ballot_sync(FULL, cand);
+        const uint32_t n_in = __popc(bal);
+        bool drop = false;  // uniform
+        if (n_in && n_obs + n_in > o_cap) {
+          if (o_hap == sh.o_hap && n_obs + n_in <= t.obs_cap) {  // move the list to its global scratch slice
+            uint64_t* g_hap = d.o_hap + t.obs_off;
+            uint32_t *g_read = d.o_read + t.obs_off, *g_key = d.o_key + t.obs_off, *g_frame = d.o_frame + t.obs_off;
+            uint8_t* g_flags = d.o_flags + t.obs_off;
+            for (uint32_t o = lane; o < n_obs; o += 32) { g_hap[o] = o_hap[o]; g_read[o] = o_read[o]; g_key[o] = o_key[o]; g_frame[o] = o_frame[o]; g_flags[o] = o_flags[o]; }
+            o_hap = g_hap; o_read = g_read; o_key = g_key; o_frame = g_frame; o_flags = g_flags;
+            o_cap = t.obs_cap;
+            __syncwarp();
+          } else {
+            err |= MPH_E_REPLAY_INPUT;
+            drop = true;
+          }
+        }
+        if (n_in && !drop) {
+          uint32_t kk = rev ? 0u : 0xFFFFFFFFu;
+          if (cand) {
+            const uint32_t p = n_obs + __popc(bal & ((1u << lane) - 1));
+            kk = rev ? rs[r] : en4[j];
+            o_read[p] = r; o_key[p] = kk; o_hap[p] = hap; o_frame[p] = frame; o_flags[p] = fl;
+            in_mat[r] = 1;
+          }
+          if (rev) key_bound = n_obs ? max(key_bound, __reduce_max_sync(FULL, kk)) : __reduce_max_sync(FULL, kk);
+          else key_bound = n_obs ? min(key_bound, __reduce_min_sync(FULL, kk)) : __reduce_min_sync(FULL, kk);
+          n_obs += n_in;
+        }
+        __syncwarp();
+       }
+      }
+    };
     for (uint32_t k = 0; k < sg.n_iter; ++k) {
       const uint64_t offset = rev ? (uint64_t)sg.off0 - k : (uint64_t)sg.off0 + k;
       const MphGeom g = mph_geom(sg, k);
@@ -202,116 +312,38 @@ __global__ void __launch_bounds__(RP_WARPS * 32) k_replay(const DeviceBatch d) {
         if (lane == 0) d.seg_err[si] = k + 1;
         break;
       }
-      // cleanup_reads (:259-278): in-place compaction, a tile is read completely before it is written
-      if (n_obs && (rev ? key_bound > g.s : key_bound < g.e)) {
-        uint32_t w = 0, kb = rev ? 0u : 0xFFFFFFFFu;
-        for (uint32_t base = 0; base < n_obs; base += 32) {
-          const uint32_t o = base + lane;
-          const bool valid = o < n_obs;
-          uint32_t r = 0, key = 0, fr = 0;
-          uint64_t hp = 0;
-          uint8_t fl = 0;
-          if (valid) { r = o_read[o]; key = o_key[o]; hp = o_hap[o]; fr = o_frame[o]; fl = o_flags[o]; }
-          const bool keep = valid && (rev ? key < g.s + 1u : key >= g.e);
-          if (valid && !keep) in_mat[r] = 0;
-          const unsigned bal = __ballot_sync(FULL, keep);
-          __syncwarp();
-          if (keep) {
-            const uint32_t p = w + __popc(bal & ((1u << lane) - 1));
-            o_read[p] = r; o_key[p] = key; o_hap[p] = hp; o_frame[p] = fr; o_flags[p] = fl;
-            kb = rev ? max(kb, key) : min(kb, key);
-          }
-          w += __popc(bal);
-          __syncwarp();
-        }
-        n_obs = w;
-        key_bound = rev ? __reduce_max_sync(FULL, kb) : __reduce_min_sync(FULL, kb);
+      // Folding: an iteration that neither adds nor removes a column and is not an enumerated window only offers reads;
+      // offering them all at once just before the next iteration that does something gives the same matrix (a read
+      // offered at a folded iteration and still alive afterwards passes the same tests against the same columns). The
+      // first two iterations are never folded: the candidate range changes shape there. core/replay_core.h states it.
+      const uint64_t skip_cnt = nvars - added_vars;  // wraps like the release build: nothing is added then
+      const uint32_t n_new_now = skip_cnt <= nvars ? (uint32_t)(nvars - skip_cnt) : 0u;
+      const bool emit_now = k == emit_k && emit_i < sg.n_win;
+      if (k >= 2 && !emit_now && n_new_now == 0 && deleted_vars == 0 && !is_short) {
+        deferred = true;
+        prev_s = g.s; prev_e = g.e;
+        last_window_vars = nvars;
+        old_offset = g.s;
+        old_end = g.e;
+        continue;
       }
+      if (deferred && deleted_vars > 0) {  // the folded reads must meet the columns as they were before this iteration's shrink_left
+        do_cleanup(prev_s, prev_e);
+        do_push(prev_s, prev_e, rev ? (prev_s > sg.K ? prev_s - sg.K : 0u) : pushed_s + 1u);
+        pushed_s = prev_s;
+      }
+      deferred = false;
+      do_cleanup(g.s, g.e);
       if (!shrink_left(deleted_vars)) {
         if (lane == 0) d.seg_err[si] = k + 1;
         break;
       }
-      // candidate reads (:1191-1249) and push_read (:297-343)
       {
         const bool wide = rev || offset == (uint64_t)sg.exon_start + sg.ceo;
-        const uint32_t lo = wide ? (g.s > sg.K ? g.s - sg.K : 0u) : g.s;
-        warp_lb2(rs, r_lo, r_hi, lo, g.s + 1u, &cur_lo, &cur_hi, lane);
-        if (cur_hi < cur_lo) cur_hi = cur_lo;
-        for (uint32_t base4 = cur_lo; base4 < cur_hi; base4 += 128) {
-         // the loads of four tiles are issued before any of them is processed
-         uint32_t en4[4];
-         uint8_t im4[4], rf4[4];
-#pragma unroll
-         for (int j = 0; j < 4; ++j) {
-           const uint32_t rj = base4 + 32 * j + lane;
-           const bool in = rj < cur_hi;
-           en4[j] = in ? re[rj] : 0u;
-           im4[j] = (in && rev) ? in_mat[rj] : (uint8_t)0;
-           rf4[j] = (in && rev) ? rf[rj] : (uint8_t)0;
-         }
-#pragma unroll
-         for (int j = 0; j < 4; ++j) {
-          const uint32_t base = base4 + 32 * j;
-          if (base >= cur_hi) break;
-          const uint32_t r = base + lane;
-          bool cand = r < cur_hi && en4[j] >= g.e;
-          if (cand && rev) {
-            // `contains` (:281-294): the read itself or the read sharing its (start, qname) is in the matrix already
-            bool dup = im4[j] != 0;
-            if (!dup && (rf4[j] & MPH_RF_PARTNER)) {
-              const uint32_t q = mph_rp_partner(c, r);
-              if (q != NONE && q >= r_lo && q < r_hi) {
-                dup = in_mat[q] != 0;
-                if (!dup && q < r && q >= cur_lo && re[q] >= g.e) {  // offered just before r in this same iteration
-                  uint64_t hq = 0;
-                  uint32_t fq = 0;
-                  uint8_t lq = 0;
-                  for (uint32_t i = 0; i < ncols; ++i) mph_rp_update(c, t, q, i, sh.dq[ncols - 1 - i], &hq, &fq, &lq, &err);
-                  dup = !(lq & 1);
-                }
-              }
-            }
-            cand = !dup;
-          }
-          uint64_t hap = 0;
-          uint32_t frame = 0;
-          uint8_t fl = 0;
-          if (cand) {
-            for (uint32_t i = 0; i < ncols; ++i) mph_rp_update(c, t, r, i, sh.dq[ncols - 1 - i], &hap, &frame, &fl, &err);
-            if (fl & 1) cand = false;  // rejected at push (:338)
-          }
-          const unsigned bal = __ballot_sync(FULL, cand);
-          const uint32_t n_in = __popc(bal);
-          bool drop = false;  // uniform
-          if (n_in && n_obs + n_in > o_cap) {
-            if (o_hap == sh.o_hap && n_obs + n_in <= t.obs_cap) {  // move the list to its global scratch slice
-              uint64_t* g_hap = d.o_hap + t.obs_off;
-              uint32_t *g_read = d.o_read + t.obs_off, *g_key = d.o_key + t.obs_off, *g_frame = d.o_frame + t.obs_off;
-              uint8_t* g_flags = d.o_flags + t.obs_off;
-              for (uint32_t o = lane; o < n_obs; o += 32) { g_hap[o] = o_hap[o]; g_read[o] = o_read[o]; g_key[o] = o_key[o]; g_frame[o] = o_frame[o]; g_flags[o] = o_flags[o]; }
-              o_hap = g_hap; o_read = g_read; o_key = g_key; o_frame = g_frame; o_flags = g_flags;
-              o_cap = t.obs_cap;
-              __syncwarp();
-            } else {
-              err |= MPH_E_REPLAY_INPUT;
-              drop = true;
-            }
-          }
-          if (n_in && !drop) {
-            uint32_t kk = rev ? 0u : 0xFFFFFFFFu;
-            if (cand) {
-              const uint32_t p = n_obs + __popc(bal & ((1u << lane) - 1));
-              kk = rev ? rs[r] : en4[j];
-              o_read[p] = r; o_key[p] = kk; o_hap[p] = hap; o_frame[p] = frame; o_flags[p] = fl;
-              in_mat[r] = 1;
-            }
-            if (rev) key_bound = n_obs ? max(key_bound, __reduce_max_sync(FULL, kk)) : __reduce_max_sync(FULL, kk);
-            else key_bound = n_obs ? min(key_bound, __reduce_min_sync(FULL, kk)) : __reduce_min_sync(FULL, kk);
-            n_obs += n_in;
-          }
-          __syncwarp();
-         }
-        }
+        uint32_t lo = wide ? (g.s > sg.K ? g.s - sg.K : 0u) : g.s;
+        if (!wide && k >= 2) lo = pushed_s + 1u;  // everything since the last offered start
+        do_push(g.s, g.e, lo);
+        pushed_s = g.s;
       }
       // newly collected variants (:1280-1296) and extend_right (:232-256)
       {
@@ -431,6 +463,10 @@ __global__ void __launch_bounds__(RP_WARPS * 32) k_replay(const DeviceBatch d) {
       old_offset = g.s;
       old_end = g.e;
       if (is_short) break;
+    }
+    if (!panicked && deferred && si + 1 < t.seg_hi) {  // folded iterations at the end of the exon: their reads may survive into the next one
+      do_cleanup(prev_s, prev_e);
+      do_push(prev_s, prev_e, rev ? (prev_s > sg.K ? prev_s - sg.K : 0u) : pushed_s + 1u);
     }
     if (panicked || __any_sync(FULL, (err & (MPH_E_REPLAY_PANIC | MPH_E_VARS_PER_WINDOW)) != 0)) break;
   }

@@ -77,6 +77,7 @@ inline void run_replay(const Batch& b, const std::vector<MphCall>& calls, const 
   c.read_flags = b.read_flags.data(); c.bases = b.bases.data(); c.cigars = b.cigars.data(); c.call_S = S.data(); c.call_B = B.data();
   c.pairs = pairs.data(); c.n_pairs = uint32_t(pairs.size() / 2); c.vars = b.vars.data(); c.segs = b.segs.data(); c.seg_chunk0 = b.seg_chunk0.data();
   c.stopmap = b.stopmap.data(); c.ref = b.ref.data(); c.dq_init = b.replay_dq.data();
+  c.batch = getenv("MPH_EMU_NO_FOLD") ? 0u : 1u;  // the kernels fold; MPH_EMU_NO_FOLD=1 runs the literal per-iteration replay
   c.mode = uint32_t(mode); c.tx_id_bytes = b.tx_id_bytes.data(); c.tx_id_off = b.tx_id_off.data();
   c.win_depth = mode == 1 ? raw.win_depth.data() : nullptr;
   c.win_id = mode == 1 ? reinterpret_cast<unsigned long long*>(raw.win_id.data()) : nullptr;
