@@ -72,6 +72,10 @@ def test_pipelined_stages_match_single_stage(product, mode, monkeypatch):
     assert records(one) == records(many)
     assert t_one["windows"] == t_many["windows"] and t_one["read_windows"] == t_many["read_windows"]
     assert t_many["kernel_launches"] >= 7 * t_one["kernel_launches"]
+    # pageable host buffers take the other copy schedule (stage s + 1 is queued after the kernels of stage s)
+    pageable = m.Batch.synthetic(n_transcripts=600 if mode == "normal" else 2000, coverage=60.0, seed=0x4D500004, pin=False)
+    again = ctx.phase_batch(pageable)
+    assert records(again) == records(one)
     if mode == "somatic":
         assert t_one["n_replay_units"] > 0, "the synthetic workload is expected to contain irregular transcripts"
     ctx.close()
