@@ -7,6 +7,7 @@
 #include <condition_variable>
 #include <deque>
 #include <mutex>
+#include <unordered_map>
 #include <atomic>
 #include <chrono>
 #include <cstdarg>
@@ -118,6 +119,7 @@ struct mph_ctx {
   DevBuf<MphHap> hap0, hapx, iw_hap0;
   DevBuf<unsigned long long> sums, win_id;
   mph_timing timing = {};
+  std::unordered_map<const void*, size_t> pinned_dl;  // page-locked download buffers: data pointer -> bytes
   std::vector<PhaseRaw> raws;  // download buffers per stage, reused across calls (no page faults after the first)
   // secondary path: normal-peptidome hash set (open addressing, 5-bit packed peptides)
   DevBuf<unsigned long long> set_table;
@@ -365,6 +367,26 @@ void run_kernels(mph_ctx* c) {
   CU(cudaGetLastError());
 }
 
+// resize of a download buffer that keeps it page-locked (device -> host copies into pageable memory go through a bounce
+// buffer at a fraction of the link speed). The registration follows the allocation: dropped before a growth, renewed after.
+template <class V>
+void resize_pinned(mph_ctx* c, V& v, size_t n) {
+  if (n > v.capacity()) {
+    auto it = c->pinned_dl.find(v.data());
+    if (it != c->pinned_dl.end()) {
+      cudaHostUnregister(const_cast<void*>(it->first));
+      c->pinned_dl.erase(it);
+    }
+    v.reserve(n + n / 4);  // the sizes of consecutive calls differ a little: avoid a re-registration per call
+  }
+  v.resize(n);
+  const size_t bytes = v.capacity() * sizeof(v[0]);
+  if (bytes >= (size_t(1) << 16) && !c->pinned_dl.count(v.data())) {
+    if (cudaHostRegister(v.data(), bytes, cudaHostRegisterDefault) == cudaSuccess) c->pinned_dl[v.data()] = bytes;
+    else cudaGetLastError();
+  }
+}
+
 // device -> host copy of what the kernels produced for the current slice; re-runs the kernels when an arena was too small
 void fetch_stage(mph_ctx* c, const Stage& s, PhaseRaw& raw, uint64_t* n_iw_total) {
   const Batch& b = c->cur->b;
@@ -395,7 +417,8 @@ void fetch_stage(mph_ctx* c, const Stage& s, PhaseRaw& raw, uint64_t* n_iw_total
   if (raw.err & MPH_E_REPLAY_PANIC) throw Fatal("bug: read starts right of variant");
   if (raw.err) throw std::logic_error("device error bits " + std::to_string(raw.err));
   const uint32_t n_iw = ctr[mphk::CTR_NIW], n_hist = ctr[mphk::CTR_HIST], n_seq = ctr[mphk::CTR_SEQ];
-  raw.iw.resize(n_iw); raw.iw_out.resize(n_iw); raw.iw_hap0.resize(n_iw); raw.hist.resize(n_hist); raw.hapx.resize(n_hist); raw.seq.resize(n_seq);
+  resize_pinned(c, raw.iw, n_iw); resize_pinned(c, raw.iw_out, n_iw); resize_pinned(c, raw.iw_hap0, n_iw); resize_pinned(c, raw.hist, n_hist);
+  resize_pinned(c, raw.hapx, n_hist); resize_pinned(c, raw.seq, n_seq);
   CU(cudaEventRecord(c->ev[0], c->stream));
   if (n_iw) {
     CU(cudaMemcpyAsync(raw.iw.data(), c->iw.p, n_iw * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
@@ -409,8 +432,8 @@ void fetch_stage(mph_ctx* c, const Stage& s, PhaseRaw& raw, uint64_t* n_iw_total
   if (n_seq) CU(cudaMemcpyAsync(raw.seq.data(), c->seq.p, n_seq, cudaMemcpyDeviceToHost, c->stream));
   const bool has_replay = c->d.n_replay != 0;
   const uint32_t n_vl = (c->d.rp1 > c->d.rp0) ? std::min<uint32_t>(ctr[mphk::CTR_VLIST], c->d.vlist_cap) : 0;
-  raw.iw_voff.resize(has_replay ? n_iw : 0);
-  raw.vlist.resize(n_vl);
+  resize_pinned(c, raw.iw_voff, has_replay ? n_iw : 0);
+  resize_pinned(c, raw.vlist, n_vl);
   if (has_replay && n_iw) CU(cudaMemcpyAsync(raw.iw_voff.data(), c->iw_voff.p, n_iw * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
   if (n_vl) CU(cudaMemcpyAsync(raw.vlist.data(), c->vlist.p, size_t(n_vl) * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
   raw.seg_base = uint32_t(s.lo.segs);
@@ -423,8 +446,8 @@ void fetch_stage(mph_ctx* c, const Stage& s, PhaseRaw& raw, uint64_t* n_iw_total
   const bool normal_mode = b.mode == 1;
   const size_t nw = size_t(s.hi.windows - s.lo.windows);
   raw.win_base = uint32_t(s.lo.windows);
-  raw.win_depth.resize(normal_mode ? nw : 0);
-  raw.win_id.resize(normal_mode ? nw : 0);
+  resize_pinned(c, raw.win_depth, normal_mode ? nw : 0);
+  resize_pinned(c, raw.win_id, normal_mode ? nw : 0);
   if (normal_mode && nw) {
     CU(cudaMemcpyAsync(raw.win_depth.data(), c->win_depth.p + s.lo.windows, nw * 4, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaMemcpyAsync(raw.win_id.data(), c->win_id.p + s.lo.windows, nw * 8, cudaMemcpyDeviceToHost, c->stream));
@@ -818,6 +841,8 @@ void mph_ctx_destroy(mph_ctx* c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   for (auto& e : c->ev)
     if (e) cudaEventDestroy(e);
+  for (auto& kv : c->pinned_dl) cudaHostUnregister(const_cast<void*>(kv.first));
+  c->pinned_dl.clear();
   for (auto& e : c->ev_copy)
     if (e) cudaEventDestroy(e);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
