@@ -26,6 +26,13 @@ struct CliSpec {
   bool value;
 };
 
+// BGZF inflate / record decode threads of the alignment reader: MPH_IO_THREADS, default 1 here (the library's file
+// drivers default to min(cores, 8))
+inline unsigned io_threads_env() {
+  const char* e = getenv("MPH_IO_THREADS");
+  return e ? unsigned(std::max(1, atoi(e))) : 1u;
+}
+
 inline CliArgs parse_cli(int argc, char** argv, int first, const std::vector<CliSpec>& specs) {
   CliArgs a;
   for (int i = first; i < argc; ++i) {
@@ -64,7 +71,7 @@ inline int run_somatic(int argc, char** argv, const PhaseFn& phase) {
                                         {"normal-output", 'n', true}, {"unsupported-allele-warning-only", 'u', false}, {"verbose", 'v', false}});
   if (a.pos.size() != 1 || !a.opt.count("ref") || !a.opt.count("variants"))
     throw std::runtime_error("error: The following required arguments were not provided: <tumor-sample> --ref <FILE> --variants <FILE>");
-  mphio::BamFile bam(a.pos[0]);
+  mphio::BamFile bam(a.pos[0], io_threads_env());
   mphio::VcfFile vcf(a.opt["variants"]);
   mphio::FastaIndexed fasta(a.opt["ref"]);
   Outputs o;
@@ -102,7 +109,7 @@ inline int run_normal(int argc, char** argv, const PhaseFn& phase) {
                                         {"unsupported-allele-warning-only", 'u', false}, {"verbose", 'v', false}});
   if (a.pos.size() != 1 || !a.opt.count("ref") || !a.opt.count("variants"))
     throw std::runtime_error("error: The following required arguments were not provided: <normal-sample> --ref <FILE> --variants <FILE>");
-  mphio::BamFile bam(a.pos[0]);
+  mphio::BamFile bam(a.pos[0], io_threads_env());
   mphio::VcfFile vcf(a.opt["variants"]);
   mphio::FastaIndexed fasta(a.opt["ref"]);
   Outputs o;

@@ -36,6 +36,15 @@ class ReadBuffer {
 
   explicit ReadBuffer(mphio::BamFile& bam) : bam_(bam) {
     by_tid_.resize(bam.ref_names.size());
+    // the arenas hold most of the uncompressed file (BAM compresses about 3-4x): one reservation instead of repeated
+    // growth, which would copy and page-fault several hundred MB (untouched reserved pages cost nothing)
+    if (bam.file_bytes()) {
+      const size_t est = bam.file_bytes() * 4;
+      qual_.reserve(est * 6 / 10);
+      seq_.reserve(est * 3 / 10);
+      cig_.reserve(est / 40);
+    }
+    if (bam.inflate_threads() > 1) { load_parallel(bam.inflate_threads()); return; }
     mphio::BamRecord r;
     while (bam.next(r)) {
       if (r.tid < 0 || size_t(r.tid) >= by_tid_.size()) continue;
@@ -49,6 +58,89 @@ class ReadBuffer {
       by_tid_[r.tid].push_back(x);
     }
   }
+
+ private:
+  // One inflated batch at a time: a serial scan of the length prefixes finds the record boundaries and the arena
+  // offsets of every record; the arenas grow once per batch and a few threads decode the records straight into them.
+  void load_parallel(unsigned threads) {
+    std::vector<uint8_t> buf, chunk;
+    std::vector<size_t> offs, seq_at, qual_at, cig_at;
+    std::vector<Rec> recs;
+    bool more = true;
+    while (more) {
+      more = bam_.next_chunk(chunk);
+      if (more) {
+        if (buf.empty()) buf.swap(chunk);
+        else buf.insert(buf.end(), chunk.begin(), chunk.end());
+      }
+      offs.clear(); seq_at.clear(); qual_at.clear(); cig_at.clear();
+      size_t o = 0, n_seq = seq_.size(), n_qual = qual_.size(), n_cig = cig_.size();
+      while (o + 4 <= buf.size()) {
+        int32_t bs;
+        memcpy(&bs, buf.data() + o, 4);
+        if (bs < 32) throw mphio::IoError("corrupt BAM record");
+        if (o + 4 + size_t(bs) > buf.size()) break;
+        uint16_t n_cigar;
+        int32_t l_seq;
+        memcpy(&n_cigar, buf.data() + o + 4 + 12, 2);
+        memcpy(&l_seq, buf.data() + o + 4 + 16, 4);
+        if (l_seq < 0 || 32 + size_t(buf[o + 4 + 8]) + 4 * size_t(n_cigar) + (size_t(l_seq) + 1) / 2 + size_t(l_seq) > size_t(bs))
+          throw mphio::IoError("corrupt BAM record");
+        offs.push_back(o); seq_at.push_back(n_seq); qual_at.push_back(n_qual); cig_at.push_back(n_cig);
+        n_seq += (size_t(l_seq) + 1) / 2; n_qual += size_t(l_seq); n_cig += n_cigar;
+        o += 4 + size_t(bs);
+      }
+      if (!more && o != buf.size()) throw mphio::IoError("truncated BAM record");
+      seq_.resize(n_seq); qual_.resize(n_qual); cig_.resize(n_cig);
+      recs.resize(offs.size());
+      const unsigned nt = offs.size() < 4096 ? 1u : threads;
+      auto work = [&](unsigned ti) {
+        const size_t i0 = offs.size() * ti / nt, i1 = offs.size() * (ti + 1) / nt;
+        for (size_t i = i0; i < i1; ++i) {
+          const uint8_t* p = buf.data() + offs[i] + 4;
+          auto i32 = [&](size_t q) { int32_t v; memcpy(&v, p + q, 4); return v; };
+          auto u16 = [&](size_t q) { uint16_t v; memcpy(&v, p + q, 2); return v; };
+          Rec x;
+          x.tid = i32(0);
+          x.pos = i32(4);
+          const uint8_t l_read_name = p[8];
+          x.mapq = p[9];
+          x.n_cigar = u16(12);
+          x.flag = u16(14);
+          x.l_seq = uint32_t(i32(16));
+          size_t q = 32;
+          x.qname_hash = fnv1a_bytes(reinterpret_cast<const char*>(p + q), l_read_name ? l_read_name - 1 : 0);
+          q += l_read_name;
+          x.cig_off = cig_at[i];
+          if (x.n_cigar) memcpy(cig_.data() + x.cig_off, p + q, 4 * size_t(x.n_cigar));
+          int64_t e = x.pos;  // CigarStringView::end_pos(): reference-consuming operations M, D, N, =, X
+          for (uint32_t z = 0; z < x.n_cigar; ++z) {
+            const uint32_t c = cig_[x.cig_off + z], op = c & 15;
+            if (op == mphio::C_M || op == mphio::C_D || op == mphio::C_N || op == mphio::C_EQ || op == mphio::C_X) e += c >> 4;
+          }
+          x.end = uint32_t(e);
+          q += 4 * size_t(x.n_cigar);
+          const size_t sb = (x.l_seq + 1) / 2;
+          x.seq_off = seq_at[i];
+          memcpy(seq_.data() + x.seq_off, p + q, sb);
+          q += sb;
+          x.qual_off = qual_at[i];
+          memcpy(qual_.data() + x.qual_off, p + q, x.l_seq);
+          recs[i] = x;
+        }
+      };
+      std::vector<std::thread> pool;
+      for (unsigned ti = 1; ti < nt; ++ti) pool.emplace_back(work, ti);
+      work(0);
+      for (auto& t : pool) t.join();
+      for (const Rec& x : recs)
+        if (x.tid >= 0 && size_t(x.tid) < by_tid_.size()) by_tid_[x.tid].push_back(x);
+      if (o == buf.size()) buf.clear();
+      else buf.erase(buf.begin(), buf.begin() + long(o));
+    }
+  }
+
+ public:
   const uint8_t* seq4(const Rec& r) const { return seq_.data() + r.seq_off; }
   const uint8_t* qual(const Rec& r) const { return qual_.data() + r.qual_off; }
   const uint32_t* cigar(const Rec& r) const { return cig_.data() + r.cig_off; }

@@ -62,6 +62,11 @@ class BgzfReader {
   explicit BgzfReader(const std::string& path, unsigned threads = 1) : path_(path), threads_(threads ? threads : 1) {
     f_ = fopen(path.c_str(), "rb");
     if (!f_) throw IoError("cannot open " + path);
+    if (fseek(f_, 0, SEEK_END) == 0) {
+      const long sz = ftell(f_);
+      if (sz > 0) file_bytes_ = size_t(sz);
+      fseek(f_, 0, SEEK_SET);
+    }
     if (threads_ > 1) producer_ = std::thread([this] { produce(); });
   }
   ~BgzfReader() {
@@ -77,6 +82,22 @@ class BgzfReader {
   }
   BgzfReader(const BgzfReader&) = delete;
   BgzfReader& operator=(const BgzfReader&) = delete;
+
+  unsigned threads() const { return threads_; }
+  size_t file_bytes() const { return file_bytes_; }  // compressed size (0 if unknown), a hint for buffer reservations
+  // hands over everything that is inflated and unread (the rest of the current block / the next batch); false at EOF
+  bool next_chunk(std::vector<uint8_t>& out) {
+    if (pos_ == block_.size() && !(threads_ > 1 ? next_batch() : next_block())) return false;
+    if (pos_ == 0) {
+      out.swap(block_);
+      block_.clear();
+    } else {
+      out.assign(block_.begin() + long(pos_), block_.end());
+      block_.clear();
+    }
+    pos_ = 0;
+    return true;
+  }
 
   // read exactly n bytes; returns false on clean EOF at a record boundary (0 bytes read)
   bool read(void* dst, size_t n) {
@@ -237,6 +258,7 @@ class BgzfReader {
   std::vector<uint8_t> cbuf_, block_;
   size_t pos_ = 0;
   unsigned threads_ = 1;
+  size_t file_bytes_ = 0;
   std::thread producer_;
   std::mutex mu_;
   std::condition_variable cv_;
@@ -364,6 +386,12 @@ struct BamFile {
       ref_lens.push_back(l_ref);
     }
   }
+
+  unsigned inflate_threads() const { return rd_.threads(); }
+  size_t file_bytes() const { return rd_.file_bytes(); }
+  // raw record stream after the header, in chunks (a record may straddle two chunks): for callers that frame and
+  // parse the records themselves, in parallel
+  bool next_chunk(std::vector<uint8_t>& out) { return rd_.next_chunk(out); }
 
   // next alignment record; false on EOF
   bool next(BamRecord& r) {

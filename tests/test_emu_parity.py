@@ -92,3 +92,30 @@ def test_emulated_normal_mode_matches_oracle_on_synthetic(emu_bin, oracle_bin, p
     assert (ro.returncode == 0) == (rp.returncode == 0), (ro.stderr.decode()[-300:], rp.stderr.decode()[-300:])
     if ro.returncode == 0:
         assert read_outputs(str(o), "normal") == read_outputs(str(p), "normal")
+
+
+@pytest.mark.parametrize("case", ["reverse_somatic", "splice_forward_somatic"])
+def test_threaded_alignment_reader_gives_the_same_records(emu_bin, case, tmp_path, monkeypatch):
+    """MPH_IO_THREADS > 1: BGZF blocks are inflated and BAM records decoded by several threads (the library's file drivers
+    do that by default); the output must not change."""
+    monkeypatch.setenv("MPH_IO_THREADS", "4")
+    d = os.path.join(GOLDEN, case)
+    fa = materialize_reference(d, str(tmp_path))
+    res = run_cli(emu_bin, d, str(tmp_path), ref=fa)
+    assert res.returncode == 0, res.stderr.decode()
+    for name in sorted(os.listdir(os.path.join(d, "expected"))):
+        assert open(tmp_path / name, "rb").read() == open(os.path.join(d, "expected", name), "rb").read(), name
+
+
+def test_threaded_alignment_reader_on_a_large_file(emu_bin, oracle_bin, tmp_path, monkeypatch):
+    """Enough records for several decode threads per batch and records that straddle batch boundaries."""
+    d = str(tmp_path / "in")
+    synth.generate(d, synth.Params(seed=99, n_genes=12, coverage=120.0, exons=(6, 8)))
+    o, p = tmp_path / "o", tmp_path / "p"
+    o.mkdir()
+    p.mkdir()
+    assert run_cli(oracle_bin, d, str(o)).returncode == 0
+    monkeypatch.setenv("MPH_IO_THREADS", "4")
+    rp = run_cli(emu_bin, d, str(p))
+    assert rp.returncode == 0, rp.stderr.decode()
+    assert read_outputs(str(o)) == read_outputs(str(p))
