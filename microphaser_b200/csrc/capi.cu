@@ -1116,12 +1116,20 @@ static void run_somatic_files(const std::vector<mph_ctx*>& ctxs, const char* bam
     if (total_reads > 500000 * n_dev)
       per_dev = std::min<size_t>(4, std::max<size_t>(1, std::thread::hardware_concurrency() / n_dev));
     if (const char* e = getenv("MPH_PACK_THREADS")) per_dev = size_t(std::max(1, atoi(e)));
-    const size_t n_shards = n_dev * per_dev;
+    // more shards than packing threads when the input is large: a shard's records are written and freed as soon as all
+    // earlier shards are out, which bounds the memory held in records (the normal mode writes one per window)
+    const uint64_t reads_per_shard = mode == 1 ? 2000000ull : 8000000ull;
+    size_t n_shards = std::max<size_t>(n_dev * per_dev, size_t((total_reads + reads_per_shard - 1) / reads_per_shard));
+    n_shards = (n_shards + n_dev - 1) / n_dev * n_dev;  // the same number of consecutive shards per device
+    const size_t shards_per_dev = n_shards / n_dev;
     const std::vector<size_t> cut = partition_genes(genes, n_shards);
-    std::vector<std::unique_ptr<mph_batch>> batches(n_shards);
     std::vector<mph_result*> results(n_shards, nullptr);
-    std::vector<std::exception_ptr> errs(n_shards);
+    std::vector<uint8_t> done(n_shards, 0);
     std::vector<std::mutex> dev_mu(n_dev);
+    std::mutex out_mu;
+    size_t next_out = 0;
+    int hw = 0;
+    std::exception_ptr first_err;
     std::vector<mph_timing> acc(n_dev, mph_timing{});  // a device's timing is the sum over its shards
     auto add_timing = [](mph_timing& a, const mph_timing& t) {
       a.h2d_ms += t.h2d_ms; a.k1_ms += t.k1_ms; a.k2_ms += t.k2_ms; a.k3_ms += t.k3_ms; a.k4_ms += t.k4_ms; a.d2h_ms += t.d2h_ms;
@@ -1129,36 +1137,59 @@ static void run_somatic_files(const std::vector<mph_ctx*>& ctxs, const char* bam
       a.windows += t.windows; a.read_windows += t.read_windows; a.windows_enumerated += t.windows_enumerated; a.n_interesting += t.n_interesting;
       a.n_records += t.n_records; a.kernel_launches += t.kernel_launches; a.n_replay_units += t.n_replay_units;
     };
-    auto shard = [&](size_t k) {
-      try {
-        Packer packer(window_len, mode);
-        pack_genes(genes, cut[k], cut[k + 1], packer);
-        batches[k].reset(new mph_batch);
-        batches[k]->b = std::move(packer.batch());
-        finish_batch(batches[k].get(), false);
-        std::lock_guard<std::mutex> lk(dev_mu[k / per_dev]);  // a context is not re-entrant
-        phase_batch_impl(ctxs[k / per_dev], batches[k].get(), &results[k]);
-        add_timing(acc[k / per_dev], ctxs[k / per_dev]->timing);
-        batches[k].reset();
-      } catch (...) {
-        errs[k] = std::current_exception();
+    // ordered concatenation: shard k goes out when shards 0 .. k-1 are out; the TSV header goes out with the first row only.
+    // After a failure nothing later than the failing shard is written (the reference stops at that point, too).
+    auto shard_finished = [&](size_t k, std::exception_ptr err) {
+      std::lock_guard<std::mutex> lk(out_mu);
+      done[k] = 1;
+      if (err && !first_err) first_err = err;
+      while (next_out < n_shards && done[next_out]) {
+        if (results[next_out]) {
+          if (!first_err && mph_result_write(results[next_out], fd_fa, fd_tsv, fd_n, &hw) != MPH_OK && !first_err)
+            first_err = std::make_exception_ptr(std::runtime_error(g_last_error));
+          delete results[next_out];
+          results[next_out] = nullptr;
+        }
+        ++next_out;
       }
     };
-    if (n_shards == 1) {
-      shard(0);
+    std::atomic<size_t> next_shard{0};
+    auto worker = [&] {
+      for (;;) {
+        const size_t k = next_shard.fetch_add(1);
+        if (k >= n_shards) return;
+        std::exception_ptr err;
+        try {
+          {
+            std::lock_guard<std::mutex> lk(out_mu);
+            if (first_err) { done[k] = 1; continue; }
+          }
+          Packer packer(window_len, mode);
+          pack_genes(genes, cut[k], cut[k + 1], packer);
+          std::unique_ptr<mph_batch> batch(new mph_batch);
+          batch->b = std::move(packer.batch());
+          finish_batch(batch.get(), false);
+          const size_t dv = k / shards_per_dev;
+          std::lock_guard<std::mutex> lk(dev_mu[dv]);  // a context is not re-entrant
+          phase_batch_impl(ctxs[dv], batch.get(), &results[k]);
+          add_timing(acc[dv], ctxs[dv]->timing);
+        } catch (...) {
+          err = std::current_exception();
+        }
+        shard_finished(k, err);
+      }
+    };
+    const size_t n_workers = std::min(n_shards, n_dev * per_dev);
+    if (n_workers == 1) {
+      worker();
     } else {
       std::vector<std::thread> th;
-      for (size_t k = 0; k < n_shards; ++k) th.emplace_back(shard, k);
+      for (size_t w = 0; w < n_workers; ++w) th.emplace_back(worker);
       for (auto& t : th) t.join();
     }
     for (size_t dv = 0; dv < n_dev; ++dv) ctxs[dv]->timing = acc[dv];
-    std::vector<std::unique_ptr<mph_result>> holders;
-    for (auto r : results) holders.emplace_back(r);
-    for (auto& e : errs)
-      if (e) std::rethrow_exception(e);
-    int hw = 0;
-    for (size_t k = 0; k < n_shards; ++k)  // ordered concatenation; the TSV header goes out with the first row only
-      if (mph_result_write(results[k], fd_fa, fd_tsv, fd_n, &hw) != MPH_OK) throw std::runtime_error(g_last_error);
+    for (auto r : results) delete r;
+    if (first_err) std::rethrow_exception(first_err);
   } catch (...) {
     close_all();
     throw;
