@@ -238,3 +238,20 @@ def test_c_abi_packer_entry_points_match_oracle_on_synthetic(abi_host, oracle_bi
                         os.path.join(d, "annotation.gtf"), str(p / "out.fa"), str(p / "out.tsv"), str(p / "out.normal.fa")], stderr=subprocess.PIPE, timeout=600)
     assert r.returncode == 0, r.stderr.decode()
     assert read_outputs(str(o)) == read_outputs(str(p))
+
+
+@pytest.mark.parametrize("sub", ["somatic", "normal"])
+def test_file_driver_shards_do_not_change_output(product, oracle_bin, sub, tmp_path, monkeypatch):
+    """The file drivers cut the genes into shards that are packed by parallel host threads, phased one after the other and
+    written in order as they complete; three shards with a threaded alignment reader must give the oracle's bytes."""
+    d = str(tmp_path / "in")
+    synth.generate(d, synth.Params(seed=2718, n_genes=9, coverage=30.0, indel_frac=0.15, multiallelic_frac=0.1, intron_len=(30, 600)))
+    o, p = tmp_path / "o", tmp_path / "p"
+    o.mkdir()
+    p.mkdir()
+    assert run_cli(oracle_bin, d, str(o), subcommand=sub).returncode == 0
+    monkeypatch.setenv("MPH_PACK_THREADS", "3")
+    monkeypatch.setenv("MPH_IO_THREADS", "4")
+    rp = run_cli(product[1], d, str(p), subcommand=sub)
+    assert rp.returncode == 0, rp.stderr.decode()
+    assert read_outputs(str(o), sub) == read_outputs(str(p), sub)
