@@ -592,7 +592,7 @@ void launch_window_hist(const DeviceBatch& d, cudaStream_t st) {
   if (d.mode == 1) return launch_window_hist_normal(d, st);
   k_window_hist<<<(nc + K2_WARPS - 1) / K2_WARPS, K2_WARPS * 32, 0, st>>>(d);
   // windows with more distinct haplotypes than a lane table holds (rare): one warp per window
-  k_window_hist_wide<<<148, K2_WARPS * 32, 0, st>>>(d);
+  k_window_hist_wide<<<148 * 8, K2_WARPS * 32, 0, st>>>(d);
 }
 void launch_assemble(const DeviceBatch& d, cudaStream_t st) {
   if (d.c1 > d.c0 && d.mode == 1) launch_assemble_normal(d, st);
