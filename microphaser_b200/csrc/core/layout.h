@@ -45,6 +45,8 @@ enum {
   MPH_SF_LAST_EXON = 8,
   MPH_SF_HAS_FS = 16,     // the gene carries frameshifting variants: every iteration is a window
   MPH_SF_KEEP_PENULT = 64,  // the next exon's only window is first and last: its junction merge reads this exon's last-but-one window (:1401-1405)
+  MPH_SF_JOIN_HEAD = 128,   // the junction at the exon's first window can produce records (a variant on either side): its list is kept
+  MPH_SF_JOIN_TAIL = 256,   // the same for the junction after the exon's last window (and the last-but-one with KEEP_PENULT)
   MPH_SF_REPLAY = 32,     // the transcript goes through the serial replay (core/replay_core.h), not the closed form
 };
 

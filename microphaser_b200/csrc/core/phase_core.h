@@ -158,11 +158,15 @@ MPH_HD MphCall mph_call_read(const MphRead& r, const uint8_t* bases, const uint3
 }
 
 // windows whose haplotype list a splice-junction merge can read (:1401-1405,1497-1510): the first and the last window
-// of an exon, every window when frameshifts keep several reading frames alive, and the last-but-one window when the
-// next exon stores its only window on the "previous exon" side
+// of an exon (the last-but-one when the next exon stores its only window on the "previous exon" side) - but only at
+// junctions that can produce a record, i.e. with a variant in one of the two windows (the packer decides; a merge of
+// reference-only lists writes nothing, :1801-1810,1887) - and every window of a short exon or when frameshifts keep
+// several reading frames alive
 MPH_HD bool mph_is_boundary(const MphSegment& g, uint32_t i) {
-  if (g.flags & MPH_SF_HAS_FS) return true;
-  if (i == 0 || i + 1 == g.n_win) return true;
+  if (g.flags & (MPH_SF_HAS_FS | MPH_SF_SHORT)) return true;
+  if (i == 0 && (g.flags & MPH_SF_JOIN_HEAD)) return true;
+  if (!(g.flags & MPH_SF_JOIN_TAIL)) return false;
+  if (i + 1 == g.n_win) return true;
   return (g.flags & MPH_SF_KEEP_PENULT) && i + 2 == g.n_win;
 }
 

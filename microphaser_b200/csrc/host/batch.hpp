@@ -381,6 +381,26 @@ class Packer {
         }
       }
       tm.seg_hi = uint32_t(b_.segs.size());
+      // junctions that can produce records: a variant inside one of the two windows whose lists the merge reads
+      {
+        auto window_has_var = [&](const MphSegment& sg, uint32_t i) {
+          if (i >= sg.n_win) return false;
+          const MphGeom gw = mph_geom(sg, sg.k_first + i * sg.k_stride);
+          const uint32_t a = mph_var_lb(b_.vars.data(), sg.var_lo, sg.var_hi, gw.s);
+          return a < sg.var_hi && b_.vars[a].pos < gw.e;
+        };
+        for (uint32_t si = tm.seg_lo; si < tm.seg_hi; ++si) {
+          MphSegment& sg = b_.segs[si];
+          if (si == tm.seg_lo) sg.flags |= MPH_SF_JOIN_HEAD;      // no junction before the first exon; its list is kept as before
+          if (si + 1 == tm.seg_hi) sg.flags |= MPH_SF_JOIN_TAIL;  // nor after the last one
+          if (si == tm.seg_lo) continue;
+          MphSegment& pa = b_.segs[si - 1];
+          const bool always = tx_replay || ((sg.flags | pa.flags) & (MPH_SF_HAS_FS | MPH_SF_SHORT)) || sg.n_win == 0 || pa.n_win == 0;
+          bool active = always || window_has_var(sg, 0) || window_has_var(pa, pa.n_win - 1);
+          if (!active && (pa.flags & MPH_SF_KEEP_PENULT) && pa.n_win >= 2) active = window_has_var(pa, pa.n_win - 2);
+          if (active) { sg.flags |= MPH_SF_JOIN_HEAD; pa.flags |= MPH_SF_JOIN_TAIL; }
+        }
+      }
       if (tx_replay && tm.seg_hi > tm.seg_lo) {
         // split the transcript into units at the exon boundaries no observation crosses; the matrix columns at a
         // unit start come from a read-free pass over the window loop's column bookkeeping (:1119-1178,1280-1296)

@@ -648,11 +648,14 @@ class Residue {
         }
         const bool at_splice_side = fwd ? offset - current_exon_offset == sg.exon_start
                                         : offset + exon_window_len + current_exon_offset == sg.exon_end;
-        if (at_splice_side && !is_first_exon) {
+        // a junction without a variant in either window merges reference-only lists and writes nothing (:1801-1810,1887):
+        // the packer marks the others (MPH_SF_JOIN_HEAD) and only their lists are kept
+        const bool junction = at_splice_side && !is_first_exon && (sg.flags & MPH_SF_JOIN_HEAD);
+        if (junction) {
           if (prev_partial || hap_partial) throw Unsupported("transcript " + tm.id + ": splice merge needs a window that is not at an exon boundary");
           prev_partial = hap_partial = false;
         }
-        if (at_splice_side && !is_first_exon)
+        if (junction)
           splice_merge(t, sg, offset, is_short_exon, is_last_exon, is_last_exon_window, exon_rest, frameshifts, ff, hap_vec, prev_hap_vec, out);
         (void)window_len;
       }
