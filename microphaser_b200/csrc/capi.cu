@@ -199,8 +199,13 @@ std::vector<Stage> plan_stages(const mph_batch* mb, unsigned want) {
   std::vector<Stage> out;
   if (want < 1) want = 1;
   size_t g = 0;
-  // the first two stages are shorter (0.35 and 0.7 of a regular one): the host residue can start earlier
-  auto weight = [](unsigned s) { return s == 0 ? 0.35 : (s == 1 ? 0.7 : 1.0); };
+  // the first two and the last two stages are shorter (0.35 and 0.7 of a regular one): the host residue can start
+  // earlier and less of it is left when the last copy has finished
+  auto weight = [want](unsigned s) {
+    const unsigned e = want - 1 - s;
+    const unsigned m = s < e ? s : e;
+    return m == 0 ? 0.35 : (m == 1 ? 0.7 : 1.0);
+  };
   double total_w = 0, acc_w = 0;
   for (unsigned s = 0; s < want; ++s) total_w += weight(s);
   for (unsigned s = 0; s < want && g < n_genes; ++s) {
@@ -659,9 +664,9 @@ void phase_stages(mph_ctx* c, const std::vector<Stage>& stages, bool copied, mph
 // host buffers in, records out: the pipelined path
 void phase_batch_impl(mph_ctx* c, const mph_batch* mb, mph_result** out) {
   prepare(c, mb);
-  // stages of about 4 M reads: long enough to keep the copy engine at full rate, short enough to hide all but the first
+  // stages of about 3.5 M reads: long enough to keep the copy engine at full rate, short enough to hide all but the first
   // copy and the last residue
-  unsigned want = unsigned(std::min<uint64_t>(12, std::max<uint64_t>(1, mb->b.n_reads() / 4000000)));
+  unsigned want = unsigned(std::min<uint64_t>(12, std::max<uint64_t>(1, mb->b.n_reads() / 3500000)));
   if (const char* e = getenv("MPH_STAGES")) want = unsigned(std::max(1, atoi(e)));
   const std::vector<Stage> stages = plan_stages(mb, want);
   c->kernels_done = false;
