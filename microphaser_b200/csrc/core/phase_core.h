@@ -120,31 +120,54 @@ MPH_HD int mph_read_pos(const uint32_t* cig, uint32_t n_cig, uint32_t l_seq, uin
   return 0;
 }
 
+// Packed read record (16-B aligned in the `bases` arena), what K1 needs of one alignment:
+//   byte 0  format: bit 0 = bases are 2-bit codes (A C G T only; else BAM 4-bit codes), bit 1 = the positions with
+//           qual < 10 are a list (else a bitmask)
+//   byte 1  list length (format bit 1)
+//   then    the bases: ceil(l_seq/4) or ceil(l_seq/2) B, first base in the high bits
+//   then    the low-quality positions: `list length` bytes (one position each), or ceil(l_seq/8) B with bit i <=> base i
+MPH_HD uint32_t mph_rec_bases_bytes(uint8_t fmt, uint32_t l_seq) { return (fmt & 1u) ? (l_seq + 3u) >> 2 : (l_seq + 1u) >> 1; }
+// qual[i] < 10 (:82-84,99-101)
+MPH_HD bool mph_rec_low(const uint8_t* rec, uint32_t l_seq, uint32_t i) {
+  const uint8_t fmt = rec[0];
+  const uint8_t* lq = rec + 2 + mph_rec_bases_bytes(fmt, l_seq);
+  if (fmt & 2u) {
+    const uint32_t n = rec[1];
+    for (uint32_t x = 0; x < n; ++x)
+      if (lq[x] == i) return true;
+    return false;
+  }
+  return (lq[i >> 3] >> (i & 7u)) & 1u;
+}
+// BAM 4-bit code of base i
+MPH_HD uint8_t mph_rec_base4(const uint8_t* rec, uint32_t i) {
+  const uint8_t* sq = rec + 2;
+  if (rec[0] & 1u) return (uint8_t)(1u << ((sq[i >> 2] >> (6u - 2u * (i & 3u))) & 3u));
+  const uint8_t b = sq[i >> 1];
+  return (i & 1u) ? (uint8_t)(b & 15u) : (uint8_t)(b >> 4);
+}
+
 // supports_variant / bad_quality for every variant with pos in [start, end) of one read.
-// `bases` points at the read's packed record: ceil(l_seq/2) B of 4-bit codes (high nibble first),
-// then ceil(l_seq/8) B with bit i set iff qual[i] < 10.
+// `bases` points at the read's packed record (above).
 MPH_HD MphCall mph_call_read(const MphRead& r, const uint8_t* bases, const uint32_t* cig, const MphVar* vars, bool use_qual = true) {
   MphCall c;
   c.S = 0;
   c.B = 0;
   const uint32_t nv = r.nv;
   if (nv == 0) return c;
-  const uint8_t* lowq = bases + ((r.l_seq + 1u) >> 1);
   for (uint32_t j = 0; j < nv; ++j) {
     const MphVar v = vars[r.vlo + j];
     bool sup = false;
     if (v.kind == MPH_SNV) {
       const uint32_t rel = v.pos - r.start;  // raw reference offset indexes the *query* qualities (:82-84,99-101)
       bool low = false;
-      if (use_qual && rel < r.l_seq) low = (lowq[rel >> 3] >> (rel & 7u)) & 1u;  // normal mode has no base-quality test (normal_microphasing.rs:43-52)
+      if (use_qual && rel < r.l_seq) low = mph_rec_low(bases, r.l_seq, rel);  // normal mode has no base-quality test (normal_microphasing.rs:43-52)
       if (low) {
         c.B |= (uint64_t)1 << j;
       } else {
         uint32_t q;
         if (mph_read_pos(cig, r.n_cig, r.l_seq, r.start, v.pos, &q) && q < r.l_seq) {
-          const uint8_t b = bases[q >> 1];
-          const uint8_t code = (q & 1u) ? (b & 15u) : (b >> 4);
-          sup = code == v.alt4;
+          sup = mph_rec_base4(bases, q) == v.alt4;
         }
       }
     } else {

@@ -96,15 +96,11 @@ MPH_HD void mph_rp_eval(const MphReplayCtx& c, uint32_t r, uint32_t v, bool* sup
   const uint32_t ncig = c.vr_ncig[e];
   const uint32_t* cig = c.cigars + c.vr_cig_off[e];
   if (var.kind == MPH_SNV) {
-    const uint8_t* b = c.bases + (size_t)soff * 16;
-    const uint8_t* lowq = b + ((l_seq + 1u) >> 1);
+    const uint8_t* rec = c.bases + (size_t)soff * 16;
     const uint32_t rel = var.pos - start;
-    if (c.mode == 0 && rel < l_seq && ((lowq[rel >> 3] >> (rel & 7u)) & 1u)) { *bad = true; return; }
+    if (c.mode == 0 && rel < l_seq && mph_rec_low(rec, l_seq, rel)) { *bad = true; return; }
     uint32_t q;
-    if (mph_read_pos(cig, ncig, l_seq, start, var.pos, &q) && q < l_seq) {
-      const uint8_t x = b[q >> 1];
-      *sup = ((q & 1u) ? (x & 15u) : (x >> 4)) == var.alt4;
-    }
+    if (mph_read_pos(cig, ncig, l_seq, start, var.pos, &q) && q < l_seq) *sup = mph_rec_base4(rec, q) == var.alt4;
   } else {
     const uint32_t want = var.kind == MPH_INS ? 1u : 2u;
     for (uint32_t i = 0; i < ncig; ++i)

@@ -8,6 +8,7 @@
 #pragma once
 #include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <stdexcept>
@@ -192,13 +193,43 @@ class Packer {
     std::unordered_map<uint64_t, uint32_t> seen;  // (start, qname) -> first read index
     const size_t bases_mark = b_.bases.size(), cigars_mark = b_.cigars.size(), vr_mark = b_.vr_read.size();
     auto add_vr = [&](uint32_t idx, uint32_t vlo, uint32_t nv, const HostRead& r) {
-      // packed record: 4-bit bases then (qual < 10) bits, 16-B aligned
+      // packed record (core/phase_core.h), 16-B aligned: 2-bit bases when the read has only A C G T, the positions with
+      // qual < 10 as a short list when there are few of them (the normal mode never tests qualities: empty list)
       const size_t off = (b_.bases.size() + 15u) & ~size_t(15);
-      const size_t nb = (r.l_seq + 1u) / 2, nq = (r.l_seq + 7u) / 8;
-      b_.bases.resize(off + nb + nq, 0);
-      memcpy(&b_.bases[off], r.seq4, nb);
-      for (uint32_t i = 0; i < r.l_seq; ++i)
-        if (r.qual[i] < 10) b_.bases[off + nb + (i >> 3)] |= uint8_t(1u << (i & 7));
+      static const bool force_wide_format = getenv("MPH_PACK_WIDE") != nullptr;  // test hook: 4-bit bases + bitmask for every read
+      bool acgt = !force_wide_format;
+      for (uint32_t i = 0; i < r.l_seq && acgt; ++i) {
+        const uint8_t c4 = (i & 1u) ? (r.seq4[i >> 1] & 15u) : (r.seq4[i >> 1] >> 4);
+        acgt = c4 == 1 || c4 == 2 || c4 == 4 || c4 == 8;
+      }
+      uint32_t n_low = 0;
+      if (b_.mode == 0)
+        for (uint32_t i = 0; i < r.l_seq; ++i) n_low += r.qual[i] < 10;
+      const bool low_list = b_.mode == 1 || (!force_wide_format && r.l_seq <= 256 && n_low <= 255 && n_low < (r.l_seq + 7u) / 8);
+      const uint8_t fmt = uint8_t((acgt ? 1u : 0u) | (low_list ? 2u : 0u));
+      const size_t nb = mph_rec_bases_bytes(fmt, r.l_seq), nq = low_list ? (b_.mode == 1 ? 0u : n_low) : (r.l_seq + 7u) / 8;
+      b_.bases.resize(off + 2 + nb + nq, 0);
+      uint8_t* rec = &b_.bases[off];
+      rec[0] = fmt;
+      rec[1] = uint8_t(low_list && b_.mode == 0 ? n_low : 0);
+      if (acgt) {
+        for (uint32_t i = 0; i < r.l_seq; ++i) {
+          const uint8_t c4 = (i & 1u) ? (r.seq4[i >> 1] & 15u) : (r.seq4[i >> 1] >> 4);
+          const uint8_t c2 = c4 == 1 ? 0 : (c4 == 2 ? 1 : (c4 == 4 ? 2 : 3));
+          rec[2 + (i >> 2)] |= uint8_t(c2 << (6u - 2u * (i & 3u)));
+        }
+      } else {
+        memcpy(rec + 2, r.seq4, nb);
+      }
+      if (b_.mode == 0) {
+        uint8_t* lq = rec + 2 + nb;
+        uint32_t x = 0;
+        for (uint32_t i = 0; i < r.l_seq; ++i)
+          if (r.qual[i] < 10) {
+            if (low_list) lq[x++] = uint8_t(i);
+            else lq[i >> 3] |= uint8_t(1u << (i & 7));
+          }
+      }
       b_.vr_read.push_back(idx);
       b_.vr_vlo.push_back(vlo);
       b_.vr_seq_off.push_back(uint32_t(off / 16));

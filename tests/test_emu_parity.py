@@ -119,3 +119,16 @@ def test_threaded_alignment_reader_on_a_large_file(emu_bin, oracle_bin, tmp_path
     rp = run_cli(emu_bin, d, str(p))
     assert rp.returncode == 0, rp.stderr.decode()
     assert read_outputs(str(o)) == read_outputs(str(p))
+
+
+@pytest.mark.parametrize("case", ["reverse_somatic", "forward_somatic"])
+def test_wide_read_record_format_gives_the_same_records(emu_bin, case, tmp_path, monkeypatch):
+    """MPH_PACK_WIDE=1 packs every read with 4-bit bases and a quality bitmask (the format of reads that contain other
+    letters than A C G T); the default is 2-bit bases and a short list of low-quality positions."""
+    monkeypatch.setenv("MPH_PACK_WIDE", "1")
+    d = os.path.join(GOLDEN, case)
+    fa = materialize_reference(d, str(tmp_path))
+    res = run_cli(emu_bin, d, str(tmp_path), ref=fa)
+    assert res.returncode == 0, res.stderr.decode()
+    for name in sorted(os.listdir(os.path.join(d, "expected"))):
+        assert open(tmp_path / name, "rb").read() == open(os.path.join(d, "expected", name), "rb").read(), name
