@@ -121,7 +121,7 @@ typedef struct {
   const uint16_t* vr_lseq;
   const uint16_t* vr_ncig;
   const uint8_t* vr_nv;
-  const uint8_t* bases;   uint64_t bases_bytes;   /* 4-bit bases + (qual < 10) bitmask per side-table entry */
+  const uint8_t* bases;   uint64_t bases_bytes;   /* packed read record per side-table entry: format byte, 2-bit or 4-bit bases, low-quality positions (csrc/core/phase_core.h) */
   const uint32_t* cigars; uint64_t n_cigar_ops;
   const void* vars;       /* MphVar[n_vars], 16 B each (csrc/core/layout.h) */
   const void* segments;   /* MphSegment[n_segments], 96 B each */
