@@ -72,26 +72,21 @@ struct ResidueStats {
 
 namespace detail {
 
-inline std::vector<std::string> split_bar(const std::string& s) {
-  std::vector<std::string> out;
-  size_t b = 0;
-  for (;;) {
-    size_t e = s.find('|', b);
-    if (e == std::string::npos) { out.emplace_back(s.substr(b)); break; }
-    out.emplace_back(s.substr(b, e - b));
-    b = e + 1;
+// Walks the '|'-separated fields of a column the way `str::split('|')` does ("" yields one empty field).
+struct BarFields {
+  std::string_view s;
+  size_t pos = 0;
+  bool done = false;
+  explicit BarFields(std::string_view v) : s(v) {}
+  bool next(std::string_view& out) {
+    if (done) return false;
+    const size_t e = s.find('|', pos);
+    if (e == std::string_view::npos) { out = s.substr(pos); done = true; }
+    else { out = s.substr(pos, e - pos); pos = e + 1; }
+    return true;
   }
-  return out;
-}
-inline std::string join_bar(const std::vector<std::string>& v) {
-  std::string s;
-  for (size_t i = 0; i < v.size(); ++i) {
-    if (i) s.push_back('|');
-    s += v[i];
-  }
-  return s;
-}
-inline uint64_t parse_u64(const std::string& p) {
+};
+inline uint64_t parse_u64(std::string_view p) {
   if (p.empty()) throw Fatal("ParseIntError");
   uint64_t v = 0;
   for (char c : p) {
@@ -100,9 +95,31 @@ inline uint64_t parse_u64(const std::string& p) {
   }
   return v;
 }
-inline const std::string& at(const std::vector<std::string>& v, size_t i) {
-  if (i >= v.size()) throw Fatal("index out of bounds");
-  return v[i];
+inline void bar_append(std::string& dst, bool& first, std::string_view field) {
+  if (!first) dst.push_back('|');
+  first = false;
+  dst.append(field);
+}
+// Keeps the (position, aa change) pairs of one record whose position passes `keep` (common.rs:399-478):
+// the walk stops at the first empty position field; indexing the change column past its end panics.
+template <class Keep>
+inline uint32_t merge_fields(std::string_view positions, std::string_view changes, std::string& out_pos, bool& first_pos,
+                             std::string& out_aa, bool& first_aa, Keep keep) {
+  BarFields pf(positions), af(changes);
+  std::string_view p, aa;
+  bool have_aa = af.next(aa);
+  uint32_t kept = 0;
+  while (pf.next(p)) {
+    if (p.empty()) break;
+    if (keep(parse_u64(p))) {
+      if (!have_aa) throw Fatal("index out of bounds");
+      bar_append(out_pos, first_pos, p);
+      bar_append(out_aa, first_aa, aa);
+      ++kept;
+    }
+    have_aa = af.next(aa);
+  }
+  return kept;
 }
 
 // IDRecord::update (common.rs:376-526)
@@ -110,36 +127,17 @@ inline InfoRecord merge_records(const InfoRecord& self, const InfoRecord& rec, b
                                 uint64_t frame, double freq, const std::string& wt_seq, const std::string& mt_seq, uint64_t wlen) {
   InfoRecord o;
   o.id = mphfmt::record_id(reinterpret_cast<const uint8_t*>(mt_seq.data()), mt_seq.size(), tx_id, offset, forward ? 'F' : 'R');
-  auto sp = split_bar(self.somatic_positions), saa = split_bar(self.somatic_aa_change), osaa = split_bar(rec.somatic_aa_change);
-  auto gp = split_bar(self.germline_positions), gaa = split_bar(self.germline_aa_change), ogaa = split_bar(rec.germline_aa_change);
-  std::vector<std::string> s_p, g_p, s_aa, g_aa;
-  uint32_t nvariants = 0, nsom = 0;
-  size_t c = 0;
-  for (auto& p : sp) {
-    if (p.empty()) break;
-    const uint64_t pv = parse_u64(p);
-    if (forward ? (self.offset + offset <= pv) : (self.offset + wlen - offset >= pv)) { s_p.push_back(p); s_aa.push_back(at(saa, c)); ++nsom; ++nvariants; }
-    ++c;
-  }
-  c = 0;
-  for (auto& p : split_bar(rec.somatic_positions)) {
-    if (p.empty()) break;
-    const uint64_t pv = parse_u64(p);
-    if (forward ? (rec.offset + offset >= pv) : (rec.offset + wlen - 3 - offset <= pv)) { s_p.push_back(p); s_aa.push_back(at(osaa, c)); ++nsom; ++nvariants; }
-    ++c;
-  }
-  c = 0;
-  for (auto& p : gp) {
-    if (p.empty()) break;
-    if (self.offset + offset <= parse_u64(p)) { g_p.push_back(p); g_aa.push_back(at(gaa, c)); ++nvariants; }
-    ++c;
-  }
-  c = 0;
-  for (auto& p : split_bar(rec.germline_positions)) {
-    if (p.empty()) break;
-    if (rec.offset >= parse_u64(p) - offset) { g_p.push_back(p); g_aa.push_back(at(ogaa, c)); ++nvariants; }
-    ++c;
-  }
+  bool f_sp = true, f_saa = true, f_gp = true, f_gaa = true;
+  uint32_t nsom = 0;
+  nsom += merge_fields(self.somatic_positions, self.somatic_aa_change, o.somatic_positions, f_sp, o.somatic_aa_change, f_saa,
+                       [&](uint64_t pv) { return forward ? (self.offset + offset <= pv) : (self.offset + wlen - offset >= pv); });
+  nsom += merge_fields(rec.somatic_positions, rec.somatic_aa_change, o.somatic_positions, f_sp, o.somatic_aa_change, f_saa,
+                       [&](uint64_t pv) { return forward ? (rec.offset + offset >= pv) : (rec.offset + wlen - 3 - offset <= pv); });
+  uint32_t nvariants = nsom;
+  nvariants += merge_fields(self.germline_positions, self.germline_aa_change, o.germline_positions, f_gp, o.germline_aa_change, f_gaa,
+                            [&](uint64_t pv) { return self.offset + offset <= pv; });
+  nvariants += merge_fields(rec.germline_positions, rec.germline_aa_change, o.germline_positions, f_gp, o.germline_aa_change, f_gaa,
+                            [&](uint64_t pv) { return rec.offset >= pv - offset; });
   o.tx = self.tx;
   o.offset = forward ? self.offset + offset : rec.offset + wlen + 3 - offset;
   o.frame = frame;
@@ -149,27 +147,26 @@ inline InfoRecord merge_records(const InfoRecord& self, const InfoRecord& rec, b
   o.nsomatic = nsom;
   o.nvariant_sites = self.nvariant_sites + rec.nvariant_sites;
   o.nsomvariant_sites = self.nsomvariant_sites + rec.nsomvariant_sites;
-  std::string vr = self.variant_sites + "|" + rec.variant_sites;
+  // "self|rec" with one leading and one trailing '|' removed (common.rs:497-503)
+  std::string& vr = o.variant_sites;
+  vr.reserve(self.variant_sites.size() + rec.variant_sites.size() + 1);
+  vr = self.variant_sites;
+  vr.push_back('|');
+  vr += rec.variant_sites;
   if (!vr.empty() && vr.front() == '|') vr.erase(0, 1);
   if (!vr.empty() && vr.back() == '|') vr.pop_back();
-  o.variant_sites = vr;
-  o.somatic_positions = join_bar(s_p);
-  o.somatic_aa_change = join_bar(s_aa);
-  o.germline_positions = join_bar(g_p);
-  o.germline_aa_change = join_bar(g_aa);
   o.normal_sequence = wt_seq;
   o.mutant_sequence = mt_seq;
   return o;
 }
 
 // IDRecord::add_freq (common.rs:528-568)
-inline InfoRecord add_freq(const InfoRecord& r, double f) {
-  InfoRecord o = r;
+inline InfoRecord add_freq(InfoRecord r, double f) {
   const uint32_t new_nvar = r.nvar == 0 ? r.nvar : (f > 0.0 ? r.nvar - 1 : r.nvar);
-  o.nsomatic = new_nvar < r.nsomatic ? r.nsomatic - 1 : r.nsomatic;
-  o.nvar = new_nvar;
-  o.freq = r.freq > 0.5 ? r.freq : r.freq + f;
-  return o;
+  r.nsomatic = new_nvar < r.nsomatic ? r.nsomatic - 1 : r.nsomatic;
+  r.nvar = new_nvar;
+  r.freq = r.freq > 0.5 ? r.freq : r.freq + f;
+  return r;
 }
 
 }  // namespace detail
@@ -329,7 +326,7 @@ class Residue {
       }
       double frame_frequency = freq;
       if (shift_is_set && frame == 0) frame = shift_in_window;
-      ff.emplace(frame, std::make_pair(0.0, false));
+      ff.try_emplace(frame, 0.0, false);
       if (shift_in_window == 0) frame_frequency = freq * ff.at(frame).first;
       if (shift_in_window == 0 && haplotype_frame > 0 && frame == 0) frame_frequency = 0.0;
       const bool germ_eq = (h.flags & MPH_HF_GERM_EQ) != 0;
@@ -740,7 +737,7 @@ class Residue {
           else { for (auto it = frameshifts.lower_bound(offset + exon_window_len); it != frameshifts.end(); ++it) active.push_back(*it); }
           for (auto& pf : active) {
             const uint64_t pos = pf.first, frameshift = pf.second;
-            ff.emplace(frameshift, std::make_pair(0.0, false));
+            ff.try_emplace(frameshift, 0.0, false);
             const bool shift_in_window = fwd ? pos >= prev_record.offset : pos < record.offset + exon_window_len;
             const bool somatic_shift = ff.at(frameshift).second;
             const double frameshift_freq = ff.at(frameshift).first;
@@ -761,32 +758,33 @@ class Residue {
               if (fwd) splice_offset = 0;
               else end_offset = 0;
             }
-            auto sub = [](const std::string& s, uint64_t a, uint64_t e) -> std::string {
+            auto sub = [](const std::string& s, uint64_t a, uint64_t e) -> std::string_view {
               if (a > e || e > s.size()) throw Fatal("slice index out of range");
-              return s.substr(size_t(a), size_t(e - a));
+              return std::string_view(s).substr(size_t(a), size_t(e - a));
             };
             while (splice_offset + window_len <= uint64_t(new_mt_sequence.size() - end_offset)) {
-              std::string out_wt_seq;
+              // most windows across a junction are identical in both sequences: compare views, build strings only to emit
+              std::string_view wt_view;
               if (splice_offset + window_len <= uint64_t(new_wt_sequence.size())) {
-                if (fwd) out_wt_seq = sub(new_wt_sequence, splice_offset, splice_offset + window_len);
-                else out_wt_seq = sub(new_wt_sequence, new_wt_sequence.size() - end_offset - size_t(window_len), new_wt_sequence.size() - end_offset);
+                if (fwd) wt_view = sub(new_wt_sequence, splice_offset, splice_offset + window_len);
+                else wt_view = sub(new_wt_sequence, new_wt_sequence.size() - end_offset - size_t(window_len), new_wt_sequence.size() - end_offset);
               }
-              std::string out_mt_seq = fwd ? sub(new_mt_sequence, splice_offset, splice_offset + window_len)
-                                           : sub(new_mt_sequence, new_mt_sequence.size() - end_offset - size_t(window_len),
-                                                 new_mt_sequence.size() - end_offset);
-              if (out_shift > 0 && out_wt_seq == out_mt_seq && somatic_shift) out_wt_seq.clear();
-              if (out_wt_seq == out_mt_seq || (out_wt_seq.empty() && frameshift == 0)) {
+              const std::string_view mt_view = fwd ? sub(new_mt_sequence, splice_offset, splice_offset + window_len)
+                                                   : sub(new_mt_sequence, new_mt_sequence.size() - end_offset - size_t(window_len),
+                                                         new_mt_sequence.size() - end_offset);
+              if (out_shift > 0 && wt_view == mt_view && somatic_shift) wt_view = std::string_view();
+              if (wt_view == mt_view || (wt_view.empty() && frameshift == 0)) {
                 if (fwd) splice_offset += 3;
                 else end_offset += 3;
                 continue;
               }
+              const std::string out_wt_seq(wt_view), out_mt_seq(mt_view);
               const uint64_t out_offset = fwd ? splice_offset : uint64_t(end_offset);
               InfoRecord out_record = fwd ? detail::merge_records(prev_record, record, true, tm.id, out_offset, frameshift, out_freq, out_wt_seq, out_mt_seq, window_len)
                                           : detail::merge_records(record, prev_record, false, tm.id, out_offset, frameshift, out_freq, out_wt_seq, out_mt_seq, window_len);
-              auto id_tuple = std::make_tuple(out_offset, out_mt_seq, out_wt_seq);
-              auto itx = output_map.find(id_tuple);
-              const double old_freq = itx != output_map.end() ? itx->second.rec.freq : 0.0;
-              output_map[id_tuple] = OutVal{out_mt_seq, detail::add_freq(out_record, old_freq), out_wt_seq};
+              auto slot = output_map.try_emplace(std::make_tuple(out_offset, out_mt_seq, out_wt_seq)).first;
+              const double old_freq = slot->second.rec.freq;  // 0.0 in a fresh slot
+              slot->second = OutVal{out_mt_seq, detail::add_freq(std::move(out_record), old_freq), out_wt_seq};
               if (fwd) splice_offset += 3;
               else end_offset += 3;
             }
@@ -798,7 +796,7 @@ class Residue {
       prev_hap_vec = std::move(new_hap_vec);
     } else {
       for (auto& kv : output_map) {
-        const OutVal& v = kv.second;
+        OutVal& v = kv.second;
         if (v.mt != v.wt) {
           OutRecord o;
           if (window_len > v.mt.size()) throw Fatal("slice index out of range");
@@ -809,7 +807,7 @@ class Residue {
             o.wt = v.wt.substr(0, size_t(window_len));
             o.has_wt = true;
           }
-          o.info = v.rec;
+          o.info = std::move(v.rec);  // the map dies with this call
           out.push_back(std::move(o));
         }
       }

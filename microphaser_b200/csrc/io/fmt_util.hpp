@@ -21,19 +21,23 @@ struct Sha1 {
 
   static uint32_t rol(uint32_t v, int s) { return (v << s) | (v >> (32 - s)); }
   void block(const uint8_t* p) {
-    uint32_t w[80];
+    uint32_t w[16];  // rolling message schedule
     for (int i = 0; i < 16; ++i) w[i] = (uint32_t(p[4 * i]) << 24) | (uint32_t(p[4 * i + 1]) << 16) | (uint32_t(p[4 * i + 2]) << 8) | p[4 * i + 3];
-    for (int i = 16; i < 80; ++i) w[i] = rol(w[i - 3] ^ w[i - 8] ^ w[i - 14] ^ w[i - 16], 1);
     uint32_t a = h[0], b = h[1], c = h[2], d = h[3], e = h[4];
-    for (int i = 0; i < 80; ++i) {
-      uint32_t f, k;
-      if (i < 20) { f = (b & c) | (~b & d); k = 0x5A827999u; }
-      else if (i < 40) { f = b ^ c ^ d; k = 0x6ED9EBA1u; }
-      else if (i < 60) { f = (b & c) | (b & d) | (c & d); k = 0x8F1BBCDCu; }
-      else { f = b ^ c ^ d; k = 0xCA62C1D6u; }
-      uint32_t t = rol(a, 5) + f + e + k + w[i];
-      e = d; d = c; c = rol(b, 30); b = a; a = t;
-    }
+    auto sched = [&](int i) { return w[i & 15] = rol(w[(i + 13) & 15] ^ w[(i + 8) & 15] ^ w[(i + 2) & 15] ^ w[i & 15], 1); };
+    // one round with the five working variables passed in rotated order, so that no value has to be moved
+    auto r0 = [&](uint32_t v, uint32_t& x, uint32_t y, uint32_t z, uint32_t& t, int i) { t += rol(v, 5) + ((x & y) | (~x & z)) + 0x5A827999u + (i < 16 ? w[i] : sched(i)); x = rol(x, 30); };
+    auto r1 = [&](uint32_t v, uint32_t& x, uint32_t y, uint32_t z, uint32_t& t, int i) { t += rol(v, 5) + (x ^ y ^ z) + 0x6ED9EBA1u + sched(i); x = rol(x, 30); };
+    auto r2 = [&](uint32_t v, uint32_t& x, uint32_t y, uint32_t z, uint32_t& t, int i) { t += rol(v, 5) + ((x & y) | (x & z) | (y & z)) + 0x8F1BBCDCu + sched(i); x = rol(x, 30); };
+    auto r3 = [&](uint32_t v, uint32_t& x, uint32_t y, uint32_t z, uint32_t& t, int i) { t += rol(v, 5) + (x ^ y ^ z) + 0xCA62C1D6u + sched(i); x = rol(x, 30); };
+#pragma GCC unroll 4
+    for (int i = 0; i < 20; i += 5) { r0(a, b, c, d, e, i); r0(e, a, b, c, d, i + 1); r0(d, e, a, b, c, i + 2); r0(c, d, e, a, b, i + 3); r0(b, c, d, e, a, i + 4); }
+#pragma GCC unroll 4
+    for (int i = 20; i < 40; i += 5) { r1(a, b, c, d, e, i); r1(e, a, b, c, d, i + 1); r1(d, e, a, b, c, i + 2); r1(c, d, e, a, b, i + 3); r1(b, c, d, e, a, i + 4); }
+#pragma GCC unroll 4
+    for (int i = 40; i < 60; i += 5) { r2(a, b, c, d, e, i); r2(e, a, b, c, d, i + 1); r2(d, e, a, b, c, i + 2); r2(c, d, e, a, b, i + 3); r2(b, c, d, e, a, i + 4); }
+#pragma GCC unroll 4
+    for (int i = 60; i < 80; i += 5) { r3(a, b, c, d, e, i); r3(e, a, b, c, d, i + 1); r3(d, e, a, b, c, i + 2); r3(c, d, e, a, b, i + 3); r3(b, c, d, e, a, i + 4); }
     h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e;
   }
   void update(const void* data, size_t n) {
@@ -46,15 +50,21 @@ struct Sha1 {
       if (fill == 64) { block(buf); fill = 0; }
     }
   }
+  void finish() {  // pads and absorbs the last block(s); h[] is the digest afterwards
+    const uint64_t bits = len * 8;
+    buf[fill++] = 0x80;
+    if (fill > 56) {
+      memset(buf + fill, 0, 64 - fill);
+      block(buf);
+      fill = 0;
+    }
+    memset(buf + fill, 0, 56 - fill);
+    for (int i = 0; i < 8; ++i) buf[56 + i] = uint8_t(bits >> (56 - 8 * i));
+    block(buf);
+    fill = 0;
+  }
   std::string hexdigest() {
-    uint64_t bits = len * 8;
-    uint8_t pad = 0x80;
-    update(&pad, 1);
-    uint8_t z = 0;
-    while (fill != 56) update(&z, 1);
-    uint8_t lb[8];
-    for (int i = 0; i < 8; ++i) lb[i] = uint8_t(bits >> (56 - 8 * i));
-    update(lb, 8);
+    finish();
     static const char* hx = "0123456789abcdef";
     std::string s(40, '0');
     for (int i = 0; i < 5; ++i)
@@ -83,15 +93,30 @@ inline void debug_bytes(const uint8_t* p, size_t n, std::string& out) {
 // followed by the first character of the strand name
 // (reference src/microphasing.rs:667-675, src/common.rs:387-395).
 inline std::string record_id(const uint8_t* seq, size_t n, const std::string& transcript, uint64_t offset, char strand_initial) {
-  std::string s;
-  s.reserve(5 * n + 48);
-  debug_bytes(seq, n, s);
-  s += transcript;
-  s += std::to_string(offset);
+  // the message is streamed into the hash in pieces; "[65, 84, 71]" is rendered 3 characters + ", " per byte at most
   Sha1 sh;
-  sh.update(s.data(), s.size());
-  std::string id = sh.hexdigest().substr(0, 15);
-  id.push_back(strand_initial);
+  char piece[5 * 64 + 2];
+  size_t fill = 0;
+  piece[fill++] = '[';
+  for (size_t i = 0; i < n; ++i) {
+    if (fill + 6 > sizeof piece) { sh.update(piece, fill); fill = 0; }
+    if (i) { piece[fill++] = ','; piece[fill++] = ' '; }
+    const unsigned v = seq[i];
+    if (v >= 100) piece[fill++] = char('0' + v / 100);
+    if (v >= 10) piece[fill++] = char('0' + v / 10 % 10);
+    piece[fill++] = char('0' + v % 10);
+  }
+  if (fill + 1 > sizeof piece) { sh.update(piece, fill); fill = 0; }
+  piece[fill++] = ']';
+  sh.update(piece, fill);
+  sh.update(transcript.data(), transcript.size());
+  char num[24];
+  auto r = std::to_chars(num, num + sizeof num, offset);
+  sh.update(num, size_t(r.ptr - num));
+  sh.finish();
+  static const char* hx = "0123456789abcdef";
+  std::string id(16, strand_initial);
+  for (int q = 0; q < 15; ++q) id[q] = hx[(sh.h[q / 8] >> (28 - 4 * (q % 8))) & 15];
   return id;
 }
 
