@@ -12,8 +12,10 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <limits>
 #include <map>
+#include <memory>
 #include <string>
 #include <string_view>
 #include <tuple>
@@ -43,26 +45,102 @@ struct PhaseRaw {
   uint64_t sum_depth = 0;         // over every enumerated window
 };
 
+// A string with N characters of inline storage, heap beyond that.  The record id is 16 characters and a
+// window sequence usually 27 — both just past what std::string keeps inline — and every record carries three.
+template <size_t N>
+class InlineStr {
+ public:
+  InlineStr() { buf_[0] = 0; }
+  InlineStr(std::string_view v) { assign(v); }
+  InlineStr(const std::string& v) { assign(std::string_view(v)); }
+  InlineStr(const char* v) { assign(std::string_view(v)); }
+  InlineStr(const InlineStr& o) { assign(o.view()); }
+  InlineStr(InlineStr&& o) noexcept { take(o); }
+  InlineStr& operator=(const InlineStr& o) {
+    if (this != &o) assign(o.view());
+    return *this;
+  }
+  InlineStr& operator=(InlineStr&& o) noexcept {
+    if (this != &o) take(o);
+    return *this;
+  }
+  InlineStr& operator=(std::string_view v) { assign(v); return *this; }
+  InlineStr& operator=(const std::string& v) { assign(std::string_view(v)); return *this; }
+
+  // `v` must not alias this string's own storage
+  void assign(std::string_view v) {
+    char* d = reset(v.size());
+    if (!v.empty()) memcpy(d, v.data(), v.size());
+  }
+  void assign(const char* p, size_t n) { assign(std::string_view(p, n)); }
+  // sets the length; the characters are zero until written through operator[]
+  void resize(size_t n) { memset(reset(n), 0, n); }
+  void clear() { reset(0); }
+
+  size_t size() const { return n_; }
+  bool empty() const { return n_ == 0; }
+  const char* data() const { return n_ <= N ? buf_ : big_.get(); }
+  const char* c_str() const { return data(); }
+  char& operator[](size_t i) { return (n_ <= N ? buf_ : big_.get())[i]; }
+  const char& operator[](size_t i) const { return data()[i]; }
+  std::string_view view() const { return std::string_view(data(), n_); }
+  operator std::string_view() const { return view(); }
+  operator std::string() const { return std::string(data(), n_); }
+
+  friend bool operator==(const InlineStr& a, const InlineStr& b) { return a.view() == b.view(); }
+  friend bool operator!=(const InlineStr& a, const InlineStr& b) { return a.view() != b.view(); }
+
+ private:
+  // storage for n characters plus the terminator, contents unspecified
+  char* reset(size_t n) {
+    char* d = buf_;
+    if (n > N) {
+      if (!big_ || n > cap_) {
+        big_.reset(new char[n + 1]);
+        cap_ = n;
+      }
+      d = big_.get();
+    }
+    n_ = n;
+    d[n] = 0;
+    return d;
+  }
+  void take(InlineStr& o) noexcept {
+    n_ = o.n_;
+    cap_ = o.cap_;
+    big_ = std::move(o.big_);
+    memcpy(buf_, o.buf_, sizeof buf_);
+    o.n_ = 0;
+    o.cap_ = 0;
+    o.buf_[0] = 0;
+  }
+  size_t n_ = 0, cap_ = 0;
+  std::unique_ptr<char[]> big_;
+  char buf_[N + 1];
+};
+using IdStr = InlineStr<23>;
+using SeqStr = InlineStr<39>;
+
 // src/common.rs:350-373
 struct InfoRecord {
-  std::string id;
+  IdStr id;
   uint32_t tx = 0;
   uint64_t offset = 0, frame = 0;
   double freq = 0;
   uint32_t depth = 0, nvar = 0, nsomatic = 0, nvariant_sites = 0, nsomvariant_sites = 0;
   std::string variant_sites, somatic_positions, somatic_aa_change, germline_positions, germline_aa_change;
-  std::string normal_sequence, mutant_sequence;
+  SeqStr normal_sequence, mutant_sequence;
 };
 
 struct OutRecord {
   InfoRecord info;       // the TSV row
-  std::string mt;        // mutant FASTA sequence (stdout), valid if has_mt && !mt_same
-  std::string wt;        // normal FASTA sequence (--normal-output), valid if has_wt && !wt_same
+  SeqStr mt;             // mutant FASTA sequence (stdout), valid if has_mt && !mt_same
+  SeqStr wt;             // normal FASTA sequence (--normal-output), valid if has_wt && !wt_same
   bool has_mt = false, has_wt = false;
   // the FASTA line is byte-identical to the TSV column (the common case): it is not stored twice
   bool mt_same = false, wt_same = false;
-  const std::string& mt_str() const { return mt_same ? info.mutant_sequence : mt; }
-  const std::string& wt_str() const { return wt_same ? info.normal_sequence : wt; }
+  const SeqStr& mt_str() const { return mt_same ? info.mutant_sequence : mt; }
+  const SeqStr& wt_str() const { return wt_same ? info.normal_sequence : wt; }
 };
 
 struct ResidueStats {
@@ -436,7 +514,7 @@ class Residue {
       if (emit) {
         OutRecord o;
         // the FASTA lines (:846-873) are the TSV columns again unless an insertion / indel changed the slice bounds
-        auto put = [](std::string_view line, std::string_view column, std::string& dst, bool& same) {
+        auto put = [](std::string_view line, std::string_view column, SeqStr& dst, bool& same) {
           same = line.data() == column.data() && line.size() == column.size();
           if (!same) dst.assign(line);
         };
@@ -701,22 +779,27 @@ class Residue {
     const double eps = std::numeric_limits<double>::epsilon();
     for (const HapSeq& hapseq : first_hap_vec) {
       const InfoRecord& record = hapseq.rec;
-      const std::string& wt_sequence = record.normal_sequence;
-      const std::string& mt_sequence = record.mutant_sequence;
+      const std::string_view wt_sequence = record.normal_sequence, mt_sequence = record.mutant_sequence;
       for (const HapSeq& prev_hapseq : sec_hap_vec) {
         const InfoRecord& prev_record = prev_hapseq.rec;
-        const std::string& prev_wt_sequence = prev_record.normal_sequence;
-        const std::string& prev_mt_sequence = prev_record.mutant_sequence;
-        const std::string new_wt_sequence = prev_wt_sequence + wt_sequence;
+        const std::string_view prev_wt_sequence = prev_record.normal_sequence, prev_mt_sequence = prev_record.mutant_sequence;
+        auto cat = [](std::string_view a, std::string_view b) {
+          std::string r;
+          r.reserve(a.size() + b.size());
+          r.append(a);
+          r.append(b);
+          return r;
+        };
+        const std::string new_wt_sequence = cat(prev_wt_sequence, wt_sequence);
         std::vector<std::string> new_mt_sequences;
         if (wt_sequence != mt_sequence) {
-          new_mt_sequences.push_back(prev_wt_sequence + mt_sequence);
+          new_mt_sequences.push_back(cat(prev_wt_sequence, mt_sequence));
           if (prev_wt_sequence != prev_mt_sequence) {
-            new_mt_sequences.push_back(prev_mt_sequence + wt_sequence);
-            new_mt_sequences.push_back(prev_mt_sequence + mt_sequence);
+            new_mt_sequences.push_back(cat(prev_mt_sequence, wt_sequence));
+            new_mt_sequences.push_back(cat(prev_mt_sequence, mt_sequence));
           }
         } else {
-          new_mt_sequences.push_back(prev_mt_sequence + mt_sequence);
+          new_mt_sequences.push_back(cat(prev_mt_sequence, mt_sequence));
         }
         if (is_short_exon && !is_last_exon) {
           const double out_freq = std::fabs(record.freq - prev_record.freq) < eps ? record.freq : record.freq * prev_record.freq;

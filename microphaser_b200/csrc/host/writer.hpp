@@ -19,7 +19,7 @@ struct Outputs {
   bool header_written = false;
 };
 
-inline void write_fasta(FILE* f, const std::string& id, const std::string& seq) {
+inline void write_fasta(FILE* f, std::string_view id, std::string_view seq) {
   fputc('>', f);
   fwrite(id.data(), 1, id.size(), f);
   fputc('\n', f);

@@ -30,14 +30,12 @@ struct Sha1 {
     auto r1 = [&](uint32_t v, uint32_t& x, uint32_t y, uint32_t z, uint32_t& t, int i) { t += rol(v, 5) + (x ^ y ^ z) + 0x6ED9EBA1u + sched(i); x = rol(x, 30); };
     auto r2 = [&](uint32_t v, uint32_t& x, uint32_t y, uint32_t z, uint32_t& t, int i) { t += rol(v, 5) + ((x & y) | (x & z) | (y & z)) + 0x8F1BBCDCu + sched(i); x = rol(x, 30); };
     auto r3 = [&](uint32_t v, uint32_t& x, uint32_t y, uint32_t z, uint32_t& t, int i) { t += rol(v, 5) + (x ^ y ^ z) + 0xCA62C1D6u + sched(i); x = rol(x, 30); };
-#pragma GCC unroll 4
-    for (int i = 0; i < 20; i += 5) { r0(a, b, c, d, e, i); r0(e, a, b, c, d, i + 1); r0(d, e, a, b, c, i + 2); r0(c, d, e, a, b, i + 3); r0(b, c, d, e, a, i + 4); }
-#pragma GCC unroll 4
-    for (int i = 20; i < 40; i += 5) { r1(a, b, c, d, e, i); r1(e, a, b, c, d, i + 1); r1(d, e, a, b, c, i + 2); r1(c, d, e, a, b, i + 3); r1(b, c, d, e, a, i + 4); }
-#pragma GCC unroll 4
-    for (int i = 40; i < 60; i += 5) { r2(a, b, c, d, e, i); r2(e, a, b, c, d, i + 1); r2(d, e, a, b, c, i + 2); r2(c, d, e, a, b, i + 3); r2(b, c, d, e, a, i + 4); }
-#pragma GCC unroll 4
-    for (int i = 60; i < 80; i += 5) { r3(a, b, c, d, e, i); r3(e, a, b, c, d, i + 1); r3(d, e, a, b, c, i + 2); r3(c, d, e, a, b, i + 3); r3(b, c, d, e, a, i + 4); }
+#define MPH_SHA1_R5(R, i) R(a, b, c, d, e, i); R(e, a, b, c, d, i + 1); R(d, e, a, b, c, i + 2); R(c, d, e, a, b, i + 3); R(b, c, d, e, a, i + 4);
+    MPH_SHA1_R5(r0, 0) MPH_SHA1_R5(r0, 5) MPH_SHA1_R5(r0, 10) MPH_SHA1_R5(r0, 15)
+    MPH_SHA1_R5(r1, 20) MPH_SHA1_R5(r1, 25) MPH_SHA1_R5(r1, 30) MPH_SHA1_R5(r1, 35)
+    MPH_SHA1_R5(r2, 40) MPH_SHA1_R5(r2, 45) MPH_SHA1_R5(r2, 50) MPH_SHA1_R5(r2, 55)
+    MPH_SHA1_R5(r3, 60) MPH_SHA1_R5(r3, 65) MPH_SHA1_R5(r3, 70) MPH_SHA1_R5(r3, 75)
+#undef MPH_SHA1_R5
     h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e;
   }
   void update(const void* data, size_t n) {
