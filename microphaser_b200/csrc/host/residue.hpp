@@ -269,6 +269,15 @@ class Residue {
 
   // Processes transcripts [tx_lo, tx_hi) and appends their records in the reference's order.
   void run(uint32_t tx_lo, uint32_t tx_hi, std::vector<OutRecord>& out, ResidueStats& stats) {
+    // records are a few hundred bytes each: size the vector once from the number of interesting windows of the range
+    // instead of letting it double its way up (about one record per three such windows on variant-dense input)
+    if (tx_lo < tx_hi && b_.txs[tx_lo].seg_lo < b_.txs[tx_hi - 1].seg_hi) {
+      const MphSegment& s0 = b_.segs[b_.txs[tx_lo].seg_lo];
+      const MphSegment& s1 = b_.segs[b_.txs[tx_hi - 1].seg_hi - 1];
+      auto lo = std::lower_bound(raw_.iw.begin(), raw_.iw.end(), s0.win_base);
+      auto hi = std::lower_bound(lo, raw_.iw.end(), s1.win_base + s1.n_win);
+      out.reserve(out.size() + size_t(hi - lo) / 3 + 16);
+    }
     for (uint32_t t = tx_lo; t < tx_hi; ++t) run_transcript(t, out, stats);
   }
 
@@ -292,10 +301,15 @@ class Residue {
     const MphHap* info;
   };
 
-  size_t find_iw(uint32_t widx) const {
-    auto it = std::lower_bound(raw_.iw.begin(), raw_.iw.end(), widx);
-    if (it == raw_.iw.end() || *it != widx) return SIZE_MAX;
-    return size_t(it - raw_.iw.begin());
+  // index of window `widx` in the interesting-window list; the serial loop asks in ascending order within one
+  // segment, so the previous answer (or its successor) is almost always the next one
+  size_t find_iw(uint32_t widx) {
+    const uint32_t* iw = raw_.iw.data();
+    for (size_t c = iw_hint_; c < iw_hi_ && c < iw_hint_ + 2; ++c)
+      if (iw[c] == widx) return iw_hint_ = c;
+    const uint32_t* it = std::lower_bound(iw + iw_lo_, iw + iw_hi_, widx);
+    if (it == iw + iw_hi_ || *it != widx) return SIZE_MAX;
+    return iw_hint_ = size_t(it - iw);
   }
 
   std::string arena(const MphHap& h, bool germ) const {
@@ -512,20 +526,23 @@ class Residue {
         }
       }
       if (emit) {
-        OutRecord o;
         // the FASTA lines (:846-873) are the TSV columns again unless an insertion / indel changed the slice bounds
+        std::string_view mt_line, wt_line;
+        bool has_mt = false, has_wt = false;
+        if (g.spos == 1) { mt_line = slice(seq, g.gap, seq.size()); has_mt = true; }
+        else if (g.spos == 0) { mt_line = slice(seq, 0, this_window_len); has_mt = true; }
+        if (!germline_seq.empty()) {
+          if (g.spos == 1) { wt_line = slice(germline_seq, g.gap, germline_seq.size()); has_wt = true; }
+          else if (g.spos == 0) { wt_line = slice(germline_seq, 0, this_window_len); has_wt = true; }
+        }
         auto put = [](std::string_view line, std::string_view column, SeqStr& dst, bool& same) {
           same = line.data() == column.data() && line.size() == column.size();
           if (!same) dst.assign(line);
         };
-        if (g.spos == 1) { put(slice(seq, g.gap, seq.size()), neopeptide, o.mt, o.mt_same); o.has_mt = true; }
-        else if (g.spos == 0) { put(slice(seq, 0, this_window_len), neopeptide, o.mt, o.mt_same); o.has_mt = true; }
-        if (!germline_seq.empty()) {
-          if (g.spos == 1) { put(slice(germline_seq, g.gap, germline_seq.size()), normal_peptide, o.wt, o.wt_same); o.has_wt = true; }
-          else if (g.spos == 0) { put(slice(germline_seq, 0, this_window_len), normal_peptide, o.wt, o.wt_same); o.has_wt = true; }
-        }
+        OutRecord& o = out.emplace_back();  // built in place: nothing below throws
+        if (has_mt) { put(mt_line, neopeptide, o.mt, o.mt_same); o.has_mt = true; }
+        if (has_wt) { put(wt_line, normal_peptide, o.wt, o.wt_same); o.has_wt = true; }
         o.info = std::move(rec);
-        out.push_back(std::move(o));
       }
     }
     (void)gm;
@@ -626,12 +643,16 @@ class Residue {
       // iterations leave the state untouched).
       std::vector<uint32_t>& ks = ks_scratch_;
       ks.clear();
+      {
+        auto lo = std::lower_bound(raw_.iw.begin(), raw_.iw.end(), sg.win_base);
+        auto hi = std::lower_bound(lo, raw_.iw.end(), sg.win_base + sg.n_win);
+        iw_lo_ = iw_hint_ = size_t(lo - raw_.iw.begin());
+        iw_hi_ = size_t(hi - raw_.iw.begin());
+      }
       if (has_fs) {
         for (uint32_t k = 0; k < sg.n_iter; ++k) ks.push_back(k);
       } else {
-        auto lo = std::lower_bound(raw_.iw.begin(), raw_.iw.end(), sg.win_base);
-        auto hi = std::lower_bound(raw_.iw.begin(), raw_.iw.end(), sg.win_base + sg.n_win);
-        for (auto it = lo; it != hi; ++it) ks.push_back(sg.k_first + (*it - sg.win_base) * sg.k_stride);
+        for (size_t c = iw_lo_; c < iw_hi_; ++c) ks.push_back(sg.k_first + (raw_.iw[c] - sg.win_base) * sg.k_stride);
       }
       uint32_t prev_vb_fs = 0, prev_va_fs = 0;
       bool fs_init = false;
@@ -907,6 +928,7 @@ class Residue {
   const PhaseRaw& raw_;
   FILE* trace_ = nullptr;
   std::vector<std::pair<uint64_t, uint64_t>> active_scratch_;
+  size_t iw_lo_ = 0, iw_hi_ = 0, iw_hint_ = 0;  // this segment's slice of raw_.iw and the last lookup (find_iw)
   std::vector<uint32_t> ks_scratch_;
 };
 
