@@ -16,6 +16,7 @@
 #include <limits>
 #include <map>
 #include <memory>
+#include <optional>
 #include <string>
 #include <string_view>
 #include <tuple>
@@ -483,9 +484,13 @@ class Residue {
         else ff.erase(frame);
       }
       // meta information (:720-769)
-      InfoRecord rec;
-      rec.tx = t;
-      if (need_rec || lazy) {
+      // built only for a haplotype that is written or that a junction merge can read (two windows in three need neither)
+      const bool have_rec = need_rec || lazy;
+      std::optional<InfoRecord> rec_slot;
+      if (have_rec) rec_slot.emplace();
+      InfoRecord& rec = have_rec ? *rec_slot : unused_rec_;
+      if (have_rec) {
+        rec.tx = t;
         rec.offset = g.spos == 0 ? uint64_t(g.s) + 1 : uint64_t(g.s) + 1 + g.gap;
         rec.frame = frame;
         rec.freq = frame_frequency;
@@ -508,19 +513,17 @@ class Residue {
         rec.mutant_sequence.assign(neopeptide);
       }
       if (!remove_peptide || frame == 0) {
-        InfoRecord rec_for_merge;
-        if (boundary) rec_for_merge = rec;
         haplotypes_vec.n += 1;
         if (boundary) {
-          HapSeq hs;
-          hs.rec = std::move(rec_for_merge);
+          HapSeq& hs = haplotypes_vec.v.emplace_back();
+          if (emit) hs.rec = rec;  // the written record keeps its own copy
+          else hs.rec = std::move(rec);
           if (lazy) {
             hs.lazy = true; hs.sg = &sg; hs.h = &h; hs.k = k; hs.wv = wv;
           } else {
             hs.rec.normal_sequence.assign(germline_seq);
             hs.rec.mutant_sequence.assign(seq);
           }
-          haplotypes_vec.v.push_back(std::move(hs));
         } else {
           haplotypes_vec.partial = true;
         }
@@ -553,7 +556,10 @@ class Residue {
   void fill_meta(InfoRecord& rec, const WinVars& wv, const MphHap& h) const {
     const uint32_t nv = wv.n;
     uint32_t n_variantsites = 0, n_som_variantsites = 0;
-    std::string s_pc, g_pc, s_pos, g_pos, sites;
+    // the columns are written in place
+    std::string &s_pc = rec.somatic_aa_change, &g_pc = rec.germline_aa_change, &s_pos = rec.somatic_positions, &g_pos = rec.germline_positions,
+                &sites = rec.variant_sites;
+    s_pc.clear(); g_pc.clear(); s_pos.clear(); g_pos.clear(); sites.clear();
     bool fs = true, fg = true, fsite = true;
     char buf[24];
     auto put = [&](std::string& dst, bool& first, uint64_t v) {
@@ -589,11 +595,6 @@ class Residue {
     rec.nsomatic = h.n_som;
     rec.nvariant_sites = n_variantsites;
     rec.nsomvariant_sites = n_som_variantsites;
-    rec.variant_sites = std::move(sites);
-    rec.somatic_positions = std::move(s_pos);
-    rec.somatic_aa_change = std::move(s_pc);
-    rec.germline_positions = std::move(g_pos);
-    rec.germline_aa_change = std::move(g_pc);
   }
 
   // builds the strings of a lazily kept boundary haplotype (plain reference window on both streams)
@@ -644,10 +645,16 @@ class Residue {
       std::vector<uint32_t>& ks = ks_scratch_;
       ks.clear();
       {
-        auto lo = std::lower_bound(raw_.iw.begin(), raw_.iw.end(), sg.win_base);
-        auto hi = std::lower_bound(lo, raw_.iw.end(), sg.win_base + sg.n_win);
-        iw_lo_ = iw_hint_ = size_t(lo - raw_.iw.begin());
-        iw_hi_ = size_t(hi - raw_.iw.begin());
+        // this segment's slice of the (ascending) list: it usually starts where the previous segment's slice ended,
+        // and it cannot hold more entries than the segment has windows
+        const uint32_t* iw = raw_.iw.data();
+        const size_t n_iw = raw_.iw.size();
+        size_t lo = std::min(iw_hi_, n_iw);
+        if ((lo > 0 && iw[lo - 1] >= sg.win_base) || (lo < n_iw && iw[lo] < sg.win_base))
+          lo = size_t(std::lower_bound(iw, iw + n_iw, sg.win_base) - iw);
+        const size_t hi = size_t(std::lower_bound(iw + lo, iw + std::min(n_iw, lo + size_t(sg.n_win)), sg.win_base + sg.n_win) - iw);
+        iw_lo_ = iw_hint_ = lo;
+        iw_hi_ = hi;
       }
       if (has_fs) {
         for (uint32_t k = 0; k < sg.n_iter; ++k) ks.push_back(k);
@@ -928,6 +935,7 @@ class Residue {
   const PhaseRaw& raw_;
   FILE* trace_ = nullptr;
   std::vector<std::pair<uint64_t, uint64_t>> active_scratch_;
+  InfoRecord unused_rec_;  // what `rec` names in print() for a haplotype that needs no record; never written
   size_t iw_lo_ = 0, iw_hi_ = 0, iw_hint_ = 0;  // this segment's slice of raw_.iw and the last lookup (find_iw)
   std::vector<uint32_t> ks_scratch_;
 };
