@@ -193,7 +193,8 @@ def main():
 
     # the host residue is multi-threaded: every rank gets its share of the cores
     local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
-    os.environ.setdefault("MPH_HOST_THREADS", str(max(1, (os.cpu_count() or 1) // max(1, local_world))))
+    if local_world > 1:  # a single rank keeps the library's default (all cores but one, which the calling thread uses)
+        os.environ.setdefault("MPH_HOST_THREADS", str(max(1, (os.cpu_count() or 1) // local_world)))
     ctx = m.Context(local_rank)
     t0 = time.time()
     batch = m.Batch.synthetic(n_transcripts=n_tx, coverage=cov, seed=shard_seed(rank), pin=True)
