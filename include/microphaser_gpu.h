@@ -212,6 +212,7 @@ typedef struct {
   uint64_t seed;
   uint32_t n_transcripts, exons_per_transcript, exon_len_min, exon_len_max, read_len;
   double coverage, germline_per_kb, somatic_per_kb, lowq_frac, indel_read_frac;
+  double ins_var_frac, del_var_frac; /* share of the variants that are 1-6 nt insertions / deletions (hypermutated config) */
 } mph_synth_params;
 int mph_synth_batch(const mph_synth_params* params, uint32_t window_len, int pin, mph_batch** out);
 /* the same genes / reads / variants as real files in `dir`: ref.fa(.fai), annotation.gtf, variants.vcf, reads.bam */

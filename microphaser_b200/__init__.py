@@ -32,7 +32,8 @@ class Timing(C.Structure):
 class SynthParams(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("n_transcripts", C.c_uint32), ("exons_per_transcript", C.c_uint32), ("exon_len_min", C.c_uint32),
                 ("exon_len_max", C.c_uint32), ("read_len", C.c_uint32), ("coverage", C.c_double), ("germline_per_kb", C.c_double),
-                ("somatic_per_kb", C.c_double), ("lowq_frac", C.c_double), ("indel_read_frac", C.c_double)]
+                ("somatic_per_kb", C.c_double), ("lowq_frac", C.c_double), ("indel_read_frac", C.c_double),
+                ("ins_var_frac", C.c_double), ("del_var_frac", C.c_double)]
 
 
 class Record(C.Structure):
@@ -110,11 +111,11 @@ def _check(rc, ctx=None):
 
 
 def synth_write_files(outdir, n_transcripts=450, coverage=30.0, read_len=150, exons=8, exon_len=(90, 250), germline_per_kb=1.0,
-                      somatic_per_kb=1.0, lowq_frac=0.02, indel_read_frac=0.03, seed=0x4D500002, window_len=27):
+                      somatic_per_kb=1.0, lowq_frac=0.02, indel_read_frac=0.03, seed=0x4D500002, window_len=27, ins_var_frac=0.0, del_var_frac=0.0):
     """Write the workload of Batch.synthetic(...) with the same arguments as FASTA / GTF / VCF / BAM files."""
     os.makedirs(outdir, exist_ok=True)
     sp = SynthParams(seed, n_transcripts, exons, exon_len[0], exon_len[1], read_len, coverage, germline_per_kb, somatic_per_kb,
-                     lowq_frac, indel_read_frac)
+                     lowq_frac, indel_read_frac, ins_var_frac, del_var_frac)
     _check(load().mph_synth_write_files(C.byref(sp), window_len, outdir.encode()))
 
 
@@ -223,11 +224,22 @@ class Batch:
 
     @classmethod
     def synthetic(cls, n_transcripts=450, coverage=30.0, read_len=150, exons=8, exon_len=(90, 250), germline_per_kb=1.0,
-                  somatic_per_kb=1.0, lowq_frac=0.02, indel_read_frac=0.03, seed=0x4D500002, window_len=27, pin=True):
+                  somatic_per_kb=1.0, lowq_frac=0.02, indel_read_frac=0.03, seed=0x4D500002, window_len=27, pin=True, ins_var_frac=0.0,
+                  del_var_frac=0.0, mode="somatic"):
         sp = SynthParams(seed, n_transcripts, exons, exon_len[0], exon_len[1], read_len, coverage, germline_per_kb, somatic_per_kb,
-                         lowq_frac, indel_read_frac)
+                         lowq_frac, indel_read_frac, ins_var_frac, del_var_frac)
         h = C.c_void_p()
-        _check(load().mph_synth_batch(C.byref(sp), window_len, int(pin), C.byref(h)))
+        old = os.environ.get("MPH_SYNTH_MODE")
+        if mode == "normal":
+            os.environ["MPH_SYNTH_MODE"] = "1"
+        try:
+            _check(load().mph_synth_batch(C.byref(sp), window_len, int(pin), C.byref(h)))
+        finally:
+            if mode == "normal":
+                if old is None:
+                    del os.environ["MPH_SYNTH_MODE"]
+                else:
+                    os.environ["MPH_SYNTH_MODE"] = old
         return cls(h)
 
     def view(self):

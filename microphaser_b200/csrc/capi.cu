@@ -1348,6 +1348,7 @@ int mph_synth_batch(const mph_synth_params* sp, uint32_t window_len, int pin, mp
     p.seed = sp->seed; p.n_transcripts = sp->n_transcripts; p.exons = sp->exons_per_transcript; p.exon_min = sp->exon_len_min;
     p.exon_max = sp->exon_len_max; p.read_len = sp->read_len; p.coverage = sp->coverage; p.germline_per_kb = sp->germline_per_kb;
     p.somatic_per_kb = sp->somatic_per_kb; p.lowq_frac = sp->lowq_frac; p.indel_read_frac = sp->indel_read_frac;
+    p.ins_var_frac = sp->ins_var_frac; p.del_var_frac = sp->del_var_frac;
     synth_into(packer, p);
     mb->b = std::move(packer.batch());
     finish_batch(mb.get(), pin != 0);
@@ -1364,6 +1365,7 @@ int mph_synth_write_files(const mph_synth_params* sp, uint32_t window_len, const
     p.seed = sp->seed; p.n_transcripts = sp->n_transcripts; p.exons = sp->exons_per_transcript; p.exon_min = sp->exon_len_min;
     p.exon_max = sp->exon_len_max; p.read_len = sp->read_len; p.coverage = sp->coverage; p.germline_per_kb = sp->germline_per_kb;
     p.somatic_per_kb = sp->somatic_per_kb; p.lowq_frac = sp->lowq_frac; p.indel_read_frac = sp->indel_read_frac;
+    p.ins_var_frac = sp->ins_var_frac; p.del_var_frac = sp->del_var_frac;
     synth_write_files(p, window_len, dir);
   });
 }

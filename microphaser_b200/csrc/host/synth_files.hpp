@@ -120,9 +120,15 @@ inline SynthFileStats synth_write_files(const SynthParams& sp, uint32_t window_l
     // VCF
     for (auto& site : sg.sites)
       for (auto& v : site) {
-        char r = char(sg.ref[v.pos - g.start]);
-        if (r >= 'a') r = char(r - 32);
-        snprintf(buf, sizeof buf, "%s\t%u\t.\t%c\t%c\t100\t.\tDP=100%s\n", g.chrom.c_str(), v.pos + 1, r, char(v.alt), v.germline ? "" : ";SOMATIC");
+        auto up = [](uint8_t c) { return c >= 'a' ? char(c - 32) : char(c); };
+        std::string ref_allele(1, up(sg.ref[v.pos - g.start])), alt_allele(1, char(v.alt));
+        if (v.kind == MPH_DEL) {
+          for (uint32_t x = 1; x <= v.len; ++x) ref_allele.push_back(up(sg.ref[v.pos - g.start + x]));
+          alt_allele = ref_allele.substr(0, 1);
+        } else if (v.kind == MPH_INS) {
+          alt_allele = v.ins;
+        }
+        snprintf(buf, sizeof buf, "%s\t%u\t.\t%s\t%s\t100\t.\tDP=100%s\n", g.chrom.c_str(), v.pos + 1, ref_allele.c_str(), alt_allele.c_str(), v.germline ? "" : ";SOMATIC");
         vcf += buf;
         ++st.variants;
       }

@@ -17,6 +17,7 @@ struct SynthParams {
   uint64_t seed = 0x4D500003ull;
   uint32_t n_transcripts = 450, exons = 8, exon_min = 90, exon_max = 250, read_len = 150;
   double coverage = 30.0, germline_per_kb = 1.0, somatic_per_kb = 1.0, lowq_frac = 0.02, indel_read_frac = 0.03;
+  double ins_var_frac = 0.0, del_var_frac = 0.0;  // share of the variants that are 1-6 nt insertions / deletions (config C4)
 };
 
 struct Rng {  // splitmix64 / xoshiro256**
@@ -66,6 +67,8 @@ struct SynthGene {
 
 // Generates gene after gene and calls sink(SynthGene&). With all_bases every read carries real
 // bases / qualities (needed to write a BAM); otherwise only reads that overlap a variant do.
+// The genes, variants and alignments do not depend on all_bases: everything structural comes from one
+// generator, the bases / qualities / carried alleles of a read from a generator seeded per read.
 template <class Sink>
 inline void synth_generate(const SynthParams& sp, uint32_t window_len, bool all_bases, Sink&& sink) {
   Rng rng(sp.seed);
@@ -158,28 +161,45 @@ inline void synth_generate(const SynthParams& sp, uint32_t window_len, bool all_
     if (reverse) for (auto it = gex.rbegin(); it != gex.rend(); ++it) t.exons.push_back(*it);
     else t.exons = gex;
     g.transcripts.push_back(t);
-    // variants (SNVs), per exon
-    struct V { uint32_t pos; char alt; bool somatic; uint8_t hap; };
+    // variants per exon: SNVs, and with ins_var_frac / del_var_frac short insertions / deletions
+    struct V { uint32_t pos; char alt; bool somatic; uint8_t hap; uint8_t kind; uint32_t len; std::string ins; };
     std::vector<V> vs;
     for (auto& e : gex) {
       const double kb = (e.end - e.start) / 1000.0;
       const uint32_t ng = rng.poisson(kb * sp.germline_per_kb), ns = rng.poisson(kb * sp.somatic_per_kb);
       for (uint32_t x = 0; x < ng + ns; ++x) {
-        const uint32_t vp = rng.range(e.start, e.end - 1);
+        uint32_t vp = rng.range(e.start, e.end - 1);
         // (a variant exactly window_len after the start of a reverse-strand exon triggers the reference's
         // stale-column quirk: such transcripts go through the serial replay kernel)
+        const double kind_draw = rng.uniform();
+        const uint32_t ilen = rng.range(1, 6);
         const char r = char(ref[vp - gstart]);
         char a;
         do a = B[rng.below(4)]; while (a == r);
-        vs.push_back(V{vp, a, x >= ng, uint8_t(rng.below(3))});
+        V v{vp, a, x >= ng, uint8_t(rng.below(3)), MPH_SNV, 0, std::string()};
+        char ib[6];
+        for (auto& c : ib) c = B[rng.below(4)];
+        // indels stay 36 nt clear of the exon ends: the reference's junction merge panics on a window pair whose
+        // wild-type side is shorter than the window (usize underflow at :1775-1790), so a workload with indels at
+        // the junctions cannot be run to completion by the reference itself
+        const bool interior = vp >= e.start + 36 && vp + 42 < e.end;
+        if (kind_draw < sp.ins_var_frac && interior) {
+          v.kind = MPH_INS; v.len = ilen;
+          v.ins.assign(1, r >= 'a' ? char(r - 32) : r);
+          v.ins.append(ib, ilen);
+        } else if (kind_draw >= sp.ins_var_frac && kind_draw < sp.ins_var_frac + sp.del_var_frac && interior) {
+          v.kind = MPH_DEL; v.len = ilen;
+        }
+        vs.push_back(std::move(v));
       }
     }
-    std::sort(vs.begin(), vs.end(), [](const V& a, const V& b) { return a.pos < b.pos; });
+    std::stable_sort(vs.begin(), vs.end(), [](const V& a, const V& b) { return a.pos < b.pos; });
     vs.erase(std::unique(vs.begin(), vs.end(), [](const V& a, const V& b) { return a.pos == b.pos; }), vs.end());
     std::vector<std::vector<HostVariant>> sites;
     for (auto& v : vs) {
       HostVariant hv;
-      hv.pos = v.pos; hv.kind = MPH_SNV; hv.alt = uint8_t(v.alt); hv.germline = !v.somatic;
+      hv.pos = v.pos; hv.kind = v.kind; hv.alt = uint8_t(v.alt); hv.germline = !v.somatic; hv.len = v.len;
+      if (v.kind == MPH_INS) hv.ins = v.ins;
       sites.push_back({hv});
     }
     // reads
@@ -205,51 +225,67 @@ inline void synth_generate(const SynthParams& sp, uint32_t window_len, bool all_
       }
     }
     std::sort(rs.begin(), rs.end(), [](const R& a, const R& b) { return a.start < b.start || (a.start == b.start && a.id < b.id); });
-    // bases / qualities only for reads that overlap a variant (the packer ships nothing else)
+    // bases / qualities only for reads that can overlap a variant (the packer ships nothing else); each read draws
+    // from its own generator, so the result does not depend on which reads are skipped
     std::vector<std::vector<uint8_t>> seqs, quals;
     std::vector<HostRead> hr(rs.size());
     seqs.reserve(rs.size() / 3);
     quals.reserve(rs.size() / 3);
+    auto carries = [](const V& v, uint32_t hap, double take) { return v.somatic ? take < 0.3 : (v.hap == 2 || v.hap == hap); };
     for (size_t i = 0; i < rs.size(); ++i) {
-      const R& r = rs[i];
+      R& r = rs[i];
       HostRead& h = hr[i];
-      h.start = r.start; h.end = r.end; h.l_seq = L; h.n_cigar = r.ncig; h.cigar = rs[i].cig;
-      h.qname_hash = (uint64_t(gi) << 32) | r.id;
       auto lo = std::lower_bound(vs.begin(), vs.end(), r.start, [](const V& v, uint32_t p) { return v.pos < p; });
-      if (!all_bases && (lo == vs.end() || lo->pos >= r.end)) {
+      const bool near_var = lo != vs.end() && lo->pos < r.start + L + 8;
+      if (near_var || all_bases) {
+        Rng rr(sp.seed ^ (0x9E3779B97F4A7C15ull * ((uint64_t(gi) << 32) | (r.id + 1u))));
+        const uint32_t hap = rr.below(2);
+        const double take = rr.uniform();
+        // a read without a private indel takes the first short insertion / deletion allele it carries into its CIGAR
+        const V* indel = nullptr;
+        if (r.ncig == 1)
+          for (auto vi = lo; vi != vs.end() && vi->pos + 20 < r.start + L; ++vi)
+            if (vi->kind != MPH_SNV && vi->pos >= r.start + 10 && carries(*vi, hap, take)) { indel = &*vi; break; }
+        if (indel) {
+          const uint32_t at = indel->pos - r.start + 1;
+          r.ncig = 3;
+          r.cig[0] = at << 4;
+          if (indel->kind == MPH_INS) { r.cig[1] = (indel->len << 4) | 1; r.cig[2] = (L - at - indel->len) << 4; r.end = r.start + L - indel->len; }
+          else { r.cig[1] = (indel->len << 4) | 2; r.cig[2] = (L - at) << 4; r.end = r.start + L + indel->len; }
+        }
+        std::vector<uint8_t> s4((L + 1) / 2, 0), q(L);
+        // walk the alignment: query index -> reference position
+        uint32_t qi = 0, rp = r.start;
+        for (uint32_t c = 0; c < r.ncig; ++c) {
+          const uint32_t op = r.cig[c] & 15, len = r.cig[c] >> 4;
+          if (op == 0) {
+            for (uint32_t x = 0; x < len; ++x, ++qi, ++rp) {
+              char base = char(ref[rp - gstart]);
+              if (base >= 'a') base = char(base - 32);
+              auto vi = std::lower_bound(vs.begin(), vs.end(), rp, [](const V& v, uint32_t p) { return v.pos < p; });
+              if (vi != vs.end() && vi->pos == rp && vi->kind == MPH_SNV && carries(*vi, hap, take)) base = vi->alt;
+              s4[qi >> 1] |= uint8_t(code4(base) << ((qi & 1) ? 0 : 4));
+            }
+          } else if (op == 1) {
+            for (uint32_t x = 0; x < len; ++x, ++qi) {
+              const char base = indel && indel->kind == MPH_INS ? indel->ins[1 + x] : B[rr.below(4)];
+              s4[qi >> 1] |= uint8_t(code4(base) << ((qi & 1) ? 0 : 4));
+            }
+          } else {
+            rp += len;
+          }
+        }
+        for (uint32_t x = 0; x < L; ++x) q[x] = rr.uniform() < sp.lowq_frac ? uint8_t(rr.range(2, 9)) : uint8_t(rr.range(30, 40));
+        seqs.push_back(std::move(s4));
+        quals.push_back(std::move(q));
+        h.seq4 = seqs.back().data();
+        h.qual = quals.back().data();
+      } else {
         h.seq4 = dummy_seq.data();
         h.qual = dummy_qual.data();
-        continue;
       }
-      const uint32_t hap = rng.below(2);
-      const double take = rng.uniform();
-      std::vector<uint8_t> s4((L + 1) / 2, 0), q(L);
-      // walk the alignment: query index -> reference position
-      uint32_t qi = 0, rp = r.start;
-      for (uint32_t c = 0; c < r.ncig; ++c) {
-        const uint32_t op = r.cig[c] & 15, len = r.cig[c] >> 4;
-        if (op == 0) {
-          for (uint32_t x = 0; x < len; ++x, ++qi, ++rp) {
-            char base = char(ref[rp - gstart]);
-            if (base >= 'a') base = char(base - 32);
-            auto vi = std::lower_bound(vs.begin(), vs.end(), rp, [](const V& v, uint32_t p) { return v.pos < p; });
-            if (vi != vs.end() && vi->pos == rp) {
-              const bool carry = vi->somatic ? take < 0.3 : (vi->hap == 2 || vi->hap == hap);
-              if (carry) base = vi->alt;
-            }
-            s4[qi >> 1] |= uint8_t(code4(base) << ((qi & 1) ? 0 : 4));
-          }
-        } else if (op == 1) {
-          for (uint32_t x = 0; x < len; ++x, ++qi) s4[qi >> 1] |= uint8_t(code4(B[rng.below(4)]) << ((qi & 1) ? 0 : 4));
-        } else {
-          rp += len;
-        }
-      }
-      for (uint32_t x = 0; x < L; ++x) q[x] = rng.uniform() < sp.lowq_frac ? uint8_t(rng.range(2, 9)) : uint8_t(rng.range(30, 40));
-      seqs.push_back(std::move(s4));
-      quals.push_back(std::move(q));
-      h.seq4 = seqs.back().data();
-      h.qual = quals.back().data();
+      h.start = r.start; h.end = r.end; h.l_seq = L; h.n_cigar = r.ncig; h.cigar = rs[i].cig;
+      h.qname_hash = (uint64_t(gi) << 32) | r.id;
     }
     for (size_t i = 0; i < rs.size(); ++i) hr[i].cigar = rs[i].cig;
     ref.resize(size_t(gend) + 100 - gstart, 'A');
@@ -271,8 +307,17 @@ inline void synth_generate(const SynthParams& sp, uint32_t window_len, bool all_
 }
 
 inline void synth_into(Packer& packer, const SynthParams& sp) {
-  synth_generate(sp, packer.batch().window_len, false,
-                 [&](SynthGene& sg) { packer.add_gene(sg.gene, sg.reads, sg.max_read_len, sg.sites, std::move(sg.ref)); });
+  const bool normal_mode = packer.batch().mode == 1;
+  synth_generate(sp, packer.batch().window_len, false, [&](SynthGene& sg) {
+    if (normal_mode) {
+      // the normal mode ignores three_prime_utr rows (src/normal_microphasing.rs:1340-1432): its exons are the CDS rows as they are
+      HostTranscript& t = sg.gene.transcripts[0];
+      t.exons.clear();
+      if (t.reverse) for (auto it = sg.cds.rbegin(); it != sg.cds.rend(); ++it) t.exons.push_back(*it);
+      else t.exons = sg.cds;
+    }
+    packer.add_gene(sg.gene, sg.reads, sg.max_read_len, sg.sites, std::move(sg.ref));
+  });
 }
 
 }  // namespace mph

@@ -90,6 +90,39 @@ def build_emu():
     return EMU_BIN
 
 
+SYNTH_CHECK_BIN = os.path.join(ROOT, "tests", "emu", "_build", "synth_check")
+
+
+def build_synth_check():
+    """tests/emu/synth_check.cpp: the native synthetic workload through the emulated device + product host code."""
+    build_emu()
+    src = os.path.join(ROOT, "tests", "emu", "synth_check.cpp")
+    if not os.path.exists(SYNTH_CHECK_BIN) or os.path.getmtime(SYNTH_CHECK_BIN) < max(os.path.getmtime(src), os.path.getmtime(EMU_BIN)):
+        subprocess.run(["g++", "-std=c++17", "-O2", "-Wall", "-Wno-missing-field-initializers", "-o", SYNTH_CHECK_BIN, src, "-lz"], check=True)
+    return SYNTH_CHECK_BIN
+
+
+# The shapes BASELINE.json names (configs[1..4]) as arguments of the native generator: n_transcripts, coverage,
+# germline / somatic variants per kb, insertion / deletion share, mode, seed. "Full" is the size the -m gpu tests
+# diff against the oracle; the CPU suite runs the same shapes through the emulator on fewer transcripts.
+CONFIG_SHAPES = {
+    "C2_chr22": dict(n_transcripts=450, coverage=30.0, germline_per_kb=1.0, somatic_per_kb=1.0, ins_var_frac=0.0, del_var_frac=0.0, mode="somatic", seed=0x4D500002),
+    "C3_exome_slice": dict(n_transcripts=2000, coverage=100.0, germline_per_kb=1.0, somatic_per_kb=1.0, ins_var_frac=0.0, del_var_frac=0.0, mode="somatic", seed=0x4D500003),
+    "C4_hypermutated": dict(n_transcripts=450, coverage=30.0, germline_per_kb=1.0, somatic_per_kb=10.0, ins_var_frac=0.1, del_var_frac=0.1, mode="somatic", seed=0x4D500004),
+    "C5a_normal": dict(n_transcripts=450, coverage=30.0, germline_per_kb=1.0, somatic_per_kb=1.0, ins_var_frac=0.0, del_var_frac=0.0, mode="normal", seed=0x4D500005),
+}
+
+
+def run_oracle_on_files(oracle_bin, files_dir, out_dir, mode="somatic", env=None):
+    """The oracle CLI on a directory written by mph_synth_write_files; returns CompletedProcess."""
+    cmd = [oracle_bin, mode, os.path.join(files_dir, "reads.bam"), "-r", os.path.join(files_dir, "ref.fa"), "-b",
+           os.path.join(files_dir, "variants.vcf"), "-t", os.path.join(out_dir, "out.tsv")]
+    if mode == "somatic":
+        cmd += ["-n", os.path.join(out_dir, "out.normal.fa")]
+    with open(os.path.join(files_dir, "annotation.gtf")) as gin, open(os.path.join(out_dir, "out.fa"), "wb") as fo:
+        return subprocess.run(cmd, stdin=gin, stdout=fo, stderr=subprocess.PIPE, timeout=1800, env=env)
+
+
 def build_product():
     from microphaser_b200 import build
     return build.build_all()
@@ -137,6 +170,11 @@ def oracle_bin():
 @pytest.fixture(scope="session")
 def emu_bin():
     return build_emu()
+
+
+@pytest.fixture(scope="session")
+def synth_check_bin():
+    return build_synth_check()
 
 
 @pytest.fixture(scope="session")
