@@ -112,7 +112,7 @@ struct mph_ctx {
   DevBuf<uint2> pairs;
   DevBuf<MphVar> vars;
   DevBuf<MphSegment> segs;
-  DevBuf<MphChunk> chunks;
+  DevBuf<MphChunk> chunks, groups;
   DevBuf<uint64_t> call_S, call_B;
   DevBuf<MphWinOut> win_out, iw_out;
   DevBuf<MphHist> hist;
@@ -166,7 +166,7 @@ void finish_batch(mph_batch* mb, bool pin) {
   auto bytes = [](auto& v) { return v.size() * sizeof(v[0]); };
   mb->h2d_bytes = bytes(b.read_start) + bytes(b.read_end) + bytes(b.read_flags) + bytes(b.vr_read) + bytes(b.vr_vlo) + bytes(b.vr_seq_off) +
                   bytes(b.vr_cig_off) + bytes(b.vr_lseq) + bytes(b.vr_ncig) + bytes(b.vr_nv) + bytes(b.bases) + bytes(b.cigars) +
-                  bytes(b.vars) + bytes(b.ins_bytes) + bytes(b.segs) + bytes(b.chunks) + bytes(b.ref) + bytes(b.stopmap) + bytes(mb->pairs) +
+                  bytes(b.vars) + bytes(b.ins_bytes) + bytes(b.segs) + bytes(b.chunks) + bytes(b.groups) + bytes(b.ref) + bytes(b.stopmap) + bytes(mb->pairs) +
                   bytes(b.tx_id_bytes) + bytes(b.tx_id_off) + bytes(b.replay) + bytes(b.replay_dq) + (b.replay.empty() ? 0 : bytes(b.seg_chunk0));
   if (pin) {
     auto reg = [&](auto& v) {
@@ -177,7 +177,7 @@ void finish_batch(mph_batch* mb, bool pin) {
         cudaGetLastError();
     };
     reg(b.read_start); reg(b.read_end); reg(b.read_flags); reg(b.vr_read); reg(b.vr_vlo); reg(b.vr_seq_off); reg(b.vr_cig_off); reg(b.vr_lseq);
-    reg(b.vr_ncig); reg(b.vr_nv); reg(b.bases); reg(b.cigars); reg(b.vars); reg(b.ins_bytes); reg(b.segs); reg(b.chunks); reg(b.ref); reg(b.stopmap);
+    reg(b.vr_ncig); reg(b.vr_nv); reg(b.bases); reg(b.cigars); reg(b.vars); reg(b.ins_bytes); reg(b.segs); reg(b.chunks); reg(b.groups); reg(b.ref); reg(b.stopmap);
     reg(mb->pairs);
     reg(b.tx_id_bytes); reg(b.tx_id_off); reg(b.replay); reg(b.replay_dq); reg(b.seg_chunk0);
     mb->pinned = true;
@@ -246,7 +246,7 @@ void prepare(mph_ctx* c, const mph_batch* mb) {
   c->vr_read.ensure(nvr + 1); c->vr_vlo.ensure(nvr + 1); c->vr_seq_off.ensure(nvr + 1); c->vr_cig_off.ensure(nvr + 1);
   c->vr_lseq.ensure(nvr + 1); c->vr_ncig.ensure(nvr + 1); c->vr_nv.ensure(nvr + 1);
   c->bases.ensure(b.bases.size() + 1); c->cigars.ensure(b.cigars.size() + 1); c->vars.ensure(b.vars.size() + 1); c->ins_bytes.ensure(b.ins_bytes.size() + 1);
-  c->segs.ensure(b.segs.size() + 1); c->chunks.ensure(b.chunks.size() + 1); c->ref.ensure(b.ref.size() + 1); c->stopmap.ensure(b.stopmap.size() + 1);
+  c->segs.ensure(b.segs.size() + 1); c->chunks.ensure(b.chunks.size() + 1); c->groups.ensure(b.groups.size() + 1); c->ref.ensure(b.ref.size() + 1); c->stopmap.ensure(b.stopmap.size() + 1);
   c->pairs.ensure(mb->pairs.size() + 1); c->tx_id_bytes.ensure(b.tx_id_bytes.size() + 1); c->tx_id_off.ensure(b.tx_id_off.size() + 1);
   c->call_S.ensure(nr + 1); c->call_B.ensure(nr + 1); c->call_flags.ensure(nr + 1);
   c->win_out.ensure(nw + 1); c->hap0.ensure(nw + 1); c->win_flag.ensure(nw + 1);
@@ -266,7 +266,7 @@ void prepare(mph_ctx* c, const mph_batch* mb) {
   d.vr_read = c->vr_read.p; d.vr_vlo = c->vr_vlo.p; d.vr_seq_off = c->vr_seq_off.p; d.vr_cig_off = c->vr_cig_off.p;
   d.vr_lseq = c->vr_lseq.p; d.vr_ncig = c->vr_ncig.p; d.vr_nv = c->vr_nv.p;
   d.bases = c->bases.p; d.cigars = c->cigars.p; d.vars = c->vars.p;
-  d.ins_bytes = c->ins_bytes.p; d.segs = c->segs.p; d.chunks = c->chunks.p; d.ref = c->ref.p; d.stopmap = c->stopmap.p;
+  d.ins_bytes = c->ins_bytes.p; d.segs = c->segs.p; d.chunks = c->chunks.p; d.groups = c->groups.p; d.ref = c->ref.p; d.stopmap = c->stopmap.p;
   d.call_S = reinterpret_cast<uint64_t*>(c->call_S.p); d.call_B = reinterpret_cast<uint64_t*>(c->call_B.p); d.call_flags = c->call_flags.p;
   d.win_out = c->win_out.p; d.hap0 = c->hap0.p; d.win_flag = c->win_flag.p; d.block_counts = c->block_counts.p;
   d.ovf_list = c->ovf_list.p;
@@ -309,7 +309,7 @@ void copy_stage(mph_ctx* c, const mph_batch* mb, const Stage& s, bool first, cud
   h2d_range(st, c->vr_nv, b.vr_nv, e0, e1);
   h2d_range(st, c->bases, b.bases, s.lo.bases, s.hi.bases); h2d_range(st, c->cigars, b.cigars, s.lo.cigars, s.hi.cigars);
   h2d_range(st, c->vars, b.vars, s.lo.vars, s.hi.vars); h2d_range(st, c->ins_bytes, b.ins_bytes, s.lo.ins, s.hi.ins);
-  h2d_range(st, c->segs, b.segs, s.lo.segs, s.hi.segs); h2d_range(st, c->chunks, b.chunks, s.lo.chunks, s.hi.chunks);
+  h2d_range(st, c->segs, b.segs, s.lo.segs, s.hi.segs); h2d_range(st, c->chunks, b.chunks, s.lo.chunks, s.hi.chunks); h2d_range(st, c->groups, b.groups, s.lo.groups, s.hi.groups);
   h2d_range(st, c->ref, b.ref, s.lo.ref, s.hi.ref);
   h2d_range(st, c->stopmap, b.stopmap, s.lo.ref / 32, s.hi.ref / 32 + 4);  // whole words; neighbouring stages rewrite the shared word with the same bits
   h2d_range(st, c->pairs, mb->pairs, s.pair_lo, s.pair_hi);
@@ -325,6 +325,7 @@ void set_ranges(mph_ctx* c, const Stage& s) {
   d.r0 = uint32_t(s.lo.reads); d.r1 = uint32_t(s.hi.reads);
   d.vr0 = uint32_t(s.lo.vr); d.vr1 = uint32_t(s.hi.vr);
   d.c0 = uint32_t(s.lo.chunks); d.c1 = uint32_t(s.hi.chunks);
+  d.g0 = uint32_t(s.lo.groups); d.g1 = uint32_t(s.hi.groups);
   d.w0 = uint32_t(s.lo.windows); d.w1 = uint32_t(s.hi.windows);
   d.rp0 = uint32_t(s.lo.replay); d.rp1 = uint32_t(s.hi.replay);
   d.pairs = c->pairs.p + s.pair_lo; d.n_pairs = s.pair_hi - s.pair_lo;
@@ -343,8 +344,7 @@ void run_kernels(mph_ctx* c) {
   if (d.r1 > d.r0) {
     // reads without an entry in the side table: no allele call, no bad base, no variant inside
     const size_t n = size_t(d.r1 - d.r0);
-    CU(cudaMemsetAsync(c->call_S.p + d.r0, 0, n * 8, c->stream));
-    CU(cudaMemsetAsync(c->call_B.p + d.r0, 0, n * 8, c->stream));
+    // (call_S / call_B are written by K1 for the reads of the side table only; every reader checks call_flags / read_nv first)
     CU(cudaMemsetAsync(c->call_flags.p + d.r0, 0, n, c->stream));
     CU(cudaMemsetAsync(c->read_nv.p + d.r0, 0, n, c->stream));
   }

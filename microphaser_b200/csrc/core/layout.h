@@ -84,6 +84,10 @@ typedef struct {
   uint32_t pad;
 } MphChunk;
 
+// The window kernel works on groups of whole chunks of one segment (an MphChunk record with n <= MPH_GROUP_WINDOWS
+// and pad = index of its first chunk): one CTA scans the group's reads once and keeps a difference array over its windows.
+enum { MPH_GROUP_WINDOWS = 128 };
+
 // Per-read fields, as the core functions see them in registers. In memory the reads are
 // structure-of-arrays (include/microphaser_gpu.h: mph_batch_in.read_*).
 //   seq_off : 16-byte units into the packed-base arena, where the read's record is

@@ -78,7 +78,7 @@ struct GeneMeta {
 
 // sizes of every per-gene-contiguous array after a gene has been packed: a batch can be cut at any gene boundary
 struct GeneMark {
-  uint64_t reads = 0, vr = 0, bases = 0, cigars = 0, vars = 0, ins = 0, segs = 0, chunks = 0, ref = 0, windows = 0, txs = 0, replay = 0, dq = 0, partners = 0;
+  uint64_t reads = 0, vr = 0, bases = 0, cigars = 0, vars = 0, ins = 0, segs = 0, chunks = 0, groups = 0, ref = 0, windows = 0, txs = 0, replay = 0, dq = 0, partners = 0;
 };
 
 struct Batch {
@@ -103,6 +103,7 @@ struct Batch {
   // geometry
   std::vector<MphSegment> segs;
   std::vector<MphChunk> chunks;
+  std::vector<MphChunk> groups;  // up to MPH_GROUP_WINDOWS consecutive windows of one segment (whole chunks): the unit of the window kernel; pad = its first chunk
   std::vector<uint8_t> ref;  // per-segment reference slices
   std::vector<uint32_t> stopmap;  // 1 bit per ref byte: a stop codon (for the slice's strand) starts here; 2 words of slack
   uint64_t n_windows = 0;
@@ -410,6 +411,24 @@ class Packer {
           c.vb1 = mph_var_lb(b_.vars.data(), c.va0, sg.var_hi, e_max);
           b_.chunks.push_back(c);
         }
+        // window-kernel groups: runs of whole chunks of this segment, MPH_GROUP_WINDOWS windows at most; the read / variant
+        // ranges of a group are the unions of its chunks' ranges (both are intervals: s and e are monotone)
+        {
+          const uint32_t c_first = b_.seg_chunk0.back(), c_end = uint32_t(b_.chunks.size());
+          const uint32_t per = MPH_GROUP_WINDOWS / chunk_windows_;
+          for (uint32_t c0 = c_first; c0 < c_end; c0 += per) {
+            const uint32_t c1 = std::min(c_end, c0 + per);
+            MphChunk gr = b_.chunks[c0];
+            gr.pad = c0;
+            for (uint32_t c = c0 + 1; c < c1; ++c) {
+              const MphChunk& ch = b_.chunks[c];
+              gr.n += ch.n;
+              gr.rlo = std::min(gr.rlo, ch.rlo); gr.rhi = std::max(gr.rhi, ch.rhi);
+              gr.va0 = std::min(gr.va0, ch.va0); gr.vb1 = std::max(gr.vb1, ch.vb1);
+            }
+            b_.groups.push_back(gr);
+          }
+        }
       }
       tm.seg_hi = uint32_t(b_.segs.size());
       // junctions that can produce records: a variant inside one of the two windows whose lists the merge reads
@@ -529,7 +548,7 @@ class Packer {
     b_.genes.push_back(std::move(gm));
     GeneMark mk;
     mk.reads = b_.read_start.size(); mk.vr = b_.vr_read.size(); mk.bases = b_.bases.size(); mk.cigars = b_.cigars.size(); mk.vars = b_.vars.size(); mk.ins = b_.ins_bytes.size();
-    mk.segs = b_.segs.size(); mk.chunks = b_.chunks.size(); mk.ref = b_.ref.size(); mk.windows = b_.n_windows; mk.txs = b_.txs.size();
+    mk.segs = b_.segs.size(); mk.chunks = b_.chunks.size(); mk.groups = b_.groups.size(); mk.ref = b_.ref.size(); mk.windows = b_.n_windows; mk.txs = b_.txs.size();
     mk.replay = b_.replay.size(); mk.dq = b_.replay_dq.size(); mk.partners = b_.partner_a.size();
     b_.marks.push_back(mk);
   }

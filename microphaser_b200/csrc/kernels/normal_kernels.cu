@@ -73,7 +73,7 @@ __device__ void window_hist_warp_normal(const DeviceBatch& d, const MphSegment& 
         uint32_t kc;
         copies = mph_nrm_rev_copies(sg, k, g, st, en, &kc);
       }
-      if (copies) { S = d.call_S[r]; vlo = d.read_vlo[r]; }
+      if (copies && (d.call_flags[r] & 1u)) { S = d.call_S[r]; vlo = d.read_vlo[r]; }  // S is only written for reads with a call
     }
     uint32_t cs = copies;
     for (int o = 16; o; o >>= 1) cs += __shfl_xor_sync(FULL, cs, o);

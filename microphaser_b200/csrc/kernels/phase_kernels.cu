@@ -4,12 +4,12 @@
 //                      over the variants inside the read (reference src/microphasing.rs:78-139), expanded to
 //                      per-read arrays; reads without an entry were zero-filled before. Packed 4-bit bases are
 //                      touched only where a variant lies.
-//   K2 k_window_hist   warp per chunk of <= 32 consecutive windows of one exon, two phases: lane = read builds a
-//                      difference array over the windows for the plain reads and a short list of the reads that
-//                      carry allele calls; lane = window prefix-sums it into depth and evaluates the closed form
-//                      of the ObservationMatrix (:157-343) for the listed reads only; haplotype keys go to
-//                      per-lane shared-memory tables (:383-411). k_window_hist_wide redoes windows whose keys
-//                      overflow a lane table, one warp per window.
+//   K2 k_window_hist   CTA per group of <= 128 consecutive windows of one exon, two phases: thread = read builds a
+//                      difference array over the windows for the plain reads (run ends by arithmetic on the window
+//                      grid) and a list of the reads that carry allele calls; thread = window prefix-sums it into
+//                      depth and evaluates the closed form of the ObservationMatrix (:157-343) for the listed reads
+//                      only; haplotype keys go to per-window shared-memory tables (:383-411). k_window_hist_wide
+//                      redoes windows whose keys overflow a table, one warp per window.
 //   K3 k_assemble      thread per extra haplotype key: sequence walk (:458-603), stop codon test (:42-76,
 //                      :694-697) and the SHA-1 record id (:667-675) while the bytes are in registers / L1.
 //   K4 k_flag_count / k_block_scan / k_scatter   stable compaction of the interesting windows so the
@@ -79,7 +79,8 @@ __device__ __forceinline__ MphPair eval_flagged(const DeviceBatch& d, const MphS
     if (q != NONE) {
       const uint32_t qs = d.read_start[q], qe = d.read_end[q], qv = d.read_vlo[q];
       if (qs <= g.s && qe >= g.e) {
-        const uint64_t Bq = d.call_B[q] | (d.call_S[q] & mph_range_mask(sg.sl_va, sg.sl_vb, qv));
+        const bool qc = (d.call_flags[q] & 1u) != 0;  // S / B are only written for reads with a call
+        const uint64_t Bq = qc ? (d.call_B[q] | (d.call_S[q] & mph_range_mask(sg.sl_va, sg.sl_vb, qv))) : 0;
         const uint32_t kq = mph_rev_entry(sg, d.vars, k, qs, qe, qv, Bq);
         if (kq != NONE && (kq < ke || (kq == ke && q < r))) ke = NONE;
       }
@@ -110,7 +111,8 @@ __device__ void window_hist_warp(const DeviceBatch& d, const MphSegment& sg, uin
       const uint32_t st = d.read_start[r], en = d.read_end[r];
       if (en >= g.e) {
         const uint32_t cf = d.call_flags[r] | ((d.read_flags[r] & MPH_RF_PARTNER) ? 2u : 0u);
-        const MphPair p = eval_flagged(d, sg, rev, k, g, va, vb, r, st, en, cf, d.read_vlo[r], d.call_S[r], d.call_B[r]);
+        const uint64_t S = (cf & 1u) ? d.call_S[r] : 0, B = (cf & 1u) ? d.call_B[r] : 0;  // S / B are only written for reads with a call
+        const MphPair p = eval_flagged(d, sg, rev, k, g, va, vb, r, st, en, cf, d.read_vlo[r], S, B);
         member = p.member != 0;
         counted = member && !p.bad;
         hap = p.hap;
@@ -197,223 +199,246 @@ __global__ void __launch_bounds__(K2_WARPS * 32) k_window_hist_wide(const Device
   }
 }
 
-// Main K2: one warp per chunk (<= 32 consecutive windows of one exon), two phases.
-//  A (lane = read): walk the union of the windows' candidate ranges 32 reads at a time. A read
-//    without allele calls / bad bases / duplicate qname is an observation of a *contiguous* run of
-//    the chunk's windows (membership is monotone in the iteration number), so it contributes a
-//    +1/-1 pair to a 33-entry difference array instead of 32 separate tests. Reads that carry an
-//    allele call go to a short list, and so do the rare reads that need the full closed form.
-//  B (lane = window): prefix-sum the difference array -> depth and the (hap 0, frame 0) count; then
-//    only the listed reads are broadcast and evaluated per window, and their haplotype keys go to
-//    per-lane shared-memory tables.
+// Main K2: one CTA per group (<= 128 consecutive windows of one exon, thread = window), two phases per tile of reads.
+//  A (thread = read): every thread takes reads of the group's candidate range (the union over its windows, resolved by
+//    the packer), four per tile. A read without allele calls / bad bases / duplicate qname is an observation of a
+//    *contiguous* run of the group's windows (membership is monotone in the iteration number); the run's ends come from
+//    arithmetic on the window grid (windows sit `k_stride` iterations apart) corrected against the table of window
+//    bounds in shared memory, and the read contributes a +1 / -1 pair to a difference array in shared memory. Reads that
+//    carry an allele call go to a list, and so do the rare reads that need the full closed form.
+//  B (thread = window): only the listed reads are evaluated per window; their haplotype keys go to per-thread
+//    shared-memory tables. After the last tile the difference array is prefix-summed into depth and the
+//    (hap 0, frame 0) count.
+// A read is visited once per exon it can overlap instead of once per 32 windows, and no per-read search runs over the
+// window table (round 1: a warp per 32-window chunk, three binary searches per read and chunk).
 constexpr int K2_LANE_KEYS = 4;
+constexpr int SG_THREADS = MPH_GROUP_WINDOWS;  // threads per CTA = windows per group
+constexpr int SG_RPT = 4;                      // reads per thread and tile
+constexpr int SG_TILE = SG_THREADS * SG_RPT;
 
-__global__ void __launch_bounds__(K2_WARPS * 32) k_window_hist(const DeviceBatch d) {
-  // per-lane key tables, [key][lane] so that a warp touches 32 distinct banks
-  __shared__ uint64_t t_hap[K2_WARPS][K2_LANE_KEYS][32];
-  __shared__ uint32_t t_cnt[K2_WARPS][K2_LANE_KEYS][32];
-  __shared__ uint32_t t_frm[K2_WARPS][K2_LANE_KEYS][32];
-  __shared__ MphSegment s_seg[K2_WARPS];
-  __shared__ uint32_t s_s[K2_WARPS][32], s_e[K2_WARPS][32];
-  __shared__ int s_add[K2_WARPS][34];
-  __shared__ uint32_t s_list[K2_WARPS][K2_LIST];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t chunk = d.c0 + blockIdx.x * K2_WARPS + warp;
-  if (chunk >= d.c1) return;
-  const MphChunk ch = d.chunks[chunk];
-  if (lane < (int)(sizeof(MphSegment) / 4)) reinterpret_cast<uint32_t*>(&s_seg[warp])[lane] = reinterpret_cast<const uint32_t*>(&d.segs[ch.seg])[lane];
-  s_add[warp][lane] = 0;
-  if (lane < 2) s_add[warp][32 + lane] = 0;
-  __syncwarp();
-  const MphSegment& sg = s_seg[warp];
+__global__ void __launch_bounds__(SG_THREADS) k_window_hist(const DeviceBatch d) {
+  // per-window key tables, [key][window] so that a warp touches 32 distinct banks
+  __shared__ uint64_t t_hap[K2_LANE_KEYS][SG_THREADS];
+  __shared__ uint32_t t_cnt[K2_LANE_KEYS][SG_THREADS];
+  __shared__ uint32_t t_frm[K2_LANE_KEYS][SG_THREADS];
+  __shared__ MphSegment s_seg;
+  __shared__ uint32_t s_s[SG_THREADS], s_e[SG_THREADS];
+  __shared__ int s_add[SG_THREADS + 2];
+  __shared__ uint32_t s_list[SG_TILE];
+  __shared__ uint32_t s_list_n;
+  __shared__ int s_wsum[SG_THREADS / 32];
+  __shared__ uint32_t s_ksum[SG_THREADS / 32];
+  __shared__ uint32_t s_base;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const MphChunk gr = d.groups[d.g0 + blockIdx.x];
+  if (t < (int)(sizeof(MphSegment) / 4)) reinterpret_cast<uint32_t*>(&s_seg)[t] = reinterpret_cast<const uint32_t*>(&d.segs[gr.seg])[t];
+  s_add[t] = 0;
+  if (t < 2) s_add[SG_THREADS + t] = 0;
+  __syncthreads();
+  const MphSegment& sg = s_seg;
   if (sg.flags & MPH_SF_REPLAY) return;  // the whole transcript goes through k_replay
   const bool rev = (sg.flags & MPH_SF_REVERSE) != 0;
   const bool has_fs = (sg.flags & MPH_SF_HAS_FS) != 0;
-  const int n = (int)ch.n;
-  const bool active = lane < n;
-  const uint32_t i = ch.i_first + (active ? lane : 0);
+  const int n = (int)gr.n;
+  const bool active = t < n;
+  const uint32_t i = gr.i_first + (active ? t : 0);
   const uint32_t k = sg.k_first + i * sg.k_stride;
   const MphGeom g = mph_geom(sg, k);
-  const uint32_t va = mph_var_lb(d.vars, ch.va0, ch.vb1, g.s);
-  const uint32_t vb = mph_var_lb(d.vars, va, ch.vb1, g.e);
+  const uint32_t va = mph_var_lb(d.vars, gr.va0, gr.vb1, g.s);
+  const uint32_t vb = mph_var_lb(d.vars, va, gr.vb1, g.e);
   const uint32_t nvar = vb - va;
   if (active && nvar > 64) raise(d, MPH_E_VARS_PER_WINDOW);
-  const bool chunk_has_var = ch.vb1 > ch.va0;
-  s_s[warp][lane] = g.s;
-  s_e[warp][lane] = g.e;
+  const bool group_has_var = gr.vb1 > gr.va0;
+  s_s[t] = g.s;
+  s_e[t] = g.e;
   const uint32_t s0 = sg.off0 - sg.ceo;
-  const uint32_t rlo = ch.rlo, rhi = ch.rhi;  // union of the lanes' candidate ranges, resolved by the packer
+  const uint32_t rlo = gr.rlo, rhi = gr.rhi;  // union of the windows' candidate ranges, resolved by the packer
   const uint32_t my_s = active ? g.s : 0u;
-  const uint32_t my_e = active ? g.e : 0xFFFFFFFFu;  // inactive lanes: nothing encloses e = 0xFFFFFFFF
+  const uint32_t my_e = active ? g.e : 0xFFFFFFFFu;  // inactive threads: nothing encloses e = 0xFFFFFFFF
   const int64_t c1_lo = (int64_t)s0 - (int64_t)sg.K;  // forward: class-1 reads (offered at iteration 0)
+  const int64_t kf = (int64_t)sg.k_first, ks = (int64_t)sg.k_stride, i_first = (int64_t)gr.i_first;
   uint32_t depth_x = 0, n_keys = 0;  // depth_x: observations counted in phase B (complex reads)
   int c0_adj = 0;
   bool overflow = false;
-  __syncwarp();
   auto add_key = [&](uint64_t hap, uint32_t frame) {
-    uint32_t t = 0;
-    for (; t < n_keys; ++t)
-      if (t_hap[warp][t][lane] == hap && t_frm[warp][t][lane] == frame) break;
-    if (t == n_keys) {
+    uint32_t q = 0;
+    for (; q < n_keys; ++q)
+      if (t_hap[q][t] == hap && t_frm[q][t] == frame) break;
+    if (q == n_keys) {
       if (n_keys == K2_LANE_KEYS || d.force_wide) { overflow = true; return; }
-      t_hap[warp][t][lane] = hap;
-      t_frm[warp][t][lane] = frame;
-      t_cnt[warp][t][lane] = 0;
+      t_hap[q][t] = hap;
+      t_frm[q][t] = frame;
+      t_cnt[q][t] = 0;
       ++n_keys;
     }
-    t_cnt[warp][t][lane] += 1;
+    t_cnt[q][t] += 1;
   };
-  // phase B body for the listed reads (lane = window)
-  auto process_list = [&](uint32_t list_n) {
-    for (uint32_t x = 0; x < list_n; ++x) {
-      const uint32_t code = s_list[warp][x];
-      const uint32_t r = code & 0x7FFFFFFFu;
-      const uint32_t st = d.read_start[r], en = d.read_end[r], vlo = d.read_vlo[r];
-      const uint64_t S = d.call_S[r];
-      if (!(code >> 31)) {
-        // already counted as a plain observation; windows with variants still need its haplotype
-        if (nvar == 0) continue;
-        bool member;
-        if (!rev) member = en >= my_e && ((st <= s0) ? ((int64_t)st >= c1_lo) : (st > sg.off0 && st - sg.off0 <= k));
-        else member = st <= my_s && en >= my_e && (uint64_t)st + sg.K >= my_s;
-        if (!member) continue;
-        const uint64_t bits = mph_window_bits(S, vlo, va, nvar);
-        const uint64_t hap = rev ? bits : (mph_bitrev64(bits) >> (64 - nvar));
-        if (hap != 0) {
-          c0_adj -= 1;
-          add_key(hap, 0);
-        }
-      } else if (en >= my_e && st <= my_s) {
-        const uint32_t cf = d.call_flags[r] | ((d.read_flags[r] & MPH_RF_PARTNER) ? 2u : 0u);
-        const MphPair p = eval_flagged(d, sg, rev, k, g, va, vb, r, st, en, cf, vlo, S, d.call_B[r]);
-        depth_x += p.member;
-        if (p.member && !p.bad) {
-          if (p.hap == 0 && p.frame == 0) c0_adj += 1;
-          else add_key(p.hap, p.frame);
-        }
+  // local window index of iteration `kk` rounded down / up on the window grid, relative to the group's first window
+  auto grid_floor = [&](int64_t kk) -> int64_t { const int64_t x = kk - kf; return (x >= 0 ? x / ks : -((-x + ks - 1) / ks)) - i_first; };
+  auto grid_ceil = [&](int64_t kk) -> int64_t { const int64_t x = kk - kf; return (x >= 0 ? (x + ks - 1) / ks : -((-x) / ks)) - i_first; };
+  auto clampi = [](int64_t v, int lo, int hi) -> int { return v < lo ? lo : (v > hi ? hi : (int)v); };
+  __syncthreads();
+  for (uint32_t base = rlo; base < rhi; base += SG_TILE) {
+    if (t == 0) s_list_n = 0;
+    __syncthreads();
+    // ---- phase A (thread = read)
+    uint32_t a_st[SG_RPT], a_en[SG_RPT], a_cf[SG_RPT];
+#pragma unroll
+    for (int u = 0; u < SG_RPT; ++u) {
+      const uint32_t r = base + u * SG_THREADS + t;
+      if (r < rhi) {
+        a_st[u] = d.read_start[r];
+        a_en[u] = d.read_end[r];
+        a_cf[u] = (uint32_t)d.call_flags[r] | ((d.read_flags[r] & MPH_RF_PARTNER) ? 2u : 0u);
       }
     }
-  };
-  // ---- phase A (lane = read)
-  uint32_t list_n = 0;
-  const uint32_t* ss = s_s[warp];
-  const uint32_t* se = s_e[warp];
-  for (uint32_t base = rlo; base < rhi; base += 32) {
-    const uint32_t r = base + lane;
-    int cls = 0, ilo = 1, ihi = 0;
-    if (r < rhi) {
-      const uint32_t st = d.read_start[r], en = d.read_end[r];
-      const uint32_t cf = d.call_flags[r] | ((d.read_flags[r] & MPH_RF_PARTNER) ? 2u : 0u);
+#pragma unroll
+    for (int u = 0; u < SG_RPT; ++u) {
+      const uint32_t r = base + u * SG_THREADS + t;
+      if (r >= rhi) continue;
+      const uint32_t st = a_st[u], en = a_en[u], cf = a_cf[u];
+      int cls;
       if (cf == 0 && !has_fs) {
         cls = 1;
       } else {
         const uint32_t vlo = d.read_vlo[r];
-        const uint64_t S = d.call_S[r], B = d.call_B[r];
+        const uint64_t S = (cf & 1u) ? d.call_S[r] : 0, B = (cf & 1u) ? d.call_B[r] : 0;
         const uint64_t Bx = B | (S & mph_range_mask(sg.sl_va, sg.sl_vb, vlo));
-        if (Bx == 0 && !(cf & 2u) && !has_fs) cls = (S != 0 && chunk_has_var) ? 2 : 1;
+        if (Bx == 0 && !(cf & 2u) && !has_fs) cls = (S != 0 && group_has_var) ? 2 : 1;
         else cls = 3;
       }
+      int ilo = 1, ihi = 0;
       if (cls != 3) {
-        // run of windows [ilo, ihi] of this chunk at which the read is an observation
+        // run of windows [ilo, ihi] of this group at which the read is an observation
         if (!rev) {
-          int a = 0, b = n;  // e non-decreasing: windows with e <= en form a prefix
-          while (a < b) { const int m = (a + b) >> 1; if (se[m] <= en) a = m + 1; else b = m; }
-          ihi = a - 1;
+          // e is non-decreasing: windows with e <= en form a prefix; e = off0 + k + ewl but for the exon's last window(s)
+          ihi = en >= sg.off0 + sg.ewl ? clampi(grid_floor((int64_t)en - sg.off0 - sg.ewl), -1, n - 1) : -1;
+          while (ihi + 1 < n && s_e[ihi + 1] <= en) ++ihi;
+          while (ihi >= 0 && s_e[ihi] > en) --ihi;
           if (st <= s0) {
             ilo = ((int64_t)st >= c1_lo) ? 0 : n;
           } else if (st <= sg.off0) {
             ilo = n;
           } else {
-            const uint32_t k_ins = st - sg.off0;  // first window with k >= k_ins
-            const uint32_t t = k_ins > sg.k_first ? (k_ins - sg.k_first + sg.k_stride - 1) / sg.k_stride : 0;
-            ilo = t > ch.i_first ? (int)min(t - ch.i_first, (uint32_t)n) : 0;
+            ilo = clampi(grid_ceil((int64_t)st - sg.off0), 0, n);  // first window at or after the iteration that offers the read
           }
         } else {
-          int a = 0, b = n;  // s non-increasing: windows with s >= st form a prefix
-          while (a < b) { const int m = (a + b) >> 1; if (ss[m] >= st) a = m + 1; else b = m; }
-          ihi = a - 1;
-          a = 0; b = n;      // first window with e <= en
-          while (a < b) { const int m = (a + b) >> 1; if (se[m] > en) a = m + 1; else b = m; }
-          ilo = a;
-          const uint64_t lim = (uint64_t)st + sg.K;
-          a = 0; b = n;      // first window with s <= st + K
-          while (a < b) { const int m = (a + b) >> 1; if ((uint64_t)ss[m] > lim) a = m + 1; else b = m; }
-          if (a > ilo) ilo = a;
+          // s is non-increasing (s = off0 - k but for the exon's last window(s)): windows with s >= st form a prefix
+          ihi = st <= sg.off0 ? clampi(grid_floor((int64_t)sg.off0 - st), -1, n - 1) : -1;
+          while (ihi + 1 < n && s_s[ihi + 1] >= st) ++ihi;
+          while (ihi >= 0 && s_s[ihi] < st) --ihi;
+          // first window with e <= en (e = off0 - k + ewl, non-increasing)
+          int a = clampi(grid_ceil((int64_t)sg.off0 + sg.ewl - en), 0, n);
+          while (a > 0 && s_e[a - 1] <= en) --a;
+          while (a < n && s_e[a] > en) ++a;
+          // first window with s <= st + K
+          const int64_t lim = (int64_t)st + sg.K;
+          int b = clampi(grid_ceil((int64_t)sg.off0 - lim), 0, n);
+          while (b > 0 && (int64_t)s_s[b - 1] <= lim) --b;
+          while (b < n && (int64_t)s_s[b] > lim) ++b;
+          ilo = a > b ? a : b;
+        }
+      }
+      const bool counted = cls != 3 && ilo <= ihi;
+      if (counted) {
+        atomicAdd(&s_add[ilo], 1);
+        atomicAdd(&s_add[ihi + 1], -1);
+      }
+      if ((cls == 2 && counted) || cls == 3) s_list[atomicAdd(&s_list_n, 1u)] = r | (cls == 3 ? 0x80000000u : 0u);
+    }
+    __syncthreads();
+    // ---- phase B (thread = window): the listed reads of this tile
+    const uint32_t list_n = s_list_n;
+    if (active) {
+      for (uint32_t x = 0; x < list_n; ++x) {
+        const uint32_t code = s_list[x];
+        const uint32_t r = code & 0x7FFFFFFFu;
+        if (!(code >> 31)) {
+          // already counted as a plain observation; windows with variants still need its haplotype
+          if (nvar == 0) continue;
+          const uint32_t st = d.read_start[r], en = d.read_end[r];
+          bool member;
+          if (!rev) member = en >= my_e && ((st <= s0) ? ((int64_t)st >= c1_lo) : (st > sg.off0 && st - sg.off0 <= k));
+          else member = st <= my_s && en >= my_e && (uint64_t)st + sg.K >= my_s;
+          if (!member) continue;
+          const uint64_t bits = mph_window_bits(d.call_S[r], d.read_vlo[r], va, nvar);
+          const uint64_t hap = rev ? bits : (mph_bitrev64(bits) >> (64 - nvar));
+          if (hap != 0) {
+            c0_adj -= 1;
+            add_key(hap, 0);
+          }
+        } else {
+          const uint32_t st = d.read_start[r], en = d.read_end[r];
+          if (en < my_e || st > my_s) continue;
+          const uint32_t cf = (uint32_t)d.call_flags[r] | ((d.read_flags[r] & MPH_RF_PARTNER) ? 2u : 0u);
+          const uint64_t S = (cf & 1u) ? d.call_S[r] : 0, B = (cf & 1u) ? d.call_B[r] : 0;
+          const MphPair p = eval_flagged(d, sg, rev, k, g, va, vb, r, st, en, cf, d.read_vlo[r], S, B);
+          depth_x += p.member;
+          if (p.member && !p.bad) {
+            if (p.hap == 0 && p.frame == 0) c0_adj += 1;
+            else add_key(p.hap, p.frame);
+          }
         }
       }
     }
-    const bool counted = (cls == 1 || cls == 2) && ilo <= ihi;
-    // warp-aggregated updates of the difference array (one writer per distinct index)
-    {
-      const int key = counted ? ilo : 33;
-      const unsigned m = __match_any_sync(FULL, key);
-      if (counted && lane == __ffs(m) - 1) s_add[warp][ilo] += __popc(m);
-      __syncwarp();
-      const int key2 = counted ? ihi + 1 : 33;
-      const unsigned m2 = __match_any_sync(FULL, key2);
-      if (counted && lane == __ffs(m2) - 1) s_add[warp][ihi + 1] -= __popc(m2);
-      __syncwarp();
-    }
-    const bool need = (cls == 2 && counted) || cls == 3;
-    const unsigned nm = __ballot_sync(FULL, need);
-    if (nm) {
-      if (list_n + __popc(nm) > K2_LIST) {
-        process_list(list_n);
-        list_n = 0;
-        __syncwarp();
-      }
-      if (need) s_list[warp][list_n + __popc(nm & ((1u << lane) - 1))] = r | (cls == 3 ? 0x80000000u : 0u);
-      list_n += __popc(nm);
-      __syncwarp();
-    }
+    __syncthreads();
   }
-  process_list(list_n);
-  // ---- phase B: prefix sum of the difference array
-  int run = s_add[warp][lane];
+  // ---- prefix sum of the difference array over the group's windows
+  int run = s_add[t];
   for (int o = 1; o < 32; o <<= 1) {
     const int y = __shfl_up_sync(FULL, run, o);
     if (lane >= o) run += y;
   }
+  if (lane == 31) s_wsum[warp] = run;
+  __syncthreads();
+  for (int w = 0; w < warp; ++w) run += s_wsum[w];
   const uint32_t depth = (uint32_t)run + depth_x;
   const uint32_t c0 = (uint32_t)(run + c0_adj);
-  // each lane sorts its keys (reference BTreeMap order :383,434)
+  // each thread sorts its keys (reference BTreeMap order :383,434)
   for (uint32_t a = 1; a < n_keys; ++a) {
     MphHist key;
-    key.hap = t_hap[warp][a][lane]; key.frame = t_frm[warp][a][lane]; key.count = t_cnt[warp][a][lane];
+    key.hap = t_hap[a][t]; key.frame = t_frm[a][t]; key.count = t_cnt[a][t];
     uint32_t b = a;
     while (b > 0) {
       MphHist prev;
-      prev.hap = t_hap[warp][b - 1][lane]; prev.frame = t_frm[warp][b - 1][lane]; prev.count = t_cnt[warp][b - 1][lane];
+      prev.hap = t_hap[b - 1][t]; prev.frame = t_frm[b - 1][t]; prev.count = t_cnt[b - 1][t];
       if (!hist_less(key, prev)) break;
-      t_hap[warp][b][lane] = prev.hap; t_frm[warp][b][lane] = prev.frame; t_cnt[warp][b][lane] = prev.count;
+      t_hap[b][t] = prev.hap; t_frm[b][t] = prev.frame; t_cnt[b][t] = prev.count;
       --b;
     }
-    t_hap[warp][b][lane] = key.hap; t_frm[warp][b][lane] = key.frame; t_cnt[warp][b][lane] = key.count;
+    t_hap[b][t] = key.hap; t_frm[b][t] = key.frame; t_cnt[b][t] = key.count;
   }
   const bool ovf = active && overflow;
   const uint32_t mine = (active && !ovf) ? n_keys : 0;
-  // warp-aggregated allocation in the key arena
+  // CTA-aggregated allocation in the key arena
   uint32_t incl = mine;
   for (int o = 1; o < 32; o <<= 1) {
     const uint32_t y = __shfl_up_sync(FULL, incl, o);
     if (lane >= o) incl += y;
   }
-  const uint32_t total = __shfl_sync(FULL, incl, 31);
-  uint32_t base_off = 0;
-  if (lane == 0 && total) base_off = atomicAdd(&d.counters[CTR_HIST], total);
-  base_off = __shfl_sync(FULL, base_off, 0);
+  if (lane == 31) s_ksum[warp] = incl;
+  __syncthreads();
+  uint32_t before = 0, total = 0;
+  for (int w = 0; w < SG_THREADS / 32; ++w) {
+    if (w < warp) before += s_ksum[w];
+    total += s_ksum[w];
+  }
+  if (t == 0) s_base = total ? atomicAdd(&d.counters[CTR_HIST], total) : 0u;
+  __syncthreads();
+  const uint32_t base_off = s_base;
   const bool fits = base_off + total <= d.hist_cap;
-  if (lane == 0 && total && !fits) raise(d, MPH_E_HIST_OVERFLOW);
+  if (t == 0 && total && !fits) raise(d, MPH_E_HIST_OVERFLOW);
+  const uint32_t chunk = gr.pad + ((uint32_t)t >> 5);
   if (active && !ovf) {
     MphWinOut wo;
     wo.depth = depth;
     wo.c0 = c0;
     wo.n_extra = fits ? mine : 0;
-    wo.extra_off = base_off + incl - mine;
+    wo.extra_off = base_off + before + incl - mine;
     if (fits)
       for (uint32_t a = 0; a < mine; ++a) {
         MphHist h;
-        h.hap = t_hap[warp][a][lane]; h.frame = t_frm[warp][a][lane]; h.count = t_cnt[warp][a][lane];
+        h.hap = t_hap[a][t]; h.frame = t_frm[a][t]; h.count = t_cnt[a][t];
         d.hist[wo.extra_off + a] = h;
         d.hist_win[wo.extra_off + a] = (chunk << 5) | (uint32_t)lane;
       }
@@ -590,7 +615,8 @@ void launch_window_hist(const DeviceBatch& d, cudaStream_t st) {
   if (d.c1 <= d.c0) return;
   const uint32_t nc = d.c1 - d.c0;
   if (d.mode == 1) return launch_window_hist_normal(d, st);
-  k_window_hist<<<(nc + K2_WARPS - 1) / K2_WARPS, K2_WARPS * 32, 0, st>>>(d);
+  (void)nc;
+  if (d.g1 > d.g0) k_window_hist<<<d.g1 - d.g0, SG_THREADS, 0, st>>>(d);
   // windows with more distinct haplotypes than a lane table holds (rare): one warp per window
   k_window_hist_wide<<<148 * 8, K2_WARPS * 32, 0, st>>>(d);
 }

@@ -16,7 +16,8 @@ struct DeviceBatch {
   // the slice of the batch one launch sequence works on (a stage of the copy / compute / residue pipeline, or everything)
   uint32_t r0 = 0, r1 = 0;    // reads
   uint32_t vr0 = 0, vr1 = 0;  // entries of the variant-read side table (K1)
-  uint32_t c0 = 0, c1 = 0;    // chunks (K2, K5)
+  uint32_t c0 = 0, c1 = 0;    // chunks (K5, normal-mode K2)
+  uint32_t g0 = 0, g1 = 0;    // window-kernel groups (K2)
   uint32_t w0 = 0, w1 = 0;    // windows (K4)
   uint32_t rp0 = 0, rp1 = 0;  // replay units
   uint32_t mode = 0;        // 0 somatic, 1 normal (reference src/normal_microphasing.rs)
@@ -43,6 +44,7 @@ struct DeviceBatch {
   const uint8_t* ins_bytes = nullptr;
   const MphSegment* segs = nullptr;
   const MphChunk* chunks = nullptr;
+  const MphChunk* groups = nullptr;  // runs of whole chunks of one segment, <= MPH_GROUP_WINDOWS windows (layout.h)
   const uint8_t* ref = nullptr;
   const uint32_t* stopmap = nullptr;  // 1 bit per ref byte: a stop codon starts here
   const uint8_t* tx_id_bytes = nullptr;  // transcript ids (record ids are hashed on the device)
