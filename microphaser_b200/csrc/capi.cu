@@ -103,7 +103,7 @@ struct mph_ctx {
   std::string last_error;
   const mph_batch* cur = nullptr;
   mphk::DeviceBatch d;
-  DevBuf<uint32_t> read_start, read_end, read_vlo, read_vr, vr_read, vr_vlo, vr_seq_off, vr_cig_off, cigars, block_counts, iw, counters, seg_live, ovf_list, stopmap, hist_win, win_depth, seg_chunk0, dq_init, seg_err, tx_id_off, o_read, o_key, o_frame, win_voff, vlist, iw_voff;
+  DevBuf<uint32_t> read_start, read_end, read_vlo, read_vr, vr_read, vr_vlo, vr_seq_off, vr_cig_off, cigars, block_counts, iw, counters, seg_live, ovf_list, stopmap, hist_win, win_depth, seg_chunk0, dq_init, seg_err, tx_id_off, o_read, o_key, o_frame, win_voff, vlist, iw_voff, seg_work_off, seg_list, seg_list_n;
   DevBuf<uint16_t> vr_lseq, vr_ncig;
   DevBuf<uint8_t> tx_id_bytes;
   DevBuf<uint8_t> read_nv, vr_nv, read_flags, bases, ins_bytes, ref, call_flags, seq, win_flag, o_flags, o_inmat;
@@ -112,7 +112,9 @@ struct mph_ctx {
   DevBuf<uint2> pairs;
   DevBuf<MphVar> vars;
   DevBuf<MphSegment> segs;
-  DevBuf<MphChunk> chunks, groups;
+  DevBuf<MphChunk> chunks;
+  DevBuf<MphSegWork> seg_work;
+  DevBuf<int> win_diff;
   DevBuf<uint64_t> call_S, call_B;
   DevBuf<MphWinOut> win_out, iw_out;
   DevBuf<MphHist> hist;
@@ -166,7 +168,7 @@ void finish_batch(mph_batch* mb, bool pin) {
   auto bytes = [](auto& v) { return v.size() * sizeof(v[0]); };
   mb->h2d_bytes = bytes(b.read_start) + bytes(b.read_end) + bytes(b.read_flags) + bytes(b.vr_read) + bytes(b.vr_vlo) + bytes(b.vr_seq_off) +
                   bytes(b.vr_cig_off) + bytes(b.vr_lseq) + bytes(b.vr_ncig) + bytes(b.vr_nv) + bytes(b.bases) + bytes(b.cigars) +
-                  bytes(b.vars) + bytes(b.ins_bytes) + bytes(b.segs) + bytes(b.chunks) + bytes(b.groups) + bytes(b.ref) + bytes(b.stopmap) + bytes(mb->pairs) +
+                  bytes(b.vars) + bytes(b.ins_bytes) + bytes(b.segs) + bytes(b.chunks) + bytes(b.seg_work) + bytes(b.seg_work_off) + bytes(b.ref) + bytes(b.stopmap) + bytes(mb->pairs) +
                   bytes(b.tx_id_bytes) + bytes(b.tx_id_off) + bytes(b.replay) + bytes(b.replay_dq) + (b.replay.empty() ? 0 : bytes(b.seg_chunk0));
   if (pin) {
     auto reg = [&](auto& v) {
@@ -177,7 +179,7 @@ void finish_batch(mph_batch* mb, bool pin) {
         cudaGetLastError();
     };
     reg(b.read_start); reg(b.read_end); reg(b.read_flags); reg(b.vr_read); reg(b.vr_vlo); reg(b.vr_seq_off); reg(b.vr_cig_off); reg(b.vr_lseq);
-    reg(b.vr_ncig); reg(b.vr_nv); reg(b.bases); reg(b.cigars); reg(b.vars); reg(b.ins_bytes); reg(b.segs); reg(b.chunks); reg(b.groups); reg(b.ref); reg(b.stopmap);
+    reg(b.vr_ncig); reg(b.vr_nv); reg(b.bases); reg(b.cigars); reg(b.vars); reg(b.ins_bytes); reg(b.segs); reg(b.chunks); reg(b.seg_work); reg(b.seg_work_off); reg(b.ref); reg(b.stopmap);
     reg(mb->pairs);
     reg(b.tx_id_bytes); reg(b.tx_id_off); reg(b.replay); reg(b.replay_dq); reg(b.seg_chunk0);
     mb->pinned = true;
@@ -246,7 +248,8 @@ void prepare(mph_ctx* c, const mph_batch* mb) {
   c->vr_read.ensure(nvr + 1); c->vr_vlo.ensure(nvr + 1); c->vr_seq_off.ensure(nvr + 1); c->vr_cig_off.ensure(nvr + 1);
   c->vr_lseq.ensure(nvr + 1); c->vr_ncig.ensure(nvr + 1); c->vr_nv.ensure(nvr + 1);
   c->bases.ensure(b.bases.size() + 1); c->cigars.ensure(b.cigars.size() + 1); c->vars.ensure(b.vars.size() + 1); c->ins_bytes.ensure(b.ins_bytes.size() + 1);
-  c->segs.ensure(b.segs.size() + 1); c->chunks.ensure(b.chunks.size() + 1); c->groups.ensure(b.groups.size() + 1); c->ref.ensure(b.ref.size() + 1); c->stopmap.ensure(b.stopmap.size() + 1);
+  c->segs.ensure(b.segs.size() + 1); c->chunks.ensure(b.chunks.size() + 1); c->seg_work.ensure(b.seg_work.size() + 1); c->seg_work_off.ensure(b.seg_work_off.size() + 1);
+  c->win_diff.ensure(nw + 1); c->seg_list.ensure(size_t(b.seg_work_off.back()) + 1); c->seg_list_n.ensure(b.segs.size() + 1); c->ref.ensure(b.ref.size() + 1); c->stopmap.ensure(b.stopmap.size() + 1);
   c->pairs.ensure(mb->pairs.size() + 1); c->tx_id_bytes.ensure(b.tx_id_bytes.size() + 1); c->tx_id_off.ensure(b.tx_id_off.size() + 1);
   c->call_S.ensure(nr + 1); c->call_B.ensure(nr + 1); c->call_flags.ensure(nr + 1);
   c->win_out.ensure(nw + 1); c->hap0.ensure(nw + 1); c->win_flag.ensure(nw + 1);
@@ -266,7 +269,8 @@ void prepare(mph_ctx* c, const mph_batch* mb) {
   d.vr_read = c->vr_read.p; d.vr_vlo = c->vr_vlo.p; d.vr_seq_off = c->vr_seq_off.p; d.vr_cig_off = c->vr_cig_off.p;
   d.vr_lseq = c->vr_lseq.p; d.vr_ncig = c->vr_ncig.p; d.vr_nv = c->vr_nv.p;
   d.bases = c->bases.p; d.cigars = c->cigars.p; d.vars = c->vars.p;
-  d.ins_bytes = c->ins_bytes.p; d.segs = c->segs.p; d.chunks = c->chunks.p; d.groups = c->groups.p; d.ref = c->ref.p; d.stopmap = c->stopmap.p;
+  d.ins_bytes = c->ins_bytes.p; d.segs = c->segs.p; d.chunks = c->chunks.p; d.seg_work = c->seg_work.p; d.seg_work_off = c->seg_work_off.p;
+  d.win_diff = c->win_diff.p; d.seg_list = c->seg_list.p; d.seg_list_n = c->seg_list_n.p; d.ref = c->ref.p; d.stopmap = c->stopmap.p;
   d.call_S = reinterpret_cast<uint64_t*>(c->call_S.p); d.call_B = reinterpret_cast<uint64_t*>(c->call_B.p); d.call_flags = c->call_flags.p;
   d.win_out = c->win_out.p; d.hap0 = c->hap0.p; d.win_flag = c->win_flag.p; d.block_counts = c->block_counts.p;
   d.ovf_list = c->ovf_list.p;
@@ -309,7 +313,8 @@ void copy_stage(mph_ctx* c, const mph_batch* mb, const Stage& s, bool first, cud
   h2d_range(st, c->vr_nv, b.vr_nv, e0, e1);
   h2d_range(st, c->bases, b.bases, s.lo.bases, s.hi.bases); h2d_range(st, c->cigars, b.cigars, s.lo.cigars, s.hi.cigars);
   h2d_range(st, c->vars, b.vars, s.lo.vars, s.hi.vars); h2d_range(st, c->ins_bytes, b.ins_bytes, s.lo.ins, s.hi.ins);
-  h2d_range(st, c->segs, b.segs, s.lo.segs, s.hi.segs); h2d_range(st, c->chunks, b.chunks, s.lo.chunks, s.hi.chunks); h2d_range(st, c->groups, b.groups, s.lo.groups, s.hi.groups);
+  h2d_range(st, c->segs, b.segs, s.lo.segs, s.hi.segs); h2d_range(st, c->chunks, b.chunks, s.lo.chunks, s.hi.chunks);
+  h2d_range(st, c->seg_work, b.seg_work, s.lo.segs, s.hi.segs); h2d_range(st, c->seg_work_off, b.seg_work_off, s.lo.segs, s.hi.segs + 1);
   h2d_range(st, c->ref, b.ref, s.lo.ref, s.hi.ref);
   h2d_range(st, c->stopmap, b.stopmap, s.lo.ref / 32, s.hi.ref / 32 + 4);  // whole words; neighbouring stages rewrite the shared word with the same bits
   h2d_range(st, c->pairs, mb->pairs, s.pair_lo, s.pair_hi);
@@ -325,7 +330,8 @@ void set_ranges(mph_ctx* c, const Stage& s) {
   d.r0 = uint32_t(s.lo.reads); d.r1 = uint32_t(s.hi.reads);
   d.vr0 = uint32_t(s.lo.vr); d.vr1 = uint32_t(s.hi.vr);
   d.c0 = uint32_t(s.lo.chunks); d.c1 = uint32_t(s.hi.chunks);
-  d.g0 = uint32_t(s.lo.groups); d.g1 = uint32_t(s.hi.groups);
+  d.s0 = uint32_t(s.lo.segs); d.s1 = uint32_t(s.hi.segs);
+  d.it0 = c->cur->b.seg_work_off[s.lo.segs]; d.it1 = c->cur->b.seg_work_off[s.hi.segs];
   d.w0 = uint32_t(s.lo.windows); d.w1 = uint32_t(s.hi.windows);
   d.rp0 = uint32_t(s.lo.replay); d.rp1 = uint32_t(s.hi.replay);
   d.pairs = c->pairs.p + s.pair_lo; d.n_pairs = s.pair_hi - s.pair_lo;
@@ -356,6 +362,8 @@ void run_kernels(mph_ctx* c) {
   } else if (d.n_replay) {
     CU(cudaMemsetAsync(c->win_voff.p + d.w0, 0xFF, size_t(d.w1 - d.w0) * sizeof(uint32_t), c->stream));
   }
+  if (d.w1 > d.w0) CU(cudaMemsetAsync(c->win_diff.p + d.w0, 0, size_t(d.w1 - d.w0) * sizeof(int), c->stream));
+  if (d.s1 > d.s0) CU(cudaMemsetAsync(c->seg_list_n.p + d.s0, 0, size_t(d.s1 - d.s0) * sizeof(uint32_t), c->stream));
   mphk::launch_allele_call(d, c->stream);
   CU(cudaEventRecord(c->ev[3], c->stream));
   // measured on B200: on a second stream (any priority, with or without a dispatch head start) the replay and the

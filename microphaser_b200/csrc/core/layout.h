@@ -84,9 +84,12 @@ typedef struct {
   uint32_t pad;
 } MphChunk;
 
-// The window kernel works on groups of whole chunks of one segment (an MphChunk record with n <= MPH_GROUP_WINDOWS
-// and pad = index of its first chunk): one CTA scans the group's reads once and keeps a difference array over its windows.
-enum { MPH_GROUP_WINDOWS = 128 };
+// Per segment, 16 B: the union of its windows' candidate reads [rlo, rhi) and of the variants inside them [va0, vb1).
+// The read-run kernel (K2a) visits every (segment, read) pair of these ranges exactly once.
+typedef struct {
+  uint32_t rlo, rhi;
+  uint32_t va0, vb1;
+} MphSegWork;
 
 // Per-read fields, as the core functions see them in registers. In memory the reads are
 // structure-of-arrays (include/microphaser_gpu.h: mph_batch_in.read_*).

@@ -78,7 +78,7 @@ struct GeneMeta {
 
 // sizes of every per-gene-contiguous array after a gene has been packed: a batch can be cut at any gene boundary
 struct GeneMark {
-  uint64_t reads = 0, vr = 0, bases = 0, cigars = 0, vars = 0, ins = 0, segs = 0, chunks = 0, groups = 0, ref = 0, windows = 0, txs = 0, replay = 0, dq = 0, partners = 0;
+  uint64_t reads = 0, vr = 0, bases = 0, cigars = 0, vars = 0, ins = 0, segs = 0, chunks = 0, ref = 0, windows = 0, txs = 0, replay = 0, dq = 0, partners = 0;
 };
 
 struct Batch {
@@ -103,7 +103,10 @@ struct Batch {
   // geometry
   std::vector<MphSegment> segs;
   std::vector<MphChunk> chunks;
-  std::vector<MphChunk> groups;  // up to MPH_GROUP_WINDOWS consecutive windows of one segment (whole chunks): the unit of the window kernel; pad = its first chunk
+  // per segment: the union of its windows' candidate reads and variants (the read-run kernel visits every (segment, read) pair
+  // of these ranges once); seg_work_off = running sum of the range lengths, n_segs + 1 entries
+  std::vector<MphSegWork> seg_work;
+  std::vector<uint32_t> seg_work_off{0};
   std::vector<uint8_t> ref;  // per-segment reference slices
   std::vector<uint32_t> stopmap;  // 1 bit per ref byte: a stop codon (for the slice's strand) starts here; 2 words of slack
   uint64_t n_windows = 0;
@@ -411,23 +414,16 @@ class Packer {
           c.vb1 = mph_var_lb(b_.vars.data(), c.va0, sg.var_hi, e_max);
           b_.chunks.push_back(c);
         }
-        // window-kernel groups: runs of whole chunks of this segment, MPH_GROUP_WINDOWS windows at most; the read / variant
-        // ranges of a group are the unions of its chunks' ranges (both are intervals: s and e are monotone)
         {
+          MphSegWork sw;
+          sw.rlo = sw.rhi = sw.va0 = sw.vb1 = 0;
           const uint32_t c_first = b_.seg_chunk0.back(), c_end = uint32_t(b_.chunks.size());
-          const uint32_t per = MPH_GROUP_WINDOWS / chunk_windows_;
-          for (uint32_t c0 = c_first; c0 < c_end; c0 += per) {
-            const uint32_t c1 = std::min(c_end, c0 + per);
-            MphChunk gr = b_.chunks[c0];
-            gr.pad = c0;
-            for (uint32_t c = c0 + 1; c < c1; ++c) {
-              const MphChunk& ch = b_.chunks[c];
-              gr.n += ch.n;
-              gr.rlo = std::min(gr.rlo, ch.rlo); gr.rhi = std::max(gr.rhi, ch.rhi);
-              gr.va0 = std::min(gr.va0, ch.va0); gr.vb1 = std::max(gr.vb1, ch.vb1);
-            }
-            b_.groups.push_back(gr);
+          for (uint32_t c = c_first; c < c_end; ++c) {  // both unions are intervals: s and e are monotone in the iteration number
+            const MphChunk& ch = b_.chunks[c];
+            if (c == c_first) { sw.rlo = ch.rlo; sw.rhi = ch.rhi; sw.va0 = ch.va0; sw.vb1 = ch.vb1; }
+            else { sw.rlo = std::min(sw.rlo, ch.rlo); sw.rhi = std::max(sw.rhi, ch.rhi); sw.va0 = std::min(sw.va0, ch.va0); sw.vb1 = std::max(sw.vb1, ch.vb1); }
           }
+          b_.seg_work.push_back(sw);
         }
       }
       tm.seg_hi = uint32_t(b_.segs.size());
@@ -545,10 +541,17 @@ class Packer {
         ++q;
       }
     }
+    // work items of the read-run kernel: (segment, read) pairs; replayed transcripts take none (k_replay does their windows)
+    for (size_t si = b_.seg_work_off.size() - 1; si < b_.segs.size(); ++si) {
+      if (b_.segs[si].flags & MPH_SF_REPLAY) b_.seg_work[si].rhi = b_.seg_work[si].rlo;
+      const uint64_t next = uint64_t(b_.seg_work_off.back()) + (b_.seg_work[si].rhi - b_.seg_work[si].rlo);
+      if (next > 0xFFFFFF00ull) throw Unsupported("batch too large: split it into gene ranges");
+      b_.seg_work_off.push_back(uint32_t(next));
+    }
     b_.genes.push_back(std::move(gm));
     GeneMark mk;
     mk.reads = b_.read_start.size(); mk.vr = b_.vr_read.size(); mk.bases = b_.bases.size(); mk.cigars = b_.cigars.size(); mk.vars = b_.vars.size(); mk.ins = b_.ins_bytes.size();
-    mk.segs = b_.segs.size(); mk.chunks = b_.chunks.size(); mk.groups = b_.groups.size(); mk.ref = b_.ref.size(); mk.windows = b_.n_windows; mk.txs = b_.txs.size();
+    mk.segs = b_.segs.size(); mk.chunks = b_.chunks.size(); mk.ref = b_.ref.size(); mk.windows = b_.n_windows; mk.txs = b_.txs.size();
     mk.replay = b_.replay.size(); mk.dq = b_.replay_dq.size(); mk.partners = b_.partner_a.size();
     b_.marks.push_back(mk);
   }

@@ -199,246 +199,250 @@ __global__ void __launch_bounds__(K2_WARPS * 32) k_window_hist_wide(const Device
   }
 }
 
-// Main K2: one CTA per group (<= 128 consecutive windows of one exon, thread = window), two phases per tile of reads.
-//  A (thread = read): every thread takes reads of the group's candidate range (the union over its windows, resolved by
-//    the packer), four per tile. A read without allele calls / bad bases / duplicate qname is an observation of a
-//    *contiguous* run of the group's windows (membership is monotone in the iteration number); the run's ends come from
-//    arithmetic on the window grid (windows sit `k_stride` iterations apart) corrected against the table of window
-//    bounds in shared memory, and the read contributes a +1 / -1 pair to a difference array in shared memory. Reads that
-//    carry an allele call go to a list, and so do the rare reads that need the full closed form.
-//  B (thread = window): only the listed reads are evaluated per window; their haplotype keys go to per-thread
-//    shared-memory tables. After the last tile the difference array is prefix-summed into depth and the
-//    (hap 0, frame 0) count.
-// A read is visited once per exon it can overlap instead of once per 32 windows, and no per-read search runs over the
-// window table (round 1: a warp per 32-window chunk, three binary searches per read and chunk).
-constexpr int K2_LANE_KEYS = 4;
-constexpr int SG_THREADS = MPH_GROUP_WINDOWS;  // threads per CTA = windows per group
-constexpr int SG_RPT = 4;                      // reads per thread and tile
-constexpr int SG_TILE = SG_THREADS * SG_RPT;
+// K2a k_read_runs: thread per (segment, read) pair of the packer-resolved candidate ranges, a pure streaming kernel.
+// A read without allele calls / bad bases / duplicate qname is an observation of a *contiguous* run of the segment's
+// windows (membership is monotone in the iteration number). The run's ends come from arithmetic on the window grid
+// (windows sit k_stride iterations apart) corrected against mph_geom, and the read adds +1 at the run's first window and
+// -1 after its last one to a per-window difference array in global memory (no-return atomics: L2 reductions). Reads that
+// carry an allele call, and the rare ones that need the full closed form, are appended to the segment's list.
+// Every read is visited once per exon it can overlap (round 1 visited it once per 32-window chunk, with three binary
+// searches over the window table each time).
+constexpr int RR_THREADS = 256;
+constexpr int RR_IPT = 4;  // work items per thread
+constexpr int RR_ITEMS = RR_THREADS * RR_IPT;
 
-__global__ void __launch_bounds__(SG_THREADS) k_window_hist(const DeviceBatch d) {
-  // per-window key tables, [key][window] so that a warp touches 32 distinct banks
-  __shared__ uint64_t t_hap[K2_LANE_KEYS][SG_THREADS];
-  __shared__ uint32_t t_cnt[K2_LANE_KEYS][SG_THREADS];
-  __shared__ uint32_t t_frm[K2_LANE_KEYS][SG_THREADS];
-  __shared__ MphSegment s_seg;
-  __shared__ uint32_t s_s[SG_THREADS], s_e[SG_THREADS];
-  __shared__ int s_add[SG_THREADS + 2];
-  __shared__ uint32_t s_list[SG_TILE];
-  __shared__ uint32_t s_list_n;
-  __shared__ int s_wsum[SG_THREADS / 32];
-  __shared__ uint32_t s_ksum[SG_THREADS / 32];
-  __shared__ uint32_t s_base;
-  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  const MphChunk gr = d.groups[d.g0 + blockIdx.x];
-  if (t < (int)(sizeof(MphSegment) / 4)) reinterpret_cast<uint32_t*>(&s_seg)[t] = reinterpret_cast<const uint32_t*>(&d.segs[gr.seg])[t];
-  s_add[t] = 0;
-  if (t < 2) s_add[SG_THREADS + t] = 0;
+__global__ void __launch_bounds__(RR_THREADS) k_read_runs(const DeviceBatch d) {
+  const uint32_t it0 = d.it0, it1 = d.it1;
+  __shared__ uint32_t s_seg0;
+  const uint32_t first = it0 + blockIdx.x * RR_ITEMS;
+  if (threadIdx.x == 0) {  // last segment whose items start at or before `first`
+    uint32_t lo = d.s0, hi = d.s1;
+    while (hi - lo > 1) {
+      const uint32_t mid = lo + ((hi - lo) >> 1);
+      if (d.seg_work_off[mid] <= first) lo = mid;
+      else hi = mid;
+    }
+    s_seg0 = lo;
+  }
   __syncthreads();
-  const MphSegment& sg = s_seg;
+  uint32_t seg = s_seg0;
+  uint32_t a_r[RR_IPT], a_seg[RR_IPT], a_st[RR_IPT], a_en[RR_IPT], a_cf[RR_IPT];
+#pragma unroll
+  for (int u = 0; u < RR_IPT; ++u) {
+    const uint32_t item = first + u * RR_THREADS + threadIdx.x;
+    a_r[u] = NONE;
+    if (item < it1) {
+      while (item >= d.seg_work_off[seg + 1]) ++seg;  // consecutive items: the same segment or one of the next few
+      const uint32_t r = d.seg_work[seg].rlo + (item - d.seg_work_off[seg]);
+      a_r[u] = r;
+      a_seg[u] = seg;
+      a_st[u] = d.read_start[r];
+      a_en[u] = d.read_end[r];
+      a_cf[u] = (uint32_t)d.call_flags[r] | ((d.read_flags[r] & MPH_RF_PARTNER) ? 2u : 0u);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < RR_IPT; ++u) {
+    const uint32_t r = a_r[u];
+    if (r == NONE) continue;
+    const uint32_t si = a_seg[u], st = a_st[u], en = a_en[u], cf = a_cf[u];
+    const MphSegment& sg = d.segs[si];
+    const uint32_t flags = sg.flags;
+    const bool rev = (flags & MPH_SF_REVERSE) != 0, has_fs = (flags & MPH_SF_HAS_FS) != 0;
+    int cls;
+    if (cf == 0 && !has_fs) {
+      cls = 1;
+    } else {
+      const uint32_t vlo = d.read_vlo[r];
+      const uint64_t S = (cf & 1u) ? d.call_S[r] : 0, B = (cf & 1u) ? d.call_B[r] : 0;  // S / B are only written for reads with a call
+      const uint64_t Bx = B | (S & mph_range_mask(sg.sl_va, sg.sl_vb, vlo));
+      const MphSegWork sw = d.seg_work[si];
+      if (Bx == 0 && !(cf & 2u) && !has_fs) cls = (S != 0 && sw.vb1 > sw.va0) ? 2 : 1;
+      else cls = 3;
+    }
+    bool counted = false;
+    if (cls != 3) {
+      // run of windows [ilo, ihi] of this segment at which the read is an observation
+      const int n = (int)sg.n_win;
+      const int64_t off0 = sg.off0, ewl = sg.ewl, kf = sg.k_first, ks = sg.k_stride;
+      auto grid_floor = [&](int64_t kk) -> int64_t { const int64_t x = kk - kf; return x >= 0 ? x / ks : -((-x + ks - 1) / ks); };
+      auto grid_ceil = [&](int64_t kk) -> int64_t { const int64_t x = kk - kf; return x >= 0 ? (x + ks - 1) / ks : -((-x) / ks); };
+      auto clampi = [](int64_t v, int lo, int hi) -> int { return v < lo ? lo : (v > hi ? hi : (int)v); };
+      auto win = [&](int i) { return mph_geom(sg, (uint32_t)(kf + (int64_t)i * ks)); };
+      int ilo, ihi;
+      if (!rev) {
+        // e is non-decreasing (off0 + k + ewl but for the exon's last window): windows with e <= en form a prefix
+        ihi = (int64_t)en >= off0 + ewl ? clampi(grid_floor((int64_t)en - off0 - ewl), -1, n - 1) : -1;
+        while (ihi + 1 < n && win(ihi + 1).e <= en) ++ihi;
+        while (ihi >= 0 && win(ihi).e > en) --ihi;
+        const uint32_t s0 = sg.off0 - sg.ceo;
+        if (st <= s0) ilo = ((int64_t)st >= (int64_t)s0 - (int64_t)sg.K) ? 0 : n;  // offered at iteration 0 (:1227-1248)
+        else if (st <= sg.off0) ilo = n;                                           // never offered
+        else ilo = clampi(grid_ceil((int64_t)st - off0), 0, n);                     // first window at or after the offering iteration
+      } else {
+        // s is non-increasing (off0 - k but for the exon's last window): windows with s >= st form a prefix
+        ihi = (int64_t)st <= off0 ? clampi(grid_floor(off0 - (int64_t)st), -1, n - 1) : -1;
+        while (ihi + 1 < n && win(ihi + 1).s >= st) ++ihi;
+        while (ihi >= 0 && win(ihi).s < st) --ihi;
+        int a = clampi(grid_ceil(off0 + ewl - (int64_t)en), 0, n);  // first window with e <= en (e non-increasing)
+        while (a > 0 && win(a - 1).e <= en) --a;
+        while (a < n && win(a).e > en) ++a;
+        const int64_t lim = (int64_t)st + sg.K;
+        int b = clampi(grid_ceil(off0 - lim), 0, n);                 // first window with s <= st + K
+        while (b > 0 && (int64_t)win(b - 1).s <= lim) --b;
+        while (b < n && (int64_t)win(b).s > lim) ++b;
+        ilo = a > b ? a : b;
+      }
+      if (ilo <= ihi) {
+        counted = true;
+        atomicAdd(&d.win_diff[sg.win_base + ilo], 1);
+        if (ihi + 1 < n) atomicAdd(&d.win_diff[sg.win_base + ihi + 1], -1);
+      }
+    }
+    if ((cls == 2 && counted) || cls == 3)
+      d.seg_list[d.seg_work_off[si] + atomicAdd(&d.seg_list_n[si], 1u)] = r | (cls == 3 ? 0x80000000u : 0u);
+  }
+}
+
+// K2b k_window_hist: warp per chunk (<= 32 consecutive windows of one exon), lane = window. Depth and the (hap 0, frame 0)
+// count are the prefix sum of K2a's difference array; only the reads K2a listed for the segment are evaluated per window
+// (closed form of the ObservationMatrix), and their haplotype keys go to per-lane shared-memory tables.
+constexpr int K2_LANE_KEYS = 4;
+constexpr int K2B_WARPS = 4;
+
+__global__ void __launch_bounds__(K2B_WARPS * 32) k_window_hist(const DeviceBatch d) {
+  // per-lane key tables, [key][lane] so that a warp touches 32 distinct banks
+  __shared__ uint64_t t_hap[K2B_WARPS][K2_LANE_KEYS][32];
+  __shared__ uint32_t t_cnt[K2B_WARPS][K2_LANE_KEYS][32];
+  __shared__ uint32_t t_frm[K2B_WARPS][K2_LANE_KEYS][32];
+  __shared__ MphSegment s_seg[K2B_WARPS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t chunk = d.c0 + blockIdx.x * K2B_WARPS + warp;
+  if (chunk >= d.c1) return;
+  const MphChunk ch = d.chunks[chunk];
+  if (lane < (int)(sizeof(MphSegment) / 4)) reinterpret_cast<uint32_t*>(&s_seg[warp])[lane] = reinterpret_cast<const uint32_t*>(&d.segs[ch.seg])[lane];
+  __syncwarp();
+  const MphSegment& sg = s_seg[warp];
   if (sg.flags & MPH_SF_REPLAY) return;  // the whole transcript goes through k_replay
   const bool rev = (sg.flags & MPH_SF_REVERSE) != 0;
-  const bool has_fs = (sg.flags & MPH_SF_HAS_FS) != 0;
-  const int n = (int)gr.n;
-  const bool active = t < n;
-  const uint32_t i = gr.i_first + (active ? t : 0);
+  const int n = (int)ch.n;
+  const bool active = lane < n;
+  const uint32_t i = ch.i_first + (active ? lane : 0);
   const uint32_t k = sg.k_first + i * sg.k_stride;
   const MphGeom g = mph_geom(sg, k);
-  const uint32_t va = mph_var_lb(d.vars, gr.va0, gr.vb1, g.s);
-  const uint32_t vb = mph_var_lb(d.vars, va, gr.vb1, g.e);
+  // prefix sum of the difference array: the windows of this segment before the chunk, then the chunk itself
+  int carry = 0;
+  for (uint32_t j = lane; j < ch.i_first; j += 32) carry += d.win_diff[sg.win_base + j];
+  for (int o = 16; o; o >>= 1) carry += __shfl_xor_sync(FULL, carry, o);
+  int run = active ? d.win_diff[sg.win_base + i] : 0;
+  for (int o = 1; o < 32; o <<= 1) {
+    const int y = __shfl_up_sync(FULL, run, o);
+    if (lane >= o) run += y;
+  }
+  run += carry;
+  const uint32_t list_n = d.seg_list_n[ch.seg];
+  const uint32_t* list = d.seg_list + d.seg_work_off[ch.seg];
+  const uint32_t va = mph_var_lb(d.vars, ch.va0, ch.vb1, g.s);
+  const uint32_t vb = mph_var_lb(d.vars, va, ch.vb1, g.e);
   const uint32_t nvar = vb - va;
   if (active && nvar > 64) raise(d, MPH_E_VARS_PER_WINDOW);
-  const bool group_has_var = gr.vb1 > gr.va0;
-  s_s[t] = g.s;
-  s_e[t] = g.e;
   const uint32_t s0 = sg.off0 - sg.ceo;
-  const uint32_t rlo = gr.rlo, rhi = gr.rhi;  // union of the windows' candidate ranges, resolved by the packer
   const uint32_t my_s = active ? g.s : 0u;
-  const uint32_t my_e = active ? g.e : 0xFFFFFFFFu;  // inactive threads: nothing encloses e = 0xFFFFFFFF
+  const uint32_t my_e = active ? g.e : 0xFFFFFFFFu;  // inactive lanes: nothing encloses e = 0xFFFFFFFF
   const int64_t c1_lo = (int64_t)s0 - (int64_t)sg.K;  // forward: class-1 reads (offered at iteration 0)
-  const int64_t kf = (int64_t)sg.k_first, ks = (int64_t)sg.k_stride, i_first = (int64_t)gr.i_first;
-  uint32_t depth_x = 0, n_keys = 0;  // depth_x: observations counted in phase B (complex reads)
+  uint32_t depth_x = 0, n_keys = 0;  // depth_x: observations counted here (reads that need the closed form)
   int c0_adj = 0;
   bool overflow = false;
   auto add_key = [&](uint64_t hap, uint32_t frame) {
     uint32_t q = 0;
     for (; q < n_keys; ++q)
-      if (t_hap[q][t] == hap && t_frm[q][t] == frame) break;
+      if (t_hap[warp][q][lane] == hap && t_frm[warp][q][lane] == frame) break;
     if (q == n_keys) {
       if (n_keys == K2_LANE_KEYS || d.force_wide) { overflow = true; return; }
-      t_hap[q][t] = hap;
-      t_frm[q][t] = frame;
-      t_cnt[q][t] = 0;
+      t_hap[warp][q][lane] = hap;
+      t_frm[warp][q][lane] = frame;
+      t_cnt[warp][q][lane] = 0;
       ++n_keys;
     }
-    t_cnt[q][t] += 1;
+    t_cnt[warp][q][lane] += 1;
   };
-  // local window index of iteration `kk` rounded down / up on the window grid, relative to the group's first window
-  auto grid_floor = [&](int64_t kk) -> int64_t { const int64_t x = kk - kf; return (x >= 0 ? x / ks : -((-x + ks - 1) / ks)) - i_first; };
-  auto grid_ceil = [&](int64_t kk) -> int64_t { const int64_t x = kk - kf; return (x >= 0 ? (x + ks - 1) / ks : -((-x) / ks)) - i_first; };
-  auto clampi = [](int64_t v, int lo, int hi) -> int { return v < lo ? lo : (v > hi ? hi : (int)v); };
-  __syncthreads();
-  for (uint32_t base = rlo; base < rhi; base += SG_TILE) {
-    if (t == 0) s_list_n = 0;
-    __syncthreads();
-    // ---- phase A (thread = read)
-    uint32_t a_st[SG_RPT], a_en[SG_RPT], a_cf[SG_RPT];
-#pragma unroll
-    for (int u = 0; u < SG_RPT; ++u) {
-      const uint32_t r = base + u * SG_THREADS + t;
-      if (r < rhi) {
-        a_st[u] = d.read_start[r];
-        a_en[u] = d.read_end[r];
-        a_cf[u] = (uint32_t)d.call_flags[r] | ((d.read_flags[r] & MPH_RF_PARTNER) ? 2u : 0u);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < SG_RPT; ++u) {
-      const uint32_t r = base + u * SG_THREADS + t;
-      if (r >= rhi) continue;
-      const uint32_t st = a_st[u], en = a_en[u], cf = a_cf[u];
-      int cls;
-      if (cf == 0 && !has_fs) {
-        cls = 1;
-      } else {
-        const uint32_t vlo = d.read_vlo[r];
+  // the listed reads of the segment (lane = window); the list order varies from run to run, the sorted keys do not
+  for (uint32_t x0 = 0; x0 < list_n; x0 += 32) {
+    // one coalesced load of 32 entries and their coordinates, then broadcast
+    const uint32_t mine_code = x0 + lane < list_n ? list[x0 + lane] : 0u;
+    const uint32_t mine_r = mine_code & 0x7FFFFFFFu;
+    uint32_t mine_st = 0, mine_en = 0;
+    if (x0 + lane < list_n) { mine_st = d.read_start[mine_r]; mine_en = d.read_end[mine_r]; }
+    const uint32_t cnt = min(32u, list_n - x0);
+    for (uint32_t x = 0; x < cnt; ++x) {
+      const uint32_t code = __shfl_sync(FULL, mine_code, x);
+      const uint32_t st = __shfl_sync(FULL, mine_st, x), en = __shfl_sync(FULL, mine_en, x);
+      const uint32_t r = code & 0x7FFFFFFFu;
+      if (!(code >> 31)) {
+        // already counted as a plain observation; windows with variants still need its haplotype
+        if (nvar == 0) continue;
+        bool member;
+        if (!rev) member = en >= my_e && ((st <= s0) ? ((int64_t)st >= c1_lo) : (st > sg.off0 && st - sg.off0 <= k));
+        else member = st <= my_s && en >= my_e && (uint64_t)st + sg.K >= my_s;
+        if (!member) continue;
+        const uint64_t bits = mph_window_bits(d.call_S[r], d.read_vlo[r], va, nvar);
+        const uint64_t hap = rev ? bits : (mph_bitrev64(bits) >> (64 - nvar));
+        if (hap != 0) {
+          c0_adj -= 1;
+          add_key(hap, 0);
+        }
+      } else if (en >= my_e && st <= my_s) {
+        const uint32_t cf = (uint32_t)d.call_flags[r] | ((d.read_flags[r] & MPH_RF_PARTNER) ? 2u : 0u);
         const uint64_t S = (cf & 1u) ? d.call_S[r] : 0, B = (cf & 1u) ? d.call_B[r] : 0;
-        const uint64_t Bx = B | (S & mph_range_mask(sg.sl_va, sg.sl_vb, vlo));
-        if (Bx == 0 && !(cf & 2u) && !has_fs) cls = (S != 0 && group_has_var) ? 2 : 1;
-        else cls = 3;
-      }
-      int ilo = 1, ihi = 0;
-      if (cls != 3) {
-        // run of windows [ilo, ihi] of this group at which the read is an observation
-        if (!rev) {
-          // e is non-decreasing: windows with e <= en form a prefix; e = off0 + k + ewl but for the exon's last window(s)
-          ihi = en >= sg.off0 + sg.ewl ? clampi(grid_floor((int64_t)en - sg.off0 - sg.ewl), -1, n - 1) : -1;
-          while (ihi + 1 < n && s_e[ihi + 1] <= en) ++ihi;
-          while (ihi >= 0 && s_e[ihi] > en) --ihi;
-          if (st <= s0) {
-            ilo = ((int64_t)st >= c1_lo) ? 0 : n;
-          } else if (st <= sg.off0) {
-            ilo = n;
-          } else {
-            ilo = clampi(grid_ceil((int64_t)st - sg.off0), 0, n);  // first window at or after the iteration that offers the read
-          }
-        } else {
-          // s is non-increasing (s = off0 - k but for the exon's last window(s)): windows with s >= st form a prefix
-          ihi = st <= sg.off0 ? clampi(grid_floor((int64_t)sg.off0 - st), -1, n - 1) : -1;
-          while (ihi + 1 < n && s_s[ihi + 1] >= st) ++ihi;
-          while (ihi >= 0 && s_s[ihi] < st) --ihi;
-          // first window with e <= en (e = off0 - k + ewl, non-increasing)
-          int a = clampi(grid_ceil((int64_t)sg.off0 + sg.ewl - en), 0, n);
-          while (a > 0 && s_e[a - 1] <= en) --a;
-          while (a < n && s_e[a] > en) ++a;
-          // first window with s <= st + K
-          const int64_t lim = (int64_t)st + sg.K;
-          int b = clampi(grid_ceil((int64_t)sg.off0 - lim), 0, n);
-          while (b > 0 && (int64_t)s_s[b - 1] <= lim) --b;
-          while (b < n && (int64_t)s_s[b] > lim) ++b;
-          ilo = a > b ? a : b;
-        }
-      }
-      const bool counted = cls != 3 && ilo <= ihi;
-      if (counted) {
-        atomicAdd(&s_add[ilo], 1);
-        atomicAdd(&s_add[ihi + 1], -1);
-      }
-      if ((cls == 2 && counted) || cls == 3) s_list[atomicAdd(&s_list_n, 1u)] = r | (cls == 3 ? 0x80000000u : 0u);
-    }
-    __syncthreads();
-    // ---- phase B (thread = window): the listed reads of this tile
-    const uint32_t list_n = s_list_n;
-    if (active) {
-      for (uint32_t x = 0; x < list_n; ++x) {
-        const uint32_t code = s_list[x];
-        const uint32_t r = code & 0x7FFFFFFFu;
-        if (!(code >> 31)) {
-          // already counted as a plain observation; windows with variants still need its haplotype
-          if (nvar == 0) continue;
-          const uint32_t st = d.read_start[r], en = d.read_end[r];
-          bool member;
-          if (!rev) member = en >= my_e && ((st <= s0) ? ((int64_t)st >= c1_lo) : (st > sg.off0 && st - sg.off0 <= k));
-          else member = st <= my_s && en >= my_e && (uint64_t)st + sg.K >= my_s;
-          if (!member) continue;
-          const uint64_t bits = mph_window_bits(d.call_S[r], d.read_vlo[r], va, nvar);
-          const uint64_t hap = rev ? bits : (mph_bitrev64(bits) >> (64 - nvar));
-          if (hap != 0) {
-            c0_adj -= 1;
-            add_key(hap, 0);
-          }
-        } else {
-          const uint32_t st = d.read_start[r], en = d.read_end[r];
-          if (en < my_e || st > my_s) continue;
-          const uint32_t cf = (uint32_t)d.call_flags[r] | ((d.read_flags[r] & MPH_RF_PARTNER) ? 2u : 0u);
-          const uint64_t S = (cf & 1u) ? d.call_S[r] : 0, B = (cf & 1u) ? d.call_B[r] : 0;
-          const MphPair p = eval_flagged(d, sg, rev, k, g, va, vb, r, st, en, cf, d.read_vlo[r], S, B);
-          depth_x += p.member;
-          if (p.member && !p.bad) {
-            if (p.hap == 0 && p.frame == 0) c0_adj += 1;
-            else add_key(p.hap, p.frame);
-          }
+        const MphPair p = eval_flagged(d, sg, rev, k, g, va, vb, r, st, en, cf, d.read_vlo[r], S, B);
+        depth_x += p.member;
+        if (p.member && !p.bad) {
+          if (p.hap == 0 && p.frame == 0) c0_adj += 1;
+          else add_key(p.hap, p.frame);
         }
       }
     }
-    __syncthreads();
   }
-  // ---- prefix sum of the difference array over the group's windows
-  int run = s_add[t];
-  for (int o = 1; o < 32; o <<= 1) {
-    const int y = __shfl_up_sync(FULL, run, o);
-    if (lane >= o) run += y;
-  }
-  if (lane == 31) s_wsum[warp] = run;
-  __syncthreads();
-  for (int w = 0; w < warp; ++w) run += s_wsum[w];
   const uint32_t depth = (uint32_t)run + depth_x;
   const uint32_t c0 = (uint32_t)(run + c0_adj);
-  // each thread sorts its keys (reference BTreeMap order :383,434)
+  // each lane sorts its keys (reference BTreeMap order :383,434)
   for (uint32_t a = 1; a < n_keys; ++a) {
     MphHist key;
-    key.hap = t_hap[a][t]; key.frame = t_frm[a][t]; key.count = t_cnt[a][t];
+    key.hap = t_hap[warp][a][lane]; key.frame = t_frm[warp][a][lane]; key.count = t_cnt[warp][a][lane];
     uint32_t b = a;
     while (b > 0) {
       MphHist prev;
-      prev.hap = t_hap[b - 1][t]; prev.frame = t_frm[b - 1][t]; prev.count = t_cnt[b - 1][t];
+      prev.hap = t_hap[warp][b - 1][lane]; prev.frame = t_frm[warp][b - 1][lane]; prev.count = t_cnt[warp][b - 1][lane];
       if (!hist_less(key, prev)) break;
-      t_hap[b][t] = prev.hap; t_frm[b][t] = prev.frame; t_cnt[b][t] = prev.count;
+      t_hap[warp][b][lane] = prev.hap; t_frm[warp][b][lane] = prev.frame; t_cnt[warp][b][lane] = prev.count;
       --b;
     }
-    t_hap[b][t] = key.hap; t_frm[b][t] = key.frame; t_cnt[b][t] = key.count;
+    t_hap[warp][b][lane] = key.hap; t_frm[warp][b][lane] = key.frame; t_cnt[warp][b][lane] = key.count;
   }
   const bool ovf = active && overflow;
   const uint32_t mine = (active && !ovf) ? n_keys : 0;
-  // CTA-aggregated allocation in the key arena
+  // warp-aggregated allocation in the key arena
   uint32_t incl = mine;
   for (int o = 1; o < 32; o <<= 1) {
     const uint32_t y = __shfl_up_sync(FULL, incl, o);
     if (lane >= o) incl += y;
   }
-  if (lane == 31) s_ksum[warp] = incl;
-  __syncthreads();
-  uint32_t before = 0, total = 0;
-  for (int w = 0; w < SG_THREADS / 32; ++w) {
-    if (w < warp) before += s_ksum[w];
-    total += s_ksum[w];
-  }
-  if (t == 0) s_base = total ? atomicAdd(&d.counters[CTR_HIST], total) : 0u;
-  __syncthreads();
-  const uint32_t base_off = s_base;
+  const uint32_t total = __shfl_sync(FULL, incl, 31);
+  uint32_t base_off = 0;
+  if (lane == 0 && total) base_off = atomicAdd(&d.counters[CTR_HIST], total);
+  base_off = __shfl_sync(FULL, base_off, 0);
   const bool fits = base_off + total <= d.hist_cap;
-  if (t == 0 && total && !fits) raise(d, MPH_E_HIST_OVERFLOW);
-  const uint32_t chunk = gr.pad + ((uint32_t)t >> 5);
+  if (lane == 0 && total && !fits) raise(d, MPH_E_HIST_OVERFLOW);
   if (active && !ovf) {
     MphWinOut wo;
     wo.depth = depth;
     wo.c0 = c0;
     wo.n_extra = fits ? mine : 0;
-    wo.extra_off = base_off + before + incl - mine;
+    wo.extra_off = base_off + incl - mine;
     if (fits)
       for (uint32_t a = 0; a < mine; ++a) {
         MphHist h;
-        h.hap = t_hap[a][t]; h.frame = t_frm[a][t]; h.count = t_cnt[a][t];
+        h.hap = t_hap[warp][a][lane]; h.frame = t_frm[warp][a][lane]; h.count = t_cnt[warp][a][lane];
         d.hist[wo.extra_off + a] = h;
         d.hist_win[wo.extra_off + a] = (chunk << 5) | (uint32_t)lane;
       }
@@ -615,8 +619,8 @@ void launch_window_hist(const DeviceBatch& d, cudaStream_t st) {
   if (d.c1 <= d.c0) return;
   const uint32_t nc = d.c1 - d.c0;
   if (d.mode == 1) return launch_window_hist_normal(d, st);
-  (void)nc;
-  if (d.g1 > d.g0) k_window_hist<<<d.g1 - d.g0, SG_THREADS, 0, st>>>(d);
+  if (d.it1 > d.it0) k_read_runs<<<(d.it1 - d.it0 + RR_ITEMS - 1) / RR_ITEMS, RR_THREADS, 0, st>>>(d);
+  k_window_hist<<<(nc + K2B_WARPS - 1) / K2B_WARPS, K2B_WARPS * 32, 0, st>>>(d);
   // windows with more distinct haplotypes than a lane table holds (rare): one warp per window
   k_window_hist_wide<<<148 * 8, K2_WARPS * 32, 0, st>>>(d);
 }
@@ -633,6 +637,6 @@ void launch_compact(const DeviceBatch& d, cudaStream_t st) {
 void launch_live_depth(const DeviceBatch& d, cudaStream_t st) {
   if (d.c1 > d.c0) k_live_depth<<<(d.c1 - d.c0 + 7) / 8, 256, 0, st>>>(d);
 }
-int kernel_launch_count() { return 7; }
+int kernel_launch_count() { return 8; }
 
 }  // namespace mphk

@@ -16,8 +16,9 @@ struct DeviceBatch {
   // the slice of the batch one launch sequence works on (a stage of the copy / compute / residue pipeline, or everything)
   uint32_t r0 = 0, r1 = 0;    // reads
   uint32_t vr0 = 0, vr1 = 0;  // entries of the variant-read side table (K1)
-  uint32_t c0 = 0, c1 = 0;    // chunks (K5, normal-mode K2)
-  uint32_t g0 = 0, g1 = 0;    // window-kernel groups (K2)
+  uint32_t c0 = 0, c1 = 0;    // chunks (K2b, K5)
+  uint32_t s0 = 0, s1 = 0;    // segments
+  uint32_t it0 = 0, it1 = 0;  // K2a work items (segment, read): seg_work_off[s0] .. seg_work_off[s1]
   uint32_t w0 = 0, w1 = 0;    // windows (K4)
   uint32_t rp0 = 0, rp1 = 0;  // replay units
   uint32_t mode = 0;        // 0 somatic, 1 normal (reference src/normal_microphasing.rs)
@@ -44,7 +45,12 @@ struct DeviceBatch {
   const uint8_t* ins_bytes = nullptr;
   const MphSegment* segs = nullptr;
   const MphChunk* chunks = nullptr;
-  const MphChunk* groups = nullptr;  // runs of whole chunks of one segment, <= MPH_GROUP_WINDOWS windows (layout.h)
+  const MphSegWork* seg_work = nullptr;   // per segment: candidate read / variant ranges (layout.h)
+  const uint32_t* seg_work_off = nullptr; // running sum of the read range lengths, n_segs + 1 entries
+  // K2a output
+  int* win_diff = nullptr;        // per window: +1 where a plain observation's run of windows starts, -1 after its end
+  uint32_t* seg_list = nullptr;   // per segment, at seg_work_off[seg]: the reads that carry calls / need the closed form (bit 31)
+  uint32_t* seg_list_n = nullptr;
   const uint8_t* ref = nullptr;
   const uint32_t* stopmap = nullptr;  // 1 bit per ref byte: a stop codon starts here
   const uint8_t* tx_id_bytes = nullptr;  // transcript ids (record ids are hashed on the device)
