@@ -103,13 +103,13 @@ struct mph_ctx {
   std::string last_error;
   const mph_batch* cur = nullptr;
   mphk::DeviceBatch d;
-  DevBuf<uint32_t> read_start, read_end, read_vlo, read_vr, vr_read, vr_vlo, vr_seq_off, vr_cig_off, cigars, block_counts, iw, counters, seg_live, ovf_list, stopmap, hist_win, win_depth, seg_chunk0, dq_init, seg_err, tx_id_off, o_read, o_key, o_frame, win_voff, vlist, iw_voff, seg_work_off, seg_list, seg_list_n;
+  DevBuf<uint32_t> read_start, read_end, read_vlo, read_vr, vr_read, vr_vlo, vr_seq_off, vr_cig_off, cigars, block_counts, iw, counters, seg_live, ovf_list, stopmap, hist_win, win_depth, seg_chunk0, dq_init, seg_err, tx_id_off, o_read, o_key, o_frame, win_voff, vlist, iw_voff, seg_work_off, seg_list_n;
   DevBuf<uint16_t> vr_lseq, vr_ncig;
   DevBuf<uint8_t> tx_id_bytes;
   DevBuf<uint8_t> read_nv, vr_nv, read_flags, bases, ins_bytes, ref, call_flags, seq, win_flag, o_flags, o_inmat;
   DevBuf<MphReplayTx> replay;
   DevBuf<uint64_t> o_hap;
-  DevBuf<uint2> pairs;
+  DevBuf<uint2> pairs, seg_list;
   DevBuf<MphVar> vars;
   DevBuf<MphSegment> segs;
   DevBuf<MphChunk> chunks;
@@ -249,7 +249,7 @@ void prepare(mph_ctx* c, const mph_batch* mb) {
   c->vr_lseq.ensure(nvr + 1); c->vr_ncig.ensure(nvr + 1); c->vr_nv.ensure(nvr + 1);
   c->bases.ensure(b.bases.size() + 1); c->cigars.ensure(b.cigars.size() + 1); c->vars.ensure(b.vars.size() + 1); c->ins_bytes.ensure(b.ins_bytes.size() + 1);
   c->segs.ensure(b.segs.size() + 1); c->chunks.ensure(b.chunks.size() + 1); c->seg_work.ensure(b.seg_work.size() + 1); c->seg_work_off.ensure(b.seg_work_off.size() + 1);
-  c->win_diff.ensure(nw + 1); c->seg_list.ensure(size_t(b.seg_work_off.back()) + 1); c->seg_list_n.ensure(b.segs.size() + 1); c->ref.ensure(b.ref.size() + 1); c->stopmap.ensure(b.stopmap.size() + 1);
+  c->win_diff.ensure(nw + 1); c->seg_list.ensure(size_t(b.seg_work_off.back()) + 1); c->seg_list_n.ensure(2 * b.segs.size() + 2); c->ref.ensure(b.ref.size() + 1); c->stopmap.ensure(b.stopmap.size() + 1);
   c->pairs.ensure(mb->pairs.size() + 1); c->tx_id_bytes.ensure(b.tx_id_bytes.size() + 1); c->tx_id_off.ensure(b.tx_id_off.size() + 1);
   c->call_S.ensure(nr + 1); c->call_B.ensure(nr + 1); c->call_flags.ensure(nr + 1);
   c->win_out.ensure(nw + 1); c->hap0.ensure(nw + 1); c->win_flag.ensure(nw + 1);
@@ -270,7 +270,7 @@ void prepare(mph_ctx* c, const mph_batch* mb) {
   d.vr_lseq = c->vr_lseq.p; d.vr_ncig = c->vr_ncig.p; d.vr_nv = c->vr_nv.p;
   d.bases = c->bases.p; d.cigars = c->cigars.p; d.vars = c->vars.p;
   d.ins_bytes = c->ins_bytes.p; d.segs = c->segs.p; d.chunks = c->chunks.p; d.seg_work = c->seg_work.p; d.seg_work_off = c->seg_work_off.p;
-  d.win_diff = c->win_diff.p; d.seg_list = c->seg_list.p; d.seg_list_n = c->seg_list_n.p; d.ref = c->ref.p; d.stopmap = c->stopmap.p;
+  d.win_diff = c->win_diff.p; d.seg_list = c->seg_list.p; d.seg_list_n = c->seg_list_n.p; d.seg_list2_n = c->seg_list_n.p + b.segs.size() + 1; d.ref = c->ref.p; d.stopmap = c->stopmap.p;
   d.call_S = reinterpret_cast<uint64_t*>(c->call_S.p); d.call_B = reinterpret_cast<uint64_t*>(c->call_B.p); d.call_flags = c->call_flags.p;
   d.win_out = c->win_out.p; d.hap0 = c->hap0.p; d.win_flag = c->win_flag.p; d.block_counts = c->block_counts.p;
   d.ovf_list = c->ovf_list.p;
@@ -363,7 +363,10 @@ void run_kernels(mph_ctx* c) {
     CU(cudaMemsetAsync(c->win_voff.p + d.w0, 0xFF, size_t(d.w1 - d.w0) * sizeof(uint32_t), c->stream));
   }
   if (d.w1 > d.w0) CU(cudaMemsetAsync(c->win_diff.p + d.w0, 0, size_t(d.w1 - d.w0) * sizeof(int), c->stream));
-  if (d.s1 > d.s0) CU(cudaMemsetAsync(c->seg_list_n.p + d.s0, 0, size_t(d.s1 - d.s0) * sizeof(uint32_t), c->stream));
+  if (d.s1 > d.s0) {
+    CU(cudaMemsetAsync(d.seg_list_n + d.s0, 0, size_t(d.s1 - d.s0) * sizeof(uint32_t), c->stream));
+    CU(cudaMemsetAsync(d.seg_list2_n + d.s0, 0, size_t(d.s1 - d.s0) * sizeof(uint32_t), c->stream));
+  }
   mphk::launch_allele_call(d, c->stream);
   CU(cudaEventRecord(c->ev[3], c->stream));
   // measured on B200: on a second stream (any priority, with or without a dispatch head start) the replay and the

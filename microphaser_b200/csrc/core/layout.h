@@ -48,6 +48,7 @@ enum {
   MPH_SF_JOIN_HEAD = 128,   // the junction at the exon's first window can produce records (a variant on either side): its list is kept
   MPH_SF_JOIN_TAIL = 256,   // the same for the junction after the exon's last window (and the last-but-one with KEEP_PENULT)
   MPH_SF_REPLAY = 32,     // the transcript goes through the serial replay (core/replay_core.h), not the closed form
+  MPH_SF_DEVREC = 512,    // the transcript's records are built on the device (core/record_core.h); set on all its segments
 };
 
 // One processed exon of one transcript, 96 B.
@@ -142,6 +143,8 @@ enum {
   MPH_HF_OVERFLOW = 32,  // assembled sequence longer than the per-haplotype arena slot
   MPH_HF_ID = 128,       // id64 holds the leading 64 bits of the record id's SHA-1 (:667-675)
   MPH_HF_REFRANGE = 64,  // the walk left the shipped reference slice: the reference panics if (and only if) it reaches this haplotype
+  MPH_HF_PEPDIFF = 256,    // normal_peptide != neopeptide (:677-693,707) with frameshift-free clearing of germline_seq (:624-631)
+  MPH_HF_SLICE_ERR = 512,  // one of the peptide slices of :677-693 is out of range (the reference panics there)
 };
 typedef struct {
   uint32_t flags;      // MPH_HF_*
@@ -166,5 +169,9 @@ enum {
   MPH_E_VARS_PER_WINDOW = 16, // > 64 variants in one window (reference: shift overflow)
   MPH_E_REPLAY_PANIC = 32,    // serial replay: the reference panics here (drain out of range, read right of a variant, inverted range)
   MPH_E_VLIST_OVERFLOW = 64,  // column-list arena exhausted -> host retries with a larger arena
-  MPH_E_REPLAY_INPUT = 128    // serial replay: observation scratch too small or read bases not shipped (internal)
+  MPH_E_REPLAY_INPUT = 128,   // serial replay: observation scratch too small or read bases not shipped (internal)
+  MPH_E_SLICE = 256,          // record kernels: a sequence slice the reference takes is out of range (reference: slice panic)
+  MPH_E_INTERNAL = 512,       // record kernels: a haplotype that is written lacks its sequence or id
+  MPH_E_SEQ_SLOT = 1024,      // assembled haplotype longer than the sequence slot / a record length field
+  MPH_E_REC_OVERFLOW = 2048   // record / merge arena exhausted -> host retries with larger arenas
 };

@@ -538,6 +538,29 @@ MPH_HD uint32_t mph_assemble(const MphSegment& g, const MphGeom& gk, const MphVa
   uint32_t a, b;
   mph_neo_slice(gk, sl < cap ? sl : cap, g.ewl, (flags & MPH_HF_INSERTION) != 0, &a, &b);
   if (mph_has_stop(seq + a, b - a, !rev)) flags |= MPH_HF_STOP;
+  {
+    // normal_peptide vs neopeptide (:677-693) when no reading frame but the main one is open: germline_seq is cleared
+    // for a somatic indel + insertion only (:624-631)
+    const bool indel = (flags & MPH_HF_INDEL) != 0, insertion = (flags & MPH_HF_INSERTION) != 0;
+    const uint32_t slc = sl < cap ? sl : cap, glc = (indel && insertion) ? 0u : (gl < cap ? gl : cap);
+    const uint32_t twl = slc < g.ewl ? slc : g.ewl, nwl = indel ? (glc < g.ewl ? glc : g.ewl) : twl;
+    uint32_t na = 0, nb = 0, pa = 0, pb = slc;
+    bool bad = false;
+    if (glc != 0) {
+      if (gk.spos == 1) { na = gk.gap; nb = glc; bad = bad || gk.gap > glc; }
+      else if (gk.spos == 0) { nb = nwl; bad = bad || nwl > glc; }
+      else nb = glc;
+    }
+    if (gk.spos == 1) { pa = gk.gap; bad = bad || gk.gap > slc; }
+    else if (gk.spos == 0 && !insertion) pb = twl;
+    if (bad) {
+      flags |= MPH_HF_SLICE_ERR;
+    } else {
+      bool diff = (nb - na) != (pb - pa);
+      for (uint32_t t = 0; !diff && t < nb - na; ++t) diff = germ[na + t] != seq[pa + t];
+      if (diff) flags |= MPH_HF_PEPDIFF;
+    }
+  }
   out->flags = flags;
   out->seq_len = (uint16_t)sl;
   out->germ_len = (uint16_t)gl;

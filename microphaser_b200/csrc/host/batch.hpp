@@ -147,6 +147,7 @@ class Packer {
   void add_gene(const HostGene& g, const std::vector<HostRead>& reads, uint32_t max_read_len,
                 const std::vector<std::vector<HostVariant>>& sites, std::vector<uint8_t> refseq) {
     const uint32_t wl = b_.window_len;
+    if (g.end > 0x7FF00000u) throw Unsupported("gene " + g.id + ": coordinates beyond 2^31 (the kernels use signed 32-bit window arithmetic)");
     GeneMeta gm;
     gm.id = g.id; gm.name = g.name; gm.chrom = g.chrom; gm.start = g.start; gm.end = g.end;
     const uint32_t gi = uint32_t(b_.genes.size());

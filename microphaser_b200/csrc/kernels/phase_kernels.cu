@@ -260,47 +260,59 @@ __global__ void __launch_bounds__(RR_THREADS) k_read_runs(const DeviceBatch d) {
       if (Bx == 0 && !(cf & 2u) && !has_fs) cls = (S != 0 && sw.vb1 > sw.va0) ? 2 : 1;
       else cls = 3;
     }
+    if (cls == 2 && sg.n_win > 0xFFFFu) cls = 3;  // the run does not fit the list entry: full closed form per window
     bool counted = false;
+    uint32_t run_lo = 0, run_hi = 0;
     if (cls != 3) {
-      // run of windows [ilo, ihi] of this segment at which the read is an observation
+      // Run of windows [ilo, ihi] of this segment at which the read is an observation. Here the segment has no
+      // frameshift enumeration (those reads are all class 3), so windows sit 3 iterations apart (k = kf + 3 i) and only
+      // the exon's first and last window deviate from s = off0 +- k, e = s + ewl (mph_geom).
       const int n = (int)sg.n_win;
-      const int64_t off0 = sg.off0, ewl = sg.ewl, kf = sg.k_first, ks = sg.k_stride;
-      auto grid_floor = [&](int64_t kk) -> int64_t { const int64_t x = kk - kf; return x >= 0 ? x / ks : -((-x + ks - 1) / ks); };
-      auto grid_ceil = [&](int64_t kk) -> int64_t { const int64_t x = kk - kf; return x >= 0 ? (x + ks - 1) / ks : -((-x) / ks); };
-      auto clampi = [](int64_t v, int lo, int hi) -> int { return v < lo ? lo : (v > hi ? hi : (int)v); };
-      auto win = [&](int i) { return mph_geom(sg, (uint32_t)(kf + (int64_t)i * ks)); };
+      const int off0 = (int)sg.off0, ewl = (int)sg.ewl, kf = (int)sg.k_first, ks = (int)sg.k_stride;
+      const int ist = (int)st, ien = (int)en;
+      const MphGeom g_first = mph_geom(sg, (uint32_t)kf), g_last = mph_geom(sg, (uint32_t)(kf + (n - 1) * ks));
+      auto fdiv = [&](int x) { return ks == 3 ? (x >= 0 ? x / 3 : -((-x + 2) / 3)) : (ks == 1 ? x : (x >= 0 ? x / ks : -((-x + ks - 1) / ks))); };  // floor(x / ks)
+      auto cdiv = [&](int x) { return -fdiv(-x); };                                                                                               // ceil(x / ks)
+      auto clampi = [](int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); };
       int ilo, ihi;
       if (!rev) {
-        // e is non-decreasing (off0 + k + ewl but for the exon's last window): windows with e <= en form a prefix
-        ihi = (int64_t)en >= off0 + ewl ? clampi(grid_floor((int64_t)en - off0 - ewl), -1, n - 1) : -1;
-        while (ihi + 1 < n && win(ihi + 1).e <= en) ++ihi;
-        while (ihi >= 0 && win(ihi).e > en) --ihi;
+        // e is non-decreasing: e(i) = off0 + k + ewl for i < n - 1, the last window ends at g_last.e
+        if (en >= g_last.e) ihi = n - 1;
+        else ihi = ien >= off0 + ewl + kf ? clampi(fdiv(ien - off0 - ewl - kf), -1, n - 2) : -1;
         const uint32_t s0 = sg.off0 - sg.ceo;
         if (st <= s0) ilo = ((int64_t)st >= (int64_t)s0 - (int64_t)sg.K) ? 0 : n;  // offered at iteration 0 (:1227-1248)
         else if (st <= sg.off0) ilo = n;                                           // never offered
-        else ilo = clampi(grid_ceil((int64_t)st - off0), 0, n);                     // first window at or after the offering iteration
+        else ilo = clampi(cdiv(ist - off0 - kf), 0, n);                            // first window at or after the offering iteration
       } else {
-        // s is non-increasing (off0 - k but for the exon's last window): windows with s >= st form a prefix
-        ihi = (int64_t)st <= off0 ? clampi(grid_floor(off0 - (int64_t)st), -1, n - 1) : -1;
-        while (ihi + 1 < n && win(ihi + 1).s >= st) ++ihi;
-        while (ihi >= 0 && win(ihi).s < st) --ihi;
-        int a = clampi(grid_ceil(off0 + ewl - (int64_t)en), 0, n);  // first window with e <= en (e non-increasing)
-        while (a > 0 && win(a - 1).e <= en) --a;
-        while (a < n && win(a).e > en) ++a;
-        const int64_t lim = (int64_t)st + sg.K;
-        int b = clampi(grid_ceil(off0 - lim), 0, n);                 // first window with s <= st + K
-        while (b > 0 && (int64_t)win(b - 1).s <= lim) --b;
-        while (b < n && (int64_t)win(b).s > lim) ++b;
+        // s is non-increasing: s(i) = off0 - k for i < n - 1, the last window starts at g_last.s
+        if (st <= g_last.s) ihi = n - 1;
+        else ihi = ist <= off0 - kf ? clampi(fdiv(off0 - kf - ist), -1, n - 2) : -1;
+        // first window with e <= en: e(0) = g_first.e, e(i) = off0 - k + ewl for i >= 1 (non-increasing)
+        int a;
+        if (g_first.e <= en) a = 0;
+        else a = clampi(cdiv(off0 - kf + ewl - ien), 1, n);
+        // first window with s <= st + K
+        const int64_t lim64 = (int64_t)st + sg.K;
+        const int lim = lim64 > 0x7FFFFFFF ? 0x7FFFFFFF : (int)lim64;
+        int b = clampi(cdiv(off0 - kf - lim), 0, n);
+        if (b > n - 2) b = ((int64_t)g_last.s <= lim64) ? n - 1 : n;
+        if (n == 1) b = ((int64_t)g_first.s <= lim64) ? 0 : 1;
         ilo = a > b ? a : b;
       }
       if (ilo <= ihi) {
         counted = true;
+        run_lo = (uint32_t)ilo;
+        run_hi = (uint32_t)ihi;
         atomicAdd(&d.win_diff[sg.win_base + ilo], 1);
         if (ihi + 1 < n) atomicAdd(&d.win_diff[sg.win_base + ihi + 1], -1);
       }
     }
-    if ((cls == 2 && counted) || cls == 3)
-      d.seg_list[d.seg_work_off[si] + atomicAdd(&d.seg_list_n[si], 1u)] = r | (cls == 3 ? 0x80000000u : 0u);
+    // the segment's list: full-closed-form reads from the front, reads that only add haplotype keys (with their run) from the back
+    if (cls == 3) {
+      d.seg_list[d.seg_work_off[si] + atomicAdd(&d.seg_list_n[si], 1u)] = make_uint2(r, 0u);
+    } else if (cls == 2 && counted) {
+      d.seg_list[d.seg_work_off[si + 1] - 1u - atomicAdd(&d.seg_list2_n[si], 1u)] = make_uint2(r, run_lo | (run_hi << 16));
+    }
   }
 }
 
@@ -340,16 +352,12 @@ __global__ void __launch_bounds__(K2B_WARPS * 32) k_window_hist(const DeviceBatc
     if (lane >= o) run += y;
   }
   run += carry;
-  const uint32_t list_n = d.seg_list_n[ch.seg];
-  const uint32_t* list = d.seg_list + d.seg_work_off[ch.seg];
   const uint32_t va = mph_var_lb(d.vars, ch.va0, ch.vb1, g.s);
   const uint32_t vb = mph_var_lb(d.vars, va, ch.vb1, g.e);
   const uint32_t nvar = vb - va;
   if (active && nvar > 64) raise(d, MPH_E_VARS_PER_WINDOW);
-  const uint32_t s0 = sg.off0 - sg.ceo;
   const uint32_t my_s = active ? g.s : 0u;
   const uint32_t my_e = active ? g.e : 0xFFFFFFFFu;  // inactive lanes: nothing encloses e = 0xFFFFFFFF
-  const int64_t c1_lo = (int64_t)s0 - (int64_t)sg.K;  // forward: class-1 reads (offered at iteration 0)
   uint32_t depth_x = 0, n_keys = 0;  // depth_x: observations counted here (reads that need the closed form)
   int c0_adj = 0;
   bool overflow = false;
@@ -366,39 +374,55 @@ __global__ void __launch_bounds__(K2B_WARPS * 32) k_window_hist(const DeviceBatc
     }
     t_cnt[warp][q][lane] += 1;
   };
-  // the listed reads of the segment (lane = window); the list order varies from run to run, the sorted keys do not
-  for (uint32_t x0 = 0; x0 < list_n; x0 += 32) {
-    // one coalesced load of 32 entries and their coordinates, then broadcast
-    const uint32_t mine_code = x0 + lane < list_n ? list[x0 + lane] : 0u;
-    const uint32_t mine_r = mine_code & 0x7FFFFFFFu;
-    uint32_t mine_st = 0, mine_en = 0;
-    if (x0 + lane < list_n) { mine_st = d.read_start[mine_r]; mine_en = d.read_end[mine_r]; }
-    const uint32_t cnt = min(32u, list_n - x0);
+  // the listed reads of the segment (lane = window); the list order varies from run to run, the sorted keys do not.
+  // (1) reads that need the full closed form (bad bases, duplicate qname, frameshift enumeration): every window
+  const uint32_t list3_n = d.seg_list_n[ch.seg];
+  const uint2* list = d.seg_list + d.seg_work_off[ch.seg];
+  for (uint32_t x0 = 0; x0 < list3_n; x0 += 32) {
+    uint32_t mine_r = 0, mine_st = 0, mine_en = 0;
+    if (x0 + lane < list3_n) { mine_r = list[x0 + lane].x; mine_st = d.read_start[mine_r]; mine_en = d.read_end[mine_r]; }
+    const uint32_t cnt = min(32u, list3_n - x0);
     for (uint32_t x = 0; x < cnt; ++x) {
-      const uint32_t code = __shfl_sync(FULL, mine_code, x);
+      const uint32_t r = __shfl_sync(FULL, mine_r, x);
       const uint32_t st = __shfl_sync(FULL, mine_st, x), en = __shfl_sync(FULL, mine_en, x);
-      const uint32_t r = code & 0x7FFFFFFFu;
-      if (!(code >> 31)) {
-        // already counted as a plain observation; windows with variants still need its haplotype
-        if (nvar == 0) continue;
-        bool member;
-        if (!rev) member = en >= my_e && ((st <= s0) ? ((int64_t)st >= c1_lo) : (st > sg.off0 && st - sg.off0 <= k));
-        else member = st <= my_s && en >= my_e && (uint64_t)st + sg.K >= my_s;
-        if (!member) continue;
-        const uint64_t bits = mph_window_bits(d.call_S[r], d.read_vlo[r], va, nvar);
+      if (en < my_e || st > my_s) continue;
+      const uint32_t cf = (uint32_t)d.call_flags[r] | ((d.read_flags[r] & MPH_RF_PARTNER) ? 2u : 0u);
+      const uint64_t S = (cf & 1u) ? d.call_S[r] : 0, B = (cf & 1u) ? d.call_B[r] : 0;
+      const MphPair p = eval_flagged(d, sg, rev, k, g, va, vb, r, st, en, cf, d.read_vlo[r], S, B);
+      depth_x += p.member;
+      if (p.member && !p.bad) {
+        if (p.hap == 0 && p.frame == 0) c0_adj += 1;
+        else add_key(p.hap, p.frame);
+      }
+    }
+  }
+  // (2) reads already counted as plain observations over a run of windows: the windows with variants need their haplotype
+  if (ch.vb1 > ch.va0) {
+    const uint32_t list2_n = d.seg_list2_n[ch.seg];
+    const uint2* list2 = d.seg_list + d.seg_work_off[ch.seg + 1] - list2_n;
+    for (uint32_t x0 = 0; x0 < list2_n; x0 += 32) {
+      // one coalesced load of 32 entries; each lane fetches its entry's allele calls once, the windows get them by shuffle
+      uint32_t mine_run = 0xFFFFu, mine_vlo = 0, mine_Slo = 0, mine_Shi = 0;
+      if (x0 + lane < list2_n) {
+        const uint2 e = list2[x0 + lane];
+        const uint64_t S = d.call_S[e.x];
+        mine_run = e.y; mine_vlo = d.read_vlo[e.x]; mine_Slo = (uint32_t)S; mine_Shi = (uint32_t)(S >> 32);
+      }
+      // skip the batch if none of its runs reaches a window with variants of this chunk
+      const uint32_t lo_i = mine_run & 0xFFFFu, hi_i = mine_run >> 16;
+      const bool touches = lo_i <= hi_i && hi_i >= ch.i_first && lo_i < ch.i_first + (uint32_t)n;
+      if (!__any_sync(FULL, touches)) continue;
+      const uint32_t cnt = min(32u, list2_n - x0);
+      for (uint32_t x = 0; x < cnt; ++x) {
+        const uint32_t rr = __shfl_sync(FULL, mine_run, x);
+        const uint32_t vlo = __shfl_sync(FULL, mine_vlo, x);
+        const uint64_t S = (uint64_t)__shfl_sync(FULL, mine_Slo, x) | ((uint64_t)__shfl_sync(FULL, mine_Shi, x) << 32);
+        if (nvar == 0 || !active || i < (rr & 0xFFFFu) || i > (rr >> 16)) continue;
+        const uint64_t bits = mph_window_bits(S, vlo, va, nvar);
         const uint64_t hap = rev ? bits : (mph_bitrev64(bits) >> (64 - nvar));
         if (hap != 0) {
           c0_adj -= 1;
           add_key(hap, 0);
-        }
-      } else if (en >= my_e && st <= my_s) {
-        const uint32_t cf = (uint32_t)d.call_flags[r] | ((d.read_flags[r] & MPH_RF_PARTNER) ? 2u : 0u);
-        const uint64_t S = (cf & 1u) ? d.call_S[r] : 0, B = (cf & 1u) ? d.call_B[r] : 0;
-        const MphPair p = eval_flagged(d, sg, rev, k, g, va, vb, r, st, en, cf, d.read_vlo[r], S, B);
-        depth_x += p.member;
-        if (p.member && !p.bad) {
-          if (p.hap == 0 && p.frame == 0) c0_adj += 1;
-          else add_key(p.hap, p.frame);
         }
       }
     }

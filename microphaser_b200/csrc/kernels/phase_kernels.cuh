@@ -49,8 +49,11 @@ struct DeviceBatch {
   const uint32_t* seg_work_off = nullptr; // running sum of the read range lengths, n_segs + 1 entries
   // K2a output
   int* win_diff = nullptr;        // per window: +1 where a plain observation's run of windows starts, -1 after its end
-  uint32_t* seg_list = nullptr;   // per segment, at seg_work_off[seg]: the reads that carry calls / need the closed form (bit 31)
+  // per segment, in [seg_work_off[seg], seg_work_off[seg + 1]): from the front the reads that need the full closed form (x = read),
+  // from the back the reads that carry allele calls and were counted as plain observations (x = read, y = first | last << 16 window of their run)
+  uint2* seg_list = nullptr;
   uint32_t* seg_list_n = nullptr;
+  uint32_t* seg_list2_n = nullptr;
   const uint8_t* ref = nullptr;
   const uint32_t* stopmap = nullptr;  // 1 bit per ref byte: a stop codon starts here
   const uint8_t* tx_id_bytes = nullptr;  // transcript ids (record ids are hashed on the device)
