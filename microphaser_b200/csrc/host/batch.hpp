@@ -448,6 +448,18 @@ class Packer {
           if (active) { sg.flags |= MPH_SF_JOIN_HEAD; pa.flags |= MPH_SF_JOIN_TAIL; }
         }
       }
+      // device class (core/record_core.h): the records of this transcript are built by the record kernels
+      {
+        static const bool no_devrec = getenv("MPH_NO_DEVREC") != nullptr;  // test hook: everything through the host residue
+        bool dev = b_.mode == 0 && !no_devrec && !tx_replay && !has_fs && need <= 240 && wl <= 32 && tm.seg_hi > tm.seg_lo &&
+                   size_t(tm.seg_hi - tm.seg_lo) == size_t(exon_count);  // no exon was skipped (:1043-1048)
+        for (uint32_t si = tm.seg_lo; dev && si < tm.seg_hi; ++si) {
+          const MphSegment& sg = b_.segs[si];
+          dev = !(sg.flags & MPH_SF_SHORT) && sg.n_win >= 2 && sg.k_first == 0 && sg.k_stride == 3;
+        }
+        if (dev)
+          for (uint32_t si = tm.seg_lo; si < tm.seg_hi; ++si) b_.segs[si].flags |= MPH_SF_DEVREC;
+      }
       if (tx_replay && tm.seg_hi > tm.seg_lo) {
         // split the transcript into units at the exon boundaries no observation crosses; the matrix columns at a
         // unit start come from a read-free pass over the window loop's column bookkeeping (:1119-1178,1280-1296)

@@ -1,0 +1,118 @@
+// records_host.hpp — host side of the device-built records (core/record_core.h): renders the text columns of an MphRec
+// (reference IDRecord, src/common.rs:350-373) and puts host-built and device-built records into one ordered stream.
+// Only formatting happens here: which variants a record lists, its counts, frequency and sequences were decided by the
+// record kernels.
+#pragma once
+#include <charconv>
+
+#include "residue.hpp"
+
+namespace mph {
+
+namespace detail {
+
+inline void append_u64(std::string& dst, uint64_t v) {
+  char buf[24];
+  auto r = std::to_chars(buf, buf + sizeof buf, v);
+  dst.append(buf, r.ptr);
+}
+
+// variant_sites of one source window (:757-769): 1-based positions of its distinct variant sites
+inline void append_sites(const Batch& b, uint32_t var_ref, uint32_t n_win, std::string& dst) {
+  bool first = true;
+  for (uint32_t c = 0; c < n_win; ++c) {
+    const MphVar& v = b.vars[var_ref + c];
+    if (c != 0 && v.pos == b.vars[var_ref + c - 1].pos) continue;
+    if (!first) dst.push_back('|');
+    first = false;
+    append_u64(dst, uint64_t(v.pos) + 1);
+  }
+}
+
+// positions / amino-acid changes of the variants a source contributes (:733-749, common.rs:399-478)
+inline void append_lists(const Batch& b, uint32_t var_ref, uint64_t profile, uint32_t n_prof, uint32_t keep, InfoRecord& o, bool& fs, bool& fsa,
+                         bool& fg, bool& fga) {
+  for (uint32_t c = 0; c < n_prof && c < 32; ++c) {
+    const unsigned code = unsigned((profile >> (2 * c)) & 3);
+    if (!code || !((keep >> c) & 1u)) continue;
+    const uint32_t vi = var_ref + c;
+    std::string& pos = code == 2 ? o.somatic_positions : o.germline_positions;
+    std::string& aa = code == 2 ? o.somatic_aa_change : o.germline_aa_change;
+    bool& fp = code == 2 ? fs : fg;
+    bool& fa = code == 2 ? fsa : fga;
+    if (!fp) pos.push_back('|');
+    fp = false;
+    append_u64(pos, uint64_t(b.vars[vi].pos) + 1);
+    if (!fa) aa.push_back('|');
+    fa = false;
+    aa += b.var_prot[vi];
+  }
+}
+
+}  // namespace detail
+
+// text form of one device-built record
+inline OutRecord render_record(const Batch& b, const PhaseRaw& raw, const MphRec& r) {
+  OutRecord o;
+  InfoRecord& info = o.info;
+  static const char* hx = "0123456789abcdef";
+  info.id.resize(16);
+  for (int q = 0; q < 15; ++q) info.id[q] = hx[(r.id64 >> (60 - 4 * q)) & 15];
+  info.id[15] = (r.flags & MPH_RC_REVERSE) ? 'R' : 'F';
+  info.tx = r.tx;
+  info.offset = r.offset;
+  info.frame = 0;
+  info.freq = r.freq;
+  info.depth = r.depth;
+  info.nvar = r.nvar;
+  info.nsomatic = r.nsomatic;
+  info.nvariant_sites = r.nsites;
+  info.nsomvariant_sites = r.nsomsites;
+  bool fs = true, fsa = true, fg = true, fga = true;
+  detail::append_lists(b, r.var_ref, r.profile, r.n_prof, r.keep, info, fs, fsa, fg, fga);
+  detail::append_sites(b, r.var_ref, r.n_win, info.variant_sites);
+  if (r.flags & MPH_RC_MERGED) {
+    const MphRecSrc& x = raw.rec_aux[r.aux];
+    detail::append_lists(b, x.var_ref, x.profile, x.n_prof, x.keep, info, fs, fsa, fg, fga);
+    // "self|rec" with one leading and one trailing '|' removed (common.rs:497-503)
+    std::string& vr = info.variant_sites;
+    vr.push_back('|');
+    detail::append_sites(b, x.var_ref, x.n_win, vr);
+    if (!vr.empty() && vr.front() == '|') vr.erase(0, 1);
+    if (!vr.empty() && vr.back() == '|') vr.pop_back();
+  }
+  const uint32_t mut_n = std::max(r.neo_len, r.mt_len), nrm_n = std::max(r.norm_len, r.wt_len);
+  const char* mp = reinterpret_cast<const char*>(raw.rec_seq.data()) + r.seq_off;
+  const char* np = mp + mut_n;
+  (void)nrm_n;
+  info.mutant_sequence.assign(mp, r.neo_len);
+  info.normal_sequence.assign(np, r.norm_len);
+  if (r.flags & MPH_RC_HAS_MT) {
+    o.has_mt = true;
+    o.mt_same = r.mt_len == r.neo_len;
+    if (!o.mt_same) o.mt.assign(mp, r.mt_len);
+  }
+  if (r.flags & MPH_RC_HAS_WT) {
+    o.has_wt = true;
+    o.wt_same = r.wt_len == r.norm_len;
+    if (!o.wt_same) o.wt.assign(np, r.wt_len);
+  }
+  return o;
+}
+
+// host-built records (host-class transcripts, ascending transcript) and device-built records (device class, ascending
+// transcript) as one stream in transcript order; a transcript belongs to exactly one class
+inline std::vector<OutRecord> ordered_records(const Batch& b, const PhaseRaw& raw, std::vector<OutRecord>&& host_recs) {
+  if (raw.recs.empty()) return std::move(host_recs);
+  std::vector<OutRecord> out;
+  out.reserve(host_recs.size() + raw.recs.size());
+  size_t h = 0, d = 0;
+  while (h < host_recs.size() || d < raw.recs.size()) {
+    const bool take_dev = h == host_recs.size() || (d < raw.recs.size() && raw.recs[d].tx < host_recs[h].info.tx);
+    if (take_dev) out.push_back(render_record(b, raw, raw.recs[d++]));
+    else out.push_back(std::move(host_recs[h++]));
+  }
+  return out;
+}
+
+}  // namespace mph

@@ -24,6 +24,7 @@
 
 #include "../io/fmt_util.hpp"
 #include "batch.hpp"
+#include "../core/record_core.h"
 
 namespace mph {
 
@@ -40,6 +41,11 @@ struct PhaseRaw {
   std::vector<uint32_t> vlist;    // column lists: count, then variant indices in print_haplotypes order
   std::vector<uint64_t> win_id;   // normal mode only, per enumerated window: leading 64 bits of the record id of the reference window (0 = not hashed)
   std::vector<uint32_t> win_depth;  // normal mode only, per enumerated window: depth | (plain window starts / ends with a stop codon) << 31
+  // device-class transcripts (core/record_core.h): their records come from the record kernels, already in the reference's order
+  std::vector<MphRec> recs;
+  std::vector<uint8_t> rec_seq;      // sequence bytes the records point into
+  std::vector<MphRecSrc> rec_aux;    // second source of the merged records
+  uint64_t dev_windows = 0, dev_read_windows = 0;  // statistics over their live windows (emulator only; the library sums on the device)
   uint32_t seg_base = 0;          // seg_err[0] belongs to this segment
   uint32_t win_base = 0;          // win_depth[0] / win_id[0] belong to this window
   uint32_t err = 0;
@@ -279,7 +285,11 @@ class Residue {
       auto hi = std::lower_bound(lo, raw_.iw.end(), s1.win_base + s1.n_win);
       out.reserve(out.size() + size_t(hi - lo) / 3 + 16);
     }
-    for (uint32_t t = tx_lo; t < tx_hi; ++t) run_transcript(t, out, stats);
+    for (uint32_t t = tx_lo; t < tx_hi; ++t) {
+      const TxMeta& tm = b_.txs[t];
+      if (tm.seg_hi > tm.seg_lo && (b_.segs[tm.seg_lo].flags & MPH_SF_DEVREC)) continue;  // built on the device
+      run_transcript(t, out, stats);
+    }
   }
 
  private:
@@ -472,13 +482,15 @@ class Residue {
         else neopeptide = seq;
         peptides_differ = normal_peptide != neopeptide;
       } else {
-        // only reachable for haplotypes without indels, where the test below ignores it (`|| !indel`)
-        peptides_differ = !seqs_equal;
+        // the sequence walk compared the two slices itself (valid while germline_seq is cleared for indel + insertion only)
+        const bool k3_valid = key.hap != 0 && germ_cleared == (indel && insertion);
+        if (indel && !k3_valid) throw std::logic_error("internal: indel haplotype without shipped sequence");
+        peptides_differ = k3_valid ? (h.flags & MPH_HF_PEPDIFF) != 0 : !seqs_equal;
       }
       bool remove_peptide = false;
       if (stop_gain && g.spos != 2 && (window_len == this_window_len || indel) && !is_first_exon_window &&
           (peptides_differ || !indel || std::fabs(freq - 1.0) < std::numeric_limits<double>::epsilon())) {
-        if (indel && !have_seq) throw std::logic_error("internal: indel haplotype without shipped sequence");
+        (void)have_seq;
         remove_peptide = true;
         if (frame == 0) ff[frame] = {0.0, false};
         else ff.erase(frame);

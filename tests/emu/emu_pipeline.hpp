@@ -227,6 +227,10 @@ inline PhaseRaw phase_somatic(const Batch& b) {
   std::vector<MphHist>& rp_hist = rp.hist;
   // K2 + K3 + K4
   std::vector<uint8_t> seqbuf(b.seq_cap), germbuf(b.seq_cap);
+  // device-class transcripts (core/record_core.h): per-window arrays and their own sequence arena, as on the device
+  std::vector<MphWinOut> d_win_out(b.n_windows);
+  std::vector<MphHap> d_hap0(b.n_windows);
+  std::vector<uint8_t> d_flag(b.n_windows, 0), d_seq;
   for (const MphChunk& ch : b.chunks) {
     const MphSegment& sg = b.segs[ch.seg];
     const bool rev = sg.flags & MPH_SF_REVERSE;
@@ -318,6 +322,8 @@ inline PhaseRaw phase_somatic(const Batch& b) {
       wo.n_extra = uint32_t(extras.size());
       // K3
       const bool boundary = mph_is_boundary(sg, i);
+      const bool devrec = (sg.flags & MPH_SF_DEVREC) != 0;
+      std::vector<uint8_t>& seq_arena = devrec ? d_seq : raw.seq;
       auto assemble = [&](uint64_t hap, MphHap* out) {
         if (hap == 0) {
           raw.err |= mph_plain_hap(sg, g, b.stopmap.data(), b.ref.data(), vb - va, out);
@@ -329,10 +335,10 @@ inline PhaseRaw phase_somatic(const Batch& b) {
           out->flags |= MPH_HF_ID;
         }
         if (boundary || out->n_som > 0) {
-          out->seq_off = uint32_t(raw.seq.size());
-          raw.seq.resize(raw.seq.size() + 2 * b.seq_cap, 0);
-          memcpy(&raw.seq[out->seq_off], seqbuf.data(), std::min<uint32_t>(out->seq_len, b.seq_cap));
-          memcpy(&raw.seq[out->seq_off + b.seq_cap], germbuf.data(), std::min<uint32_t>(out->germ_len, b.seq_cap));
+          out->seq_off = uint32_t(seq_arena.size());
+          seq_arena.resize(seq_arena.size() + 2 * b.seq_cap, 0);
+          memcpy(&seq_arena[out->seq_off], seqbuf.data(), std::min<uint32_t>(out->seq_len, b.seq_cap));
+          memcpy(&seq_arena[out->seq_off + b.seq_cap], germbuf.data(), std::min<uint32_t>(out->germ_len, b.seq_cap));
           out->flags |= MPH_HF_SEQ;
         }
       };
@@ -345,7 +351,11 @@ inline PhaseRaw phase_somatic(const Batch& b) {
         raw.hist.push_back(e);
         raw.hapx.push_back(hx);
       }
-      if (interesting) {
+      if (devrec) {
+        d_win_out[widx] = wo;
+        d_hap0[widx] = h0;
+        d_flag[widx] = interesting ? 2 : 0;
+      } else if (interesting) {
         raw.iw.push_back(widx);
         raw.iw_out.push_back(wo);
         raw.iw_hap0.push_back(h0);
@@ -353,6 +363,60 @@ inline PhaseRaw phase_somatic(const Batch& b) {
     }
   }
   if (!b.replay.empty()) raw.iw_voff.resize(raw.iw.size(), 0xFFFFFFFFu);
+  // record kernels (kernels/record_kernels.cu): first removing window per transcript, then the records of the live windows
+  {
+    MphRecCtx c;
+    c.segs = b.segs.data(); c.vars = b.vars.data(); c.ref = b.ref.data(); c.win_out = d_win_out.data(); c.hap0 = d_hap0.data();
+    c.hist = raw.hist.data(); c.hapx = raw.hapx.data(); c.seq = d_seq.data(); c.seq_cap = b.seq_cap;
+    c.tx_id_bytes = b.tx_id_bytes.data(); c.tx_id_off = b.tx_id_off.data();
+    std::vector<uint32_t> tx_stop(b.txs.size(), 0xFFFFFFFFu), stopq(b.n_windows, 0xFFFFFFFFu);
+    for (const MphSegment& sg : b.segs) {
+      if (!(sg.flags & MPH_SF_DEVREC)) continue;
+      for (uint32_t i = 0; i < sg.n_win; ++i) {
+        const uint32_t widx = sg.win_base + i;
+        if (d_flag[widx] != 2) continue;
+        const uint32_t q = mph_rc_window_stop(c, sg, i, widx);
+        if (q != 0xFFFFFFFFu) { stopq[widx] = q; tx_stop[sg.tx] = std::min(tx_stop[sg.tx], widx); }
+      }
+    }
+    uint32_t err = 0;
+    for (size_t si = 0; si < b.segs.size(); ++si) {
+      const MphSegment& sg = b.segs[si];
+      if (!(sg.flags & MPH_SF_DEVREC)) continue;
+      for (uint32_t i = 0; i < sg.n_win; ++i) {
+        const uint32_t widx = sg.win_base + i;
+        if (widx > tx_stop[sg.tx]) break;
+        raw.dev_windows += 1;
+        raw.dev_read_windows += d_win_out[widx].depth;
+        if (d_flag[widx] != 2) continue;
+        uint32_t bytes = 0;
+        const uint32_t n = mph_rc_window_count(c, sg, i, widx, stopq[widx], &bytes, &err);
+        const size_t r0 = raw.recs.size(), s0 = raw.rec_seq.size();
+        raw.recs.resize(r0 + n);
+        raw.rec_seq.resize(s0 + bytes);
+        const uint32_t wrote = mph_rc_window_emit(c, sg, i, widx, stopq[widx], raw.recs.data() + r0, raw.rec_seq.data(), uint32_t(s0), &err);
+        if (wrote != n) err |= MPH_E_INTERNAL;
+        const bool junction = i == 0 && !(sg.flags & MPH_SF_FIRST_EXON) && (sg.flags & MPH_SF_JOIN_HEAD) && widx < tx_stop[sg.tx] && si > 0 &&
+                              b.segs[si - 1].tx == sg.tx;
+        if (junction) {
+          const MphSegment& sp = b.segs[si - 1];
+          const uint32_t ub = mph_rc_merge(c, sp, sg, b.window_len, nullptr, nullptr, nullptr, 0, 0, 0, &err);
+          if (ub) {
+            std::vector<MphRec> mr(ub);
+            std::vector<MphRecSrc> ma(ub);
+            const size_t sb = raw.rec_seq.size(), ab = raw.rec_aux.size();
+            raw.rec_seq.resize(sb + size_t(ub) * MPH_RC_SEQ_SLOT, 0);
+            const uint32_t nm = mph_rc_merge(c, sp, sg, b.window_len, mr.data(), ma.data(), raw.rec_seq.data(), uint32_t(ab), uint32_t(sb), ub, &err);
+            raw.rec_aux.insert(raw.rec_aux.end(), ma.begin(), ma.begin() + nm);
+            const size_t rb = raw.recs.size();
+            raw.recs.resize(rb + nm);
+            for (uint32_t x = 0; x < nm; ++x) raw.recs[rb + mr[x].rank] = mr[x];
+          }
+        }
+      }
+    }
+    raw.err |= err;
+  }
   return raw;
 }
 

@@ -7,6 +7,7 @@
 #include <cstdlib>
 
 #include "../../microphaser_b200/csrc/host/synth_files.hpp"
+#include "../../microphaser_b200/csrc/host/records_host.hpp"
 #include "../../microphaser_b200/csrc/host/writer.hpp"
 #include "emu_pipeline.hpp"
 
@@ -32,7 +33,7 @@ int main(int argc, char** argv) {
     std::vector<mph::OutRecord> recs;
     mph::ResidueStats st;
     if (mode == 1) { mph::ResidueNormal r(b, raw); r.run(0, uint32_t(b.txs.size()), recs, st); }
-    else { mph::Residue r(b, raw); r.run(0, uint32_t(b.txs.size()), recs, st); }
+    else { mph::Residue r(b, raw); r.run(0, uint32_t(b.txs.size()), recs, st); recs = mph::ordered_records(b, raw, std::move(recs)); }
     mph::Outputs o;
     o.fasta = fopen((out + "/out.fa").c_str(), "wb");
     o.tsv = fopen((out + "/out.tsv").c_str(), "wb");
@@ -40,8 +41,8 @@ int main(int argc, char** argv) {
     mph::write_records(b, recs, o);
     fclose(o.fasta); fclose(o.tsv);
     if (o.normal) fclose(o.normal);
-    printf("{\"reads\": %zu, \"variants\": %zu, \"windows\": %llu, \"records\": %zu, \"replay_units\": %zu}\n", b.read_start.size(), b.vars.size(),
-           (unsigned long long)b.n_windows, recs.size(), b.replay.size());
+    printf("{\"reads\": %zu, \"variants\": %zu, \"windows\": %llu, \"records\": %zu, \"replay_units\": %zu, \"device_records\": %zu}\n", b.read_start.size(), b.vars.size(),
+           (unsigned long long)b.n_windows, recs.size(), b.replay.size(), raw.recs.size());
   } catch (const mph::Unsupported& e) {
     fprintf(stderr, "unsupported: %s\n", e.what());
     return 3;
