@@ -149,7 +149,9 @@ typedef struct {
   uint64_t windows_enumerated, n_interesting, n_records;
   uint32_t kernel_launches;
   uint32_t n_replay_units; /* replay units (runs of exons of irregular transcripts) that went through k_replay */
-  double replay_ms;        /* k_replay, CUDA events; k2_ms is the closed-form window kernel alone */
+  double replay_ms;        /* k_replay, CUDA events; k2_ms is the closed-form window kernels alone */
+  double k5_ms;            /* record kernels: ORF stop, emit predicate, junction merge, ordered compaction of the records */
+  double pack_ms;          /* file drivers only: host time spent in the packer (wall clock, summed over the packing threads) */
 } mph_timing;
 int mph_ctx_timing(const mph_ctx* ctx, mph_timing* out);
 

@@ -19,6 +19,7 @@
 #include "../../include/microphaser_gpu.h"
 #include "host/cli.hpp"
 #include "host/peptides_host.hpp"
+#include "host/records_host.hpp"
 #include "host/synth_files.hpp"
 #include "kernels/peptide_kernels.cuh"
 #include "kernels/phase_kernels.cuh"
@@ -97,9 +98,9 @@ struct mph_ctx {
   cudaStream_t stream = nullptr;       // compute + device -> host
   cudaStream_t copy_stream = nullptr;  // host -> device of the next stage
   std::vector<cudaEvent_t> ev_copy;
-  uint32_t stage_seg_lo = 0, stage_seg_hi = 0;
+  uint32_t stage_seg_lo = 0, stage_seg_hi = 0, stage_tx_lo = 0, stage_tx_hi = 0;
   bool kernels_done = false;           // mph_phase_resident ran for the uploaded batch: mph_phase_collect only downloads
-  cudaEvent_t ev[9] = {};
+  cudaEvent_t ev[10] = {};
   std::string last_error;
   const mph_batch* cur = nullptr;
   mphk::DeviceBatch d;
@@ -114,6 +115,10 @@ struct mph_ctx {
   DevBuf<MphSegment> segs;
   DevBuf<MphChunk> chunks;
   DevBuf<MphSegWork> seg_work;
+  DevBuf<MphRec> recs, m_recs;
+  DevBuf<MphRecSrc> m_aux;
+  DevBuf<uint8_t> seq_dev, rec_seq, m_seq;
+  DevBuf<uint32_t> win_seg, tx_stop, rw, rw_stopq, rw_info, rw_mbase, rw_bytes, rc_blocks;
   DevBuf<int> win_diff;
   DevBuf<uint64_t> call_S, call_B;
   DevBuf<MphWinOut> win_out, iw_out;
@@ -255,12 +260,20 @@ void prepare(mph_ctx* c, const mph_batch* mb) {
   c->win_out.ensure(nw + 1); c->hap0.ensure(nw + 1); c->win_flag.ensure(nw + 1);
   c->block_counts.ensure(nw / 1024 + 2);
   c->iw.ensure(nw + 1); c->iw_out.ensure(nw + 1); c->iw_hap0.ensure(nw + 1); c->ovf_list.ensure(nw + 1);
-  c->counters.ensure(8); c->sums.ensure(2); c->seg_live.ensure(b.segs.size() + 1);
+  c->counters.ensure(mphk::CTR_COUNT); c->sums.ensure(3);
+  if (b.mode == 0) {
+    c->win_seg.ensure(nw + 1); c->tx_stop.ensure(b.txs.size() + 1);
+    c->rw.ensure(nw + 1); c->rw_stopq.ensure(nw + 1); c->rw_info.ensure(nw + 1); c->rw_mbase.ensure(nw + 1); c->rw_bytes.ensure(nw + 1);
+    c->rc_blocks.ensure(nw / 256 + 4);
+    if (c->recs.cap == 0) { c->recs.ensure(std::max<size_t>(nw / 16, 1 << 14)); c->rec_seq.ensure(c->recs.cap * 64); }
+    if (c->m_recs.cap == 0) { c->m_recs.ensure(1 << 14); c->m_aux.ensure(c->m_recs.cap); c->m_seq.ensure(c->m_recs.cap * MPH_RC_SEQ_SLOT); }
+  } c->seg_live.ensure(b.segs.size() + 1);
   if (c->hist.cap == 0) { c->hist.ensure(std::max<size_t>(nw / 2, 1 << 16)); c->hapx.ensure(c->hist.cap); }
   if (c->hapx.cap < c->hist.cap) c->hapx.ensure(c->hist.cap);
   if (c->hist_win.cap < c->hist.cap) c->hist_win.ensure(c->hist.cap);
   const size_t seq_want = (2 * b.segs.size() + nw / 8 + 4096) * 2 * b.seq_cap;
   if (c->seq.cap < seq_want) c->seq.ensure(seq_want);
+  if (b.mode == 0 && c->seq_dev.cap < seq_want) c->seq_dev.ensure(seq_want);
   mphk::DeviceBatch& d = c->d;
   d.n_reads = uint32_t(nr); d.n_vars = uint32_t(b.vars.size()); d.n_segs = uint32_t(b.segs.size()); d.n_chunks = uint32_t(b.chunks.size());
   d.n_windows = uint32_t(nw); d.seq_cap = b.seq_cap;
@@ -276,6 +289,9 @@ void prepare(mph_ctx* c, const mph_batch* mb) {
   d.ovf_list = c->ovf_list.p;
   d.iw = c->iw.p; d.iw_out = c->iw_out.p; d.iw_hap0 = c->iw_hap0.p; d.counters = c->counters.p;
   d.sum_depth = c->sums.p; d.live_depth = c->sums.p + 1; d.seg_live = c->seg_live.p;
+  d.window_len = b.window_len;
+  d.win_seg = c->win_seg.p; d.tx_stop = c->tx_stop.p; d.rw = c->rw.p; d.rw_stopq = c->rw_stopq.p; d.rw_info = c->rw_info.p; d.rw_mbase = c->rw_mbase.p;
+  d.rw_bytes = c->rw_bytes.p; d.rc_blocks = c->rc_blocks.p;
   d.tx_id_bytes = c->tx_id_bytes.p; d.tx_id_off = c->tx_id_off.p;
   d.n_replay = uint32_t(b.replay.size());
   d.win_voff = nullptr; d.iw_voff = nullptr;
@@ -345,7 +361,13 @@ void run_kernels(mph_ctx* c) {
   if (c->hist_win.cap < c->hist.cap) c->hist_win.ensure(c->hist.cap);
   d.hist = c->hist.p; d.hapx = c->hapx.p; d.hist_win = c->hist_win.p; d.hist_cap = uint32_t(std::min<size_t>(c->hist.cap, 0xFFFFFFF0u));
   d.seq = c->seq.p; d.seq_cap_bytes = uint32_t(std::min<size_t>(c->seq.cap, 0xFFFFFF00u));
-  CU(cudaMemsetAsync(c->counters.p, 0, 8 * sizeof(uint32_t), c->stream));
+  d.seq_dev = c->seq_dev.p; d.seq_dev_cap_bytes = uint32_t(std::min<size_t>(c->seq_dev.cap, 0xFFFFFF00u));
+  d.recs = c->recs.p; d.rec_cap = uint32_t(std::min<size_t>(c->recs.cap, 0xFFFFFF00u));
+  d.rec_seq = c->rec_seq.p; d.rec_seq_cap = uint32_t(std::min<size_t>(c->rec_seq.cap, 0xFFFFFF00u));
+  d.m_recs = c->m_recs.p; d.m_aux = c->m_aux.p; d.m_seq = c->m_seq.p; d.m_cap = uint32_t(std::min<size_t>(c->m_recs.cap, 0x03FFFFFFu));
+  CU(cudaMemsetAsync(c->counters.p, 0, mphk::CTR_COUNT * sizeof(uint32_t), c->stream));
+  if (d.mode == 0 && c->stage_tx_hi > c->stage_tx_lo)
+    CU(cudaMemsetAsync(c->tx_stop.p + c->stage_tx_lo, 0xFF, size_t(c->stage_tx_hi - c->stage_tx_lo) * sizeof(uint32_t), c->stream));
   CU(cudaEventRecord(c->ev[2], c->stream));  // k1_ms covers the zero-fill below: it is the allele call of the reads without variants
   if (d.r1 > d.r0) {
     // reads without an entry in the side table: no allele call, no bad base, no variant inside
@@ -380,6 +402,8 @@ void run_kernels(mph_ctx* c) {
   CU(cudaEventRecord(c->ev[5], c->stream));
   mphk::launch_compact(d, c->stream);
   CU(cudaEventRecord(c->ev[6], c->stream));
+  mphk::launch_records(d, c->stream);
+  CU(cudaEventRecord(c->ev[9], c->stream));
   CU(cudaGetLastError());
 }
 
@@ -406,14 +430,21 @@ void resize_pinned(mph_ctx* c, V& v, size_t n) {
 // device -> host copy of what the kernels produced for the current slice; re-runs the kernels when an arena was too small
 void fetch_stage(mph_ctx* c, const Stage& s, PhaseRaw& raw, uint64_t* n_iw_total) {
   const Batch& b = c->cur->b;
-  uint32_t ctr[8];
+  uint32_t ctr[mphk::CTR_COUNT];
   for (int attempt = 0;; ++attempt) {
     CU(cudaMemcpyAsync(ctr, c->counters.p, sizeof ctr, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     const uint32_t err = ctr[mphk::CTR_ERR];
-    if ((err & (MPH_E_HIST_OVERFLOW | MPH_E_SEQ_OVERFLOW | MPH_E_VLIST_OVERFLOW)) && attempt < 6) {
+    if ((err & (MPH_E_HIST_OVERFLOW | MPH_E_SEQ_OVERFLOW | MPH_E_VLIST_OVERFLOW | MPH_E_REC_OVERFLOW)) && attempt < 6) {
+      if (err & MPH_E_REC_OVERFLOW) {
+        c->recs.ensure(std::max<size_t>(size_t(ctr[mphk::CTR_NREC]) * 2 + 1024, c->recs.cap));
+        c->rec_seq.ensure(std::max<size_t>(size_t(ctr[mphk::CTR_RECSEQ]) * 2 + 4096, std::max(c->rec_seq.cap, c->recs.cap * 64)));
+        c->m_recs.ensure(std::max<size_t>(size_t(ctr[mphk::CTR_MERGE]) * 2 + 1024, c->m_recs.cap));
+        c->m_aux.ensure(c->m_recs.cap); c->m_seq.ensure(c->m_recs.cap * MPH_RC_SEQ_SLOT);
+      }
+      if (err & MPH_E_SEQ_OVERFLOW) c->seq_dev.ensure(size_t(ctr[mphk::CTR_SEQD]) * 2 + 4096);
       if (err & MPH_E_VLIST_OVERFLOW) c->vlist.ensure(size_t(ctr[mphk::CTR_VLIST]) * 2 + 1024);
-      if (err & MPH_E_HIST_OVERFLOW) { c->hist.ensure(size_t(ctr[mphk::CTR_HIST]) * 2 + 1024); c->hapx.ensure(c->hist.cap); }
+      if (err & MPH_E_HIST_OVERFLOW) { c->hist.ensure((size_t(ctr[mphk::CTR_HIST]) + ctr[mphk::CTR_HISTD]) * 2 + 1024); c->hapx.ensure(c->hist.cap); }
       if (err & MPH_E_SEQ_OVERFLOW) c->seq.ensure(size_t(ctr[mphk::CTR_SEQ]) * 2 + 4096);
       run_kernels(c);
       continue;
@@ -426,13 +457,18 @@ void fetch_stage(mph_ctx* c, const Stage& s, PhaseRaw& raw, uint64_t* n_iw_total
   CU(cudaEventElapsedTime(&ms, c->ev[8], c->ev[4])); c->timing.k2_ms += ms;
   CU(cudaEventElapsedTime(&ms, c->ev[4], c->ev[5])); c->timing.k3_ms += ms;
   CU(cudaEventElapsedTime(&ms, c->ev[5], c->ev[6])); c->timing.k4_ms += ms;
+  CU(cudaEventElapsedTime(&ms, c->ev[6], c->ev[9])); c->timing.k5_ms += ms;
   raw.err = ctr[mphk::CTR_ERR];
+  if (raw.err & MPH_E_SLICE) throw Fatal("slice index out of range");
+  if (raw.err & MPH_E_SEQ_SLOT) throw Unsupported("assembled haplotype longer than the sequence slot");
   if (raw.err & MPH_E_REF_RANGE) throw Fatal("slice index out of range: refseq");
   if (raw.err & MPH_E_VARS_PER_WINDOW) throw Unsupported("more than 32 variants in one window / 64 inside one read");
   if (raw.err & MPH_E_KEYS_PER_WINDOW) throw Unsupported("more than 32 distinct haplotypes in one window");
   if (raw.err & MPH_E_REPLAY_PANIC) throw Fatal("bug: read starts right of variant");
   if (raw.err) throw std::logic_error("device error bits " + std::to_string(raw.err));
   const uint32_t n_iw = ctr[mphk::CTR_NIW], n_hist = ctr[mphk::CTR_HIST], n_seq = ctr[mphk::CTR_SEQ];
+  const uint32_t n_rec = ctr[mphk::CTR_NREC], n_recseq = ctr[mphk::CTR_RECSEQ], n_merge = ctr[mphk::CTR_MERGE];
+  resize_pinned(c, raw.recs, n_rec); resize_pinned(c, raw.rec_seq, n_recseq); resize_pinned(c, raw.rec_aux, n_merge);
   resize_pinned(c, raw.iw, n_iw); resize_pinned(c, raw.iw_out, n_iw); resize_pinned(c, raw.iw_hap0, n_iw); resize_pinned(c, raw.hist, n_hist);
   resize_pinned(c, raw.hapx, n_hist); resize_pinned(c, raw.seq, n_seq);
   CU(cudaEventRecord(c->ev[0], c->stream));
@@ -446,6 +482,9 @@ void fetch_stage(mph_ctx* c, const Stage& s, PhaseRaw& raw, uint64_t* n_iw_total
     CU(cudaMemcpyAsync(raw.hapx.data(), c->hapx.p, n_hist * sizeof(MphHap), cudaMemcpyDeviceToHost, c->stream));
   }
   if (n_seq) CU(cudaMemcpyAsync(raw.seq.data(), c->seq.p, n_seq, cudaMemcpyDeviceToHost, c->stream));
+  if (n_rec) CU(cudaMemcpyAsync(raw.recs.data(), c->recs.p, size_t(n_rec) * sizeof(MphRec), cudaMemcpyDeviceToHost, c->stream));
+  if (n_recseq) CU(cudaMemcpyAsync(raw.rec_seq.data(), c->rec_seq.p, n_recseq, cudaMemcpyDeviceToHost, c->stream));
+  if (n_merge) CU(cudaMemcpyAsync(raw.rec_aux.data(), c->m_aux.p, size_t(n_merge) * sizeof(MphRecSrc), cudaMemcpyDeviceToHost, c->stream));
   const bool has_replay = c->d.n_replay != 0;
   const uint32_t n_vl = (c->d.rp1 > c->d.rp0) ? std::min<uint32_t>(ctr[mphk::CTR_VLIST], c->d.vlist_cap) : 0;
   resize_pinned(c, raw.iw_voff, has_replay ? n_iw : 0);
@@ -473,6 +512,7 @@ void fetch_stage(mph_ctx* c, const Stage& s, PhaseRaw& raw, uint64_t* n_iw_total
   CU(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
   c->timing.d2h_ms += ms;
   c->timing.d2h_bytes += sizeof ctr + size_t(n_iw) * (4 + sizeof(MphWinOut) + sizeof(MphHap)) + size_t(n_hist) * (sizeof(MphHist) + sizeof(MphHap)) + n_seq +
+                         size_t(n_rec) * sizeof(MphRec) + n_recseq + size_t(n_merge) * sizeof(MphRecSrc) +
                          raw.win_depth.size() * 12 + (raw.iw_voff.size() + raw.vlist.size() + raw.seg_err.size()) * 4;
   *n_iw_total += n_iw;
 }
@@ -521,6 +561,8 @@ struct ResiduePool {
           Residue r(b, *t.raw);
           r.run(t.tx_lo, t.tx_hi, parts[t.part], stats[ti]);
           live[ti].insert(live[ti].end(), r.seg_live_.begin(), r.seg_live_.end());
+          // the device-built records of this block's transcripts, rendered and put in transcript order with the host-built ones
+          if (!t.raw->recs.empty()) parts[t.part] = ordered_records(b, *t.raw, std::move(parts[t.part]), t.tx_lo, t.tx_hi);
         }
       } catch (...) {
         errs[ti] = std::current_exception();
@@ -574,7 +616,7 @@ void phase_stages(mph_ctx* c, const std::vector<Stage>& stages, bool copied, mph
     c->ev_copy.resize(ns + 1);
     for (size_t i = old; i < c->ev_copy.size(); ++i) CU(cudaEventCreate(&c->ev_copy[i]));
   }
-  CU(cudaMemsetAsync(c->sums.p, 0, 2 * sizeof(unsigned long long), c->stream));
+  CU(cudaMemsetAsync(c->sums.p, 0, 3 * sizeof(unsigned long long), c->stream));
   // Host -> device copies go to the copy stream, the compute stream waits per stage. From pinned buffers they are all
   // queued now (asynchronous, back to back at link speed); from pageable buffers cudaMemcpyAsync blocks the caller, so
   // stage s + 1 is queued after the kernels of stage s have been launched.
@@ -627,6 +669,8 @@ void phase_stages(mph_ctx* c, const std::vector<Stage>& stages, bool copied, mph
         set_ranges(c, st);
         c->stage_seg_lo = uint32_t(st.lo.segs);
         c->stage_seg_hi = uint32_t(st.hi.segs);
+        c->stage_tx_lo = uint32_t(st.lo.txs);
+        c->stage_tx_hi = uint32_t(st.hi.txs);
         if (!(copied && c->kernels_done)) run_kernels(c);
         if (!copied) queue_copies(s + 2);
         fetch_stage(c, st, c->raws[s], &n_iw_total);
@@ -677,10 +721,11 @@ void phase_stages(mph_ctx* c, const std::vector<Stage>& stages, bool copied, mph
       all.pair_hi = uint32_t(mb->pairs.size());
       set_ranges(c, all);
       mphk::launch_live_depth(c->d, c->stream);
-      unsigned long long sums[2];
+      unsigned long long sums[3];
       CU(cudaMemcpyAsync(sums, c->sums.p, sizeof sums, cudaMemcpyDeviceToHost, c->stream));
       CU(cudaStreamSynchronize(c->stream));
       c->timing.read_windows += sums[1];
+      c->timing.windows += sums[2];  // live windows of the device-class transcripts (counted on the device)
     }
   }
   if (!copied) {
@@ -694,7 +739,7 @@ void phase_stages(mph_ctx* c, const std::vector<Stage>& stages, bool copied, mph
   c->timing.windows_enumerated = b.n_windows;
   c->timing.n_interesting = n_iw_total;
   c->timing.n_records = res->size();
-  c->timing.kernel_launches = (uint32_t(mphk::kernel_launch_count()) + (b.replay.empty() ? 0u : 1u)) * uint32_t(ns);
+  c->timing.kernel_launches = (uint32_t(mphk::kernel_launch_count()) + (b.replay.empty() ? 0u : 1u) + (b.mode == 0 ? uint32_t(mphk::record_kernel_launch_count()) : 0u)) * uint32_t(ns);
   c->timing.n_replay_units = uint32_t(b.replay.size());
   c->timing.total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
   if (timeline) fprintf(stderr, "[mph] call finished at %.2f ms\n", c->timing.total_ms);
@@ -1012,7 +1057,9 @@ int mph_phase_resident(mph_ctx* ctx) {
     set_ranges(ctx, all[0]);
     ctx->stage_seg_lo = 0;
     ctx->stage_seg_hi = uint32_t(all[0].hi.segs);
-    CU(cudaMemsetAsync(ctx->sums.p, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    ctx->stage_tx_lo = 0;
+    ctx->stage_tx_hi = uint32_t(all[0].hi.txs);
+    CU(cudaMemsetAsync(ctx->sums.p, 0, 3 * sizeof(unsigned long long), ctx->stream));
     run_kernels(ctx);
     CU(cudaStreamSynchronize(ctx->stream));
     float ms;
@@ -1021,6 +1068,7 @@ int mph_phase_resident(mph_ctx* ctx) {
     CU(cudaEventElapsedTime(&ms, ctx->ev[8], ctx->ev[4])); ctx->timing.k2_ms = ms;
     CU(cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5])); ctx->timing.k3_ms = ms;
     CU(cudaEventElapsedTime(&ms, ctx->ev[5], ctx->ev[6])); ctx->timing.k4_ms = ms;
+    CU(cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[9])); ctx->timing.k5_ms = ms;
     ctx->kernels_done = true;
   });
 }
@@ -1032,7 +1080,7 @@ int mph_phase_collect(mph_ctx* ctx, mph_result** out) {
     if (!ctx->cur) throw std::runtime_error("no resident run to collect");
     CU(cudaSetDevice(ctx->device));
     const std::vector<Stage> all = plan_stages(ctx->cur, 1);
-    ctx->timing.k1_ms = ctx->timing.k2_ms = ctx->timing.k3_ms = ctx->timing.k4_ms = ctx->timing.replay_ms = 0;
+    ctx->timing.k1_ms = ctx->timing.k2_ms = ctx->timing.k3_ms = ctx->timing.k4_ms = ctx->timing.k5_ms = ctx->timing.replay_ms = 0;
     ctx->timing.d2h_ms = 0;
     ctx->timing.d2h_bytes = 0;
     phase_stages(ctx, all, true, out);
@@ -1178,7 +1226,7 @@ static void run_somatic_files(const std::vector<mph_ctx*>& ctxs, const char* bam
     std::vector<mph_timing> acc(n_dev, mph_timing{});  // a device's timing is the sum over its shards
     auto add_timing = [](mph_timing& a, const mph_timing& t) {
       a.h2d_ms += t.h2d_ms; a.k1_ms += t.k1_ms; a.k2_ms += t.k2_ms; a.k3_ms += t.k3_ms; a.k4_ms += t.k4_ms; a.d2h_ms += t.d2h_ms;
-      a.residue_ms += t.residue_ms; a.total_ms += t.total_ms; a.replay_ms += t.replay_ms; a.h2d_bytes += t.h2d_bytes; a.d2h_bytes += t.d2h_bytes;
+      a.residue_ms += t.residue_ms; a.total_ms += t.total_ms; a.replay_ms += t.replay_ms; a.k5_ms += t.k5_ms; a.pack_ms += t.pack_ms; a.h2d_bytes += t.h2d_bytes; a.d2h_bytes += t.d2h_bytes;
       a.windows += t.windows; a.read_windows += t.read_windows; a.windows_enumerated += t.windows_enumerated; a.n_interesting += t.n_interesting;
       a.n_records += t.n_records; a.kernel_launches += t.kernel_launches; a.n_replay_units += t.n_replay_units;
     };

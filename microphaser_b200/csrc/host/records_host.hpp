@@ -102,13 +102,18 @@ inline OutRecord render_record(const Batch& b, const PhaseRaw& raw, const MphRec
 
 // host-built records (host-class transcripts, ascending transcript) and device-built records (device class, ascending
 // transcript) as one stream in transcript order; a transcript belongs to exactly one class
-inline std::vector<OutRecord> ordered_records(const Batch& b, const PhaseRaw& raw, std::vector<OutRecord>&& host_recs) {
-  if (raw.recs.empty()) return std::move(host_recs);
+// (restricted to the device-built records of transcripts [tx_lo, tx_hi))
+inline std::vector<OutRecord> ordered_records(const Batch& b, const PhaseRaw& raw, std::vector<OutRecord>&& host_recs, uint32_t tx_lo = 0,
+                                              uint32_t tx_hi = 0xFFFFFFFFu) {
+  auto by_tx = [](const MphRec& r, uint32_t t) { return r.tx < t; };
+  size_t d = size_t(std::lower_bound(raw.recs.begin(), raw.recs.end(), tx_lo, by_tx) - raw.recs.begin());
+  const size_t d_end = size_t(std::lower_bound(raw.recs.begin() + long(d), raw.recs.end(), tx_hi, by_tx) - raw.recs.begin());
+  if (d == d_end) return std::move(host_recs);
   std::vector<OutRecord> out;
-  out.reserve(host_recs.size() + raw.recs.size());
-  size_t h = 0, d = 0;
-  while (h < host_recs.size() || d < raw.recs.size()) {
-    const bool take_dev = h == host_recs.size() || (d < raw.recs.size() && raw.recs[d].tx < host_recs[h].info.tx);
+  out.reserve(host_recs.size() + (d_end - d));
+  size_t h = 0;
+  while (h < host_recs.size() || d < d_end) {
+    const bool take_dev = h == host_recs.size() || (d < d_end && raw.recs[d].tx < host_recs[h].info.tx);
     if (take_dev) out.push_back(render_record(b, raw, raw.recs[d++]));
     else out.push_back(std::move(host_recs[h++]));
   }

@@ -92,7 +92,7 @@ __device__ __forceinline__ MphPair eval_flagged(const DeviceBatch& d, const MphS
 
 // Wide variant: one warp per window, lanes over the candidate reads, keys in a 32-entry table.
 // Used only for windows whose key count overflows the per-lane table of k_window_hist.
-__device__ void window_hist_warp(const DeviceBatch& d, const MphSegment& sg, uint32_t i, uint32_t code, MphHist* table, int lane) {
+__device__ void window_hist_warp(const DeviceBatch& d, const MphSegment& sg, uint32_t ch_seg, uint32_t i, uint32_t code, MphHist* table, int lane) {
   const bool rev = (sg.flags & MPH_SF_REVERSE) != 0;
   const uint32_t k = sg.k_first + i * sg.k_stride;
   const uint32_t widx = sg.win_base + i;
@@ -164,8 +164,11 @@ __device__ void window_hist_warp(const DeviceBatch& d, const MphSegment& sg, uin
     wo.n_extra = n_keys;
     wo.extra_off = 0;
     if (n_keys) {
-      const uint32_t off = atomicAdd(&d.counters[CTR_HIST], n_keys);
-      if (off + n_keys <= d.hist_cap) {
+      const bool devrec = (sg.flags & MPH_SF_DEVREC) != 0;
+      uint32_t off = atomicAdd(&d.counters[devrec ? CTR_HISTD : CTR_HIST], n_keys);
+      const bool fits = off + n_keys <= d.hist_cap;
+      if (devrec && fits) off = d.hist_cap - off - n_keys;
+      if (fits) {
         wo.extra_off = off;
         for (uint32_t a = 0; a < n_keys; ++a) {
           d.hist[off + a] = table[a];
@@ -180,7 +183,8 @@ __device__ void window_hist_warp(const DeviceBatch& d, const MphSegment& sg, uin
     atomicAdd(d.sum_depth, (unsigned long long)depth);
     MphHap h0;
     const uint32_t err = mph_plain_hap(sg, g, d.stopmap, d.ref, vb - va, &h0);
-    d.win_flag[widx] = 1;  // it has extra keys, hence it is interesting
+    d.win_flag[widx] = (sg.flags & MPH_SF_DEVREC) ? 2 : 1;  // it has extra keys, hence it is interesting
+    if (sg.flags & MPH_SF_DEVREC) d.win_seg[widx] = ch_seg;
     d.hap0[widx] = h0;
     raise(d, err);
   }
@@ -195,7 +199,7 @@ __global__ void __launch_bounds__(K2_WARPS * 32) k_window_hist_wide(const Device
     const uint32_t code = d.ovf_list[o];
     const MphChunk ch = d.chunks[code >> 5];
     const MphSegment sg = d.segs[ch.seg];
-    window_hist_warp(d, sg, ch.i_first + (code & 31u), code, table[warp], lane);
+    window_hist_warp(d, sg, ch.seg, ch.i_first + (code & 31u), code, table[warp], lane);
   }
 }
 
@@ -453,10 +457,12 @@ __global__ void __launch_bounds__(K2B_WARPS * 32) k_window_hist(const DeviceBatc
   }
   const uint32_t total = __shfl_sync(FULL, incl, 31);
   uint32_t base_off = 0;
-  if (lane == 0 && total) base_off = atomicAdd(&d.counters[CTR_HIST], total);
+  const bool devrec_keys = (sg.flags & MPH_SF_DEVREC) != 0;
+  if (lane == 0 && total) base_off = atomicAdd(&d.counters[devrec_keys ? CTR_HISTD : CTR_HIST], total);
   base_off = __shfl_sync(FULL, base_off, 0);
   const bool fits = base_off + total <= d.hist_cap;
   if (lane == 0 && total && !fits) raise(d, MPH_E_HIST_OVERFLOW);
+  if (devrec_keys && fits) base_off = d.hist_cap - base_off - total;  // device-class keys grow from the back of the arena
   if (active && !ovf) {
     MphWinOut wo;
     wo.depth = depth;
@@ -478,8 +484,12 @@ __global__ void __launch_bounds__(K2B_WARPS * 32) k_window_hist(const DeviceBatc
     const uint32_t err = mph_plain_hap(sg, g, d.stopmap, d.ref, nvar, &h0);
     const bool boundary = mph_is_boundary(sg, i);
     const bool interesting = nvar > 0 || (h0.flags & MPH_HF_STOP) || boundary || wo.n_extra > 0;
-    d.win_flag[widx] = interesting ? 1 : 0;
-    if (interesting) d.hap0[widx] = h0;
+    const bool devrec = (sg.flags & MPH_SF_DEVREC) != 0;  // 2: the record kernels take the window, 1: the host residue does
+    d.win_flag[widx] = interesting ? (devrec ? 2 : 1) : 0;
+    if (interesting) {
+      d.hap0[widx] = h0;
+      if (devrec) d.win_seg[widx] = ch.seg;
+    }
     raise(d, err);
   }
   if (ovf) {
@@ -496,10 +506,16 @@ __global__ void __launch_bounds__(K2B_WARPS * 32) k_window_hist(const DeviceBatc
 // (:458-603) into thread-local buffers, then the stop test; the bytes are kept only for haplotypes
 // that can be written (n_somatic > 0) or merged across a splice junction (boundary windows).
 __global__ void __launch_bounds__(128) k_assemble(const DeviceBatch d) {
-  const uint32_t n = min(d.counters[CTR_HIST], d.hist_cap);
+  const uint32_t n_front = min(d.counters[CTR_HIST], d.hist_cap), n_back = min(d.counters[CTR_HISTD], d.hist_cap);
+  if (n_front + n_back > d.hist_cap) {  // the two ends of the key arena met: the host retries with a larger one
+    if (blockIdx.x == 0 && threadIdx.x == 0) raise(d, MPH_E_HIST_OVERFLOW);
+    return;
+  }
+  const uint32_t n = n_front + n_back;
   uint8_t seq[MAX_SEQ_CAP], germ[MAX_SEQ_CAP];
   const uint32_t cap = d.seq_cap;
-  for (uint32_t x = blockIdx.x * blockDim.x + threadIdx.x; x < n; x += gridDim.x * blockDim.x) {
+  for (uint32_t y = blockIdx.x * blockDim.x + threadIdx.x; y < n; y += gridDim.x * blockDim.x) {
+    const uint32_t x = y < n_front ? y : d.hist_cap - n_back + (y - n_front);
     const uint64_t hap = d.hist[x].hap;
     if (hap == 0) continue;  // a (hap 0, frame != 0) key shares the window's haplotype-0 record
     const uint32_t code = d.hist_win[x];
@@ -531,11 +547,15 @@ __global__ void __launch_bounds__(128) k_assemble(const DeviceBatch d) {
       out.flags |= MPH_HF_ID;
     }
     if (boundary || out.n_som > 0) {
-      const uint32_t off = atomicAdd(&d.counters[CTR_SEQ], 2 * cap);
-      if (off + 2 * cap <= d.seq_cap_bytes) {
+      // device-class transcripts keep their sequences on the device (the record kernels read them), the others are downloaded
+      const bool devrec = (sg.flags & MPH_SF_DEVREC) != 0;
+      uint8_t* arena = devrec ? d.seq_dev : d.seq;
+      const uint32_t arena_cap = devrec ? d.seq_dev_cap_bytes : d.seq_cap_bytes;
+      const uint32_t off = atomicAdd(&d.counters[devrec ? CTR_SEQD : CTR_SEQ], 2 * cap);
+      if (off + 2 * cap <= arena_cap) {
         const uint32_t sl = out.seq_len < cap ? out.seq_len : cap, gl = out.germ_len < cap ? out.germ_len : cap;
-        for (uint32_t t = 0; t < sl; ++t) d.seq[off + t] = seq[t];
-        for (uint32_t t = 0; t < gl; ++t) d.seq[off + cap + t] = germ[t];
+        for (uint32_t t = 0; t < sl; ++t) arena[off + t] = seq[t];
+        for (uint32_t t = 0; t < gl; ++t) arena[off + cap + t] = germ[t];
         out.seq_off = off;
         out.flags |= MPH_HF_SEQ;
       } else {
@@ -552,7 +572,7 @@ constexpr int SCAN_THREADS = 1024;
 
 __global__ void __launch_bounds__(SCAN_THREADS) k_flag_count(const DeviceBatch d) {
   const uint32_t w = d.w0 + blockIdx.x * SCAN_THREADS + threadIdx.x;
-  const int f = (w < d.w1) ? d.win_flag[w] : 0;
+  const int f = (w < d.w1) && d.win_flag[w] == 1;  // 2 = device-class transcript: its records are built by the record kernels
   const int n = __syncthreads_count(f);
   if (threadIdx.x == 0) d.block_counts[blockIdx.x] = (uint32_t)n;
 }
@@ -596,7 +616,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scatter(const DeviceBatch d) {
   __shared__ uint32_t warp_sums[32];
   const uint32_t w = d.w0 + blockIdx.x * SCAN_THREADS + threadIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const bool f = (w < d.w1) && d.win_flag[w];
+  const bool f = (w < d.w1) && d.win_flag[w] == 1;
   const unsigned bal = __ballot_sync(FULL, f);
   if (lane == 0) warp_sums[warp] = __popc(bal);
   __syncthreads();
@@ -616,22 +636,6 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scatter(const DeviceBatch d) {
     d.iw_hap0[pos] = d.hap0[w];
     if (d.win_voff) d.iw_voff[pos] = d.win_voff[w];
   }
-}
-
-// ------------------------------------------------------------------ K5: statistics
-__global__ void __launch_bounds__(256) k_live_depth(const DeviceBatch d) {
-  const uint32_t chunk = d.c0 + blockIdx.x * 8 + (threadIdx.x >> 5);
-  const uint32_t lane = threadIdx.x & 31;
-  unsigned long long v = 0;
-  if (chunk < d.c1) {
-    const MphChunk ch = d.chunks[chunk];
-    if (lane < ch.n) {
-      const uint32_t i = ch.i_first + lane;
-      if (i < d.seg_live[ch.seg]) v = d.win_out[d.segs[ch.seg].win_base + i].depth;
-    }
-  }
-  for (int o = 16; o; o >>= 1) v += __shfl_down_sync(FULL, v, o);
-  if (lane == 0 && v) atomicAdd(d.live_depth, v);
 }
 
 }  // namespace
@@ -657,9 +661,6 @@ void launch_compact(const DeviceBatch& d, cudaStream_t st) {
   if (nb) k_flag_count<<<nb, SCAN_THREADS, 0, st>>>(d);
   k_block_scan<<<1, SCAN_THREADS, 0, st>>>(d, nb);
   if (nb) k_scatter<<<nb, SCAN_THREADS, 0, st>>>(d);
-}
-void launch_live_depth(const DeviceBatch& d, cudaStream_t st) {
-  if (d.c1 > d.c0) k_live_depth<<<(d.c1 - d.c0 + 7) / 8, 256, 0, st>>>(d);
 }
 int kernel_launch_count() { return 8; }
 

@@ -6,6 +6,7 @@
 
 #include "../core/layout.h"
 #include "../core/replay_core.h"
+#include "../core/record_core.h"
 
 namespace mphk {
 
@@ -66,7 +67,8 @@ struct DeviceBatch {
   MphWinOut* win_out = nullptr;
   MphHist* hist = nullptr;
   uint32_t* hist_win = nullptr;  // per key: (chunk << 5 | lane) of its window
-  uint32_t hist_cap = 0;
+  uint32_t hist_cap = 0;          // keys of host-class windows fill the arena from the front (CTR_HIST, downloaded), those of
+                                  // device-class transcripts from the back (CTR_HISTD, read by K3 and the record kernels only)
   uint32_t* ovf_list = nullptr;  // (chunk << 5 | lane) of windows whose keys overflow a lane table; chunk count must be < 2^27
   // K3 output
   MphHap* hap0 = nullptr;
@@ -95,11 +97,31 @@ struct DeviceBatch {
   uint32_t vlist_cap = 0;
   uint32_t* iw_voff = nullptr;   // K4: win_voff of the interesting windows
   uint32_t* seg_err = nullptr;   // per segment: 1 + iteration at which the reference panics, 0 = none
+  // record kernels (record_kernels.cu, core/record_core.h): device-class transcripts
+  uint32_t window_len = 27;
+  uint32_t* win_seg = nullptr;      // per interesting window of a device-class transcript: its segment
+  uint8_t* seq_dev = nullptr;       // K3's sequence arena for those transcripts (never downloaded); counter CTR_SEQD
+  uint32_t seq_dev_cap_bytes = 0;
+  uint32_t* tx_stop = nullptr;      // per transcript: first window with a haplotype that ends the ORF (0xFFFFFFFF: none)
+  uint32_t* rw = nullptr;           // compacted interesting windows of device-class transcripts (counters[CTR_NRW] of them)
+  uint32_t* rw_stopq = nullptr;     // per listed window: first haplotype that removes the peptide
+  uint32_t* rw_info = nullptr;      // per listed window: own records | merged records << 12
+  uint32_t* rw_mbase = nullptr;     // per listed window: first slot of its junction's records in the merge arena
+  uint32_t* rw_bytes = nullptr;     // per listed window: sequence bytes its records need
+  uint32_t* rc_blocks = nullptr;    // block sums / offsets of the two compactions
+  MphRec* recs = nullptr;           // ordered records (counters[CTR_NREC])
+  uint32_t rec_cap = 0;
+  uint8_t* rec_seq = nullptr;       // their sequence bytes (counters[CTR_RECSEQ])
+  uint32_t rec_seq_cap = 0;
+  MphRec* m_recs = nullptr;         // merge arena: junction records before they are placed (counters[CTR_MERGE] slots)
+  MphRecSrc* m_aux = nullptr;
+  uint8_t* m_seq = nullptr;         // MPH_RC_SEQ_SLOT bytes per slot
+  uint32_t m_cap = 0;
   unsigned long long* win_id = nullptr;  // normal mode, per window: leading 64 bits of the record id of the unmodified reference window
   uint32_t* win_depth = nullptr;       // normal mode, per window: depth | (plain window begins / ends with a stop codon) << 31
 };
 
-enum { CTR_HIST = 0, CTR_SEQ = 1, CTR_NIW = 2, CTR_ERR = 3, CTR_OVF = 4, CTR_VLIST = 5 };
+enum { CTR_HIST = 0, CTR_SEQ = 1, CTR_NIW = 2, CTR_ERR = 3, CTR_OVF = 4, CTR_VLIST = 5, CTR_SEQD = 6, CTR_NRW = 7, CTR_MERGE = 8, CTR_NREC = 9, CTR_RECSEQ = 10, CTR_HISTD = 11, CTR_COUNT = 16 };
 
 void launch_allele_call(const DeviceBatch& d, cudaStream_t st);
 void launch_window_hist(const DeviceBatch& d, cudaStream_t st);
@@ -108,7 +130,9 @@ void launch_window_hist_normal(const DeviceBatch& d, cudaStream_t st);    // nor
 void launch_assemble_normal(const DeviceBatch& d, cudaStream_t st);
 void launch_assemble(const DeviceBatch& d, cudaStream_t st);
 void launch_compact(const DeviceBatch& d, cudaStream_t st);
-void launch_live_depth(const DeviceBatch& d, cudaStream_t st);
+void launch_live_depth(const DeviceBatch& d, cudaStream_t st);            // record_kernels.cu
+void launch_records(const DeviceBatch& d, cudaStream_t st);               // record_kernels.cu
+int record_kernel_launch_count();
 int kernel_launch_count();  // kernels launched by one launch_* sequence K1..K4 (for bench "gpu_launches")
 
 }  // namespace mphk

@@ -1,0 +1,233 @@
+// record_kernels.cu — record emission on the device for the device-class transcripts (core/record_core.h):
+// the emit predicate (reference src/microphasing.rs:839-844), ORF termination at the first premature stop
+// (:703-718, :1480-1488), the splice-junction merge (:1497-1908, src/common.rs:376-568) and a stable,
+// ordered compaction of the *records* — the host only renders text.
+//
+//   k_rc_flag_count / k_rc_scan / k_rc_scatter   compact the interesting windows of device-class transcripts
+//   k_rc_stop     thread per such window: does one of its haplotypes remove the peptide? -> atomicMin per transcript
+//   k_rc_count    thread per window: records it writes itself + the junction merge (run once, into the merge arena)
+//   k_rc_scan     exclusive scan of the per-block record counts
+//   k_rc_emit     thread per window: writes its records at their final, ordered positions
+//
+// All of it is integer / byte work on a few hundred thousand windows per shard; the kernels are latency bound and
+// short next to K1-K3.
+#include "kernel_common.cuh"
+#include "phase_kernels.cuh"
+
+#include "../core/record_core.h"
+
+namespace mphk {
+
+using namespace detail;
+
+namespace {
+
+constexpr int RC_THREADS = 256;
+
+__device__ __forceinline__ MphRecCtx rec_ctx(const DeviceBatch& d) {
+  MphRecCtx c;
+  c.segs = d.segs; c.vars = d.vars; c.ref = d.ref; c.win_out = d.win_out; c.hap0 = d.hap0; c.hist = d.hist; c.hapx = d.hapx;
+  c.seq = d.seq_dev; c.seq_cap = d.seq_cap; c.tx_id_bytes = d.tx_id_bytes; c.tx_id_off = d.tx_id_off;
+  return c;
+}
+
+// block-wide exclusive scan of one value per thread (RC_THREADS threads); returns the exclusive prefix, *total = block sum
+__device__ __forceinline__ uint32_t block_exclusive(uint32_t v, uint32_t* total) {
+  __shared__ uint32_t warp_sums[RC_THREADS / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t x = v;
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t y = __shfl_up_sync(FULL, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) warp_sums[warp] = x;
+  __syncthreads();
+  uint32_t before = 0, sum = 0;
+  for (int w = 0; w < RC_THREADS / 32; ++w) {
+    if (w < warp) before += warp_sums[w];
+    sum += warp_sums[w];
+  }
+  __syncthreads();
+  *total = sum;
+  return before + x - v;
+}
+
+__global__ void __launch_bounds__(RC_THREADS) k_rc_flag_count(const DeviceBatch d) {
+  const uint32_t w = d.w0 + blockIdx.x * RC_THREADS + threadIdx.x;
+  const int f = (w < d.w1) && d.win_flag[w] == 2;
+  const int n = __syncthreads_count(f);
+  if (threadIdx.x == 0) d.rc_blocks[blockIdx.x] = (uint32_t)n;
+}
+
+// exclusive scan of rc_blocks[0 .. n_blocks) in place (one CTA); total -> counters[ctr]
+__global__ void __launch_bounds__(1024) k_rc_scan(const DeviceBatch d, uint32_t n_blocks, int ctr) {
+  __shared__ uint32_t warp_sums[32];
+  __shared__ uint32_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (uint32_t base = 0; base < n_blocks; base += 1024) {
+    const uint32_t idx = base + threadIdx.x;
+    const uint32_t v = idx < n_blocks ? d.rc_blocks[idx] : 0;
+    uint32_t x = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(FULL, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) warp_sums[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t s = warp_sums[lane];
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(FULL, s, o);
+        if (lane >= o) s += y;
+      }
+      warp_sums[lane] = s;
+    }
+    __syncthreads();
+    const uint32_t before = carry + (warp ? warp_sums[warp - 1] : 0) + (x - v);
+    if (idx < n_blocks) d.rc_blocks[idx] = before;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = before + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) d.counters[ctr] = carry;
+}
+
+__global__ void __launch_bounds__(RC_THREADS) k_rc_scatter(const DeviceBatch d) {
+  const uint32_t w = d.w0 + blockIdx.x * RC_THREADS + threadIdx.x;
+  const bool f = (w < d.w1) && d.win_flag[w] == 2;
+  uint32_t total;
+  const uint32_t before = block_exclusive(f ? 1u : 0u, &total);
+  if (f) d.rw[d.rc_blocks[blockIdx.x] + before] = w;
+}
+
+__global__ void __launch_bounds__(RC_THREADS) k_rc_stop(const DeviceBatch d) {
+  const uint32_t x = blockIdx.x * RC_THREADS + threadIdx.x;
+  if (x >= d.counters[CTR_NRW]) return;
+  const uint32_t w = d.rw[x];
+  const MphSegment& sg = d.segs[d.win_seg[w]];
+  const MphRecCtx c = rec_ctx(d);
+  const uint32_t q = mph_rc_window_stop(c, sg, w - sg.win_base, w);
+  d.rw_stopq[x] = q;
+  if (q != NONE) atomicMin(&d.tx_stop[sg.tx], w);
+}
+
+__global__ void __launch_bounds__(RC_THREADS) k_rc_count(const DeviceBatch d) {
+  const uint32_t x = blockIdx.x * RC_THREADS + threadIdx.x;
+  uint32_t n = 0;
+  if (x < d.counters[CTR_NRW]) {
+    const uint32_t w = d.rw[x];
+    const uint32_t si = d.win_seg[w];
+    const MphSegment& sg = d.segs[si];
+    const uint32_t stop = d.tx_stop[sg.tx];
+    uint32_t info = 0, mbase = 0;
+    if (w <= stop) {
+      const MphRecCtx c = rec_ctx(d);
+      const uint32_t i = w - sg.win_base;
+      uint32_t bytes = 0, err = 0;
+      n = mph_rc_window_count(c, sg, i, w, d.rw_stopq[x], &bytes, &err);
+      // junction merge (:1497-1908): the transcript is still alive after the first window of a later exon
+      const bool junction = i == 0 && !(sg.flags & MPH_SF_FIRST_EXON) && (sg.flags & MPH_SF_JOIN_HEAD) && w < stop && si > 0 && d.segs[si - 1].tx == sg.tx;
+      uint32_t nm = 0;
+      if (junction) {
+        const MphSegment& sp = d.segs[si - 1];
+        const uint32_t ub = mph_rc_merge(c, sp, sg, d.window_len, nullptr, nullptr, nullptr, 0, 0, 0, &err);
+        if (ub) {
+          mbase = atomicAdd(&d.counters[CTR_MERGE], ub);
+          if (mbase + ub <= d.m_cap) nm = mph_rc_merge(c, sp, sg, d.window_len, d.m_recs + mbase, d.m_aux + mbase, d.m_seq, mbase, mbase * MPH_RC_SEQ_SLOT, ub, &err);
+          else err |= MPH_E_REC_OVERFLOW;
+        }
+      }
+      if (nm > 0xFFFu || n > 0xFFFu) { err |= MPH_E_REC_OVERFLOW; nm = 0; n = 0; }
+      info = n | (nm << 12);
+      d.rw_bytes[x] = bytes + nm * 2u * d.window_len;
+      n += nm;
+      raise(d, err);
+    }
+    d.rw_info[x] = info;
+    d.rw_mbase[x] = mbase;
+  }
+  uint32_t total;
+  block_exclusive(n, &total);
+  if (threadIdx.x == 0) d.rc_blocks[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(RC_THREADS) k_rc_emit(const DeviceBatch d) {
+  const uint32_t x = blockIdx.x * RC_THREADS + threadIdx.x;
+  const bool live = x < d.counters[CTR_NRW];
+  const uint32_t info = live ? d.rw_info[x] : 0u;
+  const uint32_t n_own = info & 0xFFFu, nm = info >> 12;
+  uint32_t total;
+  const uint32_t before = block_exclusive(n_own + nm, &total);
+  if (!live || n_own + nm == 0) return;
+  const uint32_t base = d.rc_blocks[blockIdx.x] + before;
+  if (base + n_own + nm > d.rec_cap) { raise(d, MPH_E_REC_OVERFLOW); return; }
+  const uint32_t bytes = d.rw_bytes[x];
+  const uint32_t sbase = atomicAdd(&d.counters[CTR_RECSEQ], bytes);
+  if (sbase + bytes > d.rec_seq_cap) { raise(d, MPH_E_REC_OVERFLOW); return; }
+  const uint32_t w = d.rw[x];
+  const MphSegment& sg = d.segs[d.win_seg[w]];
+  const MphRecCtx c = rec_ctx(d);
+  uint32_t err = 0;
+  const uint32_t wrote = mph_rc_window_emit(c, sg, w - sg.win_base, w, d.rw_stopq[x], d.recs + base, d.rec_seq, sbase, &err);
+  if (wrote != n_own) err |= MPH_E_INTERNAL;
+  // the junction's records follow the window's own, in output_map order (:1877-1901)
+  const uint32_t mbase = d.rw_mbase[x], wl = d.window_len;
+  uint32_t spos = sbase + bytes - nm * 2u * wl;
+  for (uint32_t m = 0; m < nm; ++m) {
+    MphRec r = d.m_recs[mbase + m];
+    const uint8_t* src = d.m_seq + (size_t)(mbase + m) * MPH_RC_SEQ_SLOT;
+    for (uint32_t t = 0; t < 2u * wl; ++t) d.rec_seq[spos + t] = src[t];
+    r.seq_off = spos;
+    spos += 2u * wl;
+    d.recs[base + n_own + r.rank] = r;
+  }
+  raise(d, err);
+}
+
+// statistics: windows the reference reaches and the sum of depth over them (K5)
+__global__ void __launch_bounds__(256) k_live_depth2(const DeviceBatch d) {
+  const uint32_t chunk = d.c0 + blockIdx.x * 8 + (threadIdx.x >> 5);
+  const uint32_t lane = threadIdx.x & 31;
+  unsigned long long v = 0, nw = 0;
+  if (chunk < d.c1) {
+    const MphChunk ch = d.chunks[chunk];
+    const MphSegment& sg = d.segs[ch.seg];
+    if (lane < ch.n) {
+      const uint32_t i = ch.i_first + lane;
+      if (sg.flags & MPH_SF_DEVREC) {
+        if (sg.win_base + i <= d.tx_stop[sg.tx]) { v = d.win_out[sg.win_base + i].depth; nw = 1; }
+      } else if (i < d.seg_live[ch.seg]) {
+        v = d.win_out[sg.win_base + i].depth;
+      }
+    }
+  }
+  for (int o = 16; o; o >>= 1) { v += __shfl_down_sync(FULL, v, o); nw += __shfl_down_sync(FULL, nw, o); }
+  if (lane == 0 && v) atomicAdd(d.live_depth, v);
+  if (lane == 0 && nw) atomicAdd(d.live_depth + 1, nw);
+}
+
+}  // namespace
+
+void launch_records(const DeviceBatch& d, cudaStream_t st) {
+  if (d.mode != 0 || d.w1 <= d.w0) return;
+  const uint32_t nb = (d.w1 - d.w0 + RC_THREADS - 1) / RC_THREADS;
+  k_rc_flag_count<<<nb, RC_THREADS, 0, st>>>(d);
+  k_rc_scan<<<1, 1024, 0, st>>>(d, nb, CTR_NRW);
+  k_rc_scatter<<<nb, RC_THREADS, 0, st>>>(d);
+  // the number of listed windows lives on the device: the grids cover the upper bound the host knows (interesting
+  // windows of the slice cannot exceed its windows); threads beyond the count return at once
+  const uint32_t nbl = nb;
+  k_rc_stop<<<nbl, RC_THREADS, 0, st>>>(d);
+  k_rc_count<<<nbl, RC_THREADS, 0, st>>>(d);
+  k_rc_scan<<<1, 1024, 0, st>>>(d, nbl, CTR_NREC);
+  k_rc_emit<<<nbl, RC_THREADS, 0, st>>>(d);
+}
+int record_kernel_launch_count() { return 7; }
+
+void launch_live_depth(const DeviceBatch& d, cudaStream_t st) {
+  if (d.c1 > d.c0) k_live_depth2<<<(d.c1 - d.c0 + 7) / 8, 256, 0, st>>>(d);
+}
+
+}  // namespace mphk
