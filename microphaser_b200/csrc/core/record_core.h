@@ -290,6 +290,9 @@ typedef struct {
   uint32_t var_ref;
   uint64_t profile;
   uint8_t n_prof, n_win, nsites, nsomsites;
+  uint8_t same;      // wt == mt
+  uint8_t aligned;   // wt and mt have the same length (<= 64): `diff` marks the positions where they differ
+  uint64_t diff;
 } MphListEntry;
 
 MPH_HD MphListEntry mph_rc_entry(const MphRecCtx& c, const MphSegment& sg, uint32_t i, uint32_t widx, uint32_t q, uint32_t* err) {
@@ -314,6 +317,17 @@ MPH_HD MphListEntry mph_rc_entry(const MphRecCtx& c, const MphSegment& sg, uint3
   en.n_win = (uint8_t)nv;
   en.nsites = (uint8_t)ns;
   en.nsomsites = (uint8_t)nss;
+  en.diff = 0;
+  en.aligned = en.s.mt_len == en.s.wt_len && en.s.mt_len <= 64;
+  if (en.s.mt == en.s.wt && en.s.mt_len == en.s.wt_len) {
+    en.same = 1;
+  } else if (en.aligned) {
+    for (uint32_t x = 0; x < en.s.mt_len; ++x)
+      if (en.s.mt[x] != en.s.wt[x]) en.diff |= (uint64_t)1 << x;
+    en.same = en.diff == 0;
+  } else {
+    en.same = 0;  // different lengths
+  }
   return en;
 }
 
@@ -368,24 +382,37 @@ MPH_HD uint32_t mph_rc_merge(const MphRecCtx& c, const MphSegment& sp, const Mph
   const double eps = 2.220446049250313e-16;
   uint32_t n_out = 0;
   const uint32_t t0 = c.tx_id_off[sj.tx], tlen = c.tx_id_off[sj.tx + 1] - t0;
+  // the two lists are small (haplotype 0 plus the few variant haplotypes of a window): build their entries once
+  enum { LIST_CACHE = 6 };
+  MphListEntry first_c[LIST_CACHE], sec_c[LIST_CACHE];
+  for (uint32_t a = 0; a < n_first && a < LIST_CACHE; ++a) first_c[a] = fwd ? mph_rc_entry(c, sj, 0, w_cur, a, err) : mph_rc_entry(c, sp, i_prv, w_prv, a, err);
+  for (uint32_t b = 0; b < n_sec && b < LIST_CACHE; ++b) sec_c[b] = fwd ? mph_rc_entry(c, sp, i_prv, w_prv, b, err) : mph_rc_entry(c, sj, 0, w_cur, b, err);
   for (uint32_t a = 0; a < n_first; ++a) {
-    const MphListEntry record = fwd ? mph_rc_entry(c, sj, 0, w_cur, a, err) : mph_rc_entry(c, sp, i_prv, w_prv, a, err);
-    const bool rec_same = mph_rc_same(record.s);
+    const MphListEntry record = a < LIST_CACHE ? first_c[a] : (fwd ? mph_rc_entry(c, sj, 0, w_cur, a, err) : mph_rc_entry(c, sp, i_prv, w_prv, a, err));
+    const bool rec_same = record.same != 0;
     for (uint32_t b = 0; b < n_sec; ++b) {
-      const MphListEntry prev = fwd ? mph_rc_entry(c, sp, i_prv, w_prv, b, err) : mph_rc_entry(c, sj, 0, w_cur, b, err);
-      const bool prev_same = mph_rc_same(prev.s);
+      const MphListEntry prev = b < LIST_CACHE ? sec_c[b] : (fwd ? mph_rc_entry(c, sp, i_prv, w_prv, b, err) : mph_rc_entry(c, sj, 0, w_cur, b, err));
+      const bool prev_same = prev.same != 0;
+      if (rec_same && prev_same) continue;  // every window of mt + mt equals wt + wt: nothing is written (:1795-1810)
       const uint32_t n_mts = rec_same ? 1u : (prev_same ? 1u : 3u);
       const double out_freq = fabs(record.freq - prev.freq) < eps ? record.freq : record.freq * prev.freq;
       // new_wt = prev.wt + record.wt
       const uint8_t* wa = prev.s.wt; const uint32_t wan = prev.s.wt_len; const uint8_t* wb = record.s.wt; const uint64_t wn = (uint64_t)wan + record.s.wt_len;
+      // when neither side changes length, new_mt and new_wt are aligned and differ exactly where the chosen sides differ
+      const bool masks = record.aligned && prev.aligned && wn <= 64;
       for (uint32_t m = 0; m < n_mts; ++m) {
         // new_mt_sequences (:1541-1556): wt != mt: [prev.wt + mt, prev.mt + wt, prev.mt + mt]; else [prev.mt + mt]
         const uint8_t *ma, *mb; uint32_t man, mbn;
-        if (rec_same) { ma = prev.s.mt; man = prev.s.mt_len; mb = record.s.mt; mbn = record.s.mt_len; }
-        else if (m == 0) { ma = prev.s.wt; man = prev.s.wt_len; mb = record.s.mt; mbn = record.s.mt_len; }
-        else if (m == 1) { ma = prev.s.mt; man = prev.s.mt_len; mb = record.s.wt; mbn = record.s.wt_len; }
-        else { ma = prev.s.mt; man = prev.s.mt_len; mb = record.s.mt; mbn = record.s.mt_len; }
+        bool prev_mt, rec_mt;
+        if (rec_same) { prev_mt = true; rec_mt = true; }
+        else if (m == 0) { prev_mt = false; rec_mt = true; }
+        else if (m == 1) { prev_mt = true; rec_mt = false; }
+        else { prev_mt = true; rec_mt = true; }
+        ma = prev_mt ? prev.s.mt : prev.s.wt; man = prev_mt ? prev.s.mt_len : prev.s.wt_len;
+        mb = rec_mt ? record.s.mt : record.s.wt; mbn = rec_mt ? record.s.mt_len : record.s.wt_len;
         const uint64_t mn = (uint64_t)man + mbn;
+        const uint64_t dmask = masks ? ((prev_mt ? prev.diff : 0) | ((rec_mt ? record.diff : 0) << wan)) : 0;
+        if (masks && dmask == 0) continue;
         uint64_t splice_offset = 3, end_offset = 3;  // frameshift 0, exon_rest >= 3 and not the exon's last window in this class
         if (mn < 2 * wl) { if (fwd) splice_offset = 0; else end_offset = 0; }
         uint32_t guard = 0;
@@ -401,7 +428,11 @@ MPH_HD uint32_t mph_rc_merge(const MphRecCtx& c, const MphSegment& sp, const Mph
             if (have_wt) { if (wn < end_offset + wl) { *err |= MPH_E_SLICE; break; } ws = wn - end_offset - wl; }
           }
           bool equal = have_wt;
-          for (uint32_t x = 0; equal && x < wl; ++x) equal = mph_rc_cat(ma, man, mb, (uint32_t)(ms + x)) == mph_rc_cat(wa, wan, wb, (uint32_t)(ws + x));
+          if (masks && have_wt) {
+            equal = ((dmask >> ms) & ((wl >= 64 ? ~(uint64_t)0 : (((uint64_t)1 << wl) - 1)))) == 0;
+          } else {
+            for (uint32_t x = 0; equal && x < wl; ++x) equal = mph_rc_cat(ma, man, mb, (uint32_t)(ms + x)) == mph_rc_cat(wa, wan, wb, (uint32_t)(ws + x));
+          }
           if (equal || !have_wt) {  // non mutated site, or no wild type at frameshift 0 (:1795-1810)
             if (fwd) splice_offset += 3; else end_offset += 3;
             continue;
