@@ -201,7 +201,7 @@ MPH_HD uint32_t mph_rc_window_count(const MphRecCtx& c, const MphSegment& sg, ui
     *err |= e.err;
     if (!(e.emit_ok && e.freq > 0.0 && q <= q_stop)) continue;  // after the removing haplotype the ORF frequency is 0 (:423)
     ++n;
-    bytes += 2u * (uint32_t)key.h->seq_len + 8u;  // upper bound, rounded per record below
+    bytes += (uint32_t)key.h->seq_len + (uint32_t)key.h->germ_len;  // upper bound: the slices are parts of seq and germline_seq
   }
   *seq_bytes = bytes;
   return n;
@@ -381,7 +381,6 @@ MPH_HD uint32_t mph_rc_merge(const MphRecCtx& c, const MphSegment& sp, const Mph
   const uint64_t wl = window_len;
   const double eps = 2.220446049250313e-16;
   uint32_t n_out = 0;
-  const uint32_t t0 = c.tx_id_off[sj.tx], tlen = c.tx_id_off[sj.tx + 1] - t0;
   // the two lists are small (haplotype 0 plus the few variant haplotypes of a window): build their entries once
   enum { LIST_CACHE = 6 };
   MphListEntry first_c[LIST_CACHE], sec_c[LIST_CACHE];
@@ -468,7 +467,7 @@ MPH_HD uint32_t mph_rc_merge(const MphRecCtx& c, const MphSegment& sp, const Mph
             mph_rc_keep(c.vars, self, true, fwd, out_offset, wl, &ka, &sa, &ga);
             mph_rc_keep(c.vars, other, false, fwd, out_offset, wl, &kb, &sb, &gb);
             MphRec r;
-            r.id64 = mph_record_id64(mtb, (uint32_t)wl, c.tx_id_bytes + t0, tlen, (uint32_t)out_offset);
+            r.id64 = out_offset;  // the id is hashed afterwards, one thread per record (mph_rc_merged_id): sha1 needs the key's offset
             r.tx = sj.tx;
             r.offset = (uint32_t)(fwd ? self.offset + out_offset : other.offset + wl + 3 - out_offset);
             r.depth = (other.depth == 0 || self.depth == 0) ? 0u : (other.depth + self.depth) / 2u;
@@ -520,4 +519,11 @@ MPH_HD uint32_t mph_rc_merge(const MphRecCtx& c, const MphSegment& sp, const Mph
     for (uint32_t x = 0; x < n_out; ++x) recs[x].aux = aux_base + x;
   }
   return n_out;
+}
+
+// record id of a merged record (common.rs:385-391: sha1 over the mutant window, the transcript id and the key's offset,
+// which mph_rc_merge left in id64); `mt` = the record's mutant window in the merge arena
+MPH_HD void mph_rc_merged_id(const MphRecCtx& c, MphRec* r, const uint8_t* mt, uint32_t window_len) {
+  const uint32_t t0 = c.tx_id_off[r->tx], tlen = c.tx_id_off[r->tx + 1] - t0;
+  r->id64 = mph_record_id64(mt, window_len, c.tx_id_bytes + t0, tlen, (uint32_t)r->id64);
 }

@@ -135,8 +135,12 @@ __global__ void __launch_bounds__(RC_THREADS) k_rc_count(const DeviceBatch d) {
         const uint32_t ub = mph_rc_merge(c, sp, sg, d.window_len, nullptr, nullptr, nullptr, 0, 0, 0, &err);
         if (ub) {
           mbase = atomicAdd(&d.counters[CTR_MERGE], ub);
-          if (mbase + ub <= d.m_cap) nm = mph_rc_merge(c, sp, sg, d.window_len, d.m_recs + mbase, d.m_aux + mbase, d.m_seq, mbase, mbase * MPH_RC_SEQ_SLOT, ub, &err);
-          else err |= MPH_E_REC_OVERFLOW;
+          if (mbase + ub <= d.m_cap) {
+            nm = mph_rc_merge(c, sp, sg, d.window_len, d.m_recs + mbase, d.m_aux + mbase, d.m_seq, mbase, mbase * MPH_RC_SEQ_SLOT, ub, &err);
+            for (uint32_t z = nm; z < ub; ++z) d.m_recs[mbase + z].flags = 0;  // slots the de-duplication left unused
+          } else {
+            err |= MPH_E_REC_OVERFLOW;
+          }
         }
       }
       if (nm > 0xFFFu || n > 0xFFFu) { err |= MPH_E_REC_OVERFLOW; nm = 0; n = 0; }
@@ -148,9 +152,21 @@ __global__ void __launch_bounds__(RC_THREADS) k_rc_count(const DeviceBatch d) {
     d.rw_info[x] = info;
     d.rw_mbase[x] = mbase;
   }
-  uint32_t total;
-  block_exclusive(n, &total);
-  if (threadIdx.x == 0) d.rc_blocks[blockIdx.x] = total;
+  // block sum without a barrier: a warp that has no junction to merge retires at once (rc_blocks was zeroed by the host)
+  for (int o = 16; o; o >>= 1) n += __shfl_down_sync(FULL, n, o);
+  if ((threadIdx.x & 31) == 0 && n) atomicAdd(&d.rc_blocks[blockIdx.x], n);
+}
+
+// record ids of the junction records: one thread per slot of the merge arena (sha1 is ~4 k instructions per record; inside
+// the merge it would run serially in the junction's thread)
+__global__ void __launch_bounds__(128) k_rc_ids(const DeviceBatch d) {
+  const uint32_t x = blockIdx.x * 128 + threadIdx.x;
+  if (x >= min(d.counters[CTR_MERGE], d.m_cap)) return;
+  MphRec r = d.m_recs[x];
+  if (!(r.flags & MPH_RC_MERGED)) return;
+  const MphRecCtx c = rec_ctx(d);
+  mph_rc_merged_id(c, &r, d.m_seq + (size_t)x * MPH_RC_SEQ_SLOT, d.window_len);
+  d.m_recs[x].id64 = r.id64;
 }
 
 __global__ void __launch_bounds__(RC_THREADS) k_rc_emit(const DeviceBatch d) {
@@ -220,11 +236,13 @@ void launch_records(const DeviceBatch& d, cudaStream_t st) {
   // windows of the slice cannot exceed its windows); threads beyond the count return at once
   const uint32_t nbl = nb;
   k_rc_stop<<<nbl, RC_THREADS, 0, st>>>(d);
+  cudaMemsetAsync(d.rc_blocks, 0, (size_t)nbl * sizeof(uint32_t), st);
   k_rc_count<<<nbl, RC_THREADS, 0, st>>>(d);
+  k_rc_ids<<<(d.m_cap + 127) / 128, 128, 0, st>>>(d);
   k_rc_scan<<<1, 1024, 0, st>>>(d, nbl, CTR_NREC);
   k_rc_emit<<<nbl, RC_THREADS, 0, st>>>(d);
 }
-int record_kernel_launch_count() { return 7; }
+int record_kernel_launch_count() { return 8; }
 
 void launch_live_depth(const DeviceBatch& d, cudaStream_t st) {
   if (d.c1 > d.c0) k_live_depth2<<<(d.c1 - d.c0 + 7) / 8, 256, 0, st>>>(d);

@@ -407,6 +407,7 @@ inline PhaseRaw phase_somatic(const Batch& b) {
             const size_t sb = raw.rec_seq.size(), ab = raw.rec_aux.size();
             raw.rec_seq.resize(sb + size_t(ub) * MPH_RC_SEQ_SLOT, 0);
             const uint32_t nm = mph_rc_merge(c, sp, sg, b.window_len, mr.data(), ma.data(), raw.rec_seq.data(), uint32_t(ab), uint32_t(sb), ub, &err);
+            for (uint32_t x = 0; x < nm; ++x) mph_rc_merged_id(c, &mr[x], raw.rec_seq.data() + mr[x].seq_off, b.window_len);
             raw.rec_aux.insert(raw.rec_aux.end(), ma.begin(), ma.begin() + nm);
             const size_t rb = raw.recs.size();
             raw.recs.resize(rb + nm);
