@@ -1,20 +1,26 @@
 #!/usr/bin/env python3
 """bench.py — phased windows/s of the per-window phasing hot path on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload exome|chr22]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload exome|chr22|hypermutated|normal|filter]
 
-Workload (config.workload): one whole-exome-shaped shard per GPU — BASELINE.json config 3
+Default workload (config.workload): one whole-exome-shaped shard per GPU — BASELINE.json configs[2]
 ("synthetic whole exome (~20k transcripts), 100x tumor BAM, somatic mode"): 20 000 single-transcript
-genes x 8 CDS exons, 150 bp reads at 100x, 1 germline + 1 somatic SNV per kb. It fits one GPU
-(~1.5 GB packed) and is far larger than the 126 MB L2, so no L2 flush is needed between steps.
-Weak scaling: every rank phases its own shard (different seed), there is no collective on the data
-path; ranks only meet at the timing barrier.
+genes x 8 CDS exons, 150 bp reads at 100x, 1 germline + 1 somatic SNV per kb. It fits one GPU and is far
+larger than the 126 MB L2, so no L2 flush is needed between steps. Weak scaling: every rank phases its own
+shard (different seed), there is no collective on the data path; ranks only meet at the timing barrier.
+The other workloads are the remaining synthetic configs of BASELINE.json (chr22 exome, hypermutated tumour,
+`normal` healthy peptidome, `filter` set probe).
 
 A step = one pass of the hot path over the shard.
-  value : windows/s with the packed shard resident in HBM (kernels K1-K4, CUDA events on the
+  value : windows/s with the packed shard resident in HBM (all kernels of the path, CUDA events on the
           library's stream, max over ranks).
-  e2e   : windows/s through the C ABI call mph_phase_batch with pinned HOST buffers: H2D copy,
-          kernels, D2H copy and the host residue that yields the ordered records.
+  e2e   : windows/s through the C ABI call mph_phase_batch with pinned HOST buffers: H2D copy, kernels,
+          D2H copy of the ordered records (plus the host residue of the irregular transcripts).
+  e2e_files : files -> files on a bounded slice of the workload: BAM / VCF / GTF / FASTA in, FASTA / TSV out
+          through mph_run_somatic (ingest, packing, phasing, text rendering and writing all on the clock),
+          next to the CPU oracle on the same files.
+  parity_checked : records of the benched batch that were compared byte for byte with the oracle's output.
   roofline     : dominant kernel vs the measured HBM copy bandwidth (MEASURED_PEAKS.json).
   cpu_baseline : the CPU oracle (a restatement of the reference's Rust code, which cannot be built
           here — no cargo/rustc) on one core over a bounded sample of the same workload.
@@ -34,13 +40,32 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: (transcripts per GPU, coverage, description)
-    "exome": (20000, 100.0, "synthetic whole exome shard per GPU (BASELINE.json configs[2]): 20000 transcripts x 8 exons, 100x, 150 bp, 1+1 SNV/kb"),
-    "chr22": (450, 30.0, "synthetic chr22 exome (BASELINE.json configs[1]): 450 transcripts x 8 exons, 30x, 150 bp, 1+1 SNV/kb"),
+    "exome": dict(n_transcripts=20000, coverage=100.0, germline_per_kb=1.0, somatic_per_kb=1.0, ins_var_frac=0.0, del_var_frac=0.0, mode="somatic",
+                  desc="synthetic whole exome shard per GPU (BASELINE.json configs[2]): 20000 transcripts x 8 exons, 100x, 150 bp, 1+1 SNV/kb"),
+    "chr22": dict(n_transcripts=450, coverage=30.0, germline_per_kb=1.0, somatic_per_kb=1.0, ins_var_frac=0.0, del_var_frac=0.0, mode="somatic",
+                  desc="synthetic chr22 exome (BASELINE.json configs[1]): 450 transcripts x 8 exons, 30x, 150 bp, 1+1 SNV/kb"),
+    "hypermutated": dict(n_transcripts=4000, coverage=100.0, germline_per_kb=1.0, somatic_per_kb=10.0, ins_var_frac=0.1, del_var_frac=0.1, mode="somatic",
+                         desc="synthetic hypermutated tumour (BASELINE.json configs[3]): 4000 transcripts x 8 exons, 100x, 150 bp, 1 germline + 10 somatic variants/kb, 10 % insertions + 10 % deletions"),
+    "normal": dict(n_transcripts=5000, coverage=30.0, germline_per_kb=1.0, somatic_per_kb=1.0, ins_var_frac=0.0, del_var_frac=0.0, mode="normal",
+                   desc="synthetic healthy peptidome, `normal` mode (BASELINE.json configs[4]a): 5000 transcripts x 8 exons, 30x, 150 bp, every window is a record"),
+    "filter": dict(desc="`filter` set probe (BASELINE.json configs[4]b): 1 M neopeptides (9-mers) against a normal peptidome of 8 M distinct 9-mers", mode="filter"),
 }
 SEED = 0x4D500003
 METRIC = "phased peptide windows/sec"
 UNIT = "windows/s"
+
+
+def config_of(name):
+    """The `config` dict of both arms (identical by construction)."""
+    w = WORKLOADS[name]
+    big = name in ("exome", "hypermutated", "normal", "filter")
+    return {"workload": w["desc"],
+            "l2": "inputs larger than the 126 MB L2, no flush between steps" if big else "inputs fit in L2: a 256 MB buffer is rewritten between steps",
+            "sharding": "one shard per GPU by gene range, no collective"}
+
+
+def synth_kw(name):
+    return {k: v for k, v in WORKLOADS[name].items() if k != "desc"}
 
 
 def clocks_sampler(device, stop, out):
@@ -80,28 +105,33 @@ def summarize_clocks(lines):
     return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons)}
 
 
-def oracle_sample(n_transcripts, coverage, seed, tmp):
-    """Write a bounded sample of the workload as files and return (dir, generation seconds)."""
-    import microphaser_b200 as m
-    d = os.path.join(tmp, "sample")
+def ensure_oracle():
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle")], check=True)
+
+
+def write_sample_files(name, n_transcripts, seed, d):
+    """The first `n_transcripts` transcripts of the workload as files, written by oracle/_build/mph_synth_files: a stand-alone
+    tool built from the generator's host-only header, so the reference arm never loads the CUDA library."""
+    kw = synth_kw(name)
+    os.makedirs(d, exist_ok=True)
     t = time.time()
-    m.synth_write_files(d, n_transcripts=n_transcripts, coverage=coverage, seed=seed)
-    return d, time.time() - t
+    subprocess.run([os.path.join(ROOT, "oracle", "_build", "mph_synth_files"), d, str(seed), str(n_transcripts), str(kw["coverage"]),
+                    str(kw["germline_per_kb"]), str(kw["somatic_per_kb"]), str(kw["ins_var_frac"]), str(kw["del_var_frac"])],
+                   check=True, stdout=subprocess.DEVNULL)
+    return time.time() - t
 
 
-def run_oracle(d, tag):
+def run_oracle(d, tag, mode="somatic"):
     stats = os.path.join(d, "stats_%s.json" % tag)
     env = dict(os.environ, MPH_ORACLE_STATS=stats)
     oracle = os.path.join(ROOT, "oracle", "_build", "mph_oracle")
+    cmd = [oracle, mode, os.path.join(d, "reads.bam"), "-r", os.path.join(d, "ref.fa"), "-b", os.path.join(d, "variants.vcf"), "-t",
+           os.path.join(d, "o_%s.tsv" % tag)]
+    if mode == "somatic":
+        cmd += ["-n", os.path.join(d, "o_%s.n.fa" % tag)]
     with open(os.path.join(d, "annotation.gtf")) as gin, open(os.path.join(d, "o_%s.fa" % tag), "wb") as fo:
-        p = subprocess.Popen([oracle, "somatic", os.path.join(d, "reads.bam"), "-r", os.path.join(d, "ref.fa"), "-b",
-                              os.path.join(d, "variants.vcf"), "-t", os.path.join(d, "o_%s.tsv" % tag), "-n", os.path.join(d, "o_%s.n.fa" % tag)],
-                             stdin=gin, stdout=fo, stderr=subprocess.DEVNULL, env=env)
+        p = subprocess.Popen(cmd, stdin=gin, stdout=fo, stderr=subprocess.DEVNULL, env=env)
     return p, stats
-
-
-def ensure_oracle():
-    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle")], check=True)
 
 
 def reference_arm(args, rank, world):
@@ -109,16 +139,21 @@ def reference_arm(args, rank, world):
     if rank != 0:
         return
     ensure_oracle()
-    n_tx, cov, desc = WORKLOADS[args.workload]
+    name = args.workload
+    if name == "filter":
+        print(json.dumps({"impl": "reference", "unavailable": "the filter probe workload has no file-level oracle arm; see tests/test_gpu_peptides.py"}))
+        return
+    w = WORKLOADS[name]
     cores = os.cpu_count() or 1
-    sample_tx = min(n_tx, 200)
+    sample_tx = min(w["n_transcripts"], 200)
     with tempfile.TemporaryDirectory() as tmp:
-        d, gen_s = oracle_sample(sample_tx, cov, SEED, tmp)
+        d = os.path.join(tmp, "sample")
+        write_sample_files(name, sample_tx, SEED, d)
         per_step = []
         windows = 0
         for step in range(args.warmup + args.steps):
             t0 = time.time()
-            procs = [run_oracle(d, "p%d" % i) for i in range(cores)]
+            procs = [run_oracle(d, "p%d" % i, w["mode"]) for i in range(cores)]
             for p, _ in procs:
                 p.wait()
             dt = time.time() - t0
@@ -127,11 +162,12 @@ def reference_arm(args, rank, world):
                 per_step.append(dt)
         ms = 1000.0 * sum(per_step) / len(per_step)
         value = windows / (ms / 1000.0)
-    sample = "%d of %d transcripts of the workload (%d main-ORF windows), one oracle process per core on the same sample" % (sample_tx, n_tx, windows // cores)
+    sample = "first %d of %d transcripts of the workload (%d main-ORF windows), one oracle process per core on the same sample, files -> files" % (
+        sample_tx, w["n_transcripts"], windows // cores)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": desc, "l2": "n/a (CPU)"},
+        "config": config_of(name),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -156,6 +192,56 @@ def aggregate_over_ranks(dist, device, dev_ms, e2e_ms, windows, read_windows):
     return mx[0].item(), mx[1].item(), sm[2].item(), sm[3].item()
 
 
+KERNEL_KEYS = ("k1_ms", "replay_ms", "k2_ms", "k3_ms", "k4_ms", "k5_ms")
+
+
+def filter_workload(args, rank, local_rank, world, dist, barrier):
+    """BASELINE.json configs[4]b: ref_set.contains(peptide) for 1 M neopeptides (reference src/peptides.rs:502,684)."""
+    import numpy as np
+    import torch
+    import microphaser_b200 as m
+    ctx = m.Context(local_rank)
+    rng = np.random.default_rng(SEED + rank)
+    aa = np.frombuffer(b"ACDEFGHIKLMNPQRSTVWY", dtype=np.uint8)
+    n_ref, n_q, k = 8_000_000, 1_000_000, 9
+    ref = aa[rng.integers(0, 20, size=(n_ref, k))]
+    queries = aa[rng.integers(0, 20, size=(n_q, k))]
+    queries[: n_q // 4] = ref[rng.integers(0, n_ref, size=n_q // 4)]  # a quarter of the queries are members
+    ctx.set_load(ref, k)
+    ms, kern = [], []
+    hits = None
+    for i in range(args.warmup + args.steps):
+        barrier()
+        t0 = time.perf_counter()
+        hits = ctx.set_probe(queries, k)
+        dt = (time.perf_counter() - t0) * 1000.0
+        if i >= args.warmup:
+            ms.append(dt)
+            kern.append(ctx.timing()["k1_ms"])
+    ref_set = set(map(bytes, ref[:200000]))
+    sample = queries[:5000]
+    for q, h in zip(sample, hits[:5000]):
+        if bytes(q) in ref_set:
+            assert h == 1, "a member of the reference set was not found"
+    assert int(hits[: n_q // 4].sum()) == n_q // 4
+    step_ms, k_ms = sum(ms) / len(ms), sum(kern) / len(kern)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak = json.load(open(peaks_path))["hbm_gbs"] if os.path.exists(peaks_path) else 6650.0
+    alg = n_q * (k + 1) + n_q * 32  # query bytes in, hit byte out, one 32 B sector of the table per probe
+    achieved = alg / (k_ms / 1000.0) / 1e9 if k_ms > 0 else 0.0
+    if rank == 0:
+        print(json.dumps({
+            "metric": "filter peptides/sec", "value": n_q * world / (k_ms / 1000.0) if k_ms > 0 else None, "unit": "peptides/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": k_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+            "data": "synthetic", "config": config_of("filter"),
+            "e2e": {"value": n_q * world / (step_ms / 1000.0), "unit": "peptides/s", "h2d_bytes_per_step": n_q * k, "d2h_bytes_per_step": n_q, "ms_per_step": step_ms},
+            "gpu_launches": args.steps,
+            "roofline": {"bound": "hbm", "kernel": "k_set_probe", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "note": "random 32 B sector reads of a 256 MB open-addressing table: sector-bound, not streaming"},
+            "cpu_baseline": None}))
+    ctx.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -163,9 +249,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="exome", choices=sorted(WORKLOADS))
-    ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--cpu-sample-transcripts", type=int, default=600)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-transcripts", type=int, default=1000)
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the oracle run (and with it the parity check and e2e_files)")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="end-to-end calls to time (default: --steps)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -184,20 +270,29 @@ def main():
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    n_tx, cov, desc = WORKLOADS[args.workload]
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # the host residue is multi-threaded: every rank gets its share of the cores
+    if args.workload == "filter":
+        filter_workload(args, rank, local_rank, world, dist, barrier)
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    name = args.workload
+    w = WORKLOADS[name]
+    kw = synth_kw(name)
+    mode = kw["mode"]
+    # the few host threads the call still uses (host-class transcripts, record copies): every rank gets its share of the cores
     local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
-    if local_world > 1:  # a single rank keeps the library's default (all cores but one, which the calling thread uses)
+    if local_world > 1:
         os.environ.setdefault("MPH_HOST_THREADS", str(max(1, (os.cpu_count() or 1) // local_world)))
     ctx = m.Context(local_rank)
     t0 = time.time()
-    batch = m.Batch.synthetic(n_transcripts=n_tx, coverage=cov, seed=shard_seed(rank), pin=True)
+    batch = m.Batch.synthetic(seed=shard_seed(rank), pin=True, **kw)
     gen_s = time.time() - t0
     view = batch.view()
 
@@ -219,7 +314,7 @@ def main():
     sampler = threading.Thread(target=clocks_sampler, args=(local_rank, stop, clk_lines), daemon=True)
     sampler.start()
     barrier()
-    per_kernel = {"k1_ms": 0.0, "replay_ms": 0.0, "k2_ms": 0.0, "k3_ms": 0.0, "k4_ms": 0.0}
+    per_kernel = {k: 0.0 for k in KERNEL_KEYS}
     wall0 = time.perf_counter()
     for _ in range(args.steps):
         l2_flush()
@@ -237,20 +332,24 @@ def main():
     dev_ms = sum(per_kernel.values()) / args.steps
 
     # ---- end to end through the C ABI: pinned host buffers -> ordered records
+    n_e2e = args.e2e_steps or args.steps
     e2e_ms, h2d_b, d2h_b = [], 0, 0
     stage = {k: 0.0 for k in ("h2d_ms", "d2h_ms", "residue_ms")}
-    for i in range(1 + args.e2e_steps):
+    last = None
+    for i in range(1 + n_e2e):
         barrier()
         w0 = time.perf_counter()
         r = ctx.phase_batch(batch)
         dt = (time.perf_counter() - w0) * 1000.0
         t = ctx.timing()
-        r.close()
+        if last is not None:
+            last.close()
+        last = r
         if i > 0:
             e2e_ms.append(dt)
             h2d_b, d2h_b = t["h2d_bytes"], t["d2h_bytes"]
             for k in stage:
-                stage[k] += t[k] / args.e2e_steps
+                stage[k] += t[k] / n_e2e
     stop.set()
     sampler.join(timeout=3)
     e2e_step_ms = sum(e2e_ms) / len(e2e_ms)
@@ -258,6 +357,7 @@ def main():
     # ---- max over ranks
     dev_ms_max, e2e_ms_max, windows_all, rw_all = aggregate_over_ranks(dist, "cuda:%d" % local_rank, dev_ms, e2e_step_ms, windows, read_windows)
     if rank != 0:
+        last.close()
         if dist is not None:
             dist.destroy_process_group()
         return
@@ -271,14 +371,16 @@ def main():
     n_reads, n_win, n_seg, n_chunk = view.n_reads, view.n_windows, view.n_segments, view.n_chunks
     n_special = float(view.n_variant_reads)  # side-table entries: reads that overlap a variant
     alg = {
-        # zero-fill of S / B / flag / nv for every read, then per side-table entry: entry in (21 B), start / end (8 B), one base
+        # zero-fill of flag / nv for every read (2 B), then per side-table entry: entry in (21 B), start / end (8 B), one base
         # sector + one quality sector (64 B), S / B / flag / vlo / nv / index out (26 B)
-        "k1_ms": n_reads * 18 + n_special * (21 + 8 + 64 + 26) + view.n_vars * 16,
-        # per read: start, end, call flag, host flag (10 B); per listed read: S + vlo + B (20 B); per window: summary + flag out (17 B);
-        # per interesting window: haplotype-0 record (32 B); per extra key (about two per record): key + window code (20 B)
-        "k2_ms": n_reads * 10 + n_special * 20 + n_win * 17 + t_res["n_interesting"] * 32 + n_records * 2 * 20 + n_seg * 96 + n_chunk * 32,
-        "k3_ms": n_win * (16 + 32 + 1) + view.ref_bytes + n_seg * 96 + n_chunk * 32,
+        "k1_ms": n_reads * 2 + n_special * (21 + 8 + 64 + 26) + view.n_vars * 16,
+        # K2a: start, end, call flag, host flag per (segment, read) pair (10 B) + S / B / vlo of the listed reads (20 B) + their list
+        # entries (8 B out); K2b: difference array in (4 B) and summary + flag out (17 B) per window, list entries in (8 B),
+        # haplotype-0 record (32 B) per interesting window, 20 B per extra key
+        "k2_ms": n_reads * 10 + n_special * (20 + 8 + 8) + n_win * (4 + 4 + 17) + (t_res["n_interesting"] + n_records) * 32 + n_records * 2 * 20 + n_seg * (96 + 16) + n_chunk * 32,
+        "k3_ms": n_records * 2 * (16 + 4 + 32) + view.ref_bytes + n_seg * 96 + n_chunk * 32,
         "k4_ms": n_win * 2 + t_res["n_interesting"] * (4 + 2 * 48),
+        "k5_ms": n_win * 3 + n_records * (64 + 64 + 48 + 32),
     }
     # k_replay (irregular transcripts) is a latency-bound dependent chain, not a streaming kernel: it counts in ms_per_step
     # but is not a roofline candidate
@@ -288,8 +390,9 @@ def main():
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
-        traffic = json.load(open(tp)).get(dom)
-    roofline = {"bound": "hbm", "kernel": {"k1_ms": "k_allele_call", "k2_ms": "k_window_hist", "k3_ms": "k_assemble", "k4_ms": "compaction"}[dom],
+        traffic = json.load(open(tp)).get(dom if mode == "somatic" else dom + "_" + mode)
+    roofline = {"bound": "hbm", "kernel": {"k1_ms": "k_allele_call", "k2_ms": "k_read_runs + k_window_hist", "k3_ms": "k_assemble", "k4_ms": "compaction",
+                                           "k5_ms": "record kernels"}[dom],
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "kernel_ms": {k: v / args.steps for k, v in per_kernel.items()},
                 "pipeline_GBs": sum(alg.values()) / (dev_ms / 1000.0) / 1e9, "pipeline_frac": sum(alg.values()) / (dev_ms / 1000.0) / 1e9 / peak,
@@ -298,30 +401,73 @@ def main():
                 "survey_model": {"bytes_per_window": 550, "GBs": 550.0 * n_win / (dev_ms / 1000.0) / 1e9,
                                  "frac": 550.0 * n_win / (dev_ms / 1000.0) / 1e9 / peak}}
 
-    # ---- CPU baseline: the oracle on one core over a bounded sample of the same workload
-    cpu = None
+    # ---- CPU baseline, parity of the benched batch, files -> files: one oracle run on a bounded slice of the rank-0 shard
+    cpu, parity_checked, e2e_files = None, 0, None
     if not args.no_cpu_baseline:
         ensure_oracle()
         with tempfile.TemporaryDirectory() as tmp:
-            sample_tx = min(n_tx, args.cpu_sample_transcripts)
-            d, _ = oracle_sample(sample_tx, cov, SEED, tmp)
-            p, stats = run_oracle(d, "one")
+            sample_tx = min(w["n_transcripts"], args.cpu_sample_transcripts)
+            d = os.path.join(tmp, "sample")
+            write_sample_files(name, sample_tx, shard_seed(0), d)
+            p, stats = run_oracle(d, "one", mode)
+            t_o = time.perf_counter()
             p.wait()
+            oracle_wall = time.perf_counter() - t_o
             st = json.load(open(stats))
             cpu = {"value": st["windows"] / st["phase_s"], "unit": UNIT, "cores": 1, "kind": "port",
-                   "sample": "first %d of %d transcripts of the rank-0 shard: %d windows, %d read*windows in %.1f s (BAM decode included)" %
-                             (sample_tx, n_tx, st["windows"], st["read_windows"], st["phase_s"]),
+                   "sample": "first %d of %d transcripts of the rank-0 shard (the same genes, reads and variants as the packed batch): %d windows, %d read*windows in %.1f s (BAM decode included)" %
+                             (sample_tx, w["n_transcripts"], st["windows"], st["read_windows"], st["phase_s"]),
                    "read_windows_per_s": st["read_windows"] / st["phase_s"]}
+            streams = [("fa", "out.fa"), ("tsv", "out.tsv")] + ([("n.fa", "out.normal.fa")] if mode == "somatic" else [])
+            # (1) the benched batch: the oracle's bytes must be a prefix of what the GPU result writes (records of the first
+            #     transcripts do not depend on the later ones)
+            outs = {n: os.path.join(tmp, "gpu_" + n) for _, n in streams}
+            last.write(outs["out.fa"], outs["out.tsv"], outs.get("out.normal.fa", os.path.join(tmp, "gpu_unused")))
+            for ext, n in streams:
+                want = open(os.path.join(d, "o_one." + ext), "rb").read()
+                got = open(outs[n], "rb").read(len(want))
+                if got != want:
+                    raise SystemExit("PARITY FAILURE: %s of the benched batch differs from the oracle on its first %d transcripts" % (n, sample_tx))
+                if n == "out.tsv":
+                    parity_checked = max(0, want.count(b"\n") - 1)
+            # (2) files -> files through the file driver on the same slice
+            fo = {n: os.path.join(tmp, "files_" + n) for _, n in streams}
+            runs = []
+            for rep in range(3):
+                t_f = time.perf_counter()
+                if mode == "normal":
+                    ctx.run_normal(os.path.join(d, "reads.bam"), os.path.join(d, "ref.fa"), os.path.join(d, "variants.vcf"), os.path.join(d, "annotation.gtf"),
+                                   fo["out.fa"], fo["out.tsv"])
+                else:
+                    ctx.run_somatic(os.path.join(d, "reads.bam"), os.path.join(d, "ref.fa"), os.path.join(d, "variants.vcf"), os.path.join(d, "annotation.gtf"),
+                                    fo["out.fa"], fo["out.tsv"], fo["out.normal.fa"])
+                runs.append((time.perf_counter() - t_f, ctx.timing()))
+            for ext, n in streams:
+                if open(fo[n], "rb").read() != open(os.path.join(d, "o_one." + ext), "rb").read():
+                    raise SystemExit("PARITY FAILURE: %s of the file driver differs from the oracle" % n)
+            wall_f, t_f = min(runs, key=lambda x: x[0])
+            cores = os.cpu_count() or 1
+            e2e_files = {"value": st["windows"] / wall_f, "unit": UNIT, "seconds": wall_f, "transcripts": sample_tx, "windows": st["windows"],
+                         "stages_ms": {k: t_f[k] for k in ("ingest_ms", "pack_ms", "h2d_ms", "d2h_ms", "residue_ms", "write_ms", "total_ms")},
+                         "oracle_1core": {"value": st["windows"] / oracle_wall, "seconds": oracle_wall},
+                         "oracle_all_cores_estimate": {"value": st["windows"] / oracle_wall * cores, "cores": cores,
+                                                       "note": "the reference is single-threaded per invocation; independent processes on disjoint gene ranges scale with the cores (--impl reference measures it)"},
+                         "ratio_vs_oracle_1core": oracle_wall / wall_f, "ratio_vs_oracle_all_cores_estimate": oracle_wall / wall_f / cores,
+                         "outputs_identical_to_oracle": True}
+    last.close()
 
     line = {
         "metric": METRIC, "value": windows_all / (dev_ms_max / 1000.0), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_ms_max, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": desc, "windows_per_gpu": windows, "reads_per_gpu": n_reads, "read_windows_per_gpu": read_windows,
-                   "records_per_gpu": n_records, "interesting_windows_per_gpu": t_res["n_interesting"], "replay_units_per_gpu": t_res["n_replay_units"], "l2": "inputs (%.2f GB/GPU) larger than L2, no flush" % (view.h2d_bytes / 1e9) if view.h2d_bytes > 3e8 else "inputs fit in L2: a 256 MB buffer is rewritten between steps",
-                   "sharding": "one shard per GPU by gene range, no collective", "generation_s": gen_s},
+        "config": config_of(name),
+        "shape": {"windows_per_gpu": windows, "reads_per_gpu": n_reads, "read_windows_per_gpu": read_windows, "records_per_gpu": n_records,
+                  "host_residue_windows_per_gpu": t_res["n_interesting"], "replay_units_per_gpu": t_res["n_replay_units"],
+                  "h2d_GB_per_gpu": view.h2d_bytes / 1e9, "generation_and_packing_s": gen_s},
         "read_windows_per_s": rw_all / (dev_ms_max / 1000.0),
         "e2e": {"value": windows_all / (e2e_ms_max / 1000.0), "unit": UNIT, "h2d_bytes_per_step": h2d_b, "d2h_bytes_per_step": d2h_b,
-                "ms_per_step": e2e_ms_max, "stages_ms": stage},
+                "ms_per_step": e2e_ms_max, "calls_timed": n_e2e, "stages_ms": stage},
+        "e2e_files": e2e_files,
+        "parity_checked": parity_checked,
         "gpu_launches": int(t_res["kernel_launches"]) * args.steps,
         "roofline": roofline,
         "cpu_baseline": cpu,

@@ -152,6 +152,8 @@ typedef struct {
   double replay_ms;        /* k_replay, CUDA events; k2_ms is the closed-form window kernels alone */
   double k5_ms;            /* record kernels: ORF stop, emit predicate, junction merge, ordered compaction of the records */
   double pack_ms;          /* file drivers only: host time spent in the packer (wall clock, summed over the packing threads) */
+  double ingest_ms;        /* file drivers only: BGZF inflate + BAM decode, GTF / VCF / FASTA parsing and the per-gene fetches (wall clock) */
+  double write_ms;         /* file drivers only: rendering and writing the three output streams (wall clock, summed over the shards) */
 } mph_timing;
 int mph_ctx_timing(const mph_ctx* ctx, mph_timing* out);
 

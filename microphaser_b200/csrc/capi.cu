@@ -79,18 +79,59 @@ struct mph_packer {
   int mode = 0;
 };
 
+// One block of consecutive transcripts of a result. Records of host-class transcripts arrive as text-ready OutRecords
+// from the host residue; records of device-class transcripts stay in the compact form the record kernels produced
+// (core/record_core.h) and are rendered when they are read or written.
+struct ResultPart {
+  std::vector<OutRecord> host;   // ascending transcript
+  std::vector<MphRec> dev;       // ascending transcript; a transcript is in exactly one of the two
+  std::vector<uint8_t> dev_seq;
+  std::vector<MphRecSrc> dev_aux;
+  std::vector<OutRecord> rendered;  // all records of the part in order, built on first access through mph_result_get
+  std::once_flag once;
+  size_t size() const { return host.size() + dev.size(); }
+};
+
 struct mph_result {
   int mode = 0;
-  // records in the reference's order: the transcript ranges of the residue threads, kept as they were produced
-  std::vector<std::vector<OutRecord>> parts;
+  // records in the reference's order: the transcript blocks of the residue threads, kept as they were produced
+  std::deque<ResultPart> parts;
   std::vector<uint64_t> part_base;  // prefix counts, parts.size() + 1 entries
   uint64_t size() const { return part_base.empty() ? 0 : part_base.back(); }
-  const OutRecord& at(uint64_t i) const {
-    size_t p = size_t(std::upper_bound(part_base.begin(), part_base.end(), i) - part_base.begin()) - 1;
-    return parts[p][size_t(i - part_base[p])];
-  }
   std::vector<std::string> tx_id, gene_id, gene_name, chrom;
   std::vector<uint8_t> tx_reverse;
+  // what rendering a device-built record needs of the batch
+  std::vector<MphVar> vars;
+  std::vector<std::string> var_prot;
+
+  RenderCtx ctx_of(const ResultPart& p) const {
+    RenderCtx c;
+    c.vars = vars.data(); c.var_prot = &var_prot; c.seq = p.dev_seq.data(); c.aux = p.dev_aux.data();
+    return c;
+  }
+  // calls f(const OutRecord&) for every record of the part in transcript order; device-built ones are rendered on the fly
+  template <class F>
+  void for_each(const ResultPart& p, F&& f) const {
+    if (!p.rendered.empty() || p.size() == 0) { for (auto& r : p.rendered) f(r); return; }
+    const RenderCtx rc = ctx_of(p);
+    size_t h = 0, d = 0;
+    while (h < p.host.size() || d < p.dev.size()) {
+      const bool take_dev = h == p.host.size() || (d < p.dev.size() && p.dev[d].tx < p.host[h].info.tx);
+      if (take_dev) { const OutRecord r = render_record(rc, p.dev[d++]); f(r); }
+      else f(p.host[h++]);
+    }
+  }
+  const OutRecord& at(uint64_t i) {
+    const size_t pi = size_t(std::upper_bound(part_base.begin(), part_base.end(), i) - part_base.begin()) - 1;
+    ResultPart& p = parts[pi];
+    std::call_once(p.once, [&] {
+      std::vector<OutRecord> all;
+      all.reserve(p.size());
+      for_each(p, [&](const OutRecord& r) { all.push_back(r); });
+      p.rendered = std::move(all);
+    });
+    return p.rendered[size_t(i - part_base[pi])];
+  }
 };
 
 struct mph_ctx {
@@ -517,11 +558,38 @@ void fetch_stage(mph_ctx* c, const Stage& s, PhaseRaw& raw, uint64_t* n_iw_total
   *n_iw_total += n_iw;
 }
 
+// copies the device-built records of transcripts [tx_lo, tx_hi) with their bytes into a result part
+void take_device_records(const PhaseRaw& raw, uint32_t tx_lo, uint32_t tx_hi, ResultPart& part) {
+  auto by_tx = [](const MphRec& r, uint32_t t) { return r.tx < t; };
+  const auto d0 = std::lower_bound(raw.recs.begin(), raw.recs.end(), tx_lo, by_tx);
+  const auto d1 = std::lower_bound(d0, raw.recs.end(), tx_hi, by_tx);
+  if (d0 == d1) return;
+  part.dev.assign(d0, d1);
+  size_t bytes = 0, n_aux = 0;
+  for (const MphRec& r : part.dev) {
+    bytes += size_t(std::max(r.neo_len, r.mt_len)) + std::max(r.norm_len, r.wt_len);
+    n_aux += (r.flags & MPH_RC_MERGED) ? 1 : 0;
+  }
+  part.dev_seq.resize(bytes);
+  part.dev_aux.reserve(n_aux);
+  size_t pos = 0;
+  for (MphRec& r : part.dev) {
+    const size_t n = size_t(std::max(r.neo_len, r.mt_len)) + std::max(r.norm_len, r.wt_len);
+    memcpy(part.dev_seq.data() + pos, raw.rec_seq.data() + r.seq_off, n);
+    r.seq_off = uint32_t(pos);
+    pos += n;
+    if (r.flags & MPH_RC_MERGED) {
+      part.dev_aux.push_back(raw.rec_aux[r.aux]);
+      r.aux = uint32_t(part.dev_aux.size() - 1);
+    }
+  }
+}
+
 // host residue workers: transcripts are independent, blocks of them are taken from a queue that the stage loop fills
 struct ResiduePool {
   struct Task { const PhaseRaw* raw; uint32_t tx_lo, tx_hi; size_t part; };
   const Batch& b;
-  std::vector<std::vector<OutRecord>>& parts;
+  std::deque<ResultPart>& parts;
   std::vector<std::thread> threads;
   std::mutex mu;
   std::condition_variable cv;
@@ -537,7 +605,7 @@ struct ResiduePool {
   bool tracing = false;
   std::chrono::steady_clock::time_point wall0;
 
-  ResiduePool(const Batch& batch, std::vector<std::vector<OutRecord>>& out, unsigned n_thr)
+  ResiduePool(const Batch& batch, std::deque<ResultPart>& out, unsigned n_thr)
       : b(batch), parts(out), stats(n_thr), live(n_thr), errs(n_thr), busy_ms(n_thr, 0.0), trace(n_thr) {
     for (unsigned ti = 0; ti < n_thr; ++ti) threads.emplace_back([this, ti] { run(ti); });
   }
@@ -556,13 +624,14 @@ struct ResiduePool {
       try {
         if (b.mode == 1) {
           ResidueNormal r(b, *t.raw);
-          r.run(t.tx_lo, t.tx_hi, parts[t.part], stats[ti]);
+          r.run(t.tx_lo, t.tx_hi, parts[t.part].host, stats[ti]);
         } else {
           Residue r(b, *t.raw);
-          r.run(t.tx_lo, t.tx_hi, parts[t.part], stats[ti]);
+          r.run(t.tx_lo, t.tx_hi, parts[t.part].host, stats[ti]);
           live[ti].insert(live[ti].end(), r.seg_live_.begin(), r.seg_live_.end());
-          // the device-built records of this block's transcripts, rendered and put in transcript order with the host-built ones
-          if (!t.raw->recs.empty()) parts[t.part] = ordered_records(b, *t.raw, std::move(parts[t.part]), t.tx_lo, t.tx_hi);
+          // the device-built records of this block's transcripts: copied out of the (reused, page-locked) download buffers in
+          // their compact form; they are rendered when the result is read or written
+          take_device_records(*t.raw, t.tx_lo, t.tx_hi, parts[t.part]);
         }
       } catch (...) {
         errs[ti] = std::current_exception();
@@ -645,10 +714,12 @@ void phase_stages(mph_ctx* c, const std::vector<Stage>& stages, bool copied, mph
     blk[s] = uint32_t(std::min<uint64_t>(128, std::max<uint64_t>(16, n / (4 * uint64_t(n_thr)))));
     part0[s + 1] = part0[s] + size_t((n + blk[s] - 1) / blk[s]);
   }
-  std::vector<std::vector<OutRecord>> parts(part0[ns]);
+  std::deque<ResultPart> parts(part0[ns]);
   // transcript metadata of the result: copied while the first host -> device copy is in flight
   res->tx_id.reserve(b.txs.size()); res->gene_id.reserve(b.txs.size()); res->gene_name.reserve(b.txs.size()); res->chrom.reserve(b.txs.size());
   res->tx_reverse.reserve(b.txs.size());
+  res->vars = b.vars;
+  res->var_prot = b.var_prot;
   for (auto& t : b.txs) {
     res->tx_id.push_back(t.id);
     res->gene_id.push_back(b.genes[t.gene].id);
@@ -749,9 +820,10 @@ void phase_stages(mph_ctx* c, const std::vector<Stage>& stages, bool copied, mph
 // host buffers in, records out: the pipelined path
 void phase_batch_impl(mph_ctx* c, const mph_batch* mb, mph_result** out) {
   prepare(c, mb);
-  // stages of about 3.5 M reads: long enough to keep the copy engine at full rate, short enough to hide all but the first
-  // copy and the last residue
-  unsigned want = unsigned(std::min<uint64_t>(12, std::max<uint64_t>(1, mb->b.n_reads() / 3500000)));
+  // stages of about 7 M reads: every stage pays the fixed latency of its kernel chain (the serial replay's longest unit, the
+  // junction merges), so a few long stages beat many short ones now that almost no host work is left to hide behind the
+  // copies (measured on B200, whole-exome shard: 3-5 stages 18.7 ms, 8 stages 21.4 ms, 12 stages 26.8 ms per call)
+  unsigned want = unsigned(std::min<uint64_t>(12, std::max<uint64_t>(1, mb->b.n_reads() / 7000000)));
   if (const char* e = getenv("MPH_STAGES")) want = unsigned(std::max(1, atoi(e)));
   const std::vector<Stage> stages = plan_stages(mb, want);
   c->kernels_done = false;
@@ -840,10 +912,15 @@ void dev_set_probe(mph_ctx* c, const uint8_t* queries, uint32_t k, uint64_t n, u
   d_q.ensure(n * k); d_h.ensure(n);
   try {
     CU(cudaMemcpyAsync(d_q.p, queries, n * k, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaEventRecord(c->ev[2], c->stream));
     mphk::launch_set_probe(d_q.p, k, n, c->set_table.p, c->set_mask, d_h.p, c->stream);
+    CU(cudaEventRecord(c->ev[3], c->stream));
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(hit, d_h.p, n, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    float probe_ms = 0;
+    CU(cudaEventElapsedTime(&probe_ms, c->ev[2], c->ev[3]));
+    c->timing.k1_ms = probe_ms;  // measurement: the probe kernel alone
   } catch (...) {
     d_q.release(); d_h.release();
     throw;
@@ -1104,7 +1181,7 @@ uint64_t mph_result_count(const mph_result* r) { return r ? r->size() : 0; }
 
 int mph_result_get(const mph_result* r, uint64_t i, mph_record* o) {
   if (!r || !o || i >= r->size()) return fail(nullptr, MPH_ERR_INPUT, "record index out of range");
-  const OutRecord& rec = r->at(i);
+  const OutRecord& rec = const_cast<mph_result*>(r)->at(i);  // renders the record's part on first access
   const uint32_t t = rec.info.tx;
   o->id = rec.info.id.c_str();
   o->transcript = r->tx_id[t].c_str(); o->gene_id = r->gene_id[t].c_str(); o->gene_name = r->gene_name[t].c_str(); o->chrom = r->chrom[t].c_str();
@@ -1131,31 +1208,67 @@ int mph_result_write(const mph_result* r, int fd_fasta, int fd_tsv, int fd_norma
     static const char* header_normal =
         "id\ttranscript\tgene_id\tgene_name\tchrom\toffset\tframe\tfreq\tdepth\tnvar\tnsomatic\tnvariant_sites\tnsomvariant_sites\t"
         "strand\tvariant_sites\tsomatic_positions\tsomatic_aa_change\tgermline_positions\tgermline_aa_change\tpeptide_sequence\n";
-    std::string fa, tsv, nrm;
     int hw = header_written ? *header_written : 0;
     const bool normal_mode = r->mode == 1;  // 20 columns, the last one is peptide_sequence (src/normal_microphasing.rs:80-102)
-    for (const auto& part : r->parts)
-    for (const OutRecord& rec : part) {
-      const uint32_t t = rec.info.tx;
-      if (rec.has_mt) { fa += '>'; fa += rec.info.id; fa += '\n'; fa += rec.mt_str(); fa += '\n'; }
-      if (rec.has_wt) { nrm += '>'; nrm += rec.info.id; nrm += '\n'; nrm += rec.wt_str(); nrm += '\n'; }
-      if (!hw) { tsv += normal_mode ? header_normal : header; hw = 1; }
-      const std::string fields[21] = {rec.info.id, r->tx_id[t], r->gene_id[t], r->gene_name[t], r->chrom[t], std::to_string(rec.info.offset),
-                                      std::to_string(rec.info.frame), mphfmt::format_f64(rec.info.freq), std::to_string(rec.info.depth),
-                                      std::to_string(rec.info.nvar), std::to_string(rec.info.nsomatic), std::to_string(rec.info.nvariant_sites),
-                                      std::to_string(rec.info.nsomvariant_sites), r->tx_reverse[t] ? "Reverse" : "Forward",
-                                      rec.info.variant_sites, rec.info.somatic_positions, rec.info.somatic_aa_change,
-                                      rec.info.germline_positions, rec.info.germline_aa_change, rec.info.normal_sequence, rec.info.mutant_sequence};
-      for (int i = 0; i < 21; ++i) {
-        if (normal_mode && i == 19) continue;
-        if (i) tsv.push_back('\t');
-        mphfmt::csv_field(fields[i], '\t', tsv);
-      }
-      tsv.push_back('\n');
+    // text of a run of parts; the parts are independent, so several host threads render and the chunks are written in order
+    struct Chunk { std::string fa, tsv, nrm; };
+    const size_t n_parts = r->parts.size();
+    unsigned n_thr = std::max(1u, std::min<unsigned>(std::thread::hardware_concurrency(), 16u));
+    if (const char* ht = getenv("MPH_HOST_THREADS")) n_thr = unsigned(std::max(1, atoi(ht)));
+    if (r->size() < 20000) n_thr = 1;
+    n_thr = unsigned(std::min<size_t>(n_thr, std::max<size_t>(1, n_parts)));
+    std::vector<Chunk> chunks(n_thr);
+    auto render = [&](unsigned ti) {
+      Chunk& ck = chunks[ti];
+      const size_t p0 = n_parts * ti / n_thr, p1 = n_parts * (ti + 1) / n_thr;
+      char num[32];
+      auto put_u = [&](std::string& dst, uint64_t v) { auto e = std::to_chars(num, num + sizeof num, v); dst.append(num, e.ptr); };
+      for (size_t pi = p0; pi < p1; ++pi)
+        r->for_each(r->parts[pi], [&](const OutRecord& rec) {
+          const uint32_t t = rec.info.tx;
+          std::string& fa = ck.fa; std::string& tsv = ck.tsv; std::string& nrm = ck.nrm;
+          if (rec.has_mt) { fa += '>'; fa += rec.info.id; fa += '\n'; fa += rec.mt_str(); fa += '\n'; }
+          if (rec.has_wt) { nrm += '>'; nrm += rec.info.id; nrm += '\n'; nrm += rec.wt_str(); nrm += '\n'; }
+          // ids, transcript / gene names, numbers and sequences never need quoting; the free-text columns go through csv_field
+          tsv += rec.info.id; tsv += '\t';
+          mphfmt::csv_field(r->tx_id[t], '\t', tsv); tsv += '\t';
+          mphfmt::csv_field(r->gene_id[t], '\t', tsv); tsv += '\t';
+          mphfmt::csv_field(r->gene_name[t], '\t', tsv); tsv += '\t';
+          mphfmt::csv_field(r->chrom[t], '\t', tsv); tsv += '\t';
+          put_u(tsv, rec.info.offset); tsv += '\t';
+          put_u(tsv, rec.info.frame); tsv += '\t';
+          tsv += mphfmt::format_f64(rec.info.freq); tsv += '\t';
+          put_u(tsv, rec.info.depth); tsv += '\t';
+          put_u(tsv, rec.info.nvar); tsv += '\t';
+          put_u(tsv, rec.info.nsomatic); tsv += '\t';
+          put_u(tsv, rec.info.nvariant_sites); tsv += '\t';
+          put_u(tsv, rec.info.nsomvariant_sites); tsv += '\t';
+          tsv += r->tx_reverse[t] ? "Reverse" : "Forward"; tsv += '\t';
+          mphfmt::csv_field(rec.info.variant_sites, '\t', tsv); tsv += '\t';
+          mphfmt::csv_field(rec.info.somatic_positions, '\t', tsv); tsv += '\t';
+          mphfmt::csv_field(rec.info.somatic_aa_change, '\t', tsv); tsv += '\t';
+          mphfmt::csv_field(rec.info.germline_positions, '\t', tsv); tsv += '\t';
+          mphfmt::csv_field(rec.info.germline_aa_change, '\t', tsv); tsv += '\t';
+          if (!normal_mode) { mphfmt::csv_field(std::string(rec.info.normal_sequence), '\t', tsv); tsv += '\t'; }
+          mphfmt::csv_field(std::string(rec.info.mutant_sequence), '\t', tsv);
+          tsv += '\n';
+        });
+    };
+    if (n_thr == 1) {
+      render(0);
+    } else {
+      std::vector<std::thread> th;
+      for (unsigned ti = 0; ti < n_thr; ++ti) th.emplace_back(render, ti);
+      for (auto& t : th) t.join();
     }
-    if (fd_fasta >= 0) write_all(fd_fasta, fa);
-    if (fd_tsv >= 0) write_all(fd_tsv, tsv);
-    if (fd_normal >= 0) write_all(fd_normal, nrm);
+    for (Chunk& ck : chunks) {
+      if (fd_fasta >= 0) write_all(fd_fasta, ck.fa);
+      if (fd_tsv >= 0 && !ck.tsv.empty()) {
+        if (!hw) { write_all(fd_tsv, normal_mode ? header_normal : header); hw = 1; }
+        write_all(fd_tsv, ck.tsv);
+      }
+      if (fd_normal >= 0) write_all(fd_normal, ck.nrm);
+    }
     if (header_written) *header_written = hw;
   });
 }
@@ -1198,8 +1311,11 @@ static void run_somatic_files(const std::vector<mph_ctx*>& ctxs, const char* bam
       if (!gf) throw std::runtime_error(std::string("cannot open ") + gtf_path);
       gin = &gf;
     }
+    const auto t_ingest0 = std::chrono::steady_clock::now();
     ReadBuffer reads(bam);
     std::vector<GeneInput> genes = ingest_genes(*gin, reads, vcf, fasta, io);
+    const double ingest_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_ingest0).count();
+    std::atomic<uint64_t> pack_us{0}, write_us{0};
     // one contiguous gene range per device, no exchange between shards; a device's range is cut
     // further so that several host threads pack in parallel, while its phase calls run one after the other
     const size_t n_dev = ctxs.size();
@@ -1238,8 +1354,10 @@ static void run_somatic_files(const std::vector<mph_ctx*>& ctxs, const char* bam
       if (err && !first_err) first_err = err;
       while (next_out < n_shards && done[next_out]) {
         if (results[next_out]) {
+          const auto tw0 = std::chrono::steady_clock::now();
           if (!first_err && mph_result_write(results[next_out], fd_fa, fd_tsv, fd_n, &hw) != MPH_OK && !first_err)
             first_err = std::make_exception_ptr(std::runtime_error(g_last_error));
+          write_us += uint64_t(std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - tw0).count());
           delete results[next_out];
           results[next_out] = nullptr;
         }
@@ -1257,11 +1375,13 @@ static void run_somatic_files(const std::vector<mph_ctx*>& ctxs, const char* bam
             std::lock_guard<std::mutex> lk(out_mu);
             if (first_err) { done[k] = 1; continue; }
           }
+          const auto tp0 = std::chrono::steady_clock::now();
           Packer packer(window_len, mode);
           pack_genes(genes, cut[k], cut[k + 1], packer);
           std::unique_ptr<mph_batch> batch(new mph_batch);
           batch->b = std::move(packer.batch());
           finish_batch(batch.get(), false);
+          pack_us += uint64_t(std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - tp0).count());
           const size_t dv = k / shards_per_dev;
           std::lock_guard<std::mutex> lk(dev_mu[dv]);  // a context is not re-entrant
           phase_batch_impl(ctxs[dv], batch.get(), &results[k]);
@@ -1281,6 +1401,10 @@ static void run_somatic_files(const std::vector<mph_ctx*>& ctxs, const char* bam
       for (auto& t : th) t.join();
     }
     for (size_t dv = 0; dv < n_dev; ++dv) ctxs[dv]->timing = acc[dv];
+    // host stages of the file driver (the first context carries them)
+    ctxs[0]->timing.ingest_ms = ingest_ms;
+    ctxs[0]->timing.pack_ms = double(pack_us.load()) / 1000.0;
+    ctxs[0]->timing.write_ms = double(write_us.load()) / 1000.0;
     for (auto r : results) delete r;
     if (first_err) std::rethrow_exception(first_err);
   } catch (...) {

@@ -9,6 +9,20 @@
 
 namespace mph {
 
+// what rendering needs besides the record itself: the batch's variants (positions, amino-acid changes), the bytes the
+// record's seq_off points into and the second sources of merged records
+struct RenderCtx {
+  const MphVar* vars = nullptr;
+  const std::vector<std::string>* var_prot = nullptr;
+  const uint8_t* seq = nullptr;
+  const MphRecSrc* aux = nullptr;
+};
+inline RenderCtx render_ctx(const Batch& b, const PhaseRaw& raw) {
+  RenderCtx c;
+  c.vars = b.vars.data(); c.var_prot = &b.var_prot; c.seq = raw.rec_seq.data(); c.aux = raw.rec_aux.data();
+  return c;
+}
+
 namespace detail {
 
 inline void append_u64(std::string& dst, uint64_t v) {
@@ -18,7 +32,7 @@ inline void append_u64(std::string& dst, uint64_t v) {
 }
 
 // variant_sites of one source window (:757-769): 1-based positions of its distinct variant sites
-inline void append_sites(const Batch& b, uint32_t var_ref, uint32_t n_win, std::string& dst) {
+inline void append_sites(const RenderCtx& b, uint32_t var_ref, uint32_t n_win, std::string& dst) {
   bool first = true;
   for (uint32_t c = 0; c < n_win; ++c) {
     const MphVar& v = b.vars[var_ref + c];
@@ -30,7 +44,7 @@ inline void append_sites(const Batch& b, uint32_t var_ref, uint32_t n_win, std::
 }
 
 // positions / amino-acid changes of the variants a source contributes (:733-749, common.rs:399-478)
-inline void append_lists(const Batch& b, uint32_t var_ref, uint64_t profile, uint32_t n_prof, uint32_t keep, InfoRecord& o, bool& fs, bool& fsa,
+inline void append_lists(const RenderCtx& b, uint32_t var_ref, uint64_t profile, uint32_t n_prof, uint32_t keep, InfoRecord& o, bool& fs, bool& fsa,
                          bool& fg, bool& fga) {
   for (uint32_t c = 0; c < n_prof && c < 32; ++c) {
     const unsigned code = unsigned((profile >> (2 * c)) & 3);
@@ -45,14 +59,14 @@ inline void append_lists(const Batch& b, uint32_t var_ref, uint64_t profile, uin
     append_u64(pos, uint64_t(b.vars[vi].pos) + 1);
     if (!fa) aa.push_back('|');
     fa = false;
-    aa += b.var_prot[vi];
+    aa += (*b.var_prot)[vi];
   }
 }
 
 }  // namespace detail
 
 // text form of one device-built record
-inline OutRecord render_record(const Batch& b, const PhaseRaw& raw, const MphRec& r) {
+inline OutRecord render_record(const RenderCtx& b, const MphRec& r) {
   OutRecord o;
   InfoRecord& info = o.info;
   static const char* hx = "0123456789abcdef";
@@ -72,7 +86,7 @@ inline OutRecord render_record(const Batch& b, const PhaseRaw& raw, const MphRec
   detail::append_lists(b, r.var_ref, r.profile, r.n_prof, r.keep, info, fs, fsa, fg, fga);
   detail::append_sites(b, r.var_ref, r.n_win, info.variant_sites);
   if (r.flags & MPH_RC_MERGED) {
-    const MphRecSrc& x = raw.rec_aux[r.aux];
+    const MphRecSrc& x = b.aux[r.aux];
     detail::append_lists(b, x.var_ref, x.profile, x.n_prof, x.keep, info, fs, fsa, fg, fga);
     // "self|rec" with one leading and one trailing '|' removed (common.rs:497-503)
     std::string& vr = info.variant_sites;
@@ -82,7 +96,7 @@ inline OutRecord render_record(const Batch& b, const PhaseRaw& raw, const MphRec
     if (!vr.empty() && vr.back() == '|') vr.pop_back();
   }
   const uint32_t mut_n = std::max(r.neo_len, r.mt_len), nrm_n = std::max(r.norm_len, r.wt_len);
-  const char* mp = reinterpret_cast<const char*>(raw.rec_seq.data()) + r.seq_off;
+  const char* mp = reinterpret_cast<const char*>(b.seq) + r.seq_off;
   const char* np = mp + mut_n;
   (void)nrm_n;
   info.mutant_sequence.assign(mp, r.neo_len);
@@ -109,12 +123,13 @@ inline std::vector<OutRecord> ordered_records(const Batch& b, const PhaseRaw& ra
   size_t d = size_t(std::lower_bound(raw.recs.begin(), raw.recs.end(), tx_lo, by_tx) - raw.recs.begin());
   const size_t d_end = size_t(std::lower_bound(raw.recs.begin() + long(d), raw.recs.end(), tx_hi, by_tx) - raw.recs.begin());
   if (d == d_end) return std::move(host_recs);
+  const RenderCtx rc = render_ctx(b, raw);
   std::vector<OutRecord> out;
   out.reserve(host_recs.size() + (d_end - d));
   size_t h = 0;
   while (h < host_recs.size() || d < d_end) {
     const bool take_dev = h == host_recs.size() || (d < d_end && raw.recs[d].tx < host_recs[h].info.tx);
-    if (take_dev) out.push_back(render_record(b, raw, raw.recs[d++]));
+    if (take_dev) out.push_back(render_record(rc, raw.recs[d++]));
     else out.push_back(std::move(host_recs[h++]));
   }
   return out;
