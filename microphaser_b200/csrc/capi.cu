@@ -159,7 +159,7 @@ struct mph_ctx {
   DevBuf<MphRec> recs, m_recs;
   DevBuf<MphRecSrc> m_aux;
   DevBuf<uint8_t> seq_dev, rec_seq, m_seq;
-  DevBuf<uint32_t> win_seg, tx_stop, rw, rw_stopq, rw_info, rw_mbase, rw_bytes, rc_blocks;
+  DevBuf<uint32_t> win_seg, tx_stop, rw, rw_stopq, rw_info, rw_mbase, rw_bytes, rw_junc, rc_blocks;
   DevBuf<int> win_diff;
   DevBuf<uint64_t> call_S, call_B;
   DevBuf<MphWinOut> win_out, iw_out;
@@ -304,7 +304,7 @@ void prepare(mph_ctx* c, const mph_batch* mb) {
   c->counters.ensure(mphk::CTR_COUNT); c->sums.ensure(3);
   if (b.mode == 0) {
     c->win_seg.ensure(nw + 1); c->tx_stop.ensure(b.txs.size() + 1);
-    c->rw.ensure(nw + 1); c->rw_stopq.ensure(nw + 1); c->rw_info.ensure(nw + 1); c->rw_mbase.ensure(nw + 1); c->rw_bytes.ensure(nw + 1);
+    c->rw.ensure(nw + 1); c->rw_stopq.ensure(nw + 1); c->rw_info.ensure(nw + 1); c->rw_mbase.ensure(nw + 1); c->rw_bytes.ensure(nw + 1); c->rw_junc.ensure(b.segs.size() + 1);
     c->rc_blocks.ensure(nw / 256 + 4);
     if (c->recs.cap == 0) { c->recs.ensure(std::max<size_t>(nw / 16, 1 << 14)); c->rec_seq.ensure(c->recs.cap * 64); }
     if (c->m_recs.cap == 0) { c->m_recs.ensure(1 << 14); c->m_aux.ensure(c->m_recs.cap); c->m_seq.ensure(c->m_recs.cap * MPH_RC_SEQ_SLOT); }
@@ -332,7 +332,7 @@ void prepare(mph_ctx* c, const mph_batch* mb) {
   d.sum_depth = c->sums.p; d.live_depth = c->sums.p + 1; d.seg_live = c->seg_live.p;
   d.window_len = b.window_len;
   d.win_seg = c->win_seg.p; d.tx_stop = c->tx_stop.p; d.rw = c->rw.p; d.rw_stopq = c->rw_stopq.p; d.rw_info = c->rw_info.p; d.rw_mbase = c->rw_mbase.p;
-  d.rw_bytes = c->rw_bytes.p; d.rc_blocks = c->rc_blocks.p;
+  d.rw_bytes = c->rw_bytes.p; d.rw_junc = c->rw_junc.p; d.rc_blocks = c->rc_blocks.p;
   d.tx_id_bytes = c->tx_id_bytes.p; d.tx_id_off = c->tx_id_off.p;
   d.n_replay = uint32_t(b.replay.size());
   d.win_voff = nullptr; d.iw_voff = nullptr;

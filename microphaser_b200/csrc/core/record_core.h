@@ -295,6 +295,51 @@ typedef struct {
   uint64_t diff;
 } MphListEntry;
 
+// byte x of the concatenation a + b
+MPH_HD uint8_t mph_rc_cat(const uint8_t* a, uint32_t an, const uint8_t* b, uint32_t x) { return x < an ? a[x] : b[x - an]; }
+
+// The byte-level steps of the merge. One thread does them with plain loops (the emulator; a lone device thread); the
+// merge kernel runs one warp per junction with every lane executing the same control flow, and replaces these steps by
+// lane-parallel versions (kernels/record_kernels.cu: MphWarpOps) - the single-thread latency of ~50 dependent byte loads
+// per step is what made a junction's chain long.
+struct MphSerialOps {
+  struct Win {  // one candidate's mutant and wild-type window
+    uint8_t mt[MPH_RC_SEQ_SLOT / 2], wt[MPH_RC_SEQ_SLOT / 2];
+  };
+  static MPH_HD bool leader() { return true; }
+  static MPH_HD void sync() {}  // orders the leader's stores before the other lanes' loads
+  static MPH_HD uint64_t diff_mask(const uint8_t* a, const uint8_t* b, uint32_t n) {  // n <= 64
+    uint64_t m = 0;
+    for (uint32_t x = 0; x < n; ++x)
+      if (a[x] != b[x]) m |= (uint64_t)1 << x;
+    return m;
+  }
+  static MPH_HD bool window_equal(const uint8_t* ma, uint32_t man, const uint8_t* mb, uint64_t ms, const uint8_t* wa, uint32_t wan,
+                                  const uint8_t* wb, uint64_t ws, uint32_t wl) {
+    for (uint32_t x = 0; x < wl; ++x)
+      if (mph_rc_cat(ma, man, mb, (uint32_t)(ms + x)) != mph_rc_cat(wa, wan, wb, (uint32_t)(ws + x))) return false;
+    return true;
+  }
+  static MPH_HD void load(Win& w, const uint8_t* ma, uint32_t man, const uint8_t* mb, uint64_t ms, const uint8_t* wa, uint32_t wan,
+                          const uint8_t* wb, uint64_t ws, uint32_t wl) {
+    for (uint32_t x = 0; x < wl; ++x) { w.mt[x] = mph_rc_cat(ma, man, mb, (uint32_t)(ms + x)); w.wt[x] = mph_rc_cat(wa, wan, wb, (uint32_t)(ws + x)); }
+  }
+  static MPH_HD bool equals_slot(const Win& w, const uint8_t* sq, uint32_t wl) {
+    for (uint32_t x = 0; x < wl; ++x)
+      if (sq[x] != w.mt[x] || sq[wl + x] != w.wt[x]) return false;
+    return true;
+  }
+  static MPH_HD void store(const Win& w, uint8_t* sq, uint32_t wl) {
+    for (uint32_t x = 0; x < wl; ++x) { sq[x] = w.mt[x]; sq[wl + x] = w.wt[x]; }
+  }
+  static MPH_HD bool slot_less(const uint8_t* sy, const uint8_t* sx, uint32_t n) {  // sy < sx over n bytes
+    for (uint32_t t = 0; t < n; ++t)
+      if (sy[t] != sx[t]) return sy[t] < sx[t];
+    return false;
+  }
+};
+
+template <class Ops>
 MPH_HD MphListEntry mph_rc_entry(const MphRecCtx& c, const MphSegment& sg, uint32_t i, uint32_t widx, uint32_t q, uint32_t* err) {
   MphListEntry en;
   const MphWinOut wo = c.win_out[widx];
@@ -322,26 +367,13 @@ MPH_HD MphListEntry mph_rc_entry(const MphRecCtx& c, const MphSegment& sg, uint3
   if (en.s.mt == en.s.wt && en.s.mt_len == en.s.wt_len) {
     en.same = 1;
   } else if (en.aligned) {
-    for (uint32_t x = 0; x < en.s.mt_len; ++x)
-      if (en.s.mt[x] != en.s.wt[x]) en.diff |= (uint64_t)1 << x;
+    en.diff = Ops::diff_mask(en.s.mt, en.s.wt, en.s.mt_len);
     en.same = en.diff == 0;
   } else {
     en.same = 0;  // different lengths
   }
   return en;
 }
-
-// wt == mt of one list entry
-MPH_HD bool mph_rc_same(const MphHapSeqs& s) {
-  if (s.mt_len != s.wt_len) return false;
-  if (s.mt == s.wt) return true;
-  for (uint32_t x = 0; x < s.mt_len; ++x)
-    if (s.mt[x] != s.wt[x]) return false;
-  return true;
-}
-
-// byte x of the concatenation a + b
-MPH_HD uint8_t mph_rc_cat(const uint8_t* a, uint32_t an, const uint8_t* b, uint32_t x) { return x < an ? a[x] : b[x - an]; }
 
 // IDRecord::update's position filters (common.rs:399-478) over one source; returns kept somatic / germline counts
 MPH_HD void mph_rc_keep(const MphVar* vars, const MphListEntry& e, bool is_self, bool forward, uint64_t offset, uint64_t wlen, uint32_t* keep,
@@ -371,7 +403,8 @@ MPH_HD void mph_rc_keep(const MphVar* vars, const MphListEntry& e, bool is_self,
 // the previous segment sp. Two modes: count (recs == nullptr) returns an upper bound of the records (no de-duplication),
 // fill writes the de-duplicated records to recs / aux / seq (slot x owns seq[x * MPH_RC_SEQ_SLOT ..)) with their ranks
 // in output_map order and returns their number. `cap` bounds the fill.
-MPH_HD uint32_t mph_rc_merge(const MphRecCtx& c, const MphSegment& sp, const MphSegment& sj, uint32_t window_len, MphRec* recs, MphRecSrc* aux,
+template <class Ops>
+MPH_HD uint32_t mph_rc_merge_t(const MphRecCtx& c, const MphSegment& sp, const MphSegment& sj, uint32_t window_len, MphRec* recs, MphRecSrc* aux,
                              uint8_t* seq, uint32_t aux_base, uint32_t seq_base, uint32_t cap, uint32_t* err) {
   const bool fwd = (sj.flags & MPH_SF_REVERSE) == 0;
   const uint32_t w_cur = sj.win_base, i_prv = sp.n_win - 1, w_prv = sp.win_base + i_prv;
@@ -384,13 +417,13 @@ MPH_HD uint32_t mph_rc_merge(const MphRecCtx& c, const MphSegment& sp, const Mph
   // the two lists are small (haplotype 0 plus the few variant haplotypes of a window): build their entries once
   enum { LIST_CACHE = 6 };
   MphListEntry first_c[LIST_CACHE], sec_c[LIST_CACHE];
-  for (uint32_t a = 0; a < n_first && a < LIST_CACHE; ++a) first_c[a] = fwd ? mph_rc_entry(c, sj, 0, w_cur, a, err) : mph_rc_entry(c, sp, i_prv, w_prv, a, err);
-  for (uint32_t b = 0; b < n_sec && b < LIST_CACHE; ++b) sec_c[b] = fwd ? mph_rc_entry(c, sp, i_prv, w_prv, b, err) : mph_rc_entry(c, sj, 0, w_cur, b, err);
+  for (uint32_t a = 0; a < n_first && a < LIST_CACHE; ++a) first_c[a] = fwd ? mph_rc_entry<Ops>(c, sj, 0, w_cur, a, err) : mph_rc_entry<Ops>(c, sp, i_prv, w_prv, a, err);
+  for (uint32_t b = 0; b < n_sec && b < LIST_CACHE; ++b) sec_c[b] = fwd ? mph_rc_entry<Ops>(c, sp, i_prv, w_prv, b, err) : mph_rc_entry<Ops>(c, sj, 0, w_cur, b, err);
   for (uint32_t a = 0; a < n_first; ++a) {
-    const MphListEntry record = a < LIST_CACHE ? first_c[a] : (fwd ? mph_rc_entry(c, sj, 0, w_cur, a, err) : mph_rc_entry(c, sp, i_prv, w_prv, a, err));
+    const MphListEntry record = a < LIST_CACHE ? first_c[a] : (fwd ? mph_rc_entry<Ops>(c, sj, 0, w_cur, a, err) : mph_rc_entry<Ops>(c, sp, i_prv, w_prv, a, err));
     const bool rec_same = record.same != 0;
     for (uint32_t b = 0; b < n_sec; ++b) {
-      const MphListEntry prev = b < LIST_CACHE ? sec_c[b] : (fwd ? mph_rc_entry(c, sp, i_prv, w_prv, b, err) : mph_rc_entry(c, sj, 0, w_cur, b, err));
+      const MphListEntry prev = b < LIST_CACHE ? sec_c[b] : (fwd ? mph_rc_entry<Ops>(c, sp, i_prv, w_prv, b, err) : mph_rc_entry<Ops>(c, sj, 0, w_cur, b, err));
       const bool prev_same = prev.same != 0;
       if (rec_same && prev_same) continue;  // every window of mt + mt equals wt + wt: nothing is written (:1795-1810)
       const uint32_t n_mts = rec_same ? 1u : (prev_same ? 1u : 3u);
@@ -430,7 +463,7 @@ MPH_HD uint32_t mph_rc_merge(const MphRecCtx& c, const MphSegment& sp, const Mph
           if (masks && have_wt) {
             equal = ((dmask >> ms) & ((wl >= 64 ? ~(uint64_t)0 : (((uint64_t)1 << wl) - 1)))) == 0;
           } else {
-            for (uint32_t x = 0; equal && x < wl; ++x) equal = mph_rc_cat(ma, man, mb, (uint32_t)(ms + x)) == mph_rc_cat(wa, wan, wb, (uint32_t)(ws + x));
+            equal = equal && Ops::window_equal(ma, man, mb, ms, wa, wan, wb, ws, (uint32_t)wl);
           }
           if (equal || !have_wt) {  // non mutated site, or no wild type at frameshift 0 (:1795-1810)
             if (fwd) splice_offset += 3; else end_offset += 3;
@@ -441,22 +474,19 @@ MPH_HD uint32_t mph_rc_merge(const MphRecCtx& c, const MphSegment& sp, const Mph
             ++n_out;
           } else {
             // key (out_offset, mt, wt): look for the slot (:1877-1901); a repeat replaces the record and folds the old frequency in (add_freq)
-            uint8_t mtb[MPH_RC_SEQ_SLOT / 2], wtb[MPH_RC_SEQ_SLOT / 2];
-            for (uint32_t x = 0; x < wl; ++x) { mtb[x] = mph_rc_cat(ma, man, mb, (uint32_t)(ms + x)); wtb[x] = mph_rc_cat(wa, wan, wb, (uint32_t)(ws + x)); }
+            typename Ops::Win win;
+            Ops::load(win, ma, man, mb, ms, wa, wan, wb, ws, (uint32_t)wl);
             uint32_t slot = 0;
             for (; slot < n_out; ++slot) {
               if (recs[slot].rank != (uint8_t)out_offset || recs[slot].aux != (uint32_t)out_offset) continue;  // rank / aux hold the key's offset until the final pass
-              const uint8_t* sq = seq + seq_base + (size_t)slot * MPH_RC_SEQ_SLOT;
-              bool same = true;
-              for (uint32_t x = 0; same && x < wl; ++x) same = sq[x] == mtb[x] && sq[wl + x] == wtb[x];
-              if (same) break;
+              if (Ops::equals_slot(win, seq + seq_base + (size_t)slot * MPH_RC_SEQ_SLOT, (uint32_t)wl)) break;
             }
             double old_freq = 0.0;
             if (slot == n_out) {
               if (n_out >= cap) { *err |= MPH_E_REC_OVERFLOW; return n_out; }
               ++n_out;
-              uint8_t* sq = seq + seq_base + (size_t)slot * MPH_RC_SEQ_SLOT;
-              for (uint32_t x = 0; x < wl; ++x) { sq[x] = mtb[x]; sq[wl + x] = wtb[x]; }
+              Ops::store(win, seq + seq_base + (size_t)slot * MPH_RC_SEQ_SLOT, (uint32_t)wl);
+              Ops::sync();
             } else {
               old_freq = recs[slot].freq;
             }
@@ -486,11 +516,12 @@ MPH_HD uint32_t mph_rc_merge(const MphRecCtx& c, const MphSegment& sp, const Mph
             r.rank = (uint8_t)out_offset;
             r.neo_len = r.mt_len = r.norm_len = r.wt_len = (uint8_t)wl;
             r.aux = (uint32_t)out_offset;
-            recs[slot] = r;
+            if (Ops::leader()) recs[slot] = r;
             MphRecSrc x;
             x.profile = other.profile; x.var_ref = other.var_ref; x.keep = kb; x.n_prof = other.n_prof; x.n_win = other.n_win;
             for (int z = 0; z < 6; ++z) x.pad[z] = 0;
-            aux[slot] = x;
+            if (Ops::leader()) aux[slot] = x;
+            Ops::sync();
           }
           if (fwd) splice_offset += 3; else end_offset += 3;
         }
@@ -507,18 +538,22 @@ MPH_HD uint32_t mph_rc_merge(const MphRecCtx& c, const MphSegment& sp, const Mph
         const uint8_t* sy = seq + seq_base + (size_t)y * MPH_RC_SEQ_SLOT;
         bool less;  // y < x ?
         if (recs[y].aux != recs[x].aux) less = recs[y].aux < recs[x].aux;
-        else {
-          int cmp = 0;
-          for (uint32_t t = 0; cmp == 0 && t < 2 * wl; ++t) cmp = (int)sy[t] - (int)sx[t];
-          less = cmp < 0;
-        }
+        else less = Ops::slot_less(sy, sx, (uint32_t)(2 * wl));
         if (less) ++rank;
       }
-      recs[x].rank = (uint8_t)rank;
+      if (Ops::leader()) recs[x].rank = (uint8_t)rank;
     }
-    for (uint32_t x = 0; x < n_out; ++x) recs[x].aux = aux_base + x;
+    Ops::sync();
+    if (Ops::leader())
+      for (uint32_t x = 0; x < n_out; ++x) recs[x].aux = aux_base + x;
+    Ops::sync();
   }
   return n_out;
+}
+
+MPH_HD uint32_t mph_rc_merge(const MphRecCtx& c, const MphSegment& sp, const MphSegment& sj, uint32_t window_len, MphRec* recs, MphRecSrc* aux,
+                             uint8_t* seq, uint32_t aux_base, uint32_t seq_base, uint32_t cap, uint32_t* err) {
+  return mph_rc_merge_t<MphSerialOps>(c, sp, sj, window_len, recs, aux, seq, aux_base, seq_base, cap, err);
 }
 
 // record id of a merged record (common.rs:385-391: sha1 over the mutant window, the transcript id and the key's offset,

@@ -108,6 +108,7 @@ struct DeviceBatch {
   uint32_t* rw_info = nullptr;      // per listed window: own records | merged records << 12
   uint32_t* rw_mbase = nullptr;     // per listed window: first slot of its junction's records in the merge arena
   uint32_t* rw_bytes = nullptr;     // per listed window: sequence bytes its records need
+  uint32_t* rw_junc = nullptr;      // listed windows (indices into rw) whose junction merge is due (counters[CTR_NJ])
   uint32_t* rc_blocks = nullptr;    // block sums / offsets of the two compactions
   MphRec* recs = nullptr;           // ordered records (counters[CTR_NREC])
   uint32_t rec_cap = 0;
@@ -121,7 +122,7 @@ struct DeviceBatch {
   uint32_t* win_depth = nullptr;       // normal mode, per window: depth | (plain window begins / ends with a stop codon) << 31
 };
 
-enum { CTR_HIST = 0, CTR_SEQ = 1, CTR_NIW = 2, CTR_ERR = 3, CTR_OVF = 4, CTR_VLIST = 5, CTR_SEQD = 6, CTR_NRW = 7, CTR_MERGE = 8, CTR_NREC = 9, CTR_RECSEQ = 10, CTR_HISTD = 11, CTR_COUNT = 16 };
+enum { CTR_HIST = 0, CTR_SEQ = 1, CTR_NIW = 2, CTR_ERR = 3, CTR_OVF = 4, CTR_VLIST = 5, CTR_SEQD = 6, CTR_NRW = 7, CTR_MERGE = 8, CTR_NREC = 9, CTR_RECSEQ = 10, CTR_HISTD = 11, CTR_NJ = 12, CTR_COUNT = 16 };
 
 void launch_allele_call(const DeviceBatch& d, cudaStream_t st);
 void launch_window_hist(const DeviceBatch& d, cudaStream_t st);

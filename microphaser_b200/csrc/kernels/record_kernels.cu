@@ -5,7 +5,9 @@
 //
 //   k_rc_flag_count / k_rc_scan / k_rc_scatter   compact the interesting windows of device-class transcripts
 //   k_rc_stop     thread per such window: does one of its haplotypes remove the peptide? -> atomicMin per transcript
-//   k_rc_count    thread per window: records it writes itself + the junction merge (run once, into the merge arena)
+//   k_rc_count    thread per window: records it writes itself; lists the windows whose junction merge is due
+//   k_rc_merge    warp per junction: the merge with its byte-level steps split over the lanes, into the merge arena
+//   k_rc_ids      thread per merged record: its SHA-1 id
 //   k_rc_scan     exclusive scan of the per-block record counts
 //   k_rc_emit     thread per window: writes its records at their final, ordered positions
 //
@@ -121,40 +123,109 @@ __global__ void __launch_bounds__(RC_THREADS) k_rc_count(const DeviceBatch d) {
     const uint32_t si = d.win_seg[w];
     const MphSegment& sg = d.segs[si];
     const uint32_t stop = d.tx_stop[sg.tx];
-    uint32_t info = 0, mbase = 0;
+    uint32_t bytes = 0;
     if (w <= stop) {
       const MphRecCtx c = rec_ctx(d);
       const uint32_t i = w - sg.win_base;
-      uint32_t bytes = 0, err = 0;
+      uint32_t err = 0;
       n = mph_rc_window_count(c, sg, i, w, d.rw_stopq[x], &bytes, &err);
-      // junction merge (:1497-1908): the transcript is still alive after the first window of a later exon
+      if (n > 0xFFFu) { err |= MPH_E_REC_OVERFLOW; n = 0; }
+      // junction merge (:1497-1908): the transcript is still alive after the first window of a later exon; k_rc_merge does it
       const bool junction = i == 0 && !(sg.flags & MPH_SF_FIRST_EXON) && (sg.flags & MPH_SF_JOIN_HEAD) && w < stop && si > 0 && d.segs[si - 1].tx == sg.tx;
-      uint32_t nm = 0;
-      if (junction) {
-        const MphSegment& sp = d.segs[si - 1];
-        const uint32_t ub = mph_rc_merge(c, sp, sg, d.window_len, nullptr, nullptr, nullptr, 0, 0, 0, &err);
-        if (ub) {
-          mbase = atomicAdd(&d.counters[CTR_MERGE], ub);
-          if (mbase + ub <= d.m_cap) {
-            nm = mph_rc_merge(c, sp, sg, d.window_len, d.m_recs + mbase, d.m_aux + mbase, d.m_seq, mbase, mbase * MPH_RC_SEQ_SLOT, ub, &err);
-            for (uint32_t z = nm; z < ub; ++z) d.m_recs[mbase + z].flags = 0;  // slots the de-duplication left unused
-          } else {
-            err |= MPH_E_REC_OVERFLOW;
-          }
-        }
-      }
-      if (nm > 0xFFFu || n > 0xFFFu) { err |= MPH_E_REC_OVERFLOW; nm = 0; n = 0; }
-      info = n | (nm << 12);
-      d.rw_bytes[x] = bytes + nm * 2u * d.window_len;
-      n += nm;
+      if (junction) d.rw_junc[atomicAdd(&d.counters[CTR_NJ], 1u)] = x;
       raise(d, err);
     }
-    d.rw_info[x] = info;
-    d.rw_mbase[x] = mbase;
+    d.rw_info[x] = n;
+    d.rw_mbase[x] = 0;
+    d.rw_bytes[x] = bytes;
   }
-  // block sum without a barrier: a warp that has no junction to merge retires at once (rc_blocks was zeroed by the host)
+  // block sum without a barrier (rc_blocks was zeroed by the host)
   for (int o = 16; o; o >>= 1) n += __shfl_down_sync(FULL, n, o);
   if ((threadIdx.x & 31) == 0 && n) atomicAdd(&d.rc_blocks[blockIdx.x], n);
+}
+
+// lane-parallel byte steps of the merge: the 32 lanes of a warp run mph_rc_merge_t with identical arguments and identical
+// control flow; only these steps split the bytes over the lanes
+struct MphWarpOps {
+  struct Win {
+    uint8_t mt, wt;  // byte `lane` of the candidate's windows (window_len <= 32)
+  };
+  static __device__ __forceinline__ int lane() { return threadIdx.x & 31; }
+  static __device__ __forceinline__ bool leader() { return lane() == 0; }
+  static __device__ __forceinline__ void sync() { __syncwarp(); }
+  static __device__ __forceinline__ uint64_t diff_mask(const uint8_t* a, const uint8_t* b, uint32_t n) {
+    const uint32_t x = lane();
+    const unsigned lo = __ballot_sync(FULL, x < n && a[x] != b[x]);
+    const unsigned hi = __ballot_sync(FULL, x + 32 < n && a[x + 32] != b[x + 32]);
+    return (uint64_t)lo | ((uint64_t)hi << 32);
+  }
+  static __device__ __forceinline__ bool window_equal(const uint8_t* ma, uint32_t man, const uint8_t* mb, uint64_t ms, const uint8_t* wa, uint32_t wan,
+                                                      const uint8_t* wb, uint64_t ws, uint32_t wl) {
+    const uint32_t x = lane();
+    const bool ne = x < wl && mph_rc_cat(ma, man, mb, (uint32_t)(ms + x)) != mph_rc_cat(wa, wan, wb, (uint32_t)(ws + x));
+    return !__any_sync(FULL, ne);
+  }
+  static __device__ __forceinline__ void load(Win& w, const uint8_t* ma, uint32_t man, const uint8_t* mb, uint64_t ms, const uint8_t* wa, uint32_t wan,
+                                              const uint8_t* wb, uint64_t ws, uint32_t wl) {
+    const uint32_t x = lane();
+    w.mt = x < wl ? mph_rc_cat(ma, man, mb, (uint32_t)(ms + x)) : 0;
+    w.wt = x < wl ? mph_rc_cat(wa, wan, wb, (uint32_t)(ws + x)) : 0;
+  }
+  static __device__ __forceinline__ bool equals_slot(const Win& w, const uint8_t* sq, uint32_t wl) {
+    const uint32_t x = lane();
+    const bool ne = x < wl && (sq[x] != w.mt || sq[wl + x] != w.wt);
+    return !__any_sync(FULL, ne);
+  }
+  static __device__ __forceinline__ void store(const Win& w, uint8_t* sq, uint32_t wl) {
+    const uint32_t x = lane();
+    if (x < wl) { sq[x] = w.mt; sq[wl + x] = w.wt; }
+  }
+  static __device__ __forceinline__ bool slot_less(const uint8_t* sy, const uint8_t* sx, uint32_t n) {
+    for (uint32_t base = 0; base < n; base += 32) {
+      const uint32_t t = base + lane();
+      const uint8_t a = t < n ? sy[t] : 0, b = t < n ? sx[t] : 0;
+      const unsigned ne = __ballot_sync(FULL, a != b);
+      if (ne) {
+        const int first = __ffs(ne) - 1;
+        return __shfl_sync(FULL, (int)a, first) < __shfl_sync(FULL, (int)b, first);
+      }
+    }
+    return false;
+  }
+};
+
+// junction merges (:1497-1908): one warp per junction; the records go to the merge arena, k_rc_emit places them
+constexpr int RM_WARPS = 4;
+__global__ void __launch_bounds__(RM_WARPS * 32) k_rc_merge(const DeviceBatch d) {
+  const uint32_t j = blockIdx.x * RM_WARPS + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (j >= d.counters[CTR_NJ]) return;
+  const uint32_t x = d.rw_junc[j];
+  const uint32_t w = d.rw[x];
+  const uint32_t si = d.win_seg[w];
+  const MphSegment& sg = d.segs[si];
+  const MphSegment& sp = d.segs[si - 1];
+  const MphRecCtx c = rec_ctx(d);
+  uint32_t err = 0, nm = 0, mbase = 0;
+  const uint32_t ub = mph_rc_merge_t<MphWarpOps>(c, sp, sg, d.window_len, nullptr, nullptr, nullptr, 0, 0, 0, &err);
+  if (ub) {
+    if (lane == 0) mbase = atomicAdd(&d.counters[CTR_MERGE], ub);
+    mbase = __shfl_sync(FULL, mbase, 0);
+    if (mbase + ub <= d.m_cap) {
+      nm = mph_rc_merge_t<MphWarpOps>(c, sp, sg, d.window_len, d.m_recs + mbase, d.m_aux + mbase, d.m_seq, mbase, mbase * MPH_RC_SEQ_SLOT, ub, &err);
+      for (uint32_t z = nm + lane; z < ub; z += 32) d.m_recs[mbase + z].flags = 0;  // slots the de-duplication left unused
+    } else {
+      err |= MPH_E_REC_OVERFLOW;
+    }
+  }
+  if (nm > 0xFFFu) { err |= MPH_E_REC_OVERFLOW; nm = 0; }
+  if (lane == 0) {
+    d.rw_info[x] |= nm << 12;
+    d.rw_mbase[x] = mbase;
+    d.rw_bytes[x] += nm * 2u * d.window_len;
+    if (nm) atomicAdd(&d.rc_blocks[x / RC_THREADS], nm);
+    raise(d, err);
+  }
 }
 
 // record ids of the junction records: one thread per slot of the merge arena (sha1 is ~4 k instructions per record; inside
@@ -238,11 +309,12 @@ void launch_records(const DeviceBatch& d, cudaStream_t st) {
   k_rc_stop<<<nbl, RC_THREADS, 0, st>>>(d);
   cudaMemsetAsync(d.rc_blocks, 0, (size_t)nbl * sizeof(uint32_t), st);
   k_rc_count<<<nbl, RC_THREADS, 0, st>>>(d);
+  if (d.s1 > d.s0) k_rc_merge<<<(d.s1 - d.s0 + RM_WARPS - 1) / RM_WARPS, RM_WARPS * 32, 0, st>>>(d);  // at most one junction per segment
   k_rc_ids<<<(d.m_cap + 127) / 128, 128, 0, st>>>(d);
   k_rc_scan<<<1, 1024, 0, st>>>(d, nbl, CTR_NREC);
   k_rc_emit<<<nbl, RC_THREADS, 0, st>>>(d);
 }
-int record_kernel_launch_count() { return 8; }
+int record_kernel_launch_count() { return 9; }
 
 void launch_live_depth(const DeviceBatch& d, cudaStream_t st) {
   if (d.c1 > d.c0) k_live_depth2<<<(d.c1 - d.c0 + 7) / 8, 256, 0, st>>>(d);

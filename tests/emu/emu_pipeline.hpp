@@ -401,6 +401,7 @@ inline PhaseRaw phase_somatic(const Batch& b) {
         if (junction) {
           const MphSegment& sp = b.segs[si - 1];
           const uint32_t ub = mph_rc_merge(c, sp, sg, b.window_len, nullptr, nullptr, nullptr, 0, 0, 0, &err);
+          if (getenv("MPH_EMU_JSTAT")) fprintf(stderr, "J %u %u %u\n", mph_rc_nkeys(d_win_out[sg.win_base]), mph_rc_nkeys(d_win_out[sp.win_base + sp.n_win - 1]), ub);
           if (ub) {
             std::vector<MphRec> mr(ub);
             std::vector<MphRecSrc> ma(ub);
