@@ -151,7 +151,8 @@ struct mph_ctx {
   DevBuf<uint8_t> read_nv, vr_nv, read_flags, bases, ins_bytes, ref, call_flags, seq, win_flag, o_flags, o_inmat;
   DevBuf<MphReplayTx> replay;
   DevBuf<uint64_t> o_hap;
-  DevBuf<uint2> pairs, seg_list;
+  DevBuf<uint2> pairs, seg_list, rd_runs, rd_span_exc, rd_flag_exc;
+  DevBuf<uint8_t> rd_delta, rd_span;
   DevBuf<MphVar> vars;
   DevBuf<MphSegment> segs;
   DevBuf<MphChunk> chunks;
@@ -212,7 +213,7 @@ void finish_batch(mph_batch* mb, bool pin) {
   }
   std::sort(mb->pairs.begin(), mb->pairs.end(), [](const uint2& a, const uint2& c) { return a.x < c.x; });
   auto bytes = [](auto& v) { return v.size() * sizeof(v[0]); };
-  mb->h2d_bytes = bytes(b.read_start) + bytes(b.read_end) + bytes(b.read_flags) + bytes(b.vr_read) + bytes(b.vr_vlo) + bytes(b.vr_seq_off) +
+  mb->h2d_bytes = bytes(b.rd_delta) + bytes(b.rd_span) + bytes(b.rd_runs) + bytes(b.rd_span_exc) + bytes(b.rd_flag_exc) + bytes(b.vr_read) + bytes(b.vr_vlo) + bytes(b.vr_seq_off) +
                   bytes(b.vr_cig_off) + bytes(b.vr_lseq) + bytes(b.vr_ncig) + bytes(b.vr_nv) + bytes(b.bases) + bytes(b.cigars) +
                   bytes(b.vars) + bytes(b.ins_bytes) + bytes(b.segs) + bytes(b.chunks) + bytes(b.seg_work) + bytes(b.seg_work_off) + bytes(b.ref) + bytes(b.stopmap) + bytes(mb->pairs) +
                   bytes(b.tx_id_bytes) + bytes(b.tx_id_off) + bytes(b.replay) + bytes(b.replay_dq) + (b.replay.empty() ? 0 : bytes(b.seg_chunk0));
@@ -224,7 +225,7 @@ void finish_batch(mph_batch* mb, bool pin) {
       else
         cudaGetLastError();
     };
-    reg(b.read_start); reg(b.read_end); reg(b.read_flags); reg(b.vr_read); reg(b.vr_vlo); reg(b.vr_seq_off); reg(b.vr_cig_off); reg(b.vr_lseq);
+    reg(b.rd_delta); reg(b.rd_span); reg(b.rd_runs); reg(b.rd_span_exc); reg(b.rd_flag_exc); reg(b.vr_read); reg(b.vr_vlo); reg(b.vr_seq_off); reg(b.vr_cig_off); reg(b.vr_lseq);
     reg(b.vr_ncig); reg(b.vr_nv); reg(b.bases); reg(b.cigars); reg(b.vars); reg(b.ins_bytes); reg(b.segs); reg(b.chunks); reg(b.seg_work); reg(b.seg_work_off); reg(b.ref); reg(b.stopmap);
     reg(mb->pairs);
     reg(b.tx_id_bytes); reg(b.tx_id_off); reg(b.replay); reg(b.replay_dq); reg(b.seg_chunk0);
@@ -290,6 +291,8 @@ void prepare(mph_ctx* c, const mph_batch* mb) {
   const size_t nr = b.n_reads(), nw = size_t(b.n_windows);
   const size_t nvr = b.vr_read.size();
   c->read_start.ensure(nr + 1); c->read_end.ensure(nr + 1); c->read_flags.ensure(nr + 1);
+  c->rd_delta.ensure(nr + 1); c->rd_span.ensure(nr + 1); c->rd_runs.ensure(b.rd_runs.size() + 1); c->rd_span_exc.ensure(b.rd_span_exc.size() + 1);
+  c->rd_flag_exc.ensure(b.rd_flag_exc.size() + 1);
   c->read_vlo.ensure(nr + 1); c->read_nv.ensure(nr + 1); c->read_vr.ensure(nr + 1);  // expanded on the device by K1
   c->vr_read.ensure(nvr + 1); c->vr_vlo.ensure(nvr + 1); c->vr_seq_off.ensure(nvr + 1); c->vr_cig_off.ensure(nvr + 1);
   c->vr_lseq.ensure(nvr + 1); c->vr_ncig.ensure(nvr + 1); c->vr_nv.ensure(nvr + 1);
@@ -319,6 +322,8 @@ void prepare(mph_ctx* c, const mph_batch* mb) {
   d.n_reads = uint32_t(nr); d.n_vars = uint32_t(b.vars.size()); d.n_segs = uint32_t(b.segs.size()); d.n_chunks = uint32_t(b.chunks.size());
   d.n_windows = uint32_t(nw); d.seq_cap = b.seq_cap;
   d.read_start = c->read_start.p; d.read_end = c->read_end.p; d.read_flags = c->read_flags.p;
+  d.read_start_w = c->read_start.p; d.read_end_w = c->read_end.p; d.read_flags_w = c->read_flags.p;
+  d.rd_delta = c->rd_delta.p; d.rd_span = c->rd_span.p; d.rd_runs = c->rd_runs.p; d.rd_span_exc = c->rd_span_exc.p; d.rd_flag_exc = c->rd_flag_exc.p;
   d.read_vlo = c->read_vlo.p; d.read_nv = c->read_nv.p; d.read_vr = c->read_vr.p;
   d.vr_read = c->vr_read.p; d.vr_vlo = c->vr_vlo.p; d.vr_seq_off = c->vr_seq_off.p; d.vr_cig_off = c->vr_cig_off.p;
   d.vr_lseq = c->vr_lseq.p; d.vr_ncig = c->vr_ncig.p; d.vr_nv = c->vr_nv.p;
@@ -363,7 +368,9 @@ void h2d_range(cudaStream_t st, DevBuf<T>& dst, const V& src, size_t lo, size_t 
 void copy_stage(mph_ctx* c, const mph_batch* mb, const Stage& s, bool first, cudaStream_t st) {
   const Batch& b = mb->b;
   const size_t r0 = s.lo.reads, r1 = s.hi.reads;
-  h2d_range(st, c->read_start, b.read_start, r0, r1); h2d_range(st, c->read_end, b.read_end, r0, r1); h2d_range(st, c->read_flags, b.read_flags, r0, r1);
+  h2d_range(st, c->rd_delta, b.rd_delta, r0, r1); h2d_range(st, c->rd_span, b.rd_span, r0, r1);
+  h2d_range(st, c->rd_runs, b.rd_runs, s.lo.runs, s.hi.runs); h2d_range(st, c->rd_span_exc, b.rd_span_exc, s.lo.span_exc, s.hi.span_exc);
+  h2d_range(st, c->rd_flag_exc, b.rd_flag_exc, s.lo.flag_exc, s.hi.flag_exc);
   const size_t e0 = s.lo.vr, e1 = s.hi.vr;
   h2d_range(st, c->vr_read, b.vr_read, e0, e1); h2d_range(st, c->vr_vlo, b.vr_vlo, e0, e1); h2d_range(st, c->vr_seq_off, b.vr_seq_off, e0, e1);
   h2d_range(st, c->vr_cig_off, b.vr_cig_off, e0, e1); h2d_range(st, c->vr_lseq, b.vr_lseq, e0, e1); h2d_range(st, c->vr_ncig, b.vr_ncig, e0, e1);
@@ -388,6 +395,8 @@ void set_ranges(mph_ctx* c, const Stage& s) {
   d.vr0 = uint32_t(s.lo.vr); d.vr1 = uint32_t(s.hi.vr);
   d.c0 = uint32_t(s.lo.chunks); d.c1 = uint32_t(s.hi.chunks);
   d.s0 = uint32_t(s.lo.segs); d.s1 = uint32_t(s.hi.segs);
+  d.run0 = uint32_t(s.lo.runs); d.run1 = uint32_t(s.hi.runs); d.sx0 = uint32_t(s.lo.span_exc); d.sx1 = uint32_t(s.hi.span_exc);
+  d.fx0 = uint32_t(s.lo.flag_exc); d.fx1 = uint32_t(s.hi.flag_exc);
   d.it0 = c->cur->b.seg_work_off[s.lo.segs]; d.it1 = c->cur->b.seg_work_off[s.hi.segs];
   d.w0 = uint32_t(s.lo.windows); d.w1 = uint32_t(s.hi.windows);
   d.rp0 = uint32_t(s.lo.replay); d.rp1 = uint32_t(s.hi.replay);
@@ -415,6 +424,7 @@ void run_kernels(mph_ctx* c) {
     const size_t n = size_t(d.r1 - d.r0);
     // (call_S / call_B are written by K1 for the reads of the side table only; every reader checks call_flags / read_nv first)
     CU(cudaMemsetAsync(c->call_flags.p + d.r0, 0, n, c->stream));
+    CU(cudaMemsetAsync(c->read_flags.p + d.r0, 0, n, c->stream));
     CU(cudaMemsetAsync(c->read_nv.p + d.r0, 0, n, c->stream));
   }
   if (d.rp1 > d.rp0) {
@@ -430,6 +440,7 @@ void run_kernels(mph_ctx* c) {
     CU(cudaMemsetAsync(d.seg_list_n + d.s0, 0, size_t(d.s1 - d.s0) * sizeof(uint32_t), c->stream));
     CU(cudaMemsetAsync(d.seg_list2_n + d.s0, 0, size_t(d.s1 - d.s0) * sizeof(uint32_t), c->stream));
   }
+  mphk::launch_read_decode(d, c->stream);  // K0: start / end / flags of the slice's reads from their 2-byte bus form
   mphk::launch_allele_call(d, c->stream);
   CU(cudaEventRecord(c->ev[3], c->stream));
   // measured on B200: on a second stream (any priority, with or without a dispatch head start) the replay and the

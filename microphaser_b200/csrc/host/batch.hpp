@@ -79,6 +79,7 @@ struct GeneMeta {
 // sizes of every per-gene-contiguous array after a gene has been packed: a batch can be cut at any gene boundary
 struct GeneMark {
   uint64_t reads = 0, vr = 0, bases = 0, cigars = 0, vars = 0, ins = 0, segs = 0, chunks = 0, ref = 0, windows = 0, txs = 0, replay = 0, dq = 0, partners = 0;
+  uint64_t runs = 0, span_exc = 0, flag_exc = 0;
 };
 
 struct Batch {
@@ -88,6 +89,15 @@ struct Batch {
   // reads (SoA)
   std::vector<uint32_t> read_start, read_end;
   std::vector<uint8_t> read_flags;
+  // what crosses the bus instead of the three arrays above (9 B per read): starts are sorted within a gene and the
+  // reference span of a short read fits a byte, so a read ships as 2 B - the distance to the previous read's start and
+  // its span - plus a run table (a new run wherever the distance exceeds a byte, and at every gene) and two exception
+  // lists (spans >= 255, non-zero flags). K0 (k_read_decode) rebuilds read_start / read_end / read_flags on the device.
+  std::vector<uint8_t> rd_delta, rd_span;
+  struct U2 { uint32_t x, y; };
+  std::vector<U2> rd_runs;      // (first read, its start)
+  std::vector<U2> rd_span_exc;  // (read, end)
+  std::vector<U2> rd_flag_exc;  // (read, flags)
   // compact side table of the reads K1 has work for (variants inside the alignment; every read of a gene with replayed
   // transcripts): read index, first variant index, offsets of the packed bases / CIGAR, lengths, variant count
   std::vector<uint32_t> vr_read, vr_vlo, vr_seq_off, vr_cig_off;
@@ -125,6 +135,23 @@ struct Batch {
 
   uint64_t n_reads() const { return read_start.size(); }
 };
+
+// host statement of K0 (k_read_decode / k_read_patch): used by the CPU checks of the bus encoding
+inline void decode_reads(const Batch& b, std::vector<uint32_t>& start, std::vector<uint32_t>& end, std::vector<uint8_t>& flags) {
+  const size_t n = b.rd_delta.size();
+  start.assign(n, 0); end.assign(n, 0); flags.assign(n, 0);
+  for (size_t j = 0; j < b.rd_runs.size(); ++j) {
+    const size_t lo = b.rd_runs[j].x, hi = j + 1 < b.rd_runs.size() ? b.rd_runs[j + 1].x : n;
+    uint32_t pos = b.rd_runs[j].y;
+    for (size_t r = lo; r < hi; ++r) {
+      pos += b.rd_delta[r];
+      start[r] = pos;
+      end[r] = pos + b.rd_span[r];
+    }
+  }
+  for (auto& e : b.rd_span_exc) end[e.x] = e.y;
+  for (auto& e : b.rd_flag_exc) flags[e.x] = uint8_t(e.y);
+}
 
 inline uint8_t base_code(uint8_t c) {
   static const char* dec = "=ACMGRSVTWYHKDBN";
@@ -554,6 +581,17 @@ class Packer {
         ++q;
       }
     }
+    // bus encoding of this gene's reads (see Batch::rd_delta)
+    for (uint32_t r = gm.read_lo; r < gm.read_hi; ++r) {
+      uint32_t delta = 0;
+      if (r == gm.read_lo || b_.read_start[r] - b_.read_start[r - 1] > 255u) b_.rd_runs.push_back(Batch::U2{r, b_.read_start[r]});
+      else delta = b_.read_start[r] - b_.read_start[r - 1];
+      b_.rd_delta.push_back(uint8_t(delta));
+      const uint32_t span = b_.read_end[r] - b_.read_start[r];
+      b_.rd_span.push_back(uint8_t(span < 255u ? span : 255u));
+      if (span >= 255u) b_.rd_span_exc.push_back(Batch::U2{r, b_.read_end[r]});
+      if (b_.read_flags[r]) b_.rd_flag_exc.push_back(Batch::U2{r, b_.read_flags[r]});
+    }
     // work items of the read-run kernel: (segment, read) pairs; replayed transcripts take none (k_replay does their windows)
     for (size_t si = b_.seg_work_off.size() - 1; si < b_.segs.size(); ++si) {
       if (b_.segs[si].flags & MPH_SF_REPLAY) b_.seg_work[si].rhi = b_.seg_work[si].rlo;
@@ -566,6 +604,7 @@ class Packer {
     mk.reads = b_.read_start.size(); mk.vr = b_.vr_read.size(); mk.bases = b_.bases.size(); mk.cigars = b_.cigars.size(); mk.vars = b_.vars.size(); mk.ins = b_.ins_bytes.size();
     mk.segs = b_.segs.size(); mk.chunks = b_.chunks.size(); mk.ref = b_.ref.size(); mk.windows = b_.n_windows; mk.txs = b_.txs.size();
     mk.replay = b_.replay.size(); mk.dq = b_.replay_dq.size(); mk.partners = b_.partner_a.size();
+    mk.runs = b_.rd_runs.size(); mk.span_exc = b_.rd_span_exc.size(); mk.flag_exc = b_.rd_flag_exc.size();
     b_.marks.push_back(mk);
   }
 

@@ -28,6 +28,38 @@ using namespace detail;
 
 namespace {
 
+// ------------------------------------------------------------------ K0: reads off the bus
+// A read crosses the bus as 2 B (distance to the previous start, reference span); one warp per run prefix-sums the
+// distances and writes the start / end arrays every later kernel uses. Exceptions (long spans, flags) are patched in after.
+__global__ void __launch_bounds__(128) k_read_decode(const DeviceBatch d) {
+  const uint32_t j = d.run0 + blockIdx.x * 4 + (threadIdx.x >> 5);
+  const uint32_t lane = threadIdx.x & 31;
+  if (j >= d.run1) return;
+  const uint2 run = d.rd_runs[j];
+  const uint32_t hi = j + 1 < d.run1 ? d.rd_runs[j + 1].x : d.r1;
+  uint32_t pos = run.y;
+  for (uint32_t base = run.x; base < hi; base += 32) {
+    const uint32_t r = base + lane;
+    uint32_t x = r < hi ? d.rd_delta[r] : 0u;
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(FULL, x, o);
+      if (lane >= (uint32_t)o) x += y;
+    }
+    if (r < hi) {
+      d.read_start_w[r] = pos + x;
+      d.read_end_w[r] = pos + x + d.rd_span[r];
+    }
+    pos += __shfl_sync(FULL, x, 31);
+  }
+}
+
+__global__ void __launch_bounds__(256) k_read_patch(const DeviceBatch d) {
+  const uint32_t t = blockIdx.x * 256 + threadIdx.x;
+  const uint32_t ns = d.sx1 - d.sx0, nf = d.fx1 - d.fx0;
+  if (t < ns) { const uint2 e = d.rd_span_exc[d.sx0 + t]; d.read_end_w[e.x] = e.y; }
+  else if (t < ns + nf) { const uint2 e = d.rd_flag_exc[d.fx0 + t - ns]; d.read_flags_w[e.x] = (uint8_t)e.y; }
+}
+
 // ------------------------------------------------------------------ K1
 __global__ void __launch_bounds__(256) k_allele_call(const DeviceBatch d) {
   const uint32_t e = d.vr0 + blockIdx.x * blockDim.x + threadIdx.x;
@@ -640,6 +672,11 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scatter(const DeviceBatch d) {
 
 }  // namespace
 
+void launch_read_decode(const DeviceBatch& d, cudaStream_t st) {
+  if (d.run1 > d.run0) k_read_decode<<<(d.run1 - d.run0 + 3) / 4, 128, 0, st>>>(d);
+  const uint32_t n = (d.sx1 - d.sx0) + (d.fx1 - d.fx0);
+  if (n) k_read_patch<<<(n + 255) / 256, 256, 0, st>>>(d);
+}
 void launch_allele_call(const DeviceBatch& d, cudaStream_t st) {
   if (d.vr1 > d.vr0) k_allele_call<<<(d.vr1 - d.vr0 + 255) / 256, 256, 0, st>>>(d);
 }
@@ -662,6 +699,6 @@ void launch_compact(const DeviceBatch& d, cudaStream_t st) {
   k_block_scan<<<1, SCAN_THREADS, 0, st>>>(d, nb);
   if (nb) k_scatter<<<nb, SCAN_THREADS, 0, st>>>(d);
 }
-int kernel_launch_count() { return 8; }
+int kernel_launch_count() { return 10; }
 
 }  // namespace mphk

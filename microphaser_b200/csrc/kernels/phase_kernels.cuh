@@ -24,9 +24,18 @@ struct DeviceBatch {
   uint32_t rp0 = 0, rp1 = 0;  // replay units
   uint32_t mode = 0;        // 0 somatic, 1 normal (reference src/normal_microphasing.rs)
   uint32_t force_wide = 0;  // test hook (MPH_FORCE_WIDE=1): send every window with extra keys through k_window_hist_wide
-  const uint32_t* read_start = nullptr;
+  const uint32_t* read_start = nullptr;  // rebuilt on the device by K0 from the 2-byte bus encoding below
   const uint32_t* read_end = nullptr;
   const uint8_t* read_flags = nullptr;
+  uint32_t* read_start_w = nullptr;      // the same buffers, writable (K0)
+  uint32_t* read_end_w = nullptr;
+  uint8_t* read_flags_w = nullptr;
+  const uint8_t* rd_delta = nullptr;     // per read: start - previous start (0 at the head of a run)
+  const uint8_t* rd_span = nullptr;      // per read: end - start, 255 = see rd_span_exc
+  const uint2* rd_runs = nullptr;        // (first read, its start), ascending; a run ends where the next begins
+  const uint2* rd_span_exc = nullptr;    // (read, end)
+  const uint2* rd_flag_exc = nullptr;    // (read, flags)
+  uint32_t run0 = 0, run1 = 0, sx0 = 0, sx1 = 0, fx0 = 0, fx1 = 0;  // the slice's runs / exceptions
   // compact side table: the reads K1 has work for
   const uint32_t* vr_read = nullptr;
   const uint32_t* vr_vlo = nullptr;
@@ -124,6 +133,7 @@ struct DeviceBatch {
 
 enum { CTR_HIST = 0, CTR_SEQ = 1, CTR_NIW = 2, CTR_ERR = 3, CTR_OVF = 4, CTR_VLIST = 5, CTR_SEQD = 6, CTR_NRW = 7, CTR_MERGE = 8, CTR_NREC = 9, CTR_RECSEQ = 10, CTR_HISTD = 11, CTR_NJ = 12, CTR_COUNT = 16 };
 
+void launch_read_decode(const DeviceBatch& d, cudaStream_t st);
 void launch_allele_call(const DeviceBatch& d, cudaStream_t st);
 void launch_window_hist(const DeviceBatch& d, cudaStream_t st);
 void launch_replay(const DeviceBatch& d, cudaStream_t st);                // replay_kernels.cu

@@ -28,6 +28,12 @@ int main(int argc, char** argv) {
     mph::Packer packer(27, mode);
     mph::synth_into(packer, sp);
     mph::Batch& b = packer.batch();
+    {  // the 2-byte bus encoding of the reads must decode to the arrays the kernels use
+      std::vector<uint32_t> ds, de;
+      std::vector<uint8_t> df;
+      mph::decode_reads(b, ds, de, df);
+      if (ds != b.read_start || de != b.read_end || df != b.read_flags) { fprintf(stderr, "read encoding does not round-trip\n"); return 4; }
+    }
     mph::PhaseRaw raw = mphemu::phase(b);
     if (raw.err) { fprintf(stderr, "device error bits %u\n", raw.err); return 3; }
     std::vector<mph::OutRecord> recs;
