@@ -207,10 +207,7 @@ void finish_batch(mph_batch* mb, bool pin) {
   Batch& b = mb->b;
   if (b.seq_cap > 256) throw Unsupported("insertion / deletion alleles too long for the device sequence slot");
   mb->pairs.clear();
-  for (size_t i = 0; i < b.partner_a.size(); ++i) {
-    mb->pairs.push_back(make_uint2(b.partner_a[i], b.partner_b[i]));
-    mb->pairs.push_back(make_uint2(b.partner_b[i], b.partner_a[i]));
-  }
+  for (auto& e : b.pair_edges) mb->pairs.push_back(make_uint2(e.first, e.second));
   std::sort(mb->pairs.begin(), mb->pairs.end(), [](const uint2& a, const uint2& c) { return a.x < c.x; });
   auto bytes = [](auto& v) { return v.size() * sizeof(v[0]); };
   mb->h2d_bytes = bytes(b.rd_delta) + bytes(b.rd_span) + bytes(b.rd_runs) + bytes(b.rd_span_exc) + bytes(b.rd_flag_exc) + bytes(b.vr_read) + bytes(b.vr_vlo) + bytes(b.vr_seq_off) +
@@ -1289,7 +1286,9 @@ static void run_somatic_files(const std::vector<mph_ctx*>& ctxs, const char* bam
                               const char* gtf_path, const char* fasta_out_path, const char* tsv_path, const char* normal_path,
                               uint32_t window_len, int warn_only, int mode = 0) {
   // BGZF inflate of the alignment file runs on a few host threads (MPH_IO_THREADS, default min(cores, 8))
-  unsigned io_threads = std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 8u);
+  // BGZF inflate is the largest single host cost of the file driver (about 0.7 core-seconds per million 150 bp reads with zlib):
+  // every core takes blocks
+  unsigned io_threads = std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 32u);
   if (const char* e = getenv("MPH_IO_THREADS")) io_threads = unsigned(std::max(1, atoi(e)));
   mphio::BamFile bam(bam_path, io_threads);
   mphio::VcfFile vcf(variants_path);
@@ -1333,8 +1332,8 @@ static void run_somatic_files(const std::vector<mph_ctx*>& ctxs, const char* bam
     uint64_t total_reads = 0;
     for (auto& g : genes) total_reads += g.reads.size();
     size_t per_dev = 1;
-    if (total_reads > 500000 * n_dev)
-      per_dev = std::min<size_t>(4, std::max<size_t>(1, std::thread::hardware_concurrency() / n_dev));
+    if (total_reads > 200000 * n_dev)
+      per_dev = std::min<size_t>(12, std::max<size_t>(1, std::thread::hardware_concurrency() / n_dev));
     if (const char* e = getenv("MPH_PACK_THREADS")) per_dev = size_t(std::max(1, atoi(e)));
     // more shards than packing threads when the input is large: a shard's records are written and freed as soon as all
     // earlier shards are out, which bounds the memory held in records (the normal mode writes one per window)

@@ -320,8 +320,12 @@ MPH_HD void mph_replay_tx(const MphReplayCtx& c, const MphReplayTx& t) {
           // `contains` (:281-294): an observation with the same start and qname is already in the matrix
           bool dup = in_mat[r - t.read_lo] != 0;
           if (!dup && (c.read_flags[r] & MPH_RF_PARTNER)) {
-            const uint32_t q = mph_rp_partner(c, r);
-            dup = q != 0xFFFFFFFFu && q >= t.read_lo && q < t.read_hi && in_mat[q - t.read_lo] != 0;
+            // the reads sharing (start, qname) form a cycle of partner edges: two of them point at each other
+            uint32_t q = mph_rp_partner(c, r);
+            for (uint32_t hops = 0; !dup && q != 0xFFFFFFFFu && q != r && hops < 4096; ++hops) {
+              dup = q >= t.read_lo && q < t.read_hi && in_mat[q - t.read_lo] != 0;
+              q = mph_rp_partner(c, q);
+            }
           }
           if (dup) continue;
         }

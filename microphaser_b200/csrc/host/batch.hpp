@@ -103,7 +103,10 @@ struct Batch {
   std::vector<uint32_t> vr_read, vr_vlo, vr_seq_off, vr_cig_off;
   std::vector<uint16_t> vr_lseq, vr_ncig;
   std::vector<uint8_t> vr_nv;
-  std::vector<uint32_t> partner_a, partner_b;  // sorted pairs (a < b) of reads with identical (start, qname)
+  std::vector<uint32_t> partner_a, partner_b;  // sorted pairs (a < b) of reads with identical (start, qname), groups of exactly two
+  // directed edges read -> next read with the same (start, qname): both directions of every pair above, and a cycle through
+  // every larger group (those genes go through the serial replay, which walks the cycle for `contains`, :281-294)
+  std::vector<std::pair<uint32_t, uint32_t>> pair_edges;
   std::vector<uint8_t> bases;                  // 16-B aligned packed records: 4-bit bases + (qual<10) bits
   std::vector<uint32_t> cigars;
   // variants
@@ -173,6 +176,41 @@ class Packer {
   // [gene.start, gene.end + 100).
   void add_gene(const HostGene& g, const std::vector<HostRead>& reads, uint32_t max_read_len,
                 const std::vector<std::vector<HostVariant>>& sites, std::vector<uint8_t> refseq) {
+    // The order of the ALT alleles of a multi-allelic site follows the transcript's strand (print_haplotypes :373-379), and the
+    // packed variant list has one order per gene. A gene with such a site and transcripts on both strands is packed as several
+    // pseudo-genes, one per run of consecutive transcripts of the same strand (the transcripts keep their GTF order, all state
+    // of the reference's loop is per transcript :953-971); each carries its own copy of the gene's reads and variants.
+    bool multi = false;
+    for (auto& site : sites) multi = multi || site.size() > 1;
+    int strand = -1;
+    bool mixed = false;
+    for (auto& t : g.transcripts) {
+      if (t.exons.empty()) continue;
+      if (strand < 0) strand = t.reverse ? 1 : 0;
+      else if (strand != (t.reverse ? 1 : 0)) mixed = true;
+    }
+    if (!(multi && mixed)) return add_gene_one(g, reads, max_read_len, sites, std::move(refseq));
+    size_t i = 0;
+    while (i < g.transcripts.size()) {
+      HostGene part;
+      part.id = g.id; part.name = g.name; part.chrom = g.chrom; part.start = g.start; part.end = g.end;
+      int run = -1;
+      for (; i < g.transcripts.size(); ++i) {
+        const HostTranscript& t = g.transcripts[i];
+        if (!t.exons.empty()) {
+          const int st = t.reverse ? 1 : 0;
+          if (run < 0) run = st;
+          else if (run != st) break;
+        }
+        part.transcripts.push_back(t);
+      }
+      add_gene_one(part, reads, max_read_len, sites, refseq);
+    }
+  }
+
+ private:
+  void add_gene_one(const HostGene& g, const std::vector<HostRead>& reads, uint32_t max_read_len,
+                    const std::vector<std::vector<HostVariant>>& sites, std::vector<uint8_t> refseq) {
     const uint32_t wl = b_.window_len;
     if (g.end > 0x7FF00000u) throw Unsupported("gene " + g.id + ": coordinates beyond 2^31 (the kernels use signed 32-bit window arithmetic)");
     GeneMeta gm;
@@ -180,9 +218,10 @@ class Packer {
     const uint32_t gi = uint32_t(b_.genes.size());
     // strand decides the ALT order inside a multi-allelic site (print_haplotypes :373-379)
     int strand = -1;
-    bool mixed = false;
+    bool mixed = false, any_reverse = false;
     for (auto& t : g.transcripts) {
       if (t.exons.empty()) continue;
+      any_reverse = any_reverse || t.reverse;
       if (strand < 0) strand = t.reverse ? 1 : 0;
       else if (strand != (t.reverse ? 1 : 0)) mixed = true;
     }
@@ -212,7 +251,7 @@ class Packer {
       }
     }
     gm.var_hi = uint32_t(b_.vars.size());
-    if (mixed && multi) throw Unsupported("gene " + g.id + ": multi-allelic sites with transcripts on both strands");
+    if (mixed && multi) throw std::logic_error("internal: a gene with multi-allelic sites and both strands reached the packer unsplit");
     // assembled sequences can grow by insertions / deleted reference bases
     uint32_t need = wl + 8 + 2 * (max_ins + max_del);
     need = (need + 15u) & ~15u;
@@ -223,6 +262,8 @@ class Packer {
     gm.read_lo = uint32_t(b_.read_start.size());
     uint32_t vcur = gm.var_lo, max_span = 0;
     std::unordered_map<uint64_t, uint32_t> seen;  // (start, qname) -> first read index
+    std::map<uint32_t, std::vector<uint32_t>> big_groups;  // first read -> third and later reads of its group
+    const size_t partners_mark = b_.partner_a.size();
     const size_t bases_mark = b_.bases.size(), cigars_mark = b_.cigars.size(), vr_mark = b_.vr_read.size();
     auto add_vr = [&](uint32_t idx, uint32_t vlo, uint32_t nv, const HostRead& r) {
       // packed record (core/phase_core.h), 16-B aligned: 2-bit bases when the read has only A C G T, the positions with
@@ -292,24 +333,46 @@ class Packer {
       b_.read_end.push_back(r.end);
       if (r.l_seq > 0xFFFF) throw Unsupported("read longer than 65535 bases");
       if (nv > 0) add_vr(idx, vcur, nv, r);
-      if (strand == 1 && b_.mode == 0) {  // `contains` only bites on the reverse strand (keys are read starts, :328-331); normal mode has none
+      if (any_reverse && b_.mode == 0) {  // `contains` only bites on the reverse strand (keys are read starts, :328-331); normal mode has none
         const uint64_t key = r.qname_hash * 0x9E3779B97F4A7C15ull ^ (uint64_t(r.start) << 1);
         auto it = seen.find(key);
         if (it == seen.end()) {
           seen.emplace(key, idx);
         } else {
           const uint32_t first = it->second;
-          if (b_.read_flags[first] & MPH_RF_PARTNER) throw Unsupported("gene " + g.id + ": more than two reads share (start, qname)");
-          b_.read_flags[first] |= MPH_RF_PARTNER;
           flags |= MPH_RF_PARTNER;
-          b_.partner_a.push_back(first);
-          b_.partner_b.push_back(idx);
+          if (b_.read_flags[first] & MPH_RF_PARTNER) {
+            big_groups[first].push_back(idx);  // a third (or later) read of the group
+          } else {
+            b_.read_flags[first] |= MPH_RF_PARTNER;
+            b_.partner_a.push_back(first);
+            b_.partner_b.push_back(idx);
+          }
         }
       }
       b_.read_flags.push_back(flags);
       if (r.end - r.start > max_span) max_span = r.end - r.start;
     }
     gm.read_hi = uint32_t(b_.read_start.size());
+    // `contains` edges: pairs in both directions; a group of three or more becomes a cycle and sends the gene's reverse-strand
+    // transcripts through the serial replay (the closed form of `contains` knows one partner per read)
+    bool force_replay = false;
+    for (size_t pi = partners_mark; pi < b_.partner_a.size();) {
+      const uint32_t a = b_.partner_a[pi], bq = b_.partner_b[pi];
+      auto bg = big_groups.find(a);
+      if (bg == big_groups.end()) {
+        b_.pair_edges.emplace_back(a, bq);
+        b_.pair_edges.emplace_back(bq, a);
+        ++pi;
+        continue;
+      }
+      std::vector<uint32_t> members{a, bq};
+      members.insert(members.end(), bg->second.begin(), bg->second.end());
+      for (size_t m = 0; m < members.size(); ++m) b_.pair_edges.emplace_back(members[m], members[(m + 1) % members.size()]);
+      force_replay = true;
+      b_.partner_a.erase(b_.partner_a.begin() + long(pi));
+      b_.partner_b.erase(b_.partner_b.begin() + long(pi));
+    }
 
     // transcripts -> segments
     const uint32_t ref_end = g.start + uint32_t(refseq.size());
@@ -326,7 +389,7 @@ class Packer {
       uint64_t exon_rest = 0;
       uint32_t exon_count = 0;
       const size_t exon_number = t.exons.size();
-      bool tx_replay = false;
+      bool tx_replay = force_replay && t.reverse && b_.mode == 0;
       for (auto& ex : t.exons) {
         if (ex.start > ex.end) continue;  // :981
         exon_count += 1;
@@ -405,12 +468,15 @@ class Packer {
           }
         }
         // reference slice: the exon plus the overhang a deletion can reach (:560-563)
-        sg.ref_pos0 = ex.start;
-        const uint32_t slice_end = std::min<uint64_t>(uint64_t(ex.end) + margin, ref_end);
-        if (ex.start < g.start || slice_end < ex.start) throw Fatal("slice index out of range: refseq");
+        // An exon that sticks out of [gene.start, gene.end + 100) has no bytes there: the reference panics on the slice
+        // (:464-471) when - and only when - its loop gets to such a window, so the slice is clipped here and the windows
+        // outside raise MPH_HF_REFRANGE when they are reached.
+        const uint32_t slice_lo = std::min(std::max(ex.start, g.start), ref_end);
+        const uint32_t slice_end = std::max<uint64_t>(slice_lo, std::min<uint64_t>(uint64_t(ex.end) + margin, ref_end));
+        sg.ref_pos0 = slice_lo;
         sg.ref_off = uint32_t(b_.ref.size());
-        sg.ref_len = slice_end - ex.start;
-        b_.ref.insert(b_.ref.end(), refseq.begin() + (ex.start - g.start), refseq.begin() + (slice_end - g.start));
+        sg.ref_len = slice_end - slice_lo;
+        b_.ref.insert(b_.ref.end(), refseq.begin() + (slice_lo - g.start), refseq.begin() + (slice_end - g.start));
         b_.stopmap.resize(b_.ref.size() / 32 + 4, 0);
         for (uint32_t x = 0; x + 3 <= sg.ref_len; ++x) {  // case-sensitive like has_stop_codon (:42-76)
           const uint8_t* c = &b_.ref[sg.ref_off + x];
@@ -608,6 +674,7 @@ class Packer {
     b_.marks.push_back(mk);
   }
 
+ public:
   Batch& batch() { return b_; }
 
  private:

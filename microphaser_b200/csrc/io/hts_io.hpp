@@ -440,8 +440,30 @@ class LineReader {
   ~LineReader() {
     if (gz_) gzclose(gz_);
   }
+  // raw bytes (binary BCF); returns the number of bytes read
+  size_t read_bytes(void* dst, size_t n) {
+    size_t got = 0;
+    while (got < n && !pre_.empty()) { static_cast<char*>(dst)[got++] = pre_.front(); pre_.erase(pre_.begin()); }
+    while (got < n) {
+      const int r = gzread(gz_, static_cast<char*>(dst) + got, unsigned(std::min<size_t>(n - got, 1u << 30)));
+      if (r <= 0) break;
+      got += size_t(r);
+    }
+    return got;
+  }
+  // gives bytes back to the stream (the format sniffing of VcfFile)
+  void unread(const char* p, size_t n) { pre_.insert(pre_.begin(), p, p + n); }
   bool getline(std::string& line) {
     line.clear();
+    while (!pre_.empty()) {
+      const char c = pre_.front();
+      pre_.erase(pre_.begin());
+      if (c == '\n') {
+        if (!line.empty() && line.back() == '\r') line.pop_back();
+        return true;
+      }
+      line.push_back(c);
+    }
     char buf[1 << 14];
     for (;;) {
       if (!gzgets(gz_, buf, sizeof buf)) return !line.empty();
@@ -457,6 +479,7 @@ class LineReader {
 
  private:
   gzFile gz_;
+  std::string pre_;
 };
 
 inline std::vector<std::string> split(const std::string& s, char d) {
@@ -493,23 +516,34 @@ struct VcfFile {
   std::unordered_map<std::string, int> rid_of;
   bool somatic_defined = false, ann_defined = false, svlen_defined = false;
 
+  // The reference opens its variants with bcf::Reader::from_path (src/main.rs:75), which takes text VCF (plain or
+  // BGZF / gzip) and binary BCF2 alike; so does this reader: the first bytes of the (inflated) stream tell which.
   explicit VcfFile(const std::string& path) : lr_(path) {
+    char magic[5];
+    const size_t got = lr_.read_bytes(magic, 5);
+    if (got == 5 && memcmp(magic, "BCF\2", 4) == 0) {
+      if (magic[4] != 1 && magic[4] != 2) throw IoError("unsupported BCF minor version in " + path);
+      bcf_ = true;
+      uint32_t l_text = 0;
+      if (lr_.read_bytes(&l_text, 4) != 4) throw IoError("truncated BCF header in " + path);
+      std::string text(l_text, '\0');
+      if (lr_.read_bytes(&text[0], l_text) != l_text) throw IoError("truncated BCF header in " + path);
+      size_t b = 0;
+      while (b < text.size()) {
+        size_t e = text.find('\n', b);
+        if (e == std::string::npos) e = text.size();
+        std::string line = text.substr(b, e - b);
+        while (!line.empty() && (line.back() == '\0' || line.back() == '\r')) line.pop_back();
+        b = e + 1;
+        if (line.rfind("##", 0) == 0) header_line(line);
+      }
+      return;
+    }
+    lr_.unread(magic, got);
     std::string line;
     while (lr_.getline(line)) {
       if (line.rfind("##", 0) == 0) {
-        if (line.rfind("##contig=<", 0) == 0) {
-          size_t p = line.find("ID=");
-          if (p != std::string::npos) {
-            size_t e = line.find_first_of(",>", p);
-            add_contig(line.substr(p + 3, e - p - 3));
-          }
-        } else if (line.rfind("##INFO=<ID=", 0) == 0) {
-          size_t e = line.find_first_of(",>", 11);
-          std::string id = line.substr(11, e - 11);
-          if (id == "SOMATIC") somatic_defined = line.find("Type=Flag") != std::string::npos;
-          if (id == "ANN") ann_defined = true;
-          if (id == "SVLEN") svlen_defined = true;
-        }
+        header_line(line);
         continue;
       }
       if (!line.empty() && line[0] == '#') break;  // #CHROM line
@@ -527,6 +561,7 @@ struct VcfFile {
   }
 
   bool next(VcfRecord& r) {
+    if (bcf_) return next_bcf(r);
     std::string line;
     for (;;) {
       if (have_pending_) {
@@ -599,9 +634,168 @@ struct VcfFile {
     rid_of[c] = id;
     return id;
   }
+
+  // value of `key=` inside a ##XXX=<...> header line ("" if absent)
+  static std::string header_attr(const std::string& line, const char* key) {
+    const std::string k = std::string(key) + "=";
+    size_t p = line.find("<" + k);
+    if (p == std::string::npos) p = line.find("," + k);
+    if (p == std::string::npos) return std::string();
+    p += 1 + k.size();
+    const size_t e = line.find_first_of(",>", p);
+    return line.substr(p, e == std::string::npos ? std::string::npos : e - p);
+  }
+
+  // one ## line of a VCF / BCF header: contigs, the INFO tags the path reads, and BCF's two dictionaries (the contig
+  // dictionary, and the FILTER / INFO / FORMAT id dictionary with PASS at 0; an IDX= attribute overrides the position)
+  void header_line(const std::string& line) {
+    if (line.rfind("##contig=<", 0) == 0) {
+      const std::string id = header_attr(line, "ID");
+      if (id.empty()) return;
+      const int rid = add_contig(id);
+      const std::string idx = header_attr(line, "IDX");
+      const size_t at = idx.empty() ? bcf_contig_rid_.size() : size_t(std::stoul(idx));
+      if (bcf_contig_rid_.size() <= at) bcf_contig_rid_.resize(at + 1, -1);
+      bcf_contig_rid_[at] = rid;
+      return;
+    }
+    const bool is_info = line.rfind("##INFO=<", 0) == 0;
+    if (!is_info && line.rfind("##FILTER=<", 0) != 0 && line.rfind("##FORMAT=<", 0) != 0) return;
+    const std::string id = header_attr(line, "ID");
+    if (id.empty()) return;
+    if (is_info) {
+      if (id == "SOMATIC") somatic_defined = line.find("Type=Flag") != std::string::npos;
+      if (id == "ANN") ann_defined = true;
+      if (id == "SVLEN") svlen_defined = true;
+    }
+    if (bcf_dict_.empty()) bcf_dict_.push_back("PASS");
+    const std::string idx = header_attr(line, "IDX");
+    size_t at;
+    if (!idx.empty()) at = size_t(std::stoul(idx));
+    else {
+      auto it = std::find(bcf_dict_.begin(), bcf_dict_.end(), id);
+      at = it == bcf_dict_.end() ? bcf_dict_.size() : size_t(it - bcf_dict_.begin());
+    }
+    if (bcf_dict_.size() <= at) bcf_dict_.resize(at + 1);
+    bcf_dict_[at] = id;
+  }
+
+  // ---- BCF2 records (VCF specification, section 6): typed values over a little-endian byte block
+  struct Cursor {
+    const uint8_t* p;
+    const uint8_t* end;
+    void need(size_t n) const { if (size_t(end - p) < n) throw IoError("truncated BCF record"); }
+    template <class T> T get() { need(sizeof(T)); T v; memcpy(&v, p, sizeof(T)); p += sizeof(T); return v; }
+    // reads one integer of BCF type 1 / 2 / 3; *missing / *eov tell the reserved values
+    int64_t get_int(int type, bool* missing, bool* eov) {
+      *missing = *eov = false;
+      if (type == 1) { const int8_t v = get<int8_t>(); *missing = v == INT8_MIN; *eov = v == INT8_MIN + 1; return v; }
+      if (type == 2) { const int16_t v = get<int16_t>(); *missing = v == INT16_MIN; *eov = v == INT16_MIN + 1; return v; }
+      if (type == 3) { const int32_t v = get<int32_t>(); *missing = v == INT32_MIN; *eov = v == INT32_MIN + 1; return v; }
+      throw IoError("BCF: integer expected");
+    }
+    // descriptor byte (+ overflow length): type and number of elements
+    void desc(int* type, size_t* len) {
+      const uint8_t d = get<uint8_t>();
+      *type = d & 15;
+      *len = d >> 4;
+      if (*len == 15) {
+        int t; size_t l;
+        desc(&t, &l);
+        if (l != 1) throw IoError("BCF: malformed length");
+        bool m, e;
+        const int64_t v = get_int(t, &m, &e);
+        if (v < 0) throw IoError("BCF: negative length");
+        *len = size_t(v);
+      }
+    }
+    static size_t width(int type) {
+      switch (type) { case 0: return 0; case 1: return 1; case 2: return 2; case 3: return 4; case 5: return 4; case 7: return 1; }
+      throw IoError("BCF: unknown value type");
+    }
+    void skip_value() { int t; size_t l; desc(&t, &l); need(width(t) * l); p += width(t) * l; }
+    std::string get_string() {
+      int t; size_t l;
+      desc(&t, &l);
+      if (t == 0) return std::string();
+      if (t != 7) throw IoError("BCF: string expected");
+      need(l);
+      std::string s(reinterpret_cast<const char*>(p), l);
+      p += l;
+      while (!s.empty() && s.back() == '\0') s.pop_back();
+      return s;
+    }
+  };
+
+  bool next_bcf(VcfRecord& r) {
+    uint32_t lens[2];
+    const size_t got = lr_.read_bytes(lens, 8);
+    if (got == 0) return false;
+    if (got != 8) throw IoError("truncated BCF record");
+    if (lens[0] < 24 || lens[0] > (1u << 30) || lens[1] > (1u << 30)) throw IoError("corrupt BCF record");
+    buf_.resize(size_t(lens[0]) + lens[1]);
+    if (lr_.read_bytes(buf_.data(), buf_.size()) != buf_.size()) throw IoError("truncated BCF record");
+    Cursor c{buf_.data(), buf_.data() + lens[0]};
+    const int32_t chrom = c.get<int32_t>(), pos = c.get<int32_t>();
+    c.get<int32_t>();  // rlen
+    c.get<float>();    // QUAL
+    const uint32_t n_allele_info = c.get<uint32_t>();
+    c.get<uint32_t>();  // n_fmt << 24 | n_sample
+    const uint32_t n_info = n_allele_info & 0xFFFFu, n_allele = n_allele_info >> 16;
+    if (chrom < 0 || size_t(chrom) >= bcf_contig_rid_.size() || bcf_contig_rid_[size_t(chrom)] < 0) throw IoError("BCF record on an undeclared contig");
+    r.rid = bcf_contig_rid_[size_t(chrom)];
+    r.pos = pos;
+    c.get_string();  // ID
+    r.ref.clear();
+    r.alts.clear();
+    for (uint32_t a = 0; a < n_allele; ++a) {
+      std::string al = c.get_string();
+      if (a == 0) r.ref = std::move(al);
+      else r.alts.push_back(std::move(al));
+    }
+    c.skip_value();  // FILTER
+    r.somatic_flag = r.has_ann = r.has_svlen = false;
+    r.ann_first.clear();
+    r.svlen.clear();
+    for (uint32_t i = 0; i < n_info; ++i) {
+      int kt; size_t kl;
+      c.desc(&kt, &kl);
+      if (kl != 1) throw IoError("BCF: malformed INFO key");
+      bool m, e;
+      const int64_t key = c.get_int(kt, &m, &e);
+      const std::string* name = key >= 0 && size_t(key) < bcf_dict_.size() ? &bcf_dict_[size_t(key)] : nullptr;
+      if (name && *name == "SOMATIC") {
+        r.somatic_flag = true;  // a Flag is present by being listed (its value is empty or a single 1)
+        c.skip_value();
+      } else if (name && *name == "ANN") {
+        r.has_ann = true;
+        const std::string v = c.get_string();
+        const size_t comma = v.find(',');
+        r.ann_first = comma == std::string::npos ? v : v.substr(0, comma);
+      } else if (name && *name == "SVLEN") {
+        r.has_svlen = true;
+        int t; size_t l;
+        c.desc(&t, &l);
+        for (size_t x = 0; x < l; ++x) {
+          bool miss, eov;
+          const int64_t v = c.get_int(t, &miss, &eov);
+          if (eov) continue;
+          r.svlen.push_back(miss ? INT64_MIN : v);
+        }
+      } else {
+        c.skip_value();
+      }
+    }
+    return true;
+  }
+
   LineReader lr_;
   std::string pending_;
   bool have_pending_ = false;
+  bool bcf_ = false;
+  std::vector<std::string> bcf_dict_;   // FILTER / INFO / FORMAT ids by dictionary index
+  std::vector<int> bcf_contig_rid_;     // contig dictionary index -> rid
+  std::vector<uint8_t> buf_;
 };
 
 // ---------------------------------------------------------------- FASTA + .fai

@@ -227,16 +227,21 @@ __global__ void __launch_bounds__(RP_WARPS * 32) k_replay(const DeviceBatch d) {
           // `contains` (:281-294): the read itself or the read sharing its (start, qname) is in the matrix already
           bool dup = im4[j] != 0;
           if (!dup && (rf4[j] & MPH_RF_PARTNER)) {
-            const uint32_t q = mph_rp_partner(c, r);
-            if (q != NONE && q >= r_lo && q < r_hi) {
-              dup = in_mat[q] != 0;
-              if (!dup && q < r && q >= cur_lo && re[q] >= ge) {  // offered just before r in this same iteration
-                uint64_t hq = 0;
-                uint32_t fq = 0;
-                uint8_t lq = 0;
-                for (uint32_t i = 0; i < ncols; ++i) mph_rp_update(c, t, q, i, sh.dq[ncols - 1 - i], &hq, &fq, &lq, &err);
-                dup = !(lq & 1);
+            // the reads sharing (start, qname) form a cycle of partner edges (two of them point at each other). Whatever makes
+            // one of them a duplicate makes this read one as well, so only their own push test matters
+            uint32_t q = mph_rp_partner(c, r);
+            for (uint32_t hops = 0; !dup && q != NONE && q != r && hops < 4096; ++hops) {
+              if (q >= r_lo && q < r_hi) {
+                dup = in_mat[q] != 0;
+                if (!dup && q < r && q >= cur_lo && re[q] >= ge) {  // offered just before r in this same iteration
+                  uint64_t hq = 0;
+                  uint32_t fq = 0;
+                  uint8_t lq = 0;
+                  for (uint32_t i = 0; i < ncols; ++i) mph_rp_update(c, t, q, i, sh.dq[ncols - 1 - i], &hq, &fq, &lq, &err);
+                  dup = !(lq & 1);
+                }
               }
+              q = mph_rp_partner(c, q);
             }
           }
           cand = !dup;

@@ -46,11 +46,13 @@ class Params:
         self.mapq0_frac = 0.01
         self.unmapped_frac = 0.005
         self.dup_mate_frac = 0.01      # pairs sharing qname and start (reverse-strand `contains`)
+        self.dup_extra_frac = 0.0      # chance that such a group gets one more copy (repeatedly): groups of three and more
         self.lowercase_frac = 0.1      # genes placed in a soft-masked (lowercase) region
         self.first_frame = False       # sometimes give the first CDS a non-zero frame column
         self.short_exon_frac = 0.0     # share of internal exons shorter than the window
         self.start_loss_frac = 0.0     # put a variant into the start codon
         self.transcripts_per_gene = 1
+        self.antisense_frac = 0.0      # chance that an additional transcript of a gene is annotated on the opposite strand
         self.variants_in_introns = True
         for k, v in kw.items():
             if not hasattr(self, k):
@@ -188,8 +190,14 @@ def generate(outdir, p):
             gname = "G%05d" % g["id"]
             ga = 'gene_id "ENSG%08d"; gene_version "1"; gene_name "%s"; gene_source "synth"; gene_biotype "protein_coding";' % (g["id"], gname)
             gtf_lines.append("%s\tsynth\tgene\t%d\t%d\t.\t%s\t.\t%s" % (cname, g["start"] + 1, g["end"], strand, ga))
+            gene_reverse, gene_strand = g["reverse"], strand
+            g = dict(g)
             for ti in range(p.transcripts_per_gene):
                 n_tx += 1
+                # an antisense transcript reads the same exons from the other strand (its ORF is whatever the sequence gives)
+                flip = ti > 0 and rng.random() < p.antisense_frac
+                g["reverse"] = (not gene_reverse) if flip else gene_reverse
+                strand = ("+" if gene_strand == "-" else "-") if flip else gene_strand
                 ta = ga[:-1] + '; transcript_id "ENST%08d%02d"; transcript_name "%s-2%02d"; transcript_biotype "protein_coding";' % (g["id"], ti, gname, ti)
                 gtf_lines.append("%s\tsynth\ttranscript\t%d\t%d\t.\t%s\t.\t%s" % (cname, g["start"] + 1, g["end"], strand, ta))
                 ex = g["exons"][::-1] if g["reverse"] else g["exons"]
@@ -362,6 +370,8 @@ def generate(outdir, p):
                         bam_recs.append((ci, pos0, mapq, flag | 128, qn, cig2, "".join(rs[:-k]), qual[:-k]))
                     else:
                         bam_recs.append((ci, pos0, mapq, flag | 128, qn, list(cigar), "".join(rs), list(qual)))
+                    while rng.random() < p.dup_extra_frac:
+                        bam_recs.append((ci, pos0, mapq, flag | 256, qn, list(cigar), "".join(rs), list(qual)))
 
     # ---- write files
     with open(os.path.join(outdir, "ref.fa"), "w") as f, open(os.path.join(outdir, "ref.fa.fai"), "w") as fai:

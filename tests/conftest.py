@@ -141,10 +141,19 @@ def build_abi_host():
     return exe
 
 
-def run_cli(binary, case_dir, out_dir, gtf="annotation.gtf", ref=None, subcommand="somatic"):
+def make_bcf(case_dir, out_dir):
+    """The case's variants as binary BCF2 (tests/golden/bcflite.py), what `bcf::Reader::from_path` also takes."""
+    sys.path.insert(0, GOLDEN)
+    import bcflite
+    path = os.path.join(out_dir, "variants.bcf")
+    bcflite.vcf_to_bcf(os.path.join(case_dir, "variants.vcf"), path)
+    return path
+
+
+def run_cli(binary, case_dir, out_dir, gtf="annotation.gtf", ref=None, subcommand="somatic", variants=None):
     """Run `<binary> somatic ...` the way the reference's tests do (tests/lib.rs:23-35); returns CompletedProcess."""
     ref = ref or os.path.join(case_dir, "ref.fa")
-    cmd = [binary, subcommand, os.path.join(case_dir, "reads.bam"), "--ref", ref, "--variants", os.path.join(case_dir, "variants.vcf"),
+    cmd = [binary, subcommand, os.path.join(case_dir, "reads.bam"), "--ref", ref, "--variants", variants or os.path.join(case_dir, "variants.vcf"),
            "--tsv", os.path.join(out_dir, "out.tsv")]
     if subcommand == "somatic":
         cmd += ["--normal-output", os.path.join(out_dir, "out.normal.fa")]

@@ -56,7 +56,7 @@ inline void run_replay(const Batch& b, const std::vector<MphCall>& calls, const 
   std::vector<uint64_t> S(nr), B(nr);
   for (size_t r = 0; r < nr; ++r) { S[r] = calls[r].S; B[r] = calls[r].B; }
   std::vector<std::pair<uint32_t, uint32_t>> pr;
-  for (size_t i = 0; i < b.partner_a.size(); ++i) { pr.push_back({b.partner_a[i], b.partner_b[i]}); pr.push_back({b.partner_b[i], b.partner_a[i]}); }
+  for (auto& e : b.pair_edges) pr.push_back(e);
   std::sort(pr.begin(), pr.end());
   std::vector<uint32_t> pairs;
   for (auto& x : pr) { pairs.push_back(x.first); pairs.push_back(x.second); }

@@ -18,6 +18,8 @@ PROFILES = {
     "fs": dict(indel_frac=0.3, frameshift_ok=True, somatic_per_kb=4.0),
     "multi": dict(transcripts_per_gene=3, indel_frac=0.1),
     "carry": dict(intron_len=(15, 80), indel_frac=0.1, multiallelic_frac=0.05),  # introns shorter than a read: observations survive into the next exon
+    "anti": dict(transcripts_per_gene=3, antisense_frac=0.6, multiallelic_frac=0.3, indel_frac=0.15),  # multi-allelic sites in genes with transcripts on both strands
+    "dups": dict(dup_mate_frac=0.15, dup_extra_frac=0.5, lowq_frac=0.06, indel_frac=0.1),  # three and more reads sharing (start, qname): `contains` on the reverse strand
 }
 
 

@@ -6,7 +6,7 @@ import sys
 
 import pytest
 
-from conftest import GOLDEN, ROOT, materialize_reference, read_outputs, run_cli
+from conftest import GOLDEN, ROOT, make_bcf, materialize_reference, read_outputs, run_cli
 
 sys.path.insert(0, ROOT)
 from microphaser_b200 import synth  # noqa: E402
@@ -20,6 +20,18 @@ def test_emulated_path_matches_reference_golden(emu_bin, case, tmp_path):
     d = os.path.join(GOLDEN, case)
     fa = materialize_reference(d, str(tmp_path))
     res = run_cli(emu_bin, d, str(tmp_path), ref=fa)
+    assert res.returncode == 0, res.stderr.decode()
+    for name in sorted(os.listdir(os.path.join(d, "expected"))):
+        assert open(tmp_path / name, "rb").read() == open(os.path.join(d, "expected", name), "rb").read(), name
+
+
+@pytest.mark.parametrize("case", ["reverse_somatic", "splice_forward_somatic"])
+def test_binary_bcf_variants_match_reference_golden(emu_bin, case, tmp_path):
+    """The reference reads its variants with bcf::Reader::from_path (src/main.rs:75): BCF2 input must give the golden bytes too
+    (typed INFO values, multi-ALT sites, the ANN string and the SOMATIC flag all come out of the binary records)."""
+    d = os.path.join(GOLDEN, case)
+    fa = materialize_reference(d, str(tmp_path))
+    res = run_cli(emu_bin, d, str(tmp_path), ref=fa, variants=make_bcf(d, str(tmp_path)))
     assert res.returncode == 0, res.stderr.decode()
     for name in sorted(os.listdir(os.path.join(d, "expected"))):
         assert open(tmp_path / name, "rb").read() == open(os.path.join(d, "expected", name), "rb").read(), name
@@ -40,6 +52,8 @@ PROFILES = {
     "fs": dict(indel_frac=0.3, frameshift_ok=True, somatic_per_kb=4.0),
     "multi": dict(transcripts_per_gene=3, indel_frac=0.1),
     "carry": dict(intron_len=(15, 80), indel_frac=0.1, multiallelic_frac=0.05),  # introns shorter than a read: observations survive into the next exon
+    "anti": dict(transcripts_per_gene=3, antisense_frac=0.6, multiallelic_frac=0.3, indel_frac=0.15),  # multi-allelic sites in genes with transcripts on both strands
+    "dups": dict(dup_mate_frac=0.15, dup_extra_frac=0.5, lowq_frac=0.06, indel_frac=0.1),  # three and more reads sharing (start, qname): `contains` on the reverse strand
 }
 
 

@@ -6,7 +6,7 @@ import sys
 
 import pytest
 
-from conftest import GOLDEN, ROOT, materialize_reference, read_outputs, run_cli
+from conftest import GOLDEN, ROOT, make_bcf, materialize_reference, read_outputs, run_cli
 
 sys.path.insert(0, ROOT)
 from microphaser_b200 import synth  # noqa: E402
@@ -20,6 +20,16 @@ def test_cuda_cli_matches_reference_golden(product, case, tmp_path):
     d = os.path.join(GOLDEN, case)
     fa = materialize_reference(d, str(tmp_path))
     res = run_cli(product[1], d, str(tmp_path), ref=fa)
+    assert res.returncode == 0, res.stderr.decode()
+    for name in sorted(os.listdir(os.path.join(d, "expected"))):
+        assert open(tmp_path / name, "rb").read() == open(os.path.join(d, "expected", name), "rb").read(), name
+
+
+def test_cuda_cli_reads_binary_bcf(product, tmp_path):
+    """Variants as BCF2 (what the reference's README examples pass) through the CUDA CLI: same golden bytes."""
+    d = os.path.join(GOLDEN, "reverse_somatic")
+    fa = materialize_reference(d, str(tmp_path))
+    res = run_cli(product[1], d, str(tmp_path), ref=fa, variants=make_bcf(d, str(tmp_path)))
     assert res.returncode == 0, res.stderr.decode()
     for name in sorted(os.listdir(os.path.join(d, "expected"))):
         assert open(tmp_path / name, "rb").read() == open(os.path.join(d, "expected", name), "rb").read(), name
