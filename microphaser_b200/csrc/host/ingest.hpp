@@ -145,8 +145,11 @@ class ReadBuffer {
   const uint8_t* qual(const Rec& r) const { return qual_.data() + r.qual_off; }
   const uint32_t* cigar(const Rec& r) const { return cig_.data() + r.cig_off; }
 
-  // bam::RecordBuffer::fetch (rust-htslib 0.36) over the in-memory records: the window of records with
-  // start <= pos < end, kept across calls for overlapping / adjacent queries
+  // bam::RecordBuffer::fetch (rust-htslib 0.36) over the in-memory records: the mapped records with pos < end, kept
+  // across calls for overlapping / adjacent queries. An indexed re-fetch yields every record that overlaps `start`
+  // (htslib's iterator: pos < region end and end_pos > region start) and the buffer's loop has no start test of its own,
+  // so reads that begin left of the gene and reach into it are buffered; without a re-fetch the records left of `start`
+  // are dropped from the front.
   const std::deque<const Rec*>& fetch(const std::string& chrom, uint64_t start, uint64_t end) {
     if (overflow_) { inner_.push_back(overflow_); overflow_ = nullptr; }
     auto it = bam_.tid_of.find(chrom);
@@ -169,7 +172,7 @@ class ReadBuffer {
       if (r->is_unmapped()) continue;
       const uint64_t pos = uint64_t(r->pos);
       if (pos >= end) { overflow_ = r; break; }
-      if (pos >= start) inner_.push_back(r);
+      if (pos >= start || (refetch && uint64_t(r->end) > start)) inner_.push_back(r);
     }
     return inner_;
   }

@@ -322,9 +322,13 @@ struct IDRecord {
 // ------------------------------------------------------------------ I/O buffers
 using ReadPtr = std::shared_ptr<const mphio::BamRecord>;
 
-// bam::RecordBuffer::new(reader, false) + fetch(chrom, start, end): keeps mapped records with
-// start <= pos < end of `chrom` in file order; one look-ahead "overflow" record is carried into
-// the next fetch; records right of `end` left over from an earlier, wider fetch stay buffered.
+// bam::RecordBuffer::new(reader, false) + fetch(chrom, start, end): keeps the mapped records of `chrom` with
+// pos < end in file order; one look-ahead "overflow" record is carried into the next fetch; records right of `end`
+// left over from an earlier, wider fetch stay buffered. After an indexed re-fetch the reader yields every record that
+// OVERLAPS `start` (htslib's iterator returns records with pos < region end and end_pos > region start), and the
+// buffer's loop has no start test of its own - only bcf::buffer has one, its reader being un-indexed - so reads that
+// begin left of the gene and reach into it are in the buffer; without a re-fetch, records left of `start` are dropped
+// from the front.
 struct BamRecordBuffer {
   std::vector<std::vector<ReadPtr>> by_tid;  // mapped+unmapped records in file order, per tid
   const mphio::BamFile* bam = nullptr;
@@ -348,8 +352,10 @@ struct BamRecordBuffer {
     if (it == bam->tid_of.end()) throw Failure("sequence " + chrom + " not found in BAM header");
     int tid = it->second;
     const auto& v = by_tid[tid];
+    bool refetched = false;
     if (inner.empty() || uint64_t(inner.back()->pos) < start || inner.front()->tid != tid || uint64_t(inner.front()->pos) > start) {
       // indexed re-fetch: position the reader at the first record that can overlap `start`
+      refetched = true;
       inner.clear();
       cur_tid = tid;
       cursor = 0;
@@ -364,7 +370,7 @@ struct BamRecordBuffer {
       if (r->is_unmapped()) continue;
       uint64_t pos = uint64_t(r->pos);
       if (pos >= end) { overflow = r; break; }
-      if (pos >= start) inner.push_back(r);
+      if (pos >= start || (refetched && uint64_t(r->end_pos()) > start)) inner.push_back(r);
     }
   }
 };
