@@ -4,6 +4,7 @@
 // rust-htslib's bam::RecordBuffer / bcf::buffer::RecordBuffer fetch semantics are restated from the
 // crate's published behaviour; the crate is not vendored under /root/reference.
 #pragma once
+#include <chrono>
 #include <deque>
 #include <istream>
 #include <memory>
@@ -35,109 +36,212 @@ class ReadBuffer {
   };
 
   explicit ReadBuffer(mphio::BamFile& bam) : bam_(bam) {
-    by_tid_.resize(bam.ref_names.size());
+    tid_range_.assign(bam.ref_names.size(), {0, 0});
     // the arenas hold most of the uncompressed file (BAM compresses about 3-4x): one reservation instead of repeated
-    // growth, which would copy and page-fault several hundred MB (untouched reserved pages cost nothing)
+    // growth, which would copy several hundred MB (untouched reserved pages cost nothing)
     if (bam.file_bytes()) {
       const size_t est = bam.file_bytes() * 4;
       qual_.reserve(est * 6 / 10);
       seq_.reserve(est * 3 / 10);
       cig_.reserve(est / 40);
+      recs_.reserve(est / 300);
     }
-    if (bam.inflate_threads() > 1) { load_parallel(bam.inflate_threads()); return; }
-    mphio::BamRecord r;
-    while (bam.next(r)) {
-      if (r.tid < 0 || size_t(r.tid) >= by_tid_.size()) continue;
-      Rec x;
-      x.tid = r.tid; x.pos = int32_t(r.pos); x.end = uint32_t(r.end_pos()); x.l_seq = r.l_seq; x.n_cigar = uint32_t(r.cigar.size());
-      x.flag = r.flag; x.mapq = r.mapq; x.qname_hash = fnv1a_bytes(r.qname.data(), r.qname.size());
-      x.seq_off = seq_.size(); x.qual_off = qual_.size(); x.cig_off = cig_.size();
-      seq_.insert(seq_.end(), r.seq4.begin(), r.seq4.end());
-      qual_.insert(qual_.end(), r.qual.begin(), r.qual.end());
-      cig_.insert(cig_.end(), r.cigar.begin(), r.cigar.end());
-      by_tid_[r.tid].push_back(x);
+    if (bam.inflate_threads() > 1) {
+      load_parallel(bam.inflate_threads());
+    } else {
+      mphio::BamRecord r;
+      while (bam.next(r)) {
+        if (r.tid < 0 || size_t(r.tid) >= tid_range_.size()) continue;
+        Rec x;
+        x.tid = r.tid; x.pos = int32_t(r.pos); x.end = uint32_t(r.end_pos()); x.l_seq = r.l_seq; x.n_cigar = uint32_t(r.cigar.size());
+        x.flag = r.flag; x.mapq = r.mapq; x.qname_hash = fnv1a_bytes(r.qname.data(), r.qname.size());
+        x.seq_off = seq_.size(); x.qual_off = qual_.size(); x.cig_off = cig_.size();
+        seq_.append(r.seq4.data(), r.seq4.size());
+        qual_.append(r.qual.data(), r.qual.size());
+        cig_.append(r.cigar.data(), r.cigar.size());
+        recs_.append(&x, 1);
+      }
     }
+    index_by_tid();
   }
 
  private:
-  // One inflated batch at a time: a serial scan of the length prefixes finds the record boundaries and the arena
-  // offsets of every record; the arenas grow once per batch and a few threads decode the records straight into them.
-  void load_parallel(unsigned threads) {
-    std::vector<uint8_t> buf, chunk;
-    std::vector<size_t> offs, seq_at, qual_at, cig_at;
-    std::vector<Rec> recs;
-    bool more = true;
-    while (more) {
-      more = bam_.next_chunk(chunk);
-      if (more) {
-        if (buf.empty()) buf.swap(chunk);
-        else buf.insert(buf.end(), chunk.begin(), chunk.end());
+  // a growable array whose new elements are NOT value-initialised: the loader overwrites every byte it adds, and
+  // zero-filling half a gigabyte first was a fifth of the load time
+  template <class T>
+  struct Arena {
+    T* p = nullptr;
+    size_t n = 0, cap = 0;
+    Arena() = default;
+    Arena(const Arena&) = delete;
+    Arena& operator=(const Arena&) = delete;
+    ~Arena() { free(p); }
+    void reserve(size_t want) {
+      if (want <= cap) return;
+      T* q = static_cast<T*>(realloc(p, want * sizeof(T)));
+      if (!q) throw std::bad_alloc();
+      p = q;
+      cap = want;
+    }
+    void grow_to(size_t size) {
+      if (size > cap) reserve(std::max(size, cap + cap / 2 + 4096));
+      n = size;
+    }
+    void append(const T* src, size_t k) {
+      const size_t at = n;
+      grow_to(n + k);
+      if (k) memcpy(p + at, src, k * sizeof(T));
+    }
+    size_t size() const { return n; }
+    T* data() { return p; }
+    const T* data() const { return p; }
+    T& operator[](size_t i) { return p[i]; }
+    const T& operator[](size_t i) const { return p[i]; }
+  };
+
+  // per contig: its records' range in recs_ (a coordinate-sorted BAM keeps each contig together; otherwise the records
+  // are brought into contig order first, keeping the file order within a contig)
+  void index_by_tid() {
+    bool grouped = true;
+    std::vector<uint8_t> seen(tid_range_.size(), 0);
+    for (size_t i = 0; i < recs_.size() && grouped; ++i)
+      if (i == 0 || recs_[i].tid != recs_[i - 1].tid) {
+        if (seen[size_t(recs_[i].tid)]) grouped = false;
+        seen[size_t(recs_[i].tid)] = 1;
       }
-      offs.clear(); seq_at.clear(); qual_at.clear(); cig_at.clear();
-      size_t o = 0, n_seq = seq_.size(), n_qual = qual_.size(), n_cig = cig_.size();
-      while (o + 4 <= buf.size()) {
+    if (!grouped) std::stable_sort(recs_.data(), recs_.data() + recs_.size(), [](const Rec& a, const Rec& b) { return a.tid < b.tid; });
+    for (size_t i = 0; i < recs_.size();) {
+      size_t j = i;
+      while (j < recs_.size() && recs_[j].tid == recs_[i].tid) ++j;
+      tid_range_[size_t(recs_[i].tid)] = {i, j};
+      i = j;
+    }
+  }
+
+  // decodes one framed record (p = first byte after the length prefix) into the arenas at the given offsets
+  void decode_record(const uint8_t* p, size_t seq_at, size_t qual_at, size_t cig_at, Rec& x) {
+    auto i32 = [&](size_t q) { int32_t v; memcpy(&v, p + q, 4); return v; };
+    auto u16 = [&](size_t q) { uint16_t v; memcpy(&v, p + q, 2); return v; };
+    x.tid = i32(0);
+    x.pos = i32(4);
+    const uint8_t l_read_name = p[8];
+    x.mapq = p[9];
+    x.n_cigar = u16(12);
+    x.flag = u16(14);
+    x.l_seq = uint32_t(i32(16));
+    size_t q = 32;
+    x.qname_hash = fnv1a_bytes(reinterpret_cast<const char*>(p + q), l_read_name ? l_read_name - 1 : 0);
+    q += l_read_name;
+    x.cig_off = cig_at;
+    if (x.n_cigar) memcpy(cig_.data() + x.cig_off, p + q, 4 * size_t(x.n_cigar));
+    int64_t e = x.pos;  // CigarStringView::end_pos(): reference-consuming operations M, D, N, =, X
+    for (uint32_t z = 0; z < x.n_cigar; ++z) {
+      const uint32_t c = cig_[x.cig_off + z], op = c & 15;
+      if (op == mphio::C_M || op == mphio::C_D || op == mphio::C_N || op == mphio::C_EQ || op == mphio::C_X) e += c >> 4;
+    }
+    x.end = uint32_t(e);
+    q += 4 * size_t(x.n_cigar);
+    const size_t sb = (x.l_seq + 1) / 2;
+    x.seq_off = seq_at;
+    memcpy(seq_.data() + x.seq_off, p + q, sb);
+    q += sb;
+    x.qual_off = qual_at;
+    memcpy(qual_.data() + x.qual_off, p + q, x.l_seq);
+  }
+
+  // One inflated batch at a time: a serial scan of the length prefixes finds the record boundaries and the arena
+  // offsets of every record (in place: the batch is not copied; the record that straddles two batches is put together
+  // in a small side buffer); the arenas grow once per batch and a few threads decode the records straight into them.
+  void load_parallel(unsigned threads) {
+    mphio::RawBytes chunk;
+    std::vector<uint8_t> carry;  // the head of a record whose tail is in the next batch
+    struct Item { const uint8_t* p; size_t seq_at, qual_at, cig_at; };
+    std::vector<Item> items;
+    std::vector<uint8_t> straddler;
+    bool more = true;
+    const bool trace = getenv("MPH_IO_TRACE") != nullptr;  // measurement hook: where the loader's wall time goes
+    double t_wait = 0, t_scan = 0, t_grow = 0, t_decode = 0;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto since = [](std::chrono::steady_clock::time_point a) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - a).count(); };
+    // frames one record at p (bs = its length prefix) and reserves its arena space
+    size_t n_seq = 0, n_qual = 0, n_cig = 0;
+    auto frame = [&](const uint8_t* p, int32_t bs) {
+      uint16_t n_cigar;
+      int32_t l_seq;
+      memcpy(&n_cigar, p + 12, 2);
+      memcpy(&l_seq, p + 16, 4);
+      if (l_seq < 0 || 32 + size_t(p[8]) + 4 * size_t(n_cigar) + (size_t(l_seq) + 1) / 2 + size_t(l_seq) > size_t(bs)) throw mphio::IoError("corrupt BAM record");
+      items.push_back(Item{p, n_seq, n_qual, n_cig});
+      n_seq += (size_t(l_seq) + 1) / 2; n_qual += size_t(l_seq); n_cig += n_cigar;
+    };
+    while (more) {
+      auto t0 = now();
+      more = bam_.next_chunk(chunk);
+      t_wait += since(t0);
+      t0 = now();
+      items.clear();
+      n_seq = seq_.size(); n_qual = qual_.size(); n_cig = cig_.size();
+      size_t o = 0;
+      if (!more) chunk.clear();
+      if (!carry.empty()) {
+        // finish the record that started in the previous batch
+        size_t need = 4;
+        if (carry.size() < 4) {
+          const size_t take = std::min(4 - carry.size(), chunk.size());
+          carry.insert(carry.end(), chunk.begin(), chunk.begin() + long(take));
+          o += take;
+        }
+        if (carry.size() >= 4) {
+          int32_t bs;
+          memcpy(&bs, carry.data(), 4);
+          if (bs < 32) throw mphio::IoError("corrupt BAM record");
+          need = 4 + size_t(bs);
+          const size_t take = std::min(need - carry.size(), chunk.size() - o);
+          carry.insert(carry.end(), chunk.begin() + long(o), chunk.begin() + long(o + take));
+          o += take;
+          if (carry.size() == need) {
+            straddler.swap(carry);
+            carry.clear();
+            frame(straddler.data() + 4, bs);
+          }
+        }
+        if (!more && !carry.empty()) throw mphio::IoError("truncated BAM record");
+      }
+      while (o + 4 <= chunk.size()) {
         int32_t bs;
-        memcpy(&bs, buf.data() + o, 4);
+        memcpy(&bs, chunk.data() + o, 4);
         if (bs < 32) throw mphio::IoError("corrupt BAM record");
-        if (o + 4 + size_t(bs) > buf.size()) break;
-        uint16_t n_cigar;
-        int32_t l_seq;
-        memcpy(&n_cigar, buf.data() + o + 4 + 12, 2);
-        memcpy(&l_seq, buf.data() + o + 4 + 16, 4);
-        if (l_seq < 0 || 32 + size_t(buf[o + 4 + 8]) + 4 * size_t(n_cigar) + (size_t(l_seq) + 1) / 2 + size_t(l_seq) > size_t(bs))
-          throw mphio::IoError("corrupt BAM record");
-        offs.push_back(o); seq_at.push_back(n_seq); qual_at.push_back(n_qual); cig_at.push_back(n_cig);
-        n_seq += (size_t(l_seq) + 1) / 2; n_qual += size_t(l_seq); n_cig += n_cigar;
+        if (o + 4 + size_t(bs) > chunk.size()) break;
+        frame(chunk.data() + o + 4, bs);
         o += 4 + size_t(bs);
       }
-      if (!more && o != buf.size()) throw mphio::IoError("truncated BAM record");
-      seq_.resize(n_seq); qual_.resize(n_qual); cig_.resize(n_cig);
-      recs.resize(offs.size());
-      const unsigned nt = offs.size() < 4096 ? 1u : threads;
+      if (o < chunk.size()) carry.assign(chunk.begin() + long(o), chunk.end());
+      t_scan += since(t0);
+      t0 = now();
+      seq_.grow_to(n_seq); qual_.grow_to(n_qual); cig_.grow_to(n_cig);
+      const size_t r0 = recs_.size();
+      recs_.grow_to(r0 + items.size());
+      t_grow += since(t0);
+      t0 = now();
+      const unsigned nt = items.size() < 4096 ? 1u : threads;
       auto work = [&](unsigned ti) {
-        const size_t i0 = offs.size() * ti / nt, i1 = offs.size() * (ti + 1) / nt;
-        for (size_t i = i0; i < i1; ++i) {
-          const uint8_t* p = buf.data() + offs[i] + 4;
-          auto i32 = [&](size_t q) { int32_t v; memcpy(&v, p + q, 4); return v; };
-          auto u16 = [&](size_t q) { uint16_t v; memcpy(&v, p + q, 2); return v; };
-          Rec x;
-          x.tid = i32(0);
-          x.pos = i32(4);
-          const uint8_t l_read_name = p[8];
-          x.mapq = p[9];
-          x.n_cigar = u16(12);
-          x.flag = u16(14);
-          x.l_seq = uint32_t(i32(16));
-          size_t q = 32;
-          x.qname_hash = fnv1a_bytes(reinterpret_cast<const char*>(p + q), l_read_name ? l_read_name - 1 : 0);
-          q += l_read_name;
-          x.cig_off = cig_at[i];
-          if (x.n_cigar) memcpy(cig_.data() + x.cig_off, p + q, 4 * size_t(x.n_cigar));
-          int64_t e = x.pos;  // CigarStringView::end_pos(): reference-consuming operations M, D, N, =, X
-          for (uint32_t z = 0; z < x.n_cigar; ++z) {
-            const uint32_t c = cig_[x.cig_off + z], op = c & 15;
-            if (op == mphio::C_M || op == mphio::C_D || op == mphio::C_N || op == mphio::C_EQ || op == mphio::C_X) e += c >> 4;
-          }
-          x.end = uint32_t(e);
-          q += 4 * size_t(x.n_cigar);
-          const size_t sb = (x.l_seq + 1) / 2;
-          x.seq_off = seq_at[i];
-          memcpy(seq_.data() + x.seq_off, p + q, sb);
-          q += sb;
-          x.qual_off = qual_at[i];
-          memcpy(qual_.data() + x.qual_off, p + q, x.l_seq);
-          recs[i] = x;
-        }
+        const size_t i0 = items.size() * ti / nt, i1 = items.size() * (ti + 1) / nt;
+        for (size_t i = i0; i < i1; ++i) decode_record(items[i].p, items[i].seq_at, items[i].qual_at, items[i].cig_at, recs_[r0 + i]);
       };
       std::vector<std::thread> pool;
       for (unsigned ti = 1; ti < nt; ++ti) pool.emplace_back(work, ti);
       work(0);
       for (auto& t : pool) t.join();
-      for (const Rec& x : recs)
-        if (x.tid >= 0 && size_t(x.tid) < by_tid_.size()) by_tid_[x.tid].push_back(x);
-      if (o == buf.size()) buf.clear();
-      else buf.erase(buf.begin(), buf.begin() + long(o));
+      t_decode += since(t0);
     }
+    // records of contigs the header does not know are dropped (compaction in place keeps the file order)
+    size_t keep = 0;
+    for (size_t i = 0; i < recs_.size(); ++i)
+      if (recs_[i].tid >= 0 && size_t(recs_[i].tid) < tid_range_.size()) recs_[keep++] = recs_[i];
+    recs_.grow_to(keep);
+    if (trace)
+      fprintf(stderr, "[mph io] BAM load: waiting for inflated batches %.1f ms, record framing %.1f, arena growth %.1f, record decode %.1f\n",
+              t_wait, t_scan, t_grow, t_decode);
   }
 
  public:
@@ -155,7 +259,13 @@ class ReadBuffer {
     auto it = bam_.tid_of.find(chrom);
     if (it == bam_.tid_of.end()) throw std::runtime_error("sequence " + chrom + " not found in BAM header");
     const int tid = it->second;
-    const auto& v = by_tid_[tid];
+    struct View {
+      const Rec* p;
+      size_t n;
+      size_t size() const { return n; }
+      const Rec& operator[](size_t i) const { return p[i]; }
+    };
+    const View v{recs_.data() + tid_range_[size_t(tid)].first, tid_range_[size_t(tid)].second - tid_range_[size_t(tid)].first};
     const bool refetch = inner_.empty() || uint64_t(inner_.back()->pos) < start || inner_.front()->tid != tid ||
                          uint64_t(inner_.front()->pos) > start;
     if (refetch) {
@@ -184,9 +294,10 @@ class ReadBuffer {
     return h;
   }
   mphio::BamFile& bam_;
-  std::vector<std::vector<Rec>> by_tid_;
-  std::vector<uint8_t> seq_, qual_;
-  std::vector<uint32_t> cig_;
+  Arena<Rec> recs_;                                     // every mapped-to-a-known-contig record, contig by contig, file order
+  std::vector<std::pair<size_t, size_t>> tid_range_;    // per contig: [first, last) in recs_
+  Arena<uint8_t> seq_, qual_;
+  Arena<uint32_t> cig_;
   std::deque<const Rec*> inner_;
   const Rec* overflow_ = nullptr;
   int tid_ = -1;

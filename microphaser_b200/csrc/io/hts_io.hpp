@@ -51,6 +51,18 @@ inline std::vector<uint8_t> read_file(const std::string& path) {
   return buf;
 }
 
+// a byte vector whose resize() does not zero the new bytes: inflated batches are overwritten completely, and clearing
+// 16 MB per batch first cost more than framing its records
+template <class T>
+struct DefaultInitAllocator : std::allocator<T> {
+  template <class U> struct rebind { using other = DefaultInitAllocator<U>; };
+  using std::allocator<T>::allocator;
+  template <class U> void construct(U* p) noexcept(std::is_nothrow_default_constructible<U>::value) { ::new (static_cast<void*>(p)) U; }
+  template <class U, class... Args> void construct(U* p, Args&&... args) { ::new (static_cast<void*>(p)) U(std::forward<Args>(args)...); }
+};
+using RawBytes = std::vector<uint8_t, DefaultInitAllocator<uint8_t>>;
+
+
 // ---------------------------------------------------------------- BGZF
 // Streaming BGZF block reader: each block is an independent gzip member with a BC extra
 // subfield holding the block size. inflate is done with raw deflate (windowBits -15).
@@ -86,7 +98,7 @@ class BgzfReader {
   unsigned threads() const { return threads_; }
   size_t file_bytes() const { return file_bytes_; }  // compressed size (0 if unknown), a hint for buffer reservations
   // hands over everything that is inflated and unread (the rest of the current block / the next batch); false at EOF
-  bool next_chunk(std::vector<uint8_t>& out) {
+  bool next_chunk(RawBytes& out) {
     if (pos_ == block_.size() && !(threads_ > 1 ? next_batch() : next_block())) return false;
     if (pos_ == 0) {
       out.swap(block_);
@@ -178,7 +190,7 @@ class BgzfReader {
 
   // ---- threaded path: producer fills `ready_` (at most two batches ahead), consumer swaps them into block_
   struct Batch {
-    std::vector<uint8_t> data;
+    RawBytes data;
     bool eof = false;
     std::exception_ptr err;
   };
@@ -255,7 +267,8 @@ class BgzfReader {
 
   std::string path_;
   FILE* f_ = nullptr;
-  std::vector<uint8_t> cbuf_, block_;
+  std::vector<uint8_t> cbuf_;
+  RawBytes block_;
   size_t pos_ = 0;
   unsigned threads_ = 1;
   size_t file_bytes_ = 0;
@@ -391,7 +404,7 @@ struct BamFile {
   size_t file_bytes() const { return rd_.file_bytes(); }
   // raw record stream after the header, in chunks (a record may straddle two chunks): for callers that frame and
   // parse the records themselves, in parallel
-  bool next_chunk(std::vector<uint8_t>& out) { return rd_.next_chunk(out); }
+  bool next_chunk(RawBytes& out) { return rd_.next_chunk(out); }
 
   // next alignment record; false on EOF
   bool next(BamRecord& r) {
