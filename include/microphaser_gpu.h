@@ -154,6 +154,8 @@ typedef struct {
   double pack_ms;          /* file drivers only: host time spent in the packer (wall clock, summed over the packing threads) */
   double ingest_ms;        /* file drivers only: BGZF inflate + BAM decode, GTF / VCF / FASTA parsing and the per-gene fetches (wall clock) */
   double write_ms;         /* file drivers only: rendering and writing the three output streams (wall clock, summed over the shards) */
+  double kernels_ms;       /* CUDA events around the whole kernel chain of a run (first launch to last), summed over the stages; k_replay
+                            * runs on a second stream beside K2, so this is less than the sum of the per-kernel figures */
 } mph_timing;
 int mph_ctx_timing(const mph_ctx* ctx, mph_timing* out);
 

@@ -23,7 +23,7 @@ class MphError(RuntimeError):
 class Timing(C.Structure):
     _fields_ = [(n, C.c_double) for n in ("h2d_ms", "k1_ms", "k2_ms", "k3_ms", "k4_ms", "d2h_ms", "residue_ms", "total_ms")] + \
                [(n, C.c_uint64) for n in ("h2d_bytes", "d2h_bytes", "windows", "read_windows", "windows_enumerated", "n_interesting", "n_records")] + \
-               [("kernel_launches", C.c_uint32), ("n_replay_units", C.c_uint32), ("replay_ms", C.c_double), ("k5_ms", C.c_double), ("pack_ms", C.c_double), ("ingest_ms", C.c_double), ("write_ms", C.c_double)]
+               [("kernel_launches", C.c_uint32), ("n_replay_units", C.c_uint32), ("replay_ms", C.c_double), ("k5_ms", C.c_double), ("pack_ms", C.c_double), ("ingest_ms", C.c_double), ("write_ms", C.c_double), ("kernels_ms", C.c_double)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

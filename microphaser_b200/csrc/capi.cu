@@ -138,8 +138,11 @@ struct mph_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;       // compute + device -> host
   cudaStream_t copy_stream = nullptr;  // host -> device of the next stage
+  cudaStream_t replay_stream = nullptr;  // the serial replay of irregular transcripts runs beside the window kernels
+  cudaEvent_t ev_rp[3] = {};           // K1 done / replay start / replay done
   std::vector<cudaEvent_t> ev_copy;
   uint32_t stage_seg_lo = 0, stage_seg_hi = 0, stage_tx_lo = 0, stage_tx_hi = 0;
+  bool replay_on_side = false;         // the last run_kernels put k_replay on replay_stream (its time comes from ev_rp)
   bool kernels_done = false;           // mph_phase_resident ran for the uploaded batch: mph_phase_collect only downloads
   cudaEvent_t ev[10] = {};
   std::string last_error;
@@ -305,7 +308,7 @@ void prepare(mph_ctx* c, const mph_batch* mb) {
   if (b.mode == 0) {
     c->win_seg.ensure(nw + 1); c->tx_stop.ensure(b.txs.size() + 1);
     c->rw.ensure(nw + 1); c->rw_stopq.ensure(nw + 1); c->rw_info.ensure(nw + 1); c->rw_mbase.ensure(nw + 1); c->rw_bytes.ensure(nw + 1); c->rw_junc.ensure(b.segs.size() + 1);
-    c->rc_blocks.ensure(nw / 256 + 4);
+    c->rc_blocks.ensure(nw / 256 + 4);  // (the record kernels use 512 windows per block)
     if (c->recs.cap == 0) { c->recs.ensure(std::max<size_t>(nw / 16, 1 << 14)); c->rec_seq.ensure(c->recs.cap * 64); }
     if (c->m_recs.cap == 0) { c->m_recs.ensure(1 << 14); c->m_aux.ensure(c->m_recs.cap); c->m_seq.ensure(c->m_recs.cap * MPH_RC_SEQ_SLOT); }
   } c->seg_live.ensure(b.segs.size() + 1);
@@ -440,13 +443,26 @@ void run_kernels(mph_ctx* c) {
   mphk::launch_read_decode(d, c->stream);  // K0: start / end / flags of the slice's reads from their 2-byte bus form
   mphk::launch_allele_call(d, c->stream);
   CU(cudaEventRecord(c->ev[3], c->stream));
-  // measured on B200: on a second stream (any priority, with or without a dispatch head start) the replay and the
-  // closed-form kernel still take the sum of their times - the replay's shared-memory footprint keeps the window
-  // kernel's CTAs off the SMs it occupies - so the two kernels simply run back to back
-  mphk::launch_replay(d, c->stream);
+  // The serial replay (a latency-bound dependent chain per unit, a few hundred warps) runs on its own stream beside the
+  // window kernels: they skip the replayed segments, and K3 is the first kernel that needs both results. (Round 1 measured
+  // no gain from this with the one-kernel K2, whose CTAs could not share an SM with the replay's shared-memory footprint;
+  // the streaming K2a needs no shared memory.) MPH_SERIAL_REPLAY=1 puts it back on the main stream.
+  static const bool serial_replay = getenv("MPH_SERIAL_REPLAY") != nullptr;
+  const bool side = !serial_replay && d.rp1 > d.rp0;
+  if (side) {
+    CU(cudaEventRecord(c->ev_rp[0], c->stream));
+    CU(cudaStreamWaitEvent(c->replay_stream, c->ev_rp[0], 0));
+    CU(cudaEventRecord(c->ev_rp[1], c->replay_stream));
+    mphk::launch_replay(d, c->replay_stream);
+    CU(cudaEventRecord(c->ev_rp[2], c->replay_stream));
+  } else {
+    mphk::launch_replay(d, c->stream);
+  }
   CU(cudaEventRecord(c->ev[8], c->stream));
   mphk::launch_window_hist(d, c->stream);
+  if (side) CU(cudaStreamWaitEvent(c->stream, c->ev_rp[2], 0));
   CU(cudaEventRecord(c->ev[4], c->stream));
+  c->replay_on_side = side;
   mphk::launch_assemble(d, c->stream);
   CU(cudaEventRecord(c->ev[5], c->stream));
   mphk::launch_compact(d, c->stream);
@@ -502,8 +518,10 @@ void fetch_stage(mph_ctx* c, const Stage& s, PhaseRaw& raw, uint64_t* n_iw_total
   }
   float ms;
   CU(cudaEventElapsedTime(&ms, c->ev[2], c->ev[3])); c->timing.k1_ms += ms;
-  CU(cudaEventElapsedTime(&ms, c->ev[3], c->ev[8])); c->timing.replay_ms += ms;
-  CU(cudaEventElapsedTime(&ms, c->ev[8], c->ev[4])); c->timing.k2_ms += ms;
+  if (c->replay_on_side) { CU(cudaEventElapsedTime(&ms, c->ev_rp[1], c->ev_rp[2])); c->timing.replay_ms += ms; }
+  else { CU(cudaEventElapsedTime(&ms, c->ev[3], c->ev[8])); c->timing.replay_ms += ms; }
+  CU(cudaEventElapsedTime(&ms, c->ev[8], c->ev[4])); c->timing.k2_ms += ms;  // includes the wait for a replay that outlasts K2
+  CU(cudaEventElapsedTime(&ms, c->ev[2], c->ev[9])); c->timing.kernels_ms += ms;
   CU(cudaEventElapsedTime(&ms, c->ev[4], c->ev[5])); c->timing.k3_ms += ms;
   CU(cudaEventElapsedTime(&ms, c->ev[5], c->ev[6])); c->timing.k4_ms += ms;
   CU(cudaEventElapsedTime(&ms, c->ev[6], c->ev[9])); c->timing.k5_ms += ms;
@@ -1003,6 +1021,8 @@ int mph_ctx_create(int device, mph_ctx** out) {
     CU(cudaSetDevice(device));
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c->replay_stream, cudaStreamNonBlocking));
+    for (auto& e3 : c->ev_rp) CU(cudaEventCreate(&e3));
     for (auto& e2 : c->ev) CU(cudaEventCreate(&e2));
   });
   if (rc != MPH_OK) return rc;
@@ -1021,6 +1041,9 @@ void mph_ctx_destroy(mph_ctx* c) {
   for (auto& e : c->ev_copy)
     if (e) cudaEventDestroy(e);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  for (auto& e : c->ev_rp)
+    if (e) cudaEventDestroy(e);
+  if (c->replay_stream) cudaStreamDestroy(c->replay_stream);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;  // the remaining device buffers are released by ~DevBuf
 }
@@ -1149,8 +1172,10 @@ int mph_phase_resident(mph_ctx* ctx) {
     CU(cudaStreamSynchronize(ctx->stream));
     float ms;
     CU(cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3])); ctx->timing.k1_ms = ms;
-    CU(cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[8])); ctx->timing.replay_ms = ms;
+    if (ctx->replay_on_side) { CU(cudaEventElapsedTime(&ms, ctx->ev_rp[1], ctx->ev_rp[2])); ctx->timing.replay_ms = ms; }
+    else { CU(cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[8])); ctx->timing.replay_ms = ms; }
     CU(cudaEventElapsedTime(&ms, ctx->ev[8], ctx->ev[4])); ctx->timing.k2_ms = ms;
+    CU(cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[9])); ctx->timing.kernels_ms = ms;
     CU(cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5])); ctx->timing.k3_ms = ms;
     CU(cudaEventElapsedTime(&ms, ctx->ev[5], ctx->ev[6])); ctx->timing.k4_ms = ms;
     CU(cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[9])); ctx->timing.k5_ms = ms;
@@ -1165,7 +1190,7 @@ int mph_phase_collect(mph_ctx* ctx, mph_result** out) {
     if (!ctx->cur) throw std::runtime_error("no resident run to collect");
     CU(cudaSetDevice(ctx->device));
     const std::vector<Stage> all = plan_stages(ctx->cur, 1);
-    ctx->timing.k1_ms = ctx->timing.k2_ms = ctx->timing.k3_ms = ctx->timing.k4_ms = ctx->timing.k5_ms = ctx->timing.replay_ms = 0;
+    ctx->timing.k1_ms = ctx->timing.k2_ms = ctx->timing.k3_ms = ctx->timing.k4_ms = ctx->timing.k5_ms = ctx->timing.replay_ms = ctx->timing.kernels_ms = 0;
     ctx->timing.d2h_ms = 0;
     ctx->timing.d2h_bytes = 0;
     phase_stages(ctx, all, true, out);
@@ -1352,7 +1377,7 @@ static void run_somatic_files(const std::vector<mph_ctx*>& ctxs, const char* bam
     std::vector<mph_timing> acc(n_dev, mph_timing{});  // a device's timing is the sum over its shards
     auto add_timing = [](mph_timing& a, const mph_timing& t) {
       a.h2d_ms += t.h2d_ms; a.k1_ms += t.k1_ms; a.k2_ms += t.k2_ms; a.k3_ms += t.k3_ms; a.k4_ms += t.k4_ms; a.d2h_ms += t.d2h_ms;
-      a.residue_ms += t.residue_ms; a.total_ms += t.total_ms; a.replay_ms += t.replay_ms; a.k5_ms += t.k5_ms; a.pack_ms += t.pack_ms; a.h2d_bytes += t.h2d_bytes; a.d2h_bytes += t.d2h_bytes;
+      a.residue_ms += t.residue_ms; a.total_ms += t.total_ms; a.replay_ms += t.replay_ms; a.k5_ms += t.k5_ms; a.pack_ms += t.pack_ms; a.kernels_ms += t.kernels_ms; a.h2d_bytes += t.h2d_bytes; a.d2h_bytes += t.d2h_bytes;
       a.windows += t.windows; a.read_windows += t.read_windows; a.windows_enumerated += t.windows_enumerated; a.n_interesting += t.n_interesting;
       a.n_records += t.n_records; a.kernel_launches += t.kernel_launches; a.n_replay_units += t.n_replay_units;
     };

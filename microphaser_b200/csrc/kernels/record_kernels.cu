@@ -24,7 +24,7 @@ using namespace detail;
 
 namespace {
 
-constexpr int RC_THREADS = 256;
+constexpr int RC_THREADS = 512;
 
 __device__ __forceinline__ MphRecCtx rec_ctx(const DeviceBatch& d) {
   MphRecCtx c;
