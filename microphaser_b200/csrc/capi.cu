@@ -443,12 +443,13 @@ void run_kernels(mph_ctx* c) {
   mphk::launch_read_decode(d, c->stream);  // K0: start / end / flags of the slice's reads from their 2-byte bus form
   mphk::launch_allele_call(d, c->stream);
   CU(cudaEventRecord(c->ev[3], c->stream));
-  // The serial replay (a latency-bound dependent chain per unit, a few hundred warps) runs on its own stream beside the
-  // window kernels: they skip the replayed segments, and K3 is the first kernel that needs both results. (Round 1 measured
-  // no gain from this with the one-kernel K2, whose CTAs could not share an SM with the replay's shared-memory footprint;
-  // the streaming K2a needs no shared memory.) MPH_SERIAL_REPLAY=1 puts it back on the main stream.
-  static const bool serial_replay = getenv("MPH_SERIAL_REPLAY") != nullptr;
-  const bool side = !serial_replay && d.rp1 > d.rp0;
+  // The serial replay (a latency-bound dependent chain per unit, a few hundred warps) can run on its own stream beside the
+  // window kernels (MPH_SIDE_REPLAY=1): they skip the replayed segments, and K3 is the first kernel that needs both results.
+  // Measured on B200 (whole-exome shard): the chain takes 3.32 ms instead of 3.56 ms, but the two slow each other down
+  // (replay 0.79 -> 1.65 ms, K2 1.19 -> ~1.5 ms), which blurs the per-kernel figures the bench reports; the default keeps
+  // them back to back.
+  static const bool side_replay = getenv("MPH_SIDE_REPLAY") != nullptr;
+  const bool side = side_replay && d.rp1 > d.rp0;
   if (side) {
     CU(cudaEventRecord(c->ev_rp[0], c->stream));
     CU(cudaStreamWaitEvent(c->replay_stream, c->ev_rp[0], 0));

@@ -304,14 +304,23 @@ __global__ void __launch_bounds__(RR_THREADS) k_read_runs(const DeviceBatch d) {
       // frameshift enumeration (those reads are all class 3), so windows sit 3 iterations apart (k = kf + 3 i) and only
       // the exon's first and last window deviate from s = off0 +- k, e = s + ewl (mph_geom).
       const int n = (int)sg.n_win;
-      const int off0 = (int)sg.off0, ewl = (int)sg.ewl, kf = (int)sg.k_first, ks = (int)sg.k_stride;
+      const int off0 = (int)sg.off0, ewl = (int)sg.ewl, kf = (int)sg.k_first;
       const int ist = (int)st, ien = (int)en;
-      const MphGeom g_first = mph_geom(sg, (uint32_t)kf), g_last = mph_geom(sg, (uint32_t)(kf + (n - 1) * ks));
-      auto fdiv = [&](int x) { return ks == 3 ? (x >= 0 ? x / 3 : -((-x + 2) / 3)) : (ks == 1 ? x : (x >= 0 ? x / ks : -((-x + ks - 1) / ks))); };  // floor(x / ks)
-      auto cdiv = [&](int x) { return -fdiv(-x); };                                                                                               // ceil(x / ks)
+      const MphGeom g_first = mph_geom(sg, (uint32_t)kf), g_last = mph_geom(sg, (uint32_t)(kf + (n - 1) * (int)sg.k_stride));
+      // a segment without frameshift enumeration has one window (short exon) or windows exactly 3 iterations apart
+      auto fdiv = [](int x) { return x >= 0 ? x / 3 : -((-x + 2) / 3); };  // floor(x / 3)
+      auto cdiv = [&](int x) { return -fdiv(-x); };                        // ceil(x / 3)
       auto clampi = [](int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); };
       int ilo, ihi;
-      if (!rev) {
+      if (n == 1) {
+        // the single window of the segment: the membership test itself
+        const uint32_t s0 = sg.off0 - sg.ceo;
+        bool member;
+        if (!rev) member = en >= g_first.e && (kf == 0 ? (st <= s0 && (int64_t)st >= (int64_t)s0 - (int64_t)sg.K) : (st <= s0 ? (int64_t)st >= (int64_t)s0 - (int64_t)sg.K : (st > sg.off0 && ist - off0 <= kf)));
+        else member = st <= g_first.s && en >= g_first.e && (int64_t)st + sg.K >= (int64_t)g_first.s;
+        ilo = member ? 0 : 1;
+        ihi = 0;
+      } else if (!rev) {
         // e is non-decreasing: e(i) = off0 + k + ewl for i < n - 1, the last window ends at g_last.e
         if (en >= g_last.e) ihi = n - 1;
         else ihi = ien >= off0 + ewl + kf ? clampi(fdiv(ien - off0 - ewl - kf), -1, n - 2) : -1;
