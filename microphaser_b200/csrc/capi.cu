@@ -846,6 +846,7 @@ void phase_stages(mph_ctx* c, const std::vector<Stage>& stages, bool copied, mph
 
 // host buffers in, records out: the pipelined path
 void phase_batch_impl(mph_ctx* c, const mph_batch* mb, mph_result** out) {
+  c->cur = nullptr;
   prepare(c, mb);
   // stages of about 7 M reads: every stage pays the fixed latency of its kernel chain (the serial replay's longest unit, the
   // junction merges), so a few long stages beat many short ones now that almost no host work is left to hide behind the
@@ -854,7 +855,14 @@ void phase_batch_impl(mph_ctx* c, const mph_batch* mb, mph_result** out) {
   if (const char* e = getenv("MPH_STAGES")) want = unsigned(std::max(1, atoi(e)));
   const std::vector<Stage> stages = plan_stages(mb, want);
   c->kernels_done = false;
-  phase_stages(c, stages, false, out);
+  // the context must not keep pointing at the caller's batch after the call, whichever way it ends: the batch may be
+  // destroyed next, and a later mph_phase_resident / mph_phase_collect has to fail cleanly ("no batch uploaded")
+  try {
+    phase_stages(c, stages, false, out);
+  } catch (...) {
+    c->cur = nullptr;
+    throw;
+  }
   c->cur = nullptr;
 }
 
@@ -1144,12 +1152,18 @@ int mph_batch_get_view(const mph_batch* mb, mph_batch_view* v) {
 int mph_batch_upload(mph_ctx* ctx, const mph_batch* batch) {
   if (!ctx || !batch) return fail(ctx, MPH_ERR_INPUT, "null argument");
   return guarded(ctx, [&] {
-    prepare(ctx, batch);
-    const std::vector<Stage> all = plan_stages(batch, 1);
-    CU(cudaEventRecord(ctx->ev[0], ctx->stream));
-    copy_stage(ctx, batch, all[0], true, ctx->stream);
-    CU(cudaEventRecord(ctx->ev[1], ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->cur = nullptr;  // stays null if the upload fails
+    try {
+      prepare(ctx, batch);
+      const std::vector<Stage> all = plan_stages(batch, 1);
+      CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+      copy_stage(ctx, batch, all[0], true, ctx->stream);
+      CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+      CU(cudaStreamSynchronize(ctx->stream));
+    } catch (...) {
+      ctx->cur = nullptr;
+      throw;
+    }
     float ms;
     CU(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
     ctx->timing.h2d_ms = ms;

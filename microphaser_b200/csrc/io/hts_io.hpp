@@ -149,10 +149,11 @@ class BgzfReader {
     int bsize = -1;
     for (size_t o = 0; o + 4 <= extra.size();) {
       uint16_t slen = extra[o + 2] | (extra[o + 3] << 8);
-      if (extra[o] == 'B' && extra[o + 1] == 'C' && slen == 2) bsize = extra[o + 4] | (extra[o + 5] << 8);
+      if (extra[o] == 'B' && extra[o + 1] == 'C' && slen == 2 && o + 6 <= extra.size()) bsize = extra[o + 4] | (extra[o + 5] << 8);
       o += 4 + slen;
     }
     if (bsize < 0) throw IoError("BGZF block without BC field in " + path_);
+    if (size_t(bsize) + 1 < size_t(12) + xlen + 8) throw IoError("corrupt BGZF block size in " + path_);
     const size_t clen = size_t(bsize) + 1 - 12 - xlen - 8;  // compressed payload
     const size_t off = cbuf.size();
     cbuf.resize(off + clen + 8);
@@ -380,20 +381,24 @@ struct BamFile {
   explicit BamFile(const std::string& path, unsigned inflate_threads = 1) : rd_(path, inflate_threads) {
     char magic[4];
     if (!rd_.read(magic, 4) || memcmp(magic, "BAM\1", 4) != 0) throw IoError("not a BAM file: " + path);
+    auto must = [&](void* dst, size_t n) { if (!rd_.read(dst, n)) throw IoError("truncated BAM header: " + path); };
     int32_t l_text;
-    rd_.read(&l_text, 4);
-    header_text.resize(l_text);
-    if (l_text) rd_.read(&header_text[0], l_text);
+    must(&l_text, 4);
+    if (l_text < 0 || l_text > (1 << 30)) throw IoError("corrupt BAM header: " + path);
+    header_text.resize(size_t(l_text));
+    if (l_text) must(&header_text[0], size_t(l_text));
     int32_t n_ref;
-    rd_.read(&n_ref, 4);
+    must(&n_ref, 4);
+    if (n_ref < 0 || n_ref > (1 << 24)) throw IoError("corrupt BAM header: " + path);
     for (int i = 0; i < n_ref; ++i) {
       int32_t l_name;
-      rd_.read(&l_name, 4);
-      std::string nm(l_name, 0);
-      rd_.read(&nm[0], l_name);
+      must(&l_name, 4);
+      if (l_name <= 0 || l_name > (1 << 16)) throw IoError("corrupt BAM header: " + path);
+      std::string nm(size_t(l_name), 0);
+      must(&nm[0], size_t(l_name));
       if (!nm.empty() && nm.back() == 0) nm.pop_back();
       int32_t l_ref;
-      rd_.read(&l_ref, 4);
+      must(&l_ref, 4);
       tid_of[nm] = i;
       ref_names.push_back(nm);
       ref_lens.push_back(l_ref);
@@ -410,8 +415,9 @@ struct BamFile {
   bool next(BamRecord& r) {
     int32_t bs;
     if (!rd_.read(&bs, 4)) return false;
-    buf_.resize(bs);
-    rd_.read(buf_.data(), bs);
+    if (bs < 32 || bs > (1 << 29)) throw IoError("corrupt BAM record");  // the fixed part alone is 32 bytes
+    buf_.resize(size_t(bs));
+    if (!rd_.read(buf_.data(), size_t(bs))) throw IoError("truncated BAM record");
     const uint8_t* p = buf_.data();
     auto i32 = [&](size_t o) { int32_t v; memcpy(&v, p + o, 4); return v; };
     auto u16 = [&](size_t o) { uint16_t v; memcpy(&v, p + o, 2); return v; };
@@ -421,7 +427,11 @@ struct BamFile {
     r.mapq = p[9];
     uint16_t n_cigar = u16(12);
     r.flag = u16(14);
-    r.l_seq = uint32_t(i32(16));
+    const int32_t l_seq = i32(16);
+    // the variable part must fit the record: name, CIGAR, packed bases, qualities (the threaded loader checks the same)
+    if (l_seq < 0 || 32 + size_t(l_read_name) + 4 * size_t(n_cigar) + (size_t(l_seq) + 1) / 2 + size_t(l_seq) > size_t(bs))
+      throw IoError("corrupt BAM record");
+    r.l_seq = uint32_t(l_seq);
     size_t o = 32;
     r.qname.assign(reinterpret_cast<const char*>(p + o), l_read_name ? l_read_name - 1 : 0);
     o += l_read_name;
