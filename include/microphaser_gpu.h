@@ -112,7 +112,8 @@ typedef struct {
   const uint32_t* read_end;
   const uint8_t* read_flags;
   /* compact side table: one entry per read that overlaps a variant (every read of a gene whose transcripts need the
-   * serial replay): read index, first variant index, offset of its packed bases (16-B units) / CIGAR, lengths */
+   * serial replay): read index, first variant index, byte offset of its packed bases / offset of its CIGAR, lengths.
+   * (On the bus the table travels as 9 B per entry - distances and record sizes - and is rebuilt on the device.) */
   uint64_t n_variant_reads;
   const uint32_t* vr_read;
   const uint32_t* vr_vlo;

@@ -154,8 +154,10 @@ struct mph_ctx {
   DevBuf<uint8_t> read_nv, vr_nv, read_flags, bases, ins_bytes, ref, call_flags, seq, win_flag, o_flags, o_inmat;
   DevBuf<MphReplayTx> replay;
   DevBuf<uint64_t> o_hap;
-  DevBuf<uint2> pairs, seg_list, rd_runs, rd_span_exc, rd_flag_exc;
-  DevBuf<uint8_t> rd_delta, rd_span;
+  DevBuf<uint2> pairs, seg_list, rd_runs, rd_span_exc, rd_flag_exc, vs_ncig_exc;
+  DevBuf<uint8_t> rd_delta, rd_span, vs_vlo_d, vs_ncig;
+  DevBuf<uint16_t> vs_read_d, vs_size;
+  DevBuf<MphSideRun> vs_runs;
   DevBuf<MphVar> vars;
   DevBuf<MphSegment> segs;
   DevBuf<MphChunk> chunks;
@@ -213,8 +215,8 @@ void finish_batch(mph_batch* mb, bool pin) {
   for (auto& e : b.pair_edges) mb->pairs.push_back(make_uint2(e.first, e.second));
   std::sort(mb->pairs.begin(), mb->pairs.end(), [](const uint2& a, const uint2& c) { return a.x < c.x; });
   auto bytes = [](auto& v) { return v.size() * sizeof(v[0]); };
-  mb->h2d_bytes = bytes(b.rd_delta) + bytes(b.rd_span) + bytes(b.rd_runs) + bytes(b.rd_span_exc) + bytes(b.rd_flag_exc) + bytes(b.vr_read) + bytes(b.vr_vlo) + bytes(b.vr_seq_off) +
-                  bytes(b.vr_cig_off) + bytes(b.vr_lseq) + bytes(b.vr_ncig) + bytes(b.vr_nv) + bytes(b.bases) + bytes(b.cigars) +
+  mb->h2d_bytes = bytes(b.rd_delta) + bytes(b.rd_span) + bytes(b.rd_runs) + bytes(b.rd_span_exc) + bytes(b.rd_flag_exc) + bytes(b.vs_read_d) + bytes(b.vs_vlo_d) + bytes(b.vs_size) +
+                  bytes(b.vs_ncig) + bytes(b.vs_runs) + bytes(b.vs_ncig_exc) + bytes(b.vr_lseq) + bytes(b.vr_nv) + bytes(b.bases) + bytes(b.cigars) +
                   bytes(b.vars) + bytes(b.ins_bytes) + bytes(b.segs) + bytes(b.chunks) + bytes(b.seg_work) + bytes(b.seg_work_off) + bytes(b.ref) + bytes(b.stopmap) + bytes(mb->pairs) +
                   bytes(b.tx_id_bytes) + bytes(b.tx_id_off) + bytes(b.replay) + bytes(b.replay_dq) + (b.replay.empty() ? 0 : bytes(b.seg_chunk0));
   if (pin) {
@@ -225,8 +227,8 @@ void finish_batch(mph_batch* mb, bool pin) {
       else
         cudaGetLastError();
     };
-    reg(b.rd_delta); reg(b.rd_span); reg(b.rd_runs); reg(b.rd_span_exc); reg(b.rd_flag_exc); reg(b.vr_read); reg(b.vr_vlo); reg(b.vr_seq_off); reg(b.vr_cig_off); reg(b.vr_lseq);
-    reg(b.vr_ncig); reg(b.vr_nv); reg(b.bases); reg(b.cigars); reg(b.vars); reg(b.ins_bytes); reg(b.segs); reg(b.chunks); reg(b.seg_work); reg(b.seg_work_off); reg(b.ref); reg(b.stopmap);
+    reg(b.rd_delta); reg(b.rd_span); reg(b.rd_runs); reg(b.rd_span_exc); reg(b.rd_flag_exc); reg(b.vs_read_d); reg(b.vs_vlo_d); reg(b.vs_size); reg(b.vs_ncig); reg(b.vs_runs); reg(b.vs_ncig_exc); reg(b.vr_lseq);
+    reg(b.vr_nv); reg(b.bases); reg(b.cigars); reg(b.vars); reg(b.ins_bytes); reg(b.segs); reg(b.chunks); reg(b.seg_work); reg(b.seg_work_off); reg(b.ref); reg(b.stopmap);
     reg(mb->pairs);
     reg(b.tx_id_bytes); reg(b.tx_id_off); reg(b.replay); reg(b.replay_dq); reg(b.seg_chunk0);
     mb->pinned = true;
@@ -296,6 +298,8 @@ void prepare(mph_ctx* c, const mph_batch* mb) {
   c->read_vlo.ensure(nr + 1); c->read_nv.ensure(nr + 1); c->read_vr.ensure(nr + 1);  // expanded on the device by K1
   c->vr_read.ensure(nvr + 1); c->vr_vlo.ensure(nvr + 1); c->vr_seq_off.ensure(nvr + 1); c->vr_cig_off.ensure(nvr + 1);
   c->vr_lseq.ensure(nvr + 1); c->vr_ncig.ensure(nvr + 1); c->vr_nv.ensure(nvr + 1);
+  c->vs_read_d.ensure(nvr + 1); c->vs_vlo_d.ensure(nvr + 1); c->vs_size.ensure(nvr + 1); c->vs_ncig.ensure(nvr + 1);
+  c->vs_runs.ensure(b.vs_runs.size() + 1); c->vs_ncig_exc.ensure(b.vs_ncig_exc.size() + 1);
   c->bases.ensure(b.bases.size() + 1); c->cigars.ensure(b.cigars.size() + 1); c->vars.ensure(b.vars.size() + 1); c->ins_bytes.ensure(b.ins_bytes.size() + 1);
   c->segs.ensure(b.segs.size() + 1); c->chunks.ensure(b.chunks.size() + 1); c->seg_work.ensure(b.seg_work.size() + 1); c->seg_work_off.ensure(b.seg_work_off.size() + 1);
   c->win_diff.ensure(nw + 1); c->seg_list.ensure(size_t(b.seg_work_off.back()) + 1); c->seg_list_n.ensure(2 * b.segs.size() + 2); c->ref.ensure(b.ref.size() + 1); c->stopmap.ensure(b.stopmap.size() + 1);
@@ -327,6 +331,9 @@ void prepare(mph_ctx* c, const mph_batch* mb) {
   d.read_vlo = c->read_vlo.p; d.read_nv = c->read_nv.p; d.read_vr = c->read_vr.p;
   d.vr_read = c->vr_read.p; d.vr_vlo = c->vr_vlo.p; d.vr_seq_off = c->vr_seq_off.p; d.vr_cig_off = c->vr_cig_off.p;
   d.vr_lseq = c->vr_lseq.p; d.vr_ncig = c->vr_ncig.p; d.vr_nv = c->vr_nv.p;
+  d.vr_read_w = c->vr_read.p; d.vr_vlo_w = c->vr_vlo.p; d.vr_seq_off_w = c->vr_seq_off.p; d.vr_cig_off_w = c->vr_cig_off.p; d.vr_ncig_w = c->vr_ncig.p;
+  d.vs_read_d = c->vs_read_d.p; d.vs_vlo_d = c->vs_vlo_d.p; d.vs_size = c->vs_size.p; d.vs_ncig = c->vs_ncig.p; d.vs_runs = c->vs_runs.p;
+  d.vs_ncig_exc = c->vs_ncig_exc.p;
   d.bases = c->bases.p; d.cigars = c->cigars.p; d.vars = c->vars.p;
   d.ins_bytes = c->ins_bytes.p; d.segs = c->segs.p; d.chunks = c->chunks.p; d.seg_work = c->seg_work.p; d.seg_work_off = c->seg_work_off.p;
   d.win_diff = c->win_diff.p; d.seg_list = c->seg_list.p; d.seg_list_n = c->seg_list_n.p; d.seg_list2_n = c->seg_list_n.p + b.segs.size() + 1; d.ref = c->ref.p; d.stopmap = c->stopmap.p;
@@ -372,9 +379,9 @@ void copy_stage(mph_ctx* c, const mph_batch* mb, const Stage& s, bool first, cud
   h2d_range(st, c->rd_runs, b.rd_runs, s.lo.runs, s.hi.runs); h2d_range(st, c->rd_span_exc, b.rd_span_exc, s.lo.span_exc, s.hi.span_exc);
   h2d_range(st, c->rd_flag_exc, b.rd_flag_exc, s.lo.flag_exc, s.hi.flag_exc);
   const size_t e0 = s.lo.vr, e1 = s.hi.vr;
-  h2d_range(st, c->vr_read, b.vr_read, e0, e1); h2d_range(st, c->vr_vlo, b.vr_vlo, e0, e1); h2d_range(st, c->vr_seq_off, b.vr_seq_off, e0, e1);
-  h2d_range(st, c->vr_cig_off, b.vr_cig_off, e0, e1); h2d_range(st, c->vr_lseq, b.vr_lseq, e0, e1); h2d_range(st, c->vr_ncig, b.vr_ncig, e0, e1);
-  h2d_range(st, c->vr_nv, b.vr_nv, e0, e1);
+  h2d_range(st, c->vs_read_d, b.vs_read_d, e0, e1); h2d_range(st, c->vs_vlo_d, b.vs_vlo_d, e0, e1); h2d_range(st, c->vs_size, b.vs_size, e0, e1);
+  h2d_range(st, c->vs_ncig, b.vs_ncig, e0, e1); h2d_range(st, c->vr_lseq, b.vr_lseq, e0, e1); h2d_range(st, c->vr_nv, b.vr_nv, e0, e1);
+  h2d_range(st, c->vs_runs, b.vs_runs, s.lo.vruns, s.hi.vruns); h2d_range(st, c->vs_ncig_exc, b.vs_ncig_exc, s.lo.ncig_exc, s.hi.ncig_exc);
   h2d_range(st, c->bases, b.bases, s.lo.bases, s.hi.bases); h2d_range(st, c->cigars, b.cigars, s.lo.cigars, s.hi.cigars);
   h2d_range(st, c->vars, b.vars, s.lo.vars, s.hi.vars); h2d_range(st, c->ins_bytes, b.ins_bytes, s.lo.ins, s.hi.ins);
   h2d_range(st, c->segs, b.segs, s.lo.segs, s.hi.segs); h2d_range(st, c->chunks, b.chunks, s.lo.chunks, s.hi.chunks);
@@ -397,6 +404,7 @@ void set_ranges(mph_ctx* c, const Stage& s) {
   d.s0 = uint32_t(s.lo.segs); d.s1 = uint32_t(s.hi.segs);
   d.run0 = uint32_t(s.lo.runs); d.run1 = uint32_t(s.hi.runs); d.sx0 = uint32_t(s.lo.span_exc); d.sx1 = uint32_t(s.hi.span_exc);
   d.fx0 = uint32_t(s.lo.flag_exc); d.fx1 = uint32_t(s.hi.flag_exc);
+  d.vrun0 = uint32_t(s.lo.vruns); d.vrun1 = uint32_t(s.hi.vruns); d.nx0 = uint32_t(s.lo.ncig_exc); d.nx1 = uint32_t(s.hi.ncig_exc);
   d.it0 = c->cur->b.seg_work_off[s.lo.segs]; d.it1 = c->cur->b.seg_work_off[s.hi.segs];
   d.w0 = uint32_t(s.lo.windows); d.w1 = uint32_t(s.hi.windows);
   d.rp0 = uint32_t(s.lo.replay); d.rp1 = uint32_t(s.hi.replay);

@@ -92,6 +92,11 @@ typedef struct {
   uint32_t va0, vb1;
 } MphSegWork;
 
+// Restart point of the side table's running sums on the bus (host: Batch::VRun), 20 B.
+typedef struct {
+  uint32_t entry, read, vlo, seq_off, cig_off;
+} MphSideRun;
+
 // Per-read fields, as the core functions see them in registers. In memory the reads are
 // structure-of-arrays (include/microphaser_gpu.h: mph_batch_in.read_*).
 //   seq_off : 16-byte units into the packed-base arena, where the read's record is

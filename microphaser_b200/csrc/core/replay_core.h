@@ -96,7 +96,7 @@ MPH_HD void mph_rp_eval(const MphReplayCtx& c, uint32_t r, uint32_t v, bool* sup
   const uint32_t ncig = c.vr_ncig[e];
   const uint32_t* cig = c.cigars + c.vr_cig_off[e];
   if (var.kind == MPH_SNV) {
-    const uint8_t* rec = c.bases + (size_t)soff * 16;
+    const uint8_t* rec = c.bases + (size_t)soff;
     const uint32_t rel = var.pos - start;
     if (c.mode == 0 && rel < l_seq && mph_rec_low(rec, l_seq, rel)) { *bad = true; return; }
     uint32_t q;

@@ -79,7 +79,7 @@ struct GeneMeta {
 // sizes of every per-gene-contiguous array after a gene has been packed: a batch can be cut at any gene boundary
 struct GeneMark {
   uint64_t reads = 0, vr = 0, bases = 0, cigars = 0, vars = 0, ins = 0, segs = 0, chunks = 0, ref = 0, windows = 0, txs = 0, replay = 0, dq = 0, partners = 0;
-  uint64_t runs = 0, span_exc = 0, flag_exc = 0;
+  uint64_t runs = 0, span_exc = 0, flag_exc = 0, vruns = 0, ncig_exc = 0;
 };
 
 struct Batch {
@@ -98,6 +98,15 @@ struct Batch {
   std::vector<U2> rd_runs;      // (first read, its start)
   std::vector<U2> rd_span_exc;  // (read, end)
   std::vector<U2> rd_flag_exc;  // (read, flags)
+  // bus form of the side table (9 B per entry instead of 21): the entries are sorted by read, their first-variant index
+  // never decreases within a gene, and the offsets of the packed bases / CIGARs are running sums of the record sizes, so an
+  // entry ships as read distance (u16), variant-index distance (u8), record bytes (u16), CIGAR ops (u8; 255 = see vs_ncig_exc)
+  // next to vr_lseq / vr_nv; a run table restarts the sums at every gene and wherever a distance does not fit.
+  std::vector<uint16_t> vs_read_d, vs_size;
+  std::vector<uint8_t> vs_vlo_d, vs_ncig;
+  struct VRun { uint32_t entry, read, vlo, seq_off, cig_off; };
+  std::vector<VRun> vs_runs;
+  std::vector<U2> vs_ncig_exc;  // (entry, CIGAR ops) for entries with 255 and more
   // compact side table of the reads K1 has work for (variants inside the alignment; every read of a gene with replayed
   // transcripts): read index, first variant index, offsets of the packed bases / CIGAR, lengths, variant count
   std::vector<uint32_t> vr_read, vr_vlo, vr_seq_off, vr_cig_off;
@@ -154,6 +163,24 @@ inline void decode_reads(const Batch& b, std::vector<uint32_t>& start, std::vect
   }
   for (auto& e : b.rd_span_exc) end[e.x] = e.y;
   for (auto& e : b.rd_flag_exc) flags[e.x] = uint8_t(e.y);
+}
+
+// host statement of k_side_decode: the side table from its bus form
+inline void decode_side_table(const Batch& b, std::vector<uint32_t>& read, std::vector<uint32_t>& vlo, std::vector<uint32_t>& seq_off,
+                              std::vector<uint32_t>& cig_off, std::vector<uint16_t>& ncig) {
+  const size_t n = b.vs_read_d.size();
+  read.assign(n, 0); vlo.assign(n, 0); seq_off.assign(n, 0); cig_off.assign(n, 0); ncig.assign(n, 0);
+  for (size_t j = 0; j < b.vs_runs.size(); ++j) {
+    const size_t lo = b.vs_runs[j].entry, hi = j + 1 < b.vs_runs.size() ? b.vs_runs[j + 1].entry : n;
+    uint32_t r = b.vs_runs[j].read, v = b.vs_runs[j].vlo, so = b.vs_runs[j].seq_off, co = b.vs_runs[j].cig_off;
+    for (size_t e = lo; e < hi; ++e) {
+      r += b.vs_read_d[e]; v += b.vs_vlo_d[e];
+      read[e] = r; vlo[e] = v; seq_off[e] = so; cig_off[e] = co; ncig[e] = b.vs_ncig[e];
+      so += b.vs_size[e];
+      co += b.vs_ncig[e] < 255 ? b.vs_ncig[e] : 0u;  // exceptions patch ncig and are followed by a fresh run
+    }
+  }
+  for (auto& x : b.vs_ncig_exc) ncig[x.x] = uint16_t(x.y);
 }
 
 inline uint8_t base_code(uint8_t c) {
@@ -268,7 +295,7 @@ class Packer {
     auto add_vr = [&](uint32_t idx, uint32_t vlo, uint32_t nv, const HostRead& r) {
       // packed record (core/phase_core.h), 16-B aligned: 2-bit bases when the read has only A C G T, the positions with
       // qual < 10 as a short list when there are few of them (the normal mode never tests qualities: empty list)
-      const size_t off = (b_.bases.size() + 15u) & ~size_t(15);
+      const size_t off = b_.bases.size();  // byte offset: the records are not aligned (K1 reads them byte-wise)
       static const bool force_wide_format = getenv("MPH_PACK_WIDE") != nullptr;  // test hook: 4-bit bases + bitmask for every read
       bool acgt = !force_wide_format;
       for (uint32_t i = 0; i < r.l_seq && acgt; ++i) {
@@ -305,7 +332,7 @@ class Packer {
       }
       b_.vr_read.push_back(idx);
       b_.vr_vlo.push_back(vlo);
-      b_.vr_seq_off.push_back(uint32_t(off / 16));
+      b_.vr_seq_off.push_back(uint32_t(off));
       b_.vr_lseq.push_back(uint16_t(r.l_seq));
       b_.vr_nv.push_back(uint8_t(nv));
       const bool single_m = r.n_cigar == 1 && (r.cigar[0] & 15u) == 0 && (r.cigar[0] >> 4) == r.l_seq;
@@ -647,6 +674,27 @@ class Packer {
         ++q;
       }
     }
+    // bus encoding of this gene's side-table entries (see Batch::vs_read_d)
+    {
+      uint32_t cig_sum = uint32_t(cigars_mark);
+      bool after_exception = false;  // the device sums the 8-bit op counts: an entry with 255+ ops is followed by a fresh run
+      for (size_t e = vr_mark; e < b_.vr_read.size(); ++e) {
+        const uint32_t size = uint32_t((e + 1 < b_.vr_read.size() ? b_.vr_seq_off[e + 1] : b_.bases.size()) - b_.vr_seq_off[e]);
+        if (size > 0xFFFFu) throw Unsupported("read record larger than 64 KB");
+        const bool fresh = e == vr_mark || after_exception || b_.vr_read[e] - b_.vr_read[e - 1] > 0xFFFFu || b_.vr_vlo[e] < b_.vr_vlo[e - 1] ||
+                           b_.vr_vlo[e] - b_.vr_vlo[e - 1] > 255u;
+        if (fresh) b_.vs_runs.push_back(Batch::VRun{uint32_t(e), b_.vr_read[e], b_.vr_vlo[e], b_.vr_seq_off[e], cig_sum});
+        b_.vs_read_d.push_back(uint16_t(fresh ? 0u : b_.vr_read[e] - b_.vr_read[e - 1]));
+        b_.vs_vlo_d.push_back(uint8_t(fresh ? 0u : b_.vr_vlo[e] - b_.vr_vlo[e - 1]));
+        b_.vs_size.push_back(uint16_t(size));
+        const uint32_t nc = b_.vr_ncig[e];
+        b_.vs_ncig.push_back(uint8_t(nc < 255u ? nc : 255u));
+        if (nc >= 255u) b_.vs_ncig_exc.push_back(Batch::U2{uint32_t(e), nc});
+        after_exception = nc >= 255u;
+        b_.vr_cig_off[e] = cig_sum;  // running sum (single-M entries ship no CIGAR and never read theirs)
+        cig_sum += nc;
+      }
+    }
     // bus encoding of this gene's reads (see Batch::rd_delta)
     for (uint32_t r = gm.read_lo; r < gm.read_hi; ++r) {
       uint32_t delta = 0;
@@ -671,6 +719,7 @@ class Packer {
     mk.segs = b_.segs.size(); mk.chunks = b_.chunks.size(); mk.ref = b_.ref.size(); mk.windows = b_.n_windows; mk.txs = b_.txs.size();
     mk.replay = b_.replay.size(); mk.dq = b_.replay_dq.size(); mk.partners = b_.partner_a.size();
     mk.runs = b_.rd_runs.size(); mk.span_exc = b_.rd_span_exc.size(); mk.flag_exc = b_.rd_flag_exc.size();
+    mk.vruns = b_.vs_runs.size(); mk.ncig_exc = b_.vs_ncig_exc.size();
     b_.marks.push_back(mk);
   }
 

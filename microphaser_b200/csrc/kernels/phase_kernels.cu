@@ -60,6 +60,40 @@ __global__ void __launch_bounds__(256) k_read_patch(const DeviceBatch d) {
   else if (t < ns + nf) { const uint2 e = d.rd_flag_exc[d.fx0 + t - ns]; d.read_flags_w[e.x] = (uint8_t)e.y; }
 }
 
+// side table off the bus: one warp per run prefix-sums the read / variant-index distances, record sizes and CIGAR counts
+__global__ void __launch_bounds__(128) k_side_decode(const DeviceBatch d) {
+  const uint32_t j = d.vrun0 + blockIdx.x * 4 + (threadIdx.x >> 5);
+  const uint32_t lane = threadIdx.x & 31;
+  if (j >= d.vrun1) return;
+  const MphSideRun run = d.vs_runs[j];
+  const uint32_t hi = j + 1 < d.vrun1 ? d.vs_runs[j + 1].entry : d.vr1;
+  uint32_t read = run.read, vlo = run.vlo, so = run.seq_off, co = run.cig_off;
+  for (uint32_t base = run.entry; base < hi; base += 32) {
+    const uint32_t e = base + lane;
+    const bool in = e < hi;
+    uint32_t a = in ? d.vs_read_d[e] : 0u, b = in ? d.vs_vlo_d[e] : 0u, c = in ? d.vs_size[e] : 0u;
+    const uint32_t nc = in ? d.vs_ncig[e] : 0u;
+    uint32_t g = nc < 255u ? nc : 0u;
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t ya = __shfl_up_sync(FULL, a, o), yb = __shfl_up_sync(FULL, b, o), yc = __shfl_up_sync(FULL, c, o), yg = __shfl_up_sync(FULL, g, o);
+      if (lane >= (uint32_t)o) { a += ya; b += yb; c += yc; g += yg; }
+    }
+    if (in) {
+      d.vr_read_w[e] = read + a;
+      d.vr_vlo_w[e] = vlo + b;
+      d.vr_seq_off_w[e] = so + c - d.vs_size[e];                 // exclusive sums for the two offsets
+      d.vr_cig_off_w[e] = co + g - (nc < 255u ? nc : 0u);
+      d.vr_ncig_w[e] = (uint16_t)nc;
+    }
+    read += __shfl_sync(FULL, a, 31); vlo += __shfl_sync(FULL, b, 31); so += __shfl_sync(FULL, c, 31); co += __shfl_sync(FULL, g, 31);
+  }
+}
+
+__global__ void __launch_bounds__(256) k_side_patch(const DeviceBatch d) {
+  const uint32_t t = d.nx0 + blockIdx.x * 256 + threadIdx.x;
+  if (t < d.nx1) { const uint2 e = d.vs_ncig_exc[t]; d.vr_ncig_w[e.x] = (uint16_t)e.y; }
+}
+
 // ------------------------------------------------------------------ K1
 __global__ void __launch_bounds__(256) k_allele_call(const DeviceBatch d) {
   const uint32_t e = d.vr0 + blockIdx.x * blockDim.x + threadIdx.x;
@@ -72,7 +106,7 @@ __global__ void __launch_bounds__(256) k_allele_call(const DeviceBatch d) {
   rd.l_seq = d.vr_lseq[e];
   rd.nv = d.vr_nv[e];
   rd.n_cig = d.vr_ncig[e];
-  const uint8_t* bases = d.bases + (size_t)d.vr_seq_off[e] * 16;
+  const uint8_t* bases = d.bases + (size_t)d.vr_seq_off[e];
   const uint32_t* cig = d.cigars + d.vr_cig_off[e];
   const MphCall c = mph_call_read(rd, bases, cig, d.vars, d.mode == 0);
   d.call_S[r] = c.S;
@@ -685,6 +719,8 @@ void launch_read_decode(const DeviceBatch& d, cudaStream_t st) {
   if (d.run1 > d.run0) k_read_decode<<<(d.run1 - d.run0 + 3) / 4, 128, 0, st>>>(d);
   const uint32_t n = (d.sx1 - d.sx0) + (d.fx1 - d.fx0);
   if (n) k_read_patch<<<(n + 255) / 256, 256, 0, st>>>(d);
+  if (d.vrun1 > d.vrun0) k_side_decode<<<(d.vrun1 - d.vrun0 + 3) / 4, 128, 0, st>>>(d);
+  if (d.nx1 > d.nx0) k_side_patch<<<(d.nx1 - d.nx0 + 255) / 256, 256, 0, st>>>(d);
 }
 void launch_allele_call(const DeviceBatch& d, cudaStream_t st) {
   if (d.vr1 > d.vr0) k_allele_call<<<(d.vr1 - d.vr0 + 255) / 256, 256, 0, st>>>(d);
@@ -708,6 +744,6 @@ void launch_compact(const DeviceBatch& d, cudaStream_t st) {
   k_block_scan<<<1, SCAN_THREADS, 0, st>>>(d, nb);
   if (nb) k_scatter<<<nb, SCAN_THREADS, 0, st>>>(d);
 }
-int kernel_launch_count() { return 10; }
+int kernel_launch_count() { return 11; }
 
 }  // namespace mphk

@@ -37,13 +37,21 @@ struct DeviceBatch {
   const uint2* rd_flag_exc = nullptr;    // (read, flags)
   uint32_t run0 = 0, run1 = 0, sx0 = 0, sx1 = 0, fx0 = 0, fx1 = 0;  // the slice's runs / exceptions
   // compact side table: the reads K1 has work for
-  const uint32_t* vr_read = nullptr;
+  const uint32_t* vr_read = nullptr;     // rebuilt on the device by K0 (k_side_decode) from the 9-byte bus form below
   const uint32_t* vr_vlo = nullptr;
-  const uint32_t* vr_seq_off = nullptr;
+  const uint32_t* vr_seq_off = nullptr;  // byte offset of the packed read record in `bases`
   const uint32_t* vr_cig_off = nullptr;
-  const uint16_t* vr_lseq = nullptr;
+  const uint16_t* vr_lseq = nullptr;     // shipped as they are
   const uint16_t* vr_ncig = nullptr;
   const uint8_t* vr_nv = nullptr;
+  uint32_t* vr_read_w = nullptr; uint32_t* vr_vlo_w = nullptr; uint32_t* vr_seq_off_w = nullptr; uint32_t* vr_cig_off_w = nullptr; uint16_t* vr_ncig_w = nullptr;
+  const uint16_t* vs_read_d = nullptr;   // per entry: read index - previous entry's (0 at the head of a run)
+  const uint8_t* vs_vlo_d = nullptr;     // per entry: first-variant index - previous entry's
+  const uint16_t* vs_size = nullptr;     // per entry: bytes of its packed read record
+  const uint8_t* vs_ncig = nullptr;      // per entry: CIGAR operations shipped (0 = one M over the read), 255 = see vs_ncig_exc
+  const MphSideRun* vs_runs = nullptr;   // where the running sums restart
+  const uint2* vs_ncig_exc = nullptr;    // (entry, CIGAR operations)
+  uint32_t vrun0 = 0, vrun1 = 0, nx0 = 0, nx1 = 0;  // the slice's runs / exceptions
   // per read, expanded by K1 (read_nv is zeroed first; read_vlo / read_vr are only defined where read_nv != 0)
   uint32_t* read_vlo = nullptr;
   uint8_t* read_nv = nullptr;

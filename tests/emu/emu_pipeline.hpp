@@ -35,7 +35,7 @@ inline std::vector<MphCall> allele_calls(const Batch& b, bool use_qual) {
   for (size_t e = 0; e < b.vr_read.size(); ++e) {
     const uint32_t r = b.vr_read[e];
     MphRead rd{b.read_start[r], b.read_end[r], b.vr_vlo[e], b.vr_lseq[e], b.vr_nv[e], b.vr_ncig[e]};
-    calls[r] = mph_call_read(rd, b.bases.data() + size_t(b.vr_seq_off[e]) * 16, b.cigars.data() + b.vr_cig_off[e], b.vars.data(), use_qual);
+    calls[r] = mph_call_read(rd, b.bases.data() + size_t(b.vr_seq_off[e]), b.cigars.data() + b.vr_cig_off[e], b.vars.data(), use_qual);
   }
   return calls;
 }

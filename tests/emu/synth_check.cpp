@@ -33,6 +33,12 @@ int main(int argc, char** argv) {
       std::vector<uint8_t> df;
       mph::decode_reads(b, ds, de, df);
       if (ds != b.read_start || de != b.read_end || df != b.read_flags) { fprintf(stderr, "read encoding does not round-trip\n"); return 4; }
+      std::vector<uint32_t> vr, vv, vso, vco;
+      std::vector<uint16_t> vn;
+      mph::decode_side_table(b, vr, vv, vso, vco, vn);
+      bool ok = vr == b.vr_read && vv == b.vr_vlo && vso == b.vr_seq_off && vn == b.vr_ncig;
+      for (size_t e = 0; ok && e < vn.size(); ++e) ok = vn[e] == 0 || vco[e] == b.vr_cig_off[e];
+      if (!ok) { fprintf(stderr, "side-table encoding does not round-trip\n"); return 4; }
     }
     mph::PhaseRaw raw = mphemu::phase(b);
     if (raw.err) { fprintf(stderr, "device error bits %u\n", raw.err); return 3; }
