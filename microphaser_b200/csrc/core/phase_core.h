@@ -122,7 +122,8 @@ MPH_HD int mph_read_pos(const uint32_t* cig, uint32_t n_cig, uint32_t l_seq, uin
 
 // Packed read record (16-B aligned in the `bases` arena), what K1 needs of one alignment:
 //   byte 0  format: bit 0 = bases are 2-bit codes (A C G T only; else BAM 4-bit codes), bit 1 = the positions with
-//           qual < 10 are a list (else a bitmask)
+//           qual < 10 are a list (else a bitmask); bit 2 = column record of an ungapped read (one byte per variant
+//           inside the read, see mph_call_read) - then nothing else follows
 //   byte 1  list length (format bit 1)
 //   then    the bases: ceil(l_seq/4) or ceil(l_seq/2) B, first base in the high bits
 //   then    the low-quality positions: `list length` bytes (one position each), or ceil(l_seq/8) B with bit i <=> base i
@@ -155,6 +156,21 @@ MPH_HD MphCall mph_call_read(const MphRead& r, const uint8_t* bases, const uint3
   c.B = 0;
   const uint32_t nv = r.nv;
   if (nv == 0) return c;
+  if (bases[0] & 4u) {
+    // column record of an ungapped read: byte 1 + j holds the base at variant j's position (BAM 4-bit code), bit 4 =
+    // its quality is below 10, bit 5 = the position is inside the read. Query position = reference offset here, so the
+    // quality test (:82-84,99-101) and read_pos (:106-110) index the same base; insertions / deletions need a CIGAR
+    // operation of their kind (:120-135), which a single-M read does not have.
+    for (uint32_t j = 0; j < nv; ++j) {
+      const MphVar v = vars[r.vlo + j];
+      if (v.kind != MPH_SNV) continue;
+      const uint8_t col = bases[1 + j];
+      if (!(col & 32u)) continue;
+      if (use_qual && (col & 16u)) c.B |= (uint64_t)1 << j;
+      else if ((col & 15u) == v.alt4) c.S |= (uint64_t)1 << j;
+    }
+    return c;
+  }
   for (uint32_t j = 0; j < nv; ++j) {
     const MphVar v = vars[r.vlo + j];
     bool sup = false;

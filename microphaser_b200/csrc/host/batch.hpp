@@ -292,11 +292,35 @@ class Packer {
     std::map<uint32_t, std::vector<uint32_t>> big_groups;  // first read -> third and later reads of its group
     const size_t partners_mark = b_.partner_a.size();
     const size_t bases_mark = b_.bases.size(), cigars_mark = b_.cigars.size(), vr_mark = b_.vr_read.size();
+    bool full_records = false;  // set for the re-pack of a gene with replayed transcripts: the replay looks at columns outside a read's own variants
     auto add_vr = [&](uint32_t idx, uint32_t vlo, uint32_t nv, const HostRead& r) {
-      // packed record (core/phase_core.h), 16-B aligned: 2-bit bases when the read has only A C G T, the positions with
-      // qual < 10 as a short list when there are few of them (the normal mode never tests qualities: empty list)
       const size_t off = b_.bases.size();  // byte offset: the records are not aligned (K1 reads them byte-wise)
       static const bool force_wide_format = getenv("MPH_PACK_WIDE") != nullptr;  // test hook: 4-bit bases + bitmask for every read
+      const bool single_m_read = r.n_cigar == 1 && (r.cigar[0] & 15u) == 0 && (r.cigar[0] >> 4) == r.l_seq;
+      if (single_m_read && !full_records && !force_wide_format) {
+        // column record (core/phase_core.h, format bit 2): an ungapped read's reference-coordinate map is the identity shift,
+        // so the only bytes K1 can ever look at are the bases at the variant positions inside it: one byte per variant
+        // (BAM 4-bit base, bit 4 = quality < 10, bit 5 = the position is inside the read) instead of the whole read
+        b_.bases.resize(off + 1 + nv, 0);
+        uint8_t* rec = &b_.bases[off];
+        rec[0] = 4;
+        for (uint32_t j = 0; j < nv; ++j) {
+          const uint32_t rel = b_.vars[vlo + j].pos - r.start;
+          if (rel >= r.l_seq) continue;
+          const uint8_t c4 = (rel & 1u) ? (r.seq4[rel >> 1] & 15u) : (r.seq4[rel >> 1] >> 4);
+          rec[1 + j] = uint8_t(c4 | ((b_.mode == 0 && r.qual[rel] < 10) ? 16u : 0u) | 32u);
+        }
+        b_.vr_read.push_back(idx);
+        b_.vr_vlo.push_back(vlo);
+        b_.vr_seq_off.push_back(uint32_t(off));
+        b_.vr_lseq.push_back(uint16_t(r.l_seq));
+        b_.vr_nv.push_back(uint8_t(nv));
+        b_.vr_cig_off.push_back(0);
+        b_.vr_ncig.push_back(0);
+        return;
+      }
+      // packed record (core/phase_core.h): 2-bit bases when the read has only A C G T, the positions with
+      // qual < 10 as a short list when there are few of them (the normal mode never tests qualities: empty list)
       bool acgt = !force_wide_format;
       for (uint32_t i = 0; i < r.l_seq && acgt; ++i) {
         const uint8_t c4 = (i & 1u) ? (r.seq4[i >> 1] & 15u) : (r.seq4[i >> 1] >> 4);
@@ -668,6 +692,7 @@ class Packer {
       b_.vr_lseq.resize(vr_mark); b_.vr_ncig.resize(vr_mark); b_.vr_nv.resize(vr_mark);
       uint32_t idx = gm.read_lo;
       size_t q = 0;
+      full_records = true;
       for (auto& r : reads) {
         add_vr(idx, read_vrange[q].first, read_vrange[q].second, r);
         ++idx;
