@@ -562,3 +562,288 @@ MPH_HD void mph_rc_merged_id(const MphRecCtx& c, MphRec* r, const uint8_t* mt, u
   const uint32_t t0 = c.tx_id_off[r->tx], tlen = c.tx_id_off[r->tx + 1] - t0;
   r->id64 = mph_record_id64(mt, window_len, c.tx_id_bytes + t0, tlen, (uint32_t)r->id64);
 }
+
+// ================================================================================================ `normal` mode
+// Record emission of the healthy-peptidome pass (reference src/normal_microphasing.rs; line numbers below refer to that
+// file) for device-class transcripts. Every window of a non-short exon writes a record per haplotype that does not start
+// (forward) / end (reverse) with a stop codon (:493-507,629-644); a window whose haplotypes all stop ends the transcript
+// (:1128-1131: the main-ORF entry is removed unconditionally). A junction merge (:1145-1250) slides over prev + cur of
+// every pair of listed haplotypes and writes every window, not only the mutated ones.
+enum {
+  MPH_RC_NORMAL = 16,  // record of the normal mode: 0-based positions, sites limited to the visited variants, 32-bit counts of merged records in `keep`
+  MPH_RC_REFSEQ = 32,  // the sequence is the reference window itself: seq_off indexes the batch's reference arena (nothing is shipped)
+};
+
+typedef struct {
+  const uint32_t* win_depth;          // per window: depth | (plain window begins / ends with a stop codon) << 31
+  const unsigned long long* win_id;   // per window: id of the reference window
+} MphNrmCtx;
+
+MPH_HD uint32_t mph_nrc_nkeys(const MphRecCtx& c, uint32_t widx, uint32_t nv) {
+  if (nv == 0) return 1;
+  return mph_rc_nkeys(c.win_out[widx]);
+}
+
+// key q of a window; for a window without variants the single reference haplotype is described by `plain`
+MPH_HD MphKeyRef mph_nrc_key(const MphRecCtx& c, const MphNrmCtx& n, const MphGeom& g, uint32_t widx, uint32_t nv, uint32_t q, MphHap* plain) {
+  if (nv == 0) {
+    const uint32_t wd = n.win_depth[widx];
+    plain->flags = (wd >> 31) ? MPH_NF_STOP : 0u;
+    plain->seq_len = (uint16_t)(g.e - g.s);
+    plain->germ_len = 0; plain->n_var = 0; plain->n_som = 0; plain->n_prof = 0; plain->brk = 0; plain->seq_off = 0xFFFFFFFFu; plain->profile = 0; plain->id64 = 0;
+    MphKeyRef k;
+    k.hap = 0; k.count = wd & 0x7FFFFFFFu; k.h = plain;
+    return k;
+  }
+  return mph_rc_key(c, c.win_out[widx], widx, q);
+}
+
+// number of haplotypes of the window that are written / listed (n_res of print_haplotypes, :629-644); MPH_E_* bits in *err
+MPH_HD uint32_t mph_nrc_window_count(const MphRecCtx& c, const MphNrmCtx& n, const MphSegment& sg, uint32_t i, uint32_t widx, uint32_t* seq_bytes,
+                                     uint32_t* err) {
+  const uint32_t k = sg.k_first + i * sg.k_stride;
+  const MphGeom g = mph_geom(sg, k);
+  const uint32_t va = mph_var_lb(c.vars, sg.var_lo, sg.var_hi, g.s);
+  const uint32_t nv = mph_var_lb(c.vars, va, sg.var_hi, g.e) - va;
+  const uint32_t nk = mph_nrc_nkeys(c, widx, nv);
+  uint32_t cnt = 0, bytes = 0;
+  for (uint32_t q = 0; q < nk; ++q) {
+    MphHap plain;
+    const MphKeyRef key = mph_nrc_key(c, n, g, widx, nv, q, &plain);
+    if (key.h->flags & MPH_NF_REFRANGE) *err |= MPH_E_REF_RANGE;
+    if ((key.h->flags & MPH_NF_STOP) && g.spos != 2) continue;
+    if (key.h->flags & MPH_NF_OVERFLOW) *err |= MPH_E_SEQ_SLOT;
+    ++cnt;
+    if (key.hap != 0) bytes += key.h->seq_len;
+  }
+  *seq_bytes = bytes;
+  return cnt;
+}
+
+// sequence of one listed haplotype (`seq` of print_haplotypes): the reference window or the assembled bytes
+MPH_HD void mph_nrc_seq(const MphRecCtx& c, const MphSegment& sg, const MphGeom& g, const MphKeyRef& key, const uint8_t** p, uint32_t* len, uint32_t* err) {
+  if (key.hap == 0) {
+    *p = c.ref + sg.ref_off + (g.s - sg.ref_pos0);
+    *len = g.e - g.s;
+    if (g.s < sg.ref_pos0 || (uint64_t)g.e - sg.ref_pos0 > sg.ref_len) { *err |= MPH_E_REF_RANGE; *len = 0; }
+    return;
+  }
+  if (!(key.h->flags & MPH_NF_SEQ)) { *err |= MPH_E_INTERNAL; *p = c.ref; *len = 0; return; }
+  *p = c.seq + key.h->seq_off;
+  *len = key.h->seq_len < c.seq_cap ? key.h->seq_len : c.seq_cap;
+}
+
+// writes the window's records; returns their number (= mph_nrc_window_count)
+MPH_HD uint32_t mph_nrc_window_emit(const MphRecCtx& c, const MphNrmCtx& n, const MphSegment& sg, uint32_t i, uint32_t widx, MphRec* recs,
+                                    uint8_t* seq_arena, uint32_t seq_base, uint32_t* err) {
+  const uint32_t k = sg.k_first + i * sg.k_stride;
+  const MphGeom g = mph_geom(sg, k);
+  const bool rev = (sg.flags & MPH_SF_REVERSE) != 0;
+  const uint32_t va = mph_var_lb(c.vars, sg.var_lo, sg.var_hi, g.s);
+  const uint32_t nv = mph_var_lb(c.vars, va, sg.var_hi, g.e) - va;
+  const uint32_t nk = mph_nrc_nkeys(c, widx, nv);
+  const uint32_t depth = n.win_depth[widx] & 0x7FFFFFFFu;
+  uint32_t cnt = 0, pos = seq_base;
+  for (uint32_t q = 0; q < nk; ++q) {
+    MphHap plain;
+    const MphKeyRef key = mph_nrc_key(c, n, g, widx, nv, q, &plain);
+    const MphHap& h = *key.h;
+    if ((h.flags & MPH_NF_STOP) && g.spos != 2) continue;
+    const uint8_t* sp;
+    uint32_t sl;
+    mph_nrc_seq(c, sg, g, key, &sp, &sl, err);
+    const bool insertion = (h.flags & MPH_NF_INSERTION) != 0;
+    const uint32_t twl = sl < sg.ewl ? sl : sg.ewl;
+    // peptide_sequence column (:485-492) and FASTA line (:629-644): both start at `a`
+    uint32_t a = 0, neo_b, mt_b;
+    if (g.spos == 1) { a = g.gap; neo_b = mt_b = sl; if (a > sl) { *err |= MPH_E_SLICE; a = sl; } }
+    else if (g.spos == 0) { neo_b = insertion ? sl : twl; mt_b = sg.ewl; if (sg.ewl > sl) { *err |= MPH_E_SLICE; mt_b = sl; } }
+    else { neo_b = sl; mt_b = 0; }
+    const uint32_t stored = (neo_b > mt_b ? neo_b : mt_b) - a;
+    if (stored > 255) { *err |= MPH_E_SEQ_SLOT; }
+    MphRec r;
+    r.id64 = key.hap == 0 ? (uint64_t)n.win_id[widx] : h.id64;
+    if (key.hap != 0 && !(h.flags & MPH_NF_ID)) *err |= MPH_E_INTERNAL;
+    r.freq = (double)key.count / (double)depth;  // NaN without observations (:397)
+    r.tx = sg.tx;
+    r.offset = g.s;
+    r.depth = depth;
+    r.var_ref = va;
+    r.keep = 0xFFFFFFFFu;
+    r.profile = h.profile;
+    r.n_prof = nv ? h.n_prof : 0;
+    r.n_win = (uint8_t)nv;
+    r.nvar = h.n_var;
+    r.nsomatic = h.n_som;
+    {
+      const uint32_t lim = nv < r.n_prof ? nv : r.n_prof;  // sites are counted while the walk produced a profile entry (:509-560)
+      uint32_t ns = 0, nss = 0;
+      mph_rc_sites(c.vars, va, lim, &ns, &nss);
+      r.nsites = (uint8_t)ns;
+      r.nsomsites = (uint8_t)nss;
+    }
+    r.flags = (uint8_t)(MPH_RC_NORMAL | (g.spos != 2 ? MPH_RC_HAS_MT : 0) | (rev ? MPH_RC_REVERSE : 0));
+    r.rank = 0;
+    r.neo_len = (uint8_t)(neo_b - a);
+    r.mt_len = (uint8_t)(mt_b > a ? mt_b - a : 0u);
+    r.norm_len = r.wt_len = 0;
+    r.aux = 0xFFFFFFFFu;
+    if (key.hap == 0) {
+      r.flags |= MPH_RC_REFSEQ;
+      r.seq_off = sg.ref_off + (g.s - sg.ref_pos0) + a;
+    } else {
+      r.seq_off = pos;
+      for (uint32_t t = 0; t < stored && stored <= 255; ++t) seq_arena[pos + t] = sp[a + t];
+      pos += stored <= 255 ? stored : 0u;
+    }
+    recs[cnt++] = r;
+  }
+  return cnt;
+}
+
+// all haplotypes of the window stop (n_res == 0): the transcript ends here
+MPH_HD bool mph_nrc_window_stops(const MphRecCtx& c, const MphNrmCtx& n, const MphSegment& sg, uint32_t i, uint32_t widx) {
+  uint32_t bytes = 0, err = 0;
+  return mph_nrc_window_count(c, n, sg, i, widx, &bytes, &err) == 0;
+}
+
+// One listed haplotype for the merge (HaplotypeSeq :182-186): its full sequence and the counts of its record.
+typedef struct {
+  const uint8_t* seq;
+  uint32_t len;
+  double freq;
+  uint32_t offset, depth, var_ref;
+  uint64_t profile;
+  uint32_t nvar, nsomatic;
+  uint8_t n_prof, n_win, nsites, nsomsites;
+} MphNrmEntry;
+
+// the a-th listed haplotype of a window (haplotypes that stop are not listed); returns false past the end
+MPH_HD bool mph_nrc_entry(const MphRecCtx& c, const MphNrmCtx& n, const MphSegment& sg, uint32_t i, uint32_t widx, uint32_t a, MphNrmEntry* en,
+                          MphHap* plain, uint32_t* err) {
+  const uint32_t k = sg.k_first + i * sg.k_stride;
+  const MphGeom g = mph_geom(sg, k);
+  const uint32_t va = mph_var_lb(c.vars, sg.var_lo, sg.var_hi, g.s);
+  const uint32_t nv = mph_var_lb(c.vars, va, sg.var_hi, g.e) - va;
+  const uint32_t nk = mph_nrc_nkeys(c, widx, nv);
+  const uint32_t depth = n.win_depth[widx] & 0x7FFFFFFFu;
+  uint32_t seen = 0;
+  for (uint32_t q = 0; q < nk; ++q) {
+    const MphKeyRef key = mph_nrc_key(c, n, g, widx, nv, q, plain);
+    if ((key.h->flags & MPH_NF_STOP) && g.spos != 2) continue;
+    if (seen++ != a) continue;
+    mph_nrc_seq(c, sg, g, key, &en->seq, &en->len, err);
+    en->freq = (double)key.count / (double)depth;
+    en->offset = g.s;
+    en->depth = depth;
+    en->var_ref = va;
+    en->profile = key.h->profile;
+    en->n_prof = nv ? key.h->n_prof : 0;
+    en->n_win = (uint8_t)nv;
+    en->nvar = key.h->n_var;
+    en->nsomatic = key.h->n_som;
+    const uint32_t lim = nv < en->n_prof ? nv : en->n_prof;
+    uint32_t ns = 0, nss = 0;
+    mph_rc_sites(c.vars, va, lim, &ns, &nss);
+    en->nsites = (uint8_t)ns;
+    en->nsomsites = (uint8_t)nss;
+    return true;
+  }
+  return false;
+}
+
+// Junction merge of the normal mode (:1145-1250) for a device-class transcript: `cur` = first window of sj, `prv` = last window
+// of sp. recs == nullptr counts (upper bound, no de-duplication); otherwise fills like mph_rc_merge_t. Only the window's
+// bytes are the key here ((splice_offset, out_seq), :1216), and every window is written.
+template <class Ops>
+MPH_HD uint32_t mph_nrc_merge_t(const MphRecCtx& c, const MphNrmCtx& n, const MphSegment& sp, const MphSegment& sj, uint32_t window_len, MphRec* recs,
+                                MphRecSrc* aux, uint8_t* seq, uint32_t aux_base, uint32_t seq_base, uint32_t cap, uint32_t* err) {
+  const bool fwd = (sj.flags & MPH_SF_REVERSE) == 0;
+  const uint32_t w_cur = sj.win_base, i_prv = sp.n_win - 1, w_prv = sp.win_base + i_prv;
+  const uint64_t wl = window_len;
+  uint32_t n_out = 0;
+  for (uint32_t a = 0;; ++a) {
+    MphNrmEntry record;  // from first_hap_vec: forward = current window, reverse = previous exon's last window
+    MphHap plain_a;
+    if (!(fwd ? mph_nrc_entry(c, n, sj, 0, w_cur, a, &record, &plain_a, err) : mph_nrc_entry(c, n, sp, i_prv, w_prv, a, &record, &plain_a, err))) break;
+    for (uint32_t b = 0;; ++b) {
+      MphNrmEntry prev;
+      MphHap plain_b;
+      if (!(fwd ? mph_nrc_entry(c, n, sp, i_prv, w_prv, b, &prev, &plain_b, err) : mph_nrc_entry(c, n, sj, 0, w_cur, b, &prev, &plain_b, err))) break;
+      const uint64_t jn = (uint64_t)prev.len + record.len;  // joined = prev.sequence + record.sequence
+      uint64_t splice_offset = 3, end_offset = 3;           // exon_rest >= 3 and not the exon's last window in this class
+      if (jn < 2 * wl) { if (fwd) splice_offset = 0; else end_offset = 0; }
+      uint32_t guard = 0;
+      while (splice_offset + wl <= jn - end_offset) {  // u64: wraps like the reference's usize
+        if (++guard > 4096 || splice_offset + wl > jn) { *err |= MPH_E_SLICE; break; }
+        if (!recs) { ++n_out; splice_offset += 3; continue; }
+        typename Ops::Win win;
+        Ops::load(win, prev.seq, prev.len, record.seq, splice_offset, prev.seq, prev.len, record.seq, splice_offset, (uint32_t)wl);
+        uint32_t slot = 0;
+        for (; slot < n_out; ++slot) {
+          if (recs[slot].aux != (uint32_t)splice_offset) continue;  // aux holds the key's offset until the final pass
+          if (Ops::equals_slot(win, seq + seq_base + (size_t)slot * MPH_RC_SEQ_SLOT, (uint32_t)wl)) break;
+        }
+        double old_freq = 0.0;
+        if (slot == n_out) {
+          if (n_out >= cap) { *err |= MPH_E_REC_OVERFLOW; return n_out; }
+          ++n_out;
+          Ops::store(win, seq + seq_base + (size_t)slot * MPH_RC_SEQ_SLOT, (uint32_t)wl);
+          Ops::sync();
+        } else {
+          old_freq = recs[slot].freq;
+        }
+        // IDRecord::update (:105-146): self = prev_record, rec = record; then add_freq (:148-179) with the slot's old frequency
+        MphRec r;
+        r.id64 = splice_offset;  // hashed afterwards (mph_rc_merged_id)
+        r.tx = sj.tx;
+        r.offset = (uint32_t)(splice_offset + prev.offset);
+        r.depth = prev.depth;
+        uint32_t nvar = prev.nvar + record.nvar, nsom = prev.nsomatic + record.nsomatic;
+        const uint32_t new_nvar = old_freq > 0.0 ? nvar - 1u : nvar;  // u32 arithmetic wraps like the release build
+        nsom = new_nvar < nsom ? nsom - 1u : nsom;
+        r.freq = prev.freq * record.freq + old_freq;
+        r.nvar = (uint8_t)new_nvar;
+        r.nsomatic = (uint8_t)nsom;
+        r.keep = new_nvar;  // the 32-bit counts of a merged normal-mode record: nvar here, nsomatic in the second source's `keep`
+        r.nsites = (uint8_t)(prev.nsites + record.nsites);
+        r.nsomsites = (uint8_t)(prev.nsomsites + record.nsomsites);
+        r.seq_off = seq_base + slot * MPH_RC_SEQ_SLOT;
+        r.var_ref = prev.var_ref; r.profile = prev.profile; r.n_prof = prev.n_prof; r.n_win = prev.n_win;
+        r.flags = (uint8_t)(MPH_RC_NORMAL | MPH_RC_MERGED | MPH_RC_HAS_MT | (fwd ? 0 : MPH_RC_REVERSE));
+        r.rank = 0;
+        r.neo_len = r.mt_len = (uint8_t)wl;
+        r.norm_len = r.wt_len = 0;
+        r.aux = (uint32_t)splice_offset;
+        if (Ops::leader()) recs[slot] = r;
+        MphRecSrc x;
+        x.profile = record.profile; x.var_ref = record.var_ref; x.keep = nsom; x.n_prof = record.n_prof; x.n_win = record.n_win;
+        for (int z = 0; z < 6; ++z) x.pad[z] = 0;
+        if (Ops::leader()) aux[slot] = x;
+        Ops::sync();
+        splice_offset += 3;
+      }
+    }
+  }
+  if (recs) {
+    // ranks in output_map order: (splice_offset, out_seq) (:1216-1222)
+    for (uint32_t x = 0; x < n_out; ++x) {
+      uint32_t rank = 0;
+      const uint8_t* sx = seq + seq_base + (size_t)x * MPH_RC_SEQ_SLOT;
+      for (uint32_t y = 0; y < n_out; ++y) {
+        if (y == x) continue;
+        const uint8_t* sy = seq + seq_base + (size_t)y * MPH_RC_SEQ_SLOT;
+        bool less;
+        if (recs[y].aux != recs[x].aux) less = recs[y].aux < recs[x].aux;
+        else less = Ops::slot_less(sy, sx, (uint32_t)wl);
+        if (less) ++rank;
+      }
+      if (Ops::leader()) recs[x].rank = (uint8_t)rank;
+    }
+    Ops::sync();
+    if (Ops::leader())
+      for (uint32_t x = 0; x < n_out; ++x) recs[x].aux = aux_base + x;
+    Ops::sync();
+  }
+  return n_out;
+}

@@ -595,7 +595,7 @@ class Packer {
       // device class (core/record_core.h): the records of this transcript are built by the record kernels
       {
         static const bool no_devrec = getenv("MPH_NO_DEVREC") != nullptr;  // test hook: everything through the host residue
-        bool dev = b_.mode == 0 && !no_devrec && !tx_replay && !has_fs && need <= 240 && wl <= 32 && tm.seg_hi > tm.seg_lo &&
+        bool dev = !no_devrec && !tx_replay && !has_fs && need <= 240 && wl <= 32 && tm.seg_hi > tm.seg_lo &&
                    size_t(tm.seg_hi - tm.seg_lo) == size_t(exon_count);  // no exon was skipped (:1043-1048)
         for (uint32_t si = tm.seg_lo; dev && si < tm.seg_hi; ++si) {
           const MphSegment& sg = b_.segs[si];

@@ -133,10 +133,13 @@ inline int run_normal(int argc, char** argv, const PhaseFn& phase) {
   if (raw.err & MPH_E_REF_RANGE) throw Fatal("index out of bounds: refseq");
   if (raw.err & MPH_E_VARS_PER_WINDOW) throw Unsupported("more than 32 variants in one window / 64 in one read");
   if (raw.err) throw std::runtime_error("device error bits " + std::to_string(raw.err));
+  if (raw.err & MPH_E_SLICE) throw Fatal("slice index out of range");
+  if (raw.err & MPH_E_SEQ_SLOT) throw Unsupported("assembled haplotype longer than the sequence slot");
   ResidueNormal res(b, raw);
-  std::vector<OutRecord> recs;
+  std::vector<OutRecord> host_recs;
   ResidueStats st;
-  res.run(0, uint32_t(b.txs.size()), recs, st);
+  res.run(0, uint32_t(b.txs.size()), host_recs, st);
+  const std::vector<OutRecord> recs = ordered_records(b, raw, std::move(host_recs));
   write_records(b, recs, o);
   fclose(o.tsv);
   fflush(stdout);

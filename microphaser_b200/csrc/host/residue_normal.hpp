@@ -16,7 +16,11 @@ class ResidueNormal {
   ResidueNormal(const Batch& b, const PhaseRaw& raw) : b_(b), raw_(raw) {}
 
   void run(uint32_t tx_lo, uint32_t tx_hi, std::vector<OutRecord>& out, ResidueStats& stats) {
-    for (uint32_t t = tx_lo; t < tx_hi; ++t) run_transcript(t, out, stats);
+    for (uint32_t t = tx_lo; t < tx_hi; ++t) {
+      const TxMeta& tm = b_.txs[t];
+      if (tm.seg_hi > tm.seg_lo && (b_.segs[tm.seg_lo].flags & MPH_SF_DEVREC)) continue;  // built on the device (core/record_core.h)
+      run_transcript(t, out, stats);
+    }
   }
 
  private:

@@ -105,6 +105,9 @@ inline PhaseRaw phase_normal(const Batch& b) {
   ReplayStage rp;
   run_replay(b, calls, per_read, 1, raw, rp);
   std::vector<uint8_t> seqbuf(b.seq_cap);
+  // device-class transcripts (core/record_core.h): full per-window arrays, as on the device
+  std::vector<MphWinOut> d_win_out(b.n_windows);
+  std::vector<MphHap> d_hap0(b.n_windows);
   for (const MphChunk& ch : b.chunks) {
     const MphSegment& sg = b.segs[ch.seg];
     const bool rev = sg.flags & MPH_SF_REVERSE;
@@ -201,12 +204,68 @@ inline PhaseRaw phase_normal(const Batch& b) {
         raw.hapx.push_back(hx);
         ++wo.n_extra;
       }
+      if (sg.flags & MPH_SF_DEVREC) {
+        d_win_out[widx] = wo;
+        d_hap0[widx] = h0;
+        continue;
+      }
       raw.iw.push_back(widx);
       raw.iw_out.push_back(wo);
       raw.iw_hap0.push_back(h0);
     }
   }
   if (!b.replay.empty()) raw.iw_voff.resize(raw.iw.size(), 0xFFFFFFFFu);
+  // record kernels of the normal mode: first window whose haplotypes all stop, then the records of the live windows
+  {
+    MphRecCtx c;
+    c.segs = b.segs.data(); c.vars = b.vars.data(); c.ref = b.ref.data(); c.win_out = d_win_out.data(); c.hap0 = d_hap0.data();
+    c.hist = raw.hist.data(); c.hapx = raw.hapx.data(); c.seq = raw.seq.data(); c.seq_cap = b.seq_cap;
+    c.tx_id_bytes = b.tx_id_bytes.data(); c.tx_id_off = b.tx_id_off.data();
+    MphNrmCtx n;
+    n.win_depth = raw.win_depth.data();
+    n.win_id = reinterpret_cast<const unsigned long long*>(raw.win_id.data());
+    std::vector<uint32_t> tx_stop(b.txs.size(), 0xFFFFFFFFu);
+    for (const MphSegment& sg : b.segs) {
+      if (!(sg.flags & MPH_SF_DEVREC)) continue;
+      for (uint32_t i = 0; i < sg.n_win; ++i)
+        if (mph_nrc_window_stops(c, n, sg, i, sg.win_base + i)) tx_stop[sg.tx] = std::min(tx_stop[sg.tx], sg.win_base + i);
+    }
+    uint32_t err = 0;
+    for (size_t si = 0; si < b.segs.size(); ++si) {
+      const MphSegment& sg = b.segs[si];
+      if (!(sg.flags & MPH_SF_DEVREC)) continue;
+      for (uint32_t i = 0; i < sg.n_win; ++i) {
+        const uint32_t widx = sg.win_base + i;
+        if (widx > tx_stop[sg.tx]) break;
+        raw.dev_windows += 1;
+        raw.dev_read_windows += raw.win_depth[widx] & 0x7FFFFFFFu;
+        uint32_t bytes = 0;
+        const uint32_t cnt = mph_nrc_window_count(c, n, sg, i, widx, &bytes, &err);
+        const size_t r0 = raw.recs.size(), s0 = raw.rec_seq.size();
+        raw.recs.resize(r0 + cnt);
+        raw.rec_seq.resize(s0 + bytes);
+        if (mph_nrc_window_emit(c, n, sg, i, widx, raw.recs.data() + r0, raw.rec_seq.data(), uint32_t(s0), &err) != cnt) err |= MPH_E_INTERNAL;
+        const bool junction = i == 0 && !(sg.flags & MPH_SF_FIRST_EXON) && widx < tx_stop[sg.tx] && si > 0 && b.segs[si - 1].tx == sg.tx;
+        if (junction) {
+          const MphSegment& sp = b.segs[si - 1];
+          const uint32_t ub = mph_nrc_merge_t<MphSerialOps>(c, n, sp, sg, b.window_len, nullptr, nullptr, nullptr, 0, 0, 0, &err);
+          if (ub) {
+            std::vector<MphRec> mr(ub);
+            std::vector<MphRecSrc> ma(ub);
+            const size_t sb = raw.rec_seq.size(), ab = raw.rec_aux.size();
+            raw.rec_seq.resize(sb + size_t(ub) * MPH_RC_SEQ_SLOT, 0);
+            const uint32_t nm = mph_nrc_merge_t<MphSerialOps>(c, n, sp, sg, b.window_len, mr.data(), ma.data(), raw.rec_seq.data(), uint32_t(ab), uint32_t(sb), ub, &err);
+            for (uint32_t x = 0; x < nm; ++x) mph_rc_merged_id(c, &mr[x], raw.rec_seq.data() + mr[x].seq_off, b.window_len);
+            raw.rec_aux.insert(raw.rec_aux.end(), ma.begin(), ma.begin() + nm);
+            const size_t rb = raw.recs.size();
+            raw.recs.resize(rb + nm);
+            for (uint32_t x = 0; x < nm; ++x) raw.recs[rb + mr[x].rank] = mr[x];
+          }
+        }
+      }
+    }
+    raw.err |= err;
+  }
   return raw;
 }
 

@@ -44,7 +44,7 @@ int main(int argc, char** argv) {
     if (raw.err) { fprintf(stderr, "device error bits %u\n", raw.err); return 3; }
     std::vector<mph::OutRecord> recs;
     mph::ResidueStats st;
-    if (mode == 1) { mph::ResidueNormal r(b, raw); r.run(0, uint32_t(b.txs.size()), recs, st); }
+    if (mode == 1) { mph::ResidueNormal r(b, raw); r.run(0, uint32_t(b.txs.size()), recs, st); recs = mph::ordered_records(b, raw, std::move(recs)); }
     else { mph::Residue r(b, raw); r.run(0, uint32_t(b.txs.size()), recs, st); recs = mph::ordered_records(b, raw, std::move(recs)); }
     mph::Outputs o;
     o.fasta = fopen((out + "/out.fa").c_str(), "wb");
