@@ -103,10 +103,11 @@ struct mph_result {
   // what rendering a device-built record needs of the batch
   std::vector<MphVar> vars;
   std::vector<std::string> var_prot;
+  std::vector<uint8_t> ref;  // normal mode: the reference arena (records of reference windows point into it)
 
   RenderCtx ctx_of(const ResultPart& p) const {
     RenderCtx c;
-    c.vars = vars.data(); c.var_prot = &var_prot; c.seq = p.dev_seq.data(); c.aux = p.dev_aux.data();
+    c.vars = vars.data(); c.var_prot = &var_prot; c.seq = p.dev_seq.data(); c.aux = p.dev_aux.data(); c.ref = ref.data();
     return c;
   }
   // calls f(const OutRecord&) for every record of the part in transcript order; device-built ones are rendered on the fly
@@ -309,11 +310,13 @@ void prepare(mph_ctx* c, const mph_batch* mb) {
   c->block_counts.ensure(nw / 1024 + 2);
   c->iw.ensure(nw + 1); c->iw_out.ensure(nw + 1); c->iw_hap0.ensure(nw + 1); c->ovf_list.ensure(nw + 1);
   c->counters.ensure(mphk::CTR_COUNT); c->sums.ensure(3);
-  if (b.mode == 0) {
+  {
     c->win_seg.ensure(nw + 1); c->tx_stop.ensure(b.txs.size() + 1);
     c->rw.ensure(nw + 1); c->rw_stopq.ensure(nw + 1); c->rw_info.ensure(nw + 1); c->rw_mbase.ensure(nw + 1); c->rw_bytes.ensure(nw + 1); c->rw_junc.ensure(b.segs.size() + 1);
     c->rc_blocks.ensure(nw / 256 + 4);  // (the record kernels use 512 windows per block)
-    if (c->recs.cap == 0) { c->recs.ensure(std::max<size_t>(nw / 16, 1 << 14)); c->rec_seq.ensure(c->recs.cap * 64); }
+    // somatic: about one record per 30 windows; normal: every window writes at least one
+    const size_t rec_want = b.mode == 1 ? nw + nw / 4 + (1 << 14) : std::max<size_t>(nw / 16, 1 << 14);
+    if (c->recs.cap < rec_want) { c->recs.ensure(rec_want); c->rec_seq.ensure(std::max<size_t>(c->rec_seq.cap, b.mode == 1 ? rec_want * 8 : rec_want * 64)); }
     if (c->m_recs.cap == 0) { c->m_recs.ensure(1 << 14); c->m_aux.ensure(c->m_recs.cap); c->m_seq.ensure(c->m_recs.cap * MPH_RC_SEQ_SLOT); }
   } c->seg_live.ensure(b.segs.size() + 1);
   if (c->hist.cap == 0) { c->hist.ensure(std::max<size_t>(nw / 2, 1 << 16)); c->hapx.ensure(c->hist.cap); }
@@ -424,7 +427,7 @@ void run_kernels(mph_ctx* c) {
   d.rec_seq = c->rec_seq.p; d.rec_seq_cap = uint32_t(std::min<size_t>(c->rec_seq.cap, 0xFFFFFF00u));
   d.m_recs = c->m_recs.p; d.m_aux = c->m_aux.p; d.m_seq = c->m_seq.p; d.m_cap = uint32_t(std::min<size_t>(c->m_recs.cap, 0x03FFFFFFu));
   CU(cudaMemsetAsync(c->counters.p, 0, mphk::CTR_COUNT * sizeof(uint32_t), c->stream));
-  if (d.mode == 0 && c->stage_tx_hi > c->stage_tx_lo)
+  if (c->stage_tx_hi > c->stage_tx_lo)
     CU(cudaMemsetAsync(c->tx_stop.p + c->stage_tx_lo, 0xFF, size_t(c->stage_tx_hi - c->stage_tx_lo) * sizeof(uint32_t), c->stream));
   CU(cudaEventRecord(c->ev[2], c->stream));  // k1_ms covers the zero-fill below: it is the allele call of the reads without variants
   if (d.r1 > d.r0) {
@@ -602,17 +605,19 @@ void take_device_records(const PhaseRaw& raw, uint32_t tx_lo, uint32_t tx_hi, Re
   part.dev.assign(d0, d1);
   size_t bytes = 0, n_aux = 0;
   for (const MphRec& r : part.dev) {
-    bytes += size_t(std::max(r.neo_len, r.mt_len)) + std::max(r.norm_len, r.wt_len);
+    if (!(r.flags & MPH_RC_REFSEQ)) bytes += size_t(std::max(r.neo_len, r.mt_len)) + std::max(r.norm_len, r.wt_len);
     n_aux += (r.flags & MPH_RC_MERGED) ? 1 : 0;
   }
   part.dev_seq.resize(bytes);
   part.dev_aux.reserve(n_aux);
   size_t pos = 0;
   for (MphRec& r : part.dev) {
-    const size_t n = size_t(std::max(r.neo_len, r.mt_len)) + std::max(r.norm_len, r.wt_len);
-    memcpy(part.dev_seq.data() + pos, raw.rec_seq.data() + r.seq_off, n);
-    r.seq_off = uint32_t(pos);
-    pos += n;
+    if (!(r.flags & MPH_RC_REFSEQ)) {  // (a reference window's bytes stay in the batch's reference arena)
+      const size_t n = size_t(std::max(r.neo_len, r.mt_len)) + std::max(r.norm_len, r.wt_len);
+      memcpy(part.dev_seq.data() + pos, raw.rec_seq.data() + r.seq_off, n);
+      r.seq_off = uint32_t(pos);
+      pos += n;
+    }
     if (r.flags & MPH_RC_MERGED) {
       part.dev_aux.push_back(raw.rec_aux[r.aux]);
       r.aux = uint32_t(part.dev_aux.size() - 1);
@@ -660,6 +665,7 @@ struct ResiduePool {
         if (b.mode == 1) {
           ResidueNormal r(b, *t.raw);
           r.run(t.tx_lo, t.tx_hi, parts[t.part].host, stats[ti]);
+          take_device_records(*t.raw, t.tx_lo, t.tx_hi, parts[t.part]);
         } else {
           Residue r(b, *t.raw);
           r.run(t.tx_lo, t.tx_hi, parts[t.part].host, stats[ti]);
@@ -755,6 +761,7 @@ void phase_stages(mph_ctx* c, const std::vector<Stage>& stages, bool copied, mph
   res->tx_reverse.reserve(b.txs.size());
   res->vars = b.vars;
   res->var_prot = b.var_prot;
+  if (b.mode == 1) res->ref = b.ref;
   for (auto& t : b.txs) {
     res->tx_id.push_back(t.id);
     res->gene_id.push_back(b.genes[t.gene].id);
@@ -816,7 +823,7 @@ void phase_stages(mph_ctx* c, const std::vector<Stage>& stages, bool copied, mph
     c->timing.read_windows = stt.read_windows;
     // statistics: depth summed on the device over the windows the reference reaches (the normal-mode residue visits
     // every window and sums the depth itself)
-    if (b.mode != 1) {
+    {
       std::vector<uint32_t> live(b.segs.size() + 1, 0);
       for (auto& pl : pool.live)
         for (auto& sl : pl) live[sl.first] = sl.second;
@@ -845,7 +852,7 @@ void phase_stages(mph_ctx* c, const std::vector<Stage>& stages, bool copied, mph
   c->timing.windows_enumerated = b.n_windows;
   c->timing.n_interesting = n_iw_total;
   c->timing.n_records = res->size();
-  c->timing.kernel_launches = (uint32_t(mphk::kernel_launch_count()) + (b.replay.empty() ? 0u : 1u) + (b.mode == 0 ? uint32_t(mphk::record_kernel_launch_count()) : 0u)) * uint32_t(ns);
+  c->timing.kernel_launches = (uint32_t(mphk::kernel_launch_count()) + (b.replay.empty() ? 0u : 1u) + uint32_t(mphk::record_kernel_launch_count())) * uint32_t(ns);
   c->timing.n_replay_units = uint32_t(b.replay.size());
   c->timing.total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
   if (timeline) fprintf(stderr, "[mph] call finished at %.2f ms\n", c->timing.total_ms);

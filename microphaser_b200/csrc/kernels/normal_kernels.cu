@@ -15,7 +15,7 @@ namespace {
 // difference arrays (slope and constant); the histogram only needs the reads that support an allele.
 constexpr int KN_LANE_KEYS = 6;
 
-__device__ __forceinline__ void normal_window_out(const DeviceBatch& d, const MphSegment& sg, const MphGeom& g, uint32_t widx, uint32_t nvar,
+__device__ __forceinline__ void normal_window_out(const DeviceBatch& d, const MphSegment& sg, uint32_t seg, const MphGeom& g, uint32_t widx, uint32_t nvar,
                                                   uint32_t depth) {
   MphHap h0;
   const uint32_t err = mph_nrm_plain(sg, g, d.ref, nvar, &h0);
@@ -27,7 +27,10 @@ __device__ __forceinline__ void normal_window_out(const DeviceBatch& d, const Mp
     id = mph_record_id64(d.ref + sg.ref_off + (g.s - sg.ref_pos0), g.e - g.s, d.tx_id_bytes + t0, d.tx_id_off[sg.tx + 1] - t0, g.s);
   }
   d.win_id[widx] = id;
-  d.win_flag[widx] = nvar > 0 ? 1 : 0;
+  // device-class transcripts: the record kernels take every window (they find its segment in win_seg); the host sees none of them
+  const bool devrec = (sg.flags & MPH_SF_DEVREC) != 0;
+  d.win_flag[widx] = nvar > 0 ? (devrec ? 2 : 1) : 0;
+  d.win_seg[widx] = devrec ? seg : NONE;
   if (nvar) d.hap0[widx] = h0;
   raise(d, err);
 }
@@ -50,7 +53,7 @@ __device__ __forceinline__ uint32_t normal_rev_kc(const MphSegment& sg, uint32_t
   return kc;
 }
 
-__device__ void window_hist_warp_normal(const DeviceBatch& d, const MphSegment& sg, uint32_t i, uint32_t code, MphHist* table, int lane) {
+__device__ void window_hist_warp_normal(const DeviceBatch& d, const MphSegment& sg, uint32_t ch_seg, uint32_t i, uint32_t code, MphHist* table, int lane) {
   const bool rev = (sg.flags & MPH_SF_REVERSE) != 0;
   const uint32_t k = sg.k_first + i * sg.k_stride;
   const uint32_t widx = sg.win_base + i;
@@ -145,7 +148,7 @@ __device__ void window_hist_warp_normal(const DeviceBatch& d, const MphSegment& 
     }
     d.win_out[widx] = wo;
     atomicAdd(d.sum_depth, (unsigned long long)depth);
-    normal_window_out(d, sg, g, widx, vb - va, depth);
+    normal_window_out(d, sg, ch_seg, g, widx, vb - va, depth);
   }
   __syncwarp();
 }
@@ -158,7 +161,7 @@ __global__ void __launch_bounds__(K2_WARPS * 32) k_window_hist_wide_normal(const
     const uint32_t code = d.ovf_list[o];
     const MphChunk ch = d.chunks[code >> 5];
     const MphSegment sg = d.segs[ch.seg];
-    window_hist_warp_normal(d, sg, ch.i_first + (code & 31u), code, table[warp], lane);
+    window_hist_warp_normal(d, sg, ch.seg, ch.i_first + (code & 31u), code, table[warp], lane);
   }
 }
 
@@ -353,7 +356,7 @@ __global__ void __launch_bounds__(K2_WARPS * 32) k_window_hist_normal(const Devi
       }
     const uint32_t widx = sg.win_base + i;
     d.win_out[widx] = wo;
-    normal_window_out(d, sg, g, widx, nvar, depth);
+    normal_window_out(d, sg, ch.seg, g, widx, nvar, depth);
   }
   if (ovf) {
     const uint32_t o = atomicAdd(&d.counters[CTR_OVF], 1u);

@@ -273,6 +273,124 @@ __global__ void __launch_bounds__(RC_THREADS) k_rc_emit(const DeviceBatch d) {
   raise(d, err);
 }
 
+// ------------------------------------------------------------------ `normal` mode (src/normal_microphasing.rs)
+// Every window of a device-class transcript writes records, so the kernels run over all windows of the slice (x = w - w0)
+// instead of a compacted list; win_seg[w] names the window's segment (0xFFFFFFFF: host class).
+__device__ __forceinline__ MphRecCtx rec_ctx_normal(const DeviceBatch& d, MphNrmCtx* n) {
+  MphRecCtx c = rec_ctx(d);
+  c.seq = d.seq;  // the normal-mode K3 has one sequence arena (slots of seq_cap bytes)
+  n->win_depth = d.win_depth;
+  n->win_id = d.win_id;
+  return c;
+}
+
+__global__ void __launch_bounds__(RC_THREADS) k_nrc_stop(const DeviceBatch d) {
+  const uint32_t w = d.w0 + blockIdx.x * RC_THREADS + threadIdx.x;
+  if (w >= d.w1) return;
+  const uint32_t si = d.win_seg[w];
+  if (si == NONE) return;
+  const MphSegment& sg = d.segs[si];
+  MphNrmCtx n;
+  const MphRecCtx c = rec_ctx_normal(d, &n);
+  if (mph_nrc_window_stops(c, n, sg, w - sg.win_base, w)) atomicMin(&d.tx_stop[sg.tx], w);
+}
+
+__global__ void __launch_bounds__(RC_THREADS) k_nrc_count(const DeviceBatch d) {
+  const uint32_t x = blockIdx.x * RC_THREADS + threadIdx.x, w = d.w0 + x;
+  uint32_t cnt = 0;
+  if (w < d.w1) {
+    uint32_t bytes = 0;
+    const uint32_t si = d.win_seg[w];
+    if (si != NONE) {
+      const MphSegment& sg = d.segs[si];
+      const uint32_t stop = d.tx_stop[sg.tx];
+      if (w <= stop) {
+        MphNrmCtx n;
+        const MphRecCtx c = rec_ctx_normal(d, &n);
+        const uint32_t i = w - sg.win_base;
+        uint32_t err = 0;
+        cnt = mph_nrc_window_count(c, n, sg, i, w, &bytes, &err);
+        if (cnt > 0xFFFu) { err |= MPH_E_REC_OVERFLOW; cnt = 0; }
+        const bool junction = i == 0 && !(sg.flags & MPH_SF_FIRST_EXON) && w < stop && si > 0 && d.segs[si - 1].tx == sg.tx;
+        if (junction) d.rw_junc[atomicAdd(&d.counters[CTR_NJ], 1u)] = x;
+        raise(d, err);
+      }
+    }
+    d.rw_info[x] = cnt;
+    d.rw_mbase[x] = 0;
+    d.rw_bytes[x] = bytes;
+  }
+  for (int o = 16; o; o >>= 1) cnt += __shfl_down_sync(FULL, cnt, o);
+  if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&d.rc_blocks[blockIdx.x], cnt);
+}
+
+__global__ void __launch_bounds__(RM_WARPS * 32) k_nrc_merge(const DeviceBatch d) {
+  const uint32_t j = blockIdx.x * RM_WARPS + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (j >= d.counters[CTR_NJ]) return;
+  const uint32_t x = d.rw_junc[j], w = d.w0 + x;
+  const uint32_t si = d.win_seg[w];
+  const MphSegment& sg = d.segs[si];
+  const MphSegment& sp = d.segs[si - 1];
+  MphNrmCtx n;
+  const MphRecCtx c = rec_ctx_normal(d, &n);
+  uint32_t err = 0, nm = 0, mbase = 0;
+  const uint32_t ub = mph_nrc_merge_t<MphWarpOps>(c, n, sp, sg, d.window_len, nullptr, nullptr, nullptr, 0, 0, 0, &err);
+  if (ub) {
+    if (lane == 0) mbase = atomicAdd(&d.counters[CTR_MERGE], ub);
+    mbase = __shfl_sync(FULL, mbase, 0);
+    if (mbase + ub <= d.m_cap) {
+      nm = mph_nrc_merge_t<MphWarpOps>(c, n, sp, sg, d.window_len, d.m_recs + mbase, d.m_aux + mbase, d.m_seq, mbase, mbase * MPH_RC_SEQ_SLOT, ub, &err);
+      for (uint32_t z = nm + lane; z < ub; z += 32) d.m_recs[mbase + z].flags = 0;
+    } else {
+      err |= MPH_E_REC_OVERFLOW;
+    }
+  }
+  if (nm > 0xFFFu) { err |= MPH_E_REC_OVERFLOW; nm = 0; }
+  if (lane == 0) {
+    d.rw_info[x] |= nm << 12;
+    d.rw_mbase[x] = mbase;
+    d.rw_bytes[x] += nm * d.window_len;
+    if (nm) atomicAdd(&d.rc_blocks[x / RC_THREADS], nm);
+    raise(d, err);
+  }
+}
+
+__global__ void __launch_bounds__(RC_THREADS) k_nrc_emit(const DeviceBatch d) {
+  const uint32_t x = blockIdx.x * RC_THREADS + threadIdx.x, w = d.w0 + x;
+  const bool live = w < d.w1;
+  const uint32_t info = live ? d.rw_info[x] : 0u;
+  const uint32_t n_own = info & 0xFFFu, nm = info >> 12;
+  uint32_t total;
+  const uint32_t before = block_exclusive(n_own + nm, &total);
+  if (!live || n_own + nm == 0) return;
+  const uint32_t base = d.rc_blocks[blockIdx.x] + before;
+  if (base + n_own + nm > d.rec_cap) { raise(d, MPH_E_REC_OVERFLOW); return; }
+  const uint32_t bytes = d.rw_bytes[x];
+  uint32_t sbase = 0;
+  if (bytes) {
+    sbase = atomicAdd(&d.counters[CTR_RECSEQ], bytes);
+    if (sbase + bytes > d.rec_seq_cap) { raise(d, MPH_E_REC_OVERFLOW); return; }
+  }
+  const MphSegment& sg = d.segs[d.win_seg[w]];
+  MphNrmCtx n;
+  const MphRecCtx c = rec_ctx_normal(d, &n);
+  uint32_t err = 0;
+  const uint32_t wrote = mph_nrc_window_emit(c, n, sg, w - sg.win_base, w, d.recs + base, d.rec_seq, sbase, &err);
+  if (wrote != n_own) err |= MPH_E_INTERNAL;
+  const uint32_t mbase = d.rw_mbase[x], wl = d.window_len;
+  uint32_t spos = sbase + bytes - nm * wl;
+  for (uint32_t m = 0; m < nm; ++m) {
+    MphRec r = d.m_recs[mbase + m];
+    const uint8_t* src = d.m_seq + (size_t)(mbase + m) * MPH_RC_SEQ_SLOT;
+    for (uint32_t t = 0; t < wl; ++t) d.rec_seq[spos + t] = src[t];
+    r.seq_off = spos;
+    spos += wl;
+    d.recs[base + n_own + r.rank] = r;
+  }
+  raise(d, err);
+}
+
 // statistics: windows the reference reaches and the sum of depth over them (K5)
 __global__ void __launch_bounds__(256) k_live_depth2(const DeviceBatch d) {
   const uint32_t chunk = d.c0 + blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -284,8 +402,8 @@ __global__ void __launch_bounds__(256) k_live_depth2(const DeviceBatch d) {
     if (lane < ch.n) {
       const uint32_t i = ch.i_first + lane;
       if (sg.flags & MPH_SF_DEVREC) {
-        if (sg.win_base + i <= d.tx_stop[sg.tx]) { v = d.win_out[sg.win_base + i].depth; nw = 1; }
-      } else if (i < d.seg_live[ch.seg]) {
+        if (sg.win_base + i <= d.tx_stop[sg.tx]) { v = d.mode == 1 ? (d.win_depth[sg.win_base + i] & 0x7FFFFFFFu) : d.win_out[sg.win_base + i].depth; nw = 1; }
+      } else if (d.mode == 0 && i < d.seg_live[ch.seg]) {
         v = d.win_out[sg.win_base + i].depth;
       }
     }
@@ -298,8 +416,18 @@ __global__ void __launch_bounds__(256) k_live_depth2(const DeviceBatch d) {
 }  // namespace
 
 void launch_records(const DeviceBatch& d, cudaStream_t st) {
-  if (d.mode != 0 || d.w1 <= d.w0) return;
+  if (d.w1 <= d.w0) return;
   const uint32_t nb = (d.w1 - d.w0 + RC_THREADS - 1) / RC_THREADS;
+  if (d.mode == 1) {
+    k_nrc_stop<<<nb, RC_THREADS, 0, st>>>(d);
+    cudaMemsetAsync(d.rc_blocks, 0, (size_t)nb * sizeof(uint32_t), st);
+    k_nrc_count<<<nb, RC_THREADS, 0, st>>>(d);
+    if (d.s1 > d.s0) k_nrc_merge<<<(d.s1 - d.s0 + RM_WARPS - 1) / RM_WARPS, RM_WARPS * 32, 0, st>>>(d);
+    k_rc_ids<<<(d.m_cap + 127) / 128, 128, 0, st>>>(d);
+    k_rc_scan<<<1, 1024, 0, st>>>(d, nb, CTR_NREC);
+    k_nrc_emit<<<nb, RC_THREADS, 0, st>>>(d);
+    return;
+  }
   k_rc_flag_count<<<nb, RC_THREADS, 0, st>>>(d);
   k_rc_scan<<<1, 1024, 0, st>>>(d, nb, CTR_NRW);
   k_rc_scatter<<<nb, RC_THREADS, 0, st>>>(d);
