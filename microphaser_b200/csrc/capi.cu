@@ -427,6 +427,9 @@ void run_kernels(mph_ctx* c) {
   d.rec_seq = c->rec_seq.p; d.rec_seq_cap = uint32_t(std::min<size_t>(c->rec_seq.cap, 0xFFFFFF00u));
   d.m_recs = c->m_recs.p; d.m_aux = c->m_aux.p; d.m_seq = c->m_seq.p; d.m_cap = uint32_t(std::min<size_t>(c->m_recs.cap, 0x03FFFFFFu));
   CU(cudaMemsetAsync(c->counters.p, 0, mphk::CTR_COUNT * sizeof(uint32_t), c->stream));
+  // normal mode: the record kernels visit every window and find its segment in win_seg; windows nobody claims (replayed
+  // transcripts) must read as host class
+  if (d.mode == 1 && d.w1 > d.w0) CU(cudaMemsetAsync(c->win_seg.p + d.w0, 0xFF, size_t(d.w1 - d.w0) * sizeof(uint32_t), c->stream));
   if (c->stage_tx_hi > c->stage_tx_lo)
     CU(cudaMemsetAsync(c->tx_stop.p + c->stage_tx_lo, 0xFF, size_t(c->stage_tx_hi - c->stage_tx_lo) * sizeof(uint32_t), c->stream));
   CU(cudaEventRecord(c->ev[2], c->stream));  // k1_ms covers the zero-fill below: it is the allele call of the reads without variants
