@@ -866,10 +866,11 @@ void phase_stages(mph_ctx* c, const std::vector<Stage>& stages, bool copied, mph
 void phase_batch_impl(mph_ctx* c, const mph_batch* mb, mph_result** out) {
   c->cur = nullptr;
   prepare(c, mb);
-  // stages of about 7 M reads: every stage pays the fixed latency of its kernel chain (the serial replay's longest unit, the
-  // junction merges), so a few long stages beat many short ones now that almost no host work is left to hide behind the
-  // copies (measured on B200, whole-exome shard: 3-5 stages 18.7 ms, 8 stages 21.4 ms, 12 stages 26.8 ms per call)
-  unsigned want = unsigned(std::min<uint64_t>(12, std::max<uint64_t>(1, mb->b.n_reads() / 7000000)));
+  // stages of about 16 M reads: every stage pays the fixed latency of its kernel chain (the serial replay's longest unit, the
+  // junction merges) and the chain of a stage starts only after the previous stage's download, so a few long stages beat
+  // many short ones now that the copy is short (6 B per read) and almost no host work is left to hide behind it. Measured
+  // on B200, whole-exome shard (35 M reads, 214 MB): 2 stages 11.1 ms, 3: 11.6, 4: 12.4, 6: 15.0, 8: 17.8 ms per call.
+  unsigned want = unsigned(std::min<uint64_t>(12, std::max<uint64_t>(1, (mb->b.n_reads() + 8000000) / 16000000)));
   if (const char* e = getenv("MPH_STAGES")) want = unsigned(std::max(1, atoi(e)));
   const std::vector<Stage> stages = plan_stages(mb, want);
   c->kernels_done = false;

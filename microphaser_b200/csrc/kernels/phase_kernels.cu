@@ -431,8 +431,9 @@ __global__ void __launch_bounds__(K2B_WARPS * 32) k_window_hist(const DeviceBatc
     if (lane >= o) run += y;
   }
   run += carry;
-  const uint32_t va = mph_var_lb(d.vars, ch.va0, ch.vb1, g.s);
-  const uint32_t vb = mph_var_lb(d.vars, va, ch.vb1, g.e);
+  const bool chunk_has_var = ch.vb1 > ch.va0;  // four chunks in five have none: no searches, no key-only list
+  const uint32_t va = chunk_has_var ? mph_var_lb(d.vars, ch.va0, ch.vb1, g.s) : ch.va0;
+  const uint32_t vb = chunk_has_var ? mph_var_lb(d.vars, va, ch.vb1, g.e) : ch.va0;
   const uint32_t nvar = vb - va;
   if (active && nvar > 64) raise(d, MPH_E_VARS_PER_WINDOW);
   const uint32_t my_s = active ? g.s : 0u;
@@ -476,7 +477,9 @@ __global__ void __launch_bounds__(K2B_WARPS * 32) k_window_hist(const DeviceBatc
     }
   }
   // (2) reads already counted as plain observations over a run of windows: the windows with variants need their haplotype
-  if (ch.vb1 > ch.va0) {
+  uint32_t single_cnt = 0;  // windows with exactly one variant: their only possible extra key is haplotype 1 - a counter, no table
+  const bool single = nvar == 1;
+  if (chunk_has_var) {
     const uint32_t list2_n = d.seg_list2_n[ch.seg];
     const uint2* list2 = d.seg_list + d.seg_work_off[ch.seg + 1] - list2_n;
     for (uint32_t x0 = 0; x0 < list2_n; x0 += 32) {
@@ -496,7 +499,15 @@ __global__ void __launch_bounds__(K2B_WARPS * 32) k_window_hist(const DeviceBatc
         const uint32_t rr = __shfl_sync(FULL, mine_run, x);
         const uint32_t vlo = __shfl_sync(FULL, mine_vlo, x);
         const uint64_t S = (uint64_t)__shfl_sync(FULL, mine_Slo, x) | ((uint64_t)__shfl_sync(FULL, mine_Shi, x) << 32);
-        if (nvar == 0 || !active || i < (rr & 0xFFFFu) || i > (rr >> 16)) continue;
+        const bool in_run = nvar != 0 && active && i >= (rr & 0xFFFFu) && i <= (rr >> 16);
+        if (single) {
+          // bit (va - vlo) of S, if the variant is among the read's own
+          const uint32_t sh = va - vlo;
+          const uint32_t bit = (in_run && va >= vlo && sh < 64u) ? (uint32_t)((S >> sh) & 1u) : 0u;
+          single_cnt += bit;
+          continue;
+        }
+        if (!in_run) continue;
         const uint64_t bits = mph_window_bits(S, vlo, va, nvar);
         const uint64_t hap = rev ? bits : (mph_bitrev64(bits) >> (64 - nvar));
         if (hap != 0) {
@@ -505,6 +516,17 @@ __global__ void __launch_bounds__(K2B_WARPS * 32) k_window_hist(const DeviceBatc
         }
       }
     }
+  }
+  if (single_cnt) {  // fold the counter into the key table (it may already hold haplotype 1 from a closed-form read)
+    c0_adj -= (int)single_cnt;
+    uint32_t q = 0;
+    for (; q < n_keys; ++q)
+      if (t_hap[warp][q][lane] == 1 && t_frm[warp][q][lane] == 0) break;
+    if (q == n_keys) {
+      if (n_keys == K2_LANE_KEYS || d.force_wide) overflow = true;
+      else { t_hap[warp][q][lane] = 1; t_frm[warp][q][lane] = 0; t_cnt[warp][q][lane] = 0; ++n_keys; }
+    }
+    if (q < K2_LANE_KEYS && !overflow) t_cnt[warp][q][lane] += single_cnt;
   }
   const uint32_t depth = (uint32_t)run + depth_x;
   const uint32_t c0 = (uint32_t)(run + c0_adj);
