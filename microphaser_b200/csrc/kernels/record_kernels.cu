@@ -3,7 +3,8 @@
 // (:703-718, :1480-1488), the splice-junction merge (:1497-1908, src/common.rs:376-568) and a stable,
 // ordered compaction of the *records* — the host only renders text.
 //
-//   k_rc_stop     thread per window (only the interesting windows of device-class transcripts act): does one of its haplotypes remove the peptide? -> atomicMin per transcript
+//   k_rc_flag_count / k_rc_scan / k_rc_scatter   compact the interesting windows of device-class transcripts
+//   k_rc_stop     thread per such window: does one of its haplotypes remove the peptide? -> atomicMin per transcript
 //   k_rc_count    thread per window: records it writes itself; lists the windows whose junction merge is due
 //   k_rc_merge    warp per junction: the merge with its byte-level steps split over the lanes, into the merge arena
 //   k_rc_ids      thread per merged record: its SHA-1 id
@@ -53,6 +54,13 @@ __device__ __forceinline__ uint32_t block_exclusive(uint32_t v, uint32_t* total)
   return before + x - v;
 }
 
+__global__ void __launch_bounds__(RC_THREADS) k_rc_flag_count(const DeviceBatch d) {
+  const uint32_t w = d.w0 + blockIdx.x * RC_THREADS + threadIdx.x;
+  const int f = (w < d.w1) && d.win_flag[w] == 2;
+  const int n = __syncthreads_count(f);
+  if (threadIdx.x == 0) d.rc_blocks[blockIdx.x] = (uint32_t)n;
+}
+
 // exclusive scan of rc_blocks[0 .. n_blocks) in place (one CTA); total -> counters[ctr]
 __global__ void __launch_bounds__(1024) k_rc_scan(const DeviceBatch d, uint32_t n_blocks, int ctr) {
   __shared__ uint32_t warp_sums[32];
@@ -88,9 +96,18 @@ __global__ void __launch_bounds__(1024) k_rc_scan(const DeviceBatch d, uint32_t 
   if (threadIdx.x == 0) d.counters[ctr] = carry;
 }
 
+__global__ void __launch_bounds__(RC_THREADS) k_rc_scatter(const DeviceBatch d) {
+  const uint32_t w = d.w0 + blockIdx.x * RC_THREADS + threadIdx.x;
+  const bool f = (w < d.w1) && d.win_flag[w] == 2;
+  uint32_t total;
+  const uint32_t before = block_exclusive(f ? 1u : 0u, &total);
+  if (f) d.rw[d.rc_blocks[blockIdx.x] + before] = w;
+}
+
 __global__ void __launch_bounds__(RC_THREADS) k_rc_stop(const DeviceBatch d) {
-  const uint32_t x = blockIdx.x * RC_THREADS + threadIdx.x, w = d.w0 + x;
-  if (w >= d.w1 || d.win_flag[w] != 2) return;  // 2 = interesting window of a device-class transcript
+  const uint32_t x = blockIdx.x * RC_THREADS + threadIdx.x;
+  if (x >= d.counters[CTR_NRW]) return;
+  const uint32_t w = d.rw[x];
   const MphSegment& sg = d.segs[d.win_seg[w]];
   const MphRecCtx c = rec_ctx(d);
   const uint32_t q = mph_rc_window_stop(c, sg, w - sg.win_base, w);
@@ -99,11 +116,10 @@ __global__ void __launch_bounds__(RC_THREADS) k_rc_stop(const DeviceBatch d) {
 }
 
 __global__ void __launch_bounds__(RC_THREADS) k_rc_count(const DeviceBatch d) {
-  const uint32_t x = blockIdx.x * RC_THREADS + threadIdx.x, w = d.w0 + x;
+  const uint32_t x = blockIdx.x * RC_THREADS + threadIdx.x;
   uint32_t n = 0;
-  if (w < d.w1 && d.win_flag[w] != 2) {
-    d.rw_info[x] = 0;
-  } else if (w < d.w1) {
+  if (x < d.counters[CTR_NRW]) {
+    const uint32_t w = d.rw[x];
     const uint32_t si = d.win_seg[w];
     const MphSegment& sg = d.segs[si];
     const uint32_t stop = d.tx_stop[sg.tx];
@@ -185,7 +201,7 @@ __global__ void __launch_bounds__(RM_WARPS * 32) k_rc_merge(const DeviceBatch d)
   const int lane = threadIdx.x & 31;
   if (j >= d.counters[CTR_NJ]) return;
   const uint32_t x = d.rw_junc[j];
-  const uint32_t w = d.w0 + x;
+  const uint32_t w = d.rw[x];
   const uint32_t si = d.win_seg[w];
   const MphSegment& sg = d.segs[si];
   const MphSegment& sp = d.segs[si - 1];
@@ -226,7 +242,7 @@ __global__ void __launch_bounds__(128) k_rc_ids(const DeviceBatch d) {
 
 __global__ void __launch_bounds__(RC_THREADS) k_rc_emit(const DeviceBatch d) {
   const uint32_t x = blockIdx.x * RC_THREADS + threadIdx.x;
-  const bool live = d.w0 + x < d.w1;
+  const bool live = x < d.counters[CTR_NRW];
   const uint32_t info = live ? d.rw_info[x] : 0u;
   const uint32_t n_own = info & 0xFFFu, nm = info >> 12;
   uint32_t total;
@@ -237,7 +253,7 @@ __global__ void __launch_bounds__(RC_THREADS) k_rc_emit(const DeviceBatch d) {
   const uint32_t bytes = d.rw_bytes[x];
   const uint32_t sbase = atomicAdd(&d.counters[CTR_RECSEQ], bytes);
   if (sbase + bytes > d.rec_seq_cap) { raise(d, MPH_E_REC_OVERFLOW); return; }
-  const uint32_t w = d.w0 + x;
+  const uint32_t w = d.rw[x];
   const MphSegment& sg = d.segs[d.win_seg[w]];
   const MphRecCtx c = rec_ctx(d);
   uint32_t err = 0;
@@ -412,8 +428,11 @@ void launch_records(const DeviceBatch& d, cudaStream_t st) {
     k_nrc_emit<<<nb, RC_THREADS, 0, st>>>(d);
     return;
   }
-  // thread per window of the slice (x = w - w0); only the interesting windows of device-class transcripts (win_flag 2) do
-  // anything. The kernels wait on a few long items (junctions), so a compaction of the windows first bought nothing.
+  k_rc_flag_count<<<nb, RC_THREADS, 0, st>>>(d);
+  k_rc_scan<<<1, 1024, 0, st>>>(d, nb, CTR_NRW);
+  k_rc_scatter<<<nb, RC_THREADS, 0, st>>>(d);
+  // the number of listed windows lives on the device: the grids cover the upper bound the host knows (interesting
+  // windows of the slice cannot exceed its windows); threads beyond the count return at once
   const uint32_t nbl = nb;
   k_rc_stop<<<nbl, RC_THREADS, 0, st>>>(d);
   cudaMemsetAsync(d.rc_blocks, 0, (size_t)nbl * sizeof(uint32_t), st);
@@ -423,7 +442,7 @@ void launch_records(const DeviceBatch& d, cudaStream_t st) {
   k_rc_scan<<<1, 1024, 0, st>>>(d, nbl, CTR_NREC);
   k_rc_emit<<<nbl, RC_THREADS, 0, st>>>(d);
 }
-int record_kernel_launch_count() { return 6; }
+int record_kernel_launch_count() { return 9; }
 
 void launch_live_depth(const DeviceBatch& d, cudaStream_t st) {
   if (d.c1 > d.c0) k_live_depth2<<<(d.c1 - d.c0 + 7) / 8, 256, 0, st>>>(d);
