@@ -392,7 +392,7 @@ def main():
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
-        traffic = json.load(open(tp)).get(dom if mode == "somatic" else dom + "_" + mode)
+        traffic = json.load(open(tp)).get(name, {}).get(dom)  # per workload: DRAM bytes of one launch from the committed ncu capture
     roofline = {"bound": "hbm", "kernel": {"k1_ms": "k_allele_call", "k2_ms": "k_read_runs + k_window_hist", "k3_ms": "k_assemble", "k4_ms": "compaction",
                                            "k5_ms": "record kernels"}[dom],
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,

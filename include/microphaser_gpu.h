@@ -199,6 +199,11 @@ int mph_run_somatic_multi(mph_ctx* const* ctxs, int n_ctx, const char* bam_path,
                           const char* gtf_path, const char* fasta_out_path, const char* tsv_path, const char* normal_path,
                           uint32_t window_len, int unsupported_allele_warning_only);
 
+/* `normal` sub-command over several devices, sharded the same way (src/normal_microphasing.rs:1281-1440) */
+int mph_run_normal_multi(mph_ctx* const* ctxs, int n_ctx, const char* bam_path, const char* ref_path, const char* variants_path,
+                         const char* gtf_path, const char* fasta_out_path, const char* tsv_path, uint32_t window_len,
+                         int unsupported_allele_warning_only);
+
 /* ---- secondary path: `filter` / `build_reference` (src/peptides.rs) ------------------------------ */
 /* to_protein (:128-146): n nucleotide sequences nt[off[i]..off[i+1]); frame[i] = +1 (forward) or -1 (reverse complement
  * first, :131-135). aa[aa_off[i]..aa_off[i+1]) receives floor(len/3) amino-acid letters ('X' = stop); bad[i] = 1 if a

@@ -57,7 +57,7 @@ class BatchView(C.Structure):
 EXPORTS = ["mph_ctx_create", "mph_ctx_destroy", "mph_last_error", "mph_packer_create", "mph_packer_destroy", "mph_packer_add_gene",
            "mph_packer_finish", "mph_batch_destroy", "mph_batch_get_view", "mph_phase_batch", "mph_batch_upload", "mph_phase_resident",
            "mph_phase_collect", "mph_ctx_timing", "mph_result_destroy", "mph_result_count", "mph_result_get", "mph_result_write",
-           "mph_run_somatic", "mph_run_normal", "mph_run_somatic_multi", "mph_translate", "mph_set_load", "mph_set_probe", "mph_run_filter",
+           "mph_run_somatic", "mph_run_normal", "mph_run_somatic_multi", "mph_run_normal_multi", "mph_translate", "mph_set_load", "mph_set_probe", "mph_run_filter",
            "mph_run_build_reference", "mph_synth_batch", "mph_synth_write_files"]
 
 _lib = None
@@ -94,6 +94,7 @@ def load():
     lib.mph_run_somatic.argtypes = [P] + [C.c_char_p] * 7 + [C.c_uint32, C.c_int]
     lib.mph_run_normal.argtypes = [P] + [C.c_char_p] * 6 + [C.c_uint32, C.c_int]
     lib.mph_run_somatic_multi.argtypes = [C.POINTER(P), C.c_int] + [C.c_char_p] * 7 + [C.c_uint32, C.c_int]
+    lib.mph_run_normal_multi.argtypes = [C.POINTER(P), C.c_int] + [C.c_char_p] * 6 + [C.c_uint32, C.c_int]
     lib.mph_translate.argtypes = [P, P, P, P, C.c_uint64, P, P, P]
     lib.mph_set_load.argtypes = [P, P, C.c_uint32, C.c_uint64]
     lib.mph_set_probe.argtypes = [P, P, C.c_uint32, C.c_uint64, P]
@@ -216,6 +217,13 @@ def run_somatic_multi(contexts, bam, ref, variants, gtf, fasta_out, tsv, normal_
     arr = (C.c_void_p * len(contexts))(*[c.h for c in contexts])
     enc = [s.encode() for s in (bam, ref, variants, gtf, fasta_out, tsv, normal_out)]
     _check(load().mph_run_somatic_multi(arr, len(contexts), *enc, window_len, int(warn_only)), contexts[0].h)
+
+
+def run_normal_multi(contexts, bam, ref, variants, gtf, fasta_out, tsv, window_len=27, warn_only=False):
+    """`microphaser normal` sharded by gene range over several devices (one Context each)."""
+    arr = (C.c_void_p * len(contexts))(*[c.h for c in contexts])
+    enc = [s.encode() for s in (bam, ref, variants, gtf, fasta_out, tsv)]
+    _check(load().mph_run_normal_multi(arr, len(contexts), *enc, window_len, int(warn_only)), contexts[0].h)
 
 
 class Batch:

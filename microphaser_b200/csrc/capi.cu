@@ -149,7 +149,7 @@ struct mph_ctx {
   std::string last_error;
   const mph_batch* cur = nullptr;
   mphk::DeviceBatch d;
-  DevBuf<uint32_t> read_start, read_end, read_vlo, read_vr, vr_read, vr_vlo, vr_seq_off, vr_cig_off, cigars, block_counts, iw, counters, seg_live, ovf_list, stopmap, hist_win, win_depth, seg_chunk0, dq_init, seg_err, tx_id_off, o_read, o_key, o_frame, win_voff, vlist, iw_voff, seg_work_off, seg_list_n;
+  DevBuf<uint32_t> read_start, read_end, read_vlo, read_vr, vr_read, vr_vlo, vr_seq_off, vr_cig_off, cigars, block_counts, iw, counters, seg_live, ovf_list, stopmap, hist_win, win_depth, seg_chunk0, dq_init, seg_err, tx_id_off, o_read, o_key, o_frame, win_voff, vlist, iw_voff, seg_work_off, seg_list_n, rr_seg0;
   DevBuf<uint16_t> vr_lseq, vr_ncig;
   DevBuf<uint8_t> tx_id_bytes;
   DevBuf<uint8_t> read_nv, vr_nv, read_flags, bases, ins_bytes, ref, call_flags, seq, win_flag, o_flags, o_inmat;
@@ -303,7 +303,7 @@ void prepare(mph_ctx* c, const mph_batch* mb) {
   c->vs_runs.ensure(b.vs_runs.size() + 1); c->vs_ncig_exc.ensure(b.vs_ncig_exc.size() + 1);
   c->bases.ensure(b.bases.size() + 1); c->cigars.ensure(b.cigars.size() + 1); c->vars.ensure(b.vars.size() + 1); c->ins_bytes.ensure(b.ins_bytes.size() + 1);
   c->segs.ensure(b.segs.size() + 1); c->chunks.ensure(b.chunks.size() + 1); c->seg_work.ensure(b.seg_work.size() + 1); c->seg_work_off.ensure(b.seg_work_off.size() + 1);
-  c->win_diff.ensure(nw + 1); c->seg_list.ensure(size_t(b.seg_work_off.back()) + 1); c->seg_list_n.ensure(2 * b.segs.size() + 2); c->ref.ensure(b.ref.size() + 1); c->stopmap.ensure(b.stopmap.size() + 1);
+  c->win_diff.ensure(nw + 1); c->seg_list.ensure(size_t(b.seg_work_off.back()) + 1); c->seg_list_n.ensure(2 * b.segs.size() + 2); c->rr_seg0.ensure(mphk::read_runs_blocks(b.seg_work_off.back()) + 2); c->ref.ensure(b.ref.size() + 1); c->stopmap.ensure(b.stopmap.size() + 1);
   c->pairs.ensure(mb->pairs.size() + 1); c->tx_id_bytes.ensure(b.tx_id_bytes.size() + 1); c->tx_id_off.ensure(b.tx_id_off.size() + 1);
   c->call_S.ensure(nr + 1); c->call_B.ensure(nr + 1); c->call_flags.ensure(nr + 1);
   c->win_out.ensure(nw + 1); c->hap0.ensure(nw + 1); c->win_flag.ensure(nw + 1);
@@ -339,7 +339,7 @@ void prepare(mph_ctx* c, const mph_batch* mb) {
   d.vs_ncig_exc = c->vs_ncig_exc.p;
   d.bases = c->bases.p; d.cigars = c->cigars.p; d.vars = c->vars.p;
   d.ins_bytes = c->ins_bytes.p; d.segs = c->segs.p; d.chunks = c->chunks.p; d.seg_work = c->seg_work.p; d.seg_work_off = c->seg_work_off.p;
-  d.win_diff = c->win_diff.p; d.seg_list = c->seg_list.p; d.seg_list_n = c->seg_list_n.p; d.seg_list2_n = c->seg_list_n.p + b.segs.size() + 1; d.ref = c->ref.p; d.stopmap = c->stopmap.p;
+  d.win_diff = c->win_diff.p; d.seg_list = c->seg_list.p; d.seg_list_n = c->seg_list_n.p; d.seg_list2_n = c->seg_list_n.p + b.segs.size() + 1; d.rr_seg0 = c->rr_seg0.p; d.ref = c->ref.p; d.stopmap = c->stopmap.p;
   d.call_S = reinterpret_cast<uint64_t*>(c->call_S.p); d.call_B = reinterpret_cast<uint64_t*>(c->call_B.p); d.call_flags = c->call_flags.p;
   d.win_out = c->win_out.p; d.hap0 = c->hap0.p; d.win_flag = c->win_flag.p; d.block_counts = c->block_counts.p;
   d.ovf_list = c->ovf_list.p;
@@ -722,6 +722,7 @@ void phase_stages(mph_ctx* c, const std::vector<Stage>& stages, bool copied, mph
   const mph_batch* mb = c->cur;
   const Batch& b = mb->b;
   const auto wall0 = std::chrono::steady_clock::now();
+  const uint64_t launches0 = mphk::kernel_launches_on_this_thread();
   const size_t ns = stages.size();
   if (c->raws.size() < ns) c->raws.resize(ns);
   if (c->ev_copy.size() < ns + 1) {
@@ -855,7 +856,7 @@ void phase_stages(mph_ctx* c, const std::vector<Stage>& stages, bool copied, mph
   c->timing.windows_enumerated = b.n_windows;
   c->timing.n_interesting = n_iw_total;
   c->timing.n_records = res->size();
-  c->timing.kernel_launches = (uint32_t(mphk::kernel_launch_count()) + (b.replay.empty() ? 0u : 1u) + uint32_t(mphk::record_kernel_launch_count())) * uint32_t(ns);
+  c->timing.kernel_launches = uint32_t(mphk::kernel_launches_on_this_thread() - launches0);  // counted at the launch sites (MPH_LAUNCH)
   c->timing.n_replay_units = uint32_t(b.replay.size());
   c->timing.total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
   if (timeline) fprintf(stderr, "[mph] call finished at %.2f ms\n", c->timing.total_ms);
@@ -1511,6 +1512,17 @@ int mph_run_somatic_multi(mph_ctx* const* ctxs, int n_ctx, const char* bam_path,
   return guarded(ctxs[0], [&] {
     run_somatic_files(std::vector<mph_ctx*>(ctxs, ctxs + n_ctx), bam_path, ref_path, variants_path, gtf_path, fasta_out_path, tsv_path,
                       normal_path, window_len, warn_only);
+  });
+}
+
+int mph_run_normal_multi(mph_ctx* const* ctxs, int n_ctx, const char* bam_path, const char* ref_path, const char* variants_path,
+                         const char* gtf_path, const char* fasta_out_path, const char* tsv_path, uint32_t window_len, int warn_only) {
+  if (!ctxs || n_ctx < 1 || !bam_path || !ref_path || !variants_path || !gtf_path || !fasta_out_path || !tsv_path)
+    return fail(nullptr, MPH_ERR_INPUT, "null argument");
+  if (window_len == 0 || window_len % 3 != 0) return fail(ctxs[0], MPH_ERR_UNSUPPORTED, "window length must be a positive multiple of 3");
+  return guarded(ctxs[0], [&] {
+    run_somatic_files(std::vector<mph_ctx*>(ctxs, ctxs + n_ctx), bam_path, ref_path, variants_path, gtf_path, fasta_out_path, tsv_path,
+                      nullptr, window_len, warn_only, 1);
   });
 }
 

@@ -6,6 +6,14 @@
 #include "../core/replay_core.h"
 
 namespace mphk {
+
+// Every launch goes through this macro: the calling thread's count is what mph_timing.kernel_launches (the bench line's
+// "gpu_launches") reports, so the figure is the number of kernels actually launched, not an estimate.
+extern thread_local uint64_t g_kernel_launches;
+#define MPH_LAUNCH_UNPACK(...) __VA_ARGS__
+#define MPH_LAUNCH(kern, cfg, ...) \
+  do { kern<<<MPH_LAUNCH_UNPACK cfg>>>(__VA_ARGS__); ++::mphk::g_kernel_launches; } while (0)
+
 namespace detail {
 
 constexpr unsigned FULL = 0xFFFFFFFFu;

@@ -418,12 +418,12 @@ __global__ void __launch_bounds__(128) k_assemble_normal(const DeviceBatch d) {
 
 void launch_window_hist_normal(const DeviceBatch& d, cudaStream_t st) {
   const uint32_t nc = d.c1 - d.c0;
-  k_window_hist_normal<<<(nc + K2_WARPS - 1) / K2_WARPS, K2_WARPS * 32, 0, st>>>(d);
+  MPH_LAUNCH(k_window_hist_normal, ((nc + K2_WARPS - 1) / K2_WARPS, K2_WARPS * 32, 0, st), d);
   // windows with more distinct haplotypes than a lane table holds (rare): one warp per window
-  k_window_hist_wide_normal<<<148 * 8, K2_WARPS * 32, 0, st>>>(d);
+  MPH_LAUNCH(k_window_hist_wide_normal, (148 * 8, K2_WARPS * 32, 0, st), d);
 }
 void launch_assemble_normal(const DeviceBatch& d, cudaStream_t st) {
-  k_assemble_normal<<<148 * 8, 128, 0, st>>>(d);  // grid-stride over the key arena (its size lives on the device)
+  MPH_LAUNCH(k_assemble_normal, (148 * 8, 128, 0, st), d);  // grid-stride over the key arena (its size lives on the device)
 }
 
 }  // namespace mphk

@@ -3,6 +3,7 @@
 // membership test (`ref_set.contains(tumor_peptide)` :502,684) as an open-addressing hash set of
 // 5-bit packed peptides probed on the device.
 #include "peptide_kernels.cuh"
+#include "kernel_common.cuh"
 
 namespace mphk {
 
@@ -111,17 +112,17 @@ __global__ void __launch_bounds__(256) k_set_export(const unsigned long long* __
 
 void launch_translate(const uint8_t* nt, const uint64_t* off, const int8_t* frame, uint64_t n, uint8_t* aa, const uint64_t* aa_off, uint8_t* bad,
                       cudaStream_t st) {
-  if (n) k_translate<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(nt, off, frame, n, aa, aa_off, bad);
+  if (n) MPH_LAUNCH(k_translate, ((unsigned)((n + 255) / 256), 256, 0, st), nt, off, frame, n, aa, aa_off, bad);
 }
 void launch_set_insert(const uint8_t* peptides, uint32_t k, uint64_t n, unsigned long long* table, uint64_t mask, unsigned long long* n_distinct,
                        cudaStream_t st) {
-  if (n) k_set_insert<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(peptides, k, n, table, mask, n_distinct);
+  if (n) MPH_LAUNCH(k_set_insert, ((unsigned)((n + 255) / 256), 256, 0, st), peptides, k, n, table, mask, n_distinct);
 }
 void launch_set_probe(const uint8_t* queries, uint32_t k, uint64_t n, const unsigned long long* table, uint64_t mask, uint8_t* hit, cudaStream_t st) {
-  if (n) k_set_probe<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(queries, k, n, table, mask, hit);
+  if (n) MPH_LAUNCH(k_set_probe, ((unsigned)((n + 255) / 256), 256, 0, st), queries, k, n, table, mask, hit);
 }
 void launch_set_export(const unsigned long long* table, uint64_t slots, uint32_t k, uint8_t* out, unsigned long long* cursor, cudaStream_t st) {
-  if (slots) k_set_export<<<(unsigned)((slots + 255) / 256), 256, 0, st>>>(table, slots, k, out, cursor);
+  if (slots) MPH_LAUNCH(k_set_export, ((unsigned)((slots + 255) / 256), 256, 0, st), table, slots, k, out, cursor);
 }
 
 }  // namespace mphk

@@ -281,21 +281,26 @@ constexpr int RR_THREADS = 256;
 constexpr int RR_IPT = 4;  // work items per thread
 constexpr int RR_ITEMS = RR_THREADS * RR_IPT;
 
+// first segment of every K2a block: last segment whose items start at or before the block's first item. One thread per
+// block searches here, in parallel, so that k_read_runs does not start every CTA with a 17-step dependent search behind a
+// barrier (a fifth of its stall samples in the round-2 ncu capture).
+__global__ void __launch_bounds__(256) k_read_runs_plan(const DeviceBatch d, uint32_t n_blocks) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n_blocks) return;
+  const uint32_t first = d.it0 + b * RR_ITEMS;
+  uint32_t lo = d.s0, hi = d.s1;
+  while (hi - lo > 1) {
+    const uint32_t mid = lo + ((hi - lo) >> 1);
+    if (d.seg_work_off[mid] <= first) lo = mid;
+    else hi = mid;
+  }
+  d.rr_seg0[b] = lo;
+}
+
 __global__ void __launch_bounds__(RR_THREADS) k_read_runs(const DeviceBatch d) {
   const uint32_t it0 = d.it0, it1 = d.it1;
-  __shared__ uint32_t s_seg0;
   const uint32_t first = it0 + blockIdx.x * RR_ITEMS;
-  if (threadIdx.x == 0) {  // last segment whose items start at or before `first`
-    uint32_t lo = d.s0, hi = d.s1;
-    while (hi - lo > 1) {
-      const uint32_t mid = lo + ((hi - lo) >> 1);
-      if (d.seg_work_off[mid] <= first) lo = mid;
-      else hi = mid;
-    }
-    s_seg0 = lo;
-  }
-  __syncthreads();
-  uint32_t seg = s_seg0;
+  uint32_t seg = d.rr_seg0[blockIdx.x];
   uint32_t a_r[RR_IPT], a_seg[RR_IPT], a_st[RR_IPT], a_en[RR_IPT], a_cf[RR_IPT];
 #pragma unroll
   for (int u = 0; u < RR_IPT; ++u) {
@@ -738,34 +743,40 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scatter(const DeviceBatch d) {
 }  // namespace
 
 void launch_read_decode(const DeviceBatch& d, cudaStream_t st) {
-  if (d.run1 > d.run0) k_read_decode<<<(d.run1 - d.run0 + 3) / 4, 128, 0, st>>>(d);
+  if (d.run1 > d.run0) MPH_LAUNCH(k_read_decode, ((d.run1 - d.run0 + 3) / 4, 128, 0, st), d);
   const uint32_t n = (d.sx1 - d.sx0) + (d.fx1 - d.fx0);
-  if (n) k_read_patch<<<(n + 255) / 256, 256, 0, st>>>(d);
-  if (d.vrun1 > d.vrun0) k_side_decode<<<(d.vrun1 - d.vrun0 + 3) / 4, 128, 0, st>>>(d);
-  if (d.nx1 > d.nx0) k_side_patch<<<(d.nx1 - d.nx0 + 255) / 256, 256, 0, st>>>(d);
+  if (n) MPH_LAUNCH(k_read_patch, ((n + 255) / 256, 256, 0, st), d);
+  if (d.vrun1 > d.vrun0) MPH_LAUNCH(k_side_decode, ((d.vrun1 - d.vrun0 + 3) / 4, 128, 0, st), d);
+  if (d.nx1 > d.nx0) MPH_LAUNCH(k_side_patch, ((d.nx1 - d.nx0 + 255) / 256, 256, 0, st), d);
 }
 void launch_allele_call(const DeviceBatch& d, cudaStream_t st) {
-  if (d.vr1 > d.vr0) k_allele_call<<<(d.vr1 - d.vr0 + 255) / 256, 256, 0, st>>>(d);
+  if (d.vr1 > d.vr0) MPH_LAUNCH(k_allele_call, ((d.vr1 - d.vr0 + 255) / 256, 256, 0, st), d);
 }
 void launch_window_hist(const DeviceBatch& d, cudaStream_t st) {
   if (d.c1 <= d.c0) return;
   const uint32_t nc = d.c1 - d.c0;
   if (d.mode == 1) return launch_window_hist_normal(d, st);
-  if (d.it1 > d.it0) k_read_runs<<<(d.it1 - d.it0 + RR_ITEMS - 1) / RR_ITEMS, RR_THREADS, 0, st>>>(d);
-  k_window_hist<<<(nc + K2B_WARPS - 1) / K2B_WARPS, K2B_WARPS * 32, 0, st>>>(d);
+  if (d.it1 > d.it0) {
+    const uint32_t nb = (d.it1 - d.it0 + RR_ITEMS - 1) / RR_ITEMS;
+    MPH_LAUNCH(k_read_runs_plan, ((nb + 255) / 256, 256, 0, st), d, nb);
+    MPH_LAUNCH(k_read_runs, (nb, RR_THREADS, 0, st), d);
+  }
+  MPH_LAUNCH(k_window_hist, ((nc + K2B_WARPS - 1) / K2B_WARPS, K2B_WARPS * 32, 0, st), d);
   // windows with more distinct haplotypes than a lane table holds (rare): one warp per window
-  k_window_hist_wide<<<148 * 8, K2_WARPS * 32, 0, st>>>(d);
+  MPH_LAUNCH(k_window_hist_wide, (148 * 8, K2_WARPS * 32, 0, st), d);
 }
 void launch_assemble(const DeviceBatch& d, cudaStream_t st) {
   if (d.c1 > d.c0 && d.mode == 1) launch_assemble_normal(d, st);
-  else if (d.c1 > d.c0) k_assemble<<<148 * 8, 128, 0, st>>>(d);  // grid-stride over the key arena (its size lives on the device)
+  else if (d.c1 > d.c0) MPH_LAUNCH(k_assemble, (148 * 8, 128, 0, st), d);  // grid-stride over the key arena (its size lives on the device)
 }
 void launch_compact(const DeviceBatch& d, cudaStream_t st) {
   const uint32_t nb = (d.w1 - d.w0 + SCAN_THREADS - 1) / SCAN_THREADS;
-  if (nb) k_flag_count<<<nb, SCAN_THREADS, 0, st>>>(d);
-  k_block_scan<<<1, SCAN_THREADS, 0, st>>>(d, nb);
-  if (nb) k_scatter<<<nb, SCAN_THREADS, 0, st>>>(d);
+  if (nb) MPH_LAUNCH(k_flag_count, (nb, SCAN_THREADS, 0, st), d);
+  MPH_LAUNCH(k_block_scan, (1, SCAN_THREADS, 0, st), d, nb);
+  if (nb) MPH_LAUNCH(k_scatter, (nb, SCAN_THREADS, 0, st), d);
 }
-int kernel_launch_count() { return 11; }
+thread_local uint64_t g_kernel_launches = 0;
+uint64_t kernel_launches_on_this_thread() { return g_kernel_launches; }
+uint32_t read_runs_blocks(uint64_t n_items) { return uint32_t((n_items + RR_ITEMS - 1) / RR_ITEMS); }
 
 }  // namespace mphk

@@ -72,6 +72,7 @@ struct DeviceBatch {
   uint2* seg_list = nullptr;
   uint32_t* seg_list_n = nullptr;
   uint32_t* seg_list2_n = nullptr;
+  uint32_t* rr_seg0 = nullptr;  // first segment of every k_read_runs block (k_read_runs_plan)
   const uint8_t* ref = nullptr;
   const uint32_t* stopmap = nullptr;  // 1 bit per ref byte: a stop codon starts here
   const uint8_t* tx_id_bytes = nullptr;  // transcript ids (record ids are hashed on the device)
@@ -151,7 +152,7 @@ void launch_assemble(const DeviceBatch& d, cudaStream_t st);
 void launch_compact(const DeviceBatch& d, cudaStream_t st);
 void launch_live_depth(const DeviceBatch& d, cudaStream_t st);            // record_kernels.cu
 void launch_records(const DeviceBatch& d, cudaStream_t st);               // record_kernels.cu
-int record_kernel_launch_count();
-int kernel_launch_count();  // kernels launched by one launch_* sequence K1..K4 (for bench "gpu_launches")
+uint64_t kernel_launches_on_this_thread();  // running count of the kernels the calling thread has launched (bench "gpu_launches")
+uint32_t read_runs_blocks(uint64_t n_items);  // CTAs k_read_runs uses for that many (segment, read) items
 
 }  // namespace mphk

@@ -419,33 +419,32 @@ void launch_records(const DeviceBatch& d, cudaStream_t st) {
   if (d.w1 <= d.w0) return;
   const uint32_t nb = (d.w1 - d.w0 + RC_THREADS - 1) / RC_THREADS;
   if (d.mode == 1) {
-    k_nrc_stop<<<nb, RC_THREADS, 0, st>>>(d);
+    MPH_LAUNCH(k_nrc_stop, (nb, RC_THREADS, 0, st), d);
     cudaMemsetAsync(d.rc_blocks, 0, (size_t)nb * sizeof(uint32_t), st);
-    k_nrc_count<<<nb, RC_THREADS, 0, st>>>(d);
-    if (d.s1 > d.s0) k_nrc_merge<<<(d.s1 - d.s0 + RM_WARPS - 1) / RM_WARPS, RM_WARPS * 32, 0, st>>>(d);
-    k_rc_ids<<<(d.m_cap + 127) / 128, 128, 0, st>>>(d);
-    k_rc_scan<<<1, 1024, 0, st>>>(d, nb, CTR_NREC);
-    k_nrc_emit<<<nb, RC_THREADS, 0, st>>>(d);
+    MPH_LAUNCH(k_nrc_count, (nb, RC_THREADS, 0, st), d);
+    if (d.s1 > d.s0) MPH_LAUNCH(k_nrc_merge, ((d.s1 - d.s0 + RM_WARPS - 1) / RM_WARPS, RM_WARPS * 32, 0, st), d);
+    MPH_LAUNCH(k_rc_ids, ((d.m_cap + 127) / 128, 128, 0, st), d);
+    MPH_LAUNCH(k_rc_scan, (1, 1024, 0, st), d, nb, CTR_NREC);
+    MPH_LAUNCH(k_nrc_emit, (nb, RC_THREADS, 0, st), d);
     return;
   }
-  k_rc_flag_count<<<nb, RC_THREADS, 0, st>>>(d);
-  k_rc_scan<<<1, 1024, 0, st>>>(d, nb, CTR_NRW);
-  k_rc_scatter<<<nb, RC_THREADS, 0, st>>>(d);
+  MPH_LAUNCH(k_rc_flag_count, (nb, RC_THREADS, 0, st), d);
+  MPH_LAUNCH(k_rc_scan, (1, 1024, 0, st), d, nb, CTR_NRW);
+  MPH_LAUNCH(k_rc_scatter, (nb, RC_THREADS, 0, st), d);
   // the number of listed windows lives on the device: the grids cover the upper bound the host knows (interesting
   // windows of the slice cannot exceed its windows); threads beyond the count return at once
   const uint32_t nbl = nb;
-  k_rc_stop<<<nbl, RC_THREADS, 0, st>>>(d);
+  MPH_LAUNCH(k_rc_stop, (nbl, RC_THREADS, 0, st), d);
   cudaMemsetAsync(d.rc_blocks, 0, (size_t)nbl * sizeof(uint32_t), st);
-  k_rc_count<<<nbl, RC_THREADS, 0, st>>>(d);
-  if (d.s1 > d.s0) k_rc_merge<<<(d.s1 - d.s0 + RM_WARPS - 1) / RM_WARPS, RM_WARPS * 32, 0, st>>>(d);  // at most one junction per segment
-  k_rc_ids<<<(d.m_cap + 127) / 128, 128, 0, st>>>(d);
-  k_rc_scan<<<1, 1024, 0, st>>>(d, nbl, CTR_NREC);
-  k_rc_emit<<<nbl, RC_THREADS, 0, st>>>(d);
+  MPH_LAUNCH(k_rc_count, (nbl, RC_THREADS, 0, st), d);
+  if (d.s1 > d.s0) MPH_LAUNCH(k_rc_merge, ((d.s1 - d.s0 + RM_WARPS - 1) / RM_WARPS, RM_WARPS * 32, 0, st), d);  // at most one junction per segment
+  MPH_LAUNCH(k_rc_ids, ((d.m_cap + 127) / 128, 128, 0, st), d);
+  MPH_LAUNCH(k_rc_scan, (1, 1024, 0, st), d, nbl, CTR_NREC);
+  MPH_LAUNCH(k_rc_emit, (nbl, RC_THREADS, 0, st), d);
 }
-int record_kernel_launch_count() { return 9; }
 
 void launch_live_depth(const DeviceBatch& d, cudaStream_t st) {
-  if (d.c1 > d.c0) k_live_depth2<<<(d.c1 - d.c0 + 7) / 8, 256, 0, st>>>(d);
+  if (d.c1 > d.c0) MPH_LAUNCH(k_live_depth2, ((d.c1 - d.c0 + 7) / 8, 256, 0, st), d);
 }
 
 }  // namespace mphk

@@ -503,8 +503,8 @@ __global__ void __launch_bounds__(64) k_replay_normal(const DeviceBatch d) {
 }  // namespace
 
 void launch_replay(const DeviceBatch& d, cudaStream_t st) {
-  if (d.rp1 > d.rp0 && d.mode == 1) k_replay_normal<<<(d.rp1 - d.rp0 + 1) / 2, 64, 0, st>>>(d);
-  else if (d.rp1 > d.rp0) k_replay<<<(d.rp1 - d.rp0 + RP_WARPS - 1) / RP_WARPS, RP_WARPS * 32, 0, st>>>(d);
+  if (d.rp1 > d.rp0 && d.mode == 1) MPH_LAUNCH(k_replay_normal, ((d.rp1 - d.rp0 + 1) / 2, 64, 0, st), d);
+  else if (d.rp1 > d.rp0) MPH_LAUNCH(k_replay, ((d.rp1 - d.rp0 + RP_WARPS - 1) / RP_WARPS, RP_WARPS * 32, 0, st), d);
 }
 
 }  // namespace mphk
