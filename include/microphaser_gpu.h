@@ -210,7 +210,8 @@ int mph_run_normal_multi(mph_ctx* const* ctxs, int n_ctx, const char* bam_path, 
  * codon is not in the table (the reference unwraps an Err there, :141). Constant-memory codon table on the device. */
 int mph_translate(mph_ctx* ctx, const uint8_t* nt, const uint64_t* off, const int8_t* frame, uint64_t n, uint8_t* aa, const uint64_t* aa_off,
                   uint8_t* bad);
-/* the normal peptidome as a device open-addressing hash set (deserialised HashSet<Vec<u8>> of :245): n peptides of k <= 12 letters */
+/* the normal peptidome as a device open-addressing hash set (deserialised HashSet<Vec<u8>> of :245): n peptides of k letters (up to 12: 5-bit packed
+ * 64-bit keys; longer ones, e.g. the 13-25 of MHC-II runs: slots index the resident byte array and equality is a byte compare) */
 int mph_set_load(mph_ctx* ctx, const uint8_t* peptides, uint32_t k, uint64_t n);
 /* ref_set.contains(tumor_peptide) (:502, :684) for n queries of k letters; hit[i] = 1 if present */
 int mph_set_probe(mph_ctx* ctx, const uint8_t* queries, uint32_t k, uint64_t n, uint8_t* hit);

@@ -2,6 +2,7 @@
 // host residue, writers and the file-level `somatic` driver. No CPU fallback: every phase call runs
 // the CUDA kernels of kernels/phase_kernels.cu or fails.
 #include <cuda_runtime.h>
+#include <cstring>
 #include <unistd.h>
 
 #include <condition_variable>
@@ -140,10 +141,12 @@ struct mph_ctx {
   cudaStream_t stream = nullptr;       // compute + device -> host
   cudaStream_t copy_stream = nullptr;  // host -> device of the next stage
   cudaStream_t replay_stream = nullptr;  // the serial replay of irregular transcripts runs beside the window kernels
-  cudaEvent_t ev_rp[3] = {};           // K1 done / replay start / replay done
+  cudaEvent_t ev_rp[5] = {};           // K1 done (main) / replay start / replay done / host-class K3 start / side chain done
+  int sm_count = 148;
   std::vector<cudaEvent_t> ev_copy;
   uint32_t stage_seg_lo = 0, stage_seg_hi = 0, stage_tx_lo = 0, stage_tx_hi = 0;
   bool replay_on_side = false;         // the last run_kernels put k_replay on replay_stream (its time comes from ev_rp)
+  bool side_chain = false;             // ... followed there by the host-class K3 walk and K4 (somatic mode)
   bool kernels_done = false;           // mph_phase_resident ran for the uploaded batch: mph_phase_collect only downloads
   cudaEvent_t ev[10] = {};
   std::string last_error;
@@ -178,6 +181,8 @@ struct mph_ctx {
   std::vector<PhaseRaw> raws;  // download buffers per stage, reused across calls (no page faults after the first)
   // secondary path: normal-peptidome hash set (open addressing, 5-bit packed peptides)
   DevBuf<unsigned long long> set_table;
+  DevBuf<uint32_t> set_idx;    // peptides longer than 12 letters: slots index set_bytes (kernels/peptide_kernels.cu)
+  DevBuf<uint8_t> set_bytes;
   uint64_t set_mask = 0;
   uint32_t set_k = 0;
   uint64_t set_distinct = 0;
@@ -457,34 +462,81 @@ void run_kernels(mph_ctx* c) {
   mphk::launch_read_decode(d, c->stream);  // K0: start / end / flags of the slice's reads from their 2-byte bus form
   mphk::launch_allele_call(d, c->stream);
   CU(cudaEventRecord(c->ev[3], c->stream));
-  // The serial replay (a latency-bound dependent chain per unit, a few hundred warps) can run on its own stream beside the
-  // window kernels (MPH_SIDE_REPLAY=1): they skip the replayed segments, and K3 is the first kernel that needs both results.
-  // Measured on B200 (whole-exome shard): the chain takes 3.32 ms instead of 3.56 ms, but the two slow each other down
-  // (replay 0.79 -> 1.65 ms, K2 1.19 -> ~1.5 ms), which blurs the per-kernel figures the bench reports; the default keeps
-  // them back to back.
-  static const bool side_replay = getenv("MPH_SIDE_REPLAY") != nullptr;
-  const bool side = side_replay && d.rp1 > d.rp0;
-  if (side) {
+  // The serial replay is a dependent chain per unit (a few hundred iterations, latency bound) over 1 % of the transcripts, all
+  // of them host class: nothing on the main chain needs its results before the download. In the somatic mode it therefore
+  // runs on its own stream, followed there by the K3 walk of the host-class keys and the compaction of the host-class windows
+  // (K4), while the main stream goes on with the K3 walk of the device-class keys and the record kernels and joins at the end.
+  // MPH_SIDE_REPLAY: "k1" (default) starts the side chain right after K1, so the replay overlaps K2, K3 and the record
+  // kernels; "k2" starts it when K2 is done (K2 then runs alone); "0" puts everything on one stream, which is how bench.py
+  // times the kernels one by one for its roofline line. MPH_REPLAY_PER_SM > 0 makes k_replay a persistent grid of that many
+  // single-warp CTAs per SM (default: one CTA per unit). `normal` mode: the replay runs beside K2 and joins before K3.
+  // Measured on B200 (whole-exome shard): DESIGN.md section 5.
+  // (read per call, not cached: bench.py times the kernels alone for the roofline line by switching the side chain off)
+  const int side_cfg = [] { const char* e = getenv("MPH_SIDE_REPLAY"); return !e ? 1 : (*e == '0' ? 0 : (strcmp(e, "k2") == 0 ? 2 : 1)); }();
+  const uint32_t replay_per_sm = [] { const char* e = getenv("MPH_REPLAY_PER_SM"); const int v = e ? atoi(e) : 0; return uint32_t(v > 0 ? v : 0); }();
+  const bool side = side_cfg != 0 && d.rp1 > d.rp0;
+  const bool side_from_k1 = side && (side_cfg == 1 || d.mode == 1);
+  const uint32_t replay_ctas = replay_per_sm * uint32_t(c->sm_count);
+  if (side_from_k1) {
     CU(cudaEventRecord(c->ev_rp[0], c->stream));
     CU(cudaStreamWaitEvent(c->replay_stream, c->ev_rp[0], 0));
     CU(cudaEventRecord(c->ev_rp[1], c->replay_stream));
-    mphk::launch_replay(d, c->replay_stream);
+    mphk::launch_replay(d, c->replay_stream, replay_ctas);
     CU(cudaEventRecord(c->ev_rp[2], c->replay_stream));
-  } else {
+  } else if (!side) {
     mphk::launch_replay(d, c->stream);
   }
   CU(cudaEventRecord(c->ev[8], c->stream));
   mphk::launch_window_hist(d, c->stream);
-  if (side) CU(cudaStreamWaitEvent(c->stream, c->ev_rp[2], 0));
   CU(cudaEventRecord(c->ev[4], c->stream));
   c->replay_on_side = side;
-  mphk::launch_assemble(d, c->stream);
-  CU(cudaEventRecord(c->ev[5], c->stream));
-  mphk::launch_compact(d, c->stream);
-  CU(cudaEventRecord(c->ev[6], c->stream));
-  mphk::launch_records(d, c->stream);
+  c->side_chain = side && d.mode == 0;
+  if (c->side_chain) {
+    // side chain: (the replay,) host-class keys (K2's and the replay's) and host-class windows
+    CU(cudaStreamWaitEvent(c->replay_stream, c->ev[4], 0));
+    if (!side_from_k1) {
+      CU(cudaEventRecord(c->ev_rp[1], c->replay_stream));
+      mphk::launch_replay(d, c->replay_stream, replay_ctas);
+      CU(cudaEventRecord(c->ev_rp[2], c->replay_stream));
+    }
+    CU(cudaEventRecord(c->ev_rp[3], c->replay_stream));
+    mphk::launch_assemble(d, c->replay_stream, mphk::ASM_HOST_CLASS);
+    mphk::launch_compact(d, c->replay_stream);
+    CU(cudaEventRecord(c->ev_rp[4], c->replay_stream));
+    // main chain: device-class keys, record kernels
+    mphk::launch_assemble(d, c->stream, mphk::ASM_DEVICE_CLASS);
+    CU(cudaEventRecord(c->ev[5], c->stream));
+    CU(cudaEventRecord(c->ev[6], c->stream));
+    mphk::launch_records(d, c->stream);
+    CU(cudaEventRecord(c->ev[7], c->stream));
+    CU(cudaStreamWaitEvent(c->stream, c->ev_rp[4], 0));
+  } else {
+    if (side) CU(cudaStreamWaitEvent(c->stream, c->ev_rp[2], 0));  // normal mode: K3 needs the replay's keys
+    mphk::launch_assemble(d, c->stream);
+    CU(cudaEventRecord(c->ev[5], c->stream));
+    mphk::launch_compact(d, c->stream);
+    CU(cudaEventRecord(c->ev[6], c->stream));
+    mphk::launch_records(d, c->stream);
+    CU(cudaEventRecord(c->ev[7], c->stream));
+  }
   CU(cudaEventRecord(c->ev[9], c->stream));
   CU(cudaGetLastError());
+}
+
+// per-kernel-group device times of the last run_kernels (CUDA events on the streams the kernels ran on), added to ctx->timing.
+// With the side chain: replay_ms is k_replay alone on its stream, k4_ms the host-class K3 walk + compaction that follow it
+// there, k2 / k3 / k5 the main chain (K3 = device-class keys); kernels_ms is the whole chain from the first kernel to the join.
+void add_kernel_times(mph_ctx* c) {
+  float ms;
+  CU(cudaEventElapsedTime(&ms, c->ev[2], c->ev[3])); c->timing.k1_ms += ms;
+  if (c->replay_on_side) { CU(cudaEventElapsedTime(&ms, c->ev_rp[1], c->ev_rp[2])); c->timing.replay_ms += ms; }
+  else { CU(cudaEventElapsedTime(&ms, c->ev[3], c->ev[8])); c->timing.replay_ms += ms; }
+  CU(cudaEventElapsedTime(&ms, c->ev[8], c->ev[4])); c->timing.k2_ms += ms;
+  CU(cudaEventElapsedTime(&ms, c->ev[2], c->ev[9])); c->timing.kernels_ms += ms;
+  CU(cudaEventElapsedTime(&ms, c->ev[4], c->ev[5])); c->timing.k3_ms += ms;
+  if (c->side_chain) { CU(cudaEventElapsedTime(&ms, c->ev_rp[3], c->ev_rp[4])); c->timing.k4_ms += ms; }
+  else { CU(cudaEventElapsedTime(&ms, c->ev[5], c->ev[6])); c->timing.k4_ms += ms; }
+  CU(cudaEventElapsedTime(&ms, c->ev[6], c->ev[7])); c->timing.k5_ms += ms;
 }
 
 // resize of a download buffer that keeps it page-locked (device -> host copies into pageable memory go through a bounce
@@ -532,14 +584,7 @@ void fetch_stage(mph_ctx* c, const Stage& s, PhaseRaw& raw, uint64_t* n_iw_total
     break;
   }
   float ms;
-  CU(cudaEventElapsedTime(&ms, c->ev[2], c->ev[3])); c->timing.k1_ms += ms;
-  if (c->replay_on_side) { CU(cudaEventElapsedTime(&ms, c->ev_rp[1], c->ev_rp[2])); c->timing.replay_ms += ms; }
-  else { CU(cudaEventElapsedTime(&ms, c->ev[3], c->ev[8])); c->timing.replay_ms += ms; }
-  CU(cudaEventElapsedTime(&ms, c->ev[8], c->ev[4])); c->timing.k2_ms += ms;  // includes the wait for a replay that outlasts K2
-  CU(cudaEventElapsedTime(&ms, c->ev[2], c->ev[9])); c->timing.kernels_ms += ms;
-  CU(cudaEventElapsedTime(&ms, c->ev[4], c->ev[5])); c->timing.k3_ms += ms;
-  CU(cudaEventElapsedTime(&ms, c->ev[5], c->ev[6])); c->timing.k4_ms += ms;
-  CU(cudaEventElapsedTime(&ms, c->ev[6], c->ev[9])); c->timing.k5_ms += ms;
+  add_kernel_times(c);
   raw.err = ctr[mphk::CTR_ERR];
   if (raw.err & MPH_E_SLICE) throw Fatal("slice index out of range");
   if (raw.err & MPH_E_SEQ_SLOT) throw Unsupported("assembled haplotype longer than the sequence slot");
@@ -926,16 +971,26 @@ void dev_translate(mph_ctx* c, const uint8_t* nt, const uint64_t* off, const int
 
 void dev_set_load(mph_ctx* c, const uint8_t* peptides, uint32_t k, uint64_t n) {
   CU(cudaSetDevice(c->device));
-  if (k == 0 || k > 12) throw Unsupported("peptide length must be 1..12 for the device hash set");
+  if (k == 0 || k > 255) throw Unsupported("peptide length must be 1..255");
+  const bool longk = k > 12;  // 5 bits per letter fill a 64-bit key up to 12 letters; longer peptides are compared as bytes
+  if (longk && n > 0xFFFFFFF0ull) throw Unsupported("more than 2^32 peptides of more than 12 letters");
   uint64_t slots = 1024;
   while (slots < 2 * n + 16) slots <<= 1;
-  c->set_table.ensure(slots);
+  if (longk) c->set_idx.ensure(slots);
+  else c->set_table.ensure(slots);
   c->set_mask = slots - 1;
   c->set_k = k;
-  CU(cudaMemsetAsync(c->set_table.p, 0, slots * 8, c->stream));
+  if (longk) CU(cudaMemsetAsync(c->set_idx.p, 0, slots * 4, c->stream));
+  else CU(cudaMemsetAsync(c->set_table.p, 0, slots * 8, c->stream));
   c->sums.ensure(2);
   CU(cudaMemsetAsync(c->sums.p, 0, 16, c->stream));
-  if (n) {
+  if (n && longk) {
+    c->set_bytes.ensure(n * k);  // stays resident: the slots point into it
+    CU(cudaMemcpyAsync(c->set_bytes.p, peptides, n * k, cudaMemcpyHostToDevice, c->stream));
+    mphk::launch_set_insert_long(c->set_bytes.p, k, n, c->set_idx.p, c->set_mask, c->sums.p, c->stream);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(c->stream));
+  } else if (n) {
     DevBuf<uint8_t> d_p;
     d_p.ensure(n * k);
     try {
@@ -957,7 +1012,7 @@ void dev_set_load(mph_ctx* c, const uint8_t* peptides, uint32_t k, uint64_t n) {
 
 void dev_set_probe(mph_ctx* c, const uint8_t* queries, uint32_t k, uint64_t n, uint8_t* hit) {
   CU(cudaSetDevice(c->device));
-  if (!c->set_table.p) throw std::runtime_error("no peptide set loaded");
+  if (c->set_k == 0) throw std::runtime_error("no peptide set loaded");
   if (n == 0) return;
   if (k != c->set_k) {  // a peptide of another length cannot be in the set
     memset(hit, 0, n);
@@ -968,7 +1023,8 @@ void dev_set_probe(mph_ctx* c, const uint8_t* queries, uint32_t k, uint64_t n, u
   try {
     CU(cudaMemcpyAsync(d_q.p, queries, n * k, cudaMemcpyHostToDevice, c->stream));
     CU(cudaEventRecord(c->ev[2], c->stream));
-    mphk::launch_set_probe(d_q.p, k, n, c->set_table.p, c->set_mask, d_h.p, c->stream);
+    if (k > 12) mphk::launch_set_probe_long(d_q.p, k, n, c->set_bytes.p, c->set_idx.p, c->set_mask, d_h.p, c->stream);
+    else mphk::launch_set_probe(d_q.p, k, n, c->set_table.p, c->set_mask, d_h.p, c->stream);
     CU(cudaEventRecord(c->ev[3], c->stream));
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(hit, d_h.p, n, cudaMemcpyDeviceToHost, c->stream));
@@ -985,14 +1041,15 @@ void dev_set_probe(mph_ctx* c, const uint8_t* queries, uint32_t k, uint64_t n, u
 
 std::vector<std::string> dev_set_export(mph_ctx* c) {
   std::vector<std::string> out;
-  if (!c->set_table.p || c->set_distinct == 0) return out;
+  if (c->set_k == 0 || c->set_distinct == 0) return out;
   const uint32_t k = c->set_k;
   DevBuf<uint8_t> d_o;
   d_o.ensure(c->set_distinct * k);
   std::vector<uint8_t> host(c->set_distinct * k);
   try {
     CU(cudaMemsetAsync(c->sums.p, 0, 16, c->stream));
-    mphk::launch_set_export(c->set_table.p, c->set_mask + 1, k, d_o.p, c->sums.p, c->stream);
+    if (k > 12) mphk::launch_set_export_long(c->set_idx.p, c->set_mask + 1, c->set_bytes.p, k, d_o.p, c->sums.p, c->stream);
+    else mphk::launch_set_export(c->set_table.p, c->set_mask + 1, k, d_o.p, c->sums.p, c->stream);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(host.data(), d_o.p, host.size(), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
@@ -1051,6 +1108,7 @@ int mph_ctx_create(int device, mph_ctx** out) {
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&c->replay_stream, cudaStreamNonBlocking));
+    { int sms = 0; if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) c->sm_count = sms; }
     for (auto& e3 : c->ev_rp) CU(cudaEventCreate(&e3));
     for (auto& e2 : c->ev) CU(cudaEventCreate(&e2));
   });
@@ -1205,15 +1263,8 @@ int mph_phase_resident(mph_ctx* ctx) {
     CU(cudaMemsetAsync(ctx->sums.p, 0, 3 * sizeof(unsigned long long), ctx->stream));
     run_kernels(ctx);
     CU(cudaStreamSynchronize(ctx->stream));
-    float ms;
-    CU(cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3])); ctx->timing.k1_ms = ms;
-    if (ctx->replay_on_side) { CU(cudaEventElapsedTime(&ms, ctx->ev_rp[1], ctx->ev_rp[2])); ctx->timing.replay_ms = ms; }
-    else { CU(cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[8])); ctx->timing.replay_ms = ms; }
-    CU(cudaEventElapsedTime(&ms, ctx->ev[8], ctx->ev[4])); ctx->timing.k2_ms = ms;
-    CU(cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[9])); ctx->timing.kernels_ms = ms;
-    CU(cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5])); ctx->timing.k3_ms = ms;
-    CU(cudaEventElapsedTime(&ms, ctx->ev[5], ctx->ev[6])); ctx->timing.k4_ms = ms;
-    CU(cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[9])); ctx->timing.k5_ms = ms;
+    ctx->timing.k1_ms = ctx->timing.k2_ms = ctx->timing.k3_ms = ctx->timing.k4_ms = ctx->timing.k5_ms = ctx->timing.replay_ms = ctx->timing.kernels_ms = 0;
+    add_kernel_times(ctx);
     ctx->kernels_done = true;
   });
 }

@@ -348,17 +348,16 @@ MPH_HD MphPair mph_rev_state(const MphSegment& g, const MphVar* vars, uint32_t k
 // 64 bytes at a time, so that no per-thread message buffer is needed.
 typedef struct {
   uint32_t h[5];
-  uint32_t w[16];
-  uint32_t fill;
-  uint32_t len;
+  uint32_t w[16];  // message words of the current block (big-endian), written one whole word at a time
+  uint32_t acc;    // the bytes of the word being filled
+  uint32_t len;    // bytes pushed so far
 } MphSha1;
 
 MPH_HD uint32_t mph_rol(uint32_t v, int s) { return (v << s) | (v >> (32 - s)); }
 
 MPH_HD void mph_sha1_init(MphSha1* s) {
   s->h[0] = 0x67452301u; s->h[1] = 0xEFCDAB89u; s->h[2] = 0x98BADCFEu; s->h[3] = 0x10325476u; s->h[4] = 0xC3D2E1F0u;
-  for (int i = 0; i < 16; ++i) s->w[i] = 0;
-  s->fill = 0;
+  s->acc = 0;
   s->len = 0;
 }
 
@@ -395,14 +394,17 @@ MPH_HD void mph_sha1_block(MphSha1* s) {
   for (int i = 60; i < 80; ++i) MPH_SHA1_ROUND(i, b ^ c ^ d, 0xCA62C1D6u);
 #undef MPH_SHA1_ROUND
   s->h[0] += a; s->h[1] += b; s->h[2] += c; s->h[3] += d; s->h[4] += e;
-  for (int i = 0; i < 16; ++i) s->w[i] = 0;
-  s->fill = 0;
 }
 
+// One byte: shifted into the word accumulator; a full word is stored once (one local-memory store per four bytes on the
+// device - the first version did a read-modify-write of w[] per byte, a third of K3's samples in the round-2 ncu capture).
 MPH_HD void mph_sha1_byte(MphSha1* s, uint8_t v) {
-  s->w[s->fill >> 2] |= (uint32_t)v << (24 - 8 * (s->fill & 3u));
+  s->acc = (s->acc << 8) | v;
   s->len += 1;
-  if (++s->fill == 64) mph_sha1_block(s);
+  if ((s->len & 3u) == 0) {
+    s->w[((s->len >> 2) - 1u) & 15u] = s->acc;
+    if ((s->len & 63u) == 0) mph_sha1_block(s);
+  }
 }
 
 MPH_HD void mph_sha1_decimal(MphSha1* s, uint32_t v) {
@@ -412,6 +414,41 @@ MPH_HD void mph_sha1_decimal(MphSha1* s, uint32_t v) {
   while (n) mph_sha1_byte(s, dig[--n]);
 }
 
+// decimal rendering of one byte (0..255) without a digit buffer
+MPH_HD void mph_sha1_decimal_u8(MphSha1* s, uint32_t v) {
+  if (v >= 100u) {
+    const uint32_t h = v >= 200u ? 2u : 1u;
+    mph_sha1_byte(s, (uint8_t)('0' + h));
+    v -= 100u * h;
+    const uint32_t t = (v * 205u) >> 11;  // v / 10 for v < 100
+    mph_sha1_byte(s, (uint8_t)('0' + t));
+    mph_sha1_byte(s, (uint8_t)('0' + (v - 10u * t)));
+  } else if (v >= 10u) {
+    const uint32_t t = (v * 205u) >> 11;
+    mph_sha1_byte(s, (uint8_t)('0' + t));
+    mph_sha1_byte(s, (uint8_t)('0' + (v - 10u * t)));
+  } else {
+    mph_sha1_byte(s, (uint8_t)('0' + v));
+  }
+}
+
+// padding, length and the last block(s); returns the leading 64 bits of the digest
+MPH_HD uint64_t mph_sha1_finish64(MphSha1* s) {
+  const uint32_t bits = s->len * 8u;  // messages are far below 2^29 bytes
+  mph_sha1_byte(s, 0x80);
+  while (s->len & 3u) mph_sha1_byte(s, 0);
+  uint32_t idx = (s->len >> 2) & 15u;  // next word of the block (0: the block was just hashed)
+  if (idx > 14u) {                     // no room for the 64-bit length: pad this block out and start another
+    s->w[15] = 0;
+    mph_sha1_block(s);
+    idx = 0;
+  }
+  for (uint32_t i = idx; i < 15u; ++i) s->w[i] = 0;
+  s->w[15] = bits;
+  mph_sha1_block(s);
+  return ((uint64_t)s->h[0] << 32) | s->h[1];
+}
+
 // leading 64 bits of sha1(format!("{:?}{}{}", seq, transcript_id, offset))
 MPH_HD uint64_t mph_record_id64(const uint8_t* seq, uint32_t n, const uint8_t* tx_id, uint32_t tx_len, uint32_t offset) {
   MphSha1 s;
@@ -419,17 +456,12 @@ MPH_HD uint64_t mph_record_id64(const uint8_t* seq, uint32_t n, const uint8_t* t
   mph_sha1_byte(&s, '[');
   for (uint32_t i = 0; i < n; ++i) {
     if (i) { mph_sha1_byte(&s, ','); mph_sha1_byte(&s, ' '); }
-    mph_sha1_decimal(&s, seq[i]);
+    mph_sha1_decimal_u8(&s, seq[i]);
   }
   mph_sha1_byte(&s, ']');
   for (uint32_t i = 0; i < tx_len; ++i) mph_sha1_byte(&s, tx_id[i]);
   mph_sha1_decimal(&s, offset);
-  const uint32_t bits = s.len * 8u;
-  mph_sha1_byte(&s, 0x80);
-  while (s.fill != 56) mph_sha1_byte(&s, 0);
-  s.w[15] = bits;  // 64-bit big-endian length; messages are far below 2^29 bytes
-  mph_sha1_block(&s);
-  return ((uint64_t)s.h[0] << 32) | s.h[1];
+  return mph_sha1_finish64(&s);
 }
 
 // ------------------------------------------------------------------ K3: haplotype assembly

@@ -1,5 +1,7 @@
 // kernel_common.cuh — constants and small device helpers shared by the phasing kernels (internal to csrc/kernels).
 #pragma once
+#include <algorithm>
+
 #include "phase_kernels.cuh"
 
 #include "../core/phase_core.h"

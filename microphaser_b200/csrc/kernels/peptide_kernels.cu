@@ -108,7 +108,75 @@ __global__ void __launch_bounds__(256) k_set_export(const unsigned long long* __
   for (int i = (int)k - 1; i >= 0; --i) { o[i] = (uint8_t)('A' + (key & 31) - 1); key >>= 5; }
 }
 
+// ---- peptides longer than 12 letters (MHC-II runs use 13-25): the slots hold 1 + the index of a peptide in the set's own
+// byte array, which stays on the device; equality is a byte comparison against that immutable array, so the insert needs
+// only a 32-bit compare-and-swap on the slot. Any k works.
+__device__ __forceinline__ uint64_t hash_bytes(const uint8_t* p, uint32_t k) {
+  uint64_t h = 0xcbf29ce484222325ull;
+  for (uint32_t i = 0; i < k; ++i) h = (h ^ p[i]) * 0x100000001b3ull;
+  return mix64(h);
+}
+__device__ __forceinline__ bool same_bytes(const uint8_t* a, const uint8_t* b, uint32_t k) {
+  for (uint32_t i = 0; i < k; ++i)
+    if (a[i] != b[i]) return false;
+  return true;
+}
+
+__global__ void __launch_bounds__(256) k_set_insert_long(const uint8_t* __restrict__ peptides, uint32_t k, uint64_t n, uint32_t* table, uint64_t mask,
+                                                         unsigned long long* n_distinct) {
+  const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint8_t* me = peptides + i * k;
+  uint64_t slot = hash_bytes(me, k) & mask;
+  for (;;) {
+    const uint32_t prev = atomicCAS(&table[slot], 0u, (uint32_t)(i + 1));
+    if (prev == 0u) { atomicAdd(n_distinct, 1ull); return; }
+    if (same_bytes(peptides + (uint64_t)(prev - 1) * k, me, k)) return;
+    slot = (slot + 1) & mask;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_set_probe_long(const uint8_t* __restrict__ queries, uint32_t k, uint64_t n, const uint8_t* __restrict__ peptides,
+                                                        const uint32_t* __restrict__ table, uint64_t mask, uint8_t* __restrict__ hit) {
+  const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint8_t* me = queries + i * k;
+  uint64_t slot = hash_bytes(me, k) & mask;
+  uint8_t h = 0;
+  for (;;) {
+    const uint32_t v = table[slot];
+    if (v == 0u) break;
+    if (same_bytes(peptides + (uint64_t)(v - 1) * k, me, k)) { h = 1; break; }
+    slot = (slot + 1) & mask;
+  }
+  hit[i] = h;
+}
+
+__global__ void __launch_bounds__(256) k_set_export_long(const uint32_t* __restrict__ table, uint64_t slots, const uint8_t* __restrict__ peptides, uint32_t k,
+                                                         uint8_t* out, unsigned long long* cursor) {
+  const uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  if (s >= slots) return;
+  const uint32_t v = table[s];
+  if (!v) return;
+  const unsigned long long at = atomicAdd(cursor, 1ull);
+  const uint8_t* src = peptides + (uint64_t)(v - 1) * k;
+  uint8_t* o = out + at * k;
+  for (uint32_t i = 0; i < k; ++i) o[i] = src[i];
+}
+
 }  // namespace
+
+void launch_set_insert_long(const uint8_t* peptides, uint32_t k, uint64_t n, uint32_t* table, uint64_t mask, unsigned long long* n_distinct, cudaStream_t st) {
+  if (n) MPH_LAUNCH(k_set_insert_long, ((unsigned)((n + 255) / 256), 256, 0, st), peptides, k, n, table, mask, n_distinct);
+}
+void launch_set_probe_long(const uint8_t* queries, uint32_t k, uint64_t n, const uint8_t* peptides, const uint32_t* table, uint64_t mask, uint8_t* hit,
+                           cudaStream_t st) {
+  if (n) MPH_LAUNCH(k_set_probe_long, ((unsigned)((n + 255) / 256), 256, 0, st), queries, k, n, peptides, table, mask, hit);
+}
+void launch_set_export_long(const uint32_t* table, uint64_t slots, const uint8_t* peptides, uint32_t k, uint8_t* out, unsigned long long* cursor,
+                            cudaStream_t st) {
+  if (slots) MPH_LAUNCH(k_set_export_long, ((unsigned)((slots + 255) / 256), 256, 0, st), table, slots, peptides, k, out, cursor);
+}
 
 void launch_translate(const uint8_t* nt, const uint64_t* off, const int8_t* frame, uint64_t n, uint8_t* aa, const uint64_t* aa_off, uint8_t* bad,
                       cudaStream_t st) {

@@ -20,6 +20,8 @@
 // No tensor cores: nothing here is a dense contraction; the path is integer / byte work bounded by
 // HBM and L2 bandwidth and by instruction issue in K2.
 #include "phase_kernels.cuh"
+#include <cstdlib>
+
 #include "kernel_common.cuh"
 
 namespace mphk {
@@ -406,7 +408,10 @@ __global__ void __launch_bounds__(RR_THREADS) k_read_runs(const DeviceBatch d) {
 constexpr int K2_LANE_KEYS = 4;
 constexpr int K2B_WARPS = 4;
 
-__global__ void __launch_bounds__(K2B_WARPS * 32) k_window_hist(const DeviceBatch d) {
+// MINB: CTAs per SM the register allocation aims at (8 -> 64 registers, 10 -> 48 with a few spilled words); both are
+// compiled and MPH_K2B_MINB picks one at run time (the default is the one measured faster on B200).
+template <int MINB>
+__global__ void __launch_bounds__(K2B_WARPS * 32, MINB) k_window_hist(const DeviceBatch d) {
   // per-lane key tables, [key][lane] so that a warp touches 32 distinct banks
   __shared__ uint64_t t_hap[K2B_WARPS][K2_LANE_KEYS][32];
   __shared__ uint32_t t_cnt[K2B_WARPS][K2_LANE_KEYS][32];
@@ -607,12 +612,19 @@ __global__ void __launch_bounds__(K2B_WARPS * 32) k_window_hist(const DeviceBatc
 // One thread per extra histogram key (haplotype != 0): the sequence walk of print_haplotypes
 // (:458-603) into thread-local buffers, then the stop test; the bytes are kept only for haplotypes
 // that can be written (n_somatic > 0) or merged across a splice junction (boundary windows).
-__global__ void __launch_bounds__(128) k_assemble(const DeviceBatch d) {
-  const uint32_t n_front = min(d.counters[CTR_HIST], d.hist_cap), n_back = min(d.counters[CTR_HISTD], d.hist_cap);
-  if (n_front + n_back > d.hist_cap) {  // the two ends of the key arena met: the host retries with a larger one
+// `part`: ASM_ALL walks both ends of the key arena; ASM_DEVICE_CLASS only the keys of device-class transcripts (the back),
+// while the serial replay may still be appending host-class keys at the front on its side stream; ASM_HOST_CLASS only the
+// front, after the replay (capi.cu).
+__global__ void __launch_bounds__(128) k_assemble(const DeviceBatch d, const int part) {
+  uint32_t n_front = min(d.counters[CTR_HIST], d.hist_cap);
+  const uint32_t n_back_all = min(d.counters[CTR_HISTD], d.hist_cap);
+  if (n_front + n_back_all > d.hist_cap) {  // the two ends of the key arena met: the host retries with a larger one
     if (blockIdx.x == 0 && threadIdx.x == 0) raise(d, MPH_E_HIST_OVERFLOW);
     return;
   }
+  uint32_t n_back = n_back_all;
+  if (part == ASM_DEVICE_CLASS) n_front = 0;
+  if (part == ASM_HOST_CLASS) n_back = 0;
   const uint32_t n = n_front + n_back;
   uint8_t seq[MAX_SEQ_CAP], germ[MAX_SEQ_CAP];
   const uint32_t cap = d.seq_cap;
@@ -621,6 +633,9 @@ __global__ void __launch_bounds__(128) k_assemble(const DeviceBatch d) {
     const uint64_t hap = d.hist[x].hap;
     if (hap == 0) continue;  // a (hap 0, frame != 0) key shares the window's haplotype-0 record
     const uint32_t code = d.hist_win[x];
+    // (a front that grew into the back while this launch walks it - ASM_DEVICE_CLASS beside the replay - is caught by the
+    // ASM_HOST_CLASS launch, which raises the overflow; until then a clobbered key must not send the walk out of bounds)
+    if ((code >> 5) >= d.n_chunks) continue;
     const MphChunk ch = d.chunks[code >> 5];
     const MphSegment sg = d.segs[ch.seg];
     const uint32_t i = ch.i_first + (code & 31u);
@@ -761,13 +776,15 @@ void launch_window_hist(const DeviceBatch& d, cudaStream_t st) {
     MPH_LAUNCH(k_read_runs_plan, ((nb + 255) / 256, 256, 0, st), d, nb);
     MPH_LAUNCH(k_read_runs, (nb, RR_THREADS, 0, st), d);
   }
-  MPH_LAUNCH(k_window_hist, ((nc + K2B_WARPS - 1) / K2B_WARPS, K2B_WARPS * 32, 0, st), d);
+  static const int minb = [] { const char* e = getenv("MPH_K2B_MINB"); return e ? atoi(e) : 8; }();
+  if (minb >= 10) MPH_LAUNCH(k_window_hist<10>, ((nc + K2B_WARPS - 1) / K2B_WARPS, K2B_WARPS * 32, 0, st), d);
+  else MPH_LAUNCH(k_window_hist<8>, ((nc + K2B_WARPS - 1) / K2B_WARPS, K2B_WARPS * 32, 0, st), d);
   // windows with more distinct haplotypes than a lane table holds (rare): one warp per window
   MPH_LAUNCH(k_window_hist_wide, (148 * 8, K2_WARPS * 32, 0, st), d);
 }
-void launch_assemble(const DeviceBatch& d, cudaStream_t st) {
+void launch_assemble(const DeviceBatch& d, cudaStream_t st, int part) {
   if (d.c1 > d.c0 && d.mode == 1) launch_assemble_normal(d, st);
-  else if (d.c1 > d.c0) MPH_LAUNCH(k_assemble, (148 * 8, 128, 0, st), d);  // grid-stride over the key arena (its size lives on the device)
+  else if (d.c1 > d.c0) MPH_LAUNCH(k_assemble, (part == ASM_HOST_CLASS ? 148 * 2 : 148 * 8, 128, 0, st), d, part);  // grid-stride over the key arena (its size lives on the device)
 }
 void launch_compact(const DeviceBatch& d, cudaStream_t st) {
   const uint32_t nb = (d.w1 - d.w0 + SCAN_THREADS - 1) / SCAN_THREADS;

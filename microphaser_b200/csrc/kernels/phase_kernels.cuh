@@ -140,15 +140,16 @@ struct DeviceBatch {
   uint32_t* win_depth = nullptr;       // normal mode, per window: depth | (plain window begins / ends with a stop codon) << 31
 };
 
-enum { CTR_HIST = 0, CTR_SEQ = 1, CTR_NIW = 2, CTR_ERR = 3, CTR_OVF = 4, CTR_VLIST = 5, CTR_SEQD = 6, CTR_NRW = 7, CTR_MERGE = 8, CTR_NREC = 9, CTR_RECSEQ = 10, CTR_HISTD = 11, CTR_NJ = 12, CTR_COUNT = 16 };
+enum { CTR_HIST = 0, CTR_SEQ = 1, CTR_NIW = 2, CTR_ERR = 3, CTR_OVF = 4, CTR_VLIST = 5, CTR_SEQD = 6, CTR_NRW = 7, CTR_MERGE = 8, CTR_NREC = 9, CTR_RECSEQ = 10, CTR_HISTD = 11, CTR_NJ = 12, CTR_RPQ = 13, CTR_MQ = 14, CTR_COUNT = 16 };
 
 void launch_read_decode(const DeviceBatch& d, cudaStream_t st);
 void launch_allele_call(const DeviceBatch& d, cudaStream_t st);
 void launch_window_hist(const DeviceBatch& d, cudaStream_t st);
-void launch_replay(const DeviceBatch& d, cudaStream_t st);                // replay_kernels.cu
+void launch_replay(const DeviceBatch& d, cudaStream_t st, uint32_t max_ctas = 0);  // replay_kernels.cu; max_ctas: size of the persistent grid (0 = one CTA per unit)
 void launch_window_hist_normal(const DeviceBatch& d, cudaStream_t st);    // normal_kernels.cu (called by launch_window_hist in mode 1)
 void launch_assemble_normal(const DeviceBatch& d, cudaStream_t st);
-void launch_assemble(const DeviceBatch& d, cudaStream_t st);
+enum { ASM_ALL = 0, ASM_DEVICE_CLASS = 1, ASM_HOST_CLASS = 2 };  // which end of the key arena a K3 launch walks
+void launch_assemble(const DeviceBatch& d, cudaStream_t st, int part = ASM_ALL);
 void launch_compact(const DeviceBatch& d, cudaStream_t st);
 void launch_live_depth(const DeviceBatch& d, cudaStream_t st);            // record_kernels.cu
 void launch_records(const DeviceBatch& d, cudaStream_t st);               // record_kernels.cu

@@ -13,6 +13,8 @@
 //
 // All of it is integer / byte work on a few hundred thousand windows per shard; the kernels are latency bound and
 // short next to K1-K3.
+#include <cstdlib>
+
 #include "kernel_common.cuh"
 #include "phase_kernels.cuh"
 
@@ -197,9 +199,15 @@ struct MphWarpOps {
 // junction merges (:1497-1908): one warp per junction; the records go to the merge arena, k_rc_emit places them
 constexpr int RM_WARPS = 4;
 __global__ void __launch_bounds__(RM_WARPS * 32) k_rc_merge(const DeviceBatch d) {
-  const uint32_t j = blockIdx.x * RM_WARPS + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  if (j >= d.counters[CTR_NJ]) return;
+  const uint32_t nj = d.counters[CTR_NJ];
+  // the number of junctions lives on the device: the warps of a grid of a few CTAs per SM pull them from a queue (a merge
+  // takes anything from a few hundred to tens of thousands of cycles, a static split leaves warps idle)
+  for (;;) {
+  uint32_t j = 0;
+  if (lane == 0) j = atomicAdd(&d.counters[CTR_MQ], 1u);
+  j = __shfl_sync(FULL, j, 0);
+  if (j >= nj) return;
   const uint32_t x = d.rw_junc[j];
   const uint32_t w = d.rw[x];
   const uint32_t si = d.win_seg[w];
@@ -226,6 +234,8 @@ __global__ void __launch_bounds__(RM_WARPS * 32) k_rc_merge(const DeviceBatch d)
     if (nm) atomicAdd(&d.rc_blocks[x / RC_THREADS], nm);
     raise(d, err);
   }
+  __syncwarp();
+  }
 }
 
 // record ids of the junction records: one thread per slot of the merge arena (sha1 is ~4 k instructions per record; inside
@@ -241,6 +251,7 @@ __global__ void __launch_bounds__(128) k_rc_ids(const DeviceBatch d) {
 }
 
 __global__ void __launch_bounds__(RC_THREADS) k_rc_emit(const DeviceBatch d) {
+  if (blockIdx.x * RC_THREADS >= d.counters[CTR_NRW]) return;  // the grid covers the host's upper bound
   const uint32_t x = blockIdx.x * RC_THREADS + threadIdx.x;
   const bool live = x < d.counters[CTR_NRW];
   const uint32_t info = live ? d.rw_info[x] : 0u;
@@ -437,7 +448,8 @@ void launch_records(const DeviceBatch& d, cudaStream_t st) {
   MPH_LAUNCH(k_rc_stop, (nbl, RC_THREADS, 0, st), d);
   cudaMemsetAsync(d.rc_blocks, 0, (size_t)nbl * sizeof(uint32_t), st);
   MPH_LAUNCH(k_rc_count, (nbl, RC_THREADS, 0, st), d);
-  if (d.s1 > d.s0) MPH_LAUNCH(k_rc_merge, ((d.s1 - d.s0 + RM_WARPS - 1) / RM_WARPS, RM_WARPS * 32, 0, st), d);  // at most one junction per segment
+  static const uint32_t merge_ctas = [] { const char* e = getenv("MPH_MERGE_CTAS"); return e ? (uint32_t)atoi(e) : 148u * 4u; }();  // 0: a warp per segment
+  if (d.s1 > d.s0) MPH_LAUNCH(k_rc_merge, (std::min<uint32_t>((d.s1 - d.s0 + RM_WARPS - 1) / RM_WARPS, merge_ctas ? merge_ctas : 0xFFFFFFFFu), RM_WARPS * 32, 0, st), d);  // at most one junction per segment
   MPH_LAUNCH(k_rc_ids, ((d.m_cap + 127) / 128, 128, 0, st), d);
   MPH_LAUNCH(k_rc_scan, (1, 1024, 0, st), d, nbl, CTR_NREC);
   MPH_LAUNCH(k_rc_emit, (nbl, RC_THREADS, 0, st), d);

@@ -50,12 +50,7 @@ __device__ __forceinline__ void warp_lb2(const uint32_t* __restrict__ a, uint32_
   *c1 = ((g1 == lo || p1 < t1) && b1) ? g1 + (uint32_t)__ffs(b1) - 1u : mph_u32_lb(a, lo, hi, t1);
 }
 
-__global__ void __launch_bounds__(RP_WARPS * 32) k_replay(const DeviceBatch d) {
-  __shared__ RpShared sh_all[RP_WARPS];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t ti = d.rp0 + blockIdx.x * RP_WARPS + warp;
-  if (ti >= d.rp1) return;
-  RpShared& sh = sh_all[warp];
+__device__ __forceinline__ void replay_unit(const DeviceBatch& d, const uint32_t ti, RpShared& sh, const int lane) {
   const MphReplayTx t = d.replay[ti];
   MphReplayCtx c;
   c.read_start = d.read_start; c.read_end = d.read_end; c.read_flags = d.read_flags;
@@ -479,6 +474,25 @@ __global__ void __launch_bounds__(RP_WARPS * 32) k_replay(const DeviceBatch d) {
   raise(d, err);
 }
 
+// Persistent launch: a few single-warp CTAs per SM pull units from a queue (counters[CTR_RPQ]) until it is empty. A unit is
+// a dependent chain of a few hundred iterations, so the kernel is as long as its longest warp whatever the grid; a small
+// grid leaves the registers and shared memory of every SM to the window / record kernels that run beside it on the main
+// stream (capi.cu: the replay and everything that depends on it form a side chain).
+__global__ void __launch_bounds__(RP_WARPS * 32, 20) k_replay(const DeviceBatch d) {
+  __shared__ RpShared sh_all[RP_WARPS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  RpShared& sh = sh_all[warp];
+  for (;;) {
+    uint32_t q = 0;
+    if (lane == 0) q = atomicAdd(&d.counters[CTR_RPQ], 1u);
+    q = __shfl_sync(FULL, q, 0);
+    const uint32_t ti = d.rp0 + q;
+    if (ti >= d.rp1) return;
+    replay_unit(d, ti, sh, lane);
+    __syncwarp();
+  }
+}
+
 // Normal mode: the same replay with the normal-mode matrix (every re-offered copy is kept, entries are
 // (read, haplotype, copies)). The normal-mode residue writes a record for every window, so this path is far from the
 // critical one; lane 0 of a warp runs the single-threaded statement of core/replay_core.h per unit.
@@ -502,9 +516,9 @@ __global__ void __launch_bounds__(64) k_replay_normal(const DeviceBatch d) {
 
 }  // namespace
 
-void launch_replay(const DeviceBatch& d, cudaStream_t st) {
+void launch_replay(const DeviceBatch& d, cudaStream_t st, uint32_t max_ctas) {
   if (d.rp1 > d.rp0 && d.mode == 1) MPH_LAUNCH(k_replay_normal, ((d.rp1 - d.rp0 + 1) / 2, 64, 0, st), d);
-  else if (d.rp1 > d.rp0) MPH_LAUNCH(k_replay, ((d.rp1 - d.rp0 + RP_WARPS - 1) / RP_WARPS, RP_WARPS * 32, 0, st), d);
+  else if (d.rp1 > d.rp0) MPH_LAUNCH(k_replay, (std::min<uint32_t>((d.rp1 - d.rp0 + RP_WARPS - 1) / RP_WARPS, max_ctas ? max_ctas : 0xFFFFFFFFu), RP_WARPS * 32, 0, st), d);
 }
 
 }  // namespace mphk

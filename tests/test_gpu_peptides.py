@@ -161,3 +161,44 @@ def test_hash_probe_at_scale(product):
         truth = np.isin(packed_o, packed)
         assert (truth == hit_out.astype(bool)).all()
     assert hit_out.sum() < 100
+
+
+def test_long_peptides_probe_and_build_match(product, oracle_bin, tmp_path):
+    """Peptide lengths above 12 (MHC-II runs use 13-25; `-l` has no upper bound in src/cli.yaml): the device set compares
+    bytes instead of 5-bit packed keys. Probe against a Python set, build_reference + filter at -l 15 against the oracle."""
+    import microphaser_b200 as m
+    rng = np.random.default_rng(5)
+    letters = np.frombuffer(b"ACDEFGHIKLMNPQRSTVWXY", dtype=np.uint8)
+    for k in (13, 15, 25):
+        members = letters[rng.integers(0, len(letters), size=(200_000, k))]
+        members[1000:2000] = members[:1000]  # duplicates in the input
+        others = letters[rng.integers(0, len(letters), size=(50_000, k))]
+        near = members[rng.integers(0, len(members), size=50_000)].copy()
+        near[:, k - 1] = letters[rng.integers(0, len(letters), size=50_000)]  # differ (mostly) in the last letter only
+        truth = set(map(bytes, members))
+        ctx = m.Context(0)
+        ctx.set_load(members, k)
+        for q in (members[::7], others, near):
+            got = ctx.set_probe(np.ascontiguousarray(q), k)
+            want = np.array([bytes(x) in truth for x in q], dtype=bool)
+            assert (got.astype(bool) == want).all(), k
+        ctx.close()
+    # files: a healthy proteome with repeats, windows of 15 amino acids
+    cod = [c for c, a in CODONS.items() if a != "X"]
+    prng = random.Random(3)
+    with open(tmp_path / "normal.fa", "w") as f:
+        for i in range(40):
+            s = "".join(prng.choice(cod) for _ in range(prng.randint(15, 40)))
+            if i % 5 == 4:
+                s = s[:45] + s[:45]
+            f.write(">tx%d\n%s\n" % (i, s))
+    outs = {}
+    for name, binary in (("oracle", oracle_bin), ("cuda", product[1])):
+        d = tmp_path / name
+        d.mkdir()
+        with open(d / "pep.fa", "wb") as fo:
+            r = subprocess.run([binary, "build_reference", "-r", str(tmp_path / "normal.fa"), "-o", str(d / "peptides.bin"), "-l", "15"], stdout=fo, stderr=subprocess.PIPE)
+        assert r.returncode == 0, r.stderr.decode()
+        outs[name] = {"pep.fa": open(d / "pep.fa", "rb").read(), "set": _set_items(d / "peptides.bin")}
+    assert outs["oracle"]["set"] == outs["cuda"]["set"] and len(outs["cuda"]["set"]) > 100
+    assert outs["oracle"]["pep.fa"] == outs["cuda"]["pep.fa"]

@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "../../microphaser_b200/csrc/host/residue.hpp"
+#include "../../microphaser_b200/csrc/core/phase_core.h"
 
 static int g_fail = 0;
 #define CHECK(c) do { if (!(c)) { fprintf(stderr, "FAIL %s:%d: %s\n", __FILE__, __LINE__, #c); ++g_fail; } } while (0)
@@ -100,7 +101,32 @@ static void sha1_checks() {
   }
 }
 
+// the streaming SHA-1 the kernels use for record ids (core/phase_core.h: word accumulator, explicit padding) against the
+// host SHA-1 on the same message, over every message length around the block and padding boundaries, bytes that render
+// as 1, 2 and 3 decimal digits included
+static void device_sha1_checks() {
+  for (size_t n = 0; n <= 140; ++n)
+    for (size_t tl : {size_t(0), size_t(1), size_t(7), size_t(17), size_t(18), size_t(19), size_t(20), size_t(33)}) {
+      std::vector<uint8_t> seq(n);
+      for (size_t i = 0; i < n; ++i) seq[i] = uint8_t((i * 37 + n * 11 + tl) % 7 == 0 ? (i * 29 + n) & 0xFF : "ACGTacgtN"[(i + n) % 9]);
+      std::string tx;
+      for (size_t i = 0; i < tl; ++i) tx.push_back("ENST0123456789._"[(i * 5 + n) % 16]);
+      const uint32_t offset = uint32_t(n * 7919u + tl * 104729u + (n % 3 == 0 ? 4000000000u : 0u));
+      std::string msg = "[";
+      for (size_t i = 0; i < n; ++i) { if (i) msg += ", "; msg += std::to_string(unsigned(seq[i])); }
+      msg += "]" + tx + std::to_string(offset);
+      mphfmt::Sha1 h;
+      h.update(msg.data(), msg.size());
+      const std::string hex = h.hexdigest().substr(0, 16);
+      const uint64_t got = mph_record_id64(seq.data(), uint32_t(n), reinterpret_cast<const uint8_t*>(tx.data()), uint32_t(tl), offset);
+      char buf[17];
+      snprintf(buf, sizeof buf, "%016llx", (unsigned long long)got);
+      CHECK(hex == buf);
+    }
+}
+
 int main() {
+  device_sha1_checks();
   inline_str_checks<23>();
   inline_str_checks<39>();
   inline_str_checks<3>();
