@@ -1433,15 +1433,15 @@ static void run_somatic_files(const std::vector<mph_ctx*>& ctxs, const char* bam
       gin = &gf;
     }
     const auto t_ingest0 = std::chrono::steady_clock::now();
-    ReadBuffer reads(bam);
-    std::vector<GeneInput> genes = ingest_genes(*gin, reads, vcf, fasta, io);
+    ReadBufferLoader loader(bam);  // the BAM loads on its own thread while this one parses the GTF and fetches reference slices and variants
+    std::vector<GeneInput> genes = ingest_genes_with(*gin, [&]() -> ReadBuffer& { return loader.get(); }, vcf, fasta, io, true);
     const double ingest_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_ingest0).count();
     std::atomic<uint64_t> pack_us{0}, write_us{0};
     // one contiguous gene range per device, no exchange between shards; a device's range is cut
     // further so that several host threads pack in parallel, while its phase calls run one after the other
     const size_t n_dev = ctxs.size();
     uint64_t total_reads = 0;
-    for (auto& g : genes) total_reads += g.reads.size();
+    for (auto& g : genes) total_reads += g.n_reads;
     size_t per_dev = 1;
     if (total_reads > 200000 * n_dev)
       per_dev = std::min<size_t>(12, std::max<size_t>(1, std::thread::hardware_concurrency() / n_dev));

@@ -7,6 +7,9 @@
 #include <sys/mman.h>
 
 #include <chrono>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
 #include <deque>
 #include <istream>
 #include <memory>
@@ -25,7 +28,9 @@ inline uint64_t fnv1a(const std::string& s) {
 // bam::RecordBuffer::fetch over a coordinate-sorted BAM held in memory per contig
 class ReadBuffer {
  public:
-  // one alignment record; sequence / quality / CIGAR live in the buffer's arenas (no allocation per record)
+  // one alignment record. Sequence and qualities are NOT copied: the pointers go into the inflated BGZF batches, which the
+  // buffer keeps alive (the threaded loader) or into the buffer's arenas (the sequential loader); CIGARs are copied into
+  // aligned 32-bit storage.
   struct Rec {
     int32_t tid, pos;
     uint32_t end;  // CigarStringView::end_pos()
@@ -33,35 +38,39 @@ class ReadBuffer {
     uint16_t flag;
     uint8_t mapq;
     uint64_t qname_hash;
-    size_t seq_off, qual_off, cig_off;
+    const uint8_t* seq_p;   // BAM 4-bit bases
+    const uint8_t* qual_p;  // raw phred
+    const uint32_t* cig_p;
     bool is_unmapped() const { return flag & 4; }
   };
 
   explicit ReadBuffer(mphio::BamFile& bam) : bam_(bam) {
     tid_range_.assign(bam.ref_names.size(), {0, 0});
-    // the arenas hold most of the uncompressed file (BAM compresses about 3-4x): one reservation instead of repeated
-    // growth, which would copy several hundred MB (untouched reserved pages cost nothing)
-    if (bam.file_bytes()) {
-      const size_t est = bam.file_bytes() * 4;
-      qual_.reserve(est * 6 / 10);
-      seq_.reserve(est * 3 / 10);
-      cig_.reserve(est / 40);
-      recs_.reserve(est / 300);
-    }
+    if (bam.file_bytes()) recs_.reserve(bam.file_bytes() / 64 + 1024);  // ~100 compressed bytes per 150 bp record; untouched pages cost nothing
     if (bam.inflate_threads() > 1) {
       load_parallel(bam.inflate_threads());
     } else {
+      // sequential loader (one core / MPH_IO_THREADS=1): records are copied into arenas; the arenas move while they grow,
+      // so the records hold offsets until the load is over
       mphio::BamRecord r;
       while (bam.next(r)) {
         if (r.tid < 0 || size_t(r.tid) >= tid_range_.size()) continue;
         Rec x;
         x.tid = r.tid; x.pos = int32_t(r.pos); x.end = uint32_t(r.end_pos()); x.l_seq = r.l_seq; x.n_cigar = uint32_t(r.cigar.size());
         x.flag = r.flag; x.mapq = r.mapq; x.qname_hash = fnv1a_bytes(r.qname.data(), r.qname.size());
-        x.seq_off = seq_.size(); x.qual_off = qual_.size(); x.cig_off = cig_.size();
+        x.seq_p = reinterpret_cast<const uint8_t*>(uintptr_t(seq_.size()));
+        x.qual_p = reinterpret_cast<const uint8_t*>(uintptr_t(qual_.size()));
+        x.cig_p = reinterpret_cast<const uint32_t*>(uintptr_t(cig_.size()));
         seq_.append(r.seq4.data(), r.seq4.size());
         qual_.append(r.qual.data(), r.qual.size());
         cig_.append(r.cigar.data(), r.cigar.size());
         recs_.append(&x, 1);
+      }
+      for (size_t i = 0; i < recs_.size(); ++i) {
+        Rec& x = recs_[i];
+        x.seq_p = seq_.data() + uintptr_t(x.seq_p);
+        x.qual_p = qual_.data() + uintptr_t(x.qual_p);
+        x.cig_p = cig_.data() + uintptr_t(x.cig_p);
       }
     }
     index_by_tid();
@@ -128,8 +137,8 @@ class ReadBuffer {
     }
   }
 
-  // decodes one framed record (p = first byte after the length prefix) into the arenas at the given offsets
-  void decode_record(const uint8_t* p, size_t seq_at, size_t qual_at, size_t cig_at, Rec& x) {
+  // decodes one framed record (p = first byte after the length prefix, bs = the prefix) in place; its CIGAR goes to `cig`
+  static void decode_record(const uint8_t* p, int32_t bs, uint32_t* cig, Rec& x) {
     auto i32 = [&](size_t q) { int32_t v; memcpy(&v, p + q, 4); return v; };
     auto u16 = [&](size_t q) { uint16_t v; memcpy(&v, p + q, 2); return v; };
     x.tid = i32(0);
@@ -138,126 +147,208 @@ class ReadBuffer {
     x.mapq = p[9];
     x.n_cigar = u16(12);
     x.flag = u16(14);
-    x.l_seq = uint32_t(i32(16));
+    const int32_t l_seq = i32(16);
+    if (l_seq < 0 || 32 + size_t(l_read_name) + 4 * size_t(x.n_cigar) + (size_t(l_seq) + 1) / 2 + size_t(l_seq) > size_t(bs)) throw mphio::IoError("corrupt BAM record");
+    x.l_seq = uint32_t(l_seq);
     size_t q = 32;
     x.qname_hash = fnv1a_bytes(reinterpret_cast<const char*>(p + q), l_read_name ? l_read_name - 1 : 0);
     q += l_read_name;
-    x.cig_off = cig_at;
-    if (x.n_cigar) memcpy(cig_.data() + x.cig_off, p + q, 4 * size_t(x.n_cigar));
+    x.cig_p = cig;
+    if (x.n_cigar) memcpy(cig, p + q, 4 * size_t(x.n_cigar));
     int64_t e = x.pos;  // CigarStringView::end_pos(): reference-consuming operations M, D, N, =, X
     for (uint32_t z = 0; z < x.n_cigar; ++z) {
-      const uint32_t c = cig_[x.cig_off + z], op = c & 15;
+      const uint32_t c = cig[z], op = c & 15;
       if (op == mphio::C_M || op == mphio::C_D || op == mphio::C_N || op == mphio::C_EQ || op == mphio::C_X) e += c >> 4;
     }
     x.end = uint32_t(e);
     q += 4 * size_t(x.n_cigar);
-    const size_t sb = (x.l_seq + 1) / 2;
-    x.seq_off = seq_at;
-    memcpy(seq_.data() + x.seq_off, p + q, sb);
-    q += sb;
-    x.qual_off = qual_at;
-    memcpy(qual_.data() + x.qual_off, p + q, x.l_seq);
+    x.seq_p = p + q;
+    x.qual_p = p + q + (x.l_seq + 1) / 2;
   }
 
-  // One inflated batch at a time: a serial scan of the length prefixes finds the record boundaries and the arena
-  // offsets of every record (in place: the batch is not copied; the record that straddles two batches is put together
-  // in a small side buffer); the arenas grow once per batch and a few threads decode the records straight into them.
+  // Threaded loader. The inflated batches are kept (records point into them: nothing but the CIGARs is copied). The calling
+  // thread only walks the length prefixes - a dependent chain, one cache miss per record - and hands slices of framed
+  // records to a small pool that parses the headers while the next batch is being framed; a record that straddles two
+  // batches is put together in a buffer of its own.
   void load_parallel(unsigned threads) {
-    mphio::RawBytes chunk;
-    std::vector<uint8_t> carry;  // the head of a record whose tail is in the next batch
-    struct Item { const uint8_t* p; size_t seq_at, qual_at, cig_at; };
-    std::vector<Item> items;
-    std::vector<uint8_t> straddler;
-    bool more = true;
+    struct Slice {
+      const uint8_t* base = nullptr;      // records at base + off[i] (first byte after the length prefix)
+      std::vector<uint32_t> off;
+      size_t rec0 = 0;                    // first slot in recs_
+    };
+    struct Pool {
+      std::mutex mu;
+      std::condition_variable cv_work, cv_idle;
+      std::deque<Slice> queue;
+      size_t running = 0;
+      bool closed = false;
+      std::exception_ptr err;
+      std::vector<std::thread> threads;
+    } pool;
+    std::mutex cig_mu;
+    auto worker = [&] {
+      for (;;) {
+        Slice sl;
+        {
+          std::unique_lock<std::mutex> lk(pool.mu);
+          pool.cv_work.wait(lk, [&] { return pool.closed || !pool.queue.empty(); });
+          if (pool.queue.empty()) return;
+          sl = std::move(pool.queue.front());
+          pool.queue.pop_front();
+          ++pool.running;
+        }
+        try {
+          // CIGAR storage of the slice: one aligned block (sizes from a first look at the headers, which the parse re-reads hot)
+          size_t n_cig = 0;
+          for (uint32_t o : sl.off) { uint16_t nc; memcpy(&nc, sl.base + o + 12, 2); n_cig += nc; }
+          std::unique_ptr<uint32_t[]> block(new uint32_t[n_cig + 1]);
+          uint32_t* cig = block.get();
+          for (size_t i = 0; i < sl.off.size(); ++i) {
+            const uint8_t* p = sl.base + sl.off[i];
+            int32_t bs;
+            memcpy(&bs, p - 4, 4);
+            Rec& x = recs_[sl.rec0 + i];
+            uint16_t nc;
+            memcpy(&nc, p + 12, 2);
+            if (32 + 4 * size_t(nc) > size_t(bs)) throw mphio::IoError("corrupt BAM record");
+            decode_record(p, bs, cig, x);
+            cig += nc;
+          }
+          std::lock_guard<std::mutex> lk(cig_mu);
+          cig_blocks_.push_back(std::move(block));
+        } catch (...) {
+          std::lock_guard<std::mutex> lk(pool.mu);
+          if (!pool.err) pool.err = std::current_exception();
+        }
+        {
+          std::lock_guard<std::mutex> lk(pool.mu);
+          --pool.running;
+        }
+        pool.cv_idle.notify_all();
+      }
+    };
+    auto wait_idle = [&] {
+      std::unique_lock<std::mutex> lk(pool.mu);
+      pool.cv_idle.wait(lk, [&] { return pool.queue.empty() && pool.running == 0; });
+    };
+    auto shutdown = [&] {
+      {
+        std::lock_guard<std::mutex> lk(pool.mu);
+        pool.closed = true;
+      }
+      pool.cv_work.notify_all();
+      for (auto& t : pool.threads) t.join();
+      pool.threads.clear();
+    };
+    const unsigned n_workers = std::max(1u, threads - 1);
+    for (unsigned ti = 0; ti < n_workers; ++ti) pool.threads.emplace_back(worker);
     const bool trace = getenv("MPH_IO_TRACE") != nullptr;  // measurement hook: where the loader's wall time goes
-    double t_wait = 0, t_scan = 0, t_grow = 0, t_decode = 0;
+    double t_wait = 0, t_scan = 0;
     auto now = [] { return std::chrono::steady_clock::now(); };
     auto since = [](std::chrono::steady_clock::time_point a) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - a).count(); };
-    // frames one record at p (bs = its length prefix) and reserves its arena space
-    size_t n_seq = 0, n_qual = 0, n_cig = 0;
-    auto frame = [&](const uint8_t* p, int32_t bs) {
-      uint16_t n_cigar;
-      int32_t l_seq;
-      memcpy(&n_cigar, p + 12, 2);
-      memcpy(&l_seq, p + 16, 4);
-      if (l_seq < 0 || 32 + size_t(p[8]) + 4 * size_t(n_cigar) + (size_t(l_seq) + 1) / 2 + size_t(l_seq) > size_t(bs)) throw mphio::IoError("corrupt BAM record");
-      items.push_back(Item{p, n_seq, n_qual, n_cig});
-      n_seq += (size_t(l_seq) + 1) / 2; n_qual += size_t(l_seq); n_cig += n_cigar;
-    };
-    while (more) {
-      auto t0 = now();
-      more = bam_.next_chunk(chunk);
-      t_wait += since(t0);
-      t0 = now();
-      items.clear();
-      n_seq = seq_.size(); n_qual = qual_.size(); n_cig = cig_.size();
-      size_t o = 0;
-      if (!more) chunk.clear();
-      if (!carry.empty()) {
-        // finish the record that started in the previous batch
-        size_t need = 4;
-        if (carry.size() < 4) {
-          const size_t take = std::min(4 - carry.size(), chunk.size());
-          carry.insert(carry.end(), chunk.begin(), chunk.begin() + long(take));
-          o += take;
+    constexpr size_t SLICE = 8192;  // records per task
+    try {
+      std::vector<uint8_t> carry;  // the head of a record whose tail is in the next batch
+      bool more = true;
+      // hands a slice over; the record array must not move while tasks are writing into it
+      auto submit = [&](Slice&& sl) {
+        if (sl.off.empty()) return;
+        const size_t n = sl.off.size();
+        if (recs_.size() + n > recs_.cap) {
+          wait_idle();
+          recs_.reserve(std::max(recs_.size() + n, recs_.cap + recs_.cap / 2 + 4096));
         }
-        if (carry.size() >= 4) {
+        sl.rec0 = recs_.size();
+        recs_.grow_to(recs_.size() + n);
+        {
+          std::lock_guard<std::mutex> lk(pool.mu);
+          pool.queue.push_back(std::move(sl));
+        }
+        pool.cv_work.notify_one();
+      };
+      while (more) {
+        auto t0 = now();
+        mphio::RawBytes chunk;
+        more = bam_.next_chunk(chunk);
+        t_wait += since(t0);
+        t0 = now();
+        if (!more) chunk.clear();
+        if (chunk.size() > 0xFFFFFF00ull) throw mphio::IoError("inflated BGZF batch too large");
+        size_t o = 0;
+        if (!carry.empty()) {
+          // finish the record that started in the previous batch
+          if (carry.size() < 4) {
+            const size_t take = std::min(4 - carry.size(), chunk.size());
+            carry.insert(carry.end(), chunk.begin(), chunk.begin() + long(take));
+            o += take;
+          }
+          if (carry.size() >= 4) {
+            int32_t bs;
+            memcpy(&bs, carry.data(), 4);
+            if (bs < 32) throw mphio::IoError("corrupt BAM record");
+            const size_t need = 4 + size_t(bs);
+            const size_t take = std::min(need - carry.size(), chunk.size() - o);
+            carry.insert(carry.end(), chunk.begin() + long(o), chunk.begin() + long(o + take));
+            o += take;
+            if (carry.size() == need) {
+              straddlers_.emplace_back(std::move(carry));
+              carry.clear();
+              Slice sl;
+              sl.base = straddlers_.back().data();
+              sl.off.push_back(4);
+              submit(std::move(sl));
+            }
+          }
+          if (!more && !carry.empty()) throw mphio::IoError("truncated BAM record");
+        }
+        const uint8_t* base = chunk.data();
+        const size_t size = chunk.size();
+        Slice sl;
+        sl.base = base;
+        sl.off.reserve(SLICE);
+        while (o + 4 <= size) {
           int32_t bs;
-          memcpy(&bs, carry.data(), 4);
+          memcpy(&bs, base + o, 4);
           if (bs < 32) throw mphio::IoError("corrupt BAM record");
-          need = 4 + size_t(bs);
-          const size_t take = std::min(need - carry.size(), chunk.size() - o);
-          carry.insert(carry.end(), chunk.begin() + long(o), chunk.begin() + long(o + take));
-          o += take;
-          if (carry.size() == need) {
-            straddler.swap(carry);
-            carry.clear();
-            frame(straddler.data() + 4, bs);
+          if (o + 4 + size_t(bs) > size) break;
+          sl.off.push_back(uint32_t(o + 4));
+          o += 4 + size_t(bs);
+          if (sl.off.size() == SLICE) {
+            submit(std::move(sl));
+            sl = Slice();
+            sl.base = base;
+            sl.off.reserve(SLICE);
           }
         }
-        if (!more && !carry.empty()) throw mphio::IoError("truncated BAM record");
+        submit(std::move(sl));
+        if (o < size) carry.assign(base + o, base + size);
+        if (size) chunks_.push_back(std::move(chunk));  // the buffer itself does not move: the slices' pointers stay valid
+        t_scan += since(t0);
       }
-      while (o + 4 <= chunk.size()) {
-        int32_t bs;
-        memcpy(&bs, chunk.data() + o, 4);
-        if (bs < 32) throw mphio::IoError("corrupt BAM record");
-        if (o + 4 + size_t(bs) > chunk.size()) break;
-        frame(chunk.data() + o + 4, bs);
-        o += 4 + size_t(bs);
-      }
-      if (o < chunk.size()) carry.assign(chunk.begin() + long(o), chunk.end());
-      t_scan += since(t0);
-      t0 = now();
-      seq_.grow_to(n_seq); qual_.grow_to(n_qual); cig_.grow_to(n_cig);
-      const size_t r0 = recs_.size();
-      recs_.grow_to(r0 + items.size());
-      t_grow += since(t0);
-      t0 = now();
-      const unsigned nt = items.size() < 4096 ? 1u : threads;
-      auto work = [&](unsigned ti) {
-        const size_t i0 = items.size() * ti / nt, i1 = items.size() * (ti + 1) / nt;
-        for (size_t i = i0; i < i1; ++i) decode_record(items[i].p, items[i].seq_at, items[i].qual_at, items[i].cig_at, recs_[r0 + i]);
-      };
-      std::vector<std::thread> pool;
-      for (unsigned ti = 1; ti < nt; ++ti) pool.emplace_back(work, ti);
-      work(0);
-      for (auto& t : pool) t.join();
-      t_decode += since(t0);
+      auto t0 = now();
+      wait_idle();
+      const double t_tail = since(t0);
+      shutdown();
+      if (pool.err) std::rethrow_exception(pool.err);
+      if (trace)
+        fprintf(stderr, "[mph io] BAM load: waiting for inflated batches %.1f ms, record framing %.1f, waiting for the header parse after the last batch %.1f\n",
+                t_wait, t_scan, t_tail);
+    } catch (...) {
+      shutdown();
+      throw;
     }
     // records of contigs the header does not know are dropped (compaction in place keeps the file order)
     size_t keep = 0;
     for (size_t i = 0; i < recs_.size(); ++i)
       if (recs_[i].tid >= 0 && size_t(recs_[i].tid) < tid_range_.size()) recs_[keep++] = recs_[i];
     recs_.grow_to(keep);
-    if (trace)
-      fprintf(stderr, "[mph io] BAM load: waiting for inflated batches %.1f ms, record framing %.1f, arena growth %.1f, record decode %.1f\n",
-              t_wait, t_scan, t_grow, t_decode);
   }
 
  public:
-  const uint8_t* seq4(const Rec& r) const { return seq_.data() + r.seq_off; }
-  const uint8_t* qual(const Rec& r) const { return qual_.data() + r.qual_off; }
-  const uint32_t* cigar(const Rec& r) const { return cig_.data() + r.cig_off; }
+  const uint8_t* seq4(const Rec& r) const { return r.seq_p; }
+  const uint8_t* qual(const Rec& r) const { return r.qual_p; }
+  const uint32_t* cigar(const Rec& r) const { return r.cig_p; }
+  size_t n_records() const { return recs_.size(); }
 
   // bam::RecordBuffer::fetch (rust-htslib 0.36) over the in-memory records: the mapped records with pos < end, kept
   // across calls for overlapping / adjacent queries. An indexed re-fetch yields every record that overlaps `start`
@@ -306,8 +397,11 @@ class ReadBuffer {
   mphio::BamFile& bam_;
   Arena<Rec> recs_;                                     // every mapped-to-a-known-contig record, contig by contig, file order
   std::vector<std::pair<size_t, size_t>> tid_range_;    // per contig: [first, last) in recs_
-  Arena<uint8_t> seq_, qual_;
+  Arena<uint8_t> seq_, qual_;                           // sequential loader only
   Arena<uint32_t> cig_;
+  std::deque<mphio::RawBytes> chunks_;                  // threaded loader: the inflated batches the records point into,
+  std::deque<std::vector<uint8_t>> straddlers_;         // the records that straddle two batches,
+  std::vector<std::unique_ptr<uint32_t[]>> cig_blocks_; // and the CIGARs, one aligned block per slice of records
   std::deque<const Rec*> inner_;
   const Rec* overflow_ = nullptr;
   int tid_ = -1;
@@ -524,48 +618,125 @@ struct IngestOptions {
 struct GeneInput {
   HostGene gene;
   std::vector<HostRead> reads;  // point into records owned by the ReadBuffer
+  // lazy form (file drivers): the buffered records themselves; `reads` is built from them when the gene is packed, which
+  // happens on the packing threads instead of the single thread that walks the GTF
+  std::vector<const ReadBuffer::Rec*> recs;
+  size_t n_reads = 0;
   uint32_t max_read_len = 0;
+  void materialize() {
+    if (!reads.empty() || recs.empty()) return;
+    reads.reserve(recs.size());
+    for (const ReadBuffer::Rec* rec : recs) {
+      HostRead h;
+      h.start = uint32_t(rec->pos);
+      h.end = rec->end;
+      h.l_seq = rec->l_seq;
+      h.seq4 = rec->seq_p;
+      h.qual = rec->qual_p;
+      h.cigar = rec->cig_p;
+      h.n_cigar = rec->n_cigar;
+      h.qname_hash = rec->qname_hash;
+      reads.push_back(h);
+    }
+    std::vector<const ReadBuffer::Rec*>().swap(recs);
+  }
   std::vector<std::vector<HostVariant>> sites;
   std::vector<uint8_t> refseq;
 };
 
 // Streams the GTF and fetches reads / variants / reference for every protein-coding gene, in GTF order.
-inline std::vector<GeneInput> ingest_genes(std::istream& gtf, ReadBuffer& reads, mphio::VcfFile& vcf, mphio::FastaIndexed& fasta,
-                                           const IngestOptions& opt) {
-  std::vector<ParsedGene> genes = read_gtf(gtf, opt.mode);
+// `reads_ready()` returns the loaded ReadBuffer, blocking until it is there: the file drivers load the BAM on another thread
+// while this one parses the GTF and fetches the reference slices and variants (a third of the per-gene work), and only the
+// read fetch waits for it. Errors keep the order of the one-pass loop (per gene: reference, reads, variants), and a failure
+// of the BAM load itself comes before all of them, as it did when the buffer was built first.
+template <class ReadsReady>
+inline std::vector<GeneInput> ingest_genes_with(std::istream& gtf, ReadsReady&& reads_ready, mphio::VcfFile& vcf, mphio::FastaIndexed& fasta,
+                                                const IngestOptions& opt, bool lazy_reads) {
+  std::vector<ParsedGene> genes;
+  try {
+    genes = read_gtf(gtf, opt.mode);
+  } catch (...) {
+    reads_ready();  // a broken BAM is reported first
+    throw;
+  }
   VariantBuffer variants(vcf);
   std::vector<GeneInput> out;
+  std::exception_ptr stashed;
+  size_t stash_gene = size_t(-1);
+  int stash_stage = 0;  // 0: reference fetch, 2: variants
   for (auto& pg : genes) {
     if (pg.biotype != "protein_coding") continue;  // :1964
     GeneInput gi;
     gi.gene = std::move(pg.gene);
     const HostGene& g = gi.gene;
-    fasta.fetch(g.chrom, g.start, uint64_t(g.end) + 100, gi.refseq);  // end_overflow (:895-901)
+    int stage = 0;
+    try {
+      fasta.fetch(g.chrom, g.start, uint64_t(g.end) + 100, gi.refseq);  // end_overflow (:895-901)
+      stage = 2;
+      // variant_tree.insert(rec.pos(), Variant::new(rec)): a later record at the same position replaces the earlier (:937)
+      std::map<uint32_t, std::vector<HostVariant>> tree;
+      for (auto& rec : variants.fetch(g.chrom, g.start, g.end)) tree[uint32_t(rec.pos)] = alleles_of(vcf, rec, opt.warn_only);
+      for (auto& kv : tree)
+        if (!kv.second.empty()) gi.sites.push_back(std::move(kv.second));
+    } catch (...) {
+      stashed = std::current_exception();
+      stash_gene = out.size();
+      stash_stage = stage;
+      out.push_back(std::move(gi));
+      break;
+    }
+    out.push_back(std::move(gi));
+  }
+  ReadBuffer& reads = reads_ready();
+  for (size_t i = 0; i < out.size(); ++i) {
+    GeneInput& gi = out[i];
+    const HostGene& g = gi.gene;
+    if (i == stash_gene && stash_stage == 0) std::rethrow_exception(stashed);
     const auto& rb = reads.fetch(g.chrom, g.start, g.end);
-    gi.reads.reserve(rb.size());
+    gi.recs.reserve(rb.size());
     for (auto& rec : rb) {
       if (rec->mapq < opt.min_mapq) continue;
       if (rec->l_seq > gi.max_read_len) gi.max_read_len = rec->l_seq;
-      HostRead h;
-      h.start = uint32_t(rec->pos);
-      h.end = rec->end;
-      h.l_seq = rec->l_seq;
-      h.seq4 = reads.seq4(*rec);
-      h.qual = reads.qual(*rec);
-      h.cigar = reads.cigar(*rec);
-      h.n_cigar = rec->n_cigar;
-      h.qname_hash = rec->qname_hash;
-      gi.reads.push_back(h);
+      gi.recs.push_back(rec);
     }
-    // variant_tree.insert(rec.pos(), Variant::new(rec)): a later record at the same position replaces the earlier (:937)
-    std::map<uint32_t, std::vector<HostVariant>> tree;
-    for (auto& rec : variants.fetch(g.chrom, g.start, g.end)) tree[uint32_t(rec.pos)] = alleles_of(vcf, rec, opt.warn_only);
-    for (auto& kv : tree)
-      if (!kv.second.empty()) gi.sites.push_back(std::move(kv.second));
-    out.push_back(std::move(gi));
+    gi.n_reads = gi.recs.size();
+    if (!lazy_reads) gi.materialize();
+    if (i == stash_gene) std::rethrow_exception(stashed);
   }
   return out;
 }
+
+inline std::vector<GeneInput> ingest_genes(std::istream& gtf, ReadBuffer& reads, mphio::VcfFile& vcf, mphio::FastaIndexed& fasta,
+                                           const IngestOptions& opt, bool lazy_reads = false) {
+  return ingest_genes_with(gtf, [&]() -> ReadBuffer& { return reads; }, vcf, fasta, opt, lazy_reads);
+}
+
+// Loads the BAM on a thread of its own; get() joins it and hands the buffer over (or rethrows what the load threw).
+class ReadBufferLoader {
+ public:
+  explicit ReadBufferLoader(mphio::BamFile& bam) {
+    thread_ = std::thread([this, &bam] {
+      try {
+        buf_.reset(new ReadBuffer(bam));
+      } catch (...) {
+        err_ = std::current_exception();
+      }
+    });
+  }
+  ~ReadBufferLoader() {
+    if (thread_.joinable()) thread_.join();
+  }
+  ReadBuffer& get() {
+    if (thread_.joinable()) thread_.join();
+    if (err_) std::rethrow_exception(err_);
+    return *buf_;
+  }
+
+ private:
+  std::thread thread_;
+  std::unique_ptr<ReadBuffer> buf_;
+  std::exception_ptr err_;
+};
 
 // Contiguous gene ranges balanced by read count, one per device: shard k is
 // genes [cut[k], cut[k+1]). Shards are independent; their records are concatenated in shard order.
@@ -573,11 +744,11 @@ inline std::vector<size_t> partition_genes(const std::vector<GeneInput>& genes, 
   std::vector<size_t> cut(n_shards + 1, genes.size());
   cut[0] = 0;
   uint64_t total = 0;
-  for (auto& g : genes) total += g.reads.size() + 1;
+  for (auto& g : genes) total += g.n_reads + 1;
   uint64_t acc = 0;
   size_t k = 1;
   for (size_t i = 0; i < genes.size() && k < n_shards; ++i) {
-    acc += genes[i].reads.size() + 1;
+    acc += genes[i].n_reads + 1;
     while (k < n_shards && acc * n_shards >= total * k) cut[k++] = i + 1;
   }
   return cut;
@@ -586,6 +757,7 @@ inline std::vector<size_t> partition_genes(const std::vector<GeneInput>& genes, 
 inline void pack_genes(std::vector<GeneInput>& genes, size_t lo, size_t hi, Packer& packer) {
   for (size_t i = lo; i < hi; ++i) {
     GeneInput& gi = genes[i];
+    gi.materialize();
     packer.add_gene(gi.gene, gi.reads, gi.max_read_len, gi.sites, std::move(gi.refseq));
     std::vector<HostRead>().swap(gi.reads);
   }
@@ -594,8 +766,8 @@ inline void pack_genes(std::vector<GeneInput>& genes, size_t lo, size_t hi, Pack
 // Builds the batch for every protein-coding gene of the GTF, in GTF order.
 inline void ingest(std::istream& gtf, mphio::BamFile& bam, mphio::VcfFile& vcf, mphio::FastaIndexed& fasta, const IngestOptions& opt,
                    Packer& packer) {
-  ReadBuffer reads(bam);
-  std::vector<GeneInput> genes = ingest_genes(gtf, reads, vcf, fasta, opt);
+  ReadBufferLoader loader(bam);
+  std::vector<GeneInput> genes = ingest_genes_with(gtf, [&]() -> ReadBuffer& { return loader.get(); }, vcf, fasta, opt, true);
   pack_genes(genes, 0, genes.size(), packer);
 }
 
