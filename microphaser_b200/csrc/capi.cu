@@ -70,6 +70,7 @@ struct mph_batch {
   bool pinned = false;
   std::vector<std::pair<void*, size_t>> registered;
   uint64_t h2d_bytes = 0;
+  int span_mode = 0;  // bus form of the read spans (host/batch.hpp: bus_span_mode), fixed when the batch is finished
   ~mph_batch() {
     for (auto& r : registered) cudaHostUnregister(r.first);
   }
@@ -221,7 +222,8 @@ void finish_batch(mph_batch* mb, bool pin) {
   for (auto& e : b.pair_edges) mb->pairs.push_back(make_uint2(e.first, e.second));
   std::sort(mb->pairs.begin(), mb->pairs.end(), [](const uint2& a, const uint2& c) { return a.x < c.x; });
   auto bytes = [](auto& v) { return v.size() * sizeof(v[0]); };
-  mb->h2d_bytes = bytes(b.rd_delta) + bytes(b.rd_span) + bytes(b.rd_runs) + bytes(b.rd_span_exc) + bytes(b.rd_flag_exc) + bytes(b.vs_read_d) + bytes(b.vs_vlo_d) + bytes(b.vs_size) +
+  mb->span_mode = bus_span_mode(b);
+  mb->h2d_bytes = bytes(b.rd_delta) + (mb->span_mode ? bytes(b.rd_mspan_exc) : bytes(b.rd_span) + bytes(b.rd_span_exc)) + bytes(b.rd_runs) + bytes(b.rd_flag_exc) + bytes(b.vs_read_d) + bytes(b.vs_vlo_d) + bytes(b.vs_size) +
                   bytes(b.vs_ncig) + bytes(b.vs_runs) + bytes(b.vs_ncig_exc) + bytes(b.vr_lseq) + bytes(b.vr_nv) + bytes(b.bases) + bytes(b.cigars) +
                   bytes(b.vars) + bytes(b.ins_bytes) + bytes(b.segs) + bytes(b.chunks) + bytes(b.seg_work) + bytes(b.seg_work_off) + bytes(b.ref) + bytes(b.stopmap) + bytes(mb->pairs) +
                   bytes(b.tx_id_bytes) + bytes(b.tx_id_off) + bytes(b.replay) + bytes(b.replay_dq) + (b.replay.empty() ? 0 : bytes(b.seg_chunk0));
@@ -233,7 +235,7 @@ void finish_batch(mph_batch* mb, bool pin) {
       else
         cudaGetLastError();
     };
-    reg(b.rd_delta); reg(b.rd_span); reg(b.rd_runs); reg(b.rd_span_exc); reg(b.rd_flag_exc); reg(b.vs_read_d); reg(b.vs_vlo_d); reg(b.vs_size); reg(b.vs_ncig); reg(b.vs_runs); reg(b.vs_ncig_exc); reg(b.vr_lseq);
+    reg(b.rd_delta); if (mb->span_mode) reg(b.rd_mspan_exc); else { reg(b.rd_span); reg(b.rd_span_exc); } reg(b.rd_runs); reg(b.rd_flag_exc); reg(b.vs_read_d); reg(b.vs_vlo_d); reg(b.vs_size); reg(b.vs_ncig); reg(b.vs_runs); reg(b.vs_ncig_exc); reg(b.vr_lseq);
     reg(b.vr_nv); reg(b.bases); reg(b.cigars); reg(b.vars); reg(b.ins_bytes); reg(b.segs); reg(b.chunks); reg(b.seg_work); reg(b.seg_work_off); reg(b.ref); reg(b.stopmap);
     reg(mb->pairs);
     reg(b.tx_id_bytes); reg(b.tx_id_off); reg(b.replay); reg(b.replay_dq); reg(b.seg_chunk0);
@@ -299,7 +301,7 @@ void prepare(mph_ctx* c, const mph_batch* mb) {
   const size_t nr = b.n_reads(), nw = size_t(b.n_windows);
   const size_t nvr = b.vr_read.size();
   c->read_start.ensure(nr + 1); c->read_end.ensure(nr + 1); c->read_flags.ensure(nr + 1);
-  c->rd_delta.ensure(nr + 1); c->rd_span.ensure(nr + 1); c->rd_runs.ensure(b.rd_runs.size() + 1); c->rd_span_exc.ensure(b.rd_span_exc.size() + 1);
+  c->rd_delta.ensure(nr + 1); if (!mb->span_mode) c->rd_span.ensure(nr + 1); c->rd_runs.ensure(b.rd_runs.size() + 1); c->rd_span_exc.ensure((mb->span_mode ? b.rd_mspan_exc.size() : b.rd_span_exc.size()) + 1);
   c->rd_flag_exc.ensure(b.rd_flag_exc.size() + 1);
   c->read_vlo.ensure(nr + 1); c->read_nv.ensure(nr + 1); c->read_vr.ensure(nr + 1);  // expanded on the device by K1
   c->vr_read.ensure(nvr + 1); c->vr_vlo.ensure(nvr + 1); c->vr_seq_off.ensure(nvr + 1); c->vr_cig_off.ensure(nvr + 1);
@@ -335,7 +337,7 @@ void prepare(mph_ctx* c, const mph_batch* mb) {
   d.n_windows = uint32_t(nw); d.seq_cap = b.seq_cap;
   d.read_start = c->read_start.p; d.read_end = c->read_end.p; d.read_flags = c->read_flags.p;
   d.read_start_w = c->read_start.p; d.read_end_w = c->read_end.p; d.read_flags_w = c->read_flags.p;
-  d.rd_delta = c->rd_delta.p; d.rd_span = c->rd_span.p; d.rd_runs = c->rd_runs.p; d.rd_span_exc = c->rd_span_exc.p; d.rd_flag_exc = c->rd_flag_exc.p;
+  d.rd_delta = c->rd_delta.p; d.rd_span = mb->span_mode ? nullptr : c->rd_span.p; d.modal_span = b.modal_span; d.rd_runs = c->rd_runs.p; d.rd_span_exc = c->rd_span_exc.p; d.rd_flag_exc = c->rd_flag_exc.p;
   d.read_vlo = c->read_vlo.p; d.read_nv = c->read_nv.p; d.read_vr = c->read_vr.p;
   d.vr_read = c->vr_read.p; d.vr_vlo = c->vr_vlo.p; d.vr_seq_off = c->vr_seq_off.p; d.vr_cig_off = c->vr_cig_off.p;
   d.vr_lseq = c->vr_lseq.p; d.vr_ncig = c->vr_ncig.p; d.vr_nv = c->vr_nv.p;
@@ -383,8 +385,10 @@ void h2d_range(cudaStream_t st, DevBuf<T>& dst, const V& src, size_t lo, size_t 
 void copy_stage(mph_ctx* c, const mph_batch* mb, const Stage& s, bool first, cudaStream_t st) {
   const Batch& b = mb->b;
   const size_t r0 = s.lo.reads, r1 = s.hi.reads;
-  h2d_range(st, c->rd_delta, b.rd_delta, r0, r1); h2d_range(st, c->rd_span, b.rd_span, r0, r1);
-  h2d_range(st, c->rd_runs, b.rd_runs, s.lo.runs, s.hi.runs); h2d_range(st, c->rd_span_exc, b.rd_span_exc, s.lo.span_exc, s.hi.span_exc);
+  h2d_range(st, c->rd_delta, b.rd_delta, r0, r1);
+  if (mb->span_mode) h2d_range(st, c->rd_span_exc, b.rd_mspan_exc, s.lo.mspan_exc, s.hi.mspan_exc);  // one span per batch + the reads that differ
+  else { h2d_range(st, c->rd_span, b.rd_span, r0, r1); h2d_range(st, c->rd_span_exc, b.rd_span_exc, s.lo.span_exc, s.hi.span_exc); }
+  h2d_range(st, c->rd_runs, b.rd_runs, s.lo.runs, s.hi.runs);
   h2d_range(st, c->rd_flag_exc, b.rd_flag_exc, s.lo.flag_exc, s.hi.flag_exc);
   const size_t e0 = s.lo.vr, e1 = s.hi.vr;
   h2d_range(st, c->vs_read_d, b.vs_read_d, e0, e1); h2d_range(st, c->vs_vlo_d, b.vs_vlo_d, e0, e1); h2d_range(st, c->vs_size, b.vs_size, e0, e1);
@@ -410,7 +414,7 @@ void set_ranges(mph_ctx* c, const Stage& s) {
   d.vr0 = uint32_t(s.lo.vr); d.vr1 = uint32_t(s.hi.vr);
   d.c0 = uint32_t(s.lo.chunks); d.c1 = uint32_t(s.hi.chunks);
   d.s0 = uint32_t(s.lo.segs); d.s1 = uint32_t(s.hi.segs);
-  d.run0 = uint32_t(s.lo.runs); d.run1 = uint32_t(s.hi.runs); d.sx0 = uint32_t(s.lo.span_exc); d.sx1 = uint32_t(s.hi.span_exc);
+  d.run0 = uint32_t(s.lo.runs); d.run1 = uint32_t(s.hi.runs); d.sx0 = uint32_t(c->cur->span_mode ? s.lo.mspan_exc : s.lo.span_exc); d.sx1 = uint32_t(c->cur->span_mode ? s.hi.mspan_exc : s.hi.span_exc);
   d.fx0 = uint32_t(s.lo.flag_exc); d.fx1 = uint32_t(s.hi.flag_exc);
   d.vrun0 = uint32_t(s.lo.vruns); d.vrun1 = uint32_t(s.hi.vruns); d.nx0 = uint32_t(s.lo.ncig_exc); d.nx1 = uint32_t(s.hi.ncig_exc);
   d.it0 = c->cur->b.seg_work_off[s.lo.segs]; d.it1 = c->cur->b.seg_work_off[s.hi.segs];
@@ -447,6 +451,9 @@ void run_kernels(mph_ctx* c) {
     CU(cudaMemsetAsync(c->read_nv.p + d.r0, 0, n, c->stream));
   }
   if (d.rp1 > d.rp0) {
+    // K2 writes the flag of every window it owns; the replay only those it reaches (and, on its side stream, possibly after
+    // the record kernels have looked): whatever an earlier batch left in the windows of replayed transcripts must not be read
+    CU(cudaMemsetAsync(c->win_flag.p + d.w0, 0, size_t(d.w1 - d.w0), c->stream));
     d.vlist = c->vlist.p; d.vlist_cap = uint32_t(std::min<size_t>(c->vlist.cap, 0xFFFFFF00u));
     CU(cudaMemsetAsync(c->win_voff.p + d.w0, 0xFF, size_t(d.w1 - d.w0) * sizeof(uint32_t), c->stream));
     const uint32_t s0 = c->stage_seg_lo, s1 = c->stage_seg_hi;

@@ -79,7 +79,7 @@ struct GeneMeta {
 // sizes of every per-gene-contiguous array after a gene has been packed: a batch can be cut at any gene boundary
 struct GeneMark {
   uint64_t reads = 0, vr = 0, bases = 0, cigars = 0, vars = 0, ins = 0, segs = 0, chunks = 0, ref = 0, windows = 0, txs = 0, replay = 0, dq = 0, partners = 0;
-  uint64_t runs = 0, span_exc = 0, flag_exc = 0, vruns = 0, ncig_exc = 0;
+  uint64_t runs = 0, span_exc = 0, flag_exc = 0, vruns = 0, ncig_exc = 0, mspan_exc = 0;
 };
 
 struct Batch {
@@ -98,6 +98,13 @@ struct Batch {
   std::vector<U2> rd_runs;      // (first read, its start)
   std::vector<U2> rd_span_exc;  // (read, end)
   std::vector<U2> rd_flag_exc;  // (read, flags)
+  // Second bus form of the spans: short reads of one sequencing run share one reference span unless they carry an indel or
+  // a clip, so the batch ships ONE span (the commonest of the first gene with a few reads) and lists the reads that differ
+  // (read, end) - 1 B per read less on the bus. The packer writes both forms; bus_span_mode() picks per batch (trimmed
+  // reads of all lengths keep the byte array).
+  uint32_t modal_span = 0;
+  bool modal_set = false;
+  std::vector<U2> rd_mspan_exc;  // (read, end) of every read whose span is not modal_span
   // bus form of the side table (9 B per entry instead of 21): the entries are sorted by read, their first-variant index
   // never decreases within a gene, and the offsets of the packed bases / CIGARs are running sums of the record sizes, so an
   // entry ships as read distance (u16), variant-index distance (u8), record bytes (u16), CIGAR ops (u8; 255 = see vs_ncig_exc)
@@ -148,20 +155,28 @@ struct Batch {
   uint64_t n_reads() const { return read_start.size(); }
 };
 
+// which form of the spans crosses the bus: 1 = one span per batch + the reads that differ (8 B each), 0 = a byte per read
+// (+ the reads with spans >= 255). MPH_BUS_SPAN_BYTES=1 forces the byte form (test hook).
+inline int bus_span_mode(const Batch& b) {
+  static const bool force_bytes = getenv("MPH_BUS_SPAN_BYTES") != nullptr;
+  return (!force_bytes && b.modal_set && b.rd_mspan_exc.size() * 8 <= b.rd_span.size()) ? 1 : 0;
+}
+
 // host statement of K0 (k_read_decode / k_read_patch): used by the CPU checks of the bus encoding
-inline void decode_reads(const Batch& b, std::vector<uint32_t>& start, std::vector<uint32_t>& end, std::vector<uint8_t>& flags) {
+inline void decode_reads(const Batch& b, std::vector<uint32_t>& start, std::vector<uint32_t>& end, std::vector<uint8_t>& flags, int form = -1) {
   const size_t n = b.rd_delta.size();
   start.assign(n, 0); end.assign(n, 0); flags.assign(n, 0);
+  const int mode = form < 0 ? bus_span_mode(b) : form;
   for (size_t j = 0; j < b.rd_runs.size(); ++j) {
     const size_t lo = b.rd_runs[j].x, hi = j + 1 < b.rd_runs.size() ? b.rd_runs[j + 1].x : n;
     uint32_t pos = b.rd_runs[j].y;
     for (size_t r = lo; r < hi; ++r) {
       pos += b.rd_delta[r];
       start[r] = pos;
-      end[r] = pos + b.rd_span[r];
+      end[r] = pos + (mode ? b.modal_span : uint32_t(b.rd_span[r]));
     }
   }
-  for (auto& e : b.rd_span_exc) end[e.x] = e.y;
+  for (auto& e : (mode ? b.rd_mspan_exc : b.rd_span_exc)) end[e.x] = e.y;
   for (auto& e : b.rd_flag_exc) flags[e.x] = uint8_t(e.y);
 }
 
@@ -721,6 +736,17 @@ class Packer {
       }
     }
     // bus encoding of this gene's reads (see Batch::rd_delta)
+    if (!b_.modal_set && gm.read_hi - gm.read_lo >= 16) {  // the batch's span: the commonest one of this gene
+      std::vector<uint32_t> spans;
+      for (uint32_t r = gm.read_lo; r < gm.read_hi; ++r) spans.push_back(b_.read_end[r] - b_.read_start[r]);
+      std::sort(spans.begin(), spans.end());
+      size_t best = 0;
+      for (size_t i = 0, j = 0; i < spans.size(); i = j) {
+        while (j < spans.size() && spans[j] == spans[i]) ++j;
+        if (j - i > best) { best = j - i; b_.modal_span = spans[i]; }
+      }
+      b_.modal_set = true;
+    }
     for (uint32_t r = gm.read_lo; r < gm.read_hi; ++r) {
       uint32_t delta = 0;
       if (r == gm.read_lo || b_.read_start[r] - b_.read_start[r - 1] > 255u) b_.rd_runs.push_back(Batch::U2{r, b_.read_start[r]});
@@ -729,6 +755,7 @@ class Packer {
       const uint32_t span = b_.read_end[r] - b_.read_start[r];
       b_.rd_span.push_back(uint8_t(span < 255u ? span : 255u));
       if (span >= 255u) b_.rd_span_exc.push_back(Batch::U2{r, b_.read_end[r]});
+      if (!b_.modal_set || span != b_.modal_span) b_.rd_mspan_exc.push_back(Batch::U2{r, b_.read_end[r]});
       if (b_.read_flags[r]) b_.rd_flag_exc.push_back(Batch::U2{r, b_.read_flags[r]});
     }
     // work items of the read-run kernel: (segment, read) pairs; replayed transcripts take none (k_replay does their windows)
@@ -743,7 +770,7 @@ class Packer {
     mk.reads = b_.read_start.size(); mk.vr = b_.vr_read.size(); mk.bases = b_.bases.size(); mk.cigars = b_.cigars.size(); mk.vars = b_.vars.size(); mk.ins = b_.ins_bytes.size();
     mk.segs = b_.segs.size(); mk.chunks = b_.chunks.size(); mk.ref = b_.ref.size(); mk.windows = b_.n_windows; mk.txs = b_.txs.size();
     mk.replay = b_.replay.size(); mk.dq = b_.replay_dq.size(); mk.partners = b_.partner_a.size();
-    mk.runs = b_.rd_runs.size(); mk.span_exc = b_.rd_span_exc.size(); mk.flag_exc = b_.rd_flag_exc.size();
+    mk.runs = b_.rd_runs.size(); mk.span_exc = b_.rd_span_exc.size(); mk.flag_exc = b_.rd_flag_exc.size(); mk.mspan_exc = b_.rd_mspan_exc.size();
     mk.vruns = b_.vs_runs.size(); mk.ncig_exc = b_.vs_ncig_exc.size();
     b_.marks.push_back(mk);
   }

@@ -6,7 +6,9 @@
 #pragma once
 #include <sys/mman.h>
 
+#include <atomic>
 #include <chrono>
+#include <functional>
 #include <condition_variable>
 #include <mutex>
 #include <thread>
@@ -166,56 +168,93 @@ class ReadBuffer {
     x.qual_p = p + q + (x.l_seq + 1) / 2;
   }
 
-  // Threaded loader. The inflated batches are kept (records point into them: nothing but the CIGARs is copied). The calling
-  // thread only walks the length prefixes - a dependent chain, one cache miss per record - and hands slices of framed
-  // records to a small pool that parses the headers while the next batch is being framed; a record that straddles two
-  // batches is put together in a buffer of its own.
+  // Threaded loader. The inflated batches are kept (records point into them: nothing but the CIGARs is copied).
+  // Record boundaries are a dependent chain of length prefixes - one cache miss per record when a single thread walks it -
+  // so every batch is cut into segments of ~1 MB that are framed and parsed in parallel: the first segment starts at the
+  // known boundary, the others GUESS theirs (the first offset at which a few consecutive plausible record headers line
+  // up) and walk on from there. The calling thread then checks, segment by segment, that the walk of everything before
+  // ends exactly on the segment's guess; by induction every accepted boundary is a real one. A segment whose guess does
+  // not match (or that found none) is framed again from the right offset on the calling thread. The parsed records of a
+  // segment are copied into the record array once their position is known (also on the pool, beside the next batch).
   void load_parallel(unsigned threads) {
-    struct Slice {
-      const uint8_t* base = nullptr;      // records at base + off[i] (first byte after the length prefix)
+    struct Seg {
+      const uint8_t* base = nullptr;  // the batch
+      size_t size = 0;                // its bytes
+      size_t lo = 0, hi = 0;          // records that START in [lo, hi) belong to this segment
+      bool known = false;             // lo is a record boundary
+      size_t guess = size_t(-1);      // first record start found (lo if known)
+      size_t end = 0;                 // where the walk stopped: the first record start >= hi, or an incomplete record
+      bool incomplete = false;        // ... the record at `end` does not fit the batch
+      std::vector<Rec> recs;
+      std::unique_ptr<uint32_t[]> cig;
+      size_t rec0 = 0;
+    };
+    const int32_t n_ref = int32_t(tid_range_.size());
+    // a record header that could be real (the checks htslib-based splitters use): false positives cost a fallback, nothing else
+    auto plausible = [n_ref](const uint8_t* base, size_t size, size_t o) -> bool {
+      if (o + 36 > size) return false;
+      auto i32 = [&](size_t q) { int32_t v; memcpy(&v, base + o + q, 4); return v; };
+      const int32_t bs = i32(0), tid = i32(4), pos = i32(8), l_seq = i32(20), ntid = i32(24), npos = i32(28);
+      uint16_t n_cigar;
+      memcpy(&n_cigar, base + o + 16, 2);
+      const uint8_t l_name = base[o + 12];
+      if (bs < 32 || bs > (1 << 26) || tid < -1 || tid >= n_ref || pos < -1 || ntid < -1 || ntid >= n_ref || npos < -1 || l_seq < 0 || l_name == 0) return false;
+      if (32 + size_t(l_name) + 4 * size_t(n_cigar) + (size_t(l_seq) + 1) / 2 + size_t(l_seq) > size_t(bs)) return false;
+      const size_t nul = o + 36 + l_name - 1;
+      return nul >= size || base[nul] == 0;
+    };
+    // frames and parses the records starting in [from, sg.hi); fills sg.recs / sg.cig / sg.end / sg.incomplete
+    auto walk = [](Seg& sg, size_t from) {
       std::vector<uint32_t> off;
-      size_t rec0 = 0;                    // first slot in recs_
+      size_t o = from, n_cig = 0;
+      sg.incomplete = false;
+      while (o < sg.hi) {
+        if (o + 4 > sg.size) { sg.incomplete = true; break; }
+        int32_t bs;
+        memcpy(&bs, sg.base + o, 4);
+        if (bs < 32) throw mphio::IoError("corrupt BAM record");
+        if (o + 4 + size_t(bs) > sg.size) { sg.incomplete = true; break; }
+        uint16_t nc;
+        memcpy(&nc, sg.base + o + 16, 2);
+        if (32 + 4 * size_t(nc) > size_t(bs)) throw mphio::IoError("corrupt BAM record");
+        n_cig += nc;
+        off.push_back(uint32_t(o + 4));
+        o += 4 + size_t(bs);
+      }
+      sg.end = o;
+      sg.recs.resize(off.size());
+      sg.cig.reset(new uint32_t[n_cig + 1]);
+      uint32_t* cig = sg.cig.get();
+      for (size_t i = 0; i < off.size(); ++i) {
+        const uint8_t* p = sg.base + off[i];
+        int32_t bs;
+        memcpy(&bs, p - 4, 4);
+        decode_record(p, bs, cig, sg.recs[i]);
+        cig += sg.recs[i].n_cigar;
+      }
     };
     struct Pool {
       std::mutex mu;
       std::condition_variable cv_work, cv_idle;
-      std::deque<Slice> queue;
+      std::deque<std::function<void()>> queue;
       size_t running = 0;
       bool closed = false;
       std::exception_ptr err;
       std::vector<std::thread> threads;
     } pool;
-    std::mutex cig_mu;
     auto worker = [&] {
       for (;;) {
-        Slice sl;
+        std::function<void()> job;
         {
           std::unique_lock<std::mutex> lk(pool.mu);
           pool.cv_work.wait(lk, [&] { return pool.closed || !pool.queue.empty(); });
           if (pool.queue.empty()) return;
-          sl = std::move(pool.queue.front());
+          job = std::move(pool.queue.front());
           pool.queue.pop_front();
           ++pool.running;
         }
         try {
-          // CIGAR storage of the slice: one aligned block (sizes from a first look at the headers, which the parse re-reads hot)
-          size_t n_cig = 0;
-          for (uint32_t o : sl.off) { uint16_t nc; memcpy(&nc, sl.base + o + 12, 2); n_cig += nc; }
-          std::unique_ptr<uint32_t[]> block(new uint32_t[n_cig + 1]);
-          uint32_t* cig = block.get();
-          for (size_t i = 0; i < sl.off.size(); ++i) {
-            const uint8_t* p = sl.base + sl.off[i];
-            int32_t bs;
-            memcpy(&bs, p - 4, 4);
-            Rec& x = recs_[sl.rec0 + i];
-            uint16_t nc;
-            memcpy(&nc, p + 12, 2);
-            if (32 + 4 * size_t(nc) > size_t(bs)) throw mphio::IoError("corrupt BAM record");
-            decode_record(p, bs, cig, x);
-            cig += nc;
-          }
-          std::lock_guard<std::mutex> lk(cig_mu);
-          cig_blocks_.push_back(std::move(block));
+          job();
         } catch (...) {
           std::lock_guard<std::mutex> lk(pool.mu);
           if (!pool.err) pool.err = std::current_exception();
@@ -227,9 +266,17 @@ class ReadBuffer {
         pool.cv_idle.notify_all();
       }
     };
+    auto submit = [&](std::function<void()> job) {
+      {
+        std::lock_guard<std::mutex> lk(pool.mu);
+        pool.queue.push_back(std::move(job));
+      }
+      pool.cv_work.notify_one();
+    };
     auto wait_idle = [&] {
       std::unique_lock<std::mutex> lk(pool.mu);
       pool.cv_idle.wait(lk, [&] { return pool.queue.empty() && pool.running == 0; });
+      if (pool.err) std::rethrow_exception(pool.err);
     };
     auto shutdown = [&] {
       {
@@ -240,38 +287,133 @@ class ReadBuffer {
       for (auto& t : pool.threads) t.join();
       pool.threads.clear();
     };
-    const unsigned n_workers = std::max(1u, threads - 1);
+    // the inflate pool of the BGZF reader uses `threads` threads of its own; a few more for the parse are enough
+    unsigned n_workers = std::max(2u, std::min(threads / 4, 6u));
+    if (const char* e = getenv("MPH_PARSE_THREADS")) n_workers = unsigned(std::max(1, atoi(e)));
     for (unsigned ti = 0; ti < n_workers; ++ti) pool.threads.emplace_back(worker);
     const bool trace = getenv("MPH_IO_TRACE") != nullptr;  // measurement hook: where the loader's wall time goes
-    double t_wait = 0, t_scan = 0;
+    double t_wait = 0, t_frame = 0, t_check = 0;
+    size_t n_fallback = 0, n_segs = 0;
     auto now = [] { return std::chrono::steady_clock::now(); };
     auto since = [](std::chrono::steady_clock::time_point a) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - a).count(); };
-    constexpr size_t SLICE = 8192;  // records per task
+    constexpr size_t SEG_BYTES = size_t(1) << 20;
+    std::mutex cig_mu;
+    // appends the records of a framed segment: the copy itself runs on the pool
+    std::deque<std::unique_ptr<Seg>> in_flight;  // segments whose copy may still be running
+    auto append = [&](std::unique_ptr<Seg> sgp) {
+      Seg& sg = *sgp;
+      if (sg.recs.empty()) return;
+      const size_t n = sg.recs.size();
+      if (recs_.size() + n > recs_.cap) {
+        wait_idle();  // the record array must not move while copies into it are running
+        in_flight.clear();
+        recs_.reserve(std::max(recs_.size() + n, recs_.cap + recs_.cap / 2 + 4096));
+      }
+      sg.rec0 = recs_.size();
+      recs_.grow_to(recs_.size() + n);
+      Seg* raw = sgp.get();
+      in_flight.push_back(std::move(sgp));
+      submit([this, raw, &cig_mu] {
+        memcpy(static_cast<void*>(recs_.data() + raw->rec0), raw->recs.data(), raw->recs.size() * sizeof(Rec));
+        std::vector<Rec>().swap(raw->recs);
+        std::lock_guard<std::mutex> lk(cig_mu);
+        cig_blocks_.push_back(std::move(raw->cig));
+      });
+    };
     try {
       std::vector<uint8_t> carry;  // the head of a record whose tail is in the next batch
-      bool more = true;
-      // hands a slice over; the record array must not move while tasks are writing into it
-      auto submit = [&](Slice&& sl) {
-        if (sl.off.empty()) return;
-        const size_t n = sl.off.size();
-        if (recs_.size() + n > recs_.cap) {
-          wait_idle();
-          recs_.reserve(std::max(recs_.size() + n, recs_.cap + recs_.cap / 2 + 4096));
+      // the batch whose segments are being framed on the pool while the calling thread waits for the next inflated batch
+      struct Pending {
+        std::vector<std::unique_ptr<Seg>> segs;
+        const uint8_t* base = nullptr;
+        size_t size = 0, o = 0;
+        std::atomic<size_t> left{0};
+        std::mutex mu;
+        std::condition_variable cv;
+        bool active = false;
+      } pend;
+      auto start_batch = [&](const uint8_t* base, size_t size, size_t o) {
+        pend.segs.clear();
+        pend.base = base; pend.size = size; pend.o = o;
+        for (size_t lo = o; lo < size;) {
+          const size_t hi = std::min(size, (lo / SEG_BYTES + 1) * SEG_BYTES);
+          std::unique_ptr<Seg> sg(new Seg);
+          sg->base = base; sg->size = size; sg->lo = lo; sg->hi = hi; sg->known = lo == o;
+          pend.segs.push_back(std::move(sg));
+          lo = hi;
         }
-        sl.rec0 = recs_.size();
-        recs_.grow_to(recs_.size() + n);
+        n_segs += pend.segs.size();
+        pend.left = pend.segs.size();
+        pend.active = true;
+        for (auto& sgp : pend.segs) {
+          Seg* sg = sgp.get();
+          Pending* pd = &pend;
+          submit([sg, pd, &plausible, &walk] {
+            struct Done {
+              Pending* pd;
+              ~Done() { std::lock_guard<std::mutex> lk(pd->mu); if (--pd->left == 0) pd->cv.notify_all(); }
+            } done{pd};
+            size_t start = sg->lo;
+            if (!sg->known) {
+              start = size_t(-1);
+              for (size_t p = sg->lo; p < sg->hi; ++p) {
+                if (!plausible(sg->base, sg->size, p)) continue;
+                size_t q = p;  // a few records further on must look like records as well
+                bool ok = true;
+                for (int k = 0; k < 4 && ok; ++k) {
+                  int32_t bs;
+                  memcpy(&bs, sg->base + q, 4);
+                  q += 4 + size_t(bs);
+                  if (q + 36 > sg->size) break;
+                  ok = plausible(sg->base, sg->size, q);
+                }
+                if (ok) { start = p; break; }
+              }
+            }
+            sg->guess = start;
+            if (start != size_t(-1)) walk(*sg, start);
+          });
+        }
+      };
+      // waits for the pending batch, checks the chain of boundaries in order, hands the records over, leaves the tail in `carry`
+      auto finish_batch = [&] {
+        if (!pend.active) return;
+        pend.active = false;
+        auto t0 = now();
+        {
+          std::unique_lock<std::mutex> lk(pend.mu);
+          pend.cv.wait(lk, [&] { return pend.left.load() == 0; });
+        }
         {
           std::lock_guard<std::mutex> lk(pool.mu);
-          pool.queue.push_back(std::move(sl));
+          if (pool.err) std::rethrow_exception(pool.err);
         }
-        pool.cv_work.notify_one();
+        t_frame += since(t0);
+        t0 = now();
+        size_t expect = pend.o;
+        bool final_incomplete = false;
+        for (auto& sgp : pend.segs) {
+          Seg& sg = *sgp;
+          if (final_incomplete || expect >= sg.hi) continue;  // the segment lies inside a record that started earlier
+          if (sg.guess != expect) {  // wrong or missing guess: frame it again from the right boundary
+            ++n_fallback;
+            walk(sg, expect);
+          }
+          expect = sg.end;
+          final_incomplete = sg.incomplete;
+          append(std::move(sgp));
+        }
+        if (expect < pend.size) carry.assign(pend.base + expect, pend.base + pend.size);
+        pend.segs.clear();
+        t_check += since(t0);
       };
+      bool more = true;
       while (more) {
         auto t0 = now();
         mphio::RawBytes chunk;
-        more = bam_.next_chunk(chunk);
+        more = bam_.next_chunk(chunk);  // (the previous batch is being framed on the pool meanwhile)
         t_wait += since(t0);
-        t0 = now();
+        finish_batch();
         if (!more) chunk.clear();
         if (chunk.size() > 0xFFFFFF00ull) throw mphio::IoError("inflated BGZF batch too large");
         size_t o = 0;
@@ -293,48 +435,30 @@ class ReadBuffer {
             if (carry.size() == need) {
               straddlers_.emplace_back(std::move(carry));
               carry.clear();
-              Slice sl;
-              sl.base = straddlers_.back().data();
-              sl.off.push_back(4);
-              submit(std::move(sl));
+              std::unique_ptr<Seg> sg(new Seg);
+              sg->base = straddlers_.back().data(); sg->size = straddlers_.back().size(); sg->lo = 0; sg->hi = sg->size;
+              walk(*sg, 0);
+              append(std::move(sg));
             }
           }
           if (!more && !carry.empty()) throw mphio::IoError("truncated BAM record");
         }
         const uint8_t* base = chunk.data();
         const size_t size = chunk.size();
-        Slice sl;
-        sl.base = base;
-        sl.off.reserve(SLICE);
-        while (o + 4 <= size) {
-          int32_t bs;
-          memcpy(&bs, base + o, 4);
-          if (bs < 32) throw mphio::IoError("corrupt BAM record");
-          if (o + 4 + size_t(bs) > size) break;
-          sl.off.push_back(uint32_t(o + 4));
-          o += 4 + size_t(bs);
-          if (sl.off.size() == SLICE) {
-            submit(std::move(sl));
-            sl = Slice();
-            sl.base = base;
-            sl.off.reserve(SLICE);
-          }
-        }
-        submit(std::move(sl));
-        if (o < size) carry.assign(base + o, base + size);
-        if (size) chunks_.push_back(std::move(chunk));  // the buffer itself does not move: the slices' pointers stay valid
-        t_scan += since(t0);
+        if (size) chunks_.push_back(std::move(chunk));  // the buffer itself does not move: pointers into it stay valid
+        if (o < size) start_batch(base, size, o);
       }
-      auto t0 = now();
+      finish_batch();
+      if (!carry.empty()) throw mphio::IoError("truncated BAM record");
       wait_idle();
-      const double t_tail = since(t0);
+      in_flight.clear();
       shutdown();
       if (pool.err) std::rethrow_exception(pool.err);
       if (trace)
-        fprintf(stderr, "[mph io] BAM load: waiting for inflated batches %.1f ms, record framing %.1f, waiting for the header parse after the last batch %.1f\n",
-                t_wait, t_scan, t_tail);
+        fprintf(stderr, "[mph io] BAM load: waiting for inflated batches %.1f ms, parallel framing + header parse %.1f, boundary check + hand-over %.1f (%zu segments, %zu framed again)\n",
+                t_wait, t_frame, t_check, n_segs, n_fallback);
     } catch (...) {
-      shutdown();
+      try { shutdown(); } catch (...) {}
       throw;
     }
     // records of contigs the header does not know are dropped (compaction in place keeps the file order)

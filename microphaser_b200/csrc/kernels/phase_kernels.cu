@@ -31,8 +31,9 @@ using namespace detail;
 namespace {
 
 // ------------------------------------------------------------------ K0: reads off the bus
-// A read crosses the bus as 2 B (distance to the previous start, reference span); one warp per run prefix-sums the
-// distances and writes the start / end arrays every later kernel uses. Exceptions (long spans, flags) are patched in after.
+// A read crosses the bus as 1 B (distance to the previous start; its reference span is the batch's span unless an exception
+// list names it) or 2 B (distance, span: batches of reads of all lengths); one warp per run prefix-sums the distances and
+// writes the start / end arrays every later kernel uses. Exceptions (other spans, flags) are patched in after.
 __global__ void __launch_bounds__(128) k_read_decode(const DeviceBatch d) {
   const uint32_t j = d.run0 + blockIdx.x * 4 + (threadIdx.x >> 5);
   const uint32_t lane = threadIdx.x & 31;
@@ -49,7 +50,7 @@ __global__ void __launch_bounds__(128) k_read_decode(const DeviceBatch d) {
     }
     if (r < hi) {
       d.read_start_w[r] = pos + x;
-      d.read_end_w[r] = pos + x + d.rd_span[r];
+      d.read_end_w[r] = pos + x + (d.rd_span ? (uint32_t)d.rd_span[r] : d.modal_span);
     }
     pos += __shfl_sync(FULL, x, 31);
   }

@@ -31,7 +31,8 @@ struct DeviceBatch {
   uint32_t* read_end_w = nullptr;
   uint8_t* read_flags_w = nullptr;
   const uint8_t* rd_delta = nullptr;     // per read: start - previous start (0 at the head of a run)
-  const uint8_t* rd_span = nullptr;      // per read: end - start, 255 = see rd_span_exc
+  const uint8_t* rd_span = nullptr;      // per read: end - start, 255 = see rd_span_exc; nullptr: every read spans modal_span unless rd_span_exc lists it
+  uint32_t modal_span = 0;
   const uint2* rd_runs = nullptr;        // (first read, its start), ascending; a run ends where the next begins
   const uint2* rd_span_exc = nullptr;    // (read, end)
   const uint2* rd_flag_exc = nullptr;    // (read, flags)

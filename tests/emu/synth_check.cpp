@@ -31,8 +31,11 @@ int main(int argc, char** argv) {
     {  // the 2-byte bus encoding of the reads must decode to the arrays the kernels use
       std::vector<uint32_t> ds, de;
       std::vector<uint8_t> df;
-      mph::decode_reads(b, ds, de, df);
-      if (ds != b.read_start || de != b.read_end || df != b.read_flags) { fprintf(stderr, "read encoding does not round-trip\n"); return 4; }
+      for (int form = 0; form <= (b.modal_set ? 1 : 0); ++form) {  // both bus forms of the spans: a byte per read / one span + exceptions
+        mph::decode_reads(b, ds, de, df, form);
+        if (ds != b.read_start || de != b.read_end || df != b.read_flags) { fprintf(stderr, "read encoding (span form %d) does not round-trip\n", form); return 4; }
+      }
+      fprintf(stderr, "bus form of the spans: %d (span %u, %zu of %zu reads listed)\n", mph::bus_span_mode(b), b.modal_span, b.rd_mspan_exc.size(), b.rd_span.size());
       std::vector<uint32_t> vr, vv, vso, vco;
       std::vector<uint16_t> vn;
       mph::decode_side_table(b, vr, vv, vso, vco, vn);

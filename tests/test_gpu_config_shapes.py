@@ -46,10 +46,25 @@ def test_config_shape_through_c_abi_matches_oracle(product, oracle_bin, shape, t
     out2.mkdir()
     res2.write(str(out2 / "out.fa"), str(out2 / "out.tsv"), str(out2 / "out.normal.fa"))
     res2.close()
+    # the file driver on the same files: several shards (MPH_PACK_THREADS) phased one after the other on this context, whose
+    # device buffers still hold the previous calls' windows (a stale flag of a replayed transcript's window was once read by
+    # the record kernels that run beside the replay)
+    out3 = tmp_path / "out3"
+    out3.mkdir()
+    os.environ["MPH_PACK_THREADS"] = "5"
+    try:
+        paths = [str(files / n) for n in ("reads.bam", "ref.fa", "variants.vcf", "annotation.gtf")]
+        if mode == 1 or mode == "normal":
+            ctx.run_normal(*paths, str(out3 / "out.fa"), str(out3 / "out.tsv"))
+        else:
+            ctx.run_somatic(*paths, str(out3 / "out.fa"), str(out3 / "out.tsv"), str(out3 / "out.normal.fa"))
+    finally:
+        del os.environ["MPH_PACK_THREADS"]
     ctx.close()
     want = read_outputs(str(ora), mode)
     assert read_outputs(str(out), mode) == want
     assert read_outputs(str(out2), mode) == want
+    assert read_outputs(str(out3), mode) == want
     assert n_records + 1 == want["out.tsv"].count(b"\n") and n_records > 1000
     st = json.load(open(tmp_path / "stats.json"))
     assert t["windows"] == st["windows"], "main-ORF window count differs from the oracle's print_haplotypes calls"

@@ -71,7 +71,8 @@ def test_pipelined_stages_match_single_stage(product, mode, monkeypatch):
     assert len(one) == len(many) > 1000
     assert records(one) == records(many)
     assert t_one["windows"] == t_many["windows"] and t_one["read_windows"] == t_many["read_windows"]
-    assert t_many["kernel_launches"] >= 7 * t_one["kernel_launches"]
+    # every stage runs the chain (the single-stage call may have run it twice: the first call on a context grows the arenas)
+    assert t_many["kernel_launches"] >= 3 * t_one["kernel_launches"]
     # pageable host buffers take the other copy schedule (stage s + 1 is queued after the kernels of stage s)
     pageable = m.Batch.synthetic(n_transcripts=600 if mode == "normal" else 2000, coverage=60.0, seed=0x4D500004, pin=False)
     again = ctx.phase_batch(pageable)
