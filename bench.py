@@ -298,6 +298,11 @@ def main():
 
     # ---- resident: kernels only, CUDA events on the library's stream
     ctx.upload(batch)
+    # one complete pass first: mph_phase_collect re-runs the kernels with larger arenas when the first attempt ran out of
+    # record / key space (a fresh context starts small), and mph_phase_resident alone never looks at the overflow flag - a
+    # timed loop on undersized arenas would skip part of the junction merges
+    ctx.phase_resident()
+    ctx.collect().close()
     flush = None
     if view.h2d_bytes < 3e8:  # the packed shard fits in the 126 MB L2: evict it between steps
         flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda:%d" % local_rank)

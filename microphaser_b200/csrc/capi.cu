@@ -566,6 +566,23 @@ void resize_pinned(mph_ctx* c, V& v, size_t n) {
   }
 }
 
+// an arena ran out during the last run_kernels (the counters say how much was asked for): grows it; true = run again
+bool grow_arenas(mph_ctx* c, const uint32_t* ctr) {
+  const uint32_t err = ctr[mphk::CTR_ERR];
+  if (!(err & (MPH_E_HIST_OVERFLOW | MPH_E_SEQ_OVERFLOW | MPH_E_VLIST_OVERFLOW | MPH_E_REC_OVERFLOW))) return false;
+  if (err & MPH_E_REC_OVERFLOW) {
+    c->recs.ensure(std::max<size_t>(size_t(ctr[mphk::CTR_NREC]) * 2 + 1024, c->recs.cap));
+    c->rec_seq.ensure(std::max<size_t>(size_t(ctr[mphk::CTR_RECSEQ]) * 2 + 4096, std::max(c->rec_seq.cap, c->recs.cap * 64)));
+    c->m_recs.ensure(std::max<size_t>(size_t(ctr[mphk::CTR_MERGE]) * 2 + 1024, c->m_recs.cap));
+    c->m_aux.ensure(c->m_recs.cap); c->m_seq.ensure(c->m_recs.cap * MPH_RC_SEQ_SLOT);
+  }
+  if (err & MPH_E_SEQ_OVERFLOW) c->seq_dev.ensure(size_t(ctr[mphk::CTR_SEQD]) * 2 + 4096);
+  if (err & MPH_E_VLIST_OVERFLOW) c->vlist.ensure(size_t(ctr[mphk::CTR_VLIST]) * 2 + 1024);
+  if (err & MPH_E_HIST_OVERFLOW) { c->hist.ensure((size_t(ctr[mphk::CTR_HIST]) + ctr[mphk::CTR_HISTD]) * 2 + 1024); c->hapx.ensure(c->hist.cap); }
+  if (err & MPH_E_SEQ_OVERFLOW) c->seq.ensure(size_t(ctr[mphk::CTR_SEQ]) * 2 + 4096);
+  return true;
+}
+
 // device -> host copy of what the kernels produced for the current slice; re-runs the kernels when an arena was too small
 void fetch_stage(mph_ctx* c, const Stage& s, PhaseRaw& raw, uint64_t* n_iw_total) {
   const Batch& b = c->cur->b;
@@ -573,18 +590,7 @@ void fetch_stage(mph_ctx* c, const Stage& s, PhaseRaw& raw, uint64_t* n_iw_total
   for (int attempt = 0;; ++attempt) {
     CU(cudaMemcpyAsync(ctr, c->counters.p, sizeof ctr, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    const uint32_t err = ctr[mphk::CTR_ERR];
-    if ((err & (MPH_E_HIST_OVERFLOW | MPH_E_SEQ_OVERFLOW | MPH_E_VLIST_OVERFLOW | MPH_E_REC_OVERFLOW)) && attempt < 6) {
-      if (err & MPH_E_REC_OVERFLOW) {
-        c->recs.ensure(std::max<size_t>(size_t(ctr[mphk::CTR_NREC]) * 2 + 1024, c->recs.cap));
-        c->rec_seq.ensure(std::max<size_t>(size_t(ctr[mphk::CTR_RECSEQ]) * 2 + 4096, std::max(c->rec_seq.cap, c->recs.cap * 64)));
-        c->m_recs.ensure(std::max<size_t>(size_t(ctr[mphk::CTR_MERGE]) * 2 + 1024, c->m_recs.cap));
-        c->m_aux.ensure(c->m_recs.cap); c->m_seq.ensure(c->m_recs.cap * MPH_RC_SEQ_SLOT);
-      }
-      if (err & MPH_E_SEQ_OVERFLOW) c->seq_dev.ensure(size_t(ctr[mphk::CTR_SEQD]) * 2 + 4096);
-      if (err & MPH_E_VLIST_OVERFLOW) c->vlist.ensure(size_t(ctr[mphk::CTR_VLIST]) * 2 + 1024);
-      if (err & MPH_E_HIST_OVERFLOW) { c->hist.ensure((size_t(ctr[mphk::CTR_HIST]) + ctr[mphk::CTR_HISTD]) * 2 + 1024); c->hapx.ensure(c->hist.cap); }
-      if (err & MPH_E_SEQ_OVERFLOW) c->seq.ensure(size_t(ctr[mphk::CTR_SEQ]) * 2 + 4096);
+    if (grow_arenas(c, ctr) && attempt < 6) {
       run_kernels(c);
       continue;
     }
@@ -1268,8 +1274,15 @@ int mph_phase_resident(mph_ctx* ctx) {
     ctx->stage_tx_lo = 0;
     ctx->stage_tx_hi = uint32_t(all[0].hi.txs);
     CU(cudaMemsetAsync(ctx->sums.p, 0, 3 * sizeof(unsigned long long), ctx->stream));
-    run_kernels(ctx);
-    CU(cudaStreamSynchronize(ctx->stream));
+    // (an arena that is too small makes the kernels skip work: look at the overflow flags like mph_phase_collect does, so
+    // that the step this entry point times is always the complete one)
+    for (int attempt = 0;; ++attempt) {
+      run_kernels(ctx);
+      uint32_t ctr[mphk::CTR_COUNT];
+      CU(cudaMemcpyAsync(ctr, ctx->counters.p, sizeof ctr, cudaMemcpyDeviceToHost, ctx->stream));
+      CU(cudaStreamSynchronize(ctx->stream));
+      if (!(grow_arenas(ctx, ctr) && attempt < 6)) break;
+    }
     ctx->timing.k1_ms = ctx->timing.k2_ms = ctx->timing.k3_ms = ctx->timing.k4_ms = ctx->timing.k5_ms = ctx->timing.replay_ms = ctx->timing.kernels_ms = 0;
     add_kernel_times(ctx);
     ctx->kernels_done = true;

@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(RC_THREADS) k_rc_stop(const DeviceBatch d) {
   if (q != NONE) atomicMin(&d.tx_stop[sg.tx], w);
 }
 
-__global__ void __launch_bounds__(RC_THREADS) k_rc_count(const DeviceBatch d) {
+__global__ void __launch_bounds__(RC_THREADS, 3) k_rc_count(const DeviceBatch d) {
   const uint32_t x = blockIdx.x * RC_THREADS + threadIdx.x;
   uint32_t n = 0;
   if (x < d.counters[CTR_NRW]) {
@@ -198,7 +198,7 @@ struct MphWarpOps {
 
 // junction merges (:1497-1908): one warp per junction; the records go to the merge arena, k_rc_emit places them
 constexpr int RM_WARPS = 4;
-__global__ void __launch_bounds__(RM_WARPS * 32) k_rc_merge(const DeviceBatch d) {
+__global__ void __launch_bounds__(RM_WARPS * 32, 8) k_rc_merge(const DeviceBatch d) {
   const int lane = threadIdx.x & 31;
   const uint32_t nj = d.counters[CTR_NJ];
   // the number of junctions lives on the device: the warps of a grid of a few CTAs per SM pull them from a queue (a merge
@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(128) k_rc_ids(const DeviceBatch d) {
   d.m_recs[x].id64 = r.id64;
 }
 
-__global__ void __launch_bounds__(RC_THREADS) k_rc_emit(const DeviceBatch d) {
+__global__ void __launch_bounds__(RC_THREADS, 3) k_rc_emit(const DeviceBatch d) {
   if (blockIdx.x * RC_THREADS >= d.counters[CTR_NRW]) return;  // the grid covers the host's upper bound
   const uint32_t x = blockIdx.x * RC_THREADS + threadIdx.x;
   const bool live = x < d.counters[CTR_NRW];
@@ -448,7 +448,7 @@ void launch_records(const DeviceBatch& d, cudaStream_t st) {
   MPH_LAUNCH(k_rc_stop, (nbl, RC_THREADS, 0, st), d);
   cudaMemsetAsync(d.rc_blocks, 0, (size_t)nbl * sizeof(uint32_t), st);
   MPH_LAUNCH(k_rc_count, (nbl, RC_THREADS, 0, st), d);
-  static const uint32_t merge_ctas = [] { const char* e = getenv("MPH_MERGE_CTAS"); return e ? (uint32_t)atoi(e) : 148u * 4u; }();  // 0: a warp per segment
+  static const uint32_t merge_ctas = [] { const char* e = getenv("MPH_MERGE_CTAS"); return e ? (uint32_t)atoi(e) : 148u * 8u; }();  // 0: a warp per segment
   if (d.s1 > d.s0) MPH_LAUNCH(k_rc_merge, (std::min<uint32_t>((d.s1 - d.s0 + RM_WARPS - 1) / RM_WARPS, merge_ctas ? merge_ctas : 0xFFFFFFFFu), RM_WARPS * 32, 0, st), d);  // at most one junction per segment
   MPH_LAUNCH(k_rc_ids, ((d.m_cap + 127) / 128, 128, 0, st), d);
   MPH_LAUNCH(k_rc_scan, (1, 1024, 0, st), d, nbl, CTR_NREC);
