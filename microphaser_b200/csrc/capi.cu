@@ -1277,7 +1277,9 @@ int mph_phase_resident(mph_ctx* ctx) {
     // (an arena that is too small makes the kernels skip work: look at the overflow flags like mph_phase_collect does, so
     // that the step this entry point times is always the complete one)
     for (int attempt = 0;; ++attempt) {
+      const uint64_t launches0 = mphk::kernel_launches_on_this_thread();
       run_kernels(ctx);
+      ctx->timing.kernel_launches = uint32_t(mphk::kernel_launches_on_this_thread() - launches0);  // of the complete pass
       uint32_t ctr[mphk::CTR_COUNT];
       CU(cudaMemcpyAsync(ctr, ctx->counters.p, sizeof ctr, cudaMemcpyDeviceToHost, ctx->stream));
       CU(cudaStreamSynchronize(ctx->stream));

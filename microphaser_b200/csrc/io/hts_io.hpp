@@ -19,6 +19,7 @@
 #include <thread>
 #include <exception>
 #include <algorithm>
+#include <functional>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -69,9 +70,27 @@ using RawBytes = std::vector<uint8_t, DefaultInitAllocator<uint8_t>>;
 // BGZF: a series of gzip members of <= 64 KiB each. With threads > 1 a producer thread reads batches of raw blocks
 // and inflates them with a small pool while the consumer parses the previous batch (rank 3 of SURVEY.md §8(f):
 // BGZF inflate is the first end-to-end bottleneck of the file drivers). threads == 1 is the plain sequential reader.
+// one raw block of a batch: compressed payload at cbuf + coff (clen bytes), inflated to out + ooff (isize bytes)
+struct BgzfRaw {
+  size_t coff, clen, ooff, isize;
+};
+// Optional replacement for the host inflate of a whole batch (the CUDA library installs the device-side inflate,
+// kernels/inflate_kernels.cu): fills out[0, obytes) from the n blocks or throws, in which case the batch - and every later
+// one - is inflated on the host. Only used for files of at least `min_bytes`, with batches of `batch_blocks` blocks.
+using BgzfBatchInflater = std::function<void(const uint8_t* cbuf, size_t cbytes, const BgzfRaw* raws, size_t n, uint8_t* out, size_t obytes)>;
+struct BgzfInflaterSpec {
+  BgzfBatchInflater fn;
+  size_t batch_blocks = 4096, min_bytes = size_t(8) << 20;
+};
+
 class BgzfReader {
  public:
-  explicit BgzfReader(const std::string& path, unsigned threads = 1) : path_(path), threads_(threads ? threads : 1) {
+  using Raw = BgzfRaw;
+  using BatchInflater = BgzfBatchInflater;
+  using InflaterSpec = BgzfInflaterSpec;
+
+  explicit BgzfReader(const std::string& path, unsigned threads = 1, InflaterSpec inflater = InflaterSpec())
+      : path_(path), threads_(threads ? threads : 1) {
     f_ = fopen(path.c_str(), "rb");
     if (!f_) throw IoError("cannot open " + path);
     if (fseek(f_, 0, SEEK_END) == 0) {
@@ -79,8 +98,13 @@ class BgzfReader {
       if (sz > 0) file_bytes_ = size_t(sz);
       fseek(f_, 0, SEEK_SET);
     }
+    if (inflater.fn && threads_ > 1 && file_bytes_ >= inflater.min_bytes) {
+      inflater_ = std::move(inflater.fn);
+      batch_blocks_ = std::max<size_t>(256, inflater.batch_blocks);
+    }
     if (threads_ > 1) producer_ = std::thread([this] { produce(); });
   }
+  bool device_inflate_used() const { return device_batches_.load() != 0; }
   ~BgzfReader() {
     if (producer_.joinable()) {
       {
@@ -132,9 +156,6 @@ class BgzfReader {
   }
 
  private:
-  struct Raw {
-    size_t coff, clen, ooff, isize;
-  };
   // reads one raw block (compressed payload appended to cbuf); false at end of file
   bool read_raw(std::vector<uint8_t>& cbuf, Raw& r) {
     uint8_t hdr[18];
@@ -210,7 +231,7 @@ class BgzfReader {
     rb.eof = false;
     rb.err = nullptr;
     try {
-      while (rb.raws.size() < 256) {
+      while (rb.raws.size() < batch_blocks_) {
         Raw r;
         if (!read_raw(rb.cbuf, r)) { rb.eof = true; break; }
         r.ooff = rb.total;
@@ -246,13 +267,31 @@ class BgzfReader {
             errs[ti] = std::current_exception();
           }
         };
-        std::vector<std::thread> pool;
-        for (unsigned ti = 1; ti < threads_; ++ti) pool.emplace_back(work, ti);
-        if (!cur.eof) { read_raw_batch(nxt); have_next = true; }  // overlaps the inflate of `cur`
-        work(0);
-        for (auto& t : pool) t.join();
-        for (auto& e : errs)
-          if (e) std::rethrow_exception(e);
+        bool on_device = false;
+        if (inflater_ && !cur.raws.empty()) {
+          // the installed batch inflater (device side) runs on a helper thread while this one reads the next raw batch
+          std::exception_ptr dev_err;
+          std::thread helper([&] {
+            try {
+              inflater_(cur.cbuf.data(), cur.cbuf.size(), cur.raws.data(), cur.raws.size(), b.data.data(), cur.total);
+            } catch (...) {
+              dev_err = std::current_exception();
+            }
+          });
+          if (!cur.eof) { read_raw_batch(nxt); have_next = true; }
+          helper.join();
+          if (dev_err) inflater_ = nullptr;  // not available / failed: this batch and the rest go through zlib
+          else { on_device = true; device_batches_ += 1; }
+        }
+        if (!on_device) {
+          std::vector<std::thread> pool;
+          for (unsigned ti = 1; ti < threads_; ++ti) pool.emplace_back(work, ti);
+          if (!cur.eof && !have_next) { read_raw_batch(nxt); have_next = true; }  // overlaps the inflate of `cur`
+          work(0);
+          for (auto& t : pool) t.join();
+          for (auto& e : errs)
+            if (e) std::rethrow_exception(e);
+        }
         if (cur.err) std::rethrow_exception(cur.err);  // what was read before the failure has been inflated; the failure ends the stream
       } catch (...) {
         b.err = std::current_exception();
@@ -303,6 +342,9 @@ class BgzfReader {
   std::condition_variable cv_;
   std::deque<Batch> ready_;
   bool stop_ = false, drained_ = false;
+  BatchInflater inflater_;
+  size_t batch_blocks_ = 256;
+  std::atomic<size_t> device_batches_{0};
 };
 
 // ---------------------------------------------------------------- BAM
@@ -403,7 +445,8 @@ struct BamFile {
   std::vector<int64_t> ref_lens;
   std::unordered_map<std::string, int> tid_of;
 
-  explicit BamFile(const std::string& path, unsigned inflate_threads = 1) : rd_(path, inflate_threads) {
+  explicit BamFile(const std::string& path, unsigned inflate_threads = 1, BgzfReader::InflaterSpec inflater = BgzfReader::InflaterSpec())
+      : rd_(path, inflate_threads, std::move(inflater)) {
     char magic[4];
     if (!rd_.read(magic, 4) || memcmp(magic, "BAM\1", 4) != 0) throw IoError("not a BAM file: " + path);
     auto must = [&](void* dst, size_t n) { if (!rd_.read(dst, n)) throw IoError("truncated BAM header: " + path); };
@@ -431,6 +474,7 @@ struct BamFile {
   }
 
   unsigned inflate_threads() const { return rd_.threads(); }
+  bool device_inflate_used() const { return rd_.device_inflate_used(); }
   size_t file_bytes() const { return rd_.file_bytes(); }
   // raw record stream after the header, in chunks (a record may straddle two chunks): for callers that frame and
   // parse the records themselves, in parallel

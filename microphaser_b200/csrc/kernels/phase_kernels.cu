@@ -785,7 +785,7 @@ void launch_window_hist(const DeviceBatch& d, cudaStream_t st) {
 }
 void launch_assemble(const DeviceBatch& d, cudaStream_t st, int part) {
   if (d.c1 > d.c0 && d.mode == 1) launch_assemble_normal(d, st);
-  else if (d.c1 > d.c0) MPH_LAUNCH(k_assemble, (part == ASM_HOST_CLASS ? 148 * 2 : 148 * 8, 128, 0, st), d, part);  // grid-stride over the key arena (its size lives on the device)
+  else if (d.c1 > d.c0) MPH_LAUNCH(k_assemble, (148 * 8, 128, 0, st), d, part);  // grid-stride over the key arena (its size lives on the device)
 }
 void launch_compact(const DeviceBatch& d, cudaStream_t st) {
   const uint32_t nb = (d.w1 - d.w0 + SCAN_THREADS - 1) / SCAN_THREADS;
