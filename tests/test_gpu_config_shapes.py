@@ -52,6 +52,7 @@ def test_config_shape_through_c_abi_matches_oracle(product, oracle_bin, shape, t
     out3 = tmp_path / "out3"
     out3.mkdir()
     os.environ["MPH_PACK_THREADS"] = "5"
+    os.environ["MPH_GPU_INFLATE"] = "1"  # and with the BGZF blocks inflated on the device (kernels/inflate_kernels.cu; off by default)
     try:
         paths = [str(files / n) for n in ("reads.bam", "ref.fa", "variants.vcf", "annotation.gtf")]
         if mode == 1 or mode == "normal":
@@ -60,6 +61,7 @@ def test_config_shape_through_c_abi_matches_oracle(product, oracle_bin, shape, t
             ctx.run_somatic(*paths, str(out3 / "out.fa"), str(out3 / "out.tsv"), str(out3 / "out.normal.fa"))
     finally:
         del os.environ["MPH_PACK_THREADS"]
+        del os.environ["MPH_GPU_INFLATE"]
     ctx.close()
     want = read_outputs(str(ora), mode)
     assert read_outputs(str(out), mode) == want

@@ -185,3 +185,16 @@ def test_threaded_bam_loader_matches_sequential_loader_on_a_multi_batch_file(tmp
     r = subprocess.run([exe, os.path.join(d, "reads.bam")], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert ", 0 differences" in r.stdout
+
+
+def test_device_deflate_decoder_matches_zlib(tmp_path):
+    """core/inflate_core.h is what one GPU thread runs per BGZF block (kernels/inflate_kernels.cu). Here it runs on the CPU
+    against zlib: every block of the fixture BAMs, zlib-written streams with stored / fixed / dynamic blocks at several levels
+    and strategies, and corrupted streams (an error code, never a write outside the output slice)."""
+    exe = str(tmp_path / "inflate_check")
+    subprocess.run(["g++", "-std=c++17", "-O2", "-Wall", "-o", exe, os.path.join(ROOT, "tests", "units", "inflate_check.cpp"), "-lz"], check=True)
+    bams = sorted(os.path.join(GOLDEN, d, "reads.bam") for d in os.listdir(GOLDEN) if os.path.exists(os.path.join(GOLDEN, d, "reads.bam")))
+    assert bams
+    r = subprocess.run([exe] + bams, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.startswith("inflate ok")
