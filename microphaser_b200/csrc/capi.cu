@@ -2,6 +2,7 @@
 // host residue, writers and the file-level `somatic` driver. No CPU fallback: every phase call runs
 // the CUDA kernels of kernels/phase_kernels.cu or fails.
 #include <cuda_runtime.h>
+#include <malloc.h>
 #include <cstring>
 #include <unistd.h>
 
@@ -1163,6 +1164,21 @@ int mph_ctx_create(int device, mph_ctx** out) {
     if (e != cudaSuccess || n == 0) throw CudaError(std::string("no CUDA device: ") + cudaGetErrorString(e));
     if (device < 0 || device >= n) throw CudaError("device index out of range");
     c->device = device;
+    // A result is a few hundred record blocks of ~100 KB that the host threads fill on every call and the caller frees
+    // afterwards. With glibc's default trim threshold (128 KB) the freed heap tops go back to the kernel each time and the
+    // next call pays a page fault per 4 KB again - most of the host threads' time once the records come from the device.
+    // Keep freed memory in the heaps (MPH_KEEP_HEAP=0 leaves the process's malloc settings alone).
+    {
+      static std::once_flag heap_once;
+      std::call_once(heap_once, [] {
+        const char* e = getenv("MPH_KEEP_HEAP");
+        if (e && *e == '0') return;
+#ifdef M_TRIM_THRESHOLD
+        mallopt(M_TRIM_THRESHOLD, 1 << 30);
+        mallopt(M_MMAP_THRESHOLD, 1 << 28);
+#endif
+      });
+    }
     CU(cudaSetDevice(device));
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));

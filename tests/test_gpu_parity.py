@@ -133,7 +133,8 @@ def test_multi_device_sharding_matches_oracle(product, oracle_bin, tmp_path):
     p.mkdir()
     ro = run_cli(oracle_bin, d, str(o))
     assert ro.returncode == 0, ro.stderr.decode()
-    devs = [0, 1, 0] if torch.cuda.device_count() >= 2 else [0, 0, 0]
+    n_dev = torch.cuda.device_count()
+    devs = (list(range(min(n_dev, 4))) + [0]) if n_dev >= 2 else [0, 0, 0]  # distinct devices when the box has them
     ctxs = [m.Context(x) for x in devs]
     try:
         m.run_somatic_multi(ctxs, os.path.join(d, "reads.bam"), os.path.join(d, "ref.fa"), os.path.join(d, "variants.vcf"),
@@ -147,6 +148,35 @@ def test_multi_device_sharding_matches_oracle(product, oracle_bin, tmp_path):
             c.close()
     assert read_outputs(str(o)) == read_outputs(str(p))
     assert len(read_outputs(str(o))["out.tsv"]) > 0
+
+
+def test_multi_device_normal_mode_matches_oracle(product, oracle_bin, tmp_path):
+    """mph_run_normal_multi: the `normal` sub-command sharded by gene range over several contexts (distinct devices when the
+    box has them); ordered concatenation must equal the oracle's single-process output."""
+    import torch
+    import microphaser_b200 as m
+    d = str(tmp_path / "in")
+    synth.generate(d, synth.Params(seed=4243, n_genes=9, coverage=20.0, indel_frac=0.1, multiallelic_frac=0.1))
+    o, p = tmp_path / "o", tmp_path / "p"
+    o.mkdir()
+    p.mkdir()
+    ro = run_cli(oracle_bin, d, str(o), subcommand="normal")
+    assert ro.returncode == 0, ro.stderr.decode()
+    n_dev = torch.cuda.device_count()
+    devs = (list(range(min(n_dev, 4))) + [0]) if n_dev >= 2 else [0, 0, 0]
+    ctxs = [m.Context(x) for x in devs]
+    try:
+        m.run_normal_multi(ctxs, os.path.join(d, "reads.bam"), os.path.join(d, "ref.fa"), os.path.join(d, "variants.vcf"),
+                           os.path.join(d, "annotation.gtf"), str(p / "out.fa"), str(p / "out.tsv"))
+    except m.MphError as e:
+        if e.code == m.MPH_ERR_UNSUPPORTED:
+            pytest.skip(str(e))
+        raise
+    finally:
+        for c in ctxs:
+            c.close()
+    assert read_outputs(str(o), "normal") == read_outputs(str(p), "normal")
+    assert len(read_outputs(str(o), "normal")["out.tsv"]) > 0
 
 
 # ---------------------------------------------------------------- `normal` mode (src/normal_microphasing.rs)
