@@ -217,7 +217,7 @@ struct mph_ctx {
   DevBuf<MphRec> recs, m_recs;
   DevBuf<MphRecSrc> m_aux;
   DevBuf<uint8_t> seq_dev, rec_seq, m_seq;
-  DevBuf<uint32_t> win_seg, tx_stop, rw, rw_stopq, rw_info, rw_mbase, rw_bytes, rw_junc, rc_blocks;
+  DevBuf<uint32_t> win_seg, tx_stop, rw, rw_stopq, rw_info, rw_mbase, rw_bytes, rw_junc, rc_blocks, rc_bblocks;
   DevBuf<int> win_diff;
   DevBuf<uint64_t> call_S, call_B;
   DevBuf<MphWinOut> win_out, iw_out;
@@ -368,6 +368,7 @@ void prepare(mph_ctx* c, const mph_batch* mb) {
     c->win_seg.ensure(nw + 1); c->tx_stop.ensure(b.txs.size() + 1);
     c->rw.ensure(nw + 1); c->rw_stopq.ensure(nw + 1); c->rw_info.ensure(nw + 1); c->rw_mbase.ensure(nw + 1); c->rw_bytes.ensure(nw + 1); c->rw_junc.ensure(b.segs.size() + 1);
     c->rc_blocks.ensure(nw / 256 + 4);  // (the record kernels use 512 windows per block)
+    c->rc_bblocks.ensure(nw / 256 + 4);
     // somatic: about one record per 30 windows; normal: every window writes at least one
     const size_t rec_want = b.mode == 1 ? nw + nw / 4 + (1 << 14) : std::max<size_t>(nw / 16, 1 << 14);
     if (c->recs.cap < rec_want) { c->recs.ensure(rec_want); c->rec_seq.ensure(std::max<size_t>(c->rec_seq.cap, b.mode == 1 ? rec_want * 8 : rec_want * 64)); }
@@ -401,7 +402,7 @@ void prepare(mph_ctx* c, const mph_batch* mb) {
   d.sum_depth = c->sums.p; d.live_depth = c->sums.p + 1; d.seg_live = c->seg_live.p;
   d.window_len = b.window_len;
   d.win_seg = c->win_seg.p; d.tx_stop = c->tx_stop.p; d.rw = c->rw.p; d.rw_stopq = c->rw_stopq.p; d.rw_info = c->rw_info.p; d.rw_mbase = c->rw_mbase.p;
-  d.rw_bytes = c->rw_bytes.p; d.rw_junc = c->rw_junc.p; d.rc_blocks = c->rc_blocks.p;
+  d.rw_bytes = c->rw_bytes.p; d.rw_junc = c->rw_junc.p; d.rc_blocks = c->rc_blocks.p; d.rc_bblocks = c->rc_bblocks.p;
   d.tx_id_bytes = c->tx_id_bytes.p; d.tx_id_off = c->tx_id_off.p;
   d.n_replay = uint32_t(b.replay.size());
   d.win_voff = nullptr; d.iw_voff = nullptr;
@@ -711,20 +712,34 @@ void take_device_records(const PhaseRaw& raw, uint32_t tx_lo, uint32_t tx_hi, Re
   const auto d1 = std::lower_bound(d0, raw.recs.end(), tx_hi, by_tx);
   if (d0 == d1) return;
   part.dev.assign(d0, d1);
-  size_t bytes = 0, n_aux = 0;
+  // the sequence bytes: the somatic record kernels lay them out in record order, so a block of transcripts owns one
+  // contiguous range (one memcpy; reading them record by record out of the freshly DMA-written download buffer was a cache
+  // miss each and most of the host threads' time); any other layout is copied record by record
+  size_t bytes = 0, n_aux = 0, lo = size_t(-1), hi = 0;
   for (const MphRec& r : part.dev) {
-    if (!(r.flags & MPH_RC_REFSEQ)) bytes += size_t(std::max(r.neo_len, r.mt_len)) + std::max(r.norm_len, r.wt_len);
+    if (!(r.flags & MPH_RC_REFSEQ)) {
+      const size_t n = size_t(std::max(r.neo_len, r.mt_len)) + std::max(r.norm_len, r.wt_len);
+      bytes += n;
+      lo = std::min<size_t>(lo, r.seq_off);
+      hi = std::max<size_t>(hi, size_t(r.seq_off) + n);
+    }
     n_aux += (r.flags & MPH_RC_MERGED) ? 1 : 0;
   }
   part.dev_seq.resize(bytes);
   part.dev_aux.reserve(n_aux);
+  const bool contiguous = bytes != 0 && hi - lo == bytes && hi <= raw.rec_seq.size();
+  if (contiguous) memcpy(part.dev_seq.data(), raw.rec_seq.data() + lo, bytes);
   size_t pos = 0;
   for (MphRec& r : part.dev) {
     if (!(r.flags & MPH_RC_REFSEQ)) {  // (a reference window's bytes stay in the batch's reference arena)
       const size_t n = size_t(std::max(r.neo_len, r.mt_len)) + std::max(r.norm_len, r.wt_len);
-      memcpy(part.dev_seq.data() + pos, raw.rec_seq.data() + r.seq_off, n);
-      r.seq_off = uint32_t(pos);
-      pos += n;
+      if (contiguous) {
+        r.seq_off = uint32_t(r.seq_off - lo);
+      } else {
+        memcpy(part.dev_seq.data() + pos, raw.rec_seq.data() + r.seq_off, n);
+        r.seq_off = uint32_t(pos);
+        pos += n;
+      }
     }
     if (r.flags & MPH_RC_MERGED) {
       part.dev_aux.push_back(raw.rec_aux[r.aux]);

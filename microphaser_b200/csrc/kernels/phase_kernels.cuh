@@ -129,6 +129,7 @@ struct DeviceBatch {
   uint32_t* rw_bytes = nullptr;     // per listed window: sequence bytes its records need
   uint32_t* rw_junc = nullptr;      // listed windows (indices into rw) whose junction merge is due (counters[CTR_NJ])
   uint32_t* rc_blocks = nullptr;    // block sums / offsets of the two compactions
+  uint32_t* rc_bblocks = nullptr;   // block sums / offsets of the records' sequence bytes (somatic mode: the bytes are laid out in record order)
   MphRec* recs = nullptr;           // ordered records (counters[CTR_NREC])
   uint32_t rec_cap = 0;
   uint8_t* rec_seq = nullptr;       // their sequence bytes (counters[CTR_RECSEQ])

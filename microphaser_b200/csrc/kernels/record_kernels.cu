@@ -63,8 +63,8 @@ __global__ void __launch_bounds__(RC_THREADS) k_rc_flag_count(const DeviceBatch 
   if (threadIdx.x == 0) d.rc_blocks[blockIdx.x] = (uint32_t)n;
 }
 
-// exclusive scan of rc_blocks[0 .. n_blocks) in place (one CTA); total -> counters[ctr]
-__global__ void __launch_bounds__(1024) k_rc_scan(const DeviceBatch d, uint32_t n_blocks, int ctr) {
+// exclusive scan of blocks[0 .. n_blocks) in place (one CTA); total -> counters[ctr]
+__global__ void __launch_bounds__(1024) k_rc_scan(const DeviceBatch d, uint32_t* blocks, uint32_t n_blocks, int ctr) {
   __shared__ uint32_t warp_sums[32];
   __shared__ uint32_t carry;
   if (threadIdx.x == 0) carry = 0;
@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(1024) k_rc_scan(const DeviceBatch d, uint32_t 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (uint32_t base = 0; base < n_blocks; base += 1024) {
     const uint32_t idx = base + threadIdx.x;
-    const uint32_t v = idx < n_blocks ? d.rc_blocks[idx] : 0;
+    const uint32_t v = idx < n_blocks ? blocks[idx] : 0;
     uint32_t x = v;
     for (int o = 1; o < 32; o <<= 1) {
       const uint32_t y = __shfl_up_sync(FULL, x, o);
@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(1024) k_rc_scan(const DeviceBatch d, uint32_t 
     }
     __syncthreads();
     const uint32_t before = carry + (warp ? warp_sums[warp - 1] : 0) + (x - v);
-    if (idx < n_blocks) d.rc_blocks[idx] = before;
+    if (idx < n_blocks) blocks[idx] = before;
     __syncthreads();
     if (threadIdx.x == 1023) carry = before + v;
     __syncthreads();
@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(RC_THREADS) k_rc_stop(const DeviceBatch d) {
 
 __global__ void __launch_bounds__(RC_THREADS, 3) k_rc_count(const DeviceBatch d) {
   const uint32_t x = blockIdx.x * RC_THREADS + threadIdx.x;
-  uint32_t n = 0;
+  uint32_t n = 0, nb = 0;
   if (x < d.counters[CTR_NRW]) {
     const uint32_t w = d.rw[x];
     const uint32_t si = d.win_seg[w];
@@ -140,10 +140,12 @@ __global__ void __launch_bounds__(RC_THREADS, 3) k_rc_count(const DeviceBatch d)
     d.rw_info[x] = n;
     d.rw_mbase[x] = 0;
     d.rw_bytes[x] = bytes;
+    nb = bytes;
   }
-  // block sum without a barrier (rc_blocks was zeroed by the host)
-  for (int o = 16; o; o >>= 1) n += __shfl_down_sync(FULL, n, o);
+  // block sums without a barrier (rc_blocks / rc_bblocks were zeroed by the host): records, and their sequence bytes
+  for (int o = 16; o; o >>= 1) { n += __shfl_down_sync(FULL, n, o); nb += __shfl_down_sync(FULL, nb, o); }
   if ((threadIdx.x & 31) == 0 && n) atomicAdd(&d.rc_blocks[blockIdx.x], n);
+  if ((threadIdx.x & 31) == 0 && nb) atomicAdd(&d.rc_bblocks[blockIdx.x], nb);
 }
 
 // lane-parallel byte steps of the merge: the 32 lanes of a warp run mph_rc_merge_t with identical arguments and identical
@@ -232,6 +234,7 @@ __global__ void __launch_bounds__(RM_WARPS * 32, 8) k_rc_merge(const DeviceBatch
     d.rw_mbase[x] = mbase;
     d.rw_bytes[x] += nm * 2u * d.window_len;
     if (nm) atomicAdd(&d.rc_blocks[x / RC_THREADS], nm);
+    if (nm) atomicAdd(&d.rc_bblocks[x / RC_THREADS], nm * 2u * d.window_len);
     raise(d, err);
   }
   __syncwarp();
@@ -258,11 +261,14 @@ __global__ void __launch_bounds__(RC_THREADS, 3) k_rc_emit(const DeviceBatch d) 
   const uint32_t n_own = info & 0xFFFu, nm = info >> 12;
   uint32_t total;
   const uint32_t before = block_exclusive(n_own + nm, &total);
+  // the sequence bytes are placed by a scan as well, so that they lie in record order: the host copies the bytes of a block
+  // of transcripts with one memcpy instead of one cache miss per record
+  const uint32_t bytes = live ? d.rw_bytes[x] : 0u;
+  const uint32_t before_bytes = block_exclusive(bytes, &total);
   if (!live || n_own + nm == 0) return;
   const uint32_t base = d.rc_blocks[blockIdx.x] + before;
   if (base + n_own + nm > d.rec_cap) { raise(d, MPH_E_REC_OVERFLOW); return; }
-  const uint32_t bytes = d.rw_bytes[x];
-  const uint32_t sbase = atomicAdd(&d.counters[CTR_RECSEQ], bytes);
+  const uint32_t sbase = d.rc_bblocks[blockIdx.x] + before_bytes;
   if (sbase + bytes > d.rec_seq_cap) { raise(d, MPH_E_REC_OVERFLOW); return; }
   const uint32_t w = d.rw[x];
   const MphSegment& sg = d.segs[d.win_seg[w]];
@@ -435,23 +441,25 @@ void launch_records(const DeviceBatch& d, cudaStream_t st) {
     MPH_LAUNCH(k_nrc_count, (nb, RC_THREADS, 0, st), d);
     if (d.s1 > d.s0) MPH_LAUNCH(k_nrc_merge, ((d.s1 - d.s0 + RM_WARPS - 1) / RM_WARPS, RM_WARPS * 32, 0, st), d);
     MPH_LAUNCH(k_rc_ids, ((d.m_cap + 127) / 128, 128, 0, st), d);
-    MPH_LAUNCH(k_rc_scan, (1, 1024, 0, st), d, nb, CTR_NREC);
+    MPH_LAUNCH(k_rc_scan, (1, 1024, 0, st), d, d.rc_blocks, nb, CTR_NREC);
     MPH_LAUNCH(k_nrc_emit, (nb, RC_THREADS, 0, st), d);
     return;
   }
   MPH_LAUNCH(k_rc_flag_count, (nb, RC_THREADS, 0, st), d);
-  MPH_LAUNCH(k_rc_scan, (1, 1024, 0, st), d, nb, CTR_NRW);
+  MPH_LAUNCH(k_rc_scan, (1, 1024, 0, st), d, d.rc_blocks, nb, CTR_NRW);
   MPH_LAUNCH(k_rc_scatter, (nb, RC_THREADS, 0, st), d);
   // the number of listed windows lives on the device: the grids cover the upper bound the host knows (interesting
   // windows of the slice cannot exceed its windows); threads beyond the count return at once
   const uint32_t nbl = nb;
   MPH_LAUNCH(k_rc_stop, (nbl, RC_THREADS, 0, st), d);
   cudaMemsetAsync(d.rc_blocks, 0, (size_t)nbl * sizeof(uint32_t), st);
+  cudaMemsetAsync(d.rc_bblocks, 0, (size_t)nbl * sizeof(uint32_t), st);
   MPH_LAUNCH(k_rc_count, (nbl, RC_THREADS, 0, st), d);
   static const uint32_t merge_ctas = [] { const char* e = getenv("MPH_MERGE_CTAS"); return e ? (uint32_t)atoi(e) : 148u * 8u; }();  // 0: a warp per segment
   if (d.s1 > d.s0) MPH_LAUNCH(k_rc_merge, (std::min<uint32_t>((d.s1 - d.s0 + RM_WARPS - 1) / RM_WARPS, merge_ctas ? merge_ctas : 0xFFFFFFFFu), RM_WARPS * 32, 0, st), d);  // at most one junction per segment
   MPH_LAUNCH(k_rc_ids, ((d.m_cap + 127) / 128, 128, 0, st), d);
-  MPH_LAUNCH(k_rc_scan, (1, 1024, 0, st), d, nbl, CTR_NREC);
+  MPH_LAUNCH(k_rc_scan, (1, 1024, 0, st), d, d.rc_blocks, nbl, CTR_NREC);
+  MPH_LAUNCH(k_rc_scan, (1, 1024, 0, st), d, d.rc_bblocks, nbl, CTR_RECSEQ);
   MPH_LAUNCH(k_rc_emit, (nbl, RC_THREADS, 0, st), d);
 }
 
