@@ -314,7 +314,7 @@ __global__ void __launch_bounds__(RC_THREADS) k_nrc_stop(const DeviceBatch d) {
 
 __global__ void __launch_bounds__(RC_THREADS) k_nrc_count(const DeviceBatch d) {
   const uint32_t x = blockIdx.x * RC_THREADS + threadIdx.x, w = d.w0 + x;
-  uint32_t cnt = 0;
+  uint32_t cnt = 0, nb = 0;
   if (w < d.w1) {
     uint32_t bytes = 0;
     const uint32_t si = d.win_seg[w];
@@ -336,9 +336,11 @@ __global__ void __launch_bounds__(RC_THREADS) k_nrc_count(const DeviceBatch d) {
     d.rw_info[x] = cnt;
     d.rw_mbase[x] = 0;
     d.rw_bytes[x] = bytes;
+    nb = bytes;
   }
-  for (int o = 16; o; o >>= 1) cnt += __shfl_down_sync(FULL, cnt, o);
+  for (int o = 16; o; o >>= 1) { cnt += __shfl_down_sync(FULL, cnt, o); nb += __shfl_down_sync(FULL, nb, o); }
   if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&d.rc_blocks[blockIdx.x], cnt);
+  if ((threadIdx.x & 31) == 0 && nb) atomicAdd(&d.rc_bblocks[blockIdx.x], nb);
 }
 
 __global__ void __launch_bounds__(RM_WARPS * 32) k_nrc_merge(const DeviceBatch d) {
@@ -369,6 +371,7 @@ __global__ void __launch_bounds__(RM_WARPS * 32) k_nrc_merge(const DeviceBatch d
     d.rw_mbase[x] = mbase;
     d.rw_bytes[x] += nm * d.window_len;
     if (nm) atomicAdd(&d.rc_blocks[x / RC_THREADS], nm);
+    if (nm) atomicAdd(&d.rc_bblocks[x / RC_THREADS], nm * d.window_len);
     raise(d, err);
   }
 }
@@ -380,15 +383,13 @@ __global__ void __launch_bounds__(RC_THREADS) k_nrc_emit(const DeviceBatch d) {
   const uint32_t n_own = info & 0xFFFu, nm = info >> 12;
   uint32_t total;
   const uint32_t before = block_exclusive(n_own + nm, &total);
+  const uint32_t bytes = live ? d.rw_bytes[x] : 0u;  // placed by a scan: record order (see k_rc_emit)
+  const uint32_t before_bytes = block_exclusive(bytes, &total);
   if (!live || n_own + nm == 0) return;
   const uint32_t base = d.rc_blocks[blockIdx.x] + before;
   if (base + n_own + nm > d.rec_cap) { raise(d, MPH_E_REC_OVERFLOW); return; }
-  const uint32_t bytes = d.rw_bytes[x];
-  uint32_t sbase = 0;
-  if (bytes) {
-    sbase = atomicAdd(&d.counters[CTR_RECSEQ], bytes);
-    if (sbase + bytes > d.rec_seq_cap) { raise(d, MPH_E_REC_OVERFLOW); return; }
-  }
+  const uint32_t sbase = d.rc_bblocks[blockIdx.x] + before_bytes;
+  if (bytes && sbase + bytes > d.rec_seq_cap) { raise(d, MPH_E_REC_OVERFLOW); return; }
   const MphSegment& sg = d.segs[d.win_seg[w]];
   MphNrmCtx n;
   const MphRecCtx c = rec_ctx_normal(d, &n);
@@ -438,10 +439,12 @@ void launch_records(const DeviceBatch& d, cudaStream_t st) {
   if (d.mode == 1) {
     MPH_LAUNCH(k_nrc_stop, (nb, RC_THREADS, 0, st), d);
     cudaMemsetAsync(d.rc_blocks, 0, (size_t)nb * sizeof(uint32_t), st);
+    cudaMemsetAsync(d.rc_bblocks, 0, (size_t)nb * sizeof(uint32_t), st);
     MPH_LAUNCH(k_nrc_count, (nb, RC_THREADS, 0, st), d);
     if (d.s1 > d.s0) MPH_LAUNCH(k_nrc_merge, ((d.s1 - d.s0 + RM_WARPS - 1) / RM_WARPS, RM_WARPS * 32, 0, st), d);
     MPH_LAUNCH(k_rc_ids, ((d.m_cap + 127) / 128, 128, 0, st), d);
     MPH_LAUNCH(k_rc_scan, (1, 1024, 0, st), d, d.rc_blocks, nb, CTR_NREC);
+    MPH_LAUNCH(k_rc_scan, (1, 1024, 0, st), d, d.rc_bblocks, nb, CTR_RECSEQ);
     MPH_LAUNCH(k_nrc_emit, (nb, RC_THREADS, 0, st), d);
     return;
   }
