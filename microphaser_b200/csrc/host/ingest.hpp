@@ -297,6 +297,7 @@ class ReadBuffer {
     auto now = [] { return std::chrono::steady_clock::now(); };
     auto since = [](std::chrono::steady_clock::time_point a) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - a).count(); };
     constexpr size_t SEG_BYTES = size_t(1) << 20;
+    const bool bad_guess_hook = getenv("MPH_IO_BAD_GUESS") != nullptr;  // test hook: every guessed boundary is discarded -> all segments go through the checker's re-framing
     std::mutex cig_mu;
     // appends the records of a framed segment: the copy itself runs on the pool
     std::deque<std::unique_ptr<Seg>> in_flight;  // segments whose copy may still be running
@@ -348,7 +349,7 @@ class ReadBuffer {
         for (auto& sgp : pend.segs) {
           Seg* sg = sgp.get();
           Pending* pd = &pend;
-          submit([sg, pd, &plausible, &walk] {
+          submit([sg, pd, &plausible, &walk, bad_guess_hook] {
             struct Done {
               Pending* pd;
               ~Done() { std::lock_guard<std::mutex> lk(pd->mu); if (--pd->left == 0) pd->cv.notify_all(); }
@@ -371,7 +372,17 @@ class ReadBuffer {
               }
             }
             sg->guess = start;
-            if (start != size_t(-1)) walk(*sg, start);
+            if (start == size_t(-1)) return;
+            if (sg->known) { walk(*sg, start); return; }
+            // a guessed boundary may be wrong: whatever the walk from it runs into is not an error of the file. The
+            // checker frames the segment again from the real boundary, and a corrupt record is reported from there.
+            try {
+              if (bad_guess_hook) throw mphio::IoError("test hook");
+              walk(*sg, start);
+            } catch (const mphio::IoError&) {
+              sg->guess = size_t(-1);
+              sg->recs.clear();
+            }
           });
         }
       };

@@ -185,6 +185,10 @@ def test_threaded_bam_loader_matches_sequential_loader_on_a_multi_batch_file(tmp
     r = subprocess.run([exe, os.path.join(d, "reads.bam")], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert ", 0 differences" in r.stdout
+    # every guessed segment boundary discarded: the checker frames all segments again from the real boundaries
+    r = subprocess.run([exe, os.path.join(d, "reads.bam")], capture_output=True, text=True, env=dict(os.environ, MPH_IO_BAD_GUESS="1", MPH_IO_TRACE="1"))
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert ", 0 differences" in r.stdout and "framed again" in r.stderr and ", 0 framed again" not in r.stderr
 
 
 def test_device_deflate_decoder_matches_zlib(tmp_path):
