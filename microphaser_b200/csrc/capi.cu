@@ -1500,6 +1500,11 @@ static void run_somatic_files(const std::vector<mph_ctx*>& ctxs, const char* bam
   // every core takes blocks
   unsigned io_threads = std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 32u);
   if (const char* e = getenv("MPH_IO_THREADS")) io_threads = unsigned(std::max(1, atoi(e)));
+  // host inflate: the reader's own decoder unless MPH_ZLIB_INFLATE=1
+  {
+    const char* z = getenv("MPH_ZLIB_INFLATE");
+    mphio::fast_inflate_enabled().store(!(z && *z == '1'));
+  }
   // MPH_GPU_INFLATE=1: the BGZF blocks of a large alignment file are inflated on the device (kernels/inflate_kernels.cu)
   // instead of by zlib on the host threads. Off by default: with one decoder thread per block every input byte and every
   // LZ77 copy is a dependent global-memory access, and the 7 436 blocks of the 183 MB sample take 287 ms (copies included)

@@ -10,6 +10,7 @@ int main(int argc, char** argv) {
   const unsigned thr = argc > 2 ? unsigned(atoi(argv[2])) : std::max(1u, std::thread::hardware_concurrency());
   auto now = [] { return std::chrono::steady_clock::now(); };
   auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+  mphio::fast_inflate_enabled().store(getenv("MPH_ZLIB_INFLATE") == nullptr);
   for (int rep = 0; rep < 3; ++rep) {
     const auto t0 = now();
     mphio::BamFile bam(d + "/reads.bam", thr);

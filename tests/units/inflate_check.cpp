@@ -1,4 +1,5 @@
-// TEST INFRASTRUCTURE ONLY — the DEFLATE decoder the GPU runs per BGZF block (core/inflate_core.h) against zlib:
+// TEST INFRASTRUCTURE ONLY — the DEFLATE decoder the GPU runs per BGZF block (core/inflate_core.h) and the host reader's
+// fast decoder (io/fast_inflate.hpp) against zlib:
 // every block of the BGZF files named on the command line, plus streams zlib writes with stored / fixed / dynamic blocks at
 // every level from inputs of several kinds, plus corrupted streams (must return an error, never crash or overrun).
 #include <zlib.h>
@@ -10,6 +11,7 @@
 #include <vector>
 
 #include "../../microphaser_b200/csrc/core/inflate_core.h"
+#include "../../microphaser_b200/csrc/io/fast_inflate.hpp"
 
 static int g_fail = 0;
 #define CHECK(c) do { if (!(c)) { fprintf(stderr, "FAIL %s:%d: %s\n", __FILE__, __LINE__, #c); ++g_fail; } } while (0)
@@ -29,6 +31,7 @@ static std::vector<uint8_t> deflate_raw(const std::vector<uint8_t>& in, int leve
 
 int main(int argc, char** argv) {
   MphInflateScratch sc;
+  static mphio::FastInflate fast;
   // 1. BGZF files, block by block
   size_t n_blocks = 0, n_bytes = 0;
   for (int a = 1; a < argc; ++a) {
@@ -59,6 +62,10 @@ int main(int argc, char** argv) {
       CHECK(st == MPH_INF_OK);
       CHECK(memcmp(got.data(), want.data(), isize) == 0);
       for (int t = 0; t < 16; ++t) CHECK(got[isize + t] == 0xAB);
+      got.assign(isize + 16, 0xAB);
+      CHECK(fast.run(cbuf.data(), clen, got.data(), isize));
+      CHECK(memcmp(got.data(), want.data(), isize) == 0);
+      for (int t = 0; t < 16; ++t) CHECK(got[isize + t] == 0xAB);
       ++n_blocks;
       n_bytes += isize;
     }
@@ -86,6 +93,18 @@ int main(int argc, char** argv) {
           CHECK(st == MPH_INF_OK);
           CHECK(n == 0 || memcmp(got.data(), in.data(), n) == 0);
           for (int t = 0; t < 8; ++t) CHECK(got[n + t] == 0xCD);
+          {
+            std::vector<uint8_t> g3(n + 8, 0xCD);
+            CHECK(fast.run(c.data(), c.size(), g3.data(), n));
+            CHECK(n == 0 || memcmp(g3.data(), in.data(), n) == 0);
+            for (int t = 0; t < 8; ++t) CHECK(g3[n + t] == 0xCD);
+            if (n) {
+              CHECK(!fast.run(c.data(), c.size(), g3.data(), n - 1));
+              CHECK(!fast.run(c.data(), c.size(), g3.data(), n + 1) || false);
+              g3[n] = 0xCD;
+              CHECK(!fast.run(c.data(), c.size() / 2, g3.data(), n) || c.size() < 2);
+            }
+          }
           ++n_streams;
           // wrong output size, truncated input, flipped bits: an error or (for a flip that keeps the stream valid) any
           // result, but never a write outside [0, n)
@@ -99,6 +118,8 @@ int main(int argc, char** argv) {
               bad[rnd() % bad.size()] ^= uint8_t(1u << (rnd() & 7));
               std::vector<uint8_t> g2(n + 8, 0xEF);
               mph_inflate_raw(bad.data(), uint32_t(bad.size()), g2.data(), uint32_t(n), &sc);
+              for (int u = 0; u < 8; ++u) CHECK(g2[n + u] == 0xEF);
+              fast.run(bad.data(), bad.size(), g2.data(), n);
               for (int u = 0; u < 8; ++u) CHECK(g2[n + u] == 0xEF);
             }
           }

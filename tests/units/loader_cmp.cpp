@@ -3,8 +3,12 @@
 #include <cstdio>
 #include "../../microphaser_b200/csrc/host/ingest.hpp"
 int main(int argc, char** argv) {
-  mphio::BamFile b1(argv[1], 1), b8(argv[1], 8);
-  mph::ReadBuffer r1(b1), r8(b8);
+  // sequential loader with zlib, threaded loader with the reader's own DEFLATE decoder (io/fast_inflate.hpp)
+  mphio::BamFile b1(argv[1], 1);
+  mph::ReadBuffer r1(b1);
+  mphio::fast_inflate_enabled().store(true);
+  mphio::BamFile b8(argv[1], 8);
+  mph::ReadBuffer r8(b8);
   printf("records %zu %zu\n", r1.n_records(), r8.n_records());
   size_t bad = 0, n = 0;
   for (auto& name : b1.ref_names) {
